@@ -1,0 +1,457 @@
+"""Host-side mirror of GiNGR's registration API over libgingr_cuda.so.
+
+Names and argument meaning follow the reference (paths relative to
+/root/reference/src/main/scala/gingr/):
+  CpdConfiguration / IcpConfiguration      registration/config/CPD.scala:105-115, ICP.scala:54-66
+  GeneralRegistrationState, ModelFittingParameters   api/GeneralRegistrationState.scala:28-41,
+                                                     api/ModelFittingParameters.scala:31-74
+  CpdRegistration / IcpRegistration (GingrAlgorithm) registration/config/CPD.scala:117-160,
+                                                     ICP.scala:84-110, api/GingrAlgorithm.scala:65-303
+Everything numeric happens in the CUDA library; this module only marshals arrays.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+from dataclasses import dataclass, field
+from typing import Callable, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+from ._native import (ALGO_CPD, ALGO_ICP, NO_TRANSFORMS, POINTCLOUD_CLOSEST_POINT, RIGID_TRANSFORMS,
+                      SIMILARITY_TRANSFORMS, STATUS_CONVERGED, STATUS_MAX_ITERATION,
+                      STATUS_MODEL_FLEXIBILITY_ERROR, STATUS_NONE, TRIANGULAR_CLOSEST_POINT,
+                      ALONG_NORMAL_CLOSEST_POINT, GingrConfig, GingrError, GingrState)
+
+
+class Context:
+    """One CUDA device + stream (gingr_ctx).  Single-threaded, like a GingrAlgorithm instance."""
+
+    def __init__(self, device: int = 0):
+        self._lib = nat.load()
+        h = ctypes.c_void_p()
+        nat.check(self._lib.gingr_ctx_create(int(device), ctypes.byref(h)))
+        self.handle = h
+        self.device = device
+        self.nranks, self.rank = 1, 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.gingr_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, code):
+        return nat.check(code, self.handle)
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.gingr_ctx_stream(self.handle) or 0)
+
+    def synchronize(self):
+        self.check(self._lib.gingr_ctx_synchronize(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.gingr_ctx_launch_count(self.handle))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (ctypes.c_char * 128)()
+        nat.check(nat.load().gingr_comm_unique_id(ctypes.byref(buf)))
+        return bytes(buf.raw)
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        buf = (ctypes.c_char * 128).from_buffer_copy(uid)
+        self.check(self._lib.gingr_comm_init(self.handle, int(nranks), int(rank), ctypes.byref(buf)))
+        self.nranks, self.rank = nranks, rank
+
+
+class Target:
+    """Target TriangleMesh (or point set) resident on the device (gingr_target)."""
+
+    def __init__(self, ctx: Context, points, triangles=None):
+        self.ctx = ctx
+        pts = nat.f64(points).reshape(-1, 3)
+        tri = None if triangles is None else nat.i32(triangles).reshape(-1, 3)
+        self.N = pts.shape[0]
+        self.T = 0 if tri is None else tri.shape[0]
+        h = ctypes.c_void_p()
+        ctx.check(ctx._lib.gingr_target_upload(ctx.handle, self.N, nat.as_dp(pts), nat.as_ip(tri), self.T,
+                                               ctypes.byref(h)))
+        self.handle = h
+        self.points = pts
+        self.triangles = tri
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx._lib.gingr_target_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Model:
+    """scalismo PointDistributionModel on the device (gingr_model): reference points, meanVector,
+    basisMatrix [3M, r] (row 3*pid+d), variance [r], optional reference triangles."""
+
+    def __init__(self, ctx: Context, ref_points, mean, basis, variance, triangles=None):
+        self.ctx = ctx
+        ref = nat.f64(ref_points).reshape(-1, 3)
+        self.M = ref.shape[0]
+        mean = nat.f64(mean).reshape(-1)
+        var = nat.f64(variance).reshape(-1)
+        self.rank = var.shape[0]
+        basis = np.asarray(basis, dtype=np.float64)
+        assert basis.shape == (3 * self.M, self.rank), basis.shape
+        basis_f = np.asfortranarray(basis)   # Breeze column-major layout; ld = 3M
+        tri = None if triangles is None else nat.i32(triangles).reshape(-1, 3)
+        self.T = 0 if tri is None else tri.shape[0]
+        h = ctypes.c_void_p()
+        ctx.check(ctx._lib.gingr_model_upload(ctx.handle, self.M, self.rank, nat.as_dp(ref), nat.as_dp(mean),
+                                              basis_f.ctypes.data_as(nat.dp), 3 * self.M, nat.as_dp(var),
+                                              nat.as_ip(tri), self.T, ctypes.byref(h)))
+        self.handle = h
+        self.triangles = tri
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx._lib.gingr_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel-level operators
+# ---------------------------------------------------------------------------------------------
+def cpd_estep(ctx: Context, target: Target, fit, sigma2: float, w: float):
+    """P1[M], Pt1[N_local], PX[M,3] of CpdRegistrationState.P (CPD.scala:54-75) without forming P."""
+    fit = nat.f64(fit).reshape(-1, 3)
+    M = fit.shape[0]
+    n_local = _local_count(target.N, ctx)
+    P1, Pt1, PX = np.empty(M), np.empty(n_local), np.empty((M, 3))
+    ctx.check(ctx._lib.gingr_cpd_estep(ctx.handle, target.handle, M, nat.as_dp(fit), float(sigma2), float(w),
+                                       nat.as_dp(P1), nat.as_dp(Pt1), nat.as_dp(PX)))
+    return P1, Pt1, PX
+
+
+def bcpd_estep(ctx: Context, target: Target, y, sigma_mm, alpha, sigma2: float, s: float, w: float):
+    """nu, nu', Nhat, xhat of BCPD.computeP + reductions (BCPD.scala:167-184, :200-209)."""
+    y = nat.f64(y).reshape(-1, 3)
+    M = y.shape[0]
+    sm, al = nat.f64(sigma_mm), nat.f64(alpha)
+    n_local = _local_count(target.N, ctx)
+    nu, nup, xhat = np.empty(M), np.empty(n_local), np.empty((M, 3))
+    nhat = ctypes.c_double()
+    ctx.check(ctx._lib.gingr_bcpd_estep(ctx.handle, target.handle, M, nat.as_dp(y), nat.as_dp(sm), nat.as_dp(al),
+                                        float(sigma2), float(s), float(w), nat.as_dp(nu), nat.as_dp(nup),
+                                        ctypes.byref(nhat), nat.as_dp(xhat)))
+    return nu, nup, float(nhat.value), xhat
+
+
+def cpd_initial_sigma2(ctx: Context, target: Target, points) -> float:
+    """computeInitialSigma2 (CPD.scala:81-90)."""
+    pts = nat.f64(points).reshape(-1, 3)
+    out = ctypes.c_double()
+    ctx.check(ctx._lib.gingr_cpd_initial_sigma2(ctx.handle, target.handle, pts.shape[0], nat.as_dp(pts),
+                                                ctypes.byref(out)))
+    return float(out.value)
+
+
+def icp_closest(ctx: Context, target: Target, template_points, template_triangles, method: int):
+    """closestPointCorrespondence (ClosestPointRegistrator.scala:74-96, :133-160):
+    returns idx[M] (nearest target vertex), cp[M,3], w[M] in {0,1}, mean distance."""
+    tpl = nat.f64(template_points).reshape(-1, 3)
+    M = tpl.shape[0]
+    tri = None if template_triangles is None else nat.i32(template_triangles).reshape(-1, 3)
+    T = 0 if tri is None else tri.shape[0]
+    idx = np.empty(M, dtype=np.int32)
+    cp = np.empty((M, 3))
+    w = np.empty(M, dtype=np.uint8)
+    md = ctypes.c_double()
+    ctx.check(ctx._lib.gingr_icp_closest(ctx.handle, target.handle, M, nat.as_dp(tpl), nat.as_ip(tri), T, int(method),
+                                         nat.as_ip(idx), nat.as_dp(cp), nat.as_bp(w), ctypes.byref(md)))
+    return idx, cp, w, float(md.value)
+
+
+def posterior_mean(ctx: Context, model: Model, R, t, pids, points, noise):
+    """model.transform(R, t).posterior(obs).mean -> (coefficients[r], mean mesh points[M,3]).
+    noise: [n] isotropic variances or [n,3,3] covariances.  (GingrAlgorithm.scala:297-301)"""
+    R = nat.f64(R).reshape(3, 3)
+    t = nat.f64(t).reshape(3)
+    pids = nat.i32(pids)
+    pts = nat.f64(points).reshape(-1, 3)
+    noise = nat.f64(noise)
+    kind = 0 if noise.ndim == 1 else 1
+    c = np.empty(model.rank)
+    mesh = np.empty((model.M, 3))
+    code = ctx.check(ctx._lib.gingr_posterior_mean(ctx.handle, model.handle, nat.as_dp(R), nat.as_dp(t),
+                                                   pids.shape[0], nat.as_ip(pids), nat.as_dp(pts), kind,
+                                                   nat.as_dp(noise), nat.as_dp(c), nat.as_dp(mesh)))
+    if code == nat.GINGR_MODEL_FLEXIBILITY:
+        raise FloatingPointError("posterior failed (ModelFlexibilityError)")
+    return c, mesh
+
+
+def coefficients(ctx: Context, model: Model, R, t, mesh_points):
+    """model.transform(R, t).coefficients(mesh) (GingrAlgorithm.scala:215, :236)."""
+    R = nat.f64(R).reshape(3, 3)
+    t = nat.f64(t).reshape(3)
+    mesh = nat.f64(mesh_points).reshape(-1, 3)
+    c = np.empty(model.rank)
+    code = ctx.check(ctx._lib.gingr_coefficients(ctx.handle, model.handle, nat.as_dp(R), nat.as_dp(t),
+                                                 nat.as_dp(mesh), nat.as_dp(c)))
+    if code == nat.GINGR_MODEL_FLEXIBILITY:
+        raise FloatingPointError("coefficients failed (ModelFlexibilityError)")
+    return c
+
+
+def _local_count(n: int, ctx: Context) -> int:
+    base, rem = divmod(n, ctx.nranks)
+    return base + (1 if ctx.rank < rem else 0)
+
+
+def shard_range(n: int, nranks: int, rank: int) -> Tuple[int, int]:
+    """[begin, begin+count) of n items owned by `rank` -- the partition libgingr_cuda uses for target
+    points (E-step) and GPMM points (Gram / fit evaluation)."""
+    base, rem = divmod(n, nranks)
+    begin = rank * base + min(rank, rem)
+    return begin, base + (1 if rank < rem else 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# state / configuration records
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class ModelFittingParameters:
+    """api/ModelFittingParameters.scala:57-74: scale, pose (translation, Euler rotation), shape."""
+    scale: float
+    translation: np.ndarray
+    euler: Tuple[float, float, float]
+    shape: np.ndarray
+    center: np.ndarray = field(default_factory=lambda: np.zeros(3))
+
+
+@dataclass
+class GeneralRegistrationState:
+    """Numeric part of api/GeneralRegistrationState.scala:28-41 (model/target live in device handles)."""
+    modelParameters: ModelFittingParameters
+    fit: np.ndarray
+    sigma2: float = 1.0
+    globalTransformation: int = RIGID_TRANSFORMS
+    stepLength: float = 1.0
+    generatedBy: str = ""
+    iteration: int = 0
+    status: int = STATUS_NONE
+
+    def to_pod(self) -> Tuple[GingrState, np.ndarray]:
+        p = self.modelParameters
+        st = GingrState()
+        st.scale = float(p.scale)
+        st.translation[:] = [float(v) for v in p.translation]
+        st.euler[:] = [float(v) for v in p.euler]
+        st.center[:] = [float(v) for v in p.center]
+        st.sigma2 = float(self.sigma2)
+        st.step_length = float(self.stepLength)
+        st.global_transformation = int(self.globalTransformation)
+        st.iteration = int(self.iteration)
+        st.status = int(self.status)
+        alpha = nat.f64(p.shape).copy()
+        st.rank = alpha.shape[0]
+        return st, alpha
+
+    @staticmethod
+    def from_pod(st: GingrState, alpha: np.ndarray, fit: np.ndarray, generatedBy: str = "") -> "GeneralRegistrationState":
+        p = ModelFittingParameters(st.scale, np.array(list(st.translation)), tuple(st.euler), alpha.copy(),
+                                   np.array(list(st.center)))
+        return GeneralRegistrationState(p, fit, st.sigma2, st.global_transformation, st.step_length, generatedBy,
+                                        st.iteration, st.status)
+
+
+@dataclass
+class CpdConfiguration:
+    """registration/config/CPD.scala:105-115"""
+    maxIterations: int = 100
+    threshold: float = 1e-10
+    converged: Callable = lambda last, cur, thr: abs(last.sigma2 - cur.sigma2) < thr
+    useLandmarkCorrespondence: bool = True
+    initialSigma: Optional[float] = None
+    w: float = 0.0
+    lambda_: float = 1.0
+
+    def to_pod(self) -> GingrConfig:
+        c = GingrConfig()
+        c.algorithm = ALGO_CPD
+        c.max_iterations = self.maxIterations
+        c.threshold = self.threshold
+        c.use_landmark_correspondence = int(self.useLandmarkCorrespondence)
+        c.has_initial_sigma = int(self.initialSigma is not None)
+        c.initial_sigma = float(self.initialSigma or 0.0)
+        c.w = self.w
+        c.lambda_ = self.lambda_
+        return c
+
+
+@dataclass
+class IcpConfiguration:
+    """registration/config/ICP.scala:54-66"""
+    maxIterations: int = 100
+    threshold: float = 1e-10
+    converged: Callable = lambda last, cur, thr: False
+    useLandmarkCorrespondence: bool = True
+    initialSigma: float = 100.0
+    endSigma: float = 1.0
+    reverseCorrespondenceDirection: bool = False
+    correspondenceMethod: int = TRIANGULAR_CLOSEST_POINT
+
+    @property
+    def sigmaStep(self) -> float:
+        return (self.initialSigma - self.endSigma) / float(self.maxIterations)
+
+    def to_pod(self) -> GingrConfig:
+        c = GingrConfig()
+        c.algorithm = ALGO_ICP
+        c.max_iterations = self.maxIterations
+        c.threshold = self.threshold
+        c.use_landmark_correspondence = int(self.useLandmarkCorrespondence)
+        c.has_initial_sigma = 1
+        c.initial_sigma = float(self.initialSigma)
+        c.end_sigma = float(self.endSigma)
+        c.reverse_correspondence_direction = int(self.reverseCorrespondenceDirection)
+        c.correspondence_method = int(self.correspondenceMethod)
+        return c
+
+
+class GingrAlgorithm:
+    """api/GingrAlgorithm.scala:65-303 with `update` (:192-254) executed on the device."""
+    name = "Gingr"
+
+    def __init__(self, ctx: Context, model: Model, target: Target, config):
+        self.ctx, self.model, self.target, self.config = ctx, model, target, config
+        pod = config.to_pod()
+        h = ctypes.c_void_p()
+        ctx.check(ctx._lib.gingr_registration_create(ctx.handle, model.handle, target.handle, ctypes.byref(pod),
+                                                     ctypes.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx._lib.gingr_registration_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setLandmarks(self, pids, points, cov=None):
+        """GeneralRegistrationState.landmarkCorrespondences (GeneralRegistrationState.scala:43-62),
+        resolved by the caller: reference vertex ids, target landmark points, 3x3 covariances (I3 default)."""
+        pids = nat.i32(pids)
+        pts = nat.f64(points).reshape(-1, 3)
+        L = pids.shape[0]
+        cov = np.tile(np.eye(3), (L, 1, 1)) if cov is None else nat.f64(cov).reshape(L, 3, 3)
+        cov = nat.f64(cov)
+        self.ctx.check(self.ctx._lib.gingr_registration_set_landmarks(self.handle, L, nat.as_ip(pids), nat.as_dp(pts),
+                                                                      nat.as_dp(cov)))
+
+    def initializeState(self, globalTransformation: int = RIGID_TRANSFORMS, rotation=None, translation=None,
+                        general: Optional[GeneralRegistrationState] = None) -> GeneralRegistrationState:
+        """GeneralRegistrationState.apply (:136-178) + initializeState (CPD.scala:92-103 / ICP.scala:74-86)."""
+        if general is None:
+            from .rotation import matrix_to_euler
+            euler = (0.0, 0.0, 0.0) if rotation is None else matrix_to_euler(np.asarray(rotation, dtype=float))
+            t = np.zeros(3) if translation is None else np.asarray(translation, dtype=float)
+            pars = ModelFittingParameters(1.0, t, euler, np.zeros(self.model.rank))
+            general = GeneralRegistrationState(pars, np.zeros((self.model.M, 3)),
+                                               globalTransformation=globalTransformation)
+        st, alpha = general.to_pod()
+        fit = np.empty((self.model.M, 3))
+        self.ctx.check(self.ctx._lib.gingr_initialize_state(self.handle, ctypes.byref(st), nat.as_dp(alpha),
+                                                            nat.as_dp(fit)))
+        return GeneralRegistrationState.from_pod(st, alpha, fit, general.generatedBy)
+
+    def update(self, current: GeneralRegistrationState, probabilistic: bool = False, seed: int = 0,
+               with_fit: bool = True) -> GeneralRegistrationState:
+        """GingrAlgorithm.update (:192-254).  The returned state's `fit` is already the refreshed fit of
+        GingrGeneratorWrapper.propose (the reference leaves the old fit in place until `propose`)."""
+        st, alpha = current.to_pod()
+        out = GingrState()
+        alpha_out = np.empty_like(alpha)
+        fit = np.empty((self.model.M, 3)) if with_fit else None
+        self.ctx.check(self.ctx._lib.gingr_update(self.handle, ctypes.byref(st), nat.as_dp(alpha), int(probabilistic),
+                                                  int(seed), ctypes.byref(out), nat.as_dp(alpha_out), nat.as_dp(fit)))
+        return GeneralRegistrationState.from_pod(out, alpha_out, fit if with_fit else current.fit, current.generatedBy)
+
+    def propose(self, current: GeneralRegistrationState) -> GeneralRegistrationState:
+        """GingrGeneratorWrapper.propose (GingrGeneratorWrapper.scala:28-39) around the deterministic
+        wrapper (GeneratorWrapperDeterministic.scala:28-34): update, refresh fit, iteration += 1."""
+        ns = self.update(current, False)
+        return dataclasses.replace(ns, generatedBy="Deterministic", iteration=ns.iteration + 1)
+
+    def run(self, initialState: GeneralRegistrationState, callBackLogger=None) -> GeneralRegistrationState:
+        """Deterministic GingrAlgorithm.run (:115-175): the chain yields the initial state first, so
+        maxIterations - 1 proposals are made; stops on converged(last, cur) or ModelFlexibilityError."""
+        st = initialState
+        last = None
+        final = STATUS_MAX_ITERATION
+        for k in range(self.config.maxIterations):
+            if k > 0:
+                st = self.propose(st)
+            if callBackLogger is not None:
+                callBackLogger(st)
+            converged = last is not None and self.config.converged(last, st, self.config.threshold)
+            error = st.status == STATUS_MODEL_FLEXIBILITY_ERROR
+            last = st
+            if converged:
+                final = STATUS_CONVERGED
+                break
+            if error:
+                break
+        if st.status == STATUS_NONE:
+            st = dataclasses.replace(st, status=final)
+        return st
+
+    # device-resident chaining (throughput runs)
+    def updateChain(self, iters: int):
+        self.ctx.check(self.ctx._lib.gingr_update_chain(self.handle, int(iters)))
+
+    def downloadState(self) -> GeneralRegistrationState:
+        st = GingrState()
+        alpha = np.empty(self.model.rank)
+        fit = np.empty((self.model.M, 3))
+        self.ctx.check(self.ctx._lib.gingr_state_download(self.handle, ctypes.byref(st), nat.as_dp(alpha),
+                                                          nat.as_dp(fit)))
+        return GeneralRegistrationState.from_pod(st, alpha, fit)
+
+
+class CpdRegistration(GingrAlgorithm):
+    """registration/config/CPD.scala:117-160"""
+    name = "CPD"
+
+    def __init__(self, ctx, model, target, config: Optional[CpdConfiguration] = None):
+        super().__init__(ctx, model, target, config or CpdConfiguration())
+
+
+class IcpRegistration(GingrAlgorithm):
+    """registration/config/ICP.scala:84-110"""
+    name = "ICP"
+
+    def __init__(self, ctx, model, target, config: Optional[IcpConfiguration] = None):
+        super().__init__(ctx, model, target, config or IcpConfiguration())

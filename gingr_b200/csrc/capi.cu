@@ -1,0 +1,321 @@
+// capi.cu -- extern "C" boundary of libgingr_cuda.so: context, uploads and the kernel-level entry
+// points (K1 E-step, K2 closest point, K3 posterior).  The full iteration lives in update.cu.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "closest.cuh"
+#include "common.cuh"
+#include "estep.cuh"
+#include "nccl_dl.cuh"
+#include "posterior.cuh"
+
+static std::mutex g_err_mutex;
+static std::string g_last_error;
+
+void gingr_set_error(gingr_ctx* ctx, const char* msg) {
+  if (ctx) ctx->last_error = msg;
+  std::lock_guard<std::mutex> lock(g_err_mutex);
+  g_last_error = msg;
+}
+
+int32_t gingr_fail(gingr_ctx* ctx, int32_t code, const char* msg) {
+  gingr_set_error(ctx, msg);
+  return code;
+}
+
+// per-ctx scratch for the kernel-level calls (the registration handle owns its own)
+struct CtxScratch {
+  gingr::EstepWorkspace estep;
+  DevBuf<double> a, b, c, d;
+  DevBuf<int32_t> ia;
+  DevBuf<uint8_t> ua;
+};
+
+static CtxScratch* scratch_of(gingr_ctx* ctx);
+
+struct gingr_ctx_full : gingr_ctx {
+  CtxScratch scratch;
+};
+
+static CtxScratch* scratch_of(gingr_ctx* ctx) { return &static_cast<gingr_ctx_full*>(ctx)->scratch; }
+
+extern "C" {
+
+int32_t gingr_version(void) { return 100; }
+
+int32_t gingr_ctx_create(int32_t device, gingr_ctx** out) {
+  if (!out) return gingr_fail(nullptr, GINGR_ERR_ARG, "gingr_ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    return gingr_fail(nullptr, GINGR_ERR_CUDA,
+                      "gingr_ctx_create: no CUDA device (libgingr_cuda has no CPU fallback)");
+  }
+  if (device < 0 || device >= count) return gingr_fail(nullptr, GINGR_ERR_ARG, "gingr_ctx_create: bad device index");
+  gingr_ctx_full* ctx = new gingr_ctx_full();
+  ctx->device = device;
+  GINGR_CUDA_TRY(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GINGR_CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    delete ctx;
+    return gingr_fail(nullptr, GINGR_ERR_CUDA, "gingr_ctx_create: device is not sm_100 (Blackwell) -- unsupported");
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  GINGR_CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  GINGR_CUDA_TRY(nullptr, cudaMallocHost((void**)&ctx->h_pinned, ctx->h_pinned_count * sizeof(double)));
+  *out = ctx;
+  return GINGR_OK;
+}
+
+int32_t gingr_ctx_destroy(gingr_ctx* ctx) {
+  if (!ctx) return GINGR_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  CtxScratch* s = scratch_of(ctx);
+  s->estep.release();
+  s->a.release();
+  s->b.release();
+  s->c.release();
+  s->d.release();
+  s->ia.release();
+  s->ua.release();
+  gingr::comm_destroy(ctx);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  cudaStreamDestroy(ctx->stream);
+  delete static_cast<gingr_ctx_full*>(ctx);
+  return GINGR_OK;
+}
+
+const char* gingr_last_error(const gingr_ctx* ctx) {
+  if (ctx) return ctx->last_error.c_str();
+  std::lock_guard<std::mutex> lock(g_err_mutex);
+  return g_last_error.c_str();
+}
+
+void* gingr_ctx_stream(gingr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int32_t gingr_ctx_synchronize(gingr_ctx* ctx) {
+  if (!ctx) return GINGR_ERR_ARG;
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return GINGR_OK;
+}
+
+int64_t gingr_ctx_launch_count(const gingr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// uploads
+// ---------------------------------------------------------------------------------------------
+int32_t gingr_target_upload(gingr_ctx* ctx, int32_t N, const double* pts, const int32_t* tri, int32_t T,
+                            gingr_target** out) {
+  if (!ctx || !out || !pts || N <= 0 || T < 0 || (T > 0 && !tri))
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_target_upload: bad argument");
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  gingr_target* t = new gingr_target();
+  t->ctx = ctx;
+  t->N_total = N;
+  shard_range(N, ctx->nranks, ctx->rank, &t->n0, &t->N);
+  // full vertex set (SoA) -- the ICP search and the single-GPU E-step use it; the E-step shard is a view
+  // into a separately packed SoA when sharded.
+  CtxScratch* s = scratch_of(ctx);
+  GINGR_CUDA_TRY(ctx, s->a.alloc((size_t)3 * N));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(s->a.p, pts, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  GINGR_CUDA_TRY(ctx, t->verts.alloc((size_t)3 * N));
+  GINGR_TRY(gingr::aos_to_soa_enqueue(ctx, N, s->a.p, t->verts.p));
+  if (t->N > 0) {
+    GINGR_CUDA_TRY(ctx, t->soa.alloc((size_t)3 * t->N));
+    GINGR_TRY(gingr::aos_to_soa_enqueue(ctx, t->N, s->a.p + (size_t)3 * t->n0, t->soa.p));
+  }
+  t->T = T;
+  if (T > 0) {
+    GINGR_CUDA_TRY(ctx, t->tri.alloc((size_t)3 * T));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(t->tri.p, tri, sizeof(int32_t) * 3 * (size_t)T, cudaMemcpyHostToDevice, ctx->stream));
+    for (int k = 0; k < 3 * T; ++k)
+      if (tri[k] < 0 || tri[k] >= N) {
+        delete t;
+        return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_target_upload: triangle index out of range");
+      }
+    GINGR_TRY(gingr::mesh_static_upload(ctx, N, pts, T, tri, &t->normals, &t->boundary));
+  }
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = t;
+  return GINGR_OK;
+}
+
+int32_t gingr_target_destroy(gingr_target* t) {
+  if (!t) return GINGR_OK;
+  cudaSetDevice(t->ctx->device);
+  t->soa.release();
+  t->verts.release();
+  t->tri.release();
+  t->normals.release();
+  t->boundary.release();
+  delete t;
+  return GINGR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 entry points
+// ---------------------------------------------------------------------------------------------
+static int32_t estep_common(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* fit,
+                            gingr::EstepWorkspace** ws_out) {
+  CtxScratch* s = scratch_of(ctx);
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  GINGR_TRY(s->estep.ensure(ctx, M, target->N));
+  GINGR_CUDA_TRY(ctx, s->a.alloc((size_t)3 * std::max(M, 1)));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(s->a.p, fit, sizeof(double) * 3 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+  GINGR_TRY(gingr::aos_to_soa_enqueue(ctx, M, s->a.p, s->estep.fit_soa.p));
+  *ws_out = &s->estep;
+  return GINGR_OK;
+}
+
+// rows [4][M] -> host P1[M], PX[M][3]; combines shards when nranks > 1
+static int32_t estep_download(gingr_ctx* ctx, gingr::EstepWorkspace* ws, int M, int N, double* P1, double* Pt1,
+                              double* PX, std::vector<double>* rows_host) {
+  if (ctx->nranks > 1) GINGR_TRY(gingr::comm_allreduce_sum(ctx, ws->rows.p, (size_t)4 * M));
+  rows_host->resize((size_t)4 * M);
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(rows_host->data(), ws->rows.p, sizeof(double) * 4 * (size_t)M,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+  if (Pt1)
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(Pt1, ws->pt1.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const double* r = rows_host->data();
+  if (P1) memcpy(P1, r, sizeof(double) * (size_t)M);
+  if (PX)
+    for (int i = 0; i < M; ++i) {
+      PX[3 * i] = r[(size_t)M + i];
+      PX[3 * i + 1] = r[(size_t)2 * M + i];
+      PX[3 * i + 2] = r[(size_t)3 * M + i];
+    }
+  return GINGR_OK;
+}
+
+int32_t gingr_cpd_estep(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* fit, double sigma2,
+                        double w, double* P1, double* Pt1, double* PX) {
+  if (!ctx || !target || !fit || M <= 0) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_cpd_estep: bad argument");
+  gingr::EstepWorkspace* ws = nullptr;
+  GINGR_TRY(estep_common(ctx, target, M, fit, &ws));
+  double* h = ctx->h_pinned;
+  memset(h, 0, sizeof(double) * 16);
+  h[0] = sigma2;
+  h[3] = w;
+  h[4] = (double)M / (double)target->N_total;
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(ws->scal.p, h, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+  GINGR_TRY(gingr::estep_cpd_scalars_enqueue(ctx, ws->scal.p));
+  if (target->N > 0) GINGR_TRY(gingr::estep_enqueue(ctx, *ws, M, target->N, target->soa.p, false));
+  std::vector<double> rows;
+  return estep_download(ctx, ws, M, target->N, P1, Pt1, PX, &rows);
+}
+
+int32_t gingr_bcpd_estep(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* y,
+                         const double* sigma_mm, const double* alpha, double sigma2, double s, double w, double* nu,
+                         double* nu_prime, double* n_hat, double* x_hat) {
+  if (!ctx || !target || !y || !sigma_mm || !alpha || M <= 0)
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_bcpd_estep: bad argument");
+  gingr::EstepWorkspace* ws = nullptr;
+  GINGR_TRY(estep_common(ctx, target, M, y, &ws));
+  CtxScratch* sc = scratch_of(ctx);
+  GINGR_CUDA_TRY(ctx, sc->b.alloc((size_t)2 * M));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(sc->b.p, sigma_mm, sizeof(double) * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(sc->b.p + M, alpha, sizeof(double) * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+  double* h = ctx->h_pinned;
+  memset(h, 0, sizeof(double) * 16);
+  h[0] = sigma2;
+  h[3] = w;
+  h[5] = s;
+  h[6] = 1.0 / (double)target->N_total;
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(ws->scal.p, h, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+  GINGR_TRY(gingr::estep_bcpd_rowf_enqueue(ctx, M, sc->b.p, sc->b.p + M, ws->scal.p, ws->rowf.p));
+  if (target->N > 0) GINGR_TRY(gingr::estep_enqueue(ctx, *ws, M, target->N, target->soa.p, true));
+  std::vector<double> rows;
+  std::vector<double> nup((size_t)target->N);
+  std::vector<double> nuv((size_t)M), px((size_t)3 * M);
+  GINGR_TRY(estep_download(ctx, ws, M, target->N, nuv.data(), nup.data(), px.data(), &rows));
+  if (nu) memcpy(nu, nuv.data(), sizeof(double) * (size_t)M);
+  if (nu_prime) memcpy(nu_prime, nup.data(), sizeof(double) * (size_t)target->N);
+  if (n_hat) {
+    // Nhat = sum(nu')  BCPD.scala:204 ; across ranks the caller sums the shard values
+    double sum = 0.0;
+    for (int j = 0; j < target->N; ++j) sum += nup[j];
+    *n_hat = sum;
+  }
+  if (x_hat)  // xhat = pinv(diag(nu (x) 1_3)) (P (x) I_3) X  BCPD.scala:209 : rows with nu == 0 map to 0
+    for (int i = 0; i < M; ++i) {
+      const double inv = nuv[i] != 0.0 ? 1.0 / nuv[i] : 0.0;
+      for (int d = 0; d < 3; ++d) x_hat[3 * i + d] = px[3 * i + d] * inv;
+    }
+  return GINGR_OK;
+}
+
+int32_t gingr_cpd_initial_sigma2(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* pts,
+                                 double* sigma2_out) {
+  if (!ctx || !target || !pts || !sigma2_out || M <= 0)
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_cpd_initial_sigma2: bad argument");
+  CtxScratch* s = scratch_of(ctx);
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  GINGR_CUDA_TRY(ctx, s->a.alloc((size_t)3 * M));
+  GINGR_CUDA_TRY(ctx, s->b.alloc(16));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(s->a.p, pts, sizeof(double) * 3 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+  GINGR_TRY(gingr::initial_sigma2_enqueue(ctx, M, s->a.p, target->N_total, target->verts.p, s->b.p));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(sigma2_out, s->b.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return GINGR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 entry point
+// ---------------------------------------------------------------------------------------------
+int32_t gingr_icp_closest(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* tpl,
+                          const int32_t* tpl_tri, int32_t T, int32_t method, int32_t* idx, double* cp, uint8_t* w,
+                          double* mean_distance) {
+  if (!ctx || !target || !tpl || M <= 0 || T < 0 || (T > 0 && !tpl_tri))
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_icp_closest: bad argument");
+  CtxScratch* s = scratch_of(ctx);
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  gingr::ClosestWorkspace ws;
+  int32_t rc = ws.ensure(ctx, M, target->N_total, target->T, T);
+  DevBuf<int32_t> d_tri, d_off, d_adj;
+  auto cleanup = [&]() {
+    ws.release();
+    d_tri.release();
+    d_off.release();
+    d_adj.release();
+  };
+  if (rc < 0) { cleanup(); return rc; }
+  GINGR_CUDA_TRY(ctx, s->a.alloc((size_t)3 * M));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(s->a.p, tpl, sizeof(double) * 3 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+  if (T > 0) {
+    for (int k = 0; k < 3 * T; ++k)
+      if (tpl_tri[k] < 0 || tpl_tri[k] >= M) {
+        cleanup();
+        return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_icp_closest: template triangle index out of range");
+      }
+    std::vector<int32_t> off, adj;
+    gingr::build_vertex_adjacency(M, T, tpl_tri, &off, &adj);
+    GINGR_CUDA_TRY(ctx, d_tri.alloc((size_t)3 * T));
+    GINGR_CUDA_TRY(ctx, d_off.alloc(off.size()));
+    GINGR_CUDA_TRY(ctx, d_adj.alloc(adj.size()));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_tri.p, tpl_tri, sizeof(int32_t) * 3 * (size_t)T, cudaMemcpyHostToDevice, ctx->stream));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_adj.p, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // off/adj are stack vectors
+  }
+  rc = gingr::icp_closest_enqueue(ctx, ws, target, M, s->a.p, T, d_tri.p, d_off.p, d_adj.p, method);
+  if (rc < 0) { cudaStreamSynchronize(ctx->stream); cleanup(); return rc; }
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = cudaSuccess;
+  if (idx && e == cudaSuccess) e = cudaMemcpyAsync(idx, ws.idx.p, sizeof(int32_t) * (size_t)M, cudaMemcpyDeviceToHost, st);
+  if (cp && e == cudaSuccess) e = cudaMemcpyAsync(cp, ws.cp.p, sizeof(double) * 3 * (size_t)M, cudaMemcpyDeviceToHost, st);
+  if (w && e == cudaSuccess) e = cudaMemcpyAsync(w, ws.w.p, (size_t)M, cudaMemcpyDeviceToHost, st);
+  if (mean_distance && e == cudaSuccess) e = cudaMemcpyAsync(mean_distance, ws.mean_dist.p, sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  GINGR_CUDA_TRY(ctx, e);
+  return GINGR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,489 @@
+// closest.cu -- K2: ICP closest-point correspondence for sm_100a.   COMPILED WITH -fmad=false.
+//
+// Replaces registration/utils/ClosestPointRegistrator.scala:
+//   ClosestPointUnstructuredPointsDomain3D (:133-148)  nearest target vertex        -> nn_vertex_kernel
+//   ClosestPointTriangleMesh3D (:74-96)                closest point on a triangle   -> surface_kernel
+//     + findClosestPoint of that point (:83), isPointOnBoundary (:53-55), isNormalDirectionOpposite
+//       (:57-60), isClosestPointIntersecting (:62-72)                                -> line_mesh_kernel,
+//                                                                                       icp_weights_kernel
+// Exactness: every distance is evaluated in FP64 with individually rounded operations in the order the
+// JVM evaluates scalismo's `norm2` (x*x + y*y + z*z, no FMA contraction -- hence -fmad=false), the scan
+// is in ascending index order with a strict `<`, and partial results of index ranges are merged lowest
+// range first, so the argmin is exact with ties broken by the lowest index.
+// The searches are tiled brute force (queries in registers, candidates staged through shared memory),
+// FP64-pipe bound at 8 M N flop for the vertex search.
+#include <algorithm>
+#include <vector>
+
+#include "closest.cuh"
+#include "common.cuh"
+
+namespace gingr {
+
+constexpr int QT = 128;    // queries (threads) per CTA
+constexpr int PT = 256;    // candidate points per shared-memory tile
+constexpr int TT = 64;     // candidate triangles per shared-memory tile
+
+// ---------------------------------------------------------------------------------------------
+// nearest vertex
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(QT) nn_vertex_kernel(int M, const double* __restrict__ q /*AoS [M][3]*/, int N,
+                                                       const double* __restrict__ pts /*SoA [3][N]*/,
+                                                       double* __restrict__ part_d2, int32_t* __restrict__ part_idx) {
+  __shared__ double sx[PT], sy[PT], sz[PT];
+  const int i = blockIdx.x * QT + threadIdx.x;
+  const int per = (N + gridDim.y - 1) / gridDim.y;
+  const int j_begin = blockIdx.y * per, j_end = min(N, j_begin + per);
+  const int ii = min(i, M - 1);
+  const double qx = q[3 * ii], qy = q[3 * ii + 1], qz = q[3 * ii + 2];
+  double best = INFINITY;
+  int32_t bi = -1;
+  for (int j0 = j_begin; j0 < j_end; j0 += PT) {
+    const int cnt = min(PT, j_end - j0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt; t += QT) {
+      sx[t] = pts[j0 + t];
+      sy[t] = pts[N + j0 + t];
+      sz[t] = pts[2 * N + j0 + t];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int t = 0; t < cnt; ++t) {
+      const double dx = qx - sx[t], dy = qy - sy[t], dz = qz - sz[t];
+      const double d = dx * dx + dy * dy + dz * dz;
+      if (d < best) {
+        best = d;
+        bi = j0 + t;
+      }
+    }
+  }
+  if (i < M) {
+    part_d2[(size_t)blockIdx.y * M + i] = best;
+    part_idx[(size_t)blockIdx.y * M + i] = bi;
+  }
+}
+
+__global__ void nn_reduce_kernel(int M, int splits, const double* __restrict__ part_d2,
+                                 const int32_t* __restrict__ part_idx, double* __restrict__ d2,
+                                 int32_t* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  double best = INFINITY;
+  int32_t bi = -1;
+  for (int k = 0; k < splits; ++k) {
+    const double d = part_d2[(size_t)k * M + i];
+    if (d < best) {
+      best = d;
+      bi = part_idx[(size_t)k * M + i];
+    }
+  }
+  d2[i] = best;
+  idx[i] = bi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// closest point on a triangle (Ericson 5.1.5).  Same operation order as the oracle.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void closest_on_triangle(double px, double py, double pz, const double* a, const double* b,
+                                                    const double* c, double& ox, double& oy, double& oz) {
+  const double abx = b[0] - a[0], aby = b[1] - a[1], abz = b[2] - a[2];
+  const double acx = c[0] - a[0], acy = c[1] - a[1], acz = c[2] - a[2];
+  const double apx = px - a[0], apy = py - a[1], apz = pz - a[2];
+  const double d1 = abx * apx + aby * apy + abz * apz;
+  const double d2 = acx * apx + acy * apy + acz * apz;
+  if (d1 <= 0.0 && d2 <= 0.0) { ox = a[0]; oy = a[1]; oz = a[2]; return; }
+  const double bpx = px - b[0], bpy = py - b[1], bpz = pz - b[2];
+  const double d3 = abx * bpx + aby * bpy + abz * bpz;
+  const double d4 = acx * bpx + acy * bpy + acz * bpz;
+  if (d3 >= 0.0 && d4 <= d3) { ox = b[0]; oy = b[1]; oz = b[2]; return; }
+  const double vc = d1 * d4 - d3 * d2;
+  if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {
+    const double v = d1 / (d1 - d3);
+    ox = a[0] + v * abx; oy = a[1] + v * aby; oz = a[2] + v * abz; return;
+  }
+  const double cpx = px - c[0], cpy = py - c[1], cpz = pz - c[2];
+  const double d5 = abx * cpx + aby * cpy + abz * cpz;
+  const double d6 = acx * cpx + acy * cpy + acz * cpz;
+  if (d6 >= 0.0 && d5 <= d6) { ox = c[0]; oy = c[1]; oz = c[2]; return; }
+  const double vb = d5 * d2 - d1 * d6;
+  if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
+    const double w = d2 / (d2 - d6);
+    ox = a[0] + w * acx; oy = a[1] + w * acy; oz = a[2] + w * acz; return;
+  }
+  const double va = d3 * d6 - d5 * d4;
+  if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) {
+    const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+    ox = b[0] + w * (c[0] - b[0]); oy = b[1] + w * (c[1] - b[1]); oz = b[2] + w * (c[2] - b[2]); return;
+  }
+  const double denom = 1.0 / (va + vb + vc);
+  const double v = vb * denom, w = vc * denom;
+  ox = a[0] + abx * v + acx * w;
+  oy = a[1] + aby * v + acy * w;
+  oz = a[2] + abz * v + acz * w;
+}
+
+// part: [splits][M] d2, tri ; [splits][M][3] cp
+__global__ void __launch_bounds__(QT) surface_kernel(int M, const double* __restrict__ q, int N,
+                                                     const double* __restrict__ verts /*SoA [3][N]*/, int T,
+                                                     const int32_t* __restrict__ tri, double* __restrict__ part_d2,
+                                                     int32_t* __restrict__ part_tri, double* __restrict__ part_cp) {
+  __shared__ double st[TT][9];
+  const int i = blockIdx.x * QT + threadIdx.x;
+  const int per = (T + gridDim.y - 1) / gridDim.y;
+  const int t_begin = blockIdx.y * per, t_end = min(T, t_begin + per);
+  const int ii = min(i, M - 1);
+  const double qx = q[3 * ii], qy = q[3 * ii + 1], qz = q[3 * ii + 2];
+  double best = INFINITY, bx = 0, by = 0, bz = 0;
+  int32_t bt = -1;
+  for (int t0 = t_begin; t0 < t_end; t0 += TT) {
+    const int cnt = min(TT, t_end - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * 9; e += QT) {
+      const int t = e / 9, k = e % 9;
+      const int v = tri[3 * (t0 + t) + k / 3];
+      st[t][k] = verts[(size_t)(k % 3) * N + v];
+    }
+    __syncthreads();
+    for (int t = 0; t < cnt; ++t) {
+      double cx, cy, cz;
+      closest_on_triangle(qx, qy, qz, &st[t][0], &st[t][3], &st[t][6], cx, cy, cz);
+      const double dx = qx - cx, dy = qy - cy, dz = qz - cz;
+      const double d = dx * dx + dy * dy + dz * dz;
+      if (d < best) { best = d; bt = t0 + t; bx = cx; by = cy; bz = cz; }
+    }
+  }
+  if (i < M) {
+    const size_t o = (size_t)blockIdx.y * M + i;
+    part_d2[o] = best;
+    part_tri[o] = bt;
+    part_cp[3 * o] = bx;
+    part_cp[3 * o + 1] = by;
+    part_cp[3 * o + 2] = bz;
+  }
+}
+
+__global__ void surface_reduce_kernel(int M, int splits, const double* __restrict__ part_d2,
+                                      const int32_t* __restrict__ part_tri, const double* __restrict__ part_cp,
+                                      double* __restrict__ d2, int32_t* __restrict__ tri_out,
+                                      double* __restrict__ cp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  double best = INFINITY;
+  int bk = 0;
+  for (int k = 0; k < splits; ++k) {
+    const double d = part_d2[(size_t)k * M + i];
+    if (d < best) { best = d; bk = k; }
+  }
+  const size_t o = (size_t)bk * M + i;
+  d2[i] = best;
+  if (tri_out) tri_out[i] = part_tri[o];
+  cp[3 * i] = part_cp[3 * o];
+  cp[3 * i + 1] = part_cp[3 * o + 1];
+  cp[3 * i + 2] = part_cp[3 * o + 2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// isClosestPointIntersecting (:62-72): for query vertex i of the template with direction v = p - cp,
+// the minimum distance from p to an intersection (!= p) of the infinite line p + s v with the template
+// mesh.  Triangles incident to vertex i only touch the line at p itself (the reference drops those hits
+// with `.filter(f => f != p)`), so they are skipped.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(QT) line_mesh_kernel(int M, const double* __restrict__ p /*AoS*/,
+                                                       const double* __restrict__ cp /*AoS*/, int T,
+                                                       const int32_t* __restrict__ tri,
+                                                       double* __restrict__ part_min) {
+  __shared__ double st[TT][9];
+  __shared__ int32_t sv[TT][3];
+  const int i = blockIdx.x * QT + threadIdx.x;
+  const int per = (T + gridDim.y - 1) / gridDim.y;
+  const int t_begin = blockIdx.y * per, t_end = min(T, t_begin + per);
+  const int ii = min(i, M - 1);
+  const double ox = p[3 * ii], oy = p[3 * ii + 1], oz = p[3 * ii + 2];
+  const double dx = ox - cp[3 * ii], dy = oy - cp[3 * ii + 1], dz = oz - cp[3 * ii + 2];
+  double best = INFINITY;
+  for (int t0 = t_begin; t0 < t_end; t0 += TT) {
+    const int cnt = min(TT, t_end - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * 9; e += QT) {
+      const int t = e / 9, k = e % 9;
+      const int v = tri[3 * (t0 + t) + k / 3];
+      st[t][k] = p[3 * v + (k % 3)];
+      if (k % 3 == 0) sv[t][k / 3] = v;
+    }
+    __syncthreads();
+    for (int t = 0; t < cnt; ++t) {
+      if (sv[t][0] == ii || sv[t][1] == ii || sv[t][2] == ii) continue;
+      const double* a = &st[t][0];
+      const double e1x = st[t][3] - a[0], e1y = st[t][4] - a[1], e1z = st[t][5] - a[2];
+      const double e2x = st[t][6] - a[0], e2y = st[t][7] - a[1], e2z = st[t][8] - a[2];
+      const double hx = dy * e2z - dz * e2y, hy = dz * e2x - dx * e2z, hz = dx * e2y - dy * e2x;
+      const double det = e1x * hx + e1y * hy + e1z * hz;
+      if (det == 0.0) continue;
+      const double inv = 1.0 / det;
+      const double tx = ox - a[0], ty = oy - a[1], tz = oz - a[2];
+      const double u = (tx * hx + ty * hy + tz * hz) * inv;
+      if (u < 0.0 || u > 1.0) continue;
+      const double qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+      const double vv = (dx * qx + dy * qy + dz * qz) * inv;
+      if (vv < 0.0 || u + vv > 1.0) continue;
+      const double s = (e2x * qx + e2y * qy + e2z * qz) * inv;
+      const double ix = ox + s * dx, iy = oy + s * dy, iz = oz + s * dz;
+      if (ix == ox && iy == oy && iz == oz) continue;
+      const double ex = ox - ix, ey = oy - iy, ez = oz - iz;
+      const double d = sqrt(ex * ex + ey * ey + ez * ez);
+      if (d < best) best = d;
+    }
+  }
+  if (i < M) part_min[(size_t)blockIdx.y * M + i] = best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vertex normals from a CSR vertex -> triangle adjacency (ascending triangle ids = the accumulation
+// order of a triangle-ordered scatter).  verts AoS [n][3]; normals AoS [n][3].   SURVEY.md A6
+// ---------------------------------------------------------------------------------------------
+__global__ void vertex_normals_kernel(int n, const double* __restrict__ v, const int32_t* __restrict__ tri,
+                                      const int32_t* __restrict__ adj_off, const int32_t* __restrict__ adj,
+                                      double* __restrict__ normals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double ax = 0, ay = 0, az = 0;
+  const int b = adj_off[i], e = adj_off[i + 1];
+  for (int k = b; k < e; ++k) {
+    const int t = adj[k];
+    const double* a = v + 3 * tri[3 * t];
+    const double* bb = v + 3 * tri[3 * t + 1];
+    const double* c = v + 3 * tri[3 * t + 2];
+    const double ux = bb[0] - a[0], uy = bb[1] - a[1], uz = bb[2] - a[2];
+    const double wx = c[0] - a[0], wy = c[1] - a[1], wz = c[2] - a[2];
+    double nx = uy * wz - uz * wy, ny = uz * wx - ux * wz, nz = ux * wy - uy * wx;
+    const double len = sqrt(nx * nx + ny * ny + nz * nz);
+    nx /= len; ny /= len; nz /= len;
+    ax += nx; ay += ny; az += nz;
+  }
+  const int cnt = e - b;
+  if (cnt > 0) { ax /= cnt; ay /= cnt; az /= cnt; }
+  const double len = sqrt(ax * ax + ay * ay + az * az);
+  normals[3 * i] = ax / len;
+  normals[3 * i + 1] = ay / len;
+  normals[3 * i + 2] = az / len;
+}
+
+// w = 0 if target vertex on boundary, else 0 if normals opposite, else 0 if intersecting, else 1
+// (ClosestPointRegistrator.scala:84-90).  min_part: [splits][M]
+__global__ void icp_weights_kernel(int M, const double* __restrict__ p, const double* __restrict__ cp,
+                                   const int32_t* __restrict__ idx, const uint8_t* __restrict__ tgt_boundary,
+                                   const double* __restrict__ n_tpl /*AoS*/, const double* __restrict__ n_tgt /*AoS*/,
+                                   int splits, const double* __restrict__ min_part, uint8_t* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int j = idx[i];
+  uint8_t out = 1;
+  if (tgt_boundary[j]) {
+    out = 0;
+  } else {
+    const double dot = n_tpl[3 * i] * n_tgt[3 * j] + n_tpl[3 * i + 1] * n_tgt[3 * j + 1] + n_tpl[3 * i + 2] * n_tgt[3 * j + 2];
+    if (dot < 0.0) {
+      out = 0;
+    } else {
+      double md = INFINITY;
+      for (int k = 0; k < splits; ++k) md = fmin(md, min_part[(size_t)k * M + i]);
+      const double vx = p[3 * i] - cp[3 * i], vy = p[3 * i + 1] - cp[3 * i + 1], vz = p[3 * i + 2] - cp[3 * i + 2];
+      if (md < sqrt(vx * vx + vy * vy + vz * vz)) out = 0;
+    }
+  }
+  w[i] = out;
+}
+
+__global__ void gather_points_kernel(int M, const int32_t* __restrict__ idx, int N, const double* __restrict__ soa,
+                                     double* __restrict__ out /*AoS*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int j = idx[i];
+  out[3 * i] = soa[j];
+  out[3 * i + 1] = soa[N + j];
+  out[3 * i + 2] = soa[2 * N + j];
+}
+
+// deterministic mean of sqrt(d2): one block, fixed-order tree
+__global__ void mean_sqrt_kernel(int M, const double* __restrict__ d2, double* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < M; i += 256) s += sqrt(d2[i]);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0] / M;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+void build_vertex_adjacency(int n, int T, const int32_t* tri, std::vector<int32_t>* off, std::vector<int32_t>* adj) {
+  off->assign((size_t)n + 1, 0);
+  for (int k = 0; k < 3 * T; ++k) (*off)[tri[k] + 1]++;
+  for (int i = 0; i < n; ++i) (*off)[i + 1] += (*off)[i];
+  adj->assign((size_t)3 * T, 0);
+  std::vector<int32_t> cur(off->begin(), off->end() - 1);
+  for (int t = 0; t < T; ++t)  // ascending triangle id per vertex
+    for (int k = 0; k < 3; ++k) (*adj)[cur[tri[3 * t + k]]++] = t;
+}
+
+// pointIsOnBoundary for every vertex: a vertex touching an edge that belongs to exactly one triangle
+void compute_boundary_flags(int n, int T, const int32_t* tri, std::vector<uint8_t>* flags) {
+  flags->assign((size_t)n, 0);
+  std::vector<uint64_t> edges;
+  edges.reserve((size_t)3 * T);
+  for (int t = 0; t < T; ++t)
+    for (int k = 0; k < 3; ++k) {
+      uint32_t a = (uint32_t)tri[3 * t + k], b = (uint32_t)tri[3 * t + (k + 1) % 3];
+      if (a > b) std::swap(a, b);
+      edges.push_back(((uint64_t)a << 32) | b);
+    }
+  std::sort(edges.begin(), edges.end());
+  for (size_t i = 0; i < edges.size();) {
+    size_t j = i + 1;
+    while (j < edges.size() && edges[j] == edges[i]) ++j;
+    if (j - i == 1) {
+      (*flags)[edges[i] >> 32] = 1;
+      (*flags)[edges[i] & 0xffffffffu] = 1;
+    }
+    i = j;
+  }
+}
+
+int32_t vertex_normals_enqueue(gingr_ctx* ctx, int n, const double* d_verts_aos, const int32_t* d_tri,
+                               const int32_t* d_adj_off, const int32_t* d_adj, double* d_normals) {
+  vertex_normals_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(n, d_verts_aos, d_tri, d_adj_off, d_adj, d_normals);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+// static per-mesh data for a target: vertex normals (AoS) and boundary flags
+int32_t mesh_static_upload(gingr_ctx* ctx, int n, const double* verts_aos_host, int T, const int32_t* tri_host,
+                           DevBuf<double>* normals, DevBuf<uint8_t>* boundary) {
+  std::vector<int32_t> off, adj;
+  build_vertex_adjacency(n, T, tri_host, &off, &adj);
+  std::vector<uint8_t> flags;
+  compute_boundary_flags(n, T, tri_host, &flags);
+  DevBuf<int32_t> d_off, d_adj, d_tri;
+  DevBuf<double> d_v;
+  GINGR_CUDA_TRY(ctx, d_off.alloc(off.size()));
+  GINGR_CUDA_TRY(ctx, d_adj.alloc(adj.size()));
+  GINGR_CUDA_TRY(ctx, d_tri.alloc((size_t)3 * T));
+  GINGR_CUDA_TRY(ctx, d_v.alloc((size_t)3 * n));
+  GINGR_CUDA_TRY(ctx, normals->alloc((size_t)3 * n));
+  GINGR_CUDA_TRY(ctx, boundary->alloc((size_t)n));
+  cudaStream_t st = ctx->stream;
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_adj.p, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice, st));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_tri.p, tri_host, (size_t)3 * T * 4, cudaMemcpyHostToDevice, st));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_v.p, verts_aos_host, (size_t)3 * n * 8, cudaMemcpyHostToDevice, st));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(boundary->p, flags.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+  GINGR_TRY(vertex_normals_enqueue(ctx, n, d_v.p, d_tri.p, d_off.p, d_adj.p, normals->p));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  d_off.release();
+  d_adj.release();
+  d_tri.release();
+  d_v.release();
+  return GINGR_OK;
+}
+
+static int pick_splits(const gingr_ctx* ctx, int M, int candidates, int tile) {
+  const int qblocks = ceil_div(M, QT);
+  const int want = ceil_div(ctx->num_sms * 4, qblocks);
+  return std::max(1, std::min(want, ceil_div(candidates, tile)));
+}
+
+int32_t ClosestWorkspace::ensure(gingr_ctx* ctx, int M, int N, int T_target, int T_template) {
+  s_nn = pick_splits(ctx, M, N, PT);
+  s_surf = T_target > 0 ? pick_splits(ctx, M, T_target, TT) : 1;
+  s_line = T_template > 0 ? pick_splits(ctx, M, T_template, TT) : 1;
+  const int smax = std::max(s_nn, std::max(s_surf, s_line));
+  GINGR_CUDA_TRY(ctx, part_d2.alloc((size_t)smax * M));
+  GINGR_CUDA_TRY(ctx, part_idx.alloc((size_t)smax * M));
+  GINGR_CUDA_TRY(ctx, part_cp.alloc((size_t)3 * s_surf * M));
+  GINGR_CUDA_TRY(ctx, d2.alloc((size_t)M));
+  GINGR_CUDA_TRY(ctx, idx.alloc((size_t)M));
+  GINGR_CUDA_TRY(ctx, cp.alloc((size_t)3 * M));
+  GINGR_CUDA_TRY(ctx, w.alloc((size_t)M));
+  GINGR_CUDA_TRY(ctx, n_tpl.alloc((size_t)3 * M));
+  GINGR_CUDA_TRY(ctx, mean_dist.alloc(1));
+  return GINGR_OK;
+}
+
+void ClosestWorkspace::release() {
+  part_d2.release();
+  part_idx.release();
+  part_cp.release();
+  d2.release();
+  idx.release();
+  cp.release();
+  w.release();
+  n_tpl.release();
+  mean_dist.release();
+}
+
+// Nearest target vertex of arbitrary query points (AoS, device).
+int32_t nn_vertex_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, const double* d_q, int N,
+                          const double* d_pts_soa, double* d_d2, int32_t* d_idx) {
+  nn_vertex_kernel<<<dim3(ceil_div(M, QT), ws.s_nn), QT, 0, ctx->stream>>>(M, d_q, N, d_pts_soa, ws.part_d2.p,
+                                                                          ws.part_idx.p);
+  GINGR_LAUNCHED(ctx);
+  nn_reduce_kernel<<<ceil_div(M, 128), 128, 0, ctx->stream>>>(M, ws.s_nn, ws.part_d2.p, ws.part_idx.p, d_d2, d_idx);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+// The ICP correspondence of one flavour.  Template: d_tpl (AoS [M][3]), triangles/adjacency on device.
+// Results in ws.idx / ws.cp / ws.w / ws.mean_dist.
+int32_t icp_closest_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const gingr_target* tgt, int M, const double* d_tpl,
+                            int T_tpl, const int32_t* d_tpl_tri, const int32_t* d_adj_off, const int32_t* d_adj,
+                            int method) {
+  cudaStream_t st = ctx->stream;
+  const int N = tgt->N_total;
+  if (method == GINGR_POINTCLOUD_CLOSEST_POINT) {
+    GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, d_tpl, N, tgt->verts.p, ws.d2.p, ws.idx.p));
+    gather_points_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, ws.idx.p, N, tgt->verts.p, ws.cp.p);
+    GINGR_LAUNCHED(ctx);
+    GINGR_CUDA_TRY(ctx, cudaMemsetAsync(ws.w.p, 1, (size_t)M, st));
+  } else if (method == GINGR_TRIANGULAR_CLOSEST_POINT) {
+    if (tgt->T <= 0 || T_tpl <= 0)
+      return gingr_fail(ctx, GINGR_ERR_ARG, "TriangularClosestPoint needs target and template triangles");
+    surface_kernel<<<dim3(ceil_div(M, QT), ws.s_surf), QT, 0, st>>>(M, d_tpl, N, tgt->verts.p, tgt->T, tgt->tri.p,
+                                                                    ws.part_d2.p, ws.part_idx.p, ws.part_cp.p);
+    GINGR_LAUNCHED(ctx);
+    surface_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, ws.s_surf, ws.part_d2.p, ws.part_idx.p, ws.part_cp.p,
+                                                            ws.d2.p, nullptr, ws.cp.p);
+    GINGR_LAUNCHED(ctx);
+    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.d2.p, ws.mean_dist.p);
+    GINGR_LAUNCHED(ctx);
+    // nearest target vertex of the surface point (:83); d2 of that search is not needed afterwards
+    nn_vertex_kernel<<<dim3(ceil_div(M, QT), ws.s_nn), QT, 0, st>>>(M, ws.cp.p, N, tgt->verts.p, ws.part_d2.p,
+                                                                    ws.part_idx.p);
+    GINGR_LAUNCHED(ctx);
+    nn_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, ws.s_nn, ws.part_d2.p, ws.part_idx.p, ws.d2.p, ws.idx.p);
+    GINGR_LAUNCHED(ctx);
+    GINGR_TRY(vertex_normals_enqueue(ctx, M, d_tpl, d_tpl_tri, d_adj_off, d_adj, ws.n_tpl.p));
+    line_mesh_kernel<<<dim3(ceil_div(M, QT), ws.s_line), QT, 0, st>>>(M, d_tpl, ws.cp.p, T_tpl, d_tpl_tri,
+                                                                      ws.part_d2.p);
+    GINGR_LAUNCHED(ctx);
+    icp_weights_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, d_tpl, ws.cp.p, ws.idx.p, tgt->boundary.p, ws.n_tpl.p,
+                                                         tgt->normals.p, ws.s_line, ws.part_d2.p, ws.w.p);
+    GINGR_LAUNCHED(ctx);
+    GINGR_CUDA_TRY(ctx, cudaGetLastError());
+    return GINGR_OK;
+  } else {
+    return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "AlongNormalClosestPoint is not implemented yet");
+  }
+  mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.d2.p, ws.mean_dist.p);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+}  // namespace gingr

@@ -1,0 +1,218 @@
+/*
+ * gingr_cuda.h -- C ABI of libgingr_cuda.so, the B200 (sm_100a) implementation of GiNGR's
+ * per-iteration hot path `GingrAlgorithm.update`.
+ *
+ * The reference (unibas-gravis/GiNGR, Scala 3) has NO native / FFI boundary today; the
+ * extension surface is the Scala trait `GingrAlgorithm[State, config]`
+ * (src/main/scala/gingr/api/GingrAlgorithm.scala:65).  A Scala shim (scala/ in this repo,
+ * binding shown in INTEGRATION.md) subclasses that trait, overrides `update` (:192) and
+ * `generatorCombined` (:177) and calls the entry points below through Panama FFM / JNI.
+ * Each entry point cites the reference statement it replaces (paths relative to
+ * /root/reference/src/main/scala/gingr/).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - All floating point is IEEE double (the reference is Breeze/scalismo Double end to end);
+ *     indices are int32 (scalismo PointId(id: Int)).
+ *   - Host arrays are caller-owned: inputs are read-only, outputs are caller-allocated.
+ *     Points are row-major [n][3].  The GPMM basis is COLUMN-major [3M x r] with leading
+ *     dimension `ld_basis` (Breeze DenseMatrix layout of scalismo's basisMatrix), row 3*pid+d.
+ *   - Device memory is library-owned behind opaque handles and freed only by *_destroy.
+ *   - A gingr_ctx is bound to one CUDA device and is single-threaded (the reference calls
+ *     `update` from one thread per algorithm instance, GingrAlgorithm.scala:70).  Distinct
+ *     contexts may be used concurrently.  Multi-GPU = one process (or thread) per GPU, each
+ *     with its own ctx, joined by gingr_comm_init (NCCL).
+ *   - Every function returns an int32 status: 0 = OK, 1 = MODEL_FLEXIBILITY (the numerical
+ *     failure the reference maps to FittingStatuses.ModelFlexibilityError,
+ *     GingrAlgorithm.scala:194-208, :214-217, :235-251), negative = error; text via
+ *     gingr_last_error.  No exceptions cross the ABI.  There is no CPU fallback: without a
+ *     CUDA device gingr_ctx_create fails with GINGR_ERR_CUDA.
+ */
+#ifndef GINGR_CUDA_H
+#define GINGR_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GINGR_API __attribute__((visibility("default")))
+
+/* ---- status codes -------------------------------------------------------------------------- */
+#define GINGR_OK 0
+#define GINGR_MODEL_FLEXIBILITY 1 /* non-finite result or matrix not SPD */
+#define GINGR_ERR_ARG (-1)
+#define GINGR_ERR_CUDA (-2)
+#define GINGR_ERR_NCCL (-3)
+#define GINGR_ERR_UNSUPPORTED (-4)
+
+/* ---- enums mirroring the reference --------------------------------------------------------- */
+/* api/FittingStatuses.scala:20-23 (Enumeration order) */
+#define GINGR_STATUS_NONE 0
+#define GINGR_STATUS_MAX_ITERATION 1
+#define GINGR_STATUS_CONVERGED 2
+#define GINGR_STATUS_MODEL_FLEXIBILITY_ERROR 3
+/* api/GlobalTranformationType.scala:20-24 */
+#define GINGR_SIMILARITY_TRANSFORMS 0
+#define GINGR_RIGID_TRANSFORMS 1
+#define GINGR_NO_TRANSFORMS 2
+/* registration/config/ICP.scala:29-33 ICPCorrespondenceMethod */
+#define GINGR_TRIANGULAR_CLOSEST_POINT 0
+#define GINGR_ALONG_NORMAL_CLOSEST_POINT 1
+#define GINGR_POINTCLOUD_CLOSEST_POINT 2
+/* which GingrAlgorithm subclass */
+#define GINGR_ALGO_CPD 0 /* registration/config/CPD.scala:117 CpdRegistration */
+#define GINGR_ALGO_ICP 1 /* registration/config/ICP.scala:84 IcpRegistration */
+
+typedef struct gingr_ctx gingr_ctx;
+typedef struct gingr_model gingr_model;               /* scalismo PointDistributionModel on device */
+typedef struct gingr_target gingr_target;             /* target TriangleMesh on device */
+typedef struct gingr_registration gingr_registration; /* model + target + config + workspaces */
+
+/*
+ * POD mirror of the numeric part of GeneralRegistrationState (api/GeneralRegistrationState.scala:28-41)
+ * and ModelFittingParameters (api/ModelFittingParameters.scala:31-74).  The shape coefficient
+ * vector alpha[rank] travels beside it as a plain double array.  `model`, `target`, landmarks live
+ * in the handles; `fit` is an explicit array argument.
+ */
+typedef struct gingr_state {
+  double scale;          /* ScaleParameter.s */
+  double translation[3]; /* PoseParameters.translation */
+  double euler[3];       /* EulerAngles phi, theta, psi  (R = Rz(phi) Ry(theta) Rx(psi)) */
+  double center[3];      /* EulerRotation.center -- GiNGR always uses the origin */
+  double sigma2;         /* GeneralRegistrationState.sigma2 */
+  double step_length;    /* GeneralRegistrationState.stepLength */
+  int32_t global_transformation; /* GINGR_*_TRANSFORMS */
+  int32_t iteration;
+  int32_t status; /* GINGR_STATUS_* */
+  int32_t rank;   /* length of alpha */
+} gingr_state;
+
+/*
+ * POD mirror of CpdConfiguration (registration/config/CPD.scala:105-115) and IcpConfiguration
+ * (registration/config/ICP.scala:54-66).  The `converged` closure stays on the host side.
+ */
+typedef struct gingr_config {
+  int32_t algorithm; /* GINGR_ALGO_* */
+  int32_t max_iterations;
+  double threshold;
+  int32_t use_landmark_correspondence;
+  int32_t has_initial_sigma; /* CPD: initialSigma: Option[Double] */
+  double initial_sigma;      /* CPD (if has_initial_sigma) / ICP initialSigma (used as sigma2, ICP.scala:74-78) */
+  double w;                  /* CPD outlier weight */
+  double lambda;             /* CPD noise scaling (CPD.scala:114, :125) */
+  double end_sigma;          /* ICP */
+  int32_t reverse_correspondence_direction; /* ICP */
+  int32_t correspondence_method;            /* ICP, GINGR_*_CLOSEST_POINT */
+} gingr_config;
+
+/* ---- context --------------------------------------------------------------------------------- */
+GINGR_API int32_t gingr_version(void);
+GINGR_API int32_t gingr_ctx_create(int32_t device, gingr_ctx** out);
+GINGR_API int32_t gingr_ctx_destroy(gingr_ctx* ctx);
+/* Text of the last error on this ctx (or of the last ctx-less error when ctx == NULL). */
+GINGR_API const char* gingr_last_error(const gingr_ctx* ctx);
+/* cudaStream_t all work of this ctx is enqueued on (for CUDA-event timing by the caller). */
+GINGR_API void* gingr_ctx_stream(gingr_ctx* ctx);
+GINGR_API int32_t gingr_ctx_synchronize(gingr_ctx* ctx);
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+GINGR_API int64_t gingr_ctx_launch_count(const gingr_ctx* ctx);
+
+/* ---- multi-GPU (new: the reference has no distributed code) ------------------- */
+/* Rank 0 creates an id and ships it to the other ranks by any host channel. */
+GINGR_API int32_t gingr_comm_unique_id(char id[128]);
+/* Join an NCCL communicator of `nranks` contexts.  After this call, target points (E-step) and
+ * GPMM basis rows (Gram, fit evaluation) uploaded through this ctx are sharded by rank and the
+ * partial sums are combined with ncclAllReduce inside gingr_update. */
+GINGR_API int32_t gingr_comm_init(gingr_ctx* ctx, int32_t nranks, int32_t rank, const char id[128]);
+
+/* ---- uploads ----------------------------------------------------------------------------------- */
+/* scalismo PointDistributionModel: reference points, meanVector, basisMatrix, variance
+ * (SURVEY.md A1).  tri may be NULL (T = 0) for CPD-only use; ICP needs the reference triangles. */
+GINGR_API int32_t gingr_model_upload(gingr_ctx* ctx, int32_t M, int32_t r, const double* ref_pts /*[3M]*/,
+                                     const double* mean /*[3M]*/, const double* basis /*col-major*/,
+                                     int64_t ld_basis, const double* variance /*[r]*/,
+                                     const int32_t* tri /*[3T]*/, int32_t T, gingr_model** out);
+GINGR_API int32_t gingr_model_destroy(gingr_model* m);
+GINGR_API int32_t gingr_target_upload(gingr_ctx* ctx, int32_t N, const double* pts /*[3N]*/,
+                                      const int32_t* tri /*[3T]*/, int32_t T, gingr_target** out);
+GINGR_API int32_t gingr_target_destroy(gingr_target* t);
+
+/* ---- K1: CPD / BCPD E-step ------------------------------------------------------------------- */
+/* Replaces CpdRegistrationState.P (CPD.scala:54-75) + its reductions: P1 = sum(P,Axis._1)
+ * (CPD.scala:36, :122, :139), Pt1 = sum(P,Axis._0) (:140), PX = P*X (:145).  P is never
+ * materialised.  Any output pointer may be NULL. */
+GINGR_API int32_t gingr_cpd_estep(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* fit /*[3M]*/,
+                                  double sigma2, double w, double* P1 /*[M]*/, double* Pt1 /*[N]*/,
+                                  double* PX /*[3M]*/);
+/* Replaces BCPD.computeP + the P reductions of BCPD.Iteration
+ * (other/algorithms/cpd/BCPD.scala:167-184, :200-209); quirks of the reference kept. */
+GINGR_API int32_t gingr_bcpd_estep(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* y /*[3M]*/,
+                                   const double* sigma_mm /*[M]*/, const double* alpha /*[M]*/, double sigma2,
+                                   double s, double w, double* nu /*[M]*/, double* nu_prime /*[N]*/,
+                                   double* n_hat /*[1]*/, double* x_hat /*[3M]*/);
+/* computeInitialSigma2 (CPD.scala:81-90): sum_ij |x_j - m_i|^2 / (3 N M). */
+GINGR_API int32_t gingr_cpd_initial_sigma2(gingr_ctx* ctx, const gingr_target* target, int32_t M,
+                                           const double* pts /*[3M]*/, double* sigma2_out);
+
+/* ---- K2: ICP closest-point correspondence ---------------------------------------------------- */
+/* Replaces closestPointCorrespondence of registration/utils/ClosestPointRegistrator.scala
+ * (:74-96 triangular, :133-160 point cloud) and, with reverse != 0, closestPointCorrespondenceReversal
+ * (:34-45).  `tpl` / `tpl_tri` are the template (current fit) vertices and triangles.
+ * Outputs per template vertex (or per target vertex when reversed): idx = nearest target vertex id
+ * (exact argmin, ties -> lowest index), cp = corresponding point, w = 0/1 robustness weight. */
+GINGR_API int32_t gingr_icp_closest(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* tpl /*[3M]*/,
+                                    const int32_t* tpl_tri /*[3T]*/, int32_t T, int32_t method, int32_t* idx /*[M]*/,
+                                    double* cp /*[3M]*/, uint8_t* w /*[M]*/, double* mean_distance /*[1]*/);
+
+/* ---- K3: low-rank GPMM posterior ------------------------------------------------------------- */
+/* Replaces model.transform(rigid).posterior(obs).mean (GingrAlgorithm.scala:297-301, :211;
+ * scalismo regression): weighted Gram Q^T L^-1 Q + I on the FP64 tensor pipe,
+ * Cholesky solve, mean evaluation at all M points.
+ * R[9] row-major rotation about the origin, t[3]; n observations (pid, point); noise_kind 0:
+ * noise[n] isotropic variances (cov_i = noise_i * I3), 1: noise[9n] full row-major covariances. */
+GINGR_API int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t,
+                                       int32_t n, const int32_t* pid, const double* points /*[3n]*/,
+                                       int32_t noise_kind, const double* noise, double* coeffs /*[r]*/,
+                                       double* mean_pts /*[3M]*/);
+/* Replaces model.transform(rigid).coefficients(mesh) (GingrAlgorithm.scala:215, :236): regression on
+ * all M points with noise 1e-5 * I3. */
+GINGR_API int32_t gingr_coefficients(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t,
+                                     const double* mesh_pts /*[3M]*/, double* coeffs /*[r]*/);
+/* Replaces ModelFittingParameters.modelInstanceShapePoseScale (ModelFittingParameters.scala:130-143):
+ * fit = s * (R * instance(alpha) + t). */
+GINGR_API int32_t gingr_model_instance(gingr_ctx* ctx, const gingr_model* model, const gingr_state* st,
+                                       const double* alpha /*[r]*/, double* fit /*[3M]*/);
+
+/* ---- the full iteration ------------------------------------------------------------------------ */
+GINGR_API int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, const gingr_target* target,
+                                            const gingr_config* cfg, gingr_registration** out);
+GINGR_API int32_t gingr_registration_destroy(gingr_registration* reg);
+/* GeneralRegistrationState.landmarkCorrespondences (GeneralRegistrationState.scala:43-62), already
+ * resolved by the host: nearest reference vertex id, target landmark point, 3x3 row-major covariance. */
+GINGR_API int32_t gingr_registration_set_landmarks(gingr_registration* reg, int32_t L, const int32_t* pid,
+                                                   const double* points /*[3L]*/, const double* cov /*[9L]*/);
+/* initializeState (CPD.scala:92-103 / ICP.scala:74-86): sets st->sigma2 (computeInitialSigma2 over
+ * model.mean for CPD without initialSigma) and evaluates the initial fit. */
+GINGR_API int32_t gingr_initialize_state(gingr_registration* reg, gingr_state* st /*in/out*/,
+                                         const double* alpha /*[r]*/, double* fit_out /*[3M], may be NULL*/);
+/* GingrAlgorithm.update (GingrAlgorithm.scala:192-254) for the deterministic branch, followed by the
+ * fit refresh of GingrGeneratorWrapper.propose (sampling/generators/GingrGeneratorWrapper.scala:28-39)
+ * delivered in fit_out (state_out->iteration is NOT incremented here: that stays with `propose`).
+ * state_out->status is GINGR_STATUS_MODEL_FLEXIBILITY_ERROR exactly where the reference's Try fails;
+ * the function's own return value is then GINGR_OK (the state carries the failure, as in the reference). */
+GINGR_API int32_t gingr_update(gingr_registration* reg, const gingr_state* state_in, const double* alpha_in /*[r]*/,
+                               int32_t probabilistic, uint64_t seed, gingr_state* state_out,
+                               double* alpha_out /*[r]*/, double* fit_out /*[3M], may be NULL*/);
+/* Device-resident chaining for throughput runs: enqueue `iters` consecutive update+propose steps
+ * starting from the state of the last gingr_update / gingr_initialize_state without host round trips. */
+GINGR_API int32_t gingr_update_chain(gingr_registration* reg, int32_t iters);
+/* Read back the device-resident state after gingr_update_chain. */
+GINGR_API int32_t gingr_state_download(gingr_registration* reg, gingr_state* state_out, double* alpha_out,
+                                       double* fit_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GINGR_CUDA_H */

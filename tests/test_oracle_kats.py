@@ -1,0 +1,227 @@
+"""Known-answer tests pinning the CPU oracle (CPU only).  The reference ships no golden vectors
+(src/test/scala/DummyTest.scala.scala:1-3 -- PARITY UNPINNED), so these follow from the reference's
+formulas alone."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+
+def _cloud(n, seed, scale=50.0):
+    return np.random.default_rng(seed).normal(scale=scale, size=(n, 3))
+
+
+def test_P_columns_sum_to_one_without_outliers(oracle):
+    # w = 0  =>  c = 0, Pt1_j = 1, sum_i P1_i = N        (CPD.scala:69-74)
+    fit, tgt = _cloud(37, 0), _cloud(53, 1)
+    P = oracle.cpd_P(fit, tgt, 400.0, 0.0)
+    P1, Pt1, PX = oracle.P_reductions(P, tgt)
+    np.testing.assert_allclose(Pt1, 1.0, rtol=0, atol=1e-14)
+    assert abs(P1.sum() - 53) < 1e-11
+
+
+def test_outlier_term_matches_formula(oracle):
+    fit, tgt = _cloud(20, 2), _cloud(30, 3)
+    s2, w = 250.0, 0.3
+    P = oracle.cpd_P(fit, tgt, s2, w)
+    K = np.exp(-((tgt[None, :, :] - fit[:, None, :]) ** 2).sum(-1) / (2 * s2))
+    c = w / (1 - w) * (2 * np.pi * s2) ** 1.5 * 20 / 30
+    np.testing.assert_allclose(P, K / (K.sum(0, keepdims=True) + c), rtol=1e-13)
+
+
+@pytest.mark.parametrize("w", [0.0, 0.1])
+def test_streaming_estep_equals_literal(oracle, w):
+    fit, tgt = _cloud(65, 4), _cloud(129, 5)
+    P = oracle.cpd_P(fit, tgt, 300.0, w)
+    P1, Pt1, PX = oracle.P_reductions(P, tgt)
+    for fast in (False, True):
+        q1, qt1, qx = oracle.cpd_estep(fit, tgt, 300.0, w, fast=fast)
+        assert rel_err(q1, P1) < 1e-13 and rel_err(qt1, Pt1) < 1e-13 and rel_err(qx, PX) < 1e-13
+
+
+def test_correspondence_is_PX_over_P1(oracle):
+    fit, tgt = _cloud(40, 6), _cloud(60, 7)
+    P = oracle.cpd_P(fit, tgt, 500.0, 0.05)
+    P1, _, PX = oracle.P_reductions(P, tgt)
+    td = oracle.cpd_correspondence(P, fit, tgt)
+    assert rel_err(td, PX / P1[:, None]) < 1e-13
+
+
+def test_sigma2_update_equals_brute_force(oracle):
+    # CPD.scala:142-145 == sum_ij P_ij |x_j - ty_i|^2 / (3 Np)
+    fit, tgt = _cloud(31, 8), _cloud(47, 9)
+    P = oracle.cpd_P(fit, tgt, 700.0, 0.1)
+    P1, Pt1, PX = oracle.P_reductions(P, tgt)
+    s2 = oracle.cpd_sigma2_update(P1, Pt1, PX, tgt, fit)
+    d2 = ((tgt[None, :, :] - fit[:, None, :]) ** 2).sum(-1)
+    assert abs(s2 - (P * d2).sum() / (3 * P1.sum())) < 1e-9 * s2
+
+
+def test_initial_sigma2(oracle):
+    a, b = _cloud(23, 10), _cloud(29, 11)
+    ref = ((b[None] - a[:, None]) ** 2).sum() / (3 * 23 * 29)
+    assert abs(oracle.cpd_initial_sigma2(a, b) - ref) < 1e-12 * ref
+
+
+def test_femur_scale_dynamic_range(oracle):
+    # DemoCPD setting sigma2 = 1 on coordinates of +-200: column sums far below FP32 range, still finite
+    rng = np.random.default_rng(12)
+    fit = rng.uniform(-200, 200, size=(100, 3))
+    tgt = fit[rng.permutation(100)] + rng.normal(scale=8.0, size=(100, 3))
+    P = oracle.cpd_P(fit, tgt, 1.0, 0.0)
+    assert np.all(np.isfinite(P))
+    K = np.exp(-((tgt[None] - fit[:, None]) ** 2).sum(-1) / 2.0)
+    assert K.sum(0).min() < 1e-45  # below FP32 range (1.4e-45)
+
+
+def test_bcpd_P_matches_dense_formula(oracle):
+    y, x = _cloud(12, 13, 5.0), _cloud(17, 14, 5.0)
+    sig = np.random.default_rng(15).uniform(0.1, 1.0, 12)
+    al = np.full(12, 1 / 12)
+    s2, s, w = 9.0, 1.1, 0.2
+    P = oracle.bcpd_P(y, x, sig, al, s2, s, w)
+    d2 = ((x[None] - y[:, None]) ** 2).sum(-1)
+    phi = (2 * np.pi * s2) ** -1.5 * np.exp(-d2 / (2 * s2)) * np.exp(-s / (2 * s2) * 3 * sig)[:, None] * al[:, None]
+    Pinit = phi * (1 - w)
+    den = Pinit.sum(0) * (1 - w) + w / 17
+    np.testing.assert_allclose(P, Pinit / den, rtol=1e-12)
+
+
+def test_nearest_vertex_lowest_index_on_ties(oracle):
+    pts = np.array([[0, 0, 0], [2, 0, 0], [0, 2, 0], [2, 0, 0.0]])
+    q = np.array([[1, 0, 0], [2, 0.1, 0], [0.2, 1.9, 0.0]])
+    idx, d2 = oracle.nearest_vertex(q, pts)
+    assert idx.tolist() == [0, 1, 2]
+    assert d2[0] == 1.0
+
+
+def test_nearest_vertex_matches_numpy(oracle):
+    q, p = _cloud(200, 16), _cloud(333, 17)
+    idx, d2 = oracle.nearest_vertex(q, p)
+    D = ((q[:, None] - p[None]) ** 2).sum(-1)
+    assert np.array_equal(idx, D.argmin(1))
+
+
+def test_closest_on_triangle_regions(oracle):
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0.0]])
+    tri = np.array([[0, 1, 2]], dtype=np.int32)
+    q = np.array([[0.25, 0.25, 1.0], [-1, -1, 0], [2, 0, 0], [0, 3, 0], [0.5, -1, 0], [1, 1, 0], [-1, 0.5, 2]])
+    cp, d2, ti = oracle.closest_on_surface(q, v, tri)
+    expect = np.array([[0.25, 0.25, 0], [0, 0, 0], [1, 0, 0], [0, 1, 0], [0.5, 0, 0], [0.5, 0.5, 0], [0, 0.5, 0]])
+    np.testing.assert_allclose(cp, expect, atol=1e-15)
+    np.testing.assert_allclose(d2, ((q - expect) ** 2).sum(1), atol=1e-15)
+
+
+def test_closest_on_surface_of_sphere_mesh(oracle):
+    from gingr_b200 import synthetic
+    v, tri = synthetic.sphere_mesh(300)
+    q = synthetic.fibonacci_sphere(50, 130.0)
+    cp, d2, ti = oracle.closest_on_surface(q, v, tri)
+    # closest point lies on the returned triangle's plane and is no farther than any vertex
+    assert np.all(np.sqrt(d2) <= np.sqrt(((q[:, None] - v[None]) ** 2).sum(-1)).min(1) + 1e-12)
+    assert np.all(np.sqrt(d2) > 25.0)
+
+
+def test_boundary_and_normals(oracle):
+    from gingr_b200 import synthetic
+    v, tri = synthetic.sphere_mesh(200)
+    assert not oracle.boundary_vertices(200, tri).any()          # closed mesh
+    n = oracle.vertex_normals(v, tri)
+    assert np.all(np.einsum("ij,ij->i", n, v / 100.0) > 0.95)     # outward
+    open_tri = tri[~np.any(tri == 0, axis=1)]                    # remove the fan around vertex 0
+    b = oracle.boundary_vertices(200, open_tri)
+    ring = np.unique(tri[np.any(tri == 0, axis=1)])
+    assert set(np.nonzero(b)[0]) == set(ring) - {0}
+
+
+def test_euler_round_trip(oracle):
+    for ang in [(0.1, 0.2, 0.3), (-1.0, 0.5, 2.0), (0.0, 0.0, 0.0)]:
+        R = oracle.euler_to_matrix(*ang)
+        np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-15)
+        np.testing.assert_allclose(oracle.matrix_to_euler(R), ang, atol=1e-14)
+
+
+def test_umeyama_recovers_planted_motion(oracle):
+    X = _cloud(50, 18)
+    R0 = oracle.euler_to_matrix(0.3, -0.2, 0.1)
+    t0 = np.array([5.0, -3.0, 2.0])
+    R, t, s = oracle.umeyama(X, X @ R0.T + t0, False)
+    np.testing.assert_allclose(R, R0, atol=1e-12)
+    np.testing.assert_allclose(t, t0, atol=1e-10)
+    R, t, s = oracle.umeyama(X, 1.7 * (X @ R0.T) + t0, True)
+    assert abs(s - 1.7) < 1e-12
+
+
+def _small_model(oracle, M=60, r=12, seed=0):
+    from gingr_b200 import synthetic
+    ref, tri = synthetic.sphere_mesh(M)
+    mean, basis, var = synthetic.make_gpmm(ref, r, seed)
+    return oracle.Gpmm(ref, mean, basis, var, tri)
+
+
+def test_coefficients_of_instance_shrink(oracle):
+    # orthonormal basis: coefficients(instance(a)) = a * l/(l + 1e-5)
+    m = _small_model(oracle)
+    a = np.random.default_rng(1).normal(size=m.rank)
+    c = m.coefficients(m.instance(a))
+    np.testing.assert_allclose(c, a * m.variance / (m.variance + 1e-5), rtol=1e-9)
+
+
+def test_posterior_limits(oracle):
+    m = _small_model(oracle)
+    a = np.random.default_rng(2).normal(size=m.rank)
+    obs = m.instance(a)
+    pids = np.arange(m.M)
+    big = np.eye(3)[None] * 1e12 * np.ones((m.M, 1, 1))
+    c, _ = m.posterior_coefficients(pids, obs, big)
+    assert np.abs(c).max() < 1e-6                                 # noise -> inf : prior mean
+    tiny = np.eye(3)[None] * 1e-9 * np.ones((m.M, 1, 1))
+    c, _ = m.posterior_coefficients(pids, obs, tiny)
+    np.testing.assert_allclose(m.instance(c), obs, atol=1e-6)     # noise -> 0 : interpolates
+
+
+def test_transform_commutes_with_instance(oracle):
+    m = _small_model(oracle)
+    a = np.random.default_rng(3).normal(size=m.rank)
+    R, t = oracle.euler_to_matrix(0.2, 0.1, -0.3), np.array([1.0, 2.0, 3.0])
+    np.testing.assert_allclose(m.transform(R, t).instance(a), m.instance(a) @ R.T + t, atol=1e-11)
+
+
+def test_update_runs_and_reduces_distance(oracle):
+    from gingr_b200 import synthetic
+    m = _small_model(oracle, M=80, r=15)
+    a_true = np.random.default_rng(4).normal(size=m.rank)
+    target = m.instance(a_true)
+    st = oracle.initial_state(m, target, global_transformation=oracle.NO_TRANSFORMS)
+    algo = oracle.CpdAlgorithm(oracle.CpdConfig(max_iterations=15))
+    out = oracle.run(algo, st)
+    d0 = np.abs(st.fit - target).mean()
+    d1 = np.abs(out.fit - target).mean()
+    assert d1 < 0.2 * d0
+    assert out.status in (oracle.STATUS_MAX_ITERATION, oracle.STATUS_CONVERGED)
+    assert out.iteration >= 1
+
+
+def test_update_literal_equals_streaming(oracle):
+    m = _small_model(oracle, M=50, r=10)
+    target = m.instance(np.random.default_rng(5).normal(size=m.rank))
+    st = oracle.initial_state(m, target, global_transformation=oracle.RIGID_TRANSFORMS)
+    a = oracle.CpdAlgorithm(oracle.CpdConfig(), literal=True)
+    b = oracle.CpdAlgorithm(oracle.CpdConfig(), literal=False)
+    sa = oracle.propose(a, a.initialize(st))
+    sb = oracle.propose(b, b.initialize(st))
+    assert rel_err(sa.params.shape, sb.params.shape) < 1e-10
+    assert rel_err(sa.fit, sb.fit) < 1e-12
+    assert abs(sa.sigma2 - sb.sigma2) < 1e-10 * sa.sigma2
+
+
+def test_icp_update_runs(oracle):
+    from gingr_b200 import synthetic
+    m = _small_model(oracle, M=120, r=15)
+    tv, tt = synthetic.sphere_mesh(150)
+    target = synthetic.make_target(tv, 0, t=(1.0, 1.0, 1.0), euler=(0.01, 0.01, 0.01))
+    st = oracle.initial_state(m, target, tt, global_transformation=oracle.NO_TRANSFORMS)
+    algo = oracle.IcpAlgorithm(oracle.IcpConfig(max_iterations=5, initial_sigma=1.0, end_sigma=1.0))
+    out = oracle.run(algo, st)
+    assert out.iteration == 4 and out.status == oracle.STATUS_MAX_ITERATION
+    assert np.all(np.isfinite(out.fit))
