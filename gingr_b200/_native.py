@@ -115,7 +115,9 @@ def load(bind: bool = True):
     lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
     if bind:
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)
+            fn = getattr(lib, name, None)
+            if fn is None:   # stale build: calling it raises, nothing is emulated
+                raise GingrError(GINGR_ERR_UNSUPPORTED, f"{LIB_PATH} does not export {name}; rebuild it")
             fn.restype = res
             fn.argtypes = args
     _lib = lib

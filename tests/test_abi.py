@@ -39,8 +39,8 @@ def test_pod_layout_matches_header():
     # gingr_state: 12 doubles + 4 int32 ; gingr_config: see header
     assert ctypes.sizeof(nat.GingrState) == 12 * 8 + 4 * 4
     assert nat.GingrState.sigma2.offset == 80 and nat.GingrState.rank.offset == 108
-    assert ctypes.sizeof(nat.GingrConfig) == 72
-    assert nat.GingrConfig.threshold.offset == 8 and nat.GingrConfig.correspondence_method.offset == 68
+    assert ctypes.sizeof(nat.GingrConfig) == 64
+    assert nat.GingrConfig.threshold.offset == 8 and nat.GingrConfig.correspondence_method.offset == 60
 
 
 def test_no_cpu_fallback_without_gpu():
