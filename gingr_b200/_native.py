@@ -1,7 +1,7 @@
 """ctypes binding of libgingr_cuda.so (the C ABI of include/gingr_cuda.h).
 
 There is deliberately NO fallback: if the library is missing, or no B200 is present when a context is
-created, the calls raise.  Nothing here imports oracle/.
+created, the calls raise.  The CPU oracle (test infrastructure) is never imported here.
 """
 from __future__ import annotations
 
