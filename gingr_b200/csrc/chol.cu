@@ -1,0 +1,245 @@
+// chol.cu -- K3b: on-device r x r Cholesky factorisation and triangular solves (sm_100a).
+//
+// Replaces `Minv = breeze.linalg.pinv(M)` of scalismo's regression (call sites
+// GingrAlgorithm.scala:300, :215, :236).  M = Q^T L^-1 Q + I is symmetric positive definite, so
+// M^-1 b is obtained from M = L L^T; a failed pivot (M not SPD / non-finite input) is reported through
+// d_info and becomes FittingStatuses.ModelFlexibilityError where the reference's Try fails.
+//
+// Blocked right-looking factorisation, block 64:
+//   chol_panel_kernel   every CTA factorises the 64 x 64 diagonal block redundantly in shared memory
+//                       (no extra launch / grid sync) and solves its own 64 rows of the panel
+//   chol_syrk_kernel    trailing update C -= X X^T on DMMA.8x8x4 (64 x 64 tiles, K = 64)
+// Rows below the square part (right-hand sides stored as extra rows) ride along, which performs the
+// forward substitution L^-1 b inside the factorisation.  The backward substitution L^-T z is a sync-free
+// multi-CTA kernel: one CTA per 64-block, consuming solved blocks as their ready flags appear.
+#include "common.cuh"
+#include "posterior.cuh"
+
+namespace gingr {
+
+constexpr int NB = 64;
+constexpr int SP = NB + 1;  // shared pitch for the scalar kernels
+constexpr size_t PANEL_SMEM = 2 * NB * SP * sizeof(double);
+
+// ---------------------------------------------------------------------------------------------
+// panel: diagonal block factorisation + triangular solve of the rows below
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chol_panel_kernel(int nrows, int j0, int jb, double* __restrict__ A, int ld,
+                                                         int* __restrict__ info) {
+  extern __shared__ __align__(16) double psm[];
+  double* sD = psm;
+  double* sX = psm + NB * SP;
+  const int tid = threadIdx.x;
+  // load the diagonal block (lower part; upper set to 0)
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e / NB, k = e % NB;
+    sD[i * SP + k] = (i < jb && k <= i) ? A[(size_t)(j0 + i) * ld + j0 + k] : (i == k ? 1.0 : 0.0);
+  }
+  bool bad = false;
+  for (int j = 0; j < jb; ++j) {
+    __syncthreads();
+    const double d = sD[j * SP + j];
+    if (!(d > 0.0) || !(d < INFINITY)) bad = true;
+    const double djj = sqrt(d);
+    __syncthreads();
+    if (tid == 0) sD[j * SP + j] = djj;
+    if (tid > j && tid < jb) sD[tid * SP + j] /= djj;
+    __syncthreads();
+    // trailing rank-1 update of the lower part: rows i in (j, jb), cols k in (j, i]
+    const int m = jb - j - 1;
+    for (int e = tid; e < m * m; e += 256) {
+      const int i = j + 1 + e / m, k = j + 1 + e % m;
+      if (k <= i) sD[i * SP + k] -= sD[i * SP + j] * sD[k * SP + j];
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (bad && tid == 0) info[0] = 1;
+    for (int e = tid; e < jb * jb; e += 256) {
+      const int i = e / jb, k = e % jb;
+      if (k <= i) A[(size_t)(j0 + i) * ld + j0 + k] = sD[i * SP + k];
+    }
+  }
+  // rows of this CTA
+  const int i0 = j0 + jb + blockIdx.x * NB;
+  const int cnt = min(NB, nrows - i0);
+  if (cnt <= 0) return;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e / NB, k = e % NB;
+    sX[i * SP + k] = (i < cnt && k < jb) ? A[(size_t)(i0 + i) * ld + j0 + k] : 0.0;
+  }
+  __syncthreads();
+  // X <- X D^-T : column c of X is final after dividing by D[c][c]; then eliminate it from later columns
+  for (int c = 0; c < jb; ++c) {
+    if (tid < NB) sX[tid * SP + c] /= sD[c * SP + c];
+    __syncthreads();
+    const int m = jb - c - 1;
+    for (int e = tid; e < NB * m; e += 256) {
+      const int i = e / m, cc = c + 1 + e % m;
+      sX[i * SP + cc] -= sX[i * SP + c] * sD[cc * SP + c];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < cnt * jb; e += 256) {
+    const int i = e / jb, k = e % jb;
+    A[(size_t)(i0 + i) * ld + j0 + k] = sX[i * SP + k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// trailing update on DMMA:  C[i][k] -= sum_c X[i][c] X[k][c],  c in [j0, j0 + 64)
+// grid (col tiles, row tiles) over the region rows >= r0, cols in [r0, n); tiles above the diagonal exit.
+// ---------------------------------------------------------------------------------------------
+constexpr int UP = NB + 4;  // pitch == 4 mod 16: conflict-free DMMA fragment loads
+constexpr size_t SYRK_SMEM = 2 * NB * UP * sizeof(double);
+
+__device__ __forceinline__ void dmma884s(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128) chol_syrk_kernel(int nrows, int n, int j0, int jb, int r0,
+                                                        double* __restrict__ A, int ld) {
+  extern __shared__ __align__(16) double sm[];
+  double* sI = sm;            // [64][UP] rows of the row tile
+  double* sK = sm + NB * UP;  // [64][UP] rows of the column tile
+  const int ti = blockIdx.y, tk = blockIdx.x;
+  const int i0 = r0 + ti * NB, k0 = r0 + tk * NB;
+  if (k0 > i0 || k0 >= n || i0 >= nrows) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
+  const int icnt = min(NB, nrows - i0), kcnt = min(NB, n - k0);
+  for (int e = tid; e < NB * NB; e += 128) {
+    const int i = e / NB, c = e % NB;
+    sI[i * UP + c] = (i < icnt && c < jb) ? A[(size_t)(i0 + i) * ld + j0 + c] : 0.0;
+    sK[i * UP + c] = (i < kcnt && c < jb) ? A[(size_t)(k0 + i) * ld + j0 + c] : 0.0;
+  }
+  __syncthreads();
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
+  for (int c4 = 0; c4 < NB / 4; ++c4) {
+    double af[4], bf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) af[i] = sI[(wm * 32 + i * 8 + g) * UP + c4 * 4 + t];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bf[j] = sK[(wn * 32 + j * 8 + g) * UP + c4 * 4 + t];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884s(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = wm * 32 + i * 8 + g, col = wn * 32 + j * 8 + 2 * t;
+      if (row < icnt) {
+        double* p = A + (size_t)(i0 + row) * ld + k0 + col;
+        if (col + 1 < kcnt) {
+          double2 v = *reinterpret_cast<double2*>(p);
+          v.x -= acc[i][j][0];
+          v.y -= acc[i][j][1];
+          *reinterpret_cast<double2*>(p) = v;
+        } else if (col < kcnt) {
+          p[0] -= acc[i][j][0];
+        }
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward substitution  L^T c = z,  one CTA per 64-block, blocks become ready from the last one up
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chol_backsolve_kernel(int n, const double* __restrict__ L, int ld,
+                                                             const double* __restrict__ z, double* __restrict__ c,
+                                                             volatile int* __restrict__ flags) {
+  __shared__ double sD[NB * SP];
+  __shared__ double sc[NB];
+  __shared__ double sacc[4][NB];
+  __shared__ double acc[NB];
+  const int nb = (n + NB - 1) / NB;
+  const int k = nb - 1 - blockIdx.x;  // first CTAs own the last blocks (solved first)
+  const int tid = threadIdx.x;
+  const int k0 = k * NB, kcnt = min(NB, n - k0);
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e / NB, j = e % NB;
+    sD[i * SP + j] = (i < kcnt && j <= i) ? L[(size_t)(k0 + i) * ld + k0 + j] : (i == j ? 1.0 : 0.0);
+  }
+  if (tid < NB) acc[tid] = tid < kcnt ? z[k0 + tid] : 0.0;
+  const int col = tid & 63, part = tid >> 6;
+  double s = 0.0;
+  for (int i = nb - 1; i > k; --i) {
+    if (tid == 0) {
+      while (flags[i] == 0) {
+      }
+    }
+    __syncthreads();
+    __threadfence();
+    const int i0 = i * NB, icnt = min(NB, n - i0);
+    if (tid < NB) sc[tid] = tid < icnt ? __ldcg(c + i0 + tid) : 0.0;
+    __syncthreads();
+    if (col < kcnt) {
+      const int r_begin = part * 16, r_end = min(icnt, r_begin + 16);
+      for (int rr = r_begin; rr < r_end; ++rr) s = fma(L[(size_t)(i0 + rr) * ld + k0 + col], sc[rr], s);
+    }
+  }
+  sacc[part][col] = s;
+  __syncthreads();
+  if (tid < NB) acc[tid] -= (sacc[0][tid] + sacc[1][tid]) + (sacc[2][tid] + sacc[3][tid]);
+  __syncthreads();
+  // solve D^T x = acc within the block (D lower): x_j = acc_j / D[j][j]; acc_m -= D[j][m] x_j (m < j)
+  for (int j = kcnt - 1; j >= 0; --j) {
+    if (tid == 0) acc[j] = acc[j] / sD[j * SP + j];
+    __syncthreads();
+    if (tid < j) acc[tid] -= sD[j * SP + tid] * acc[j];
+    __syncthreads();
+  }
+  if (tid < kcnt) c[k0 + tid] = acc[tid];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) flags[k] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, int* d_info) {
+  GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(chol_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)SYRK_SMEM));
+  GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)PANEL_SMEM));
+  cudaStream_t st = ctx->stream;
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    const int jb = std::min(NB, n - j0);
+    const int below = nrows - (j0 + jb);
+    const int pblocks = std::max(1, ceil_div(below, NB));
+    chol_panel_kernel<<<pblocks, 256, PANEL_SMEM, st>>>(nrows, j0, jb, d_A, ld, d_info);
+    GINGR_LAUNCHED(ctx);
+    if (below > 0 && j0 + jb < n) {
+      const int r0 = j0 + jb;
+      const int nti = ceil_div(nrows - r0, NB), ntk = ceil_div(n - r0, NB);
+      chol_syrk_kernel<<<dim3(ntk, nti), 128, SYRK_SMEM, st>>>(nrows, n, j0, jb, r0, d_A, ld);
+      GINGR_LAUNCHED(ctx);
+    }
+  }
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+int32_t chol_backsolve_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld, const double* d_z, double* d_c,
+                               int* d_flags) {
+  const int nb = ceil_div(n, NB);
+  if (nb > ctx->num_sms) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "rank too large for the sync-free back solve");
+  GINGR_CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, sizeof(int) * nb, ctx->stream));
+  chol_backsolve_kernel<<<nb, 256, 0, ctx->stream>>>(n, d_L, ld, d_z, d_c, d_flags);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+}  // namespace gingr

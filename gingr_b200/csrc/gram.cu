@@ -1,0 +1,290 @@
+// gram.cu -- K3a: weighted Gram matrix of the GPMM basis on the FP64 tensor pipe (sm_100a).
+//
+// Replaces the dense products of scalismo's regression at the call site GingrAlgorithm.scala:300
+// (`model.transform(rigid).posterior(obs)`):  Mx = Q^T L^-1 Q + I_r  with
+// Q = Phi' diag(sqrt(lambda)), L^-1 = blockdiag(inv(cov_i)).  For the isotropic noise GiNGR's CPD/ICP
+// configs hand over (CPD.scala:120-128, ICP.scala:90-92) cov_i = v_i I3 and the rotation of the posed model
+// cancels ((I (x) R)^T (W (x) I3) (I (x) R) = W (x) I3), so
+//     Mx = I + D G D,   G = Phi^T diag(w_row) Phi,   w_row[3i+d] = 1 / v_i,   D = diag(sqrt(lambda)).
+// G is a real dense FP64 contraction (3n x r by r) and runs on DMMA: tcgen05 has no FP64 kind, the sm_100a
+// FP64 tensor instruction is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; the m16n8k{4,8,16} PTX shapes lower to it).
+//
+// Kernel: only the lower-triangular 128x128 tiles are computed (symmetric minimum 3n r (r+1) flop).
+// The (tile, k-chunk) work space is linearised tile-major and cut into equal contiguous pieces, one per
+// CTA (stream-K, one persistent CTA per SM), so 148 SMs stay busy for any r.  Each piece accumulates in
+// registers (warp tile 64x32 = 32 DMMA accumulator fragments), operands stream global -> shared with a
+// 4-stage cp.async pipeline ([k][col] tiles, pitch 132 doubles: conflict-free LDS.64 fragment loads), the
+// row weights are multiplied into the B fragments.  Partial tiles go to a workspace and are summed in fixed
+// order by gram_finish_kernel (deterministic; no atomics), which also applies D, adds I and the landmark
+// blocks (full 3x3 covariances, GeneralRegistrationState.scala:43-62).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "posterior.cuh"
+
+namespace gingr {
+
+constexpr int BT = 128;          // output tile edge
+constexpr int BK = 16;           // rows of Phi per pipeline stage
+constexpr int STAGES = 4;
+constexpr int PITCH = BT + 4;    // smem row pitch in doubles (== 4 mod 16 -> conflict-free fragment loads)
+constexpr int GRAM_THREADS = 256;
+constexpr size_t GRAM_SMEM = (size_t)STAGES * (2 * BK * PITCH + BK) * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// segment of work of one CTA: tile (ta >= tb), chunk range [c0, c1), output slot
+struct GramSegment {
+  int ta, tb, c0, c1, slot, pad0, pad1, pad2;
+};
+
+// phi: [rows][rp] row-major, wrow: [rows] (may be null = unit weights)
+__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_streamk_kernel(int rows, int rp,
+                                                                       const double* __restrict__ phi,
+                                                                       const double* __restrict__ wrow,
+                                                                       const GramSegment* __restrict__ segs,
+                                                                       const int* __restrict__ seg_begin,
+                                                                       double* __restrict__ partial) {
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;                                   // [STAGES][BK][PITCH]
+  double* sB = sA + (size_t)STAGES * BK * PITCH;       // [STAGES][BK][PITCH]
+  double* sW = sB + (size_t)STAGES * BK * PITCH;       // [STAGES][BK]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;             // 2 x 4 warps, warp tile 64 x 32
+  const int g = lane >> 2, t = lane & 3;
+
+  for (int si = seg_begin[blockIdx.x]; si < seg_begin[blockIdx.x + 1]; ++si) {
+    const GramSegment sg = segs[si];
+    const int a0 = sg.ta * BT, b0 = sg.tb * BT;
+    const bool diag = sg.ta == sg.tb;
+    const int nchunks = sg.c1 - sg.c0;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto issue = [&](int chunk) {
+      const int stage = chunk % STAGES;
+      const int krow0 = (sg.c0 + chunk) * BK;
+      double* dA = sA + (size_t)stage * BK * PITCH;
+      double* dB = sB + (size_t)stage * BK * PITCH;
+      // 16 rows x 64 16-byte pieces per operand tile = 1024 pieces, 4 per thread
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = tid + q * GRAM_THREADS;
+        const int kr = e >> 6, c2 = (e & 63) * 2;
+        const int krow = krow0 + kr;
+        const bool rok = krow < rows;
+        {
+          const int col = a0 + c2;
+          const bool ok = rok && col < rp;
+          cp_async16(dA + kr * PITCH + c2, ok ? (const void*)(phi + (size_t)krow * rp + col) : (const void*)phi,
+                     ok ? 16 : 0);
+        }
+        if (!diag) {
+          const int col = b0 + c2;
+          const bool ok = rok && col < rp;
+          cp_async16(dB + kr * PITCH + c2, ok ? (const void*)(phi + (size_t)krow * rp + col) : (const void*)phi,
+                     ok ? 16 : 0);
+        }
+      }
+      if (tid < BK) {
+        const int krow = krow0 + tid;
+        const bool ok = krow < rows && wrow != nullptr;
+        cp_async8(sW + stage * BK + tid, ok ? (const void*)(wrow + krow) : (const void*)phi, ok ? 8 : 0);
+      }
+    };
+
+    __syncthreads();  // previous segment's readers are done with the stages
+#pragma unroll
+    for (int p = 0; p < STAGES - 1; ++p) {
+      if (p < nchunks) issue(p);
+      cp_async_commit();
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      if (ch + STAGES - 1 < nchunks) issue(ch + STAGES - 1);
+      cp_async_commit();
+      const int stage = ch % STAGES;
+      const double* tA = sA + (size_t)stage * BK * PITCH + wm * 64 + g;
+      const double* tB = (diag ? sA : sB) + (size_t)stage * BK * PITCH + wn * 32 + g;
+      const double* tW = sW + stage * BK;
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 4; ++k4) {
+        const int kk = k4 * 4 + t;
+        const double wk = wrow ? tW[kk] : 1.0;
+        double af[8], bf[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) af[i] = tA[kk * PITCH + i * 8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = tB[kk * PITCH + j * 8] * wk;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    }
+    cp_async_wait<0>();
+    // store the partial tile: slot-major [slot][128][128]
+    double* out = partial + (size_t)sg.slot * BT * BT;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int row = wm * 64 + i * 8 + g, col = wn * 32 + j * 8 + 2 * t;
+        *reinterpret_cast<double2*>(out + (size_t)row * BT + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+      }
+  }
+}
+
+// Sum the partial tiles in slot order and emit  out = add_identity * I + D (G + LM) D  (both triangles).
+// tile_first[t] .. tile_first[t+1] are the slots of lower-triangular tile t (t = ta (ta+1)/2 + tb).
+// Landmark term: LM[a][b] = sum_l sum_{d,e} phi_l[d][a] A_l[d][e] phi_l[e][b]  with lm_rows [L][3][rp], lm_A [L][9].
+__global__ void __launch_bounds__(256) gram_finish_kernel(int r, int rp, int ld_out, const double* __restrict__ partial,
+                                                          const int* __restrict__ tile_first,
+                                                          const double* __restrict__ sqrt_lambda,
+                                                          double add_identity, int L,
+                                                          const double* __restrict__ lm_rows,
+                                                          const double* __restrict__ lm_A, double* __restrict__ out) {
+  const int ta = blockIdx.y, tb = blockIdx.x;
+  if (tb > ta) return;
+  const int tile = ta * (ta + 1) / 2 + tb;
+  const int s0 = tile_first[tile], s1 = tile_first[tile + 1];
+  for (int e = threadIdx.x; e < BT * BT; e += 256) {
+    const int row = e / BT, col = e % BT;
+    const int a = ta * BT + row, b = tb * BT + col;
+    if (a >= r || b >= r || b > a) continue;
+    double s = 0.0;
+    for (int k = s0; k < s1; ++k) s += partial[(size_t)k * BT * BT + e];
+    for (int l = 0; l < L; ++l) {
+      const double* pr = lm_rows + (size_t)l * 3 * rp;
+      const double* A = lm_A + l * 9;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double pa = pr[d * rp + a];
+        s += pa * (A[d * 3] * pr[b] + A[d * 3 + 1] * pr[rp + b] + A[d * 3 + 2] * pr[2 * rp + b]);
+      }
+    }
+    const double da = sqrt_lambda ? sqrt_lambda[a] : 1.0, db = sqrt_lambda ? sqrt_lambda[b] : 1.0;
+    const double v = da * s * db;
+    out[(size_t)a * ld_out + b] = v + (a == b ? add_identity : 0.0);
+    if (a != b) out[(size_t)b * ld_out + a] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: static stream-K schedule
+// ---------------------------------------------------------------------------------------------
+int32_t GramPlan::build(gingr_ctx* ctx, int rows_, int r_, int rp_) {
+  rows = rows_;
+  r = r_;
+  rp = rp_;
+  nt = ceil_div(r, BT);
+  ntiles = nt * (nt + 1) / 2;
+  nchunks = std::max(1, ceil_div(rows, BK));
+  ncta = ctx->num_sms;
+  const int64_t total = (int64_t)ntiles * nchunks;
+  if (total < ncta) ncta = (int)total;
+  std::vector<GramSegment> segs;
+  std::vector<int> seg_begin(ncta + 1, 0), tile_first(ntiles + 1, 0);
+  std::vector<std::pair<int, int>> tile_ab(ntiles);
+  for (int a = 0, k = 0; a < nt; ++a)
+    for (int b = 0; b <= a; ++b) tile_ab[k++] = {a, b};
+  for (int c = 0; c < ncta; ++c) {
+    const int64_t u0 = total * c / ncta, u1 = total * (c + 1) / ncta;
+    seg_begin[c] = (int)segs.size();
+    int64_t u = u0;
+    while (u < u1) {
+      const int tile = (int)(u / nchunks);
+      const int c0 = (int)(u % nchunks);
+      const int c1 = (int)std::min<int64_t>(nchunks, c0 + (u1 - u));
+      GramSegment s;
+      s.ta = tile_ab[tile].first;
+      s.tb = tile_ab[tile].second;
+      s.c0 = c0;
+      s.c1 = c1;
+      s.slot = (int)segs.size();
+      s.pad0 = s.pad1 = s.pad2 = 0;
+      segs.push_back(s);
+      u += c1 - c0;
+    }
+  }
+  seg_begin[ncta] = (int)segs.size();
+  // segments are in linearised order, so the slots of a tile are consecutive
+  for (size_t i = 0; i < segs.size(); ++i) {
+    const int tile = segs[i].ta * (segs[i].ta + 1) / 2 + segs[i].tb;
+    tile_first[tile + 1] = (int)i + 1;
+  }
+  for (int tix = 1; tix <= ntiles; ++tix) tile_first[tix] = std::max(tile_first[tix], tile_first[tix - 1]);
+  nsegs = (int)segs.size();
+  GINGR_CUDA_TRY(ctx, d_segs.alloc(segs.size() * sizeof(GramSegment) / sizeof(int)));
+  GINGR_CUDA_TRY(ctx, d_seg_begin.alloc(seg_begin.size()));
+  GINGR_CUDA_TRY(ctx, d_tile_first.alloc(tile_first.size()));
+  GINGR_CUDA_TRY(ctx, d_partial.alloc((size_t)nsegs * BT * BT));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(GramSegment), cudaMemcpyHostToDevice,
+                                      ctx->stream));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_seg_begin.p, seg_begin.data(), seg_begin.size() * sizeof(int),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_tile_first.p, tile_first.data(), tile_first.size() * sizeof(int),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+  GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(gram_streamk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)GRAM_SMEM));
+  return GINGR_OK;
+}
+
+void GramPlan::release() {
+  d_segs.release();
+  d_seg_begin.release();
+  d_tile_first.release();
+  d_partial.release();
+}
+
+// partial tiles of G = Phi^T diag(wrow) Phi  (wrow may be null)
+int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_phi, const double* d_wrow) {
+  if (plan.rows > 0) {
+    gram_streamk_kernel<<<plan.ncta, GRAM_THREADS, GRAM_SMEM, ctx->stream>>>(
+        plan.rows, plan.rp, d_phi, d_wrow, reinterpret_cast<const GramSegment*>(plan.d_segs.p), plan.d_seg_begin.p,
+        plan.d_partial.p);
+    GINGR_LAUNCHED(ctx);
+    GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  } else {
+    GINGR_CUDA_TRY(ctx, cudaMemsetAsync(plan.d_partial.p, 0, plan.d_partial.n * sizeof(double), ctx->stream));
+  }
+  return GINGR_OK;
+}
+
+// out[r x r] (pitch ld_out) = add_identity I + D (sum of partial tiles + landmark blocks) D
+int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_partial, const double* d_sqrt_lambda,
+                            double add_identity, int L, const double* d_lm_rows, const double* d_lm_A, int ld_out,
+                            double* d_out) {
+  gram_finish_kernel<<<dim3(plan.nt, plan.nt), 256, 0, ctx->stream>>>(plan.r, plan.rp, ld_out, d_partial,
+                                                                      plan.d_tile_first.p, d_sqrt_lambda, add_identity,
+                                                                      L, d_lm_rows, d_lm_A, d_out);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+}  // namespace gingr

@@ -3,4 +3,50 @@
 #include "common.cuh"
 
 namespace gingr {
+
+// ---- gram.cu -------------------------------------------------------------------------------------
+struct GramPlan {
+  int rows = 0, r = 0, rp = 0;
+  int nt = 0, ntiles = 0, nchunks = 0, ncta = 0, nsegs = 0;
+  DevBuf<int> d_segs;        // GramSegment[nsegs]
+  DevBuf<int> d_seg_begin;   // [ncta + 1]
+  DevBuf<int> d_tile_first;  // [ntiles + 1]
+  DevBuf<double> d_partial;  // [nsegs][128][128]
+  int32_t build(gingr_ctx* ctx, int rows, int r, int rp);
+  void release();
+};
+int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_phi, const double* d_wrow);
+int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_partial, const double* d_sqrt_lambda,
+                            double add_identity, int L, const double* d_lm_rows, const double* d_lm_A, int ld_out,
+                            double* d_out);
+
+// ---- chol.cu -------------------------------------------------------------------------------------
+// In-place blocked Cholesky A = L L^T of the leading n x n block (lower triangle, row-major, pitch ld) of a
+// matrix with nrows >= n rows.  The extra rows i >= n are carried through the panel solves, so on return
+// row n + q holds  L^-1 b_q  for the right-hand side b_q that was stored there (forward substitution for free).
+// d_info[0] is set to 1 if a non-positive / non-finite pivot appears (matrix not SPD).
+int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, int* d_info);
+// c = L^-T z  (sync-free multi-CTA backward substitution).  d_flags: >= ceil(n/64) ints of scratch.
+int32_t chol_backsolve_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld, const double* d_z, double* d_c,
+                               int* d_flags);
+
+// ---- vecops.cu -----------------------------------------------------------------------------------
+// out_q[k] = sum_a phi[k][a] v_q[a],  q < nvec (1 or 2), k < rows
+int32_t gemv_rows_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_phi, int nvec, const double* d_v0,
+                          const double* d_v1, double* d_out0, double* d_out1);
+// out[a] = scale[a] * sum_k phi[k][a] u[k]   (scale may be null).  d_part: >= gemvT_splits(ctx, rows) * rp doubles
+int gemvT_splits(const gingr_ctx* ctx, int rows);
+int32_t gemvT_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_phi, const double* d_u,
+                      const double* d_scale, double* d_part, double* d_out);
+// y[a] = sum_b A[a][b] x[b]  for a dense r x r row-major matrix (pitch ld)
+int32_t dense_matvec_enqueue(gingr_ctx* ctx, int r, const double* d_A, int ld, const double* d_x, double* d_y);
+// B[c][r] = A[r][c]  (n x n, pitches lda / ldb)
+int32_t transpose_enqueue(gingr_ctx* ctx, int n, const double* d_A, int lda, double* d_B, int ldb);
+
+// dst[k * ld_dst + j] = tmp[j * rows + k]  (column slab [nc][rows] -> row-major rows of Phi)
+int32_t slab_transpose_enqueue(gingr_ctx* ctx, int rows, int nc, const double* d_tmp, double* d_dst, int ld_dst);
+// B = [eps I + S ; I]  ((2r) x r, pitch rp)
+int32_t build_regression_system_enqueue(gingr_ctx* ctx, int r, int rp, const double* d_S, double eps, double* d_B);
+int32_t add_vectors_enqueue(gingr_ctx* ctx, int n, const double* d_a, const double* d_b, double* d_out);
+
 }  // namespace gingr

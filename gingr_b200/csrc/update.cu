@@ -1,0 +1,1283 @@
+// update.cu -- the full GiNGR iteration on the device: GingrAlgorithm.update (api/GingrAlgorithm.scala:192-254)
+// with computePosterior (:281-302), the CPD / ICP plugin functions (registration/config/CPD.scala:32-49,
+// :120-147; ICP.scala:37-51, :90-99), the rigid / similarity extraction (:260-279) and the fit refresh of
+// GingrGeneratorWrapper.propose (sampling/generators/GingrGeneratorWrapper.scala:28-39).
+//
+// One call enqueues a fixed sequence of kernels on the ctx stream; every scalar the kernels need (pose,
+// sigma2, status flags) lives in a small device-resident state block, so iterations can be chained without
+// host round trips (gingr_update_chain).  Data flow of one iteration:
+//
+//   pose_kernel            R = Rz(phi) Ry(theta) Rx(psi) from the Euler angles of the state
+//   [CPD] E-step (estep.cu) on this rank's target shard  -> P1, PX, Pt1 ; all-reduce over ranks
+//   [ICP] closest point (closest.cu)                     -> cp, 0/1 weights
+//   obs_kernel             correspondence point, observation weight 1/var, residual u = w R^T (y - m'),
+//                          per-row weights; sums for the sigma2 update (pre-update fit, CPD.scala:133-147)
+//   gemvT                  rhs = D Phi^T u                         (Q^T L^-1 (y - m))
+//   gram (DMMA) + finish   Mx = I + D Phi^T W Phi D (+ landmark blocks) ; all-reduce over ranks
+//   cholesky (+ rhs row)   z = L^-1 rhs ; backsolve c = L^-T z     (posterior mean coefficients)
+//   shrink                 alpha* = W0 (S c)   == transformedModelInit.coefficients(posterior.mean) (:214-216)
+//   combine                alpha_c = alpha + (alpha* - alpha) stepLength                          (:218-220)
+//   gemv_rows x2           instance(alpha) and instance(alpha_c) at the mesh points               (:222-224)
+//   procrustes             Umeyama about the origin, Euler round trips                             (:227-231)
+//   gemvT + W0             alpha_new = transformedModel.coefficients(newshape)                    (:234-237)
+//   finalize               new state or ModelFlexibilityError, sigma2 hook                        (:239-251)
+//   gemv_rows + pose       fit = s (R instance(alpha_new) + t)            (ModelFittingParameters.scala:130-143)
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "closest.cuh"
+#include "common.cuh"
+#include "estep.cuh"
+#include "nccl_dl.cuh"
+#include "posterior.cuh"
+
+namespace gingr {
+
+// ---- device state block layout (doubles) ---------------------------------------------------------
+enum {
+  DS_SCALE = 0, DS_T = 1, DS_EULER = 4, DS_CENTER = 7, DS_SIGMA2 = 10, DS_STEP = 11, DS_R = 12,
+  DS_NEW_SCALE = 24, DS_NEW_T = 25, DS_NEW_EULER = 28, DS_R1 = 31, DS_R2 = 40,
+  DS_NEW_SIGMA2 = 50, DS_NP = 51, DS_XPX = 52, DS_YPY = 53, DS_TRPXY = 54,
+  DS_MUX = 56, DS_MUY = 59, DS_S2X = 62, DS_SXY = 63, DS_COUNT = 80
+};
+enum { IS_GT = 0, IS_ITER = 1, IS_STATUS = 2, IS_INFO = 3, IS_FAIL_POST = 4, IS_FAIL_COEF = 5, IS_COUNT = 16 };
+
+__device__ __forceinline__ void euler_to_matrix_dev(double phi, double theta, double psi, double* R) {
+  const double cph = cos(phi), sph = sin(phi), cth = cos(theta), sth = sin(theta), cps = cos(psi), sps = sin(psi);
+  R[0] = cth * cph; R[1] = sps * sth * cph - cps * sph; R[2] = sps * sph + cps * sth * cph;
+  R[3] = cth * sph; R[4] = cps * cph + sps * sth * sph; R[5] = cps * sth * sph - sps * cph;
+  R[6] = -sth;      R[7] = sps * cth;                   R[8] = cps * cth;
+}
+
+// RotationSpace3D.rotMatrixToEulerAngles (Slabaugh), SURVEY.md A4
+__device__ __forceinline__ void matrix_to_euler_dev(const double* R, double* e) {
+  if (fabs(fabs(R[6]) - 1.0) > 0.0001) {
+    const double theta = asin(-R[6]);
+    const double ct = cos(theta);
+    e[0] = atan2(R[3] / ct, R[0] / ct);
+    e[1] = theta;
+    e[2] = atan2(R[7] / ct, R[8] / ct);
+  } else if (fabs(R[6] + 1.0) < 0.0001) {
+    e[0] = 0.0; e[1] = 3.14159265358979323846 / 2.0; e[2] = atan2(R[1], R[2]);
+  } else {
+    e[0] = 0.0; e[1] = -3.14159265358979323846 / 2.0; e[2] = atan2(-R[1], -R[2]);
+  }
+}
+
+__global__ void pose_kernel(double* ds, int* is) {
+  euler_to_matrix_dev(ds[DS_EULER], ds[DS_EULER + 1], ds[DS_EULER + 2], ds + DS_R);
+  is[IS_INFO] = 0;
+  is[IS_FAIL_POST] = 0;
+  is[IS_FAIL_COEF] = 0;
+}
+
+// fit_i = s (R (ref_i + mean_i + a_i) + t)  for the local point range [m0, m0 + Ml); a: [3 Ml] local.
+// pose offsets select which (scale, t, R) of the state block to use.
+__global__ void fit_from_instance_kernel(int m0, int Ml, const double* __restrict__ ref, const double* __restrict__ mean,
+                                         const double* __restrict__ a, const double* __restrict__ ds, int off_s,
+                                         int off_t, int off_R, double* __restrict__ out /*[3 Ml] local*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ml) return;
+  const int gi = m0 + i;
+  const double* R = ds + off_R;
+  const double s = ds[off_s];
+  const double x = ref[3 * gi] + mean[3 * gi] + a[3 * i];
+  const double y = ref[3 * gi + 1] + mean[3 * gi + 1] + a[3 * i + 1];
+  const double z = ref[3 * gi + 2] + mean[3 * gi + 2] + a[3 * i + 2];
+  out[3 * i] = (R[0] * x + R[1] * y + R[2] * z + ds[off_t]) * s;
+  out[3 * i + 1] = (R[3] * x + R[4] * y + R[5] * z + ds[off_t + 1]) * s;
+  out[3 * i + 2] = (R[6] * x + R[7] * y + R[8] * z + ds[off_t + 2]) * s;
+}
+
+// v[a] = sqrt_lambda[a] * alpha[a]
+__global__ void scale_vec_kernel(int r, const double* __restrict__ sl, const double* __restrict__ alpha,
+                                 double* __restrict__ out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < r) out[a] = sl[a] * alpha[a];
+}
+
+// gather padded all-gather blocks [nranks][3 Mmax] into fit [3 M]
+__global__ void compact_gather_kernel(int M, int nranks, int Mmax, const double* __restrict__ gathered,
+                                      double* __restrict__ fit) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * M) return;
+  const int i = e / 3, d = e % 3;
+  const int base = M / nranks, rem = M % nranks;
+  // rank owning point i
+  int rk, start;
+  if (i < rem * (base + 1)) { rk = i / (base + 1); start = rk * (base + 1); }
+  else { rk = rem + (i - rem * (base + 1)) / max(base, 1); start = rem * (base + 1) + (rk - rem) * base; }
+  fit[e] = gathered[(size_t)rk * 3 * Mmax + 3 * (i - start) + d];
+}
+
+// ---- CPD scalars for the E-step from the state block --------------------------------------------
+__global__ void cpd_estep_scalars_kernel(const double* __restrict__ ds, double w, double ratio, double* scal) {
+  const double sigma2 = ds[DS_SIGMA2];
+  const double t = 2.0 * 3.14159265358979323846 * sigma2;
+  scal[0] = sigma2;
+  scal[1] = 1.0;
+  scal[2] = w / (1.0 - w) * (t * sqrt(t)) * ratio;  // CPD.scala:69-70
+}
+
+// xpx total (fixed order) appended behind the row block for the all-reduce
+__global__ void xpx_total_kernel(int nparts, const double* __restrict__ parts, double* __restrict__ out) {
+  double s = 0.0;
+  for (int k = 0; k < nparts; ++k) s += parts[k];
+  out[0] = s;
+}
+
+// ---- observations ---------------------------------------------------------------------------------
+// CPD (CPD.scala:32-49, :120-128): point PX_i / P1_i, variance sigma2 * lambda / P1_i.
+// ICP (ICP.scala:37-51, :90-92):  point cp_i (kept only if w_i == 1), variance sigma2.
+// Output for local points [m0, m0 + Ml): wrow[3 Ml], u[3 Ml] = w R^T (y - (R (ref + mean) + t)).
+// Sums for CPD's sigma2 update over ALL points (every rank computes the same): per-block partials of
+// P1, P1 |fit|^2, fit . PX.
+struct ObsArgs {
+  int algo, M, m0, Ml, use_lm, L;
+  double lambda;
+};
+
+__global__ void __launch_bounds__(256) obs_kernel(ObsArgs a, const double* __restrict__ rows /*[4][M] CPD*/,
+                                                  const double* __restrict__ cp /*[M][3] ICP*/,
+                                                  const uint8_t* __restrict__ w01, const double* __restrict__ fit,
+                                                  const double* __restrict__ ref, const double* __restrict__ mean,
+                                                  const int32_t* __restrict__ lm_pid, const double* __restrict__ ds,
+                                                  int* __restrict__ is, double* __restrict__ wrow,
+                                                  double* __restrict__ u, double* __restrict__ sums_part /*[blocks][3]*/) {
+  __shared__ double red[3][8];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double sP1 = 0.0, sY = 0.0, sT = 0.0;
+  if (i < a.M) {
+    const double sigma2 = ds[DS_SIGMA2];
+    double px, py, pz, wt;
+    if (a.algo == GINGR_ALGO_CPD) {
+      const double p1 = rows[i];
+      const double X = rows[(size_t)a.M + i], Y = rows[(size_t)2 * a.M + i], Z = rows[(size_t)3 * a.M + i];
+      const double inv = 1.0 / p1;
+      px = X * inv; py = Y * inv; pz = Z * inv;
+      const double var = sigma2 * a.lambda * inv;  // eye(3) * sigma2 * lambda * P1inv(id)  CPD.scala:125
+      wt = 1.0 / var;
+      if (!(var < INFINITY) || !(var > 0.0) || !(wt < INFINITY)) is[IS_FAIL_POST] = 1;  // breeze inv(cov) not finite
+      const double fx = fit[3 * i], fy = fit[3 * i + 1], fz = fit[3 * i + 2];
+      sP1 = p1;
+      sY = p1 * (fx * fx + fy * fy + fz * fz);
+      sT = fx * X + fy * Y + fz * Z;
+    } else {
+      px = cp[3 * i]; py = cp[3 * i + 1]; pz = cp[3 * i + 2];
+      wt = w01[i] ? 1.0 / sigma2 : 0.0;  // pairs with w != 1 are dropped (ICP.scala:50)
+      if (w01[i] && (!(wt < INFINITY) || !(wt > 0.0))) is[IS_FAIL_POST] = 1;
+    }
+    if (a.use_lm)
+      for (int l = 0; l < a.L; ++l)
+        if (lm_pid[l] == i) wt = 0.0;  // correspondences at landmark ids are replaced (GingrAlgorithm.scala:288-296)
+    const int li = i - a.m0;
+    if (li >= 0 && li < a.Ml) {
+      const double* R = ds + DS_R;
+      const double bx = ref[3 * i] + mean[3 * i], by = ref[3 * i + 1] + mean[3 * i + 1], bz = ref[3 * i + 2] + mean[3 * i + 2];
+      double rx = px - (R[0] * bx + R[1] * by + R[2] * bz + ds[DS_T]);
+      double ry = py - (R[3] * bx + R[4] * by + R[5] * bz + ds[DS_T + 1]);
+      double rz = pz - (R[6] * bx + R[7] * by + R[8] * bz + ds[DS_T + 2]);
+      if (wt == 0.0) { rx = ry = rz = 0.0; }  // dropped observation: contributes nothing (and no 0 * NaN)
+      wrow[3 * li] = wrow[3 * li + 1] = wrow[3 * li + 2] = wt;
+      u[3 * li] = wt * (R[0] * rx + R[3] * ry + R[6] * rz);
+      u[3 * li + 1] = wt * (R[1] * rx + R[4] * ry + R[7] * rz);
+      u[3 * li + 2] = wt * (R[2] * rx + R[5] * ry + R[8] * rz);
+    }
+  }
+  // block sums (fixed order)
+  double v[3] = {sP1, sY, sT};
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int k = 0; k < 8; ++k) s += red[threadIdx.x][k];
+    sums_part[blockIdx.x * 3 + threadIdx.x] = s;
+  }
+}
+
+// sigma2 hook: CPD (xPx - 2 trPXY + yPy) / (3 Np) (CPD.scala:133-147); ICP linear anneal (ICP.scala:96-99)
+__global__ void sigma2_kernel(int algo, int nblocks, const double* __restrict__ sums_part, const double* __restrict__ xpx,
+                              double sigma_step, double end_sigma, double* __restrict__ ds) {
+  if (algo == GINGR_ALGO_CPD) {
+    double np = 0.0, ypy = 0.0, tr = 0.0;
+    for (int k = 0; k < nblocks; ++k) {
+      np += sums_part[3 * k];
+      ypy += sums_part[3 * k + 1];
+      tr += sums_part[3 * k + 2];
+    }
+    ds[DS_NP] = np; ds[DS_XPX] = xpx[0]; ds[DS_YPY] = ypy; ds[DS_TRPXY] = tr;
+    ds[DS_NEW_SIGMA2] = (xpx[0] - 2.0 * tr + ypy) / (np * 3.0);
+  } else {
+    ds[DS_NEW_SIGMA2] = fmax(ds[DS_SIGMA2] - sigma_step, end_sigma);
+  }
+}
+
+// ---- landmarks ------------------------------------------------------------------------------------
+// A_l = R^T C_l^-1 R ; rhs += D Phi_l^T A_l R^T (y_l - (R (ref + mean)_pid + t))   for local landmarks
+__global__ void landmark_prepare_kernel(int L, const double* __restrict__ cinv, const double* __restrict__ ds,
+                                        double* __restrict__ A) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  const double* R = ds + DS_R;
+  const double* C = cinv + 9 * l;
+  double T[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) T[3 * i + j] = C[3 * i] * R[j] + C[3 * i + 1] * R[3 + j] + C[3 * i + 2] * R[6 + j];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A[9 * l + 3 * i + j] = R[i] * T[j] + R[3 + i] * T[3 + j] + R[6 + i] * T[6 + j];
+}
+
+__global__ void landmark_rhs_kernel(int r, int rp, int L, const int32_t* __restrict__ pid,
+                                    const double* __restrict__ pts, const double* __restrict__ A,
+                                    const double* __restrict__ lm_rows, const double* __restrict__ ref,
+                                    const double* __restrict__ mean, const double* __restrict__ sl,
+                                    const double* __restrict__ ds, double* __restrict__ rhs) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= r) return;
+  const double* R = ds + DS_R;
+  double s = 0.0;
+  for (int l = 0; l < L; ++l) {
+    const int p = pid[l];
+    const double bx = ref[3 * p] + mean[3 * p], by = ref[3 * p + 1] + mean[3 * p + 1], bz = ref[3 * p + 2] + mean[3 * p + 2];
+    const double rx = pts[3 * l] - (R[0] * bx + R[1] * by + R[2] * bz + ds[DS_T]);
+    const double ry = pts[3 * l + 1] - (R[3] * bx + R[4] * by + R[5] * bz + ds[DS_T + 1]);
+    const double rz = pts[3 * l + 2] - (R[6] * bx + R[7] * by + R[8] * bz + ds[DS_T + 2]);
+    const double qx = R[0] * rx + R[3] * ry + R[6] * rz, qy = R[1] * rx + R[4] * ry + R[7] * rz,
+                 qz = R[2] * rx + R[5] * ry + R[8] * rz;
+    const double* Al = A + 9 * l;
+    const double vx = Al[0] * qx + Al[1] * qy + Al[2] * qz, vy = Al[3] * qx + Al[4] * qy + Al[5] * qz,
+                 vz = Al[6] * qx + Al[7] * qy + Al[8] * qz;
+    const double* pr = lm_rows + (size_t)l * 3 * rp;
+    s += pr[a] * vx + pr[rp + a] * vy + pr[2 * rp + a] * vz;
+  }
+  rhs[a] += sl[a] * s;
+}
+
+// gather the 3 basis rows of each landmark vertex: lm_rows [L][3][rp]
+__global__ void gather_rows_kernel(int L, int rp, int m0, const int32_t* __restrict__ pid, const double* __restrict__ phi,
+                                   double* __restrict__ out) {
+  const int l = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * rp) return;
+  const int d = e / rp, a = e % rp;
+  out[(size_t)l * 3 * rp + e] = phi[((size_t)3 * (pid[l] - m0) + d) * rp + a];
+}
+
+// ---- small vector kernels -------------------------------------------------------------------------
+__global__ void check_finite_kernel(int n, const double* __restrict__ v, int* __restrict__ flag) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < n && !(fabs(v[a]) < INFINITY)) *flag = 1;
+}
+
+// alpha_c = alpha + (alpha* - alpha) * stepLength   (GingrAlgorithm.scala:218-220)
+__global__ void combine_kernel(int r, const double* __restrict__ alpha, const double* __restrict__ astar,
+                               const double* __restrict__ ds, double* __restrict__ out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < r) out[a] = alpha[a] + (astar[a] - alpha[a]) * ds[DS_STEP];
+}
+
+// X_i = ref + mean + a (currentFitNoTransform, :224), Y_i = R (ref + mean + b) + t (newshape, :222), local points.
+// pass 0: partial sums of X and Y ; pass 1: centred sums |X - mux|^2 and (Y - muy)(X - mux)^T.
+__global__ void __launch_bounds__(256) procrustes_sums_kernel(int pass, int m0, int Ml, const double* __restrict__ ref,
+                                                              const double* __restrict__ mean,
+                                                              const double* __restrict__ a, const double* __restrict__ b,
+                                                              const double* __restrict__ ds,
+                                                              double* __restrict__ newshape /*[3 Ml]*/,
+                                                              double* __restrict__ part /*[blocks][16]*/) {
+  __shared__ double red[10][8];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double v[10];
+#pragma unroll
+  for (int q = 0; q < 10; ++q) v[q] = 0.0;
+  if (i < Ml) {
+    const int gi = m0 + i;
+    const double* R = ds + DS_R;
+    const double cx = ref[3 * gi] + mean[3 * gi], cy = ref[3 * gi + 1] + mean[3 * gi + 1], cz = ref[3 * gi + 2] + mean[3 * gi + 2];
+    const double X0 = cx + a[3 * i], X1 = cy + a[3 * i + 1], X2 = cz + a[3 * i + 2];
+    const double bx = cx + b[3 * i], by = cy + b[3 * i + 1], bz = cz + b[3 * i + 2];
+    const double Y0 = R[0] * bx + R[1] * by + R[2] * bz + ds[DS_T];
+    const double Y1 = R[3] * bx + R[4] * by + R[5] * bz + ds[DS_T + 1];
+    const double Y2 = R[6] * bx + R[7] * by + R[8] * bz + ds[DS_T + 2];
+    if (pass == 0) {
+      newshape[3 * i] = Y0; newshape[3 * i + 1] = Y1; newshape[3 * i + 2] = Y2;
+      v[0] = X0; v[1] = X1; v[2] = X2; v[3] = Y0; v[4] = Y1; v[5] = Y2;
+    } else {
+      const double x0 = X0 - ds[DS_MUX], x1 = X1 - ds[DS_MUX + 1], x2 = X2 - ds[DS_MUX + 2];
+      const double y0 = Y0 - ds[DS_MUY], y1 = Y1 - ds[DS_MUY + 1], y2 = Y2 - ds[DS_MUY + 2];
+      v[0] = x0 * x0 + x1 * x1 + x2 * x2;
+      v[1] = y0 * x0; v[2] = y0 * x1; v[3] = y0 * x2;
+      v[4] = y1 * x0; v[5] = y1 * x1; v[6] = y1 * x2;
+      v[7] = y2 * x0; v[8] = y2 * x1; v[9] = y2 * x2;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 10; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    double s = 0.0;
+    for (int k = 0; k < 8; ++k) s += red[threadIdx.x][k];
+    part[blockIdx.x * 16 + threadIdx.x] = s;
+  }
+}
+
+__global__ void procrustes_reduce_kernel(int nblocks, int count, const double* __restrict__ part,
+                                         double* __restrict__ out /*[16]*/) {
+  const int q = threadIdx.x;
+  if (q >= count) return;
+  double s = 0.0;
+  for (int k = 0; k < nblocks; ++k) s += part[k * 16 + q];
+  out[q] = s;
+}
+
+__global__ void procrustes_means_kernel(int M, const double* __restrict__ sums, double* __restrict__ ds) {
+  for (int d = 0; d < 3; ++d) {
+    ds[DS_MUX + d] = sums[d] / M;
+    ds[DS_MUY + d] = sums[3 + d] / M;
+  }
+}
+
+// 3x3 SVD by one-sided Jacobi (Hestenes): A V = U diag(s), s sorted descending.
+__device__ void svd3(const double* Ain, double* U, double* S, double* V) {
+  double A[9], Vm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) A[i] = Ain[i];
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int k = 0; k < 3; ++k) {
+          alpha += A[3 * k + p] * A[3 * k + p];
+          beta += A[3 * k + q] * A[3 * k + q];
+          gamma += A[3 * k + p] * A[3 * k + q];
+        }
+        if (gamma == 0.0) continue;
+        off = fmax(off, fabs(gamma) / sqrt(alpha * beta));
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+        for (int k = 0; k < 3; ++k) {
+          const double ap = A[3 * k + p], aq = A[3 * k + q];
+          A[3 * k + p] = c * ap - s * aq;
+          A[3 * k + q] = s * ap + c * aq;
+          const double vp = Vm[3 * k + p], vq = Vm[3 * k + q];
+          Vm[3 * k + p] = c * vp - s * vq;
+          Vm[3 * k + q] = s * vp + c * vq;
+        }
+      }
+    if (off < 1e-17) break;
+  }
+  double sv[3];
+  for (int j = 0; j < 3; ++j) sv[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
+  int idx[3] = {0, 1, 2};
+  for (int i = 0; i < 2; ++i)
+    for (int j = i + 1; j < 3; ++j)
+      if (sv[idx[j]] > sv[idx[i]]) { const int tmp = idx[i]; idx[i] = idx[j]; idx[j] = tmp; }
+  for (int j = 0; j < 3; ++j) {
+    const int c = idx[j];
+    S[j] = sv[c];
+    for (int k = 0; k < 3; ++k) {
+      U[3 * k + j] = sv[c] > 0.0 ? A[3 * k + c] / sv[c] : 0.0;
+      V[3 * k + j] = Vm[3 * k + c];
+    }
+  }
+  // a zero singular value leaves a zero column in U: complete it to a right-handed orthonormal frame
+  if (S[2] <= 0.0) {
+    U[2] = U[3] * U[7] - U[6] * U[4];
+    U[5] = U[6] * U[1] - U[0] * U[7];
+    U[8] = U[0] * U[4] - U[3] * U[1];
+  }
+}
+
+__device__ double det3(const double* A) {
+  return A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+}
+
+// Umeyama about the origin (LandmarkRegistration.{rigid,similarity}3DLandmarkRegistration, SURVEY.md A4;
+// GingrAlgorithm.scala:227-231, :260-279) and the Euler round trips of the state update (:239-243,
+// GeneralRegistrationState.scala:83-87).  sums: [0] sum |x - mux|^2, [1..9] sum (y - muy)(x - mux)^T
+__global__ void procrustes_solve_kernel(int M, const double* __restrict__ sums, double* __restrict__ ds,
+                                        const int* __restrict__ is) {
+  const int gt = is[IS_GT];
+  double R1[9], t[3], c = 1.0;
+  if (gt == GINGR_NO_TRANSFORMS) {
+    for (int i = 0; i < 9; ++i) R1[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    t[0] = t[1] = t[2] = 0.0;
+  } else {
+    double Sxy[9], U[9], S[3], V[9], Rm[9];
+    const double s2x = sums[0] / M;
+    for (int i = 0; i < 9; ++i) Sxy[i] = sums[1 + i] / M;
+    svd3(Sxy, U, S, V);
+    const double sign = det3(Sxy) < 0.0 ? -1.0 : 1.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        Rm[3 * i + j] = U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1] + sign * U[3 * i + 2] * V[3 * j + 2];
+    if (gt == GINGR_SIMILARITY_TRANSFORMS) c = (S[0] + S[1] + sign * S[2]) / s2x;
+    for (int i = 0; i < 3; ++i)
+      t[i] = ds[DS_MUY + i] - c * (Rm[3 * i] * ds[DS_MUX] + Rm[3 * i + 1] * ds[DS_MUX + 1] + Rm[3 * i + 2] * ds[DS_MUX + 2]);
+    double e[3];
+    matrix_to_euler_dev(Rm, e);  // the registration result carries the rotation as Euler angles
+    euler_to_matrix_dev(e[0], e[1], e[2], R1);
+  }
+  double e2[3];
+  matrix_to_euler_dev(R1, e2);  // updateRotation(Rotation) -> Euler angles stored in the state
+  ds[DS_NEW_SCALE] = c;
+  for (int i = 0; i < 3; ++i) { ds[DS_NEW_T + i] = t[i]; ds[DS_NEW_EULER + i] = e2[i]; }
+  for (int i = 0; i < 9; ++i) ds[DS_R1 + i] = R1[i];
+  euler_to_matrix_dev(e2[0], e2[1], e2[2], ds + DS_R2);
+}
+
+// u_i = R1^T (newshape_i - (R1 (ref + mean)_i + t_new))  for the second `coefficients` call (:234-237)
+__global__ void coeff_residual_kernel(int m0, int Ml, const double* __restrict__ newshape, const double* __restrict__ ref,
+                                      const double* __restrict__ mean, const double* __restrict__ ds,
+                                      double* __restrict__ u) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ml) return;
+  const int gi = m0 + i;
+  const double* R = ds + DS_R1;
+  const double bx = ref[3 * gi] + mean[3 * gi], by = ref[3 * gi + 1] + mean[3 * gi + 1], bz = ref[3 * gi + 2] + mean[3 * gi + 2];
+  const double rx = newshape[3 * i] - (R[0] * bx + R[1] * by + R[2] * bz + ds[DS_NEW_T]);
+  const double ry = newshape[3 * i + 1] - (R[3] * bx + R[4] * by + R[5] * bz + ds[DS_NEW_T + 1]);
+  const double rz = newshape[3 * i + 2] - (R[6] * bx + R[7] * by + R[8] * bz + ds[DS_NEW_T + 2]);
+  u[3 * i] = R[0] * rx + R[3] * ry + R[6] * rz;
+  u[3 * i + 1] = R[1] * rx + R[4] * ry + R[7] * rz;
+  u[3 * i + 2] = R[2] * rx + R[5] * ry + R[8] * rz;
+}
+
+// Commit the iteration (GingrAlgorithm.scala:193-208, :239-251): on success pose/scale/alpha/sigma2 are
+// replaced; a failed posterior leaves the state unchanged (status ModelFlexibilityError if iteration > 0), a
+// failed `coefficients` sets ModelFlexibilityError.  DS_R2 is left holding the rotation of the committed state.
+__global__ void finalize_kernel(int r, const double* __restrict__ alpha_new, double* __restrict__ alpha,
+                                double* __restrict__ ds, int* __restrict__ is) {
+  __shared__ int mode;  // 0 commit, 1 keep
+  if (threadIdx.x == 0) {
+    const bool fail_post = is[IS_INFO] != 0 || is[IS_FAIL_POST] != 0;
+    const bool fail_coef = is[IS_FAIL_COEF] != 0;
+    if (fail_post) {
+      if (is[IS_ITER] > 0) is[IS_STATUS] = GINGR_STATUS_MODEL_FLEXIBILITY_ERROR;
+      mode = 1;
+    } else if (fail_coef) {
+      is[IS_STATUS] = GINGR_STATUS_MODEL_FLEXIBILITY_ERROR;
+      mode = 1;
+    } else {
+      mode = 0;
+      ds[DS_SCALE] = ds[DS_NEW_SCALE];
+      for (int i = 0; i < 3; ++i) { ds[DS_T + i] = ds[DS_NEW_T + i]; ds[DS_EULER + i] = ds[DS_NEW_EULER + i]; }
+      ds[DS_SIGMA2] = ds[DS_NEW_SIGMA2];
+    }
+    if (mode == 1) euler_to_matrix_dev(ds[DS_EULER], ds[DS_EULER + 1], ds[DS_EULER + 2], ds + DS_R2);
+  }
+  __syncthreads();
+  if (mode == 0)
+    for (int a = threadIdx.x; a < r; a += blockDim.x) alpha[a] = alpha_new[a];
+}
+
+__global__ void bump_iteration_kernel(int* is) { is[IS_ITER] += 1; }
+
+__global__ void set_iteration_kernel(int* is, int iteration, int status) {
+  is[IS_ITER] = iteration;
+  is[IS_STATUS] = status;
+}
+
+}  // namespace gingr
+
+// =================================================================================================
+// handles
+// =================================================================================================
+using namespace gingr;
+
+struct gingr_registration {
+  gingr_ctx* ctx = nullptr;
+  const gingr_model* model = nullptr;
+  const gingr_target* target = nullptr;
+  gingr_config cfg;
+  // landmarks (all, replicated) and the subset whose vertex lives in this rank's shard
+  int L = 0, Ll = 0;
+  DevBuf<int32_t> lm_pid;      // [L] all landmark vertex ids (for the correspondence filter)
+  DevBuf<int32_t> lml_pid;     // [Ll] local
+  DevBuf<double> lml_pts, lml_cinv, lml_A, lml_rows;
+  // workspaces
+  EstepWorkspace estep;
+  ClosestWorkspace closest;
+  GramPlan gram;
+  DevBuf<double> rows_ext;     // [4 M + 8]  E-step rows + xPx (all-reduced together)
+  DevBuf<double> Mx;           // [(r + 8)][rp]  posterior matrix + rhs row
+  DevBuf<double> wrow, u, inst_a, inst_b, newshape, fit_local, gathered, fit;
+  DevBuf<double> vec;          // 8 * rp scratch vectors
+  DevBuf<double> gt_part, sums_part, pro_part, pro_sums;
+  DevBuf<double> ds;
+  DevBuf<int> is, flags;
+  DevBuf<double> alpha;
+  bool state_valid = false;
+  gingr_state last_out;
+  std::vector<double> last_alpha;
+};
+
+static int32_t model_build_constants(gingr_ctx* ctx, gingr_model* m);
+
+extern "C" {
+
+int32_t gingr_model_upload(gingr_ctx* ctx, int32_t M, int32_t r, const double* ref_pts, const double* mean,
+                           const double* basis, int64_t ld_basis, const double* variance, const int32_t* tri,
+                           int32_t T, gingr_model** out) {
+  if (!ctx || !out || !ref_pts || !mean || !basis || !variance || M <= 0 || r <= 0 || ld_basis < 3 * (int64_t)M ||
+      T < 0 || (T > 0 && !tri))
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_model_upload: bad argument");
+  for (int k = 0; k < r; ++k)
+    if (!(variance[k] >= 0.0)) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_model_upload: negative or NaN variance");
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  gingr_model* m = new gingr_model();
+  m->ctx = ctx;
+  m->M = M;
+  m->r = r;
+  m->rp = (r + 7) / 8 * 8;
+  shard_range(M, ctx->nranks, ctx->rank, &m->m0, &m->Ml);
+  cudaStream_t st = ctx->stream;
+  GINGR_CUDA_TRY(ctx, m->ref.alloc((size_t)3 * M));
+  GINGR_CUDA_TRY(ctx, m->mean.alloc((size_t)3 * M));
+  GINGR_CUDA_TRY(ctx, m->sqrt_lambda.alloc((size_t)m->rp));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->ref.p, ref_pts, sizeof(double) * 3 * (size_t)M, cudaMemcpyHostToDevice, st));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->mean.p, mean, sizeof(double) * 3 * (size_t)M, cudaMemcpyHostToDevice, st));
+  std::vector<double> sl((size_t)m->rp, 0.0);
+  for (int k = 0; k < r; ++k) sl[k] = sqrt(variance[k]);
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->sqrt_lambda.p, sl.data(), sizeof(double) * m->rp, cudaMemcpyHostToDevice, st));
+  // basis: column-major host -> row-major [3 Ml][rp] device, in column slabs through a transpose kernel
+  const size_t rows = (size_t)3 * m->Ml;
+  GINGR_CUDA_TRY(ctx, m->phi.alloc(std::max<size_t>(rows, 1) * m->rp));
+  GINGR_CUDA_TRY(ctx, cudaMemsetAsync(m->phi.p, 0, sizeof(double) * std::max<size_t>(rows, 1) * m->rp, st));
+  if (rows > 0) {
+    const int slab = 128;
+    DevBuf<double> tmp;
+    GINGR_CUDA_TRY(ctx, tmp.alloc((size_t)slab * rows));
+    for (int a0 = 0; a0 < r; a0 += slab) {
+      const int nc = std::min(slab, r - a0);
+      GINGR_CUDA_TRY(ctx, cudaMemcpy2DAsync(tmp.p, rows * sizeof(double), basis + (size_t)a0 * ld_basis + (size_t)3 * m->m0,
+                                            (size_t)ld_basis * sizeof(double), rows * sizeof(double), nc,
+                                            cudaMemcpyHostToDevice, st));
+      GINGR_TRY(slab_transpose_enqueue(ctx, (int)rows, nc, tmp.p, m->phi.p + a0, m->rp));
+    }
+    GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    tmp.release();
+  }
+  m->T = T;
+  if (T > 0) {
+    for (int k = 0; k < 3 * T; ++k)
+      if (tri[k] < 0 || tri[k] >= M) {
+        delete m;
+        return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_model_upload: triangle index out of range");
+      }
+    std::vector<int32_t> off, adj;
+    build_vertex_adjacency(M, T, tri, &off, &adj);
+    GINGR_CUDA_TRY(ctx, m->tri.alloc((size_t)3 * T));
+    GINGR_CUDA_TRY(ctx, m->adj_off.alloc(off.size()));
+    GINGR_CUDA_TRY(ctx, m->adj.alloc(adj.size()));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->tri.p, tri, sizeof(int32_t) * 3 * (size_t)T, cudaMemcpyHostToDevice, st));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->adj_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->adj.p, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice, st));
+    GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  }
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  int32_t rc = model_build_constants(ctx, m);
+  if (rc != GINGR_OK) {
+    gingr_model_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return GINGR_OK;
+}
+
+int32_t gingr_model_destroy(gingr_model* m) {
+  if (!m) return GINGR_OK;
+  cudaSetDevice(m->ctx->device);
+  m->ref.release();
+  m->mean.release();
+  m->phi.release();
+  m->sqrt_lambda.release();
+  m->tri.release();
+  m->adj_off.release();
+  m->adj.release();
+  m->S.release();
+  m->W0.release();
+  delete m;
+  return GINGR_OK;
+}
+
+}  // extern "C"
+
+// S = D Phi^T Phi D and W0 = (1e-5 I + S)^-1: the constants of scalismo's `coefficients` regression (all M
+// points, noise 1e-5 I3).  Phi'^T Phi' = Phi^T Phi for any rigid pose, so they are per model.
+static int32_t model_build_constants(gingr_ctx* ctx, gingr_model* m) {
+  const int r = m->r, rp = m->rp;
+  GramPlan plan;
+  GINGR_TRY(plan.build(ctx, 3 * m->Ml, r, rp));
+  GINGR_CUDA_TRY(ctx, m->S.alloc((size_t)rp * rp));
+  GINGR_CUDA_TRY(ctx, m->W0.alloc((size_t)rp * rp));
+  GINGR_CUDA_TRY(ctx, cudaMemsetAsync(m->S.p, 0, sizeof(double) * rp * rp, ctx->stream));
+  GINGR_TRY(gram_partials_enqueue(ctx, plan, m->phi.p, nullptr));
+  GINGR_TRY(gram_finish_enqueue(ctx, plan, plan.d_partial.p, m->sqrt_lambda.p, 0.0, 0, nullptr, nullptr, rp, m->S.p));
+  GINGR_TRY(comm_allreduce_sum(ctx, m->S.p, (size_t)rp * rp));
+  // B = [1e-5 I + S ; I]  (2r x r), factorise; rows r..2r-1 then hold L^-T... i.e. Rm with Rm L^T = I
+  DevBuf<double> B, Rt;
+  DevBuf<int> info;
+  GINGR_CUDA_TRY(ctx, B.alloc((size_t)2 * r * rp));
+  GINGR_CUDA_TRY(ctx, Rt.alloc((size_t)r * rp));
+  GINGR_CUDA_TRY(ctx, info.alloc(4));
+  GINGR_CUDA_TRY(ctx, cudaMemsetAsync(info.p, 0, sizeof(int) * 4, ctx->stream));
+  GINGR_TRY(build_regression_system_enqueue(ctx, r, rp, m->S.p, 1e-5, B.p));
+  GINGR_TRY(cholesky_enqueue(ctx, r, 2 * r, B.p, rp, info.p));
+  // W0 = Rm Rm^T = Gram of Rm^T
+  GINGR_CUDA_TRY(ctx, cudaMemsetAsync(Rt.p, 0, sizeof(double) * r * rp, ctx->stream));
+  GINGR_TRY(transpose_enqueue(ctx, r, B.p + (size_t)r * rp, rp, Rt.p, rp));
+  GramPlan plan2;
+  GINGR_TRY(plan2.build(ctx, r, r, rp));
+  GINGR_TRY(gram_partials_enqueue(ctx, plan2, Rt.p, nullptr));
+  GINGR_CUDA_TRY(ctx, cudaMemsetAsync(m->W0.p, 0, sizeof(double) * rp * rp, ctx->stream));
+  GINGR_TRY(gram_finish_enqueue(ctx, plan2, plan2.d_partial.p, nullptr, 0.0, 0, nullptr, nullptr, rp, m->W0.p));
+  int h_info = 0;
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  plan.release();
+  plan2.release();
+  B.release();
+  Rt.release();
+  info.release();
+  if (h_info != 0) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_model_upload: basis/variance not finite (1e-5 I + S not SPD)");
+  m->has_regression_constants = true;
+  return GINGR_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// building blocks shared by the kernel-level K3 entry points and gingr_update
+// -------------------------------------------------------------------------------------------------
+namespace gingr {
+
+// instance coefficients -> local mesh rows: out[3 Ml] = Phi_local (sqrt_lambda * alpha) for 1 or 2 alphas
+static int32_t instance_rows(gingr_ctx* ctx, const gingr_model* m, double* d_vec_scratch, int nvec, const double* d_alpha0,
+                             const double* d_alpha1, double* d_out0, double* d_out1) {
+  const int r = m->r, rp = m->rp;
+  scale_vec_kernel<<<ceil_div(r, 256), 256, 0, ctx->stream>>>(r, m->sqrt_lambda.p, d_alpha0, d_vec_scratch);
+  GINGR_LAUNCHED(ctx);
+  if (nvec > 1) {
+    scale_vec_kernel<<<ceil_div(r, 256), 256, 0, ctx->stream>>>(r, m->sqrt_lambda.p, d_alpha1, d_vec_scratch + rp);
+    GINGR_LAUNCHED(ctx);
+  }
+  return gemv_rows_enqueue(ctx, 3 * m->Ml, r, rp, m->phi.p, nvec, d_vec_scratch, d_vec_scratch + rp, d_out0, d_out1);
+}
+
+// local fit rows -> full fit on every rank
+static int32_t gather_fit(gingr_ctx* ctx, const gingr_model* m, const double* d_fit_local, double* d_gathered,
+                          double* d_fit) {
+  if (ctx->nranks == 1) {
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_fit, d_fit_local, sizeof(double) * 3 * (size_t)m->M, cudaMemcpyDeviceToDevice,
+                                        ctx->stream));
+    return GINGR_OK;
+  }
+  const int Mmax = ceil_div(m->M, ctx->nranks);
+  GINGR_TRY(comm_allgather(ctx, d_fit_local, d_gathered, (size_t)3 * Mmax));
+  compact_gather_kernel<<<ceil_div(3 * m->M, 256), 256, 0, ctx->stream>>>(m->M, ctx->nranks, Mmax, d_gathered, d_fit);
+  GINGR_LAUNCHED(ctx);
+  return GINGR_OK;
+}
+
+}  // namespace gingr
+
+struct PosteriorScratch {
+  GramPlan gram;
+  DevBuf<double> Mx, wrow, u, vec, gt_part, inst, fit_local, gathered, fit, ds;
+  DevBuf<int> is, flags;
+  void release() {
+    gram.release();
+    Mx.release(); wrow.release(); u.release(); vec.release(); gt_part.release(); inst.release();
+    fit_local.release(); gathered.release(); fit.release(); ds.release(); is.release(); flags.release();
+  }
+};
+
+extern "C" {
+
+// ---- K3 kernel-level entry points -----------------------------------------------------------------
+int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t, int32_t n,
+                             const int32_t* pid, const double* points, int32_t noise_kind, const double* noise,
+                             double* coeffs, double* mean_pts) {
+  if (!ctx || !model || !R || !t || n < 0 || (n > 0 && (!pid || !points || !noise)) || noise_kind < 0 || noise_kind > 1)
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_posterior_mean: bad argument");
+  if (ctx->nranks != 1) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "gingr_posterior_mean: single-GPU entry point");
+  const gingr_model* m = model;
+  const int M = m->M, r = m->r, rp = m->rp;
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  // Host-side marshalling of the observation list into per-vertex weights / residuals.  Isotropic
+  // observations of the same vertex add up (W = sum 1/var, W y = sum y/var); full-covariance ones become
+  // "landmark" blocks.
+  std::vector<double> wrow((size_t)3 * M, 0.0), u((size_t)3 * M, 0.0);
+  std::vector<int32_t> lpid;
+  std::vector<double> lpts, lcinv;
+  std::vector<double> href((size_t)3 * M), hmean((size_t)3 * M);
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(href.data(), m->ref.p, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, ctx->stream));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(hmean.data(), m->mean.p, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, ctx->stream));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  bool bad = false;
+  for (int k = 0; k < n; ++k) {
+    const int p = pid[k];
+    if (p < 0 || p >= M) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_posterior_mean: point id out of range");
+    if (noise_kind == 0) {
+      const double var = noise[k];
+      if (!(var > 0.0) || !(var < INFINITY)) { bad = true; continue; }
+      const double w = 1.0 / var;
+      double b[3], res[3];
+      for (int d = 0; d < 3; ++d) b[d] = href[3 * p + d] + hmean[3 * p + d];
+      for (int d = 0; d < 3; ++d)
+        res[d] = points[3 * k + d] - (R[3 * d] * b[0] + R[3 * d + 1] * b[1] + R[3 * d + 2] * b[2] + t[d]);
+      for (int d = 0; d < 3; ++d) {
+        wrow[3 * p + d] += w;
+        u[3 * p + d] += w * (R[d] * res[0] + R[3 + d] * res[1] + R[6 + d] * res[2]);
+      }
+    } else {
+      const double* C = noise + 9 * (size_t)k;
+      double inv[9];
+      const double det = C[0] * (C[4] * C[8] - C[5] * C[7]) - C[1] * (C[3] * C[8] - C[5] * C[6]) +
+                         C[2] * (C[3] * C[7] - C[4] * C[6]);
+      if (!(fabs(det) > 0.0) || !(fabs(det) < INFINITY)) { bad = true; continue; }
+      inv[0] = (C[4] * C[8] - C[5] * C[7]) / det; inv[1] = (C[2] * C[7] - C[1] * C[8]) / det; inv[2] = (C[1] * C[5] - C[2] * C[4]) / det;
+      inv[3] = (C[5] * C[6] - C[3] * C[8]) / det; inv[4] = (C[0] * C[8] - C[2] * C[6]) / det; inv[5] = (C[2] * C[3] - C[0] * C[5]) / det;
+      inv[6] = (C[3] * C[7] - C[4] * C[6]) / det; inv[7] = (C[1] * C[6] - C[0] * C[7]) / det; inv[8] = (C[0] * C[4] - C[1] * C[3]) / det;
+      lpid.push_back(p);
+      for (int d = 0; d < 3; ++d) lpts.push_back(points[3 * k + d]);
+      for (int d = 0; d < 9; ++d) lcinv.push_back(inv[d]);
+    }
+  }
+  if (bad) return GINGR_MODEL_FLEXIBILITY;
+  const int L = (int)lpid.size();
+  PosteriorScratch s;
+  auto fail = [&](int32_t rc) { cudaStreamSynchronize(ctx->stream); s.release(); return rc; };
+  int32_t rc;
+  if ((rc = s.gram.build(ctx, 3 * M, r, rp)) < 0) return fail(rc);
+  cudaStream_t st = ctx->stream;
+  DevBuf<int32_t> d_lpid;
+  DevBuf<double> d_lpts, d_lcinv, d_lA, d_lrows;
+#define PM_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { gingr_set_error(ctx, cudaGetErrorString(_e)); s.release(); d_lpid.release(); d_lpts.release(); d_lcinv.release(); d_lA.release(); d_lrows.release(); return GINGR_ERR_CUDA; } } while (0)
+  PM_TRY(s.Mx.alloc((size_t)(r + 8) * rp));
+  PM_TRY(s.wrow.alloc((size_t)3 * M));
+  PM_TRY(s.u.alloc((size_t)3 * M));
+  PM_TRY(s.vec.alloc((size_t)8 * rp));
+  PM_TRY(s.gt_part.alloc((size_t)gemvT_splits(ctx, 3 * M) * rp));
+  PM_TRY(s.inst.alloc((size_t)3 * M));
+  PM_TRY(s.fit_local.alloc((size_t)3 * M));
+  PM_TRY(s.ds.alloc(DS_COUNT));
+  PM_TRY(s.is.alloc(IS_COUNT));
+  PM_TRY(s.flags.alloc(256));
+  PM_TRY(cudaMemsetAsync(s.Mx.p, 0, sizeof(double) * (size_t)(r + 8) * rp, st));
+  PM_TRY(cudaMemsetAsync(s.is.p, 0, sizeof(int) * IS_COUNT, st));
+  PM_TRY(cudaMemcpyAsync(s.wrow.p, wrow.data(), sizeof(double) * 3 * M, cudaMemcpyHostToDevice, st));
+  PM_TRY(cudaMemcpyAsync(s.u.p, u.data(), sizeof(double) * 3 * M, cudaMemcpyHostToDevice, st));
+  double hds[DS_COUNT];
+  memset(hds, 0, sizeof(hds));
+  hds[DS_SCALE] = 1.0;
+  for (int d = 0; d < 3; ++d) hds[DS_T + d] = t[d];
+  for (int d = 0; d < 9; ++d) hds[DS_R + d] = R[d];
+  PM_TRY(cudaMemcpyAsync(s.ds.p, hds, sizeof(hds), cudaMemcpyHostToDevice, st));
+  double* rhs = s.Mx.p + (size_t)r * rp;
+  if ((rc = gemvT_enqueue(ctx, 3 * M, r, rp, m->phi.p, s.u.p, m->sqrt_lambda.p, s.gt_part.p, rhs)) < 0) return fail(rc);
+  if (L > 0) {
+    PM_TRY(d_lpid.alloc(L)); PM_TRY(d_lpts.alloc(3 * L)); PM_TRY(d_lcinv.alloc(9 * L)); PM_TRY(d_lA.alloc(9 * L));
+    PM_TRY(d_lrows.alloc((size_t)L * 3 * rp));
+    PM_TRY(cudaMemcpyAsync(d_lpid.p, lpid.data(), sizeof(int32_t) * L, cudaMemcpyHostToDevice, st));
+    PM_TRY(cudaMemcpyAsync(d_lpts.p, lpts.data(), sizeof(double) * 3 * L, cudaMemcpyHostToDevice, st));
+    PM_TRY(cudaMemcpyAsync(d_lcinv.p, lcinv.data(), sizeof(double) * 9 * L, cudaMemcpyHostToDevice, st));
+    gather_rows_kernel<<<dim3(ceil_div(3 * rp, 256), L), 256, 0, st>>>(L, rp, 0, d_lpid.p, m->phi.p, d_lrows.p);
+    landmark_prepare_kernel<<<ceil_div(L, 64), 64, 0, st>>>(L, d_lcinv.p, s.ds.p, d_lA.p);
+    landmark_rhs_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, rp, L, d_lpid.p, d_lpts.p, d_lA.p, d_lrows.p, m->ref.p,
+                                                          m->mean.p, m->sqrt_lambda.p, s.ds.p, rhs);
+    ctx->launches += 3;
+  }
+  if ((rc = gram_partials_enqueue(ctx, s.gram, m->phi.p, s.wrow.p)) < 0) return fail(rc);
+  if ((rc = gram_finish_enqueue(ctx, s.gram, s.gram.d_partial.p, m->sqrt_lambda.p, 1.0, L, d_lrows.p, d_lA.p, rp, s.Mx.p)) < 0) return fail(rc);
+  if ((rc = cholesky_enqueue(ctx, r, r + 1, s.Mx.p, rp, s.is.p + IS_INFO)) < 0) return fail(rc);
+  double* c = s.vec.p;
+  if ((rc = chol_backsolve_enqueue(ctx, r, s.Mx.p, rp, rhs, c, s.flags.p)) < 0) return fail(rc);
+  check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, c, s.is.p + IS_FAIL_POST);
+  GINGR_LAUNCHED(ctx);
+  if (mean_pts) {
+    if ((rc = instance_rows(ctx, m, s.vec.p + 2 * rp, 1, c, nullptr, s.inst.p, nullptr)) < 0) return fail(rc);
+    fit_from_instance_kernel<<<ceil_div(M, 256), 256, 0, st>>>(0, M, m->ref.p, m->mean.p, s.inst.p, s.ds.p, DS_SCALE, DS_T,
+                                                               DS_R, s.fit_local.p);
+    GINGR_LAUNCHED(ctx);
+    PM_TRY(cudaMemcpyAsync(mean_pts, s.fit_local.p, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, st));
+  }
+  int his[IS_COUNT];
+  if (coeffs) PM_TRY(cudaMemcpyAsync(coeffs, c, sizeof(double) * r, cudaMemcpyDeviceToHost, st));
+  PM_TRY(cudaMemcpyAsync(his, s.is.p, sizeof(int) * IS_COUNT, cudaMemcpyDeviceToHost, st));
+  PM_TRY(cudaStreamSynchronize(st));
+#undef PM_TRY
+  s.release();
+  d_lpid.release(); d_lpts.release(); d_lcinv.release(); d_lA.release(); d_lrows.release();
+  return (his[IS_INFO] || his[IS_FAIL_POST]) ? GINGR_MODEL_FLEXIBILITY : GINGR_OK;
+}
+
+int32_t gingr_coefficients(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t,
+                           const double* mesh_pts, double* coeffs) {
+  if (!ctx || !model || !R || !t || !mesh_pts || !coeffs)
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_coefficients: bad argument");
+  if (ctx->nranks != 1) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "gingr_coefficients: single-GPU entry point");
+  const gingr_model* m = model;
+  const int M = m->M, r = m->r, rp = m->rp;
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf<double> mesh, u, part, vec, ds;
+  DevBuf<int> flag;
+  cudaStream_t st = ctx->stream;
+  auto rel = [&]() { mesh.release(); u.release(); part.release(); vec.release(); ds.release(); flag.release(); };
+#define CO_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { gingr_set_error(ctx, cudaGetErrorString(_e)); rel(); return GINGR_ERR_CUDA; } } while (0)
+  CO_TRY(mesh.alloc((size_t)3 * M)); CO_TRY(u.alloc((size_t)3 * M)); CO_TRY(vec.alloc((size_t)4 * rp));
+  CO_TRY(part.alloc((size_t)gemvT_splits(ctx, 3 * M) * rp)); CO_TRY(ds.alloc(DS_COUNT)); CO_TRY(flag.alloc(4));
+  double hds[DS_COUNT];
+  memset(hds, 0, sizeof(hds));
+  for (int d = 0; d < 3; ++d) hds[DS_NEW_T + d] = t[d];
+  for (int d = 0; d < 9; ++d) hds[DS_R1 + d] = R[d];
+  CO_TRY(cudaMemcpyAsync(ds.p, hds, sizeof(hds), cudaMemcpyHostToDevice, st));
+  CO_TRY(cudaMemcpyAsync(mesh.p, mesh_pts, sizeof(double) * 3 * M, cudaMemcpyHostToDevice, st));
+  CO_TRY(cudaMemsetAsync(flag.p, 0, sizeof(int) * 4, st));
+  coeff_residual_kernel<<<ceil_div(M, 256), 256, 0, st>>>(0, M, mesh.p, m->ref.p, m->mean.p, ds.p, u.p);
+  GINGR_LAUNCHED(ctx);
+  int32_t rc = gemvT_enqueue(ctx, 3 * M, r, rp, m->phi.p, u.p, m->sqrt_lambda.p, part.p, vec.p);
+  if (rc >= 0) rc = dense_matvec_enqueue(ctx, r, m->W0.p, rp, vec.p, vec.p + rp);
+  if (rc < 0) { cudaStreamSynchronize(st); rel(); return rc; }
+  check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, vec.p + rp, flag.p);
+  GINGR_LAUNCHED(ctx);
+  int hflag = 0;
+  CO_TRY(cudaMemcpyAsync(coeffs, vec.p + rp, sizeof(double) * r, cudaMemcpyDeviceToHost, st));
+  CO_TRY(cudaMemcpyAsync(&hflag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CO_TRY(cudaStreamSynchronize(st));
+#undef CO_TRY
+  rel();
+  return hflag ? GINGR_MODEL_FLEXIBILITY : GINGR_OK;
+}
+
+int32_t gingr_model_instance(gingr_ctx* ctx, const gingr_model* model, const gingr_state* stt, const double* alpha,
+                             double* fit) {
+  if (!ctx || !model || !stt || !alpha || !fit) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_model_instance: bad argument");
+  if (ctx->nranks != 1) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "gingr_model_instance: single-GPU entry point");
+  const gingr_model* m = model;
+  const int M = m->M, r = m->r, rp = m->rp;
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf<double> vec, inst, out, ds;
+  DevBuf<int> is;
+  cudaStream_t st = ctx->stream;
+  auto rel = [&]() { vec.release(); inst.release(); out.release(); ds.release(); is.release(); };
+#define MI_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { gingr_set_error(ctx, cudaGetErrorString(_e)); rel(); return GINGR_ERR_CUDA; } } while (0)
+  MI_TRY(vec.alloc((size_t)4 * rp)); MI_TRY(inst.alloc((size_t)3 * M)); MI_TRY(out.alloc((size_t)3 * M));
+  MI_TRY(ds.alloc(DS_COUNT)); MI_TRY(is.alloc(IS_COUNT));
+  double hds[DS_COUNT];
+  memset(hds, 0, sizeof(hds));
+  hds[DS_SCALE] = stt->scale;
+  for (int d = 0; d < 3; ++d) { hds[DS_T + d] = stt->translation[d]; hds[DS_EULER + d] = stt->euler[d]; }
+  MI_TRY(cudaMemcpyAsync(ds.p, hds, sizeof(hds), cudaMemcpyHostToDevice, st));
+  MI_TRY(cudaMemcpyAsync(vec.p, alpha, sizeof(double) * r, cudaMemcpyHostToDevice, st));
+  pose_kernel<<<1, 1, 0, st>>>(ds.p, is.p);
+  GINGR_LAUNCHED(ctx);
+  int32_t rc = instance_rows(ctx, m, vec.p + rp, 1, vec.p, nullptr, inst.p, nullptr);
+  if (rc < 0) { cudaStreamSynchronize(st); rel(); return rc; }
+  fit_from_instance_kernel<<<ceil_div(M, 256), 256, 0, st>>>(0, M, m->ref.p, m->mean.p, inst.p, ds.p, DS_SCALE, DS_T, DS_R,
+                                                             out.p);
+  GINGR_LAUNCHED(ctx);
+  MI_TRY(cudaMemcpyAsync(fit, out.p, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, st));
+  MI_TRY(cudaStreamSynchronize(st));
+#undef MI_TRY
+  rel();
+  return GINGR_OK;
+}
+
+// ---- registration handle ---------------------------------------------------------------------------
+int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, const gingr_target* target,
+                                  const gingr_config* cfg, gingr_registration** out) {
+  if (!ctx || !model || !target || !cfg || !out) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_registration_create: bad argument");
+  if (cfg->algorithm != GINGR_ALGO_CPD && cfg->algorithm != GINGR_ALGO_ICP)
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_registration_create: unknown algorithm");
+  if (cfg->algorithm == GINGR_ALGO_CPD && !(cfg->w >= 0.0 && cfg->w < 1.0))
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_registration_create: CPD w must be in [0, 1)");
+  if (cfg->algorithm == GINGR_ALGO_ICP) {
+    if (cfg->reverse_correspondence_direction)
+      return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "reverseCorrespondenceDirection is not implemented in gingr_update yet");
+    if (cfg->correspondence_method == GINGR_ALONG_NORMAL_CLOSEST_POINT)
+      return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "AlongNormalClosestPoint is not implemented yet");
+    if (cfg->correspondence_method == GINGR_TRIANGULAR_CLOSEST_POINT && (model->T <= 0 || target->T <= 0))
+      return gingr_fail(ctx, GINGR_ERR_ARG, "TriangularClosestPoint needs model and target triangles");
+  }
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  gingr_registration* g = new gingr_registration();
+  g->ctx = ctx;
+  g->model = model;
+  g->target = target;
+  g->cfg = *cfg;
+  const int M = model->M, r = model->r, rp = model->rp, Ml = model->Ml;
+  const int Mmax = ceil_div(M, ctx->nranks);
+  int32_t rc = GINGR_OK;
+  auto A = [&](cudaError_t e) { if (e != cudaSuccess && rc == GINGR_OK) { gingr_set_error(ctx, cudaGetErrorString(e)); rc = GINGR_ERR_CUDA; } };
+  if (cfg->algorithm == GINGR_ALGO_CPD) { int32_t q = g->estep.ensure(ctx, M, std::max(target->N, 1)); if (q < 0) rc = q; }
+  else { int32_t q = g->closest.ensure(ctx, M, target->N_total, target->T, model->T); if (q < 0) rc = q; }
+  if (rc == GINGR_OK) { int32_t q = g->gram.build(ctx, 3 * Ml, r, rp); if (q < 0) rc = q; }
+  A(g->rows_ext.alloc((size_t)4 * M + 8));
+  A(g->Mx.alloc((size_t)(r + 8) * rp));
+  A(g->wrow.alloc((size_t)3 * Mmax)); A(g->u.alloc((size_t)3 * Mmax));
+  A(g->inst_a.alloc((size_t)3 * Mmax)); A(g->inst_b.alloc((size_t)3 * Mmax));
+  A(g->newshape.alloc((size_t)3 * Mmax)); A(g->fit_local.alloc((size_t)3 * Mmax));
+  A(g->gathered.alloc((size_t)3 * Mmax * ctx->nranks)); A(g->fit.alloc((size_t)3 * M));
+  A(g->vec.alloc((size_t)8 * rp));
+  A(g->gt_part.alloc((size_t)gemvT_splits(ctx, 3 * Ml) * rp));
+  A(g->sums_part.alloc((size_t)3 * ceil_div(M, 256)));
+  A(g->pro_part.alloc((size_t)16 * ceil_div(std::max(Ml, 1), 256)));
+  A(g->pro_sums.alloc(32));
+  A(g->ds.alloc(DS_COUNT)); A(g->is.alloc(IS_COUNT)); A(g->flags.alloc(256));
+  A(g->alpha.alloc((size_t)rp));
+  if (rc == GINGR_OK) {
+    A(cudaMemsetAsync(g->Mx.p, 0, sizeof(double) * (size_t)(r + 8) * rp, ctx->stream));
+    A(cudaMemsetAsync(g->fit_local.p, 0, sizeof(double) * 3 * Mmax, ctx->stream));
+    A(cudaMemsetAsync(g->ds.p, 0, sizeof(double) * DS_COUNT, ctx->stream));
+    A(cudaMemsetAsync(g->is.p, 0, sizeof(int) * IS_COUNT, ctx->stream));
+    A(cudaMemsetAsync(g->alpha.p, 0, sizeof(double) * rp, ctx->stream));
+    A(cudaMemsetAsync(g->rows_ext.p, 0, sizeof(double) * ((size_t)4 * M + 8), ctx->stream));
+    A(cudaStreamSynchronize(ctx->stream));
+  }
+  if (rc != GINGR_OK) {
+    gingr_registration_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return GINGR_OK;
+}
+
+int32_t gingr_registration_destroy(gingr_registration* g) {
+  if (!g) return GINGR_OK;
+  cudaSetDevice(g->ctx->device);
+  cudaStreamSynchronize(g->ctx->stream);
+  g->lm_pid.release(); g->lml_pid.release(); g->lml_pts.release(); g->lml_cinv.release(); g->lml_A.release();
+  g->lml_rows.release();
+  g->estep.release(); g->closest.release(); g->gram.release();
+  g->rows_ext.release(); g->Mx.release(); g->wrow.release(); g->u.release(); g->inst_a.release(); g->inst_b.release();
+  g->newshape.release(); g->fit_local.release(); g->gathered.release(); g->fit.release(); g->vec.release();
+  g->gt_part.release(); g->sums_part.release(); g->pro_part.release(); g->pro_sums.release();
+  g->ds.release(); g->is.release(); g->flags.release(); g->alpha.release();
+  delete g;
+  return GINGR_OK;
+}
+
+int32_t gingr_registration_set_landmarks(gingr_registration* g, int32_t L, const int32_t* pid, const double* points,
+                                         const double* cov) {
+  if (!g || L < 0 || (L > 0 && (!pid || !points || !cov))) return gingr_fail(g ? g->ctx : nullptr, GINGR_ERR_ARG, "set_landmarks: bad argument");
+  gingr_ctx* ctx = g->ctx;
+  const gingr_model* m = g->model;
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::vector<int32_t> lpid;
+  std::vector<double> lpts, lcinv;
+  for (int l = 0; l < L; ++l) {
+    if (pid[l] < 0 || pid[l] >= m->M) return gingr_fail(ctx, GINGR_ERR_ARG, "set_landmarks: vertex id out of range");
+    const double* C = cov + 9 * (size_t)l;
+    const double det = C[0] * (C[4] * C[8] - C[5] * C[7]) - C[1] * (C[3] * C[8] - C[5] * C[6]) + C[2] * (C[3] * C[7] - C[4] * C[6]);
+    if (!(fabs(det) > 0.0) || !(fabs(det) < INFINITY)) return gingr_fail(ctx, GINGR_ERR_ARG, "set_landmarks: singular covariance");
+    if (pid[l] >= m->m0 && pid[l] < m->m0 + m->Ml) {
+      lpid.push_back(pid[l]);
+      for (int d = 0; d < 3; ++d) lpts.push_back(points[3 * l + d]);
+      const double inv[9] = {(C[4] * C[8] - C[5] * C[7]) / det, (C[2] * C[7] - C[1] * C[8]) / det, (C[1] * C[5] - C[2] * C[4]) / det,
+                             (C[5] * C[6] - C[3] * C[8]) / det, (C[0] * C[8] - C[2] * C[6]) / det, (C[2] * C[3] - C[0] * C[5]) / det,
+                             (C[3] * C[7] - C[4] * C[6]) / det, (C[1] * C[6] - C[0] * C[7]) / det, (C[0] * C[4] - C[1] * C[3]) / det};
+      for (int d = 0; d < 9; ++d) lcinv.push_back(inv[d]);
+    }
+  }
+  g->L = L;
+  g->Ll = (int)lpid.size();
+  cudaStream_t st = ctx->stream;
+  GINGR_CUDA_TRY(ctx, g->lm_pid.alloc(std::max(L, 1)));
+  if (L > 0) GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->lm_pid.p, pid, sizeof(int32_t) * L, cudaMemcpyHostToDevice, st));
+  const int Ll = g->Ll;
+  GINGR_CUDA_TRY(ctx, g->lml_pid.alloc(std::max(Ll, 1)));
+  GINGR_CUDA_TRY(ctx, g->lml_pts.alloc(std::max(3 * Ll, 1)));
+  GINGR_CUDA_TRY(ctx, g->lml_cinv.alloc(std::max(9 * Ll, 1)));
+  GINGR_CUDA_TRY(ctx, g->lml_A.alloc(std::max(9 * Ll, 1)));
+  GINGR_CUDA_TRY(ctx, g->lml_rows.alloc(std::max<size_t>((size_t)Ll * 3 * m->rp, 1)));
+  if (Ll > 0) {
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->lml_pid.p, lpid.data(), sizeof(int32_t) * Ll, cudaMemcpyHostToDevice, st));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->lml_pts.p, lpts.data(), sizeof(double) * 3 * Ll, cudaMemcpyHostToDevice, st));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->lml_cinv.p, lcinv.data(), sizeof(double) * 9 * Ll, cudaMemcpyHostToDevice, st));
+    gather_rows_kernel<<<dim3(ceil_div(3 * m->rp, 256), Ll), 256, 0, st>>>(Ll, m->rp, m->m0, g->lml_pid.p, m->phi.p,
+                                                                          g->lml_rows.p);
+    GINGR_LAUNCHED(ctx);
+  }
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  g->state_valid = false;
+  return GINGR_OK;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// state upload / fit evaluation / one iteration
+// -------------------------------------------------------------------------------------------------
+static int32_t upload_state(gingr_registration* g, const gingr_state* s, const double* alpha) {
+  gingr_ctx* ctx = g->ctx;
+  if (s->rank != g->model->r) return gingr_fail(ctx, GINGR_ERR_ARG, "state rank does not match the model rank");
+  if (s->center[0] != 0.0 || s->center[1] != 0.0 || s->center[2] != 0.0)
+    return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "rotation centre must be the origin (GeneralRegistrationState.scala:147)");
+  double* h = ctx->h_pinned;
+  memset(h, 0, sizeof(double) * DS_COUNT);
+  h[DS_SCALE] = s->scale;
+  for (int d = 0; d < 3; ++d) { h[DS_T + d] = s->translation[d]; h[DS_EULER + d] = s->euler[d]; h[DS_CENTER + d] = s->center[d]; }
+  h[DS_SIGMA2] = s->sigma2;
+  h[DS_STEP] = s->step_length;
+  int* hi = reinterpret_cast<int*>(h + DS_COUNT);
+  memset(hi, 0, sizeof(int) * IS_COUNT);
+  hi[IS_GT] = s->global_transformation;
+  hi[IS_ITER] = s->iteration;
+  hi[IS_STATUS] = s->status;
+  double* ha = h + DS_COUNT + IS_COUNT;
+  if ((size_t)(DS_COUNT + IS_COUNT + g->model->r) > ctx->h_pinned_count) {
+    // large ranks: alpha goes straight from the caller's buffer
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->alpha.p, alpha, sizeof(double) * g->model->r, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    memcpy(ha, alpha, sizeof(double) * g->model->r);
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->alpha.p, ha, sizeof(double) * g->model->r, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->ds.p, h, sizeof(double) * DS_COUNT, cudaMemcpyHostToDevice, ctx->stream));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->is.p, hi, sizeof(int) * IS_COUNT, cudaMemcpyHostToDevice, ctx->stream));
+  pose_kernel<<<1, 1, 0, ctx->stream>>>(g->ds.p, g->is.p);
+  GINGR_LAUNCHED(ctx);
+  return GINGR_OK;
+}
+
+// fit = s (R instance(alpha) + t) with the pose at the given state-block offsets; result in g->fit (all ranks)
+static int32_t evaluate_fit(gingr_registration* g, int off_s, int off_t, int off_R) {
+  gingr_ctx* ctx = g->ctx;
+  const gingr_model* m = g->model;
+  GINGR_TRY(instance_rows(ctx, m, g->vec.p + 6 * m->rp, 1, g->alpha.p, nullptr, g->inst_a.p, nullptr));
+  if (m->Ml > 0) {
+    fit_from_instance_kernel<<<ceil_div(m->Ml, 256), 256, 0, ctx->stream>>>(m->m0, m->Ml, m->ref.p, m->mean.p, g->inst_a.p,
+                                                                            g->ds.p, off_s, off_t, off_R, g->fit_local.p);
+    GINGR_LAUNCHED(ctx);
+  }
+  return gather_fit(ctx, m, g->fit_local.p, g->gathered.p, g->fit.p);
+}
+
+static int32_t enqueue_iteration(gingr_registration* g) {
+  gingr_ctx* ctx = g->ctx;
+  const gingr_model* m = g->model;
+  const gingr_target* tg = g->target;
+  const gingr_config& cfg = g->cfg;
+  const int M = m->M, r = m->r, rp = m->rp, Ml = m->Ml, m0 = m->m0;
+  cudaStream_t st = ctx->stream;
+  double* vec = g->vec.p;  // [0] c_post  [1] S c  [2] alpha*  [3] alpha_c  [4] q  [5] alpha_new  [6,7] scaled scratch
+  pose_kernel<<<1, 1, 0, st>>>(g->ds.p, g->is.p);
+  GINGR_LAUNCHED(ctx);
+  // ---- correspondence -------------------------------------------------------------------------------
+  if (cfg.algorithm == GINGR_ALGO_CPD) {
+    GINGR_TRY(aos_to_soa_enqueue(ctx, M, g->fit.p, g->estep.fit_soa.p));
+    cpd_estep_scalars_kernel<<<1, 1, 0, st>>>(g->ds.p, cfg.w, (double)M / (double)tg->N_total, g->estep.scal.p);
+    GINGR_LAUNCHED(ctx);
+    if (tg->N > 0) {
+      GINGR_TRY(estep_enqueue(ctx, g->estep, M, tg->N, tg->soa.p, false));
+      GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->rows_ext.p, g->estep.rows.p, sizeof(double) * 4 * (size_t)M,
+                                          cudaMemcpyDeviceToDevice, st));
+      xpx_total_kernel<<<1, 1, 0, st>>>(g->estep.plan.den_blocks, g->estep.xpx_part.p, g->rows_ext.p + (size_t)4 * M);
+      GINGR_LAUNCHED(ctx);
+    } else {
+      GINGR_CUDA_TRY(ctx, cudaMemsetAsync(g->rows_ext.p, 0, sizeof(double) * ((size_t)4 * M + 8), st));
+    }
+    GINGR_TRY(comm_allreduce_sum(ctx, g->rows_ext.p, (size_t)4 * M + 8));
+  } else {
+    GINGR_TRY(icp_closest_enqueue(ctx, g->closest, tg, M, g->fit.p, m->T, m->tri.p, m->adj_off.p, m->adj.p,
+                                  cfg.correspondence_method));
+  }
+  // ---- observations, sigma2 hook ----------------------------------------------------------------------
+  ObsArgs oa;
+  oa.algo = cfg.algorithm; oa.M = M; oa.m0 = m0; oa.Ml = Ml; oa.use_lm = cfg.use_landmark_correspondence && g->L > 0;
+  oa.L = g->L; oa.lambda = cfg.lambda;
+  const int oblocks = ceil_div(M, 256);
+  obs_kernel<<<oblocks, 256, 0, st>>>(oa, g->rows_ext.p, g->closest.cp.p, g->closest.w.p, g->fit.p, m->ref.p, m->mean.p,
+                                      g->lm_pid.p, g->ds.p, g->is.p, g->wrow.p, g->u.p, g->sums_part.p);
+  GINGR_LAUNCHED(ctx);
+  const double sigma_step = cfg.algorithm == GINGR_ALGO_ICP ? (cfg.initial_sigma - cfg.end_sigma) / (double)cfg.max_iterations : 0.0;
+  sigma2_kernel<<<1, 1, 0, st>>>(cfg.algorithm, oblocks, g->sums_part.p, g->rows_ext.p + (size_t)4 * M, sigma_step,
+                                 cfg.end_sigma, g->ds.p);
+  GINGR_LAUNCHED(ctx);
+  // ---- posterior: rhs, Gram, Cholesky --------------------------------------------------------------------
+  double* rhs = g->Mx.p + (size_t)r * rp;
+  GINGR_TRY(gemvT_enqueue(ctx, 3 * Ml, r, rp, m->phi.p, g->u.p, m->sqrt_lambda.p, g->gt_part.p, rhs));
+  const bool use_lm = cfg.use_landmark_correspondence && g->Ll > 0;
+  if (use_lm) {
+    landmark_prepare_kernel<<<ceil_div(g->Ll, 64), 64, 0, st>>>(g->Ll, g->lml_cinv.p, g->ds.p, g->lml_A.p);
+    landmark_rhs_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, rp, g->Ll, g->lml_pid.p, g->lml_pts.p, g->lml_A.p, g->lml_rows.p,
+                                                          m->ref.p, m->mean.p, m->sqrt_lambda.p, g->ds.p, rhs);
+    ctx->launches += 2;
+  }
+  GINGR_TRY(gram_partials_enqueue(ctx, g->gram, m->phi.p, g->wrow.p));
+  GINGR_TRY(gram_finish_enqueue(ctx, g->gram, g->gram.d_partial.p, m->sqrt_lambda.p, ctx->rank == 0 ? 1.0 : 0.0,
+                                use_lm ? g->Ll : 0, g->lml_rows.p, g->lml_A.p, rp, g->Mx.p));
+  GINGR_TRY(comm_allreduce_sum(ctx, g->Mx.p, (size_t)(r + 1) * rp));
+  GINGR_TRY(cholesky_enqueue(ctx, r, r + 1, g->Mx.p, rp, g->is.p + IS_INFO));
+  GINGR_TRY(chol_backsolve_enqueue(ctx, r, g->Mx.p, rp, rhs, vec, g->flags.p));
+  check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, vec, g->is.p + IS_FAIL_POST);
+  GINGR_LAUNCHED(ctx);
+  // ---- alpha* = coefficients(posterior mean) = W0 S c ; combine ---------------------------------------------
+  GINGR_TRY(dense_matvec_enqueue(ctx, r, m->S.p, rp, vec, vec + rp));
+  GINGR_TRY(dense_matvec_enqueue(ctx, r, m->W0.p, rp, vec + rp, vec + 2 * rp));
+  combine_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, g->alpha.p, vec + 2 * rp, g->ds.p, vec + 3 * rp);
+  GINGR_LAUNCHED(ctx);
+  // ---- instances, Procrustes -----------------------------------------------------------------------------------
+  GINGR_TRY(instance_rows(ctx, m, vec + 6 * rp, 2, g->alpha.p, vec + 3 * rp, g->inst_a.p, g->inst_b.p));
+  const int pblocks = ceil_div(std::max(Ml, 1), 256);
+  for (int pass = 0; pass < 2; ++pass) {
+    procrustes_sums_kernel<<<pblocks, 256, 0, st>>>(pass, m0, Ml, m->ref.p, m->mean.p, g->inst_a.p, g->inst_b.p, g->ds.p,
+                                                    g->newshape.p, g->pro_part.p);
+    procrustes_reduce_kernel<<<1, 32, 0, st>>>(pblocks, 10, g->pro_part.p, g->pro_sums.p);
+    ctx->launches += 2;
+    GINGR_TRY(comm_allreduce_sum(ctx, g->pro_sums.p, 16));
+    if (pass == 0) {
+      procrustes_means_kernel<<<1, 1, 0, st>>>(M, g->pro_sums.p, g->ds.p);
+      GINGR_LAUNCHED(ctx);
+    }
+  }
+  procrustes_solve_kernel<<<1, 1, 0, st>>>(M, g->pro_sums.p, g->ds.p, g->is.p);
+  GINGR_LAUNCHED(ctx);
+  // ---- alpha_new = transformedModel.coefficients(newshape) ---------------------------------------------------------
+  if (Ml > 0) {
+    coeff_residual_kernel<<<ceil_div(Ml, 256), 256, 0, st>>>(m0, Ml, g->newshape.p, m->ref.p, m->mean.p, g->ds.p, g->u.p);
+    GINGR_LAUNCHED(ctx);
+  }
+  GINGR_TRY(gemvT_enqueue(ctx, 3 * Ml, r, rp, m->phi.p, g->u.p, m->sqrt_lambda.p, g->gt_part.p, vec + 4 * rp));
+  GINGR_TRY(comm_allreduce_sum(ctx, vec + 4 * rp, (size_t)r));
+  GINGR_TRY(dense_matvec_enqueue(ctx, r, m->W0.p, rp, vec + 4 * rp, vec + 5 * rp));
+  check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, vec + 5 * rp, g->is.p + IS_FAIL_COEF);
+  GINGR_LAUNCHED(ctx);
+  // ---- commit, refresh the fit ------------------------------------------------------------------------------------------
+  finalize_kernel<<<1, 256, 0, st>>>(r, vec + 5 * rp, g->alpha.p, g->ds.p, g->is.p);
+  GINGR_LAUNCHED(ctx);
+  GINGR_TRY(evaluate_fit(g, DS_SCALE, DS_T, DS_R2));
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+static int32_t download_state(gingr_registration* g, gingr_state* out, double* alpha_out, double* fit_out) {
+  gingr_ctx* ctx = g->ctx;
+  const gingr_model* m = g->model;
+  double* h = ctx->h_pinned;
+  int* hi = reinterpret_cast<int*>(h + DS_COUNT);
+  cudaStream_t st = ctx->stream;
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(h, g->ds.p, sizeof(double) * DS_COUNT, cudaMemcpyDeviceToHost, st));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(hi, g->is.p, sizeof(int) * IS_COUNT, cudaMemcpyDeviceToHost, st));
+  if (alpha_out) GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(alpha_out, g->alpha.p, sizeof(double) * m->r, cudaMemcpyDeviceToHost, st));
+  if (fit_out) GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(fit_out, g->fit.p, sizeof(double) * 3 * (size_t)m->M, cudaMemcpyDeviceToHost, st));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  out->scale = h[DS_SCALE];
+  for (int d = 0; d < 3; ++d) { out->translation[d] = h[DS_T + d]; out->euler[d] = h[DS_EULER + d]; out->center[d] = h[DS_CENTER + d]; }
+  out->sigma2 = h[DS_SIGMA2];
+  out->step_length = h[DS_STEP];
+  out->global_transformation = hi[IS_GT];
+  out->iteration = hi[IS_ITER];
+  out->status = hi[IS_STATUS];
+  out->rank = m->r;
+  return GINGR_OK;
+}
+
+// equal up to the bookkeeping fields the host-side `propose` touches (iteration, status)
+static bool same_state(gingr_state a, const gingr_state& b) {
+  a.iteration = b.iteration;
+  a.status = b.status;
+  return memcmp(&a, &b, sizeof(gingr_state)) == 0;
+}
+
+extern "C" {
+
+int32_t gingr_initialize_state(gingr_registration* g, gingr_state* s, const double* alpha, double* fit_out) {
+  if (!g || !s || !alpha) return gingr_fail(g ? g->ctx : nullptr, GINGR_ERR_ARG, "gingr_initialize_state: bad argument");
+  gingr_ctx* ctx = g->ctx;
+  const gingr_model* m = g->model;
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  s->rank = m->r;
+  if (g->cfg.algorithm == GINGR_ALGO_ICP || g->cfg.has_initial_sigma) {
+    s->sigma2 = g->cfg.initial_sigma;  // ICP.scala:74-78 ; CPD.scala:94 (initialSigma given)
+  } else {
+    // computeInitialSigma2 over model.mean = ref + meanVector (CPD.scala:95)
+    DevBuf<double> mp, outv;
+    GINGR_CUDA_TRY(ctx, mp.alloc((size_t)3 * m->M));
+    GINGR_CUDA_TRY(ctx, outv.alloc(4));
+    add_vectors_enqueue(ctx, 3 * m->M, m->ref.p, m->mean.p, mp.p);
+    int32_t rc = initial_sigma2_enqueue(ctx, m->M, mp.p, g->target->N_total, g->target->verts.p, outv.p);
+    double v = 0.0;
+    cudaError_t e = cudaMemcpyAsync(&v, outv.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    mp.release();
+    outv.release();
+    if (rc < 0) return rc;
+    GINGR_CUDA_TRY(ctx, e);
+    s->sigma2 = v;
+  }
+  GINGR_TRY(upload_state(g, s, alpha));
+  GINGR_TRY(evaluate_fit(g, DS_SCALE, DS_T, DS_R));
+  gingr_state tmp;
+  GINGR_TRY(download_state(g, &tmp, nullptr, fit_out));
+  g->last_out = *s;
+  g->last_alpha.assign(alpha, alpha + m->r);
+  g->state_valid = true;
+  return GINGR_OK;
+}
+
+int32_t gingr_update(gingr_registration* g, const gingr_state* state_in, const double* alpha_in, int32_t probabilistic,
+                     uint64_t seed, gingr_state* state_out, double* alpha_out, double* fit_out) {
+  (void)seed;
+  if (!g || !state_in || !alpha_in || !state_out || !alpha_out)
+    return gingr_fail(g ? g->ctx : nullptr, GINGR_ERR_ARG, "gingr_update: bad argument");
+  gingr_ctx* ctx = g->ctx;
+  if (probabilistic)
+    return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "probabilistic update (posterior.sample) is not implemented yet (SURVEY 8f.1)");
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const gingr_model* m = g->model;
+  // Re-seed the device state unless the caller hands back exactly what the previous call returned
+  // (then the device-resident fit is already the fit of this state).
+  const bool resume = g->state_valid && same_state(*state_in, g->last_out) &&
+                      memcmp(alpha_in, g->last_alpha.data(), sizeof(double) * m->r) == 0;
+  if (!resume) {
+    GINGR_TRY(upload_state(g, state_in, alpha_in));
+    GINGR_TRY(evaluate_fit(g, DS_SCALE, DS_T, DS_R));
+  } else {
+    set_iteration_kernel<<<1, 1, 0, ctx->stream>>>(g->is.p, state_in->iteration, state_in->status);
+    GINGR_LAUNCHED(ctx);
+  }
+  g->state_valid = false;
+  GINGR_TRY(enqueue_iteration(g));
+  GINGR_TRY(download_state(g, state_out, alpha_out, fit_out));
+  g->last_out = *state_out;
+  g->last_alpha.assign(alpha_out, alpha_out + m->r);
+  g->state_valid = true;
+  return GINGR_OK;
+}
+
+int32_t gingr_update_chain(gingr_registration* g, int32_t iters) {
+  if (!g || iters < 0) return gingr_fail(g ? g->ctx : nullptr, GINGR_ERR_ARG, "gingr_update_chain: bad argument");
+  gingr_ctx* ctx = g->ctx;
+  if (!g->state_valid) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_chain: no device-resident state (call gingr_initialize_state / gingr_update first)");
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int k = 0; k < iters; ++k) {
+    GINGR_TRY(enqueue_iteration(g));
+    bump_iteration_kernel<<<1, 1, 0, ctx->stream>>>(g->is.p);  // GingrGeneratorWrapper.propose: updateIteration()
+    GINGR_LAUNCHED(ctx);
+  }
+  return GINGR_OK;
+}
+
+int32_t gingr_state_download(gingr_registration* g, gingr_state* state_out, double* alpha_out, double* fit_out) {
+  if (!g || !state_out) return gingr_fail(g ? g->ctx : nullptr, GINGR_ERR_ARG, "gingr_state_download: bad argument");
+  GINGR_CUDA_TRY(g->ctx, cudaSetDevice(g->ctx->device));
+  GINGR_TRY(download_state(g, state_out, alpha_out, fit_out));
+  g->last_out = *state_out;
+  if (alpha_out) g->last_alpha.assign(alpha_out, alpha_out + g->model->r);
+  else g->state_valid = false;
+  return GINGR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+// vecops.cu -- K3c: HBM-bound passes over the GPMM basis and small dense helpers (sm_100a).
+//
+//   gemv_rows   out[k] = sum_a Phi[k][a] v[a]      instance / posterior mean evaluation at the mesh points:
+//               scalismo `instance(alpha) = ref + mean + basis (sqrt(lambda) * alpha)`, call sites
+//               GingrAlgorithm.scala:211, :222, :224 and ModelFittingParameters.scala:134.  One warp per row,
+//               two right-hand sides per pass (instance(alpha_old) and instance(alpha_new) share the read).
+//   gemvT       out[a] = s_a sum_k Phi[k][a] u[k]   right-hand side Q^T L^-1 (y - m) of the regression
+//               (SURVEY.md A3).  Thread per column, rows split over CTAs, fixed-order reduction.
+// Both read Phi (8 * 3M * r bytes) exactly once; Phi is row-major [3M][rp] so both are fully coalesced.
+#include "common.cuh"
+#include "posterior.cuh"
+
+namespace gingr {
+
+template <int NVEC>
+__global__ void __launch_bounds__(256) gemv_rows_kernel(int rows, int r, int rp, const double* __restrict__ phi,
+                                                        const double* __restrict__ v0, const double* __restrict__ v1,
+                                                        double* __restrict__ out0, double* __restrict__ out1) {
+  extern __shared__ double sv[];  // [NVEC][r]
+  for (int a = threadIdx.x; a < r; a += 256) {
+    sv[a] = v0[a];
+    if (NVEC > 1) sv[r + a] = v1[a];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = (gridDim.x * 256) >> 5;
+  for (int k = warp; k < rows; k += nwarps) {
+    const double* row = phi + (size_t)k * rp;
+    double s0 = 0.0, s1 = 0.0;
+    // rp is a multiple of 8: 16-byte vector loads
+    for (int a = lane * 2; a < r; a += 64) {
+      const double2 p = *reinterpret_cast<const double2*>(row + a);
+      s0 = fma(p.x, sv[a], s0);
+      if (a + 1 < r) s0 = fma(p.y, sv[a + 1], s0);
+      if (NVEC > 1) {
+        s1 = fma(p.x, sv[r + a], s1);
+        if (a + 1 < r) s1 = fma(p.y, sv[r + a + 1], s1);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      if (NVEC > 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) {
+      out0[k] = s0;
+      if (NVEC > 1) out1[k] = s1;
+    }
+  }
+}
+
+constexpr int GT_ROWS = 512;  // rows per CTA of gemvT
+
+__global__ void __launch_bounds__(256) gemvT_kernel(int rows, int rp, const double* __restrict__ phi,
+                                                    const double* __restrict__ u, double* __restrict__ part) {
+  __shared__ double su[GT_ROWS];
+  const int k0 = blockIdx.y * GT_ROWS;
+  const int cnt = min(GT_ROWS, rows - k0);
+  for (int t = threadIdx.x; t < cnt; t += 256) su[t] = u[k0 + t];
+  __syncthreads();
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  if (a >= rp) return;
+  const double* p = phi + (size_t)k0 * rp + a;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int t = 0;
+  for (; t + 4 <= cnt; t += 4) {
+    s0 = fma(p[(size_t)t * rp], su[t], s0);
+    s1 = fma(p[(size_t)(t + 1) * rp], su[t + 1], s1);
+    s2 = fma(p[(size_t)(t + 2) * rp], su[t + 2], s2);
+    s3 = fma(p[(size_t)(t + 3) * rp], su[t + 3], s3);
+  }
+  for (; t < cnt; ++t) s0 = fma(p[(size_t)t * rp], su[t], s0);
+  part[(size_t)blockIdx.y * rp + a] = (s0 + s1) + (s2 + s3);
+}
+
+__global__ void gemvT_reduce_kernel(int r, int rp, int splits, const double* __restrict__ part,
+                                    const double* __restrict__ scale, double* __restrict__ out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= r) return;
+  double s = 0.0;
+  for (int k = 0; k < splits; ++k) s += part[(size_t)k * rp + a];
+  out[a] = scale ? scale[a] * s : s;
+}
+
+__global__ void __launch_bounds__(256) dense_matvec_kernel(int r, const double* __restrict__ A, int ld,
+                                                           const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (row >= r) return;
+  const double* p = A + (size_t)row * ld;
+  double s = 0.0;
+  for (int b = lane; b < r; b += 32) s = fma(p[b], x[b], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) y[row] = s;
+}
+
+__global__ void transpose_kernel(int n, const double* __restrict__ A, int lda, double* __restrict__ B, int ldb) {
+  __shared__ double tile[32][33];
+  const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (x < n && y0 + j < n) tile[j][threadIdx.x] = A[(size_t)(y0 + j) * lda + x];
+  __syncthreads();
+  const int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (xo < n && yo0 + j < n) B[(size_t)(yo0 + j) * ldb + xo] = tile[threadIdx.x][j];
+}
+
+__global__ void slab_transpose_kernel(int rows, int nc, const double* __restrict__ tmp, double* __restrict__ dst,
+                                      int ld_dst) {
+  __shared__ double tile[32][33];
+  const int k = blockIdx.x * 32 + threadIdx.x;  // row of Phi (contiguous in tmp)
+  const int j0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (k < rows && j0 + j < nc) tile[j][threadIdx.x] = tmp[(size_t)(j0 + j) * rows + k];
+  __syncthreads();
+  const int jo = j0 + threadIdx.x, k0 = blockIdx.x * 32;
+  for (int q = threadIdx.y; q < 32; q += 8)
+    if (jo < nc && k0 + q < rows) dst[(size_t)(k0 + q) * ld_dst + jo] = tile[threadIdx.x][q];
+}
+
+__global__ void build_regression_system_kernel(int r, int rp, const double* __restrict__ S, double eps,
+                                               double* __restrict__ B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = blockIdx.y;
+  if (b >= rp) return;
+  B[(size_t)a * rp + b] = (b < r ? S[(size_t)a * rp + b] : 0.0) + (a == b ? eps : 0.0);
+  B[(size_t)(r + a) * rp + b] = a == b ? 1.0 : 0.0;
+}
+
+__global__ void add_vectors_kernel(int n, const double* __restrict__ a, const double* __restrict__ b,
+                                   double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+int32_t slab_transpose_enqueue(gingr_ctx* ctx, int rows, int nc, const double* d_tmp, double* d_dst, int ld_dst) {
+  slab_transpose_kernel<<<dim3(ceil_div(rows, 32), ceil_div(nc, 32)), dim3(32, 8), 0, ctx->stream>>>(rows, nc, d_tmp,
+                                                                                                     d_dst, ld_dst);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+int32_t build_regression_system_enqueue(gingr_ctx* ctx, int r, int rp, const double* d_S, double eps, double* d_B) {
+  build_regression_system_kernel<<<dim3(ceil_div(rp, 256), r), 256, 0, ctx->stream>>>(r, rp, d_S, eps, d_B);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+int32_t add_vectors_enqueue(gingr_ctx* ctx, int n, const double* d_a, const double* d_b, double* d_out) {
+  add_vectors_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, d_a, d_b, d_out);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int32_t gemv_rows_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_phi, int nvec, const double* d_v0,
+                          const double* d_v1, double* d_out0, double* d_out1) {
+  if (rows <= 0) return GINGR_OK;
+  const int blocks = std::max(1, std::min(ctx->num_sms * 4, ceil_div(rows, 8)));
+  const size_t smem = (size_t)nvec * r * sizeof(double);
+  if (smem > 48 * 1024) {
+    static bool set1 = false, set2 = false;
+    if (nvec == 1 && !set1) {
+      GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      set1 = true;
+    }
+    if (nvec == 2 && !set2) {
+      GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(gemv_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      set2 = true;
+    }
+    if (smem > 200 * 1024) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "rank too large for gemv_rows shared memory");
+  }
+  if (nvec == 1)
+    gemv_rows_kernel<1><<<blocks, 256, smem, ctx->stream>>>(rows, r, rp, d_phi, d_v0, d_v0, d_out0, d_out0);
+  else
+    gemv_rows_kernel<2><<<blocks, 256, smem, ctx->stream>>>(rows, r, rp, d_phi, d_v0, d_v1, d_out0, d_out1);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+int gemvT_splits(const gingr_ctx* ctx, int rows) {
+  (void)ctx;
+  return std::max(1, ceil_div(rows, GT_ROWS));
+}
+
+int32_t gemvT_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_phi, const double* d_u,
+                      const double* d_scale, double* d_part, double* d_out) {
+  const int splits = gemvT_splits(ctx, rows);
+  if (rows > 0) {
+    gemvT_kernel<<<dim3(ceil_div(rp, 256), splits), 256, 0, ctx->stream>>>(rows, rp, d_phi, d_u, d_part);
+    GINGR_LAUNCHED(ctx);
+  } else {
+    GINGR_CUDA_TRY(ctx, cudaMemsetAsync(d_part, 0, sizeof(double) * rp, ctx->stream));
+  }
+  gemvT_reduce_kernel<<<ceil_div(r, 256), 256, 0, ctx->stream>>>(r, rp, splits, d_part, d_scale, d_out);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+int32_t dense_matvec_enqueue(gingr_ctx* ctx, int r, const double* d_A, int ld, const double* d_x, double* d_y) {
+  dense_matvec_kernel<<<ceil_div(r * 32, 256), 256, 0, ctx->stream>>>(r, d_A, ld, d_x, d_y);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+int32_t transpose_enqueue(gingr_ctx* ctx, int n, const double* d_A, int lda, double* d_B, int ldb) {
+  transpose_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32)), dim3(32, 8), 0, ctx->stream>>>(n, d_A, lda, d_B, ldb);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+}  // namespace gingr

@@ -1,0 +1,230 @@
+"""Full-iteration parity: gingr_update through the C ABI against the oracle's literal restatement of
+GingrAlgorithm.update, per iteration and after a whole run.  Tolerances (north-star): coefficients and fitted
+vertices 1e-6 relative (coefficients relative to |alpha|_inf, vertices to the bounding-box diagonal), sigma2
+1e-6 relative, status codes equal."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(oracle, M, N, r, seed, with_tri=True):
+    from gingr_b200 import synthetic
+    ref, tri = synthetic.sphere_mesh(M)
+    mean, basis, var = synthetic.make_gpmm(ref, r, seed + 1)
+    tv, tt = synthetic.sphere_mesh(N)
+    target = synthetic.make_target(tv, seed)
+    return oracle.Gpmm(ref, mean, basis, var, tri), target, tt
+
+
+def _to_api_state(ost, api):
+    p = ost.params
+    return api.GeneralRegistrationState(
+        api.ModelFittingParameters(p.scale, np.asarray(p.translation, float), tuple(p.euler), p.shape.copy()),
+        ost.fit.copy(), ost.sigma2, ost.global_transformation, ost.step_length, "", ost.iteration, ost.status)
+
+
+def _compare(gst, ost, diag, tol=1e-6):
+    a_scale = max(np.max(np.abs(ost.params.shape)), 1e-12)
+    assert np.max(np.abs(gst.modelParameters.shape - ost.params.shape)) < tol * a_scale
+    assert np.max(np.abs(gst.fit - ost.fit)) < tol * diag
+    assert abs(gst.sigma2 - ost.sigma2) <= tol * abs(ost.sigma2)
+    assert np.max(np.abs(np.asarray(gst.modelParameters.translation) - ost.params.translation)) < tol * diag
+    assert np.max(np.abs(np.asarray(gst.modelParameters.euler) - np.asarray(ost.params.euler))) < tol
+    assert abs(gst.modelParameters.scale - ost.params.scale) < tol
+    assert gst.status == ost.status and gst.iteration == ost.iteration
+
+
+@pytest.mark.parametrize("gt", ["none", "rigid", "similarity"])
+@pytest.mark.parametrize("w", [0.0, 0.1])
+def test_cpd_iterations_match_oracle(ctx, oracle, gt, w):
+    from gingr_b200 import api
+    gtc = {"none": oracle.NO_TRANSFORMS, "rigid": oracle.RIGID_TRANSFORMS, "similarity": oracle.SIMILARITY_TRANSFORMS}[gt]
+    m, target, tt = _problem(oracle, 100, 100, 50, seed=0)
+    diag = np.linalg.norm(m.ref.max(0) - m.ref.min(0))
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    cfg = api.CpdConfiguration(maxIterations=100, w=w)
+    reg = api.CpdRegistration(ctx, dm, dt, cfg)
+    oalgo = oracle.CpdAlgorithm(oracle.CpdConfig(max_iterations=100, w=w))
+    ost = oalgo.initialize(oracle.initial_state(m, target, tt, global_transformation=gtc))
+    gst = reg.initializeState(globalTransformation=gtc)
+    assert abs(gst.sigma2 - ost.sigma2) < 1e-12 * ost.sigma2
+    assert np.max(np.abs(gst.fit - ost.fit)) < 1e-10
+    for it in range(6):
+        # feed the oracle's state to the GPU each iteration (per-iteration parity, no drift accumulation)
+        gst = reg.propose(_to_api_state(ost, api))
+        ost = oracle.propose(oalgo, ost)
+        _compare(gst, ost, diag)
+    reg.close()
+
+
+def test_cpd_chained_run_matches_oracle(ctx, oracle):
+    """A whole deterministic run (GingrAlgorithm.run): maxIterations - 1 proposals, states chained on each side."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 100, 100, 50, seed=1)
+    diag = np.linalg.norm(m.ref.max(0) - m.ref.min(0))
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    reg = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration(maxIterations=30))
+    oalgo = oracle.CpdAlgorithm(oracle.CpdConfig(max_iterations=30))
+    ofinal = oracle.run(oalgo, oracle.initial_state(m, target, tt, global_transformation=oracle.RIGID_TRANSFORMS))
+    gfinal = reg.run(reg.initializeState(globalTransformation=api.RIGID_TRANSFORMS))
+    _compare(gfinal, ofinal, diag, tol=1e-6)
+    assert gfinal.iteration == 29 and gfinal.status == api.STATUS_MAX_ITERATION
+    # device-resident chaining gives the same end state as host round trips
+    st0 = reg.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
+    reg.updateChain(29)
+    chained = reg.downloadState()
+    assert np.max(np.abs(chained.fit - gfinal.fit)) < 1e-9 * diag
+    assert chained.iteration == 29
+    reg.close()
+
+
+def test_cpd_democpd_setting(ctx, oracle):
+    """DemoCPD.scala:21-23: initialSigma = 1, NoTransforms, femur-like scale: kernel values down to 1e-150."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 100, 100, 50, seed=2)
+    diag = np.linalg.norm(m.ref.max(0) - m.ref.min(0))
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    reg = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration(maxIterations=100, initialSigma=1.0))
+    oalgo = oracle.CpdAlgorithm(oracle.CpdConfig(max_iterations=100, initial_sigma=1.0))
+    ost = oalgo.initialize(oracle.initial_state(m, target, tt, global_transformation=oracle.NO_TRANSFORMS))
+    gst = reg.initializeState(globalTransformation=api.NO_TRANSFORMS)
+    assert gst.sigma2 == 1.0
+    for it in range(5):
+        gst = reg.propose(_to_api_state(ost, api))
+        ost = oracle.propose(oalgo, ost)
+        assert gst.status == ost.status
+        if ost.status == oracle.STATUS_NONE:
+            _compare(gst, ost, diag)
+    reg.close()
+
+
+def test_cpd_with_landmarks(ctx, oracle):
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 120, 140, 40, seed=3)
+    diag = np.linalg.norm(m.ref.max(0) - m.ref.min(0))
+    rng = np.random.default_rng(4)
+    lm_pid = np.array([3, 40, 77, 111], dtype=np.int32)
+    lm_pts = m.ref[lm_pid] + rng.normal(scale=2.0, size=(4, 3)) + 5.0
+    A = rng.normal(size=(4, 3, 3))
+    lm_cov = A @ np.transpose(A, (0, 2, 1)) + np.eye(3)
+    lm_cov[0] = np.eye(3)
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    reg = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration(maxIterations=50, w=0.05))
+    reg.setLandmarks(lm_pid, lm_pts, lm_cov)
+    oalgo = oracle.CpdAlgorithm(oracle.CpdConfig(max_iterations=50, w=0.05))
+    ost = oalgo.initialize(oracle.initial_state(m, target, tt, global_transformation=oracle.RIGID_TRANSFORMS,
+                                                landmarks=oracle.Landmarks(lm_pid, lm_pts, lm_cov)))
+    for it in range(4):
+        gst = reg.propose(_to_api_state(ost, api))
+        ost = oracle.propose(oalgo, ost)
+        _compare(gst, ost, diag)
+    reg.close()
+
+
+def test_cpd_step_length_and_initial_pose(ctx, oracle):
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 90, 110, 30, seed=5)
+    diag = np.linalg.norm(m.ref.max(0) - m.ref.min(0))
+    R0, t0 = oracle.euler_to_matrix(0.05, -0.03, 0.02), np.array([2.0, -1.0, 3.0])
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    reg = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration())
+    oalgo = oracle.CpdAlgorithm(oracle.CpdConfig())
+    ost = oalgo.initialize(oracle.initial_state(m, target, tt, global_transformation=oracle.RIGID_TRANSFORMS, R0=R0, t0=t0))
+    ost = dataclasses.replace(ost, step_length=0.5)
+    gst0 = reg.initializeState(globalTransformation=api.RIGID_TRANSFORMS, rotation=R0, translation=t0)
+    assert np.max(np.abs(gst0.fit - ost.fit)) < 1e-10
+    for it in range(4):
+        gst = reg.propose(_to_api_state(ost, api))
+        ost = oracle.propose(oalgo, ost)
+        _compare(gst, ost, diag)
+    reg.close()
+
+
+def test_cpd_model_flexibility_error_status(ctx, oracle):
+    """A target point far from every model point with w = 0 and a small sigma2: the column underflows, P has
+    NaNs, the posterior fails; iteration 0 returns the state unchanged, later iterations set
+    ModelFlexibilityError (GingrAlgorithm.scala:194-208)."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 60, 60, 20, seed=6)
+    target = target.copy()
+    target[0] = [5000.0, 0.0, 0.0]
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target)
+    reg = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration(initialSigma=0.5))
+    oalgo = oracle.CpdAlgorithm(oracle.CpdConfig(initial_sigma=0.5))
+    ost = oalgo.initialize(oracle.initial_state(m, target, None, global_transformation=oracle.NO_TRANSFORMS))
+    g1 = reg.propose(_to_api_state(ost, api))
+    o1 = oracle.propose(oalgo, ost)
+    assert o1.status == oracle.STATUS_NONE and g1.status == api.STATUS_NONE          # iteration 0: unchanged
+    assert np.array_equal(g1.modelParameters.shape, ost.params.shape) and g1.iteration == 1
+    g2 = reg.propose(_to_api_state(o1, api))
+    o2 = oracle.propose(oalgo, o1)
+    assert o2.status == oracle.STATUS_MODEL_FLEXIBILITY_ERROR
+    assert g2.status == api.STATUS_MODEL_FLEXIBILITY_ERROR
+    reg.close()
+
+
+@pytest.mark.parametrize("method", ["triangular", "pointcloud"])
+def test_icp_iterations_match_oracle(ctx, oracle, method):
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 200, 260, 40, seed=7)
+    diag = np.linalg.norm(m.ref.max(0) - m.ref.min(0))
+    om = oracle.METHOD_TRIANGULAR if method == "triangular" else oracle.METHOD_POINTCLOUD
+    gm = api.TRIANGULAR_CLOSEST_POINT if method == "triangular" else api.POINTCLOUD_CLOSEST_POINT
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    reg = api.IcpRegistration(ctx, dm, dt, api.IcpConfiguration(maxIterations=100, initialSigma=2.0, endSigma=0.01,
+                                                                correspondenceMethod=gm))
+    oalgo = oracle.IcpAlgorithm(oracle.IcpConfig(max_iterations=100, initial_sigma=2.0, end_sigma=0.01, method=om))
+    ost = oalgo.initialize(oracle.initial_state(m, target, tt, global_transformation=oracle.NO_TRANSFORMS))
+    gst = reg.initializeState(globalTransformation=api.NO_TRANSFORMS)
+    assert gst.sigma2 == 2.0
+    for it in range(5):
+        gst = reg.propose(_to_api_state(ost, api))
+        ost = oracle.propose(oalgo, ost)
+        _compare(gst, ost, diag)
+    reg.close()
+
+
+def test_icp_run_demoicp_setting(ctx, oracle):
+    """DemoICP.scala:22-24: maxIterations = 100 -> 99 updates, sigma2 1 -> 1, NoTransforms."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 100, 100, 50, seed=8)
+    diag = np.linalg.norm(m.ref.max(0) - m.ref.min(0))
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    reg = api.IcpRegistration(ctx, dm, dt, api.IcpConfiguration(maxIterations=100, initialSigma=1.0, endSigma=1.0))
+    oalgo = oracle.IcpAlgorithm(oracle.IcpConfig(max_iterations=100, initial_sigma=1.0, end_sigma=1.0))
+    ofinal = oracle.run(oalgo, oracle.initial_state(m, target, tt, global_transformation=oracle.NO_TRANSFORMS))
+    gfinal = reg.run(reg.initializeState(globalTransformation=api.NO_TRANSFORMS))
+    assert gfinal.iteration == 99 and ofinal.iteration == 99
+    _compare(gfinal, ofinal, diag, tol=1e-6)
+    reg.close()
+
+
+def test_update_resumes_from_device_state(ctx, oracle):
+    """Feeding back exactly the state the previous call returned reuses the device-resident fit; feeding
+    anything else re-seeds from (alpha, pose, sigma2).  Both give the same result."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 80, 90, 25, seed=9)
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    reg = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration())
+    s0 = reg.initializeState()
+    s1 = reg.propose(s0)
+    s2 = reg.propose(s1)                       # resumed
+    reg2 = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration())
+    t2 = reg2.propose(dataclasses.replace(s1))  # fresh handle: re-seeded
+    assert np.array_equal(s2.fit, t2.fit) and np.array_equal(s2.modelParameters.shape, t2.modelParameters.shape)
+    reg.close()
+    reg2.close()
