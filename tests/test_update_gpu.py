@@ -75,13 +75,14 @@ def test_cpd_chained_run_matches_oracle(ctx, oracle):
     ofinal = oracle.run(oalgo, oracle.initial_state(m, target, tt, global_transformation=oracle.RIGID_TRANSFORMS))
     gfinal = reg.run(reg.initializeState(globalTransformation=api.RIGID_TRANSFORMS))
     _compare(gfinal, ofinal, diag, tol=1e-6)
-    assert gfinal.iteration == 29 and gfinal.status == api.STATUS_MAX_ITERATION
+    assert gfinal.iteration == ofinal.iteration and gfinal.status == ofinal.status
+    assert gfinal.status in (api.STATUS_MAX_ITERATION, api.STATUS_CONVERGED)
     # device-resident chaining gives the same end state as host round trips
     st0 = reg.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
-    reg.updateChain(29)
+    reg.updateChain(gfinal.iteration)
     chained = reg.downloadState()
     assert np.max(np.abs(chained.fit - gfinal.fit)) < 1e-9 * diag
-    assert chained.iteration == 29
+    assert chained.iteration == gfinal.iteration
     reg.close()
 
 
