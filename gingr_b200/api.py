@@ -441,6 +441,17 @@ class GingrAlgorithm:
         return GeneralRegistrationState.from_pod(st, alpha, fit)
 
 
+    def setProfiling(self, enable: bool):
+        self.ctx.check(self.ctx._lib.gingr_registration_set_profiling(self.handle, int(enable)))
+
+    def getProfile(self):
+        """(ms[8] summed over `iterations`, iterations) since the last call; see include/gingr_cuda.h."""
+        ms = np.zeros(8)
+        it = ctypes.c_int32()
+        self.ctx.check(self.ctx._lib.gingr_registration_get_profile(self.handle, nat.as_dp(ms), ctypes.byref(it)))
+        return ms, int(it.value)
+
+
 class CpdRegistration(GingrAlgorithm):
     """registration/config/CPD.scala:117-160"""
     name = "CPD"

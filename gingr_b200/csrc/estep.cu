@@ -332,18 +332,23 @@ void EstepWorkspace::release() {
 
 // Enqueue the E-step on ctx->stream.  fit_soa / rowf (may be null) / scal must be set up by the caller:
 // scal[0] = sigma2, scal[1] = a, scal[2] = c.  Results: ws.pt1 [N], ws.rows [4][M], ws.xpx_part.
-int32_t estep_enqueue(gingr_ctx* ctx, EstepWorkspace& ws, int M, int N, const double* target_soa, bool use_rowf) {
+int32_t estep_enqueue(gingr_ctx* ctx, EstepWorkspace& ws, int M, int N, const double* target_soa, bool use_rowf,
+                      const EstepEvents* ev) {
   const EstepPlan& p = ws.plan;
   const double* rowf = use_rowf ? ws.rowf.p : nullptr;
   cudaStream_t st = ctx->stream;
+  if (ev) cudaEventRecord(ev->a0, st);
   estep_colsum_kernel<<<dim3(p.col_blocks, p.row_splits), TPB, 0, st>>>(M, N, ws.fit_soa.p, rowf, target_soa,
                                                                         ws.scal.p, ws.colpart.p);
+  if (ev) cudaEventRecord(ev->a1, st);
   GINGR_LAUNCHED(ctx);
   estep_den_kernel<<<p.den_blocks, TPB, 0, st>>>(N, p.row_splits, ws.colpart.p, target_soa, ws.scal.p, ws.pack.p,
                                                  ws.pt1.p, ws.xpx_part.p);
   GINGR_LAUNCHED(ctx);
+  if (ev) cudaEventRecord(ev->b0, st);
   estep_rowsum_kernel<<<dim3(p.row_blocks, p.col_splits), TPB, 0, st>>>(M, N, ws.fit_soa.p, ws.pack.p, ws.scal.p,
                                                                         ws.rowpart.p);
+  if (ev) cudaEventRecord(ev->b1, st);
   GINGR_LAUNCHED(ctx);
   estep_rowreduce_kernel<<<ceil_div(M, TPB), TPB, 0, st>>>(M, p.col_splits, ws.rowpart.p, rowf, ws.rows.p);
   GINGR_LAUNCHED(ctx);

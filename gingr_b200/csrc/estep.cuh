@@ -26,7 +26,11 @@ struct EstepWorkspace {
 };
 
 void estep_plan(const gingr_ctx* ctx, int M, int N, EstepPlan* p);
-int32_t estep_enqueue(gingr_ctx* ctx, EstepWorkspace& ws, int M, int N, const double* target_soa, bool use_rowf);
+struct EstepEvents {
+  cudaEvent_t a0, a1, b0, b1;  // around the sweep A and sweep B kernels
+};
+int32_t estep_enqueue(gingr_ctx* ctx, EstepWorkspace& ws, int M, int N, const double* target_soa, bool use_rowf,
+                      const EstepEvents* ev = nullptr);
 int32_t aos_to_soa_enqueue(gingr_ctx* ctx, int n, const double* d_aos, double* d_soa);
 int32_t estep_cpd_scalars_enqueue(gingr_ctx* ctx, double* d_scal);
 int32_t estep_bcpd_rowf_enqueue(gingr_ctx* ctx, int M, const double* d_sigma_mm, const double* d_alpha,

@@ -262,7 +262,9 @@ void GramPlan::release() {
 }
 
 // partial tiles of G = Phi^T diag(wrow) Phi  (wrow may be null)
-int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_phi, const double* d_wrow) {
+int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_phi, const double* d_wrow,
+                              cudaEvent_t ev0, cudaEvent_t ev1) {
+  if (ev0) cudaEventRecord(ev0, ctx->stream);
   if (plan.rows > 0) {
     gram_streamk_kernel<<<plan.ncta, GRAM_THREADS, GRAM_SMEM, ctx->stream>>>(
         plan.rows, plan.rp, d_phi, d_wrow, reinterpret_cast<const GramSegment*>(plan.d_segs.p), plan.d_seg_begin.p,
@@ -272,6 +274,7 @@ int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_ph
   } else {
     GINGR_CUDA_TRY(ctx, cudaMemsetAsync(plan.d_partial.p, 0, plan.d_partial.n * sizeof(double), ctx->stream));
   }
+  if (ev1) cudaEventRecord(ev1, ctx->stream);
   return GINGR_OK;
 }
 

@@ -15,7 +15,8 @@ struct GramPlan {
   int32_t build(gingr_ctx* ctx, int rows, int r, int rp);
   void release();
 };
-int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_phi, const double* d_wrow);
+int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_phi, const double* d_wrow,
+                              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_partial, const double* d_sqrt_lambda,
                             double add_identity, int L, const double* d_lm_rows, const double* d_lm_A, int ld_out,
                             double* d_out);

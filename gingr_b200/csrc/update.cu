@@ -522,6 +522,13 @@ struct gingr_registration {
   bool state_valid = false;
   gingr_state last_out;
   std::vector<double> last_alpha;
+  // profiling: per recorded iteration 14 events
+  bool profiling = false;
+  std::vector<cudaEvent_t> events;
+  int prof_iters = 0;
+  static constexpr int EV_PER_ITER = 14, EV_MAX_ITERS = 256;
+  cudaEvent_t* ev(int k) { return profiling && prof_iters < EV_MAX_ITERS ? &events[(size_t)prof_iters * EV_PER_ITER + k] : nullptr; }
+  void rec(int k) { if (cudaEvent_t* e = ev(k)) cudaEventRecord(*e, ctx->stream); }
 };
 
 static int32_t model_build_constants(gingr_ctx* ctx, gingr_model* m);
@@ -965,6 +972,7 @@ int32_t gingr_registration_destroy(gingr_registration* g) {
   g->newshape.release(); g->fit_local.release(); g->gathered.release(); g->fit.release(); g->vec.release();
   g->gt_part.release(); g->sums_part.release(); g->pro_part.release(); g->pro_sums.release();
   g->ds.release(); g->is.release(); g->flags.release(); g->alpha.release();
+  for (auto& e : g->events) cudaEventDestroy(e);
   delete g;
   return GINGR_OK;
 }
@@ -1072,6 +1080,8 @@ static int32_t enqueue_iteration(gingr_registration* g) {
   const int M = m->M, r = m->r, rp = m->rp, Ml = m->Ml, m0 = m->m0;
   cudaStream_t st = ctx->stream;
   double* vec = g->vec.p;  // [0] c_post  [1] S c  [2] alpha*  [3] alpha_c  [4] q  [5] alpha_new  [6,7] scaled scratch
+  // events: 0/1 iteration, 2..5 E-step sweeps, 6/7 Gram, 8/9 Cholesky + back solve, 10/11 closest point, 12/13 unused
+  g->rec(0);
   pose_kernel<<<1, 1, 0, st>>>(g->ds.p, g->is.p);
   GINGR_LAUNCHED(ctx);
   // ---- correspondence -------------------------------------------------------------------------------
@@ -1080,7 +1090,10 @@ static int32_t enqueue_iteration(gingr_registration* g) {
     cpd_estep_scalars_kernel<<<1, 1, 0, st>>>(g->ds.p, cfg.w, (double)M / (double)tg->N_total, g->estep.scal.p);
     GINGR_LAUNCHED(ctx);
     if (tg->N > 0) {
-      GINGR_TRY(estep_enqueue(ctx, g->estep, M, tg->N, tg->soa.p, false));
+      EstepEvents ee;
+      const bool pe = g->ev(2) != nullptr;
+      if (pe) { ee.a0 = *g->ev(2); ee.a1 = *g->ev(3); ee.b0 = *g->ev(4); ee.b1 = *g->ev(5); }
+      GINGR_TRY(estep_enqueue(ctx, g->estep, M, tg->N, tg->soa.p, false, pe ? &ee : nullptr));
       GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->rows_ext.p, g->estep.rows.p, sizeof(double) * 4 * (size_t)M,
                                           cudaMemcpyDeviceToDevice, st));
       xpx_total_kernel<<<1, 1, 0, st>>>(g->estep.plan.den_blocks, g->estep.xpx_part.p, g->rows_ext.p + (size_t)4 * M);
@@ -1090,8 +1103,10 @@ static int32_t enqueue_iteration(gingr_registration* g) {
     }
     GINGR_TRY(comm_allreduce_sum(ctx, g->rows_ext.p, (size_t)4 * M + 8));
   } else {
+    g->rec(10);
     GINGR_TRY(icp_closest_enqueue(ctx, g->closest, tg, M, g->fit.p, m->T, m->tri.p, m->adj_off.p, m->adj.p,
                                   cfg.correspondence_method));
+    g->rec(11);
   }
   // ---- observations, sigma2 hook ----------------------------------------------------------------------
   ObsArgs oa;
@@ -1115,12 +1130,15 @@ static int32_t enqueue_iteration(gingr_registration* g) {
                                                           m->ref.p, m->mean.p, m->sqrt_lambda.p, g->ds.p, rhs);
     ctx->launches += 2;
   }
-  GINGR_TRY(gram_partials_enqueue(ctx, g->gram, m->phi.p, g->wrow.p));
+  GINGR_TRY(gram_partials_enqueue(ctx, g->gram, m->phi.p, g->wrow.p, g->ev(6) ? *g->ev(6) : nullptr,
+                                  g->ev(7) ? *g->ev(7) : nullptr));
   GINGR_TRY(gram_finish_enqueue(ctx, g->gram, g->gram.d_partial.p, m->sqrt_lambda.p, ctx->rank == 0 ? 1.0 : 0.0,
                                 use_lm ? g->Ll : 0, g->lml_rows.p, g->lml_A.p, rp, g->Mx.p));
   GINGR_TRY(comm_allreduce_sum(ctx, g->Mx.p, (size_t)(r + 1) * rp));
+  g->rec(8);
   GINGR_TRY(cholesky_enqueue(ctx, r, r + 1, g->Mx.p, rp, g->is.p + IS_INFO));
   GINGR_TRY(chol_backsolve_enqueue(ctx, r, g->Mx.p, rp, rhs, vec, g->flags.p));
+  g->rec(9);
   check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, vec, g->is.p + IS_FAIL_POST);
   GINGR_LAUNCHED(ctx);
   // ---- alpha* = coefficients(posterior mean) = W0 S c ; combine ---------------------------------------------
@@ -1158,6 +1176,8 @@ static int32_t enqueue_iteration(gingr_registration* g) {
   finalize_kernel<<<1, 256, 0, st>>>(r, vec + 5 * rp, g->alpha.p, g->ds.p, g->is.p);
   GINGR_LAUNCHED(ctx);
   GINGR_TRY(evaluate_fit(g, DS_SCALE, DS_T, DS_R2));
+  g->rec(1);
+  if (g->profiling && g->prof_iters < gingr_registration::EV_MAX_ITERS) g->prof_iters++;
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
 }
@@ -1267,6 +1287,42 @@ int32_t gingr_update_chain(gingr_registration* g, int32_t iters) {
     bump_iteration_kernel<<<1, 1, 0, ctx->stream>>>(g->is.p);  // GingrGeneratorWrapper.propose: updateIteration()
     GINGR_LAUNCHED(ctx);
   }
+  return GINGR_OK;
+}
+
+int32_t gingr_registration_set_profiling(gingr_registration* g, int32_t enable) {
+  if (!g) return GINGR_ERR_ARG;
+  gingr_ctx* ctx = g->ctx;
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (enable && g->events.empty()) {
+    g->events.resize((size_t)gingr_registration::EV_PER_ITER * gingr_registration::EV_MAX_ITERS);
+    for (auto& e : g->events) GINGR_CUDA_TRY(ctx, cudaEventCreate(&e));
+  }
+  g->profiling = enable != 0;
+  g->prof_iters = 0;
+  return GINGR_OK;
+}
+
+int32_t gingr_registration_get_profile(gingr_registration* g, double* ms, int32_t* iterations) {
+  if (!g || !ms || !iterations) return GINGR_ERR_ARG;
+  gingr_ctx* ctx = g->ctx;
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 8; ++k) ms[k] = 0.0;
+  const bool cpd = g->cfg.algorithm == GINGR_ALGO_CPD && g->target->N > 0;
+  for (int it = 0; it < g->prof_iters; ++it) {
+    cudaEvent_t* e = &g->events[(size_t)it * gingr_registration::EV_PER_ITER];
+    float t = 0.f;
+    auto el = [&](int a, int b) { t = 0.f; cudaEventElapsedTime(&t, e[a], e[b]); return (double)t; };
+    if (cpd) { ms[0] += el(2, 3); ms[1] += el(4, 5); } else if (g->cfg.algorithm == GINGR_ALGO_ICP) { ms[5] += el(10, 11); }
+    ms[2] += el(6, 7);
+    ms[3] += el(8, 9);
+    ms[4] += el(0, 1);
+  }
+  *iterations = g->prof_iters;
+  g->prof_iters = 0;
+  cudaGetLastError();
   return GINGR_OK;
 }
 
