@@ -118,6 +118,8 @@ int32_t gingr_target_upload(gingr_ctx* ctx, int32_t N, const double* pts, const 
   gingr_target* t = new gingr_target();
   t->ctx = ctx;
   t->N_total = N;
+  for (size_t k = 0; k < (size_t)3 * N; ++k)
+    if (!(fabs(pts[k]) < INFINITY)) { t->nonfinite = true; break; }
   shard_range(N, ctx->nranks, ctx->rank, &t->n0, &t->N);
   // full vertex set (SoA) -- the ICP search and the single-GPU E-step use it; the E-step shard is a view
   // into a separately packed SoA when sharded.
@@ -161,6 +163,17 @@ int32_t gingr_target_destroy(gingr_target* t) {
 // ---------------------------------------------------------------------------------------------
 // K1 entry points
 // ---------------------------------------------------------------------------------------------
+static bool host_nonfinite(const double* v, size_t n) {
+  for (size_t k = 0; k < n; ++k)
+    if (!(fabs(v[k]) < INFINITY)) return true;
+  return false;
+}
+
+static void fill_nan(double* p, size_t n) {
+  if (p)
+    for (size_t k = 0; k < n; ++k) p[k] = NAN;
+}
+
 static int32_t estep_common(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* fit,
                             gingr::EstepWorkspace** ws_out) {
   CtxScratch* s = scratch_of(ctx);
@@ -197,6 +210,11 @@ static int32_t estep_download(gingr_ctx* ctx, gingr::EstepWorkspace* ws, int M, 
 int32_t gingr_cpd_estep(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* fit, double sigma2,
                         double w, double* P1, double* Pt1, double* PX) {
   if (!ctx || !target || !fit || M <= 0) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_cpd_estep: bad argument");
+  if (target->nonfinite || host_nonfinite(fit, (size_t)3 * M) || !(fabs(sigma2) < INFINITY)) {
+    // a NaN coordinate makes every entry of the reference's P NaN (CPD.scala:54-75)
+    fill_nan(P1, M); fill_nan(Pt1, target->N); fill_nan(PX, (size_t)3 * M);
+    return GINGR_OK;
+  }
   gingr::EstepWorkspace* ws = nullptr;
   GINGR_TRY(estep_common(ctx, target, M, fit, &ws));
   double* h = ctx->h_pinned;
@@ -216,6 +234,11 @@ int32_t gingr_bcpd_estep(gingr_ctx* ctx, const gingr_target* target, int32_t M, 
                          double* nu_prime, double* n_hat, double* x_hat) {
   if (!ctx || !target || !y || !sigma_mm || !alpha || M <= 0)
     return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_bcpd_estep: bad argument");
+  if (target->nonfinite || host_nonfinite(y, (size_t)3 * M) || host_nonfinite(sigma_mm, M) || host_nonfinite(alpha, M) ||
+      !(fabs(sigma2) < INFINITY)) {
+    fill_nan(nu, M); fill_nan(nu_prime, target->N); fill_nan(n_hat, 1); fill_nan(x_hat, (size_t)3 * M);
+    return GINGR_OK;
+  }
   gingr::EstepWorkspace* ws = nullptr;
   GINGR_TRY(estep_common(ctx, target, M, y, &ws));
   CtxScratch* sc = scratch_of(ctx);

@@ -19,70 +19,70 @@ namespace gingr {
 
 constexpr int NB = 64;
 constexpr int SP = NB + 1;  // shared pitch for the scalar kernels
-constexpr size_t PANEL_SMEM = 2 * NB * SP * sizeof(double);
+constexpr size_t PANEL_SMEM = (3 * NB * SP + NB) * sizeof(double);
 
 // ---------------------------------------------------------------------------------------------
-// panel: diagonal block factorisation + triangular solve of the rows below
+// panel: diagonal block factorisation + triangular solve of the rows below, fused in ONE loop over the 64
+// columns with a single barrier per column.  At step j (pivot d = D[j][j], still unscaled):
+//   L[i][j] = D[i][j] / sqrt(d)            (final, stored transposed in the unused upper triangle of sD)
+//   X[r][j] = X[r][j] / sqrt(d)            (final, stored in sXo)
+//   D[i][k] -= (D[i][j] / d) D[k][j]       trailing block, k > j        (right-looking, unscaled column j)
+//   X[r][c] -= (X[r][j] / d) D[c][j]       panel rows, c > j
+// Column j of sD / sX is only read in step j and never written afterwards, so no second barrier is needed.
+// Thread layout: tx = tid & 63 (column / row index), ty = tid >> 6 (4 row groups): no integer division.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) chol_panel_kernel(int nrows, int j0, int jb, double* __restrict__ A, int ld,
                                                          int* __restrict__ info) {
   extern __shared__ __align__(16) double psm[];
-  double* sD = psm;
-  double* sX = psm + NB * SP;
-  const int tid = threadIdx.x;
-  // load the diagonal block (lower part; upper set to 0)
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e / NB, k = e % NB;
-    sD[i * SP + k] = (i < jb && k <= i) ? A[(size_t)(j0 + i) * ld + j0 + k] : (i == k ? 1.0 : 0.0);
-  }
-  bool bad = false;
-  for (int j = 0; j < jb; ++j) {
-    __syncthreads();
-    const double d = sD[j * SP + j];
-    if (!(d > 0.0) || !(d < INFINITY)) bad = true;
-    const double djj = sqrt(d);
-    __syncthreads();
-    if (tid == 0) sD[j * SP + j] = djj;
-    if (tid > j && tid < jb) sD[tid * SP + j] /= djj;
-    __syncthreads();
-    // trailing rank-1 update of the lower part: rows i in (j, jb), cols k in (j, i]
-    const int m = jb - j - 1;
-    for (int e = tid; e < m * m; e += 256) {
-      const int i = j + 1 + e / m, k = j + 1 + e % m;
-      if (k <= i) sD[i * SP + k] -= sD[i * SP + j] * sD[k * SP + j];
-    }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    if (bad && tid == 0) info[0] = 1;
-    for (int e = tid; e < jb * jb; e += 256) {
-      const int i = e / jb, k = e % jb;
-      if (k <= i) A[(size_t)(j0 + i) * ld + j0 + k] = sD[i * SP + k];
-    }
-  }
-  // rows of this CTA
+  double* sD = psm;                  // [64][65] working diagonal block (lower) / final L^T (upper)
+  double* sX = psm + NB * SP;        // [64][65] working panel rows
+  double* sXo = psm + 2 * NB * SP;   // [64][65] final panel rows
+  double* sDiag = psm + 3 * NB * SP; // [64] final diagonal
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
   const int i0 = j0 + jb + blockIdx.x * NB;
-  const int cnt = min(NB, nrows - i0);
-  if (cnt <= 0) return;
+  const int cnt = max(0, min(NB, nrows - i0));
   for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e / NB, k = e % NB;
+    const int i = e >> 6, k = e & 63;
+    sD[i * SP + k] = (i < jb && k <= i) ? A[(size_t)(j0 + i) * ld + j0 + k] : (i == k ? 1.0 : 0.0);
     sX[i * SP + k] = (i < cnt && k < jb) ? A[(size_t)(i0 + i) * ld + j0 + k] : 0.0;
   }
   __syncthreads();
-  // X <- X D^-T : column c of X is final after dividing by D[c][c]; then eliminate it from later columns
-  for (int c = 0; c < jb; ++c) {
-    if (tid < NB) sX[tid * SP + c] /= sD[c * SP + c];
-    __syncthreads();
-    const int m = jb - c - 1;
-    for (int e = tid; e < NB * m; e += 256) {
-      const int i = e / m, cc = c + 1 + e % m;
-      sX[i * SP + cc] -= sX[i * SP + c] * sD[cc * SP + c];
+  bool bad = false;
+  for (int j = 0; j < jb; ++j) {
+    const double d = sD[j * SP + j];
+    if (!(d > 0.0) || !(d < INFINITY)) bad = true;
+    const double djj = sqrt(d);
+    const double inv = 1.0 / d;
+    if (ty == 0) {
+      if (tx == j) sDiag[j] = djj;
+      else if (tx > j && tx < jb) sD[j * SP + tx] = sD[tx * SP + j] / djj;  // transposed slot (upper triangle)
+    } else if (ty == 1) {
+      sXo[tx * SP + j] = sX[tx * SP + j] / djj;
+    }
+    {
+      const int k = j + 1 + tx;
+      if (k < jb) {
+        const double dkj = sD[k * SP + j];
+        for (int i = j + 1 + ty; i < jb; i += 4)
+          if (k <= i) sD[i * SP + k] -= (sD[i * SP + j] * inv) * dkj;
+      }
+    }
+    {
+      const double xs = sX[tx * SP + j] * inv;
+      for (int cc = j + 1 + ty; cc < jb; cc += 4) sX[tx * SP + cc] -= xs * sD[cc * SP + j];
     }
     __syncthreads();
   }
-  for (int e = tid; e < cnt * jb; e += 256) {
-    const int i = e / jb, k = e % jb;
-    A[(size_t)(i0 + i) * ld + j0 + k] = sX[i * SP + k];
+  if (blockIdx.x == 0) {
+    if (bad && tid == 0) info[0] = 1;
+    for (int e = tid; e < NB * NB; e += 256) {
+      const int i = e >> 6, k = e & 63;
+      if (i < jb && k <= i) A[(size_t)(j0 + i) * ld + j0 + k] = (i == k) ? sDiag[i] : sD[k * SP + i];
+    }
+  }
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e >> 6, k = e & 63;
+    if (i < cnt && k < jb) A[(size_t)(i0 + i) * ld + j0 + k] = sXo[i * SP + k];
   }
 }
 
@@ -153,12 +153,16 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(int nrows, int n, int j0
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward substitution  L^T c = z,  one CTA per 64-block, blocks become ready from the last one up
+// backward substitution  L^T c = z,  one CTA per 64-block, blocks become ready from the last one up.
+// Each CTA first inverts its own diagonal block (off the critical path: it would otherwise spin on the
+// ready flags), accumulates  z_k - sum_{i>k} L_ik^T c_i  as the c_i appear, and finishes with the
+// 64 x 64 product  c_k = D^-T acc.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) chol_backsolve_kernel(int n, const double* __restrict__ L, int ld,
                                                              const double* __restrict__ z, double* __restrict__ c,
                                                              volatile int* __restrict__ flags) {
-  __shared__ double sD[NB * SP];
+  __shared__ double sD[NB * SP];  // lower: D ; strict upper: (D^-1)^T ; diagonal of D^-1 in sZd
+  __shared__ double sZd[NB];
   __shared__ double sc[NB];
   __shared__ double sacc[4][NB];
   __shared__ double acc[NB];
@@ -167,10 +171,31 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(int n, const double
   const int tid = threadIdx.x;
   const int k0 = k * NB, kcnt = min(NB, n - k0);
   for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e / NB, j = e % NB;
+    const int i = e >> 6, j = e & 63;
     sD[i * SP + j] = (i < kcnt && j <= i) ? L[(size_t)(k0 + i) * ld + k0 + j] : (i == j ? 1.0 : 0.0);
   }
   if (tid < NB) acc[tid] = tid < kcnt ? z[k0 + tid] : 0.0;
+  __syncthreads();
+  // Z = D^-1 by columns: thread (col = tid & 63, part = tid >> 6) -- the 4 parts split the inner sums
+  {
+    const int col = tid & 63, part = tid >> 6;
+    // one warp-pair per ... keep it simple: part 0 does the column, sequentially
+    if (part == 0) {
+      // Z[i][col] lives at sD[col][i] (i > col); thread `col` only touches row `col` of the upper triangle
+      const double zcc = 1.0 / sD[col * SP + col];
+      sZd[col] = zcc;
+      for (int i = col + 1; i < NB; ++i) {
+        double s0 = sD[i * SP + col] * zcc, s1 = 0.0;
+        int kk = col + 1;
+        for (; kk + 1 < i; kk += 2) {
+          s0 = fma(sD[i * SP + kk], sD[col * SP + kk], s0);
+          s1 = fma(sD[i * SP + kk + 1], sD[col * SP + kk + 1], s1);
+        }
+        if (kk < i) s0 = fma(sD[i * SP + kk], sD[col * SP + kk], s0);
+        sD[col * SP + i] = -(s0 + s1) / sD[i * SP + i];
+      }
+    }
+  }
   const int col = tid & 63, part = tid >> 6;
   double s = 0.0;
   for (int i = nb - 1; i > k; --i) {
@@ -192,14 +217,14 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(int n, const double
   __syncthreads();
   if (tid < NB) acc[tid] -= (sacc[0][tid] + sacc[1][tid]) + (sacc[2][tid] + sacc[3][tid]);
   __syncthreads();
-  // solve D^T x = acc within the block (D lower): x_j = acc_j / D[j][j]; acc_m -= D[j][m] x_j (m < j)
-  for (int j = kcnt - 1; j >= 0; --j) {
-    if (tid == 0) acc[j] = acc[j] / sD[j * SP + j];
-    __syncthreads();
-    if (tid < j) acc[tid] -= sD[j * SP + tid] * acc[j];
-    __syncthreads();
+  // c_k = D^-T acc :  c[j] = sum_{i >= j} Z[i][j] acc[i]   (4 partial sums per output)
+  {
+    double t = part == 0 ? sZd[col] * acc[col] : 0.0;
+    for (int i = col + 1 + part; i < NB; i += 4) t = fma(sD[col * SP + i], acc[i], t);
+    sacc[part][col] = t;
   }
-  if (tid < kcnt) c[k0 + tid] = acc[tid];
+  __syncthreads();
+  if (tid < kcnt) c[k0 + tid] = (sacc[0][tid] + sacc[1][tid]) + (sacc[2][tid] + sacc[3][tid]);
   __threadfence();
   __syncthreads();
   if (tid == 0) flags[k] = 1;

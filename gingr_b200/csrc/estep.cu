@@ -28,8 +28,8 @@
 namespace gingr {
 
 constexpr int TPB = 256;       // threads per CTA in both sweeps
-constexpr int CA = 2;          // columns per thread, sweep A
-constexpr int RB = 2;          // rows per thread, sweep B
+constexpr int CA = 4;          // columns per thread, sweep A
+constexpr int RB = 4;          // rows per thread, sweep B
 constexpr int TILE_ROWS = 512; // rows staged per shared-memory tile in sweep A
 constexpr int TILE_COLS = 256; // columns staged per shared-memory tile in sweep B
 
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(TPB) estep_colsum_kernel(int M, int N, const d
         double d2 = dx * dx;
         d2 = fma(dy, dy, d2);
         d2 = fma(dz, dz, d2);
-        acc[c] = fma(gauss_exp2(d2, negk), y.w, acc[c]);
+        acc[c] = fma(gauss_exp2_biased(d2, negk), y.w, acc[c]);
       }
     }
   }
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(TPB) estep_colsum_kernel(int M, int N, const d
 }
 
 // ---------------------------------------------------------------------------------------------
-// denominators.  scal[1] = a, scal[2] = c.  pack[j] = {x, y, z, w_j, w_j x, w_j y, w_j z, 0}
+// denominators.  scal[1] = a, scal[2] = c.  pack[j] = {x, y, z, w_j, w_j x, w_j y, w_j z, 0} * {1,1,1,2^-64,...}
 // xpx_part[blockIdx.x] = sum over the block's columns of Pt1_j |x_j|^2  (CPD.scala:142)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) estep_den_kernel(int N, int splits, const double* __restrict__ part,
@@ -101,13 +101,15 @@ __global__ void __launch_bounds__(TPB) estep_den_kernel(int N, int splits, const
   if (j < N) {
     double s = 0.0;
     for (int k = 0; k < splits; ++k) s += part[(size_t)k * N + j];
+    s *= GAUSS_BIAS_UNSCALE;  // the sweeps accumulate 2^64 K (exp2_poly.cuh); exact power-of-two rescale
     const double den = scal[1] * s + scal[2];
     const double w = 1.0 / den;
     const double p = s / den;
     const double x = target[j], y = target[N + j], z = target[2 * N + j];
     double4* o = reinterpret_cast<double4*>(pack + (size_t)j * 8);
-    o[0] = make_double4(x, y, z, w);
-    o[1] = make_double4(w * x, w * y, w * z, 0.0);
+    const double wb = w * GAUSS_BIAS_UNSCALE;  // sweep B multiplies 2^64 K by these
+    o[0] = make_double4(x, y, z, wb);
+    o[1] = make_double4(wb * x, wb * y, wb * z, 0.0);
     pt1[j] = p;
     xpx = p * (x * x + y * y + z * z);
   }
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(TPB) estep_rowsum_kernel(int M, int N, const d
         double d2 = dx * dx;
         d2 = fma(dy, dy, d2);
         d2 = fma(dz, dz, d2);
-        const double k = gauss_exp2(d2, negk);
+        const double k = gauss_exp2_biased(d2, negk);
         a0[q] = fma(k, xa.w, a0[q]);
         a1[q] = fma(k, xb.x, a1[q]);
         a2[q] = fma(k, xb.y, a2[q]);
@@ -196,6 +198,12 @@ __global__ void __launch_bounds__(TPB) estep_rowreduce_kernel(int M, int splits,
     for (int k = 0; k < splits; ++k) s += part[((size_t)k * 4 + q) * M + i];
     out[(size_t)q * M + i] = f * s;
   }
+}
+
+// sets *flag when any of the n doubles is NaN / Inf (the E-step kernels assume finite input, exp2_poly.cuh)
+__global__ void validate_finite_kernel(int n, const double* __restrict__ v, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(fabs(v[i]) < INFINITY)) *flag = 1;
 }
 
 // AoS [n][3] -> SoA [3][n]
@@ -360,6 +368,12 @@ int32_t aos_to_soa_enqueue(gingr_ctx* ctx, int n, const double* d_aos, double* d
   aos_to_soa_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, d_aos, d_soa);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+int32_t validate_finite_enqueue(gingr_ctx* ctx, int n, const double* d_v, int* d_flag) {
+  validate_finite_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, d_v, d_flag);
+  GINGR_LAUNCHED(ctx);
   return GINGR_OK;
 }
 

@@ -31,6 +31,7 @@ struct EstepEvents {
 };
 int32_t estep_enqueue(gingr_ctx* ctx, EstepWorkspace& ws, int M, int N, const double* target_soa, bool use_rowf,
                       const EstepEvents* ev = nullptr);
+int32_t validate_finite_enqueue(gingr_ctx* ctx, int n, const double* d_v, int* d_flag);
 int32_t aos_to_soa_enqueue(gingr_ctx* ctx, int n, const double* d_aos, double* d_soa);
 int32_t estep_cpd_scalars_enqueue(gingr_ctx* ctx, double* d_scal);
 int32_t estep_bcpd_rowf_enqueue(gingr_ctx* ctx, int M, const double* d_sigma_mm, const double* d_alpha,

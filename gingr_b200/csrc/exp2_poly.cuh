@@ -1,15 +1,25 @@
 // exp2_poly.cuh -- FP64 2^x for x <= 0 on the FP64 pipe, used by the E-step kernels.
 //
 // The Gaussian affinity exp(-d2 / (2 sigma2)) (CPD.scala:55-57) is evaluated as 2^(negk * d2) with
-// negk = -log2(e) / (2 sigma2): the scale folds into the range reduction FMA, so no extra multiply.
-//   tmp = fma(d2, negk, 1.5*2^52)   -> low word of tmp = n = rint(negk*d2)
-//   r   = fma(d2, negk, -(tmp - 1.5*2^52))  in [-0.5, 0.5], exact single rounding
+// negk = -log2(e) / (2 sigma2): the scale folds into the range-reduction FMA, so no extra multiply.
+//   tmp = fma(d2, negk, SHIFT)      SHIFT = 1.5*2^52 + 2048  ->  low word of tmp = 2048 + n, n = rint(negk*d2)
+//   r   = fma(d2, negk, -(tmp - SHIFT))      in [-0.5, 0.5], one rounding
 //   2^r = degree-10 minimax polynomial (max relative error 2.1e-16; tools/gen_exp2_poly.py 10 0.5)
-//   result = p * 2^n by exponent-field addition; gradual underflow handled on a rare path.
+//   K'  = p * 2^(n + 64)  by exponent-field addition
+// The value returned is K' = 2^64 * K.  The bias keeps every representable K (down to the smallest subnormal,
+// 2^-1074) in the NORMAL range of K', so gradual underflow needs no special path: n in [-1085, 0] is the fast
+// and only path, anything smaller is exactly 0 (K < 2^-1085 rounds to 0 in the reference as well).  Callers
+// fold the 2^-64 into their column weights (a power of two: exact).  ncu showed each FP64 instruction costs
+// two issue slots on B200 and every other instruction one, so the integer tail is kept to six instructions:
+// two compares, two for the exponent, two selects.  Non-finite inputs are caught by a separate O(M+N)
+// validation pass (a NaN would otherwise select the zero branch).
 // 13 FP64 instructions per evaluation (3 range reduction + 10 Horner FMAs).
 #pragma once
 
 namespace gingr {
+
+constexpr double GAUSS_BIAS_SCALE = 0x1p+64;      // K' = K * 2^64
+constexpr double GAUSS_BIAS_UNSCALE = 0x1p-64;
 
 __device__ __forceinline__ double exp2_poly10(double r) {
   double p = 0x1.e3991ef300b90p-28;
@@ -26,28 +36,20 @@ __device__ __forceinline__ double exp2_poly10(double r) {
   return p;
 }
 
-// 2^(negk * d2) for negk * d2 <= 0 (any magnitude).  NaN propagates.
-__device__ __forceinline__ double gauss_exp2(double d2, double negk) {
-  const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52
+// 2^64 * 2^(negk * d2) for finite negk * d2 <= 0 (any magnitude).
+__device__ __forceinline__ double gauss_exp2_biased(double d2, double negk) {
+  const double SHIFT = 6755399441055744.0 + 2048.0;  // 1.5 * 2^52 + 2048
   const double tmp = fma(d2, negk, SHIFT);
-  const int n = __double2loint(tmp);
-  const int hi = __double2hiint(tmp);
+  const int lo = __double2loint(tmp);   // 2048 + n
+  const int hi = __double2hiint(tmp);   // 0x43380000 exactly while -2048 <= n < 2^32 - 2048
   const double nf = tmp - SHIFT;
   const double r = fma(d2, negk, -nf);
   const double p = exp2_poly10(r);
-  // fast path: -1021 <= n <= 0 and |negk*d2| < 2^32 (hi word of tmp is 0x4337FFFF or 0x43380000, or NaN)
-  const bool in_range = (hi >= 0x4337FFFF) && ((unsigned)(n + 1021) <= 1021u);
-  const int nn = in_range ? n : 0;
-  double res = __hiloint2double(__double2hiint(p) + (nn << 20), __double2loint(p));
-  if (!in_range) {
-    res = 0.0;
-    // gradual underflow band 2^-1080 .. 2^-1021: scale in two steps (rare)
-    if (hi == 0x4337FFFF && n < -1021 && n >= -1080) {
-      const double s = __hiloint2double(__double2hiint(p) + ((n + 128) << 20), __double2loint(p));
-      res = s * 0x1p-128;
-    }
-  }
-  return res;
+  // n in [-1085, 0]  <=>  lo in [963, 2048]
+  const bool ok = (hi == 0x43380000) && ((unsigned)(lo - 963) <= 1085u);
+  // exponent += n + 64 = lo - 1984
+  const int phi = __double2hiint(p) + ((lo - 1984) << 20);
+  return __hiloint2double(ok ? phi : 0, ok ? __double2loint(p) : 0);
 }
 
 }  // namespace gingr

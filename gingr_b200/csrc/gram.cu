@@ -10,11 +10,14 @@
 // FP64 tensor instruction is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; the m16n8k{4,8,16} PTX shapes lower to it).
 //
 // Kernel: only the lower-triangular 128x128 tiles are computed (symmetric minimum 3n r (r+1) flop).
-// The (tile, k-chunk) work space is linearised tile-major and cut into equal contiguous pieces, one per
-// CTA (stream-K, one persistent CTA per SM), so 148 SMs stay busy for any r.  Each piece accumulates in
-// registers (warp tile 64x32 = 32 DMMA accumulator fragments), operands stream global -> shared with a
-// 4-stage cp.async pipeline ([k][col] tiles, pitch 132 doubles: conflict-free LDS.64 fragment loads), the
-// row weights are multiplied into the B fragments.  Partial tiles go to a workspace and are summed in fixed
+// One persistent CTA per SM works through a static list of (tile, k-chunk range) segments (split-K schedule
+// built on the host, GramPlan::build): with T tiles on n SMs, T "main" CTAs each own one tile and walk the
+// rows of Phi in lockstep from the top (every row slab is fetched from HBM once and served to the other
+// tiles from L2), while the remaining n - T CTAs take the bottom slab of every tile, so all SMs finish
+// together for any r.  Each segment accumulates in registers (warp tile 64x32 = 32 DMMA accumulator
+// fragments), operands stream global -> shared with a 3-stage cp.async pipeline ([k][col] tiles of 32 rows,
+// pitch 132 doubles: conflict-free LDS.64 fragment loads), the row weights are multiplied into the B
+// fragments.  Partial tiles go to a workspace and are summed in fixed
 // order by gram_finish_kernel (deterministic; no atomics), which also applies D, adds I and the landmark
 // blocks (full 3x3 covariances, GeneralRegistrationState.scala:43-62).
 #include <algorithm>
@@ -26,8 +29,8 @@
 namespace gingr {
 
 constexpr int BT = 128;          // output tile edge
-constexpr int BK = 16;           // rows of Phi per pipeline stage
-constexpr int STAGES = 4;
+constexpr int BK = 32;           // rows of Phi per pipeline stage
+constexpr int STAGES = 3;
 constexpr int PITCH = BT + 4;    // smem row pitch in doubles (== 4 mod 16 -> conflict-free fragment loads)
 constexpr int GRAM_THREADS = 256;
 constexpr size_t GRAM_SMEM = (size_t)STAGES * (2 * BK * PITCH + BK) * sizeof(double);
@@ -88,9 +91,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_streamk_kernel(int rows,
       const int krow0 = (sg.c0 + chunk) * BK;
       double* dA = sA + (size_t)stage * BK * PITCH;
       double* dB = sB + (size_t)stage * BK * PITCH;
-      // 16 rows x 64 16-byte pieces per operand tile = 1024 pieces, 4 per thread
+      // BK rows x 64 16-byte pieces per operand tile, BK * 64 / 256 per thread
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < BK * 64 / GRAM_THREADS; ++q) {
         const int e = tid + q * GRAM_THREADS;
         const int kr = e >> 6, c2 = (e & 63) * 2;
         const int krow = krow0 + kr;
@@ -204,46 +207,75 @@ int32_t GramPlan::build(gingr_ctx* ctx, int rows_, int r_, int rp_) {
   ntiles = nt * (nt + 1) / 2;
   nchunks = std::max(1, ceil_div(rows, BK));
   ncta = ctx->num_sms;
-  const int64_t total = (int64_t)ntiles * nchunks;
-  if (total < ncta) ncta = (int)total;
-  std::vector<GramSegment> segs;
-  std::vector<int> seg_begin(ncta + 1, 0), tile_first(ntiles + 1, 0);
+  const int n = ncta, K = nchunks;
   std::vector<std::pair<int, int>> tile_ab(ntiles);
   for (int a = 0, k = 0; a < nt; ++a)
     for (int b = 0; b <= a; ++b) tile_ab[k++] = {a, b};
-  for (int c = 0; c < ncta; ++c) {
-    const int64_t u0 = total * c / ncta, u1 = total * (c + 1) / ncta;
-    seg_begin[c] = (int)segs.size();
-    int64_t u = u0;
-    while (u < u1) {
-      const int tile = (int)(u / nchunks);
-      const int c0 = (int)(u % nchunks);
-      const int c1 = (int)std::min<int64_t>(nchunks, c0 + (u1 - u));
-      GramSegment s;
-      s.ta = tile_ab[tile].first;
-      s.tb = tile_ab[tile].second;
-      s.c0 = c0;
-      s.c1 = c1;
-      s.slot = (int)segs.size();
-      s.pad0 = s.pad1 = s.pad2 = 0;
-      segs.push_back(s);
-      u += c1 - c0;
+  struct Seg { int cta, tile, c0, c1; };
+  std::vector<Seg> list;
+  // full rounds: n tiles at a time, every CTA walks all K chunks of its tile (lockstep -> L2 reuse)
+  const int full_rounds = ntiles / n, rem = ntiles % n;
+  for (int round = 0; round < full_rounds; ++round)
+    for (int c = 0; c < n; ++c) list.push_back({c, round * n + c, 0, K});
+  if (rem > 0) {
+    // last round: rem main CTAs take chunks [0, K1) of their tile, the other n - rem CTAs share the bottom
+    // slabs [K1, K) of all rem tiles; every CTA ends up with ~ rem K / n chunks
+    const int K1 = (int)((int64_t)K * rem / n);
+    const int base_tile = full_rounds * n;
+    for (int c = 0; c < rem; ++c)
+      if (K1 > 0) list.push_back({c, base_tile + c, 0, K1});
+    const int tail = K - K1, ntail = n - rem;
+    const int64_t total = (int64_t)rem * tail;
+    for (int j = 0; j < ntail; ++j) {
+      int64_t u = total * j / ntail;
+      const int64_t u1 = total * (j + 1) / ntail;
+      while (u < u1) {
+        const int tile = (int)(u / tail), c0 = (int)(u % tail);
+        const int c1 = (int)std::min<int64_t>(tail, c0 + (u1 - u));
+        list.push_back({rem + j, base_tile + tile, K1 + c0, K1 + c1});
+        u += c1 - c0;
+      }
     }
   }
-  seg_begin[ncta] = (int)segs.size();
-  // segments are in linearised order, so the slots of a tile are consecutive
-  for (size_t i = 0; i < segs.size(); ++i) {
-    const int tile = segs[i].ta * (segs[i].ta + 1) / 2 + segs[i].tb;
-    tile_first[tile + 1] = (int)i + 1;
+  // slots: segments of a tile are numbered consecutively (ascending chunk) -> fixed summation order
+  std::vector<int> order(list.size());
+  for (size_t i = 0; i < list.size(); ++i) order[i] = (int)i;
+  std::sort(order.begin(), order.end(), [&](int x, int y) {
+    return list[x].tile != list[y].tile ? list[x].tile < list[y].tile : list[x].c0 < list[y].c0;
+  });
+  std::vector<int> slot_of(list.size());
+  std::vector<int> tile_first(ntiles + 1, 0);
+  for (size_t s = 0; s < order.size(); ++s) {
+    slot_of[order[s]] = (int)s;
+    tile_first[list[order[s]].tile + 1] = (int)s + 1;
   }
   for (int tix = 1; tix <= ntiles; ++tix) tile_first[tix] = std::max(tile_first[tix], tile_first[tix - 1]);
+  // per-CTA lists in launch order (a CTA's main segment first, then its tail pieces)
+  std::vector<GramSegment> segs;
+  std::vector<int> seg_begin(n + 1, 0);
+  for (int c = 0; c < n; ++c) {
+    seg_begin[c] = (int)segs.size();
+    for (size_t i = 0; i < list.size(); ++i)
+      if (list[i].cta == c) {
+        GramSegment g;
+        g.ta = tile_ab[list[i].tile].first;
+        g.tb = tile_ab[list[i].tile].second;
+        g.c0 = list[i].c0;
+        g.c1 = list[i].c1;
+        g.slot = slot_of[i];
+        g.pad0 = g.pad1 = g.pad2 = 0;
+        segs.push_back(g);
+      }
+  }
+  seg_begin[n] = (int)segs.size();
   nsegs = (int)segs.size();
-  GINGR_CUDA_TRY(ctx, d_segs.alloc(segs.size() * sizeof(GramSegment) / sizeof(int)));
+  GINGR_CUDA_TRY(ctx, d_segs.alloc(std::max<size_t>(segs.size(), 1) * sizeof(GramSegment) / sizeof(int)));
   GINGR_CUDA_TRY(ctx, d_seg_begin.alloc(seg_begin.size()));
   GINGR_CUDA_TRY(ctx, d_tile_first.alloc(tile_first.size()));
-  GINGR_CUDA_TRY(ctx, d_partial.alloc((size_t)nsegs * BT * BT));
-  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(GramSegment), cudaMemcpyHostToDevice,
-                                      ctx->stream));
+  GINGR_CUDA_TRY(ctx, d_partial.alloc((size_t)std::max(nsegs, 1) * BT * BT));
+  if (nsegs > 0)
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(GramSegment), cudaMemcpyHostToDevice,
+                                        ctx->stream));
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_seg_begin.p, seg_begin.data(), seg_begin.size() * sizeof(int),
                                       cudaMemcpyHostToDevice, ctx->stream));
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_tile_first.p, tile_first.data(), tile_first.size() * sizeof(int),
@@ -265,7 +297,7 @@ void GramPlan::release() {
 int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_phi, const double* d_wrow,
                               cudaEvent_t ev0, cudaEvent_t ev1) {
   if (ev0) cudaEventRecord(ev0, ctx->stream);
-  if (plan.rows > 0) {
+  if (plan.rows > 0 && plan.nsegs > 0) {
     gram_streamk_kernel<<<plan.ncta, GRAM_THREADS, GRAM_SMEM, ctx->stream>>>(
         plan.rows, plan.rp, d_phi, d_wrow, reinterpret_cast<const GramSegment*>(plan.d_segs.p), plan.d_seg_begin.p,
         plan.d_partial.p);

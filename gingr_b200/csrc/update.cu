@@ -122,11 +122,18 @@ __global__ void cpd_estep_scalars_kernel(const double* __restrict__ ds, double w
   scal[2] = w / (1.0 - w) * (t * sqrt(t)) * ratio;  // CPD.scala:69-70
 }
 
-// xpx total (fixed order) appended behind the row block for the all-reduce
+// xpx total (fixed order) appended behind the row block for the all-reduce.  One CTA of 256 threads.
 __global__ void xpx_total_kernel(int nparts, const double* __restrict__ parts, double* __restrict__ out) {
+  __shared__ double red[256];
   double s = 0.0;
-  for (int k = 0; k < nparts; ++k) s += parts[k];
-  out[0] = s;
+  for (int k = threadIdx.x; k < nparts; k += 256) s += parts[k];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
 }
 
 // ---- observations ---------------------------------------------------------------------------------
@@ -376,7 +383,7 @@ __device__ void svd3(const double* Ain, double* U, double* S, double* V) {
           Vm[3 * k + q] = s * vp + c * vq;
         }
       }
-    if (off < 1e-17) break;
+    if (off < 2.3e-16) break;  // columns orthogonal to machine precision
   }
   double sv[3];
   for (int j = 0; j < 3; ++j) sv[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
@@ -1086,6 +1093,10 @@ static int32_t enqueue_iteration(gingr_registration* g) {
   GINGR_LAUNCHED(ctx);
   // ---- correspondence -------------------------------------------------------------------------------
   if (cfg.algorithm == GINGR_ALGO_CPD) {
+    // non-finite fit / sigma2 / target: the reference's P is all NaN and the posterior fails
+    GINGR_TRY(validate_finite_enqueue(ctx, 3 * M, g->fit.p, g->is.p + IS_FAIL_POST));
+    GINGR_TRY(validate_finite_enqueue(ctx, 1, g->ds.p + DS_SIGMA2, g->is.p + IS_FAIL_POST));
+    if (tg->nonfinite) GINGR_TRY(validate_finite_enqueue(ctx, 3 * tg->N_total, tg->verts.p, g->is.p + IS_FAIL_POST));
     GINGR_TRY(aos_to_soa_enqueue(ctx, M, g->fit.p, g->estep.fit_soa.p));
     cpd_estep_scalars_kernel<<<1, 1, 0, st>>>(g->ds.p, cfg.w, (double)M / (double)tg->N_total, g->estep.scal.p);
     GINGR_LAUNCHED(ctx);
@@ -1096,7 +1107,7 @@ static int32_t enqueue_iteration(gingr_registration* g) {
       GINGR_TRY(estep_enqueue(ctx, g->estep, M, tg->N, tg->soa.p, false, pe ? &ee : nullptr));
       GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->rows_ext.p, g->estep.rows.p, sizeof(double) * 4 * (size_t)M,
                                           cudaMemcpyDeviceToDevice, st));
-      xpx_total_kernel<<<1, 1, 0, st>>>(g->estep.plan.den_blocks, g->estep.xpx_part.p, g->rows_ext.p + (size_t)4 * M);
+      xpx_total_kernel<<<1, 256, 0, st>>>(g->estep.plan.den_blocks, g->estep.xpx_part.p, g->rows_ext.p + (size_t)4 * M);
       GINGR_LAUNCHED(ctx);
     } else {
       GINGR_CUDA_TRY(ctx, cudaMemsetAsync(g->rows_ext.p, 0, sizeof(double) * ((size_t)4 * M + 8), st));

@@ -154,3 +154,22 @@ def test_gram_large_property(ctx):
     expect = a * var / (var + 1e-8)
     assert rel_err(c, expect) < 1e-9
     assert np.max(np.abs(mesh - obs)) < 1e-5
+
+
+def test_gram_more_tiles_than_sms(ctx, oracle):
+    """r = 2304 -> 171 lower-triangular tiles > 148 SMs: the schedule has a full round plus a main/tail round."""
+    from gingr_b200 import api, synthetic
+    M, r = 900, 2304
+    ref = synthetic.fibonacci_sphere(M)
+    rng = np.random.default_rng(31)
+    basis = rng.normal(size=(3 * M, r)) / np.sqrt(3 * M)
+    var = 50.0 * 0.999 ** np.arange(r)
+    m = oracle.Gpmm(ref, np.zeros(3 * M), basis, var, None)
+    dm = api.Model(ctx, ref, m.mean, basis, var)
+    obs = ref + rng.normal(scale=1.0, size=(M, 3))
+    noise = rng.uniform(0.5, 2.0, size=M)
+    pids = np.arange(M, dtype=np.int32)
+    c, mesh = api.posterior_mean(ctx, dm, np.eye(3), np.zeros(3), pids, obs, noise)
+    c_ref, _ = m.posterior_coefficients(pids, obs, np.eye(3)[None] * noise[:, None, None])
+    diag = np.linalg.norm(ref.max(0) - ref.min(0))
+    assert np.max(np.abs(mesh - m.instance(c_ref))) < 1e-9 * diag
