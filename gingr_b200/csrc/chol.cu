@@ -6,8 +6,8 @@
 // d_info and becomes FittingStatuses.ModelFlexibilityError where the reference's Try fails.
 //
 // Blocked right-looking factorisation, block 64:
-//   chol_panel_kernel   every CTA factorises the 64 x 64 diagonal block redundantly in shared memory
-//                       (no extra launch / grid sync) and solves its own 64 rows of the panel
+//   chol_panel_kernel   every CTA factorises the 64 x 64 diagonal block redundantly (no extra launch / grid
+//                       sync; warp-level in-register 32 x 32 factorisations) and solves its own 128 panel rows
 //   chol_syrk_kernel    trailing update C -= X X^T on DMMA.8x8x4 (64 x 64 tiles, K = 64)
 // Rows below the square part (right-hand sides stored as extra rows) ride along, which performs the
 // forward substitution L^-1 b inside the factorisation.  The backward substitution L^-T z is a sync-free
@@ -19,70 +19,143 @@ namespace gingr {
 
 constexpr int NB = 64;
 constexpr int SP = NB + 1;  // shared pitch for the scalar kernels
-constexpr size_t PANEL_SMEM = (3 * NB * SP + NB) * sizeof(double);
 
 // ---------------------------------------------------------------------------------------------
-// panel: diagonal block factorisation + triangular solve of the rows below, fused in ONE loop over the 64
-// columns with a single barrier per column.  At step j (pivot d = D[j][j], still unscaled):
-//   L[i][j] = D[i][j] / sqrt(d)            (final, stored transposed in the unused upper triangle of sD)
-//   X[r][j] = X[r][j] / sqrt(d)            (final, stored in sXo)
-//   D[i][k] -= (D[i][j] / d) D[k][j]       trailing block, k > j        (right-looking, unscaled column j)
-//   X[r][c] -= (X[r][j] / d) D[c][j]       panel rows, c > j
-// Column j of sD / sX is only read in step j and never written afterwards, so no second barrier is needed.
-// Thread layout: tx = tid & 63 (column / row index), ty = tid >> 6 (4 row groups): no integer division.
+// panel kernel.  Every CTA factorises the 64 x 64 diagonal block redundantly (no extra launch, no grid sync)
+// and then solves its own PR rows of the panel.  The diagonal block is done recursively on 32 x 32 halves:
+//   L11 = chol32(A11)            one warp, lane i owns row i in REGISTERS, pivots/columns move by shuffles:
+//                                no block barrier inside the 32 sequential column steps
+//   L21 = A21 L11^-T             one warp, lane = row, right-looking substitution against L11 in shared memory
+//   A22 -= L21 L21^T             all threads
+//   L22 = chol32(A22)
+// The panel rows are solved one row per thread, the row held in registers (x[64]), right-looking so the 63
+// updates of a step are independent FMAs; L is read from shared memory as a broadcast.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) chol_panel_kernel(int nrows, int j0, int jb, double* __restrict__ A, int ld,
-                                                         int* __restrict__ info) {
+constexpr int PR = 128;  // panel rows (threads) per CTA
+constexpr size_t PANEL_SMEM = ((size_t)NB * SP + NB + (size_t)PR * SP) * sizeof(double);
+
+// In-register Cholesky of a 32 x 32 block: lane i holds row i (a[k], k <= i).  On return a[k] = L[i][k] for
+// k <= i and *invd = 1 / L[i][i].  Returns true if a pivot was not positive and finite.
+__device__ __forceinline__ bool warp_chol32(double (&a)[32], int lane, double* invd) {
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const double d = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(d > 0.0) || !(d < INFINITY)) bad = true;
+    const double rs = rsqrt(d);
+    const double l = a[j] * rs;  // lane j: sqrt(d); lanes > j: L[i][j]
+    a[j] = l;
+    if (lane == j) *invd = rs;
+#pragma unroll
+    for (int k = j + 1; k < 32; ++k) {
+      const double lk = __shfl_sync(0xffffffffu, l, k);  // L[k][j]
+      a[k] = fma(-l, lk, a[k]);
+    }
+  }
+  return bad;
+}
+
+// x <- x L^-T for one row held in registers: L (NC x NC lower, pitch SP) and 1/diag in shared memory.
+template <int NC>
+__device__ __forceinline__ void row_trsm(double (&x)[NC], const double* __restrict__ sLm,
+                                         const double* __restrict__ sInv) {
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    x[j] *= sInv[j];
+    const double xj = x[j];
+#pragma unroll
+    for (int m = j + 1; m < NC; ++m) x[m] = fma(-xj, sLm[m * SP + j], x[m]);
+  }
+}
+
+__global__ void __launch_bounds__(PR) chol_panel_kernel(int nrows, int j0, int jb, double* __restrict__ A, int ld,
+                                                        int* __restrict__ info) {
   extern __shared__ __align__(16) double psm[];
-  double* sD = psm;                  // [64][65] working diagonal block (lower) / final L^T (upper)
-  double* sX = psm + NB * SP;        // [64][65] working panel rows
-  double* sXo = psm + 2 * NB * SP;   // [64][65] final panel rows
-  double* sDiag = psm + 3 * NB * SP; // [64] final diagonal
-  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
-  const int i0 = j0 + jb + blockIdx.x * NB;
-  const int cnt = max(0, min(NB, nrows - i0));
-  for (int e = tid; e < NB * NB; e += 256) {
+  double* sL = psm;                    // [64][65] diagonal block -> L (lower)
+  double* sInvD = psm + NB * SP;       // [64] 1 / L[j][j]
+  double* sX = psm + NB * SP + NB;     // [PR][65] panel rows
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = j0 + jb + blockIdx.x * PR;
+  const int cnt = max(0, min(PR, nrows - i0));
+  for (int e = tid; e < NB * NB; e += PR) {
     const int i = e >> 6, k = e & 63;
-    sD[i * SP + k] = (i < jb && k <= i) ? A[(size_t)(j0 + i) * ld + j0 + k] : (i == k ? 1.0 : 0.0);
+    sL[i * SP + k] = (i < jb && k <= i) ? A[(size_t)(j0 + i) * ld + j0 + k] : (i == k ? 1.0 : 0.0);
+  }
+  for (int e = tid; e < PR * NB; e += PR) {
+    const int i = e >> 6, k = e & 63;
     sX[i * SP + k] = (i < cnt && k < jb) ? A[(size_t)(i0 + i) * ld + j0 + k] : 0.0;
   }
   __syncthreads();
+  // All four warps run the warp-level pieces redundantly and convergently (no divergent region around the
+  // shuffles); only warp 0 stores.  h = 0: (L11, L21, A22 update), h = 1: L22 -- one copy of the unrolled code.
   bool bad = false;
-  for (int j = 0; j < jb; ++j) {
-    const double d = sD[j * SP + j];
-    if (!(d > 0.0) || !(d < INFINITY)) bad = true;
-    const double djj = sqrt(d);
-    const double inv = 1.0 / d;
-    if (ty == 0) {
-      if (tx == j) sDiag[j] = djj;
-      else if (tx > j && tx < jb) sD[j * SP + tx] = sD[tx * SP + j] / djj;  // transposed slot (upper triangle)
-    } else if (ty == 1) {
-      sXo[tx * SP + j] = sX[tx * SP + j] / djj;
-    }
-    {
-      const int k = j + 1 + tx;
-      if (k < jb) {
-        const double dkj = sD[k * SP + j];
-        for (int i = j + 1 + ty; i < jb; i += 4)
-          if (k <= i) sD[i * SP + k] -= (sD[i * SP + j] * inv) * dkj;
-      }
-    }
-    {
-      const double xs = sX[tx * SP + j] * inv;
-      for (int cc = j + 1 + ty; cc < jb; cc += 4) sX[tx * SP + cc] -= xs * sD[cc * SP + j];
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    double* blk = sL + (h * 32) * SP + h * 32;  // A11 or A22
+    double a[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a[k] = blk[lane * SP + k];
+    double invd = 0.0;
+    bad = warp_chol32(a, lane, &invd) || bad;
+    __syncthreads();  // every warp has read the block
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k <= lane) blk[lane * SP + k] = a[k];
+      sInvD[h * 32 + lane] = invd;
     }
     __syncthreads();
+    if (h == 0) {
+      // L21 = A21 L11^-T  (lane = row of A21)
+      double x[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) x[k] = sL[(32 + lane) * SP + k];
+      row_trsm<32>(x, sL, sInvD);
+      __syncthreads();
+      if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) sL[(32 + lane) * SP + k] = x[k];
+      }
+      __syncthreads();
+      // A22 -= L21 L21^T : thread -> row i = tid / 4, 8 columns
+      const int i = tid >> 2, k0 = (tid & 3) * 8;
+      const double* li = sL + (32 + i) * SP;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = k0 + q;
+        if (k <= i) {
+          const double* lk = sL + (32 + k) * SP;
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            s0 = fma(li[c], lk[c], s0);
+            s1 = fma(li[c + 1], lk[c + 1], s1);
+          }
+          sL[(32 + i) * SP + 32 + k] -= s0 + s1;
+        }
+      }
+      __syncthreads();
+    }
   }
   if (blockIdx.x == 0) {
     if (bad && tid == 0) info[0] = 1;
-    for (int e = tid; e < NB * NB; e += 256) {
+    for (int e = tid; e < NB * NB; e += PR) {
       const int i = e >> 6, k = e & 63;
-      if (i < jb && k <= i) A[(size_t)(j0 + i) * ld + j0 + k] = (i == k) ? sDiag[i] : sD[k * SP + i];
+      if (i < jb && k <= i) A[(size_t)(j0 + i) * ld + j0 + k] = sL[i * SP + k];
     }
   }
-  for (int e = tid; e < NB * NB; e += 256) {
+  if (cnt > 0) {
+    double x[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) x[k] = sX[tid * SP + k];
+    row_trsm<NB>(x, sL, sInvD);
+#pragma unroll
+    for (int k = 0; k < NB; ++k) sX[tid * SP + k] = x[k];
+  }
+  __syncthreads();
+  for (int e = tid; e < PR * NB; e += PR) {
     const int i = e >> 6, k = e & 63;
-    if (i < cnt && k < jb) A[(size_t)(i0 + i) * ld + j0 + k] = sXo[i * SP + k];
+    if (i < cnt && k < jb) A[(size_t)(i0 + i) * ld + j0 + k] = sX[i * SP + k];
   }
 }
 
@@ -242,8 +315,8 @@ int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, 
   for (int j0 = 0; j0 < n; j0 += NB) {
     const int jb = std::min(NB, n - j0);
     const int below = nrows - (j0 + jb);
-    const int pblocks = std::max(1, ceil_div(below, NB));
-    chol_panel_kernel<<<pblocks, 256, PANEL_SMEM, st>>>(nrows, j0, jb, d_A, ld, d_info);
+    const int pblocks = std::max(1, ceil_div(below, PR));
+    chol_panel_kernel<<<pblocks, PR, PANEL_SMEM, st>>>(nrows, j0, jb, d_A, ld, d_info);
     GINGR_LAUNCHED(ctx);
     if (below > 0 && j0 + jb < n) {
       const int r0 = j0 + jb;
