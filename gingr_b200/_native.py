@@ -12,7 +12,8 @@ from ctypes import POINTER, c_char, c_char_p, c_double, c_int32, c_int64, c_uint
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libgingr_cuda.so")
+# GINGR_CUDA_LIB: alternative build of the same library (kernel tuning experiments); never a fallback
+LIB_PATH = os.environ.get("GINGR_CUDA_LIB") or os.path.join(HERE, "lib", "libgingr_cuda.so")
 
 GINGR_OK = 0
 GINGR_MODEL_FLEXIBILITY = 1

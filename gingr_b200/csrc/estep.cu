@@ -27,9 +27,22 @@
 
 namespace gingr {
 
+// tuning knobs (overridable with -D for experiments; the defaults are the measured best on B200)
+#ifndef ESTEP_CA
+#define ESTEP_CA 4
+#endif
+#ifndef ESTEP_RB
+#define ESTEP_RB 4
+#endif
+#ifndef ESTEP_MINB_A
+#define ESTEP_MINB_A 4
+#endif
+#ifndef ESTEP_MINB_B
+#define ESTEP_MINB_B 2
+#endif
 constexpr int TPB = 256;       // threads per CTA in both sweeps
-constexpr int CA = 4;          // columns per thread, sweep A
-constexpr int RB = 4;          // rows per thread, sweep B
+constexpr int CA = ESTEP_CA;   // columns per thread, sweep A
+constexpr int RB = ESTEP_RB;   // rows per thread, sweep B
 constexpr int TILE_ROWS = 512; // rows staged per shared-memory tile in sweep A
 constexpr int TILE_COLS = 256; // columns staged per shared-memory tile in sweep B
 
@@ -38,14 +51,17 @@ constexpr int TILE_COLS = 256; // columns staged per shared-memory tile in sweep
 // fit  : moving points SoA [3][M] (+ row factor f[M]), target: SoA [3][N]
 // part : [gridDim.y][N] partial column sums
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) estep_colsum_kernel(int M, int N, const double* __restrict__ fit,
+__global__ void __launch_bounds__(TPB, ESTEP_MINB_A) estep_colsum_kernel(int M, int N, const double* __restrict__ fit,
                                                            const double* __restrict__ rowf,
                                                            const double* __restrict__ target,
                                                            const double* __restrict__ scal,
                                                            double* __restrict__ part) {
   __shared__ double4 ytile[TILE_ROWS];
+  __shared__ __align__(16) unsigned int s_tab[GAUSS_TAB_BYTES / 4];
+  gauss_tab_fill(s_tab, threadIdx.x, TPB);
+  const int lane_off = (threadIdx.x & 15) * 8;
   const double sigma2 = scal[0];
-  const double negk = -1.4426950408889634074 / (2.0 * sigma2);
+  const double negk = -64.0 * 1.4426950408889634074 / (2.0 * sigma2);
   const int rows_per_split = (M + gridDim.y - 1) / gridDim.y;
   const int i_begin = blockIdx.y * rows_per_split;
   const int i_end = min(M, i_begin + rows_per_split);
@@ -78,7 +94,7 @@ __global__ void __launch_bounds__(TPB) estep_colsum_kernel(int M, int N, const d
         double d2 = dx * dx;
         d2 = fma(dy, dy, d2);
         d2 = fma(dz, dz, d2);
-        acc[c] = fma(gauss_exp2_biased(d2, negk), y.w, acc[c]);
+        acc[c] = fma(gauss_exp2_tab(d2, negk, s_tab, lane_off), y.w, acc[c]);
       }
     }
   }
@@ -128,13 +144,16 @@ __global__ void __launch_bounds__(TPB) estep_den_kernel(int N, int splits, const
 // sweep B: row sums.   grid = (row blocks, column splits)
 // part : [gridDim.y][4][M]  (P1, PX.x, PX.y, PX.z) partials, without the row factor
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) estep_rowsum_kernel(int M, int N, const double* __restrict__ fit,
+__global__ void __launch_bounds__(TPB, ESTEP_MINB_B) estep_rowsum_kernel(int M, int N, const double* __restrict__ fit,
                                                            const double* __restrict__ pack,
                                                            const double* __restrict__ scal,
                                                            double* __restrict__ part) {
   __shared__ double4 xtile[TILE_COLS * 2];
+  __shared__ __align__(16) unsigned int s_tab[GAUSS_TAB_BYTES / 4];
+  gauss_tab_fill(s_tab, threadIdx.x, TPB);
+  const int lane_off = (threadIdx.x & 15) * 8;
   const double sigma2 = scal[0];
-  const double negk = -1.4426950408889634074 / (2.0 * sigma2);
+  const double negk = -64.0 * 1.4426950408889634074 / (2.0 * sigma2);
   const int cols_per_split = (N + gridDim.y - 1) / gridDim.y;
   const int j_begin = blockIdx.y * cols_per_split;
   const int j_end = min(N, j_begin + cols_per_split);
@@ -166,7 +185,7 @@ __global__ void __launch_bounds__(TPB) estep_rowsum_kernel(int M, int N, const d
         double d2 = dx * dx;
         d2 = fma(dy, dy, d2);
         d2 = fma(dz, dz, d2);
-        const double k = gauss_exp2_biased(d2, negk);
+        const double k = gauss_exp2_tab(d2, negk, s_tab, lane_off);
         a0[q] = fma(k, xa.w, a0[q]);
         a1[q] = fma(k, xb.x, a1[q]);
         a2[q] = fma(k, xb.y, a2[q]);
@@ -303,12 +322,36 @@ int32_t initial_sigma2_enqueue(gingr_ctx* ctx, int M, const double* d_pts_aos, i
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// Number of splits s (1 <= s <= max_splits) of the streamed dimension such that the grid of blocks * s CTAs fills
+// whole waves of `capacity` resident CTAs: the kernels are throughput bound, so a last wave that is 10 % full
+// costs a whole wave (ncu: 4.05 waves/SM on sweep B before this planner).  Prefers 2..6 waves.
+static int pick_splits_for_waves(int blocks, int max_splits, int capacity) {
+  if (blocks >= 8 * capacity || max_splits <= 1) return 1;
+  int best = 1;
+  double best_score = -1.0;
+  for (int s = 1; s <= max_splits; ++s) {
+    const double ctas = (double)blocks * s;
+    const double waves = ctas / capacity;
+    if (waves > 6.0 && best_score >= 0.0) break;
+    const double fill = waves / ceil(waves);
+    // below one wave: plain parallelism counts; above: fill of the last wave, slight preference for more waves
+    const double score = waves < 1.0 ? waves : 1.0 + fill + 0.002 * waves;
+    if (score > best_score) {
+      best_score = score;
+      best = s;
+    }
+  }
+  return best;
+}
+
 void estep_plan(const gingr_ctx* ctx, int M, int N, EstepPlan* p) {
-  const int target_ctas = ctx->num_sms * 16;
+  int occ_a = 4, occ_b = 4;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, estep_colsum_kernel, TPB, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, estep_rowsum_kernel, TPB, 0);
   p->col_blocks = ceil_div(N, TPB * CA);
-  p->row_splits = max(1, min(ceil_div(target_ctas, p->col_blocks), ceil_div(M, 256)));
+  p->row_splits = pick_splits_for_waves(p->col_blocks, ceil_div(M, 128), max(occ_a, 1) * ctx->num_sms);
   p->row_blocks = ceil_div(M, TPB * RB);
-  p->col_splits = max(1, min(ceil_div(target_ctas, p->row_blocks), ceil_div(N, 256)));
+  p->col_splits = pick_splits_for_waves(p->row_blocks, ceil_div(N, 128), max(occ_b, 1) * ctx->num_sms);
   p->den_blocks = ceil_div(N, TPB);
 }
 

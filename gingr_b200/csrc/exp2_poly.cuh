@@ -15,6 +15,7 @@
 // validation pass (a NaN would otherwise select the zero branch).
 // 13 FP64 instructions per evaluation (3 range reduction + 10 Horner FMAs).
 #pragma once
+#include "exp2_tab.cuh"
 
 namespace gingr {
 
@@ -50,6 +51,56 @@ __device__ __forceinline__ double gauss_exp2_biased(double d2, double negk) {
   // exponent += n + 64 = lo - 1984
   const int phi = __double2hiint(p) + ((lo - 1984) << 20);
   return __hiloint2double(ok ? phi : 0, ok ? __double2loint(p) : 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Table variant (the one the E-step sweeps use): 2^x = 2^n * 2^(k/64) * 2^(r/64), x*64 = 64 n + k + r, |r| <= 1/2.
+//   tmp = fma(d2, negk64, SHIFT64)        low word = (2048 + n) * 64 + k          negk64 = -64 log2(e) / (2 sigma2)
+//   r   = fma(d2, negk64, -(tmp - SHIFT64))
+//   T   = table[k] with its exponent field advanced by n + 64 in ONE integer multiply-add (the table's hi words
+//         are pre-adjusted, exp2_tab.cuh); the table lives in shared memory, replicated 16x so that the 16 lanes of
+//         a half warp hit 16 distinct bank pairs whatever their k (LDS.64 is served per half warp)
+//   K'  = T + (T r) q(r),  q = degree-4 Taylor tail (truncation 3.5e-17)
+// 9 FP64 instructions (3 range reduction, 4 Horner, 1 mul, 1 fma) instead of 13, and 7 other instructions instead
+// of 12: the sweeps are bound by the FP64 pipe (2 cycles per warp instruction), so this is a direct 4/20 saving
+// per pair in sweep A and 4/23 in sweep B.
+constexpr int GAUSS_TAB_BYTES = 64 * 16 * 8;
+
+__device__ __forceinline__ void gauss_tab_fill(unsigned int* s_tab /*[64*16*2]*/, int tid, int nthreads) {
+  for (int e = tid; e < 64 * 16; e += nthreads) {
+    s_tab[2 * e] = GAUSS_EXP2_TAB[e >> 4][0];
+    s_tab[2 * e + 1] = GAUSS_EXP2_TAB[e >> 4][1];
+  }
+}
+
+// polynomial constants in constant memory: DFMA takes a c[bank][offset] operand directly, whereas 64-bit
+// immediates are re-materialised with UMOV pairs in the loop (3 extra issue slots per evaluation)
+__constant__ double GAUSS_C[8] = {GAUSS_EXP2_A1, GAUSS_EXP2_A2, GAUSS_EXP2_A3, GAUSS_EXP2_A4, GAUSS_EXP2_A5,
+                                  6755399441055744.0 + 131072.0 /* SHIFT = 1.5 * 2^52 + 2048 * 64 */, 0.0, 0.0};
+
+// Returns K' = 2^64 * 2^(negk64 * d2 / 64), or exactly 0 when K underflows (n < -1085) or the argument is out of
+// range.  The zero is SELECTED (not a skipped accumulation): the reference evaluates 0 * (1 / 0) = NaN for a column
+// whose denominators vanish (CPD.scala:71-74), and that NaN must reach P1 / PX.
+// lane_off = (lane & 15) * 8; s_tab = the CTA's table (gauss_tab_fill).
+__device__ __forceinline__ double gauss_exp2_tab(double d2, double negk64, const unsigned int* s_tab, int lane_off) {
+  const double SHIFT = GAUSS_C[5];
+  const double tmp = fma(d2, negk64, SHIFT);
+  const int lo = __double2loint(tmp);  // (2048 + n) * 64 + k
+  const int hi = __double2hiint(tmp);
+  const double nf = tmp - SHIFT;
+  const double r = fma(d2, negk64, -nf);
+  const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(s_tab) + (((lo << 7) & 0x1F80) | lane_off));
+  const double T = __hiloint2double((int)(((unsigned)lo << 14) + t.y), (int)t.x);
+  double p = GAUSS_C[4];
+  p = fma(p, r, GAUSS_C[3]);
+  p = fma(p, r, GAUSS_C[2]);
+  p = fma(p, r, GAUSS_C[1]);
+  p = fma(p, r, GAUSS_C[0]);
+  const double s = T * r;
+  const double v = fma(s, p, T);
+  // n in [-1085, 0]  <=>  lo in [963 * 64, 2048 * 64]
+  const bool ok = (hi == 0x43380000) && ((unsigned)(lo - 963 * 64) <= 1085u * 64u);
+  return __hiloint2double(ok ? __double2hiint(v) : 0, ok ? __double2loint(v) : 0);
 }
 
 }  // namespace gingr

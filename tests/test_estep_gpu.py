@@ -126,3 +126,28 @@ def test_initial_sigma2(ctx, oracle):
     got = api.cpd_initial_sigma2(ctx, target, a)
     ref = oracle.cpd_initial_sigma2(a, b)
     assert abs(got - ref) < 1e-12 * ref
+
+
+@pytest.mark.gpu
+def test_gaussian_kernel_accuracy_over_the_whole_range(ctx):
+    """The device 2^x (table + degree-5 tail, exp2_poly.cuh) against numpy's exp, isolated through a 1 x N E-step:
+    Pt1_j = K_j / (K_j + c)  =>  K_j = c Pt1_j / (1 - Pt1_j).  Distances are multiples of 1/64, so d^2 is exact.
+    Both sides round the scaled argument x = d^2 / (2 sigma2) once (the reference divides, CPD.scala:55-57; the
+    kernel folds log2(e) / (2 sigma2) into one constant), so the error bound grows like |x| eps."""
+    n = 13000
+    sigma2, w = 1.0, 0.999
+    d = np.arange(n) / 64.0 * 0.18                       # x = d^2 / 2 up to 668 -> K down to 1e-290
+    d = np.round(d * 64) / 64
+    target = np.zeros((n, 3))
+    target[:, 0] = d
+    fit = np.zeros((1, 3))
+    tgt = api.Target(ctx, target)
+    P1, Pt1, PX = api.cpd_estep(ctx, tgt, fit, sigma2, w)
+    c = w / (1 - w) * (2 * np.pi * sigma2) ** 1.5 * 1 / n
+    K = c * Pt1 / (1 - Pt1)
+    x = (d * d) / (2 * sigma2)
+    Kref = np.exp(-x)
+    rel = np.abs(K - Kref) / Kref
+    bound = (2.0 * x + 8.0) * 1.2e-16
+    assert np.all(rel < bound), float(np.max(rel / bound))
+    tgt.close()
