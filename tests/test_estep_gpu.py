@@ -134,6 +134,7 @@ def test_gaussian_kernel_accuracy_over_the_whole_range(ctx):
     Pt1_j = K_j / (K_j + c)  =>  K_j = c Pt1_j / (1 - Pt1_j).  Distances are multiples of 1/64, so d^2 is exact.
     Both sides round the scaled argument x = d^2 / (2 sigma2) once (the reference divides, CPD.scala:55-57; the
     kernel folds log2(e) / (2 sigma2) into one constant), so the error bound grows like |x| eps."""
+    from gingr_b200 import api
     n = 13000
     sigma2, w = 1.0, 0.999
     d = np.arange(n) / 64.0 * 0.18                       # x = d^2 / 2 up to 668 -> K down to 1e-290
