@@ -32,7 +32,12 @@ constexpr int BT = 128;          // output tile edge
 constexpr int BK = 32;           // rows of Phi per pipeline stage
 constexpr int STAGES = 3;
 constexpr int PITCH = BT + 4;    // smem row pitch in doubles (== 4 mod 16 -> conflict-free fragment loads)
-constexpr int GRAM_THREADS = 256;
+#ifndef GRAM_WARPS_M
+#define GRAM_WARPS_M 2           // warps along the tile rows: 2 -> 8 warps of 64x32, 4 -> 16 warps of 32x32
+#endif
+constexpr int GRAM_THREADS = GRAM_WARPS_M * 4 * 32;
+constexpr int WTM = BT / GRAM_WARPS_M;   // warp tile rows
+constexpr int MI = WTM / 8;              // 8-row DMMA fragments per warp tile
 constexpr size_t GRAM_SMEM = (size_t)STAGES * (2 * BK * PITCH + BK) * sizeof(double);
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_streamk_kernel(int rows,
   double* sW = sB + (size_t)STAGES * BK * PITCH;       // [STAGES][BK]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;             // 2 x 4 warps, warp tile 64 x 32
+  const int wm = warp >> 2, wn = warp & 3;             // GRAM_WARPS_M x 4 warps, warp tile WTM x 32
   const int g = lane >> 2, t = lane & 3;
 
   for (int si = seg_begin[blockIdx.x]; si < seg_begin[blockIdx.x + 1]; ++si) {
@@ -80,9 +85,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_streamk_kernel(int rows,
     const bool diag = sg.ta == sg.tb;
     const int nchunks = sg.c1 - sg.c0;
 
-    double acc[8][4][2];
+    double acc[MI][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -130,20 +135,20 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_streamk_kernel(int rows,
       if (ch + STAGES - 1 < nchunks) issue(ch + STAGES - 1);
       cp_async_commit();
       const int stage = ch % STAGES;
-      const double* tA = sA + (size_t)stage * BK * PITCH + wm * 64 + g;
+      const double* tA = sA + (size_t)stage * BK * PITCH + wm * WTM + g;
       const double* tB = (diag ? sA : sB) + (size_t)stage * BK * PITCH + wn * 32 + g;
       const double* tW = sW + stage * BK;
 #pragma unroll
       for (int k4 = 0; k4 < BK / 4; ++k4) {
         const int kk = k4 * 4 + t;
         const double wk = wrow ? tW[kk] : 1.0;
-        double af[8], bf[4];
+        double af[MI], bf[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) af[i] = tA[kk * PITCH + i * 8];
+        for (int i = 0; i < MI; ++i) af[i] = tA[kk * PITCH + i * 8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) bf[j] = tB[kk * PITCH + j * 8] * wk;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
@@ -152,10 +157,10 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_streamk_kernel(int rows,
     // store the partial tile: slot-major [slot][128][128]
     double* out = partial + (size_t)sg.slot * BT * BT;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int row = wm * 64 + i * 8 + g, col = wn * 32 + j * 8 + 2 * t;
+        const int row = wm * WTM + i * 8 + g, col = wn * 32 + j * 8 + 2 * t;
         *reinterpret_cast<double2*>(out + (size_t)row * BT + col) = make_double2(acc[i][j][0], acc[i][j][1]);
       }
   }
