@@ -399,11 +399,15 @@ class GingrAlgorithm:
                                                   int(seed), ctypes.byref(out), nat.as_dp(alpha_out), nat.as_dp(fit)))
         return GeneralRegistrationState.from_pod(out, alpha_out, fit if with_fit else current.fit, current.generatedBy)
 
-    def propose(self, current: GeneralRegistrationState) -> GeneralRegistrationState:
+    def propose(self, current: GeneralRegistrationState, probabilistic: bool = False,
+                seed: int = 0) -> GeneralRegistrationState:
         """GingrGeneratorWrapper.propose (GingrGeneratorWrapper.scala:28-39) around the deterministic
-        wrapper (GeneratorWrapperDeterministic.scala:28-34): update, refresh fit, iteration += 1."""
-        ns = self.update(current, False)
-        return dataclasses.replace(ns, generatedBy="Deterministic", iteration=ns.iteration + 1)
+        wrapper (GeneratorWrapperDeterministic.scala:28-34) or, with probabilistic=True, the informed proposal of
+        GeneratorWrapperStochastic.gingrPropose (GeneratorWrapperStochastic.scala:34-40): update, refresh fit,
+        iteration += 1."""
+        ns = self.update(current, probabilistic, seed)
+        return dataclasses.replace(ns, generatedBy="Stochastic" if probabilistic else "Deterministic",
+                                   iteration=ns.iteration + 1)
 
     def run(self, initialState: GeneralRegistrationState, callBackLogger=None) -> GeneralRegistrationState:
         """Deterministic GingrAlgorithm.run (:115-175): the chain yields the initial state first, so
@@ -431,6 +435,9 @@ class GingrAlgorithm:
     # device-resident chaining (throughput runs)
     def updateChain(self, iters: int):
         self.ctx.check(self.ctx._lib.gingr_update_chain(self.handle, int(iters)))
+
+    def updateChainSampled(self, iters: int, seed: int):
+        self.ctx.check(self.ctx._lib.gingr_update_chain_sampled(self.handle, int(iters), int(seed)))
 
     def downloadState(self) -> GeneralRegistrationState:
         st = GingrState()

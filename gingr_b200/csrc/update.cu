@@ -43,7 +43,8 @@ enum {
   DS_NEW_SIGMA2 = 50, DS_NP = 51, DS_XPX = 52, DS_YPY = 53, DS_TRPXY = 54,
   DS_MUX = 56, DS_MUY = 59, DS_S2X = 62, DS_SXY = 63, DS_COUNT = 80
 };
-enum { IS_GT = 0, IS_ITER = 1, IS_STATUS = 2, IS_INFO = 3, IS_FAIL_POST = 4, IS_FAIL_COEF = 5, IS_COUNT = 16 };
+enum { IS_GT = 0, IS_ITER = 1, IS_STATUS = 2, IS_INFO = 3, IS_FAIL_POST = 4, IS_FAIL_COEF = 5, IS_RETRY = 6, IS_COUNT = 16 };
+constexpr int RETRY_COUNTER_INIT = 10;  // GingrAlgorithm.scala:69-70
 
 __device__ __forceinline__ void euler_to_matrix_dev(double phi, double theta, double psi, double* R) {
   const double cph = cos(phi), sph = sin(phi), cth = cos(theta), sth = sin(theta), cps = cos(psi), sps = sin(psi);
@@ -278,6 +279,39 @@ __global__ void gather_rows_kernel(int L, int rp, int m0, const int32_t* __restr
   out[(size_t)l * 3 * rp + e] = phi[((size_t)3 * (pid[l] - m0) + d) * rp + a];
 }
 
+// ---- posterior sampling -----------------------------------------------------------------------------
+// posterior.sample() (GingrAlgorithm.scala:211; scalismo: mean + Phi' U_s (sqrt(s) z)) draws the
+// coefficients from N(c, Minv).  With Mx = L L^T the same distribution is  c + L^-T z = L^-T (L^-1 rhs + z):
+// z is added to the forward-substituted right-hand side before the back solve.  (scalismo rotates the basis with
+// an SVD and uses its own RNG stream, so the individual draws differ; the distribution is identical.)
+// z comes from Philox4x32-10 keyed by the caller's seed, counter = (pair index, iteration, 0, 0), and Box-Muller in
+// FP64 -- a counter-based stream that any host (the oracle, the JVM) can reproduce.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void add_normal_kernel(int r, uint64_t seed, const int* __restrict__ is, double* __restrict__ y) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;  // pair index: entries 2p, 2p + 1
+  if (2 * p >= r) return;
+  uint32_t x[4];
+  philox4x32_10((uint32_t)p, (uint32_t)is[IS_ITER], 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+  const double u1 = ((double)(x[0] >> 5) * 67108864.0 + (double)(x[1] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(x[2] >> 5) * 67108864.0 + (double)(x[3] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+  const double rad = sqrt(-2.0 * log(u1));
+  const double ang = 6.283185307179586476925 * u2;
+  y[2 * p] += rad * cos(ang);
+  if (2 * p + 1 < r) y[2 * p + 1] += rad * sin(ang);
+}
+
 // ---- small vector kernels -------------------------------------------------------------------------
 __global__ void check_finite_kernel(int n, const double* __restrict__ v, int* __restrict__ flag) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -463,25 +497,32 @@ __global__ void coeff_residual_kernel(int m0, int Ml, const double* __restrict__
 }
 
 // Commit the iteration (GingrAlgorithm.scala:193-208, :239-251): on success pose/scale/alpha/sigma2 are
-// replaced; a failed posterior leaves the state unchanged (status ModelFlexibilityError if iteration > 0), a
+// replaced; a failed posterior leaves the state unchanged (status ModelFlexibilityError if iteration > 0; in the
+// probabilistic branch only once the retry counter of :69-70 has run out), a
 // failed `coefficients` sets ModelFlexibilityError.  DS_R2 is left holding the rotation of the committed state.
-__global__ void finalize_kernel(int r, const double* __restrict__ alpha_new, double* __restrict__ alpha,
+__global__ void finalize_kernel(int r, int probabilistic, const double* __restrict__ alpha_new, double* __restrict__ alpha,
                                 double* __restrict__ ds, int* __restrict__ is) {
   __shared__ int mode;  // 0 commit, 1 keep
   if (threadIdx.x == 0) {
     const bool fail_post = is[IS_INFO] != 0 || is[IS_FAIL_POST] != 0;
     const bool fail_coef = is[IS_FAIL_COEF] != 0;
     if (fail_post) {
-      if (is[IS_ITER] > 0) is[IS_STATUS] = GINGR_STATUS_MODEL_FLEXIBILITY_ERROR;
-      mode = 1;
-    } else if (fail_coef) {
-      is[IS_STATUS] = GINGR_STATUS_MODEL_FLEXIBILITY_ERROR;
+      if (is[IS_ITER] > 0) {
+        if (probabilistic && is[IS_RETRY] != 0) is[IS_RETRY] -= 1;  // :197-202 retry: state returned unchanged
+        else is[IS_STATUS] = GINGR_STATUS_MODEL_FLEXIBILITY_ERROR;
+      }
       mode = 1;
     } else {
-      mode = 0;
-      ds[DS_SCALE] = ds[DS_NEW_SCALE];
-      for (int i = 0; i < 3; ++i) { ds[DS_T + i] = ds[DS_NEW_T + i]; ds[DS_EULER + i] = ds[DS_NEW_EULER + i]; }
-      ds[DS_SIGMA2] = ds[DS_NEW_SIGMA2];
+      is[IS_RETRY] = min(RETRY_COUNTER_INIT, is[IS_RETRY] + 1);  // :210
+      if (fail_coef) {
+        is[IS_STATUS] = GINGR_STATUS_MODEL_FLEXIBILITY_ERROR;
+        mode = 1;
+      } else {
+        mode = 0;
+        ds[DS_SCALE] = ds[DS_NEW_SCALE];
+        for (int i = 0; i < 3; ++i) { ds[DS_T + i] = ds[DS_NEW_T + i]; ds[DS_EULER + i] = ds[DS_NEW_EULER + i]; }
+        ds[DS_SIGMA2] = ds[DS_NEW_SIGMA2];
+      }
     }
     if (mode == 1) euler_to_matrix_dev(ds[DS_EULER], ds[DS_EULER + 1], ds[DS_EULER + 2], ds + DS_R2);
   }
@@ -526,6 +567,7 @@ struct gingr_registration {
   DevBuf<double> ds;
   DevBuf<int> is, flags;
   DevBuf<double> alpha;
+  int retry_counter = RETRY_COUNTER_INIT;  // mirror of the device counter, refreshed by download_state
   bool state_valid = false;
   gingr_state last_out;
   std::vector<double> last_alpha;
@@ -956,6 +998,7 @@ int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, cons
     A(cudaMemsetAsync(g->fit_local.p, 0, sizeof(double) * 3 * Mmax, ctx->stream));
     A(cudaMemsetAsync(g->ds.p, 0, sizeof(double) * DS_COUNT, ctx->stream));
     A(cudaMemsetAsync(g->is.p, 0, sizeof(int) * IS_COUNT, ctx->stream));
+    A(cudaMemcpyAsync(g->is.p + IS_RETRY, &g->retry_counter, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     A(cudaMemsetAsync(g->alpha.p, 0, sizeof(double) * rp, ctx->stream));
     A(cudaMemsetAsync(g->rows_ext.p, 0, sizeof(double) * ((size_t)4 * M + 8), ctx->stream));
     A(cudaStreamSynchronize(ctx->stream));
@@ -1051,6 +1094,7 @@ static int32_t upload_state(gingr_registration* g, const gingr_state* s, const d
   hi[IS_GT] = s->global_transformation;
   hi[IS_ITER] = s->iteration;
   hi[IS_STATUS] = s->status;
+  hi[IS_RETRY] = g->retry_counter;  // the counter belongs to the algorithm instance, not to the state (:70)
   double* ha = h + DS_COUNT + IS_COUNT;
   if ((size_t)(DS_COUNT + IS_COUNT + g->model->r) > ctx->h_pinned_count) {
     // large ranks: alpha goes straight from the caller's buffer
@@ -1079,7 +1123,7 @@ static int32_t evaluate_fit(gingr_registration* g, int off_s, int off_t, int off
   return gather_fit(ctx, m, g->fit_local.p, g->gathered.p, g->fit.p);
 }
 
-static int32_t enqueue_iteration(gingr_registration* g) {
+static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, uint64_t seed = 0) {
   gingr_ctx* ctx = g->ctx;
   const gingr_model* m = g->model;
   const gingr_target* tg = g->target;
@@ -1148,6 +1192,10 @@ static int32_t enqueue_iteration(gingr_registration* g) {
   GINGR_TRY(comm_allreduce_sum(ctx, g->Mx.p, (size_t)(r + 1) * rp));
   g->rec(8);
   GINGR_TRY(cholesky_enqueue(ctx, r, r + 1, g->Mx.p, rp, g->is.p + IS_INFO));
+  if (probabilistic) {  // posterior.sample() instead of posterior.mean (:211)
+    add_normal_kernel<<<ceil_div(ceil_div(r, 2), 128), 128, 0, st>>>(r, seed, g->is.p, rhs);
+    GINGR_LAUNCHED(ctx);
+  }
   GINGR_TRY(chol_backsolve_enqueue(ctx, r, g->Mx.p, rp, rhs, vec, g->flags.p));
   g->rec(9);
   check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, vec, g->is.p + IS_FAIL_POST);
@@ -1184,7 +1232,7 @@ static int32_t enqueue_iteration(gingr_registration* g) {
   check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, vec + 5 * rp, g->is.p + IS_FAIL_COEF);
   GINGR_LAUNCHED(ctx);
   // ---- commit, refresh the fit ------------------------------------------------------------------------------------------
-  finalize_kernel<<<1, 256, 0, st>>>(r, vec + 5 * rp, g->alpha.p, g->ds.p, g->is.p);
+  finalize_kernel<<<1, 256, 0, st>>>(r, probabilistic, vec + 5 * rp, g->alpha.p, g->ds.p, g->is.p);
   GINGR_LAUNCHED(ctx);
   GINGR_TRY(evaluate_fit(g, DS_SCALE, DS_T, DS_R2));
   g->rec(1);
@@ -1212,6 +1260,7 @@ static int32_t download_state(gingr_registration* g, gingr_state* out, double* a
   out->iteration = hi[IS_ITER];
   out->status = hi[IS_STATUS];
   out->rank = m->r;
+  g->retry_counter = hi[IS_RETRY];
   return GINGR_OK;
 }
 
@@ -1260,12 +1309,9 @@ int32_t gingr_initialize_state(gingr_registration* g, gingr_state* s, const doub
 
 int32_t gingr_update(gingr_registration* g, const gingr_state* state_in, const double* alpha_in, int32_t probabilistic,
                      uint64_t seed, gingr_state* state_out, double* alpha_out, double* fit_out) {
-  (void)seed;
   if (!g || !state_in || !alpha_in || !state_out || !alpha_out)
     return gingr_fail(g ? g->ctx : nullptr, GINGR_ERR_ARG, "gingr_update: bad argument");
   gingr_ctx* ctx = g->ctx;
-  if (probabilistic)
-    return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "probabilistic update (posterior.sample) is not implemented yet (SURVEY 8f.1)");
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const gingr_model* m = g->model;
   // Re-seed the device state unless the caller hands back exactly what the previous call returned
@@ -1280,7 +1326,7 @@ int32_t gingr_update(gingr_registration* g, const gingr_state* state_in, const d
     GINGR_LAUNCHED(ctx);
   }
   g->state_valid = false;
-  GINGR_TRY(enqueue_iteration(g));
+  GINGR_TRY(enqueue_iteration(g, probabilistic != 0, seed));
   GINGR_TRY(download_state(g, state_out, alpha_out, fit_out));
   g->last_out = *state_out;
   g->last_alpha.assign(alpha_out, alpha_out + m->r);
@@ -1296,6 +1342,19 @@ int32_t gingr_update_chain(gingr_registration* g, int32_t iters) {
   for (int k = 0; k < iters; ++k) {
     GINGR_TRY(enqueue_iteration(g));
     bump_iteration_kernel<<<1, 1, 0, ctx->stream>>>(g->is.p);  // GingrGeneratorWrapper.propose: updateIteration()
+    GINGR_LAUNCHED(ctx);
+  }
+  return GINGR_OK;
+}
+
+int32_t gingr_update_chain_sampled(gingr_registration* g, int32_t iters, uint64_t seed) {
+  if (!g || iters < 0) return gingr_fail(g ? g->ctx : nullptr, GINGR_ERR_ARG, "gingr_update_chain_sampled: bad argument");
+  gingr_ctx* ctx = g->ctx;
+  if (!g->state_valid) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_chain_sampled: no device-resident state");
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int k = 0; k < iters; ++k) {
+    GINGR_TRY(enqueue_iteration(g, 1, seed));  // the Philox counter carries the device iteration number
+    bump_iteration_kernel<<<1, 1, 0, ctx->stream>>>(g->is.p);
     GINGR_LAUNCHED(ctx);
   }
   return GINGR_OK;

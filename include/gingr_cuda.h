@@ -197,17 +197,24 @@ GINGR_API int32_t gingr_registration_set_landmarks(gingr_registration* reg, int3
  * model.mean for CPD without initialSigma) and evaluates the initial fit. */
 GINGR_API int32_t gingr_initialize_state(gingr_registration* reg, gingr_state* st /*in/out*/,
                                          const double* alpha /*[r]*/, double* fit_out /*[3M], may be NULL*/);
-/* GingrAlgorithm.update (GingrAlgorithm.scala:192-254) for the deterministic branch, followed by the
+/* GingrAlgorithm.update (GingrAlgorithm.scala:192-254), followed by the
  * fit refresh of GingrGeneratorWrapper.propose (sampling/generators/GingrGeneratorWrapper.scala:28-39)
  * delivered in fit_out (state_out->iteration is NOT incremented here: that stays with `propose`).
  * state_out->status is GINGR_STATUS_MODEL_FLEXIBILITY_ERROR exactly where the reference's Try fails;
- * the function's own return value is then GINGR_OK (the state carries the failure, as in the reference). */
+ * the function's own return value is then GINGR_OK (the state carries the failure, as in the reference).
+ * probabilistic != 0: posterior.sample() replaces posterior.mean (:211).  The coefficients are drawn from
+ * N(c, Minv) as c + L^-T z with z ~ N(0, I_r) from Philox4x32-10 (key = seed, counter = (pair, iteration, 0, 0)) +
+ * Box-Muller: the same distribution as scalismo's SVD-rotated basis, not the same draws.  The retry counter of
+ * GingrAlgorithm.scala:69-70, :197-202 lives in the registration handle. */
 GINGR_API int32_t gingr_update(gingr_registration* reg, const gingr_state* state_in, const double* alpha_in /*[r]*/,
                                int32_t probabilistic, uint64_t seed, gingr_state* state_out,
                                double* alpha_out /*[r]*/, double* fit_out /*[3M], may be NULL*/);
 /* Device-resident chaining for throughput runs: enqueue `iters` consecutive update+propose steps
  * starting from the state of the last gingr_update / gingr_initialize_state without host round trips. */
 GINGR_API int32_t gingr_update_chain(gingr_registration* reg, int32_t iters);
+/* The same with probabilistic = true in every step (a chain of informed posterior-sample proposals that are all
+ * accepted, i.e. GeneratorWrapperStochastic.gingrPropose without the MH accept/reject of the caller). */
+GINGR_API int32_t gingr_update_chain_sampled(gingr_registration* reg, int32_t iters, uint64_t seed);
 /* Read back the device-resident state after gingr_update_chain. */
 GINGR_API int32_t gingr_state_download(gingr_registration* reg, gingr_state* state_out, double* alpha_out,
                                        double* fit_out);

@@ -356,6 +356,7 @@ class Gpmm:
         n = pids.shape[0]
         QtL = np.einsum("nak,nab->kbn", Q.reshape(n, 3, -1), cov_inv).transpose(0, 2, 1).reshape(self.rank, 3 * n)
         Mx = QtL @ Q + np.eye(self.rank)
+        self._last_Mx = Mx   # kept for posterior sampling (test infrastructure convenience)
         Minv = breeze_pinv(Mx)
         y = np.asarray(values).reshape(-1)
         return Minv, QtL, y, m
@@ -561,7 +562,40 @@ def compute_posterior_coefficients(algo, st: State):
     return posed, c, Minv
 
 
-def update(algo, st: State, probabilistic: bool = False, rng=None) -> State:
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al. 2011), vectorised over numpy uint64 arrays holding 32-bit words."""
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & MASK for c in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0 & MASK), np.uint64(k1 & MASK)
+    for _ in range(10):
+        p0, p1 = np.uint64(M0) * c0, np.uint64(M1) * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & np.uint64(MASK), p1 >> np.uint64(32), p1 & np.uint64(MASK)
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0, k1 = (k0 + np.uint64(W0)) & np.uint64(MASK), (k1 + np.uint64(W1)) & np.uint64(MASK)
+    return c0, c1, c2, c3
+
+
+def standard_normals(r: int, seed: int, iteration: int):
+    """z[r] ~ N(0, 1): the stream gingr_update(probabilistic) uses (include/gingr_cuda.h): Philox4x32-10 with
+    key = seed, counter = (pair index, iteration, 0, 0), 53-bit uniforms, Box-Muller."""
+    npair = (r + 1) // 2
+    p = np.arange(npair, dtype=np.uint64)
+    zero = np.zeros(npair, dtype=np.uint64)
+    x0, x1, x2, x3 = philox4x32_10(p, zero + np.uint64(iteration & 0xFFFFFFFF), zero, zero, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u1 = ((x0 >> np.uint64(5)).astype(np.float64) * 67108864.0 + (x1 >> np.uint64(6)).astype(np.float64) + 0.5) / 9007199254740992.0
+    u2 = ((x2 >> np.uint64(5)).astype(np.float64) * 67108864.0 + (x3 >> np.uint64(6)).astype(np.float64) + 0.5) / 9007199254740992.0
+    rad = np.sqrt(-2.0 * np.log(u1))
+    ang = 6.283185307179586476925 * u2
+    z = np.empty(2 * npair)
+    z[0::2] = rad * np.cos(ang)
+    z[1::2] = rad * np.sin(ang)
+    return z[:r]
+
+
+RETRY_COUNTER_INIT = 10  # GingrAlgorithm.scala:69-70
+
+
+def update(algo, st: State, probabilistic: bool = False, seed: int = 0) -> State:
     """GingrAlgorithm.update, literal.  api/GingrAlgorithm.scala:192-254"""
     try:
         with np.errstate(all="ignore"):
@@ -569,12 +603,21 @@ def update(algo, st: State, probabilistic: bool = False, rng=None) -> State:
         if not np.all(np.isfinite(c_post)):
             raise FloatingPointError("posterior not finite")
     except (FloatingPointError, np.linalg.LinAlgError, ValueError):
-        if st.iteration > 0:                                              # :195-205 (deterministic branch)
+        if st.iteration > 0:                                              # :195-205
+            if probabilistic and getattr(algo, "retry_counter", RETRY_COUNTER_INIT) != 0:
+                algo.retry_counter = getattr(algo, "retry_counter", RETRY_COUNTER_INIT) - 1   # :200-201
+                return st
             return dataclasses.replace(st, status=STATUS_MODEL_FLEXIBILITY_ERROR)
         return st                                                         # :206-208
+    algo.retry_counter = min(RETRY_COUNTER_INIT, getattr(algo, "retry_counter", RETRY_COUNTER_INIT) + 1)   # :210
     if probabilistic:
-        raise NotImplementedError("posterior.sample() path is SURVEY 8(f) item 1")
-    shapeproposal = posed.instance(c_post)                                # posterior.mean  :211
+        # posterior.sample() :211 [scalismo-recalled A3]: coefficients ~ N(c, Minv).  scalismo draws them as
+        # D^-1 U_s sqrt(s) z from svd(D Minv D); the same law is c + L^-T z with Mx = L L^T, which is the form
+        # (and the z stream) libgingr_cuda documents -- identical distribution, different individual draws.
+        L = np.linalg.cholesky(posed._last_Mx)
+        z = standard_normals(st.model.rank, seed, st.iteration)
+        c_post = c_post + np.linalg.solve(L.T, z)
+    shapeproposal = posed.instance(c_post)                                # posterior.mean | sample  :211
     transformed_init = posed                                              # :212 (same transform)
     try:
         new_coeffs = transformed_init.coefficients(shapeproposal)         # :214-216
@@ -603,10 +646,10 @@ def update(algo, st: State, probabilistic: bool = False, rng=None) -> State:
     return dataclasses.replace(new_state, sigma2=float(sigma2))
 
 
-def propose(algo, st: State, probabilistic: bool = False) -> State:
+def propose(algo, st: State, probabilistic: bool = False, seed: int = 0) -> State:
     """GingrGeneratorWrapper.propose: update, refresh fit, iteration += 1.
     api/sampling/generators/GingrGeneratorWrapper.scala:28-39"""
-    ns = update(algo, st, probabilistic)
+    ns = update(algo, st, probabilistic, seed)
     fit = model_instance_shape_pose_scale(ns.model, ns.params)
     return dataclasses.replace(ns, fit=fit, iteration=ns.iteration + 1)
 

@@ -225,3 +225,34 @@ def test_icp_update_runs(oracle):
     out = oracle.run(algo, st)
     assert out.iteration == 4 and out.status == oracle.STATUS_MAX_ITERATION
     assert np.all(np.isfinite(out.fit))
+
+
+def test_philox_known_answers(oracle):
+    """Random123 known-answer vectors for Philox4x32-10 (kat_vectors of the Random123 distribution)."""
+    out = oracle.philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(v[0]) for v in out] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xffffffff
+    out = oracle.philox4x32_10([f], [f], [f], [f], f, f)
+    assert [int(v[0]) for v in out] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    out = oracle.philox4x32_10([0x243f6a88], [0x85a308d3], [0x13198a2e], [0x03707344], 0xa4093822, 0x299f31d0)
+    assert [int(v[0]) for v in out] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_standard_normals_moments_and_counter_separation(oracle):
+    z = oracle.standard_normals(200001, 99, 3)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01 and np.all(np.isfinite(z))
+    assert abs(np.mean(z ** 4) - 3.0) < 0.1
+    assert not np.array_equal(z[:100], oracle.standard_normals(100, 99, 4))
+    assert not np.array_equal(z[:100], oracle.standard_normals(100, 98, 3))
+    assert np.array_equal(z[:101], oracle.standard_normals(101, 99, 3))
+
+
+def test_posterior_sample_has_covariance_minv(oracle):
+    """c + L^-T z with Mx = L L^T has covariance L^-T L^-1 = Minv, the covariance of scalismo's posterior
+    (SURVEY.md A3): checked exactly through the unit vectors z = e_k."""
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(40, 12))
+    Mx = A.T @ A + np.eye(12)
+    L = np.linalg.cholesky(Mx)
+    S = np.linalg.solve(L.T, np.eye(12))
+    np.testing.assert_allclose(S @ S.T, oracle.breeze_pinv(Mx), rtol=1e-10, atol=1e-12)

@@ -229,3 +229,78 @@ def test_update_resumes_from_device_state(ctx, oracle):
     assert np.array_equal(s2.fit, t2.fit) and np.array_equal(s2.modelParameters.shape, t2.modelParameters.shape)
     reg.close()
     reg2.close()
+
+
+@pytest.mark.parametrize("algo", ["cpd", "icp"])
+def test_probabilistic_update_matches_oracle(ctx, oracle, algo):
+    """update(current, probabilistic = true): posterior.sample() (GingrAlgorithm.scala:211) with the documented
+    Philox/Box-Muller stream -- coefficients c + L^-T z.  Same tolerances as the deterministic branch."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 150, 170, 30, seed=11)
+    diag = np.linalg.norm(m.ref.max(0) - m.ref.min(0))
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    if algo == "cpd":
+        reg = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration(w=0.05))
+        oalgo = oracle.CpdAlgorithm(oracle.CpdConfig(w=0.05))
+    else:
+        reg = api.IcpRegistration(ctx, dm, dt, api.IcpConfiguration(initialSigma=3.0, endSigma=1.0))
+        oalgo = oracle.IcpAlgorithm(oracle.IcpConfig(initial_sigma=3.0, end_sigma=1.0))
+    ost = oalgo.initialize(oracle.initial_state(m, target, tt, global_transformation=oracle.RIGID_TRANSFORMS))
+    det = oracle.propose(oalgo, ost)
+    for it in range(4):
+        seed = 0x1234567890ABCDEF + it
+        gst = reg.propose(_to_api_state(ost, api), probabilistic=True, seed=seed)
+        ost = oracle.propose(oalgo, ost, probabilistic=True, seed=seed)
+        _compare(gst, ost, diag)
+        assert gst.generatedBy == "Stochastic"
+    # the sample is not the mean
+    assert np.max(np.abs(ost.params.shape - det.params.shape)) > 1e-3
+    reg.close()
+
+
+def test_probabilistic_chain_is_reproducible_and_seed_dependent(ctx, oracle):
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 120, 130, 24, seed=12)
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    outs = []
+    for seed in (7, 7, 8):
+        reg = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration(w=0.1))
+        reg.initializeState()
+        reg.updateChainSampled(5, seed)
+        outs.append(reg.downloadState())
+        reg.close()
+    assert np.array_equal(outs[0].fit, outs[1].fit) and outs[0].iteration == 5
+    assert not np.array_equal(outs[0].fit, outs[2].fit)
+    # against the oracle, step by step with the device's iteration counter as the Philox counter
+    oalgo = oracle.CpdAlgorithm(oracle.CpdConfig(w=0.1))
+    ost = oalgo.initialize(oracle.initial_state(m, target, tt, global_transformation=oracle.RIGID_TRANSFORMS))
+    for _ in range(5):
+        ost = oracle.propose(oalgo, ost, probabilistic=True, seed=7)
+    diag = np.linalg.norm(m.ref.max(0) - m.ref.min(0))
+    assert np.max(np.abs(outs[0].fit - ost.fit)) < 1e-6 * diag
+
+
+def test_probabilistic_retry_counter(ctx, oracle):
+    """A failing posterior in the probabilistic branch returns the state unchanged retryCounter (= 10) times and
+    only then sets ModelFlexibilityError (GingrAlgorithm.scala:69-70, :195-202)."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 60, 60, 20, seed=6)
+    target = target.copy()
+    target[0] = [5000.0, 0.0, 0.0]
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target)
+    reg = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration(initialSigma=0.5))
+    oalgo = oracle.CpdAlgorithm(oracle.CpdConfig(initial_sigma=0.5))
+    ost = oalgo.initialize(oracle.initial_state(m, target, None, global_transformation=oracle.NO_TRANSFORMS))
+    gst = _to_api_state(ost, api)
+    statuses_g, statuses_o = [], []
+    for it in range(13):
+        gst = reg.propose(gst, probabilistic=True, seed=it)
+        ost = oracle.propose(oalgo, ost, probabilistic=True, seed=it)
+        statuses_g.append(gst.status)
+        statuses_o.append(ost.status)
+    assert statuses_g == statuses_o
+    assert statuses_g[:11] == [api.STATUS_NONE] * 11 and statuses_g[11] == api.STATUS_MODEL_FLEXIBILITY_ERROR
+    reg.close()
