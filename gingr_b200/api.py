@@ -189,6 +189,21 @@ def icp_closest(ctx: Context, target: Target, template_points, template_triangle
     return idx, cp, w, float(md.value)
 
 
+def icp_closest_reversal(ctx: Context, target: Target, template_points, template_triangles, method: int):
+    """closestPointCorrespondenceReversal (ClosestPointRegistrator.scala:34-45): per TARGET vertex j the template
+    vertex id its correspondence maps back to and the 0/1 weight; the observation is (tpl_id[j], target[j], w[j])."""
+    tpl = nat.f64(template_points).reshape(-1, 3)
+    M = tpl.shape[0]
+    tri = None if template_triangles is None else nat.i32(template_triangles).reshape(-1, 3)
+    T = 0 if tri is None else tri.shape[0]
+    tid = np.empty(target.N, dtype=np.int32)
+    w = np.empty(target.N, dtype=np.uint8)
+    md = ctypes.c_double()
+    ctx.check(ctx._lib.gingr_icp_closest_reversal(ctx.handle, target.handle, M, nat.as_dp(tpl), nat.as_ip(tri), T,
+                                                  int(method), nat.as_ip(tid), nat.as_bp(w), ctypes.byref(md)))
+    return tid, w, float(md.value)
+
+
 def posterior_mean(ctx: Context, model: Model, R, t, pids, points, noise):
     """model.transform(R, t).posterior(obs).mean -> (coefficients[r], mean mesh points[M,3]).
     noise: [n] isotropic variances or [n,3,3] covariances.  (GingrAlgorithm.scala:297-301)"""

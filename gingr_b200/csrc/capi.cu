@@ -128,6 +128,8 @@ int32_t gingr_target_upload(gingr_ctx* ctx, int32_t N, const double* pts, const 
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(s->a.p, pts, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
   GINGR_CUDA_TRY(ctx, t->verts.alloc((size_t)3 * N));
   GINGR_TRY(gingr::aos_to_soa_enqueue(ctx, N, s->a.p, t->verts.p));
+  GINGR_CUDA_TRY(ctx, t->aos.alloc((size_t)3 * N));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(t->aos.p, s->a.p, sizeof(double) * 3 * (size_t)N, cudaMemcpyDeviceToDevice, ctx->stream));
   if (t->N > 0) {
     GINGR_CUDA_TRY(ctx, t->soa.alloc((size_t)3 * t->N));
     GINGR_TRY(gingr::aos_to_soa_enqueue(ctx, t->N, s->a.p + (size_t)3 * t->n0, t->soa.p));
@@ -153,6 +155,7 @@ int32_t gingr_target_destroy(gingr_target* t) {
   cudaSetDevice(t->ctx->device);
   t->soa.release();
   t->verts.release();
+  t->aos.release();
   t->tri.release();
   t->normals.release();
   t->boundary.release();
@@ -292,51 +295,121 @@ int32_t gingr_cpd_initial_sigma2(gingr_ctx* ctx, const gingr_target* target, int
 // ---------------------------------------------------------------------------------------------
 // K2 entry point
 // ---------------------------------------------------------------------------------------------
+// shared by the two K2 entry points: uploads the template, computes its normals / boundary flags
+struct TemplateUpload {
+  DevBuf<double> aos, soa, normals;
+  DevBuf<int32_t> tri, off, adj;
+  DevBuf<uint8_t> boundary;
+  void release() { aos.release(); soa.release(); normals.release(); tri.release(); off.release(); adj.release(); boundary.release(); }
+};
+
+static int32_t upload_template(gingr_ctx* ctx, int M, const double* tpl, const int32_t* tpl_tri, int T, TemplateUpload* u,
+                               gingr::MeshView* view) {
+  cudaStream_t st = ctx->stream;
+  GINGR_CUDA_TRY(ctx, u->aos.alloc((size_t)3 * M));
+  GINGR_CUDA_TRY(ctx, u->soa.alloc((size_t)3 * M));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(u->aos.p, tpl, sizeof(double) * 3 * (size_t)M, cudaMemcpyHostToDevice, st));
+  GINGR_TRY(gingr::aos_to_soa_enqueue(ctx, M, u->aos.p, u->soa.p));
+  view->n = M;
+  view->aos = u->aos.p;
+  view->soa = u->soa.p;
+  view->T = T;
+  if (T > 0) {
+    for (int k = 0; k < 3 * T; ++k)
+      if (tpl_tri[k] < 0 || tpl_tri[k] >= M) return gingr_fail(ctx, GINGR_ERR_ARG, "template triangle index out of range");
+    std::vector<int32_t> off, adj;
+    std::vector<uint8_t> flags;
+    gingr::build_vertex_adjacency(M, T, tpl_tri, &off, &adj);
+    gingr::compute_boundary_flags(M, T, tpl_tri, &flags);
+    GINGR_CUDA_TRY(ctx, u->tri.alloc((size_t)3 * T));
+    GINGR_CUDA_TRY(ctx, u->off.alloc(off.size()));
+    GINGR_CUDA_TRY(ctx, u->adj.alloc(adj.size()));
+    GINGR_CUDA_TRY(ctx, u->normals.alloc((size_t)3 * M));
+    GINGR_CUDA_TRY(ctx, u->boundary.alloc((size_t)M));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(u->tri.p, tpl_tri, sizeof(int32_t) * 3 * (size_t)T, cudaMemcpyHostToDevice, st));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(u->off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(u->adj.p, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice, st));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(u->boundary.p, flags.data(), (size_t)M, cudaMemcpyHostToDevice, st));
+    GINGR_TRY(gingr::vertex_normals_enqueue(ctx, M, u->aos.p, u->tri.p, u->off.p, u->adj.p, u->normals.p));
+    GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // off / adj / flags are stack vectors
+    view->tri = u->tri.p;
+    view->normals = u->normals.p;
+    view->boundary = u->boundary.p;
+  }
+  return GINGR_OK;
+}
+
+static gingr::MeshView target_view(const gingr_target* t) {
+  gingr::MeshView v;
+  v.n = t->N_total;
+  v.aos = t->aos.p;
+  v.soa = t->verts.p;
+  v.T = t->T;
+  v.tri = t->tri.p;
+  v.normals = t->normals.p;
+  v.boundary = t->boundary.p;
+  return v;
+}
+
 int32_t gingr_icp_closest(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* tpl,
                           const int32_t* tpl_tri, int32_t T, int32_t method, int32_t* idx, double* cp, uint8_t* w,
                           double* mean_distance) {
   if (!ctx || !target || !tpl || M <= 0 || T < 0 || (T > 0 && !tpl_tri))
     return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_icp_closest: bad argument");
-  CtxScratch* s = scratch_of(ctx);
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   gingr::ClosestWorkspace ws;
+  TemplateUpload up;
+  gingr::MeshView tv;
   int32_t rc = ws.ensure(ctx, M, target->N_total, target->T, T);
-  DevBuf<int32_t> d_tri, d_off, d_adj;
-  auto cleanup = [&]() {
-    ws.release();
-    d_tri.release();
-    d_off.release();
-    d_adj.release();
-  };
-  if (rc < 0) { cleanup(); return rc; }
-  GINGR_CUDA_TRY(ctx, s->a.alloc((size_t)3 * M));
-  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(s->a.p, tpl, sizeof(double) * 3 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
-  if (T > 0) {
-    for (int k = 0; k < 3 * T; ++k)
-      if (tpl_tri[k] < 0 || tpl_tri[k] >= M) {
-        cleanup();
-        return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_icp_closest: template triangle index out of range");
-      }
-    std::vector<int32_t> off, adj;
-    gingr::build_vertex_adjacency(M, T, tpl_tri, &off, &adj);
-    GINGR_CUDA_TRY(ctx, d_tri.alloc((size_t)3 * T));
-    GINGR_CUDA_TRY(ctx, d_off.alloc(off.size()));
-    GINGR_CUDA_TRY(ctx, d_adj.alloc(adj.size()));
-    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_tri.p, tpl_tri, sizeof(int32_t) * 3 * (size_t)T, cudaMemcpyHostToDevice, ctx->stream));
-    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(d_adj.p, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // off/adj are stack vectors
-  }
-  rc = gingr::icp_closest_enqueue(ctx, ws, target, M, s->a.p, T, d_tri.p, d_off.p, d_adj.p, method);
-  if (rc < 0) { cudaStreamSynchronize(ctx->stream); cleanup(); return rc; }
+  if (rc >= 0) rc = upload_template(ctx, M, tpl, tpl_tri, T, &up, &tv);
+  if (rc >= 0) rc = gingr::icp_correspondence_enqueue(ctx, ws, tv, target_view(target), method);
   cudaStream_t st = ctx->stream;
   cudaError_t e = cudaSuccess;
-  if (idx && e == cudaSuccess) e = cudaMemcpyAsync(idx, ws.idx.p, sizeof(int32_t) * (size_t)M, cudaMemcpyDeviceToHost, st);
-  if (cp && e == cudaSuccess) e = cudaMemcpyAsync(cp, ws.cp.p, sizeof(double) * 3 * (size_t)M, cudaMemcpyDeviceToHost, st);
-  if (w && e == cudaSuccess) e = cudaMemcpyAsync(w, ws.w.p, (size_t)M, cudaMemcpyDeviceToHost, st);
-  if (mean_distance && e == cudaSuccess) e = cudaMemcpyAsync(mean_distance, ws.mean_dist.p, sizeof(double), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cleanup();
+  if (rc >= 0) {
+    if (idx && e == cudaSuccess) e = cudaMemcpyAsync(idx, ws.idx.p, sizeof(int32_t) * (size_t)M, cudaMemcpyDeviceToHost, st);
+    if (cp && e == cudaSuccess) e = cudaMemcpyAsync(cp, ws.cp.p, sizeof(double) * 3 * (size_t)M, cudaMemcpyDeviceToHost, st);
+    if (w && e == cudaSuccess) e = cudaMemcpyAsync(w, ws.w.p, (size_t)M, cudaMemcpyDeviceToHost, st);
+    if (mean_distance && e == cudaSuccess) e = cudaMemcpyAsync(mean_distance, ws.mean_dist.p, sizeof(double), cudaMemcpyDeviceToHost, st);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = e2;
+  ws.release();
+  up.release();
+  if (rc < 0) return rc;
+  GINGR_CUDA_TRY(ctx, e);
+  return GINGR_OK;
+}
+
+int32_t gingr_icp_closest_reversal(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* tpl,
+                                   const int32_t* tpl_tri, int32_t T, int32_t method, int32_t* tpl_id, uint8_t* w,
+                                   double* mean_distance) {
+  if (!ctx || !target || !tpl || M <= 0 || T < 0 || (T > 0 && !tpl_tri))
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_icp_closest_reversal: bad argument");
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int N = target->N_total;
+  gingr::ClosestWorkspace ws;
+  TemplateUpload up;
+  gingr::MeshView tv;
+  DevBuf<int32_t> tid;
+  int32_t rc = ws.ensure(ctx, N, M, T, target->T);
+  if (rc >= 0) rc = upload_template(ctx, M, tpl, tpl_tri, T, &up, &tv);
+  // corr = closestPointCorrespondence(target, template): the roles are swapped (:38)
+  if (rc >= 0) rc = gingr::icp_correspondence_enqueue(ctx, ws, target_view(target), tv, method);
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = tid.alloc((size_t)N);
+  // templateId = template.pointSet.findClosestPoint(p).id for the corresponding point p (:40)
+  if (rc >= 0 && e == cudaSuccess) rc = gingr::nn_vertex_enqueue(ctx, ws, N, ws.cp.p, M, up.soa.p, ws.d2.p, tid.p);
+  if (rc >= 0) {
+    if (tpl_id && e == cudaSuccess) e = cudaMemcpyAsync(tpl_id, tid.p, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, st);
+    if (w && e == cudaSuccess) e = cudaMemcpyAsync(w, ws.w.p, (size_t)N, cudaMemcpyDeviceToHost, st);
+    if (mean_distance && e == cudaSuccess) e = cudaMemcpyAsync(mean_distance, ws.mean_dist.p, sizeof(double), cudaMemcpyDeviceToHost, st);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = e2;
+  ws.release();
+  up.release();
+  tid.release();
+  if (rc < 0) return rc;
   GINGR_CUDA_TRY(ctx, e);
   return GINGR_OK;
 }

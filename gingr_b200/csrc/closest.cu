@@ -183,36 +183,43 @@ __global__ void surface_reduce_kernel(int M, int splits, const double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// isClosestPointIntersecting (:62-72): for query vertex i of the template with direction v = p - cp,
-// the minimum distance from p to an intersection (!= p) of the infinite line p + s v with the template
-// mesh.  Triangles incident to vertex i only touch the line at p itself (the reference drops those hits
-// with `.filter(f => f != p)`), so they are skipped.
+// Intersections of the infinite line o + s d with a mesh (scalismo getIntersectionPoints), hits
+// equal to o dropped (`.filter(f => f != p)`), nearest hit kept (strict <, ascending triangle id: lowest id on
+// ties).  Two users:
+//   isClosestPointIntersecting (:62-72)   o = vertex i of the mesh itself, d = o - cp_i; triangles incident to
+//                                         vertex i only touch the line at o and are skipped (SELF = true)
+//   ClosestPointAlongNormal (:105-110)    o = template vertex, d = its normal, mesh = the target (SELF = false);
+//                                         the hit point itself is needed (WITH_POINT = true)
+// DIFF = true: the direction is o - other[i] (computed in registers), else other[i] is the direction.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(QT) line_mesh_kernel(int M, const double* __restrict__ p /*AoS*/,
-                                                       const double* __restrict__ cp /*AoS*/, int T,
+template <bool SELF, bool DIFF, bool WITH_POINT>
+__global__ void __launch_bounds__(QT) line_mesh_kernel(int M, const double* __restrict__ o /*AoS*/,
+                                                       const double* __restrict__ other /*AoS*/,
+                                                       const double* __restrict__ mesh /*AoS vertices*/, int T,
                                                        const int32_t* __restrict__ tri,
-                                                       double* __restrict__ part_min) {
+                                                       double* __restrict__ part_min, double* __restrict__ part_pt) {
   __shared__ double st[TT][9];
   __shared__ int32_t sv[TT][3];
   const int i = blockIdx.x * QT + threadIdx.x;
   const int per = (T + gridDim.y - 1) / gridDim.y;
   const int t_begin = blockIdx.y * per, t_end = min(T, t_begin + per);
   const int ii = min(i, M - 1);
-  const double ox = p[3 * ii], oy = p[3 * ii + 1], oz = p[3 * ii + 2];
-  const double dx = ox - cp[3 * ii], dy = oy - cp[3 * ii + 1], dz = oz - cp[3 * ii + 2];
-  double best = INFINITY;
+  const double ox = o[3 * ii], oy = o[3 * ii + 1], oz = o[3 * ii + 2];
+  double dx = other[3 * ii], dy = other[3 * ii + 1], dz = other[3 * ii + 2];
+  if (DIFF) { dx = ox - dx; dy = oy - dy; dz = oz - dz; }
+  double best = INFINITY, bx = ox, by = oy, bz = oz;
   for (int t0 = t_begin; t0 < t_end; t0 += TT) {
     const int cnt = min(TT, t_end - t0);
     __syncthreads();
     for (int e = threadIdx.x; e < cnt * 9; e += QT) {
       const int t = e / 9, k = e % 9;
       const int v = tri[3 * (t0 + t) + k / 3];
-      st[t][k] = p[3 * v + (k % 3)];
+      st[t][k] = mesh[3 * v + (k % 3)];
       if (k % 3 == 0) sv[t][k / 3] = v;
     }
     __syncthreads();
     for (int t = 0; t < cnt; ++t) {
-      if (sv[t][0] == ii || sv[t][1] == ii || sv[t][2] == ii) continue;
+      if (SELF && (sv[t][0] == ii || sv[t][1] == ii || sv[t][2] == ii)) continue;
       const double* a = &st[t][0];
       const double e1x = st[t][3] - a[0], e1y = st[t][4] - a[1], e1z = st[t][5] - a[2];
       const double e2x = st[t][6] - a[0], e2y = st[t][7] - a[1], e2z = st[t][8] - a[2];
@@ -231,10 +238,46 @@ __global__ void __launch_bounds__(QT) line_mesh_kernel(int M, const double* __re
       if (ix == ox && iy == oy && iz == oz) continue;
       const double ex = ox - ix, ey = oy - iy, ez = oz - iz;
       const double d = sqrt(ex * ex + ey * ey + ez * ez);
-      if (d < best) best = d;
+      if (d < best) {
+        best = d;
+        if (WITH_POINT) { bx = ix; by = iy; bz = iz; }
+      }
     }
   }
-  if (i < M) part_min[(size_t)blockIdx.y * M + i] = best;
+  if (i < M) {
+    const size_t oidx = (size_t)blockIdx.y * M + i;
+    part_min[oidx] = best;
+    if (WITH_POINT) {
+      part_pt[3 * oidx] = bx;
+      part_pt[3 * oidx + 1] = by;
+      part_pt[3 * oidx + 2] = bz;
+    }
+  }
+}
+
+// nearest hit over the triangle-range splits (lowest range first on ties); no hit: dist = 0, point = o, hit = 0
+// (ClosestPointRegistrator.scala:127 "return p to avoid influencing the distance measure")
+__global__ void line_hit_reduce_kernel(int M, int splits, const double* __restrict__ o,
+                                       const double* __restrict__ part_min, const double* __restrict__ part_pt,
+                                       double* __restrict__ dist, double* __restrict__ pt, uint8_t* __restrict__ hit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  double best = INFINITY;
+  int bk = -1;
+  for (int k = 0; k < splits; ++k) {
+    const double d = part_min[(size_t)k * M + i];
+    if (d < best) { best = d; bk = k; }
+  }
+  if (bk >= 0) {
+    const size_t oidx = (size_t)bk * M + i;
+    dist[i] = best;
+    pt[3 * i] = part_pt[3 * oidx]; pt[3 * i + 1] = part_pt[3 * oidx + 1]; pt[3 * i + 2] = part_pt[3 * oidx + 2];
+    hit[i] = 1;
+  } else {
+    dist[i] = 0.0;
+    pt[3 * i] = o[3 * i]; pt[3 * i + 1] = o[3 * i + 1]; pt[3 * i + 2] = o[3 * i + 2];
+    hit[i] = 0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -273,12 +316,15 @@ __global__ void vertex_normals_kernel(int n, const double* __restrict__ v, const
 __global__ void icp_weights_kernel(int M, const double* __restrict__ p, const double* __restrict__ cp,
                                    const int32_t* __restrict__ idx, const uint8_t* __restrict__ tgt_boundary,
                                    const double* __restrict__ n_tpl /*AoS*/, const double* __restrict__ n_tgt /*AoS*/,
-                                   int splits, const double* __restrict__ min_part, uint8_t* __restrict__ w) {
+                                   int splits, const double* __restrict__ min_part,
+                                   const uint8_t* __restrict__ hit /*may be null*/, uint8_t* __restrict__ w) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   const int j = idx[i];
   uint8_t out = 1;
-  if (tgt_boundary[j]) {
+  if (hit && !hit[i]) {
+    out = 0;  // no intersection along the normal (:127)
+  } else if (tgt_boundary[j]) {
     out = 0;
   } else {
     const double dot = n_tpl[3 * i] * n_tgt[3 * j] + n_tpl[3 * i + 1] * n_tgt[3 * j + 1] + n_tpl[3 * i + 2] * n_tgt[3 * j + 2];
@@ -304,11 +350,11 @@ __global__ void gather_points_kernel(int M, const int32_t* __restrict__ idx, int
   out[3 * i + 2] = soa[2 * N + j];
 }
 
-// deterministic mean of sqrt(d2): one block, fixed-order tree
-__global__ void mean_sqrt_kernel(int M, const double* __restrict__ d2, double* __restrict__ out) {
+// deterministic mean of sqrt(d2) (squared = 1) or of d2 itself (squared = 0): one block, fixed-order tree
+__global__ void mean_sqrt_kernel(int M, const double* __restrict__ d2, double* __restrict__ out, int squared = 1) {
   __shared__ double red[256];
   double s = 0.0;
-  for (int i = threadIdx.x; i < M; i += 256) s += sqrt(d2[i]);
+  for (int i = threadIdx.x; i < M; i += 256) s += squared ? sqrt(d2[i]) : d2[i];
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -398,19 +444,20 @@ static int pick_splits(const gingr_ctx* ctx, int M, int candidates, int tile) {
   return std::max(1, std::min(want, ceil_div(candidates, tile)));
 }
 
-int32_t ClosestWorkspace::ensure(gingr_ctx* ctx, int M, int N, int T_target, int T_template) {
-  s_nn = pick_splits(ctx, M, N, PT);
-  s_surf = T_target > 0 ? pick_splits(ctx, M, T_target, TT) : 1;
-  s_line = T_template > 0 ? pick_splits(ctx, M, T_template, TT) : 1;
+int32_t ClosestWorkspace::ensure(gingr_ctx* ctx, int nq, int n_search, int T_search, int T_query_mesh) {
+  const int M = nq;
+  s_nn = pick_splits(ctx, M, n_search, PT);
+  s_surf = T_search > 0 ? pick_splits(ctx, M, T_search, TT) : 1;
+  s_line = T_query_mesh > 0 ? pick_splits(ctx, M, T_query_mesh, TT) : 1;
   const int smax = std::max(s_nn, std::max(s_surf, s_line));
   GINGR_CUDA_TRY(ctx, part_d2.alloc((size_t)smax * M));
   GINGR_CUDA_TRY(ctx, part_idx.alloc((size_t)smax * M));
-  GINGR_CUDA_TRY(ctx, part_cp.alloc((size_t)3 * s_surf * M));
+  GINGR_CUDA_TRY(ctx, part_cp.alloc((size_t)3 * std::max(s_surf, s_line) * M));
   GINGR_CUDA_TRY(ctx, d2.alloc((size_t)M));
   GINGR_CUDA_TRY(ctx, idx.alloc((size_t)M));
   GINGR_CUDA_TRY(ctx, cp.alloc((size_t)3 * M));
   GINGR_CUDA_TRY(ctx, w.alloc((size_t)M));
-  GINGR_CUDA_TRY(ctx, n_tpl.alloc((size_t)3 * M));
+  GINGR_CUDA_TRY(ctx, hit.alloc((size_t)M));
   GINGR_CUDA_TRY(ctx, mean_dist.alloc(1));
   return GINGR_OK;
 }
@@ -423,64 +470,116 @@ void ClosestWorkspace::release() {
   idx.release();
   cp.release();
   w.release();
-  n_tpl.release();
+  hit.release();
   mean_dist.release();
 }
 
-// Nearest target vertex of arbitrary query points (AoS, device).
+// Nearest vertex (of a SoA point set) of arbitrary query points (AoS, device).
 int32_t nn_vertex_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, const double* d_q, int N,
                           const double* d_pts_soa, double* d_d2, int32_t* d_idx) {
-  nn_vertex_kernel<<<dim3(ceil_div(M, QT), ws.s_nn), QT, 0, ctx->stream>>>(M, d_q, N, d_pts_soa, ws.part_d2.p,
+  const int splits = std::min(ws.s_nn, std::max(1, ceil_div(N, PT)));
+  nn_vertex_kernel<<<dim3(ceil_div(M, QT), splits), QT, 0, ctx->stream>>>(M, d_q, N, d_pts_soa, ws.part_d2.p,
                                                                           ws.part_idx.p);
   GINGR_LAUNCHED(ctx);
-  nn_reduce_kernel<<<ceil_div(M, 128), 128, 0, ctx->stream>>>(M, ws.s_nn, ws.part_d2.p, ws.part_idx.p, d_d2, d_idx);
+  nn_reduce_kernel<<<ceil_div(M, 128), 128, 0, ctx->stream>>>(M, splits, ws.part_d2.p, ws.part_idx.p, d_d2, d_idx);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
 }
 
-// The ICP correspondence of one flavour.  Template: d_tpl (AoS [M][3]), triangles/adjacency on device.
-// Results in ws.idx / ws.cp / ws.w / ws.mean_dist.
-int32_t icp_closest_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const gingr_target* tgt, int M, const double* d_tpl,
-                            int T_tpl, const int32_t* d_tpl_tri, const int32_t* d_adj_off, const int32_t* d_adj,
-                            int method) {
+// closestPointCorrespondence(template, target) of one flavour (ClosestPointRegistrator.scala:74-160).  Both meshes
+// are views; for the reversed direction (:34-45) the caller swaps them.  Needs: tpl.aos, (tpl.tri, tpl.normals for
+// the mesh flavours); tgt.soa, (tgt.aos, tgt.tri, tgt.normals, tgt.boundary for the mesh flavours).
+// Results for the tpl.n template vertices in ws.idx (nearest target vertex) / ws.cp / ws.w / ws.mean_dist.
+int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const MeshView& tpl, const MeshView& tgt,
+                                   int method) {
   cudaStream_t st = ctx->stream;
-  const int N = tgt->N_total;
+  const int M = tpl.n, N = tgt.n;
   if (method == GINGR_POINTCLOUD_CLOSEST_POINT) {
-    GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, d_tpl, N, tgt->verts.p, ws.d2.p, ws.idx.p));
-    gather_points_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, ws.idx.p, N, tgt->verts.p, ws.cp.p);
+    GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, tpl.aos, N, tgt.soa, ws.d2.p, ws.idx.p));
+    gather_points_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, ws.idx.p, N, tgt.soa, ws.cp.p);
     GINGR_LAUNCHED(ctx);
     GINGR_CUDA_TRY(ctx, cudaMemsetAsync(ws.w.p, 1, (size_t)M, st));
-  } else if (method == GINGR_TRIANGULAR_CLOSEST_POINT) {
-    if (tgt->T <= 0 || T_tpl <= 0)
-      return gingr_fail(ctx, GINGR_ERR_ARG, "TriangularClosestPoint needs target and template triangles");
-    surface_kernel<<<dim3(ceil_div(M, QT), ws.s_surf), QT, 0, st>>>(M, d_tpl, N, tgt->verts.p, tgt->T, tgt->tri.p,
-                                                                    ws.part_d2.p, ws.part_idx.p, ws.part_cp.p);
+    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.d2.p, ws.mean_dist.p);
     GINGR_LAUNCHED(ctx);
-    surface_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, ws.s_surf, ws.part_d2.p, ws.part_idx.p, ws.part_cp.p,
+    GINGR_CUDA_TRY(ctx, cudaGetLastError());
+    return GINGR_OK;
+  }
+  if (tgt.T <= 0 || tpl.T <= 0 || !tpl.normals || !tgt.normals || !tgt.boundary || !tgt.aos)
+    return gingr_fail(ctx, GINGR_ERR_ARG, "the mesh flavours of the ICP correspondence need template and target triangles");
+  const int s_surf = std::min(ws.s_surf, std::max(1, ceil_div(tgt.T, TT)));
+  const int s_line = std::min(ws.s_line, std::max(1, ceil_div(tpl.T, TT)));
+  if (method == GINGR_TRIANGULAR_CLOSEST_POINT) {
+    surface_kernel<<<dim3(ceil_div(M, QT), s_surf), QT, 0, st>>>(M, tpl.aos, N, tgt.soa, tgt.T, tgt.tri, ws.part_d2.p,
+                                                                 ws.part_idx.p, ws.part_cp.p);
+    GINGR_LAUNCHED(ctx);
+    surface_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, s_surf, ws.part_d2.p, ws.part_idx.p, ws.part_cp.p,
                                                             ws.d2.p, nullptr, ws.cp.p);
     GINGR_LAUNCHED(ctx);
     mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.d2.p, ws.mean_dist.p);
     GINGR_LAUNCHED(ctx);
-    // nearest target vertex of the surface point (:83); d2 of that search is not needed afterwards
-    nn_vertex_kernel<<<dim3(ceil_div(M, QT), ws.s_nn), QT, 0, st>>>(M, ws.cp.p, N, tgt->verts.p, ws.part_d2.p,
-                                                                    ws.part_idx.p);
+  } else if (method == GINGR_ALONG_NORMAL_CLOSEST_POINT) {
+    // nearest intersection of the line (p, n_p) with the target mesh (:105-110)
+    const int s_hit = s_surf;
+    line_mesh_kernel<false, false, true><<<dim3(ceil_div(M, QT), s_hit), QT, 0, st>>>(
+        M, tpl.aos, tpl.normals, tgt.aos, tgt.T, tgt.tri, ws.part_d2.p, ws.part_cp.p);
     GINGR_LAUNCHED(ctx);
-    nn_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, ws.s_nn, ws.part_d2.p, ws.part_idx.p, ws.d2.p, ws.idx.p);
+    line_hit_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, s_hit, tpl.aos, ws.part_d2.p, ws.part_cp.p, ws.d2.p,
+                                                             ws.cp.p, ws.hit.p);
     GINGR_LAUNCHED(ctx);
-    GINGR_TRY(vertex_normals_enqueue(ctx, M, d_tpl, d_tpl_tri, d_adj_off, d_adj, ws.n_tpl.p));
-    line_mesh_kernel<<<dim3(ceil_div(M, QT), ws.s_line), QT, 0, st>>>(M, d_tpl, ws.cp.p, T_tpl, d_tpl_tri,
-                                                                      ws.part_d2.p);
+    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.d2.p, ws.mean_dist.p, 0);  // distance += (p - closestPoint).norm (:128)
     GINGR_LAUNCHED(ctx);
-    icp_weights_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, d_tpl, ws.cp.p, ws.idx.p, tgt->boundary.p, ws.n_tpl.p,
-                                                         tgt->normals.p, ws.s_line, ws.part_d2.p, ws.w.p);
-    GINGR_LAUNCHED(ctx);
-    GINGR_CUDA_TRY(ctx, cudaGetLastError());
-    return GINGR_OK;
   } else {
-    return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "AlongNormalClosestPoint is not implemented yet");
+    return gingr_fail(ctx, GINGR_ERR_ARG, "unknown ICP correspondence method");
   }
-  mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.d2.p, ws.mean_dist.p);
+  // nearest target vertex of the corresponding point (:83 / :113); d2 of that search is not needed afterwards
+  GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, ws.cp.p, N, tgt.soa, ws.d2.p, ws.idx.p));
+  // isClosestPointIntersecting on the template itself (:62-72)
+  line_mesh_kernel<true, true, false><<<dim3(ceil_div(M, QT), s_line), QT, 0, st>>>(M, tpl.aos, ws.cp.p, tpl.aos, tpl.T,
+                                                                                   tpl.tri, ws.part_d2.p, nullptr);
+  GINGR_LAUNCHED(ctx);
+  icp_weights_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, tpl.aos, ws.cp.p, ws.idx.p, tgt.boundary, tpl.normals,
+                                                       tgt.normals, s_line, ws.part_d2.p,
+                                                       method == GINGR_ALONG_NORMAL_CLOSEST_POINT ? ws.hit.p : nullptr,
+                                                       ws.w.p);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+// closestPointCorrespondenceReversal (:34-45), second half: the observations (templateId_j, target point x_j, w_j)
+// of all target vertices j, folded per template vertex i in ascending j (deterministic, no atomics):
+//   wcnt_i = #{j : tid_j = i, w_j = 1},  cp_i = mean of those x_j   (wcnt_i / sigma2 and the mean reproduce the
+//   summed duplicate observations of the reference's regression exactly up to rounding)
+__global__ void __launch_bounds__(128) reverse_fold_kernel(int M, int N, const int32_t* __restrict__ tid,
+                                                           const uint8_t* __restrict__ w,
+                                                           const double* __restrict__ x /*AoS target points*/,
+                                                           double* __restrict__ cp, double* __restrict__ wcnt) {
+  __shared__ int32_t s_tid[512];
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  int cnt = 0;
+  for (int j0 = 0; j0 < N; j0 += 512) {
+    const int c = min(512, N - j0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < c; t += 128) s_tid[t] = w[j0 + t] ? tid[j0 + t] : -1;
+    __syncthreads();
+    for (int t = 0; t < c; ++t)
+      if (s_tid[t] == i) {
+        sx += x[3 * (j0 + t)]; sy += x[3 * (j0 + t) + 1]; sz += x[3 * (j0 + t) + 2];
+        ++cnt;
+      }
+  }
+  if (i < M) {
+    wcnt[i] = (double)cnt;
+    const double inv = cnt > 0 ? 1.0 / (double)cnt : 0.0;
+    cp[3 * i] = sx * inv; cp[3 * i + 1] = sy * inv; cp[3 * i + 2] = sz * inv;
+  }
+}
+
+int32_t reverse_fold_enqueue(gingr_ctx* ctx, int M, int N, const int32_t* d_tid, const uint8_t* d_w,
+                             const double* d_target_aos, double* d_cp, double* d_wcnt) {
+  reverse_fold_kernel<<<ceil_div(M, 128), 128, 0, ctx->stream>>>(M, N, d_tid, d_w, d_target_aos, d_cp, d_wcnt);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

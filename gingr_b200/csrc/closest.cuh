@@ -6,18 +6,31 @@
 
 namespace gingr {
 
+// A mesh as the correspondence kernels see it: device pointers, any of which may be null when the flavour does
+// not need it.  "template" = the mesh whose vertices are the queries, "target" = the mesh that is searched.
+struct MeshView {
+  int n = 0;                          // vertices
+  const double* aos = nullptr;        // [n][3]
+  const double* soa = nullptr;        // [3][n]
+  int T = 0;                          // triangles
+  const int32_t* tri = nullptr;       // [3T]
+  const double* normals = nullptr;    // [n][3] vertex normals of THIS geometry
+  const uint8_t* boundary = nullptr;  // [n] pointIsOnBoundary
+};
+
 struct ClosestWorkspace {
   int s_nn = 1, s_surf = 1, s_line = 1;  // candidate-range splits of the three scans
-  DevBuf<double> part_d2;     // [smax][M]
-  DevBuf<int32_t> part_idx;   // [smax][M]
-  DevBuf<double> part_cp;     // [s_surf][M][3]
-  DevBuf<double> d2;          // [M]
-  DevBuf<int32_t> idx;        // [M]   nearest target vertex
-  DevBuf<double> cp;          // [M][3] corresponding point
-  DevBuf<uint8_t> w;          // [M]   0/1 weight
-  DevBuf<double> n_tpl;       // [M][3] template vertex normals
+  DevBuf<double> part_d2;     // [smax][nq]
+  DevBuf<int32_t> part_idx;   // [smax][nq]
+  DevBuf<double> part_cp;     // [max(s_surf, s_line)][nq][3]
+  DevBuf<double> d2;          // [nq]
+  DevBuf<int32_t> idx;        // [nq]   nearest target vertex
+  DevBuf<double> cp;          // [nq][3] corresponding point
+  DevBuf<uint8_t> w;          // [nq]   0/1 weight
+  DevBuf<uint8_t> hit;        // [nq]   along-normal: the line met the target
   DevBuf<double> mean_dist;   // [1]
-  int32_t ensure(gingr_ctx* ctx, int M, int N, int T_target, int T_template);
+  // nq queries against a mesh of n_search vertices / T_search triangles; T_query_mesh triangles of the query mesh
+  int32_t ensure(gingr_ctx* ctx, int nq, int n_search, int T_search, int T_query_mesh);
   void release();
 };
 
@@ -29,8 +42,9 @@ int32_t vertex_normals_enqueue(gingr_ctx* ctx, int n, const double* d_verts_aos,
                                const int32_t* d_adj_off, const int32_t* d_adj, double* d_normals);
 int32_t nn_vertex_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, const double* d_q, int N,
                           const double* d_pts_soa, double* d_d2, int32_t* d_idx);
-int32_t icp_closest_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const gingr_target* tgt, int M, const double* d_tpl,
-                            int T_tpl, const int32_t* d_tpl_tri, const int32_t* d_adj_off, const int32_t* d_adj,
-                            int method);
+int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const MeshView& tpl, const MeshView& tgt,
+                                   int method);
+int32_t reverse_fold_enqueue(gingr_ctx* ctx, int M, int N, const int32_t* d_tid, const uint8_t* d_w,
+                             const double* d_target_aos, double* d_cp, double* d_wcnt);
 
 }  // namespace gingr

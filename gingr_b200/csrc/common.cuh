@@ -55,6 +55,7 @@ struct gingr_target {
   DevBuf<double> soa;   // E-step shard, SoA [3][N] (x[], y[], z[])
   // full mesh (ICP): vertices SoA [3][N_total], triangles, per-vertex normals and boundary flags
   DevBuf<double> verts; // [3][N_total]
+  DevBuf<double> aos;   // [N_total][3] the same vertices, AoS (queries of the reversed ICP direction, line tests)
   int T = 0;
   DevBuf<int32_t> tri;      // [3T]
   DevBuf<double> normals;   // [3][N_total]
@@ -73,6 +74,7 @@ struct gingr_model {
   DevBuf<int32_t> tri;        // [3T] reference triangles (ICP)
   DevBuf<int32_t> adj_off;    // [M+1] CSR vertex -> incident triangles (ascending triangle id)
   DevBuf<int32_t> adj;        // [3T]
+  DevBuf<uint8_t> boundary;   // [M] pointIsOnBoundary of the reference topology (reversed ICP direction)
   // constants of the `coefficients` regression (noise 1e-5 on all M points):
   DevBuf<double> S;           // [rp][rp] S = D Phi^T Phi D, D = diag(sqrt(lambda))
   DevBuf<double> W0;          // [rp][rp] (1e-5 I + S)^-1

@@ -150,7 +150,9 @@ struct ObsArgs {
 
 __global__ void __launch_bounds__(256) obs_kernel(ObsArgs a, const double* __restrict__ rows /*[4][M] CPD*/,
                                                   const double* __restrict__ cp /*[M][3] ICP*/,
-                                                  const uint8_t* __restrict__ w01, const double* __restrict__ fit,
+                                                  const uint8_t* __restrict__ w01,
+                                                  const double* __restrict__ wcnt /*reversed ICP, else null*/,
+                                                  const double* __restrict__ fit,
                                                   const double* __restrict__ ref, const double* __restrict__ mean,
                                                   const int32_t* __restrict__ lm_pid, const double* __restrict__ ds,
                                                   int* __restrict__ is, double* __restrict__ wrow,
@@ -175,8 +177,10 @@ __global__ void __launch_bounds__(256) obs_kernel(ObsArgs a, const double* __res
       sT = fx * X + fy * Y + fz * Z;
     } else {
       px = cp[3 * i]; py = cp[3 * i + 1]; pz = cp[3 * i + 2];
-      wt = w01[i] ? 1.0 / sigma2 : 0.0;  // pairs with w != 1 are dropped (ICP.scala:50)
-      if (w01[i] && (!(wt < INFINITY) || !(wt > 0.0))) is[IS_FAIL_POST] = 1;
+      // pairs with w != 1 are dropped (ICP.scala:50); reversed direction: cnt observations of this vertex, cp = their mean
+      const double cnt = wcnt ? wcnt[i] : (w01[i] ? 1.0 : 0.0);
+      wt = cnt > 0.0 ? cnt / sigma2 : 0.0;
+      if (cnt > 0.0 && (!(wt < INFINITY) || !(wt > 0.0))) is[IS_FAIL_POST] = 1;
     }
     if (a.use_lm)
       for (int l = 0; l < a.L; ++l)
@@ -559,6 +563,10 @@ struct gingr_registration {
   EstepWorkspace estep;
   ClosestWorkspace closest;
   GramPlan gram;
+  DevBuf<double> fit_normals;  // [M][3] vertex normals of the current fit (ICP mesh flavours)
+  DevBuf<double> fit_soa;      // [3][M] (reversed ICP: the fit is the mesh that is searched)
+  DevBuf<int32_t> rev_tid;     // [N] reversed ICP: template vertex each target vertex maps back to
+  DevBuf<double> rev_cp, rev_wcnt;  // [M][3], [M] folded observations of the reversed direction
   DevBuf<double> rows_ext;     // [4 M + 8]  E-step rows + xPx (all-reduced together)
   DevBuf<double> Mx;           // [(r + 8)][rp]  posterior matrix + rhs row
   DevBuf<double> wrow, u, inst_a, inst_b, newshape, fit_local, gathered, fit;
@@ -634,7 +642,11 @@ int32_t gingr_model_upload(gingr_ctx* ctx, int32_t M, int32_t r, const double* r
         return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_model_upload: triangle index out of range");
       }
     std::vector<int32_t> off, adj;
+    std::vector<uint8_t> bflags;
     build_vertex_adjacency(M, T, tri, &off, &adj);
+    compute_boundary_flags(M, T, tri, &bflags);
+    GINGR_CUDA_TRY(ctx, m->boundary.alloc((size_t)M));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->boundary.p, bflags.data(), (size_t)M, cudaMemcpyHostToDevice, st));
     GINGR_CUDA_TRY(ctx, m->tri.alloc((size_t)3 * T));
     GINGR_CUDA_TRY(ctx, m->adj_off.alloc(off.size()));
     GINGR_CUDA_TRY(ctx, m->adj.alloc(adj.size()));
@@ -663,6 +675,7 @@ int32_t gingr_model_destroy(gingr_model* m) {
   m->tri.release();
   m->adj_off.release();
   m->adj.release();
+  m->boundary.release();
   m->S.release();
   m->W0.release();
   delete m;
@@ -960,12 +973,10 @@ int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, cons
   if (cfg->algorithm == GINGR_ALGO_CPD && !(cfg->w >= 0.0 && cfg->w < 1.0))
     return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_registration_create: CPD w must be in [0, 1)");
   if (cfg->algorithm == GINGR_ALGO_ICP) {
-    if (cfg->reverse_correspondence_direction)
-      return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "reverseCorrespondenceDirection is not implemented in gingr_update yet");
-    if (cfg->correspondence_method == GINGR_ALONG_NORMAL_CLOSEST_POINT)
-      return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "AlongNormalClosestPoint is not implemented yet");
-    if (cfg->correspondence_method == GINGR_TRIANGULAR_CLOSEST_POINT && (model->T <= 0 || target->T <= 0))
-      return gingr_fail(ctx, GINGR_ERR_ARG, "TriangularClosestPoint needs model and target triangles");
+    if (cfg->correspondence_method < GINGR_TRIANGULAR_CLOSEST_POINT || cfg->correspondence_method > GINGR_POINTCLOUD_CLOSEST_POINT)
+      return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_registration_create: unknown correspondence method");
+    if (cfg->correspondence_method != GINGR_POINTCLOUD_CLOSEST_POINT && (model->T <= 0 || target->T <= 0))
+      return gingr_fail(ctx, GINGR_ERR_ARG, "the mesh flavours of the ICP correspondence need model and target triangles");
   }
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   gingr_registration* g = new gingr_registration();
@@ -978,7 +989,19 @@ int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, cons
   int32_t rc = GINGR_OK;
   auto A = [&](cudaError_t e) { if (e != cudaSuccess && rc == GINGR_OK) { gingr_set_error(ctx, cudaGetErrorString(e)); rc = GINGR_ERR_CUDA; } };
   if (cfg->algorithm == GINGR_ALGO_CPD) { int32_t q = g->estep.ensure(ctx, M, std::max(target->N, 1)); if (q < 0) rc = q; }
-  else { int32_t q = g->closest.ensure(ctx, M, target->N_total, target->T, model->T); if (q < 0) rc = q; }
+  else {
+    const bool rev = cfg->reverse_correspondence_direction != 0;
+    int32_t q = rev ? g->closest.ensure(ctx, target->N_total, M, model->T, target->T)
+                    : g->closest.ensure(ctx, M, target->N_total, target->T, model->T);
+    if (q < 0) rc = q;
+    A(g->fit_normals.alloc((size_t)3 * M));
+    if (rev) {
+      A(g->fit_soa.alloc((size_t)3 * M));
+      A(g->rev_tid.alloc((size_t)target->N_total));
+      A(g->rev_cp.alloc((size_t)3 * M));
+      A(g->rev_wcnt.alloc((size_t)M));
+    }
+  }
   if (rc == GINGR_OK) { int32_t q = g->gram.build(ctx, 3 * Ml, r, rp); if (q < 0) rc = q; }
   A(g->rows_ext.alloc((size_t)4 * M + 8));
   A(g->Mx.alloc((size_t)(r + 8) * rp));
@@ -1018,6 +1041,7 @@ int32_t gingr_registration_destroy(gingr_registration* g) {
   g->lm_pid.release(); g->lml_pid.release(); g->lml_pts.release(); g->lml_cinv.release(); g->lml_A.release();
   g->lml_rows.release();
   g->estep.release(); g->closest.release(); g->gram.release();
+  g->fit_normals.release(); g->fit_soa.release(); g->rev_tid.release(); g->rev_cp.release(); g->rev_wcnt.release();
   g->rows_ext.release(); g->Mx.release(); g->wrow.release(); g->u.release(); g->inst_a.release(); g->inst_b.release();
   g->newshape.release(); g->fit_local.release(); g->gathered.release(); g->fit.release(); g->vec.release();
   g->gt_part.release(); g->sums_part.release(); g->pro_part.release(); g->pro_sums.release();
@@ -1136,6 +1160,8 @@ static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, u
   pose_kernel<<<1, 1, 0, st>>>(g->ds.p, g->is.p);
   GINGR_LAUNCHED(ctx);
   // ---- correspondence -------------------------------------------------------------------------------
+  const double* icp_cp = nullptr;
+  const double* icp_wcnt = nullptr;
   if (cfg.algorithm == GINGR_ALGO_CPD) {
     // non-finite fit / sigma2 / target: the reference's P is all NaN and the posterior fails
     GINGR_TRY(validate_finite_enqueue(ctx, 3 * M, g->fit.p, g->is.p + IS_FAIL_POST));
@@ -1159,8 +1185,31 @@ static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, u
     GINGR_TRY(comm_allreduce_sum(ctx, g->rows_ext.p, (size_t)4 * M + 8));
   } else {
     g->rec(10);
-    GINGR_TRY(icp_closest_enqueue(ctx, g->closest, tg, M, g->fit.p, m->T, m->tri.p, m->adj_off.p, m->adj.p,
-                                  cfg.correspondence_method));
+    const bool mesh_flavour = cfg.correspondence_method != GINGR_POINTCLOUD_CLOSEST_POINT;
+    MeshView fv, tv;
+    fv.n = M; fv.aos = g->fit.p; fv.T = m->T; fv.tri = m->tri.p; fv.boundary = m->boundary.p;
+    if (mesh_flavour) {
+      GINGR_TRY(vertex_normals_enqueue(ctx, M, g->fit.p, m->tri.p, m->adj_off.p, m->adj.p, g->fit_normals.p));
+      fv.normals = g->fit_normals.p;
+    }
+    tv.n = tg->N_total; tv.aos = tg->aos.p; tv.soa = tg->verts.p; tv.T = tg->T; tv.tri = tg->tri.p;
+    tv.normals = tg->normals.p; tv.boundary = tg->boundary.p;
+    if (!cfg.reverse_correspondence_direction) {
+      GINGR_TRY(icp_correspondence_enqueue(ctx, g->closest, fv, tv, cfg.correspondence_method));
+      icp_cp = g->closest.cp.p;
+    } else {
+      // closestPointCorrespondenceReversal (ClosestPointRegistrator.scala:34-45): search from the target to the fit,
+      // map every corresponding point back to its nearest fit vertex, observe the TARGET point there
+      GINGR_TRY(aos_to_soa_enqueue(ctx, M, g->fit.p, g->fit_soa.p));
+      fv.soa = g->fit_soa.p;
+      GINGR_TRY(icp_correspondence_enqueue(ctx, g->closest, tv, fv, cfg.correspondence_method));
+      GINGR_TRY(nn_vertex_enqueue(ctx, g->closest, tg->N_total, g->closest.cp.p, M, g->fit_soa.p, g->closest.d2.p,
+                                  g->rev_tid.p));
+      GINGR_TRY(reverse_fold_enqueue(ctx, M, tg->N_total, g->rev_tid.p, g->closest.w.p, tg->aos.p, g->rev_cp.p,
+                                     g->rev_wcnt.p));
+      icp_cp = g->rev_cp.p;
+      icp_wcnt = g->rev_wcnt.p;
+    }
     g->rec(11);
   }
   // ---- observations, sigma2 hook ----------------------------------------------------------------------
@@ -1168,7 +1217,7 @@ static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, u
   oa.algo = cfg.algorithm; oa.M = M; oa.m0 = m0; oa.Ml = Ml; oa.use_lm = cfg.use_landmark_correspondence && g->L > 0;
   oa.L = g->L; oa.lambda = cfg.lambda;
   const int oblocks = ceil_div(M, 256);
-  obs_kernel<<<oblocks, 256, 0, st>>>(oa, g->rows_ext.p, g->closest.cp.p, g->closest.w.p, g->fit.p, m->ref.p, m->mean.p,
+  obs_kernel<<<oblocks, 256, 0, st>>>(oa, g->rows_ext.p, icp_cp, g->closest.w.p, icp_wcnt, g->fit.p, m->ref.p, m->mean.p,
                                       g->lm_pid.p, g->ds.p, g->is.p, g->wrow.p, g->u.p, g->sums_part.p);
   GINGR_LAUNCHED(ctx);
   const double sigma_step = cfg.algorithm == GINGR_ALGO_ICP ? (cfg.initial_sigma - cfg.end_sigma) / (double)cfg.max_iterations : 0.0;

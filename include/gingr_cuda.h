@@ -158,13 +158,20 @@ GINGR_API int32_t gingr_cpd_initial_sigma2(gingr_ctx* ctx, const gingr_target* t
 
 /* ---- K2: ICP closest-point correspondence ---------------------------------------------------- */
 /* Replaces closestPointCorrespondence of registration/utils/ClosestPointRegistrator.scala
- * (:74-96 triangular, :133-160 point cloud) and, with reverse != 0, closestPointCorrespondenceReversal
- * (:34-45).  `tpl` / `tpl_tri` are the template (current fit) vertices and triangles.
- * Outputs per template vertex (or per target vertex when reversed): idx = nearest target vertex id
- * (exact argmin, ties -> lowest index), cp = corresponding point, w = 0/1 robustness weight. */
+ * (:74-96 triangular, :98-131 along normal, :133-160 point cloud).  `tpl` / `tpl_tri` are the template
+ * (current fit) vertices and triangles.  Outputs per template vertex: idx = nearest target vertex id
+ * (exact argmin, ties -> lowest index), cp = corresponding point, w = 0/1 robustness weight,
+ * mean_distance = the second component of the reference's result. */
 GINGR_API int32_t gingr_icp_closest(gingr_ctx* ctx, const gingr_target* target, int32_t M, const double* tpl /*[3M]*/,
                                     const int32_t* tpl_tri /*[3T]*/, int32_t T, int32_t method, int32_t* idx /*[M]*/,
                                     double* cp /*[3M]*/, uint8_t* w /*[M]*/, double* mean_distance /*[1]*/);
+/* closestPointCorrespondenceReversal (ClosestPointRegistrator.scala:34-45): the search runs from every TARGET
+ * vertex j to the template; outputs per target vertex: tpl_id = template.findClosestPoint(corresponding point).id,
+ * w = the weight of that search.  The observation the reference forms is (tpl_id[j], target point j, w[j]). */
+GINGR_API int32_t gingr_icp_closest_reversal(gingr_ctx* ctx, const gingr_target* target, int32_t M,
+                                             const double* tpl /*[3M]*/, const int32_t* tpl_tri /*[3T]*/, int32_t T,
+                                             int32_t method, int32_t* tpl_id /*[N]*/, uint8_t* w /*[N]*/,
+                                             double* mean_distance /*[1]*/);
 
 /* ---- K3: low-rank GPMM posterior ------------------------------------------------------------- */
 /* Replaces model.transform(rigid).posterior(obs).mean (GingrAlgorithm.scala:297-301, :211;

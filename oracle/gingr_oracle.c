@@ -422,14 +422,31 @@ ORACLE_API void oracle_boundary_vertices(int N, int T, const int32_t* tri, uint8
  * Line/triangle test: Moeller-Trumbore without the s >= 0 restriction.  Returns, per query,
  * the minimum distance to an intersection point != p (INFINITY if none).
  * ------------------------------------------------------------------------------------------ */
+static void line_mesh_nearest(int M, const double* p, const double* dir, const double* verts, int T, const int32_t* tri,
+                              int skip_incident, double* min_dist, double* hit_pt);
+
 ORACLE_API void oracle_line_mesh_min_dist(int M, const double* p, const double* dir, int N, const double* verts, int T,
                                           const int32_t* tri, int skip_incident, double* min_dist) {
   (void)N;
+  line_mesh_nearest(M, p, dir, verts, T, tri, skip_incident, min_dist, NULL);
+}
+
+/* ClosestPointAlongNormalTriangleMesh3D (ClosestPointRegistrator.scala:105-110): nearest intersection != p of the
+ * line (p, n) with the TARGET mesh: intersectingPoints.minBy(ip => (p - ip).norm); minBy keeps the FIRST minimum,
+ * i.e. the lowest triangle index in this scan order.  hit_pt[i] = p_i and min_dist = INFINITY when there is none. */
+ORACLE_API void oracle_line_mesh_nearest(int M, const double* p, const double* dir, int N, const double* verts, int T,
+                                         const int32_t* tri, double* min_dist, double* hit_pt) {
+  (void)N;
+  line_mesh_nearest(M, p, dir, verts, T, tri, 0, min_dist, hit_pt);
+}
+
+static void line_mesh_nearest(int M, const double* p, const double* dir, const double* verts, int T, const int32_t* tri,
+                              int skip_incident, double* min_dist, double* hit_pt) {
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < M; ++i) {
     const double ox = p[3 * i], oy = p[3 * i + 1], oz = p[3 * i + 2];
     const double dx = dir[3 * i], dy = dir[3 * i + 1], dz = dir[3 * i + 2];
-    double best = INFINITY;
+    double best = INFINITY, bx = ox, by = oy, bz = oz;
     for (int t = 0; t < T; ++t) {
       /* query i is vertex i of this mesh: its incident triangles meet the line only at p itself, which
        * the reference removes with .filter(f => f != p) (:67) -- skip them outright */
@@ -453,8 +470,9 @@ ORACLE_API void oracle_line_mesh_min_dist(int M, const double* p, const double* 
       const double ix = ox + s * dx, iy = oy + s * dy, iz = oz + s * dz;
       if (ix == ox && iy == oy && iz == oz) continue; /* .filter(f => f != p)  :67 */
       const double d = sqrt(norm2_3(ox - ix, oy - iy, oz - iz));
-      if (d < best) best = d;
+      if (d < best) { best = d; bx = ix; by = iy; bz = iz; }
     }
     min_dist[i] = best;
+    if (hit_pt) { hit_pt[3 * i] = bx; hit_pt[3 * i + 1] = by; hit_pt[3 * i + 2] = bz; }
   }
 }

@@ -210,6 +210,16 @@ def line_mesh_min_dist(p, direction, verts, tri, skip_incident=True):
     return out
 
 
+def line_mesh_nearest(p, direction, verts, tri):
+    """nearest intersection != p of the infinite line p + s*dir with a mesh (the along-normal flavour):
+    (distance, hit point); distance = inf and hit = p when the line misses the mesh."""
+    p, d, v, t = _c(p), _c(direction), _c(verts), _c(tri, np.int32)
+    dist = np.empty(p.shape[0])
+    hit = np.empty_like(p)
+    lib().oracle_line_mesh_nearest(p.shape[0], _d(p), _d(d), v.shape[0], _d(v), t.shape[0], _i(t), _d(dist), _d(hit))
+    return dist, hit
+
+
 METHOD_TRIANGULAR, METHOD_ALONG_NORMAL, METHOD_POINTCLOUD = 0, 1, 2
 
 
@@ -237,7 +247,22 @@ def closest_point_correspondence(method, template_v, template_tri, target_v, tar
         vnorm = np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1] + v[:, 2] * v[:, 2])
         w[md < vnorm] = 0.0  # :71, :89
         return cp, w, float(np.sum(np.sqrt(d2)) / M), idx
-    raise NotImplementedError("AlongNormalClosestPoint is not part of the round-1 oracle")
+    # ClosestPointAlongNormalTriangleMesh3D  :98-131
+    dist, hit = line_mesh_nearest(template_v, n_tpl, target_v, target_tri)        # :105-110
+    has = np.isfinite(dist)
+    idx, _ = nearest_vertex(hit, target_v)                                         # :113
+    w = np.ones(M)
+    w[tgt_boundary[idx]] = 0.0                                                     # :115
+    nt = n_tgt[idx]
+    opp = (n_tpl[:, 0] * nt[:, 0] + n_tpl[:, 1] * nt[:, 1] + n_tpl[:, 2] * nt[:, 2]) < 0   # :116-122
+    w[opp] = 0.0
+    v = template_v - hit
+    md = line_mesh_min_dist(template_v, v, template_v, template_tri)               # :123
+    vnorm = np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1] + v[:, 2] * v[:, 2])
+    w[md < vnorm] = 0.0
+    w[~has] = 0.0                                                                  # :127 (p, 0.0)
+    cp = np.where(has[:, None], hit, template_v)
+    return cp, w, float(np.sum(np.where(has, dist, 0.0)) / M), idx                 # :128
 
 
 def icp_correspondence(method, reverse, fit_v, fit_tri, target_v, target_tri):

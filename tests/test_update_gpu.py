@@ -175,18 +175,25 @@ def test_cpd_model_flexibility_error_status(ctx, oracle):
     reg.close()
 
 
-@pytest.mark.parametrize("method", ["triangular", "pointcloud"])
-def test_icp_iterations_match_oracle(ctx, oracle, method):
+@pytest.mark.parametrize("reverse", [False, True])
+@pytest.mark.parametrize("method", ["triangular", "along_normal", "pointcloud"])
+def test_icp_iterations_match_oracle(ctx, oracle, method, reverse):
+    """All three ICPCorrespondenceMethods (ICP.scala:29-33) in both directions (reverseCorrespondenceDirection,
+    ICP.scala:46-49): the reversed direction observes target points at template vertices, several per vertex."""
     from gingr_b200 import api
     m, target, tt = _problem(oracle, 200, 260, 40, seed=7)
     diag = np.linalg.norm(m.ref.max(0) - m.ref.min(0))
-    om = oracle.METHOD_TRIANGULAR if method == "triangular" else oracle.METHOD_POINTCLOUD
-    gm = api.TRIANGULAR_CLOSEST_POINT if method == "triangular" else api.POINTCLOUD_CLOSEST_POINT
+    om = {"triangular": oracle.METHOD_TRIANGULAR, "along_normal": oracle.METHOD_ALONG_NORMAL,
+          "pointcloud": oracle.METHOD_POINTCLOUD}[method]
+    gm = {"triangular": api.TRIANGULAR_CLOSEST_POINT, "along_normal": api.ALONG_NORMAL_CLOSEST_POINT,
+          "pointcloud": api.POINTCLOUD_CLOSEST_POINT}[method]
     dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
     dt = api.Target(ctx, target, tt)
     reg = api.IcpRegistration(ctx, dm, dt, api.IcpConfiguration(maxIterations=100, initialSigma=2.0, endSigma=0.01,
-                                                                correspondenceMethod=gm))
-    oalgo = oracle.IcpAlgorithm(oracle.IcpConfig(max_iterations=100, initial_sigma=2.0, end_sigma=0.01, method=om))
+                                                                correspondenceMethod=gm,
+                                                                reverseCorrespondenceDirection=reverse))
+    oalgo = oracle.IcpAlgorithm(oracle.IcpConfig(max_iterations=100, initial_sigma=2.0, end_sigma=0.01, method=om,
+                                                 reverse=reverse))
     ost = oalgo.initialize(oracle.initial_state(m, target, tt, global_transformation=oracle.NO_TRANSFORMS))
     gst = reg.initializeState(globalTransformation=api.NO_TRANSFORMS)
     assert gst.sigma2 == 2.0
