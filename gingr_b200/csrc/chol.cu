@@ -307,10 +307,14 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(int n, const double
 // host side
 // ---------------------------------------------------------------------------------------------
 int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, int* d_info) {
-  GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(chol_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)SYRK_SMEM));
-  GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)PANEL_SMEM));
+  static thread_local int attr_device = -1;  // once per device (and host thread): not a stream operation
+  if (attr_device != ctx->device) {
+    GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(chol_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)SYRK_SMEM));
+    GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)PANEL_SMEM));
+    attr_device = ctx->device;
+  }
   cudaStream_t st = ctx->stream;
   for (int j0 = 0; j0 < n; j0 += NB) {
     const int jb = std::min(NB, n - j0);

@@ -23,6 +23,7 @@
 //   finalize               new state or ModelFlexibilityError, sigma2 hook                        (:239-251)
 //   gemv_rows + pose       fit = s (R instance(alpha_new) + t)            (ModelFittingParameters.scala:130-143)
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -576,6 +577,12 @@ struct gingr_registration {
   DevBuf<int> is, flags;
   DevBuf<double> alpha;
   int retry_counter = RETRY_COUNTER_INIT;  // mirror of the device counter, refreshed by download_state
+  // One iteration captured as a CUDA graph: the ~100-launch sequence of a small registration (C1-C3 sizes) is
+  // launch-latency bound, the graph replays it with one driver call.  Key = (probabilistic, seed).
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_prob = -1;
+  uint64_t graph_seed = 0;
+  int64_t graph_launches = 0;
   bool state_valid = false;
   gingr_state last_out;
   std::vector<double> last_alpha;
@@ -589,6 +596,7 @@ struct gingr_registration {
 };
 
 static int32_t model_build_constants(gingr_ctx* ctx, gingr_model* m);
+static void drop_graph(gingr_registration* g);
 
 extern "C" {
 
@@ -1038,6 +1046,7 @@ int32_t gingr_registration_destroy(gingr_registration* g) {
   if (!g) return GINGR_OK;
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
+  drop_graph(g);
   g->lm_pid.release(); g->lml_pid.release(); g->lml_pts.release(); g->lml_cinv.release(); g->lml_A.release();
   g->lml_rows.release();
   g->estep.release(); g->closest.release(); g->gram.release();
@@ -1094,6 +1103,7 @@ int32_t gingr_registration_set_landmarks(gingr_registration* g, int32_t L, const
   }
   GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
   g->state_valid = false;
+  drop_graph(g);  // the landmark buffers (and their count) are baked into the captured launches
   return GINGR_OK;
 }
 
@@ -1290,6 +1300,46 @@ static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, u
   return GINGR_OK;
 }
 
+static bool graphs_enabled(const gingr_ctx* ctx) {
+  static const int env = [] { const char* e = getenv("GINGR_CUDA_GRAPH"); return e ? atoi(e) : 1; }();
+  return env != 0 && ctx->nranks == 1;  // NCCL collectives stay outside graphs
+}
+
+static void drop_graph(gingr_registration* g) {
+  if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
+  g->graph_exec = nullptr;
+  g->graph_prob = -1;
+}
+
+// One iteration, through the captured graph when possible (not while profiling: the events live outside graphs).
+static int32_t run_iteration(gingr_registration* g, int probabilistic, uint64_t seed) {
+  gingr_ctx* ctx = g->ctx;
+  if (g->profiling || !graphs_enabled(ctx)) return enqueue_iteration(g, probabilistic, seed);
+  if (!g->graph_exec || g->graph_prob != probabilistic || (probabilistic && g->graph_seed != seed)) {
+    drop_graph(g);
+    const int64_t l0 = ctx->launches;
+    GINGR_CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int32_t rc = enqueue_iteration(g, probabilistic, seed);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    g->graph_launches = ctx->launches - l0;
+    ctx->launches = l0;  // nothing ran yet
+    if (rc < 0) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    GINGR_CUDA_TRY(ctx, e);
+    const cudaError_t e2 = cudaGraphInstantiate(&g->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    GINGR_CUDA_TRY(ctx, e2);
+    g->graph_prob = probabilistic;
+    g->graph_seed = seed;
+  }
+  GINGR_CUDA_TRY(ctx, cudaGraphLaunch(g->graph_exec, ctx->stream));
+  ctx->launches += g->graph_launches;
+  return GINGR_OK;
+}
+
 static int32_t download_state(gingr_registration* g, gingr_state* out, double* alpha_out, double* fit_out) {
   gingr_ctx* ctx = g->ctx;
   const gingr_model* m = g->model;
@@ -1375,7 +1425,7 @@ int32_t gingr_update(gingr_registration* g, const gingr_state* state_in, const d
     GINGR_LAUNCHED(ctx);
   }
   g->state_valid = false;
-  GINGR_TRY(enqueue_iteration(g, probabilistic != 0, seed));
+  GINGR_TRY(run_iteration(g, probabilistic != 0, seed));
   GINGR_TRY(download_state(g, state_out, alpha_out, fit_out));
   g->last_out = *state_out;
   g->last_alpha.assign(alpha_out, alpha_out + m->r);
@@ -1389,7 +1439,7 @@ int32_t gingr_update_chain(gingr_registration* g, int32_t iters) {
   if (!g->state_valid) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_chain: no device-resident state (call gingr_initialize_state / gingr_update first)");
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   for (int k = 0; k < iters; ++k) {
-    GINGR_TRY(enqueue_iteration(g));
+    GINGR_TRY(run_iteration(g, 0, 0));
     bump_iteration_kernel<<<1, 1, 0, ctx->stream>>>(g->is.p);  // GingrGeneratorWrapper.propose: updateIteration()
     GINGR_LAUNCHED(ctx);
   }
@@ -1402,7 +1452,7 @@ int32_t gingr_update_chain_sampled(gingr_registration* g, int32_t iters, uint64_
   if (!g->state_valid) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_chain_sampled: no device-resident state");
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   for (int k = 0; k < iters; ++k) {
-    GINGR_TRY(enqueue_iteration(g, 1, seed));  // the Philox counter carries the device iteration number
+    GINGR_TRY(run_iteration(g, 1, seed));  // the Philox counter carries the device iteration number
     bump_iteration_kernel<<<1, 1, 0, ctx->stream>>>(g->is.p);
     GINGR_LAUNCHED(ctx);
   }

@@ -7,6 +7,8 @@
 //   gemvT       out[a] = s_a sum_k Phi[k][a] u[k]   right-hand side Q^T L^-1 (y - m) of the regression
 //               (SURVEY.md A3).  Thread per column, rows split over CTAs, fixed-order reduction.
 // Both read Phi (8 * 3M * r bytes) exactly once; Phi is row-major [3M][rp] so both are fully coalesced.
+#include <algorithm>
+
 #include "common.cuh"
 #include "posterior.cuh"
 
@@ -49,13 +51,20 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(int rows, int r, int rp,
   }
 }
 
-constexpr int GT_ROWS = 512;  // rows per CTA of gemvT
+constexpr int GT_ROWS = 512;  // max rows per CTA of gemvT
 
-__global__ void __launch_bounds__(256) gemvT_kernel(int rows, int rp, const double* __restrict__ phi,
+// rows per CTA: ~2 CTAs of rows per SM so that small problems (C1-C3: a few hundred rows) still spread over the
+// machine instead of one CTA walking every row with dependent loads; large problems keep long streaming CTAs
+static int gemvT_rows_per_cta(const gingr_ctx* ctx, int rows) {
+  const int want = ceil_div(std::max(rows, 1), 2 * ctx->num_sms);
+  return std::max(16, std::min(GT_ROWS, (want + 3) / 4 * 4));
+}
+
+__global__ void __launch_bounds__(256) gemvT_kernel(int rows, int rp, int rows_per_cta, const double* __restrict__ phi,
                                                     const double* __restrict__ u, double* __restrict__ part) {
   __shared__ double su[GT_ROWS];
-  const int k0 = blockIdx.y * GT_ROWS;
-  const int cnt = min(GT_ROWS, rows - k0);
+  const int k0 = blockIdx.y * rows_per_cta;
+  const int cnt = min(rows_per_cta, rows - k0);
   for (int t = threadIdx.x; t < cnt; t += 256) su[t] = u[k0 + t];
   __syncthreads();
   const int a = blockIdx.x * 256 + threadIdx.x;
@@ -184,15 +193,15 @@ int32_t gemv_rows_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double*
 }
 
 int gemvT_splits(const gingr_ctx* ctx, int rows) {
-  (void)ctx;
-  return std::max(1, ceil_div(rows, GT_ROWS));
+  return std::max(1, ceil_div(rows, gemvT_rows_per_cta(ctx, rows)));
 }
 
 int32_t gemvT_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_phi, const double* d_u,
                       const double* d_scale, double* d_part, double* d_out) {
   const int splits = gemvT_splits(ctx, rows);
   if (rows > 0) {
-    gemvT_kernel<<<dim3(ceil_div(rp, 256), splits), 256, 0, ctx->stream>>>(rows, rp, d_phi, d_u, d_part);
+    gemvT_kernel<<<dim3(ceil_div(rp, 256), splits), 256, 0, ctx->stream>>>(rows, rp, gemvT_rows_per_cta(ctx, rows), d_phi,
+                                                                           d_u, d_part);
     GINGR_LAUNCHED(ctx);
   } else {
     GINGR_CUDA_TRY(ctx, cudaMemsetAsync(d_part, 0, sizeof(double) * rp, ctx->stream));
