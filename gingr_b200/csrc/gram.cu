@@ -20,6 +20,8 @@
 // fragments.  Partial tiles go to a workspace and are summed in fixed
 // order by gram_finish_kernel (deterministic; no atomics), which also applies D, adds I and the landmark
 // blocks (full 3x3 covariances, GeneralRegistrationState.scala:43-62).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -166,6 +168,156 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_streamk_kernel(int rows,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised variant (default): 8 consumer warps + 1 producer warp, stages handed over through mbarriers
+// instead of a CTA-wide barrier per chunk.  ncu on the barrier version: 6 % of the warp samples sit in `barrier`
+// and 7 % in `short scoreboard` right after it (the whole CTA drains the DMMA pipe every 32 rows); here a consumer
+// warp only waits for "its" stage to be full and the producer refills a stage as soon as the 8 warps released it,
+// also across segment boundaries (the partial-tile store of one segment overlaps the loads of the next).
+//   full[s]   count 32 + transaction bytes: every producer lane arrives (lane 0 with expect_tx) and issues one
+//             cp.async.bulk (global -> shared, 1 KB, completes on the mbarrier) per operand row
+//   empty[s]  count 8 : one arrive per consumer warp after its last fragment load of the stage
+// ---------------------------------------------------------------------------------------------
+constexpr int GRAM_WS_THREADS = 256 + 32;
+constexpr size_t GRAM_WS_SMEM = GRAM_SMEM + 2 * STAGES * sizeof(unsigned long long);
+
+__device__ __forceinline__ void mbar_init(unsigned addr, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(addr), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_cp_async_arrive(unsigned addr) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(GRAM_WS_THREADS, 1) gram_ws_kernel(int rows, int rp, const double* __restrict__ phi,
+                                                                     const double* __restrict__ wrow,
+                                                                     const GramSegment* __restrict__ segs,
+                                                                     const int* __restrict__ seg_begin,
+                                                                     double* __restrict__ partial) {
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;                                   // [STAGES][BK][PITCH]
+  double* sB = sA + (size_t)STAGES * BK * PITCH;       // [STAGES][BK][PITCH]
+  double* sW = sB + (size_t)STAGES * BK * PITCH;       // [STAGES][BK]
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(sW + STAGES * BK);  // full[STAGES], empty[STAGES]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar0 + 8 * s, 32);
+      mbar_init(bar0 + 8 * (STAGES + s), 8);
+    }
+  }
+  __syncthreads();
+  const int s_first = seg_begin[blockIdx.x], s_last = seg_begin[blockIdx.x + 1];
+
+  if (warp == 8) {
+    // ---------------- producer: one bulk copy (TMA engine, SASS UBLKCP) per operand row and lane ----------------
+    unsigned it = 0;
+    for (int si = s_first; si < s_last; ++si) {
+      const GramSegment sg = segs[si];
+      const int a0 = sg.ta * BT, b0 = sg.tb * BT;
+      const bool diag = sg.ta == sg.tb;
+      const unsigned bytes_a = (unsigned)(min(BT, rp - a0) * 8), bytes_b = diag ? 0u : (unsigned)(min(BT, rp - b0) * 8);
+      for (int ch = sg.c0; ch < sg.c1; ++ch, ++it) {
+        const int stage = it % STAGES;
+        const int krow = ch * BK + lane;                 // this lane's row of the chunk
+        const bool rok = krow < rows;
+        const double wv = (rok && wrow) ? wrow[krow] : 0.0;   // issued before the wait: latency off the critical path
+        mbar_wait(bar0 + 8 * (STAGES + stage), ((it / STAGES) & 1) ^ 1);  // stage released by all consumer warps
+        double* dA = sA + (size_t)stage * BK * PITCH + lane * PITCH;
+        double* dB = sB + (size_t)stage * BK * PITCH + lane * PITCH;
+        sW[stage * BK + lane] = wv;
+        if (!rok) {  // rows past the end of Phi contribute zero (the tail chunk only)
+          for (int c = 0; c < BT; ++c) { dA[c] = 0.0; if (!diag) dB[c] = 0.0; }
+        }
+        const int valid = min(BK, rows - ch * BK);
+        const unsigned full_bar = bar0 + 8 * stage;
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(full_bar),
+                       "r"((unsigned)valid * (bytes_a + bytes_b))
+                       : "memory");
+        } else {
+          mbar_arrive(full_bar);  // releases this lane's plain stores (weights, zero rows)
+        }
+        if (rok) {
+          const double* src = phi + (size_t)krow * rp;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                           (unsigned)__cvta_generic_to_shared(dA)),
+                       "l"(src + a0), "r"(bytes_a), "r"(full_bar)
+                       : "memory");
+          if (!diag)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(dB)),
+                         "l"(src + b0), "r"(bytes_b), "r"(full_bar)
+                         : "memory");
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const int wm = warp >> 2, wn = warp & 3;             // 2 x 4 warps, warp tile 64 x 32
+  const int g = lane >> 2, t = lane & 3;
+  unsigned it = 0;
+  for (int si = s_first; si < s_last; ++si) {
+    const GramSegment sg = segs[si];
+    const bool diag = sg.ta == sg.tb;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int ch = sg.c0; ch < sg.c1; ++ch, ++it) {
+      const int stage = it % STAGES;
+      mbar_wait(bar0 + 8 * stage, (it / STAGES) & 1);
+      const double* tA = sA + (size_t)stage * BK * PITCH + wm * 64 + g;
+      const double* tB = (diag ? sA : sB) + (size_t)stage * BK * PITCH + wn * 32 + g;
+      const double* tW = sW + stage * BK;
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 4; ++k4) {
+        const int kk = k4 * 4 + t;
+        const double wk = wrow ? tW[kk] : 1.0;
+        double af[8], bf[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) af[i] = tA[kk * PITCH + i * 8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = tB[kk * PITCH + j * 8] * wk;
+        if (k4 == BK / 4 - 1) {  // last fragment loads of the stage are in registers: hand the stage back
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar0 + 8 * (STAGES + stage));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    }
+    double* out = partial + (size_t)sg.slot * BT * BT;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int row = wm * 64 + i * 8 + g, col = wn * 32 + j * 8 + 2 * t;
+        *reinterpret_cast<double2*>(out + (size_t)row * BT + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+      }
+  }
+}
+
 // Sum the partial tiles in slot order and emit  out = add_identity * I + D (G + LM) D  (both triangles).
 // tile_first[t] .. tile_first[t+1] are the slots of lower-triangular tile t (t = ta (ta+1)/2 + tb).
 // Landmark term: LM[a][b] = sum_l sum_{d,e} phi_l[d][a] A_l[d][e] phi_l[e][b]  with lm_rows [L][3][rp], lm_A [L][9].
@@ -288,6 +440,8 @@ int32_t GramPlan::build(gingr_ctx* ctx, int rows_, int r_, int rp_) {
   GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
   GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(gram_streamk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)GRAM_SMEM));
+  GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(gram_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)GRAM_WS_SMEM));
   return GINGR_OK;
 }
 
@@ -303,9 +457,15 @@ int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_ph
                               cudaEvent_t ev0, cudaEvent_t ev1) {
   if (ev0) cudaEventRecord(ev0, ctx->stream);
   if (plan.rows > 0 && plan.nsegs > 0) {
-    gram_streamk_kernel<<<plan.ncta, GRAM_THREADS, GRAM_SMEM, ctx->stream>>>(
-        plan.rows, plan.rp, d_phi, d_wrow, reinterpret_cast<const GramSegment*>(plan.d_segs.p), plan.d_seg_begin.p,
-        plan.d_partial.p);
+    static const int use_ws = [] { const char* e = getenv("GINGR_GRAM_WS"); return e ? atoi(e) : 1; }();
+    if (use_ws && GRAM_WARPS_M == 2)
+      gram_ws_kernel<<<plan.ncta, GRAM_WS_THREADS, GRAM_WS_SMEM, ctx->stream>>>(
+          plan.rows, plan.rp, d_phi, d_wrow, reinterpret_cast<const GramSegment*>(plan.d_segs.p), plan.d_seg_begin.p,
+          plan.d_partial.p);
+    else
+      gram_streamk_kernel<<<plan.ncta, GRAM_THREADS, GRAM_SMEM, ctx->stream>>>(
+          plan.rows, plan.rp, d_phi, d_wrow, reinterpret_cast<const GramSegment*>(plan.d_segs.p), plan.d_seg_begin.p,
+          plan.d_partial.p);
     GINGR_LAUNCHED(ctx);
     GINGR_CUDA_TRY(ctx, cudaGetLastError());
   } else {
