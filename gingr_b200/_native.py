@@ -95,6 +95,7 @@ SIGNATURES = {
     "gingr_update": (c_int32, [c_void_p, POINTER(GingrState), dp, c_int32, c_uint64, POINTER(GingrState), dp, dp]),
     "gingr_update_chain": (c_int32, [c_void_p, c_int32]),
     "gingr_update_chain_sampled": (c_int32, [c_void_p, c_int32, c_uint64]),
+    "gingr_update_batch": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_uint64]),
     "gingr_state_download": (c_int32, [c_void_p, POINTER(GingrState), dp, dp]),
     "gingr_registration_set_profiling": (c_int32, [c_void_p, c_int32]),
     "gingr_registration_get_profile": (c_int32, [c_void_p, dp, ip]),

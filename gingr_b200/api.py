@@ -474,6 +474,14 @@ class GingrAlgorithm:
         return ms, int(it.value)
 
 
+def update_batch(chains: Sequence[GingrAlgorithm], iters: int, probabilistic: bool = False, seed: int = 0):
+    """`iters` update+propose steps of every chain (independent registrations on one ctx; gingr_update_batch).
+    Each chain must hold a device-resident state (initializeState / update); read results with downloadState()."""
+    ctx = chains[0].ctx
+    arr = (ctypes.c_void_p * len(chains))(*[c.handle for c in chains])
+    ctx.check(ctx._lib.gingr_update_batch(arr, len(chains), int(iters), int(probabilistic), int(seed)))
+
+
 class CpdRegistration(GingrAlgorithm):
     """registration/config/CPD.scala:117-160"""
     name = "CPD"

@@ -1459,6 +1459,73 @@ int32_t gingr_update_chain_sampled(gingr_registration* g, int32_t iters, uint64_
   return GINGR_OK;
 }
 
+// Independent registrations / MCMC chains (SURVEY.md 8e "replicas only"; BASELINE config 5): every chain is its own
+// gingr_registration (own state and workspaces; model and target handles are shared), its iteration is one captured
+// CUDA graph, and the graphs of different chains are replayed round-robin on a small pool of streams so that the
+// launch-latency-bound kernels of ~16 chains are in flight at once.  No collective, no cross-chain data.
+int32_t gingr_update_batch(gingr_registration** regs, int32_t n, int32_t iters, int32_t probabilistic, uint64_t seed) {
+  if (!regs || n <= 0 || iters < 0) return gingr_fail(nullptr, GINGR_ERR_ARG, "gingr_update_batch: bad argument");
+  gingr_ctx* ctx = regs[0]->ctx;
+  for (int k = 0; k < n; ++k) {
+    if (!regs[k] || regs[k]->ctx != ctx) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_batch: chains must share one ctx");
+    if (!regs[k]->state_valid) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_batch: chain without device-resident state");
+    if (regs[k]->profiling) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_batch: profiling is per registration");
+  }
+  if (ctx->nranks != 1) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "gingr_update_batch: chains are replicas, one ctx per GPU without a communicator");
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  constexpr int NS = 16;
+  static thread_local cudaStream_t pool[NS] = {nullptr};
+  static thread_local cudaEvent_t fork_ev = nullptr, join_ev[NS] = {nullptr};
+  static thread_local int pool_device = -1;
+  if (pool_device != ctx->device) {
+    for (int q = 0; q < NS; ++q) {
+      GINGR_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&pool[q], cudaStreamNonBlocking));
+      GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&join_ev[q], cudaEventDisableTiming));
+    }
+    GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+    pool_device = ctx->device;
+  }
+  // capture (or re-key) every chain's graph on the ctx stream first: capture is not concurrent
+  for (int k = 0; k < n; ++k) {
+    gingr_registration* g = regs[k];
+    const uint64_t sk = seed + (uint64_t)k;
+    if (!g->graph_exec || g->graph_prob != (probabilistic != 0) || (probabilistic && g->graph_seed != sk)) {
+      drop_graph(g);
+      const int64_t l0 = ctx->launches;
+      GINGR_CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      const int32_t rc = enqueue_iteration(g, probabilistic != 0, sk);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+      g->graph_launches = ctx->launches - l0;
+      ctx->launches = l0;
+      if (rc < 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+      GINGR_CUDA_TRY(ctx, e);
+      const cudaError_t e2 = cudaGraphInstantiate(&g->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      GINGR_CUDA_TRY(ctx, e2);
+      g->graph_prob = probabilistic != 0;
+      g->graph_seed = sk;
+    }
+  }
+  const int ns = std::min(NS, (int)n);
+  GINGR_CUDA_TRY(ctx, cudaEventRecord(fork_ev, ctx->stream));
+  for (int q = 0; q < ns; ++q) GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(pool[q], fork_ev, 0));
+  for (int it = 0; it < iters; ++it)
+    for (int k = 0; k < n; ++k) {  // chain k always runs on stream k % ns: its iterations stay ordered
+      gingr_registration* g = regs[k];
+      cudaStream_t st = pool[k % ns];
+      GINGR_CUDA_TRY(ctx, cudaGraphLaunch(g->graph_exec, st));
+      bump_iteration_kernel<<<1, 1, 0, st>>>(g->is.p);
+      ctx->launches += g->graph_launches + 1;
+    }
+  for (int q = 0; q < ns; ++q) {
+    GINGR_CUDA_TRY(ctx, cudaEventRecord(join_ev[q], pool[q]));
+    GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, join_ev[q], 0));
+  }
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
 int32_t gingr_registration_set_profiling(gingr_registration* g, int32_t enable) {
   if (!g) return GINGR_ERR_ARG;
   gingr_ctx* ctx = g->ctx;

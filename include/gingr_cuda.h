@@ -222,7 +222,14 @@ GINGR_API int32_t gingr_update_chain(gingr_registration* reg, int32_t iters);
 /* The same with probabilistic = true in every step (a chain of informed posterior-sample proposals that are all
  * accepted, i.e. GeneratorWrapperStochastic.gingrPropose without the MH accept/reject of the caller). */
 GINGR_API int32_t gingr_update_chain_sampled(gingr_registration* reg, int32_t iters, uint64_t seed);
-/* Read back the device-resident state after gingr_update_chain. */
+/* Independent registrations / MCMC chains batched on one GPU (BASELINE config 5; SURVEY.md 8e "replicas only"):
+ * `iters` update+propose steps of each of the n registrations (all created on the same ctx, typically sharing one
+ * model and one target handle, each with its own device-resident state).  Chain k uses seed + k when
+ * probabilistic != 0.  The chains' captured iteration graphs are replayed on a pool of streams; the call returns
+ * after enqueueing, results are read with gingr_state_download per chain. */
+GINGR_API int32_t gingr_update_batch(gingr_registration** regs, int32_t n, int32_t iters, int32_t probabilistic,
+                                     uint64_t seed);
+/* Read back the device-resident state after gingr_update_chain / gingr_update_batch. */
 GINGR_API int32_t gingr_state_download(gingr_registration* reg, gingr_state* state_out, double* alpha_out,
                                        double* fit_out);
 

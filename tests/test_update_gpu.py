@@ -311,3 +311,37 @@ def test_probabilistic_retry_counter(ctx, oracle):
     assert statuses_g == statuses_o
     assert statuses_g[:11] == [api.STATUS_NONE] * 11 and statuses_g[11] == api.STATUS_MODEL_FLEXIBILITY_ERROR
     reg.close()
+
+
+def test_batched_chains_equal_independent_chains(ctx, oracle):
+    """gingr_update_batch (BASELINE config 5: batched MCMC chains, replicas only): n chains sharing model and target,
+    each with its own state and Philox stream, give exactly what the same chains give one by one."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 100, 100, 30, seed=13)
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    n, iters, seed = 24, 4, 1000
+    cfg = api.IcpConfiguration(initialSigma=2.0, endSigma=1.0)
+    chains = [api.IcpRegistration(ctx, dm, dt, cfg) for _ in range(n)]
+    for c in chains:
+        c.initializeState()
+    api.update_batch(chains, iters, probabilistic=True, seed=seed)
+    got = [c.downloadState() for c in chains]
+    for k in (0, 1, 7, 23):
+        solo = api.IcpRegistration(ctx, dm, dt, cfg)
+        solo.initializeState()
+        solo.updateChainSampled(iters, seed + k)
+        ref = solo.downloadState()
+        assert np.array_equal(got[k].fit, ref.fit) and got[k].iteration == iters
+        assert np.array_equal(got[k].modelParameters.shape, ref.modelParameters.shape)
+        solo.close()
+    assert not np.array_equal(got[0].fit, got[1].fit)          # different seeds, different chains
+    # and against the oracle for one chain
+    oalgo = oracle.IcpAlgorithm(oracle.IcpConfig(initial_sigma=2.0, end_sigma=1.0))
+    ost = oalgo.initialize(oracle.initial_state(m, target, tt, global_transformation=oracle.RIGID_TRANSFORMS))
+    for _ in range(iters):
+        ost = oracle.propose(oalgo, ost, probabilistic=True, seed=seed + 7)
+    diag = np.linalg.norm(m.ref.max(0) - m.ref.min(0))
+    assert np.max(np.abs(got[7].fit - ost.fit)) < 1e-6 * diag
+    for c in chains:
+        c.close()
