@@ -304,13 +304,23 @@ def run_ours(args):
         gram_flop = 3.0 * m_local * r * (r + 1)
         estep_tf = estep_flop / ((t_a + t_b) * 1e-3) / 1e12 if (t_a + t_b) > 0 else 0.0
         gram_tf = gram_flop / (t_g * 1e-3) / 1e12 if t_g > 0 else 0.0
+        # DRAM bytes per launch from the committed ncu --set full capture of this workload (profiles/ncu_traffic.json);
+        # only valid for the configuration it was captured on (C4, 1 GPU)
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if name == "c4" and world == 1 and os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = {k: v["dram_bytes"] for k, v in json.load(f)["kernels"].items()}
+        tr_estep = (traffic.get("estep_colsum_kernel", 0) + traffic.get("estep_rowsum_kernel", 0)) or None
         rl_estep = {"kernel": "estep_colsum_kernel+estep_rowsum_kernel (K1)", "bound": "fp64", "achieved": estep_tf,
-                    "peak": dfma_peak, "unit": "TFLOP/s", "frac": estep_tf / dfma_peak, "traffic": None,
+                    "peak": dfma_peak, "unit": "TFLOP/s", "frac": estep_tf / dfma_peak, "traffic": tr_estep,
                     "ms": t_a + t_b, "algorithmic_flop": estep_flop,
+                    "algorithmic_bytes": 24.0 * (M + n_local) + 8.0 * (4 * M + n_local),
                     "peak_source": "FP64_PEAKS.json dfma_tflops_sustained (measured, tools/fp64_peaks.cu)"}
-        rl_gram = {"kernel": "gram_streamk_kernel (K3, DMMA.8x8x4)", "bound": "tensor", "achieved": gram_tf,
-                   "peak": dmma_peak, "unit": "TFLOP/s", "frac": gram_tf / dmma_peak, "traffic": None,
-                   "ms": t_g, "algorithmic_flop": gram_flop,
+        rl_gram = {"kernel": "gram_ws_kernel (K3, DMMA.8x8x4, warp-specialised, cp.async.bulk)", "bound": "tensor",
+                   "achieved": gram_tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": gram_tf / dmma_peak,
+                   "traffic": traffic.get("gram_ws_kernel"), "ms": t_g, "algorithmic_flop": gram_flop,
+                   "algorithmic_bytes": 8.0 * 3 * m_local * r,
                    "peak_source": "FP64_PEAKS.json max(cuBLAS DGEMM sustained, DMMA issue peak) (measured)"}
         dominant = rl_estep if (t_a + t_b) >= t_g else rl_gram
         cpu = None
