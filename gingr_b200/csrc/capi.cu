@@ -66,7 +66,10 @@ int32_t gingr_ctx_create(int32_t device, gingr_ctx** out) {
     return gingr_fail(nullptr, GINGR_ERR_CUDA, "gingr_ctx_create: device is not sm_100 (Blackwell) -- unsupported");
   }
   ctx->num_sms = prop.multiProcessorCount;
-  GINGR_CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  GINGR_CUDA_TRY(nullptr, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  GINGR_CUDA_TRY(nullptr, cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
+  GINGR_CUDA_TRY(nullptr, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_lo));
   GINGR_CUDA_TRY(nullptr, cudaMallocHost((void**)&ctx->h_pinned, ctx->h_pinned_count * sizeof(double)));
   *out = ctx;
   return GINGR_OK;
@@ -86,6 +89,8 @@ int32_t gingr_ctx_destroy(gingr_ctx* ctx) {
   s->ua.release();
   gingr::comm_destroy(ctx);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (auto& e : ctx->chol_events) cudaEventDestroy(e);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   cudaStreamDestroy(ctx->stream);
   delete static_cast<gingr_ctx_full*>(ctx);
   return GINGR_OK;

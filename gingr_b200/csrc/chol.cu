@@ -12,6 +12,10 @@
 // Rows below the square part (right-hand sides stored as extra rows) ride along, which performs the
 // forward substitution L^-1 b inside the factorisation.  The backward substitution L^-T z is a sync-free
 // multi-CTA kernel: one CTA per 64-block, consuming solved blocks as their ready flags appear.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "posterior.cuh"
 
@@ -172,12 +176,12 @@ __device__ __forceinline__ void dmma884s(double& c0, double& c1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(128) chol_syrk_kernel(int nrows, int n, int j0, int jb, int r0,
+__global__ void __launch_bounds__(128) chol_syrk_kernel(int nrows, int n, int j0, int jb, int r0, int tk_begin,
                                                         double* __restrict__ A, int ld) {
   extern __shared__ __align__(16) double sm[];
   double* sI = sm;            // [64][UP] rows of the row tile
   double* sK = sm + NB * UP;  // [64][UP] rows of the column tile
-  const int ti = blockIdx.y, tk = blockIdx.x;
+  const int ti = blockIdx.y, tk = blockIdx.x + tk_begin;
   const int i0 = r0 + ti * NB, k0 = r0 + tk * NB;
   if (k0 > i0 || k0 >= n || i0 >= nrows) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -316,7 +320,21 @@ int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, 
     attr_device = ctx->device;
   }
   cudaStream_t st = ctx->stream;
-  for (int j0 = 0; j0 < n; j0 += NB) {
+  // Lookahead: the trailing update of step j is split into A(j) = the next block column (what the next panel
+  // needs) on the main stream and B(j) = everything to the right of it on the low-priority side stream, which then
+  // overlaps panel(j + 1).  Dependencies: B(j) after panel(j); A(j) after B(j - 1) (both update block column j + 1).
+  // Inside a stream capture these event edges become graph dependencies.
+  static const int env_la = [] { const char* e = getenv("GINGR_CHOL_LOOKAHEAD"); return e ? atoi(e) : 1; }();
+  const int nb = ceil_div(n, NB);
+  const bool lookahead = env_la != 0 && ctx->side_stream != nullptr && nb >= 4;
+  if (lookahead && (int)ctx->chol_events.size() < 2 * nb) {
+    const size_t old = ctx->chol_events.size();
+    ctx->chol_events.resize((size_t)2 * nb);
+    for (size_t k = old; k < ctx->chol_events.size(); ++k)
+      GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->chol_events[k], cudaEventDisableTiming));
+  }
+  int last_b = -1;
+  for (int j0 = 0, j = 0; j0 < n; j0 += NB, ++j) {
     const int jb = std::min(NB, n - j0);
     const int below = nrows - (j0 + jb);
     const int pblocks = std::max(1, ceil_div(below, PR));
@@ -325,10 +343,25 @@ int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, 
     if (below > 0 && j0 + jb < n) {
       const int r0 = j0 + jb;
       const int nti = ceil_div(nrows - r0, NB), ntk = ceil_div(n - r0, NB);
-      chol_syrk_kernel<<<dim3(ntk, nti), 128, SYRK_SMEM, st>>>(nrows, n, j0, jb, r0, d_A, ld);
-      GINGR_LAUNCHED(ctx);
+      if (!lookahead || ntk < 2) {
+        if (last_b >= 0) { GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chol_events[2 * last_b + 1], 0)); last_b = -1; }
+        chol_syrk_kernel<<<dim3(ntk, nti), 128, SYRK_SMEM, st>>>(nrows, n, j0, jb, r0, 0, d_A, ld);
+        GINGR_LAUNCHED(ctx);
+      } else {
+        cudaEvent_t ev_p = ctx->chol_events[2 * j], ev_b = ctx->chol_events[2 * j + 1];
+        GINGR_CUDA_TRY(ctx, cudaEventRecord(ev_p, st));
+        GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side_stream, ev_p, 0));
+        chol_syrk_kernel<<<dim3(ntk - 1, nti), 128, SYRK_SMEM, ctx->side_stream>>>(nrows, n, j0, jb, r0, 1, d_A, ld);  // B(j)
+        GINGR_LAUNCHED(ctx);
+        GINGR_CUDA_TRY(ctx, cudaEventRecord(ev_b, ctx->side_stream));
+        if (last_b >= 0) GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chol_events[2 * last_b + 1], 0));
+        chol_syrk_kernel<<<dim3(1, nti), 128, SYRK_SMEM, st>>>(nrows, n, j0, jb, r0, 0, d_A, ld);                       // A(j)
+        GINGR_LAUNCHED(ctx);
+        last_b = j;
+      }
     }
   }
+  if (last_b >= 0) GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chol_events[2 * last_b + 1], 0));
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
 }

@@ -1301,8 +1301,10 @@ static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, u
 }
 
 static bool graphs_enabled(const gingr_ctx* ctx) {
-  static const int env = [] { const char* e = getenv("GINGR_CUDA_GRAPH"); return e ? atoi(e) : 1; }();
-  return env != 0 && ctx->nranks == 1;  // NCCL collectives stay outside graphs
+  static const int env = [] { const char* e = getenv("GINGR_CUDA_GRAPH"); return e ? atoi(e) : 2; }();
+  // GINGR_CUDA_GRAPH: 0 = off, 1 = single-GPU contexts only, 2 (default) = also capture the NCCL collectives of a
+  // multi-rank iteration (NCCL >= 2.9 supports stream capture; the ranks run the same deterministic sequence)
+  return env != 0 && (ctx->nranks == 1 || env >= 2);
 }
 
 static void drop_graph(gingr_registration* g) {
