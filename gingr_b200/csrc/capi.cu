@@ -123,8 +123,10 @@ int32_t gingr_target_upload(gingr_ctx* ctx, int32_t N, const double* pts, const 
   gingr_target* t = new gingr_target();
   t->ctx = ctx;
   t->N_total = N;
-  for (size_t k = 0; k < (size_t)3 * N; ++k)
+  for (size_t k = 0; k < (size_t)3 * N; ++k) {
     if (!(fabs(pts[k]) < INFINITY)) { t->nonfinite = true; break; }
+    t->maxabs = std::max(t->maxabs, fabs(pts[k]));
+  }
   shard_range(N, ctx->nranks, ctx->rank, &t->n0, &t->N);
   // full vertex set (SoA) -- the ICP search and the single-GPU E-step use it; the E-step shard is a view
   // into a separately packed SoA when sharded.
@@ -175,6 +177,14 @@ static bool host_nonfinite(const double* v, size_t n) {
   for (size_t k = 0; k < n; ++k)
     if (!(fabs(v[k]) < INFINITY)) return true;
   return false;
+}
+
+// upper bound of every squared pair distance from the coordinate ranges: |x - y|^2 <= 3 (max|x| + max|y|)^2
+static double d2_bound(const gingr_target* target, const double* fit, size_t n3) {
+  double m = 0.0;
+  for (size_t k = 0; k < n3; ++k) m = std::max(m, fabs(fit[k]));
+  const double s = m + target->maxabs;
+  return 3.0 * s * s;
 }
 
 static void fill_nan(double* p, size_t n) {
@@ -230,6 +240,7 @@ int32_t gingr_cpd_estep(gingr_ctx* ctx, const gingr_target* target, int32_t M, c
   h[0] = sigma2;
   h[3] = w;
   h[4] = (double)M / (double)target->N_total;
+  h[7] = d2_bound(target, fit, (size_t)3 * M);
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(ws->scal.p, h, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
   GINGR_TRY(gingr::estep_cpd_scalars_enqueue(ctx, ws->scal.p));
   if (target->N > 0) GINGR_TRY(gingr::estep_enqueue(ctx, *ws, M, target->N, target->soa.p, false));
@@ -259,6 +270,7 @@ int32_t gingr_bcpd_estep(gingr_ctx* ctx, const gingr_target* target, int32_t M, 
   h[3] = w;
   h[5] = s;
   h[6] = 1.0 / (double)target->N_total;
+  h[7] = d2_bound(target, y, (size_t)3 * M);
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(ws->scal.p, h, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
   GINGR_TRY(gingr::estep_bcpd_rowf_enqueue(ctx, M, sc->b.p, sc->b.p + M, ws->scal.p, ws->rowf.p));
   if (target->N > 0) GINGR_TRY(gingr::estep_enqueue(ctx, *ws, M, target->N, target->soa.p, true));

@@ -53,6 +53,7 @@ struct gingr_target {
   gingr_ctx* ctx = nullptr;
   int N_total = 0;      // number of target points in the whole target
   int n0 = 0, N = 0;    // this rank's shard [n0, n0 + N) for the E-step (== whole target when nranks == 1)
+  double maxabs = 0.0;  // max |coordinate| (bounds the pair distances: gauss_exp2_tab<SAFE>)
   bool nonfinite = false;  // a NaN/Inf coordinate: every E-step on it fails like the reference's NaN-filled P
   DevBuf<double> soa;   // E-step shard, SoA [3][N] (x[], y[], z[])
   // full mesh (ICP): vertices SoA [3][N_total], triangles, per-vertex normals and boundary flags

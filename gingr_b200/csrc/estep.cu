@@ -35,7 +35,7 @@ namespace gingr {
 #define ESTEP_RB 4
 #endif
 #ifndef ESTEP_MINB_A
-#define ESTEP_MINB_A 4
+#define ESTEP_MINB_A 3
 #endif
 #ifndef ESTEP_MINB_B
 #define ESTEP_MINB_B 2
@@ -45,6 +45,55 @@ constexpr int CA = ESTEP_CA;   // columns per thread, sweep A
 constexpr int RB = ESTEP_RB;   // rows per thread, sweep B
 constexpr int TILE_ROWS = 512; // rows staged per shared-memory tile in sweep A
 constexpr int TILE_COLS = 256; // columns staged per shared-memory tile in sweep B
+
+// True when every pair of this launch satisfies 0 <= d2 * |negk64| < 2^31 - 2^18 (gauss_exp2_tab<SAFE>):
+// scal[7] = upper bound of d2 from the coordinate ranges of both clouds (<= 0 / non-finite: unknown).
+__device__ __forceinline__ bool estep_safe_range(const double* __restrict__ scal) {
+  const double sigma2 = scal[0], d2max = scal[7];
+  return sigma2 > 0.0 && d2max > 0.0 && d2max * (64.0 * 1.4426950408889634074 / (2.0 * sigma2)) < 2147221504.0;
+}
+
+template <bool SAFE>
+__device__ __forceinline__ void colsum_tile(int cnt, const double4* __restrict__ ytile, const double (&xj)[CA],
+                                            const double (&yj)[CA], const double (&zj)[CA], double (&acc)[CA],
+                                            double negk, const unsigned int* s_tab, int lane_off) {
+#pragma unroll 2
+  for (int t = 0; t < cnt; ++t) {
+    const double4 y = ytile[t];
+#pragma unroll
+    for (int c = 0; c < CA; ++c) {
+      const double dx = xj[c] - y.x, dy = yj[c] - y.y, dz = zj[c] - y.z;
+      double d2 = dx * dx;
+      d2 = fma(dy, dy, d2);
+      d2 = fma(dz, dz, d2);
+      acc[c] = fma(gauss_exp2_tab<SAFE>(d2, negk, s_tab, lane_off), y.w, acc[c]);
+    }
+  }
+}
+
+template <bool SAFE>
+__device__ __forceinline__ void rowsum_tile(int cnt, const double4* __restrict__ xtile, const double (&yx)[RB],
+                                            const double (&yy)[RB], const double (&yz)[RB], double (&a0)[RB],
+                                            double (&a1)[RB], double (&a2)[RB], double (&a3)[RB], double negk,
+                                            const unsigned int* s_tab, int lane_off) {
+#pragma unroll 2
+  for (int t = 0; t < cnt; ++t) {
+    const double4 xa = xtile[2 * t];
+    const double4 xb = xtile[2 * t + 1];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      const double dx = xa.x - yx[q], dy = xa.y - yy[q], dz = xa.z - yz[q];
+      double d2 = dx * dx;
+      d2 = fma(dy, dy, d2);
+      d2 = fma(dz, dz, d2);
+      const double k = gauss_exp2_tab<SAFE>(d2, negk, s_tab, lane_off);
+      a0[q] = fma(k, xa.w, a0[q]);
+      a1[q] = fma(k, xb.x, a1[q]);
+      a2[q] = fma(k, xb.y, a2[q]);
+      a3[q] = fma(k, xb.z, a3[q]);
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // sweep A: column sums.   grid = (col blocks, row splits)
@@ -77,6 +126,7 @@ __global__ void __launch_bounds__(TPB, ESTEP_MINB_A) estep_colsum_kernel(int M, 
     zj[c] = target[2 * N + j];
     acc[c] = 0.0;
   }
+  const bool safe = estep_safe_range(scal);
   for (int i0 = i_begin; i0 < i_end; i0 += TILE_ROWS) {
     const int cnt = min(TILE_ROWS, i_end - i0);
     __syncthreads();
@@ -85,18 +135,8 @@ __global__ void __launch_bounds__(TPB, ESTEP_MINB_A) estep_colsum_kernel(int M, 
       ytile[t] = make_double4(fit[i], fit[M + i], fit[2 * M + i], rowf ? rowf[i] : 1.0);
     }
     __syncthreads();
-#pragma unroll 2
-    for (int t = 0; t < cnt; ++t) {
-      const double4 y = ytile[t];
-#pragma unroll
-      for (int c = 0; c < CA; ++c) {
-        const double dx = xj[c] - y.x, dy = yj[c] - y.y, dz = zj[c] - y.z;
-        double d2 = dx * dx;
-        d2 = fma(dy, dy, d2);
-        d2 = fma(dz, dz, d2);
-        acc[c] = fma(gauss_exp2_tab(d2, negk, s_tab, lane_off), y.w, acc[c]);
-      }
-    }
+    if (safe) colsum_tile<true>(cnt, ytile, xj, yj, zj, acc, negk, s_tab, lane_off);
+    else colsum_tile<false>(cnt, ytile, xj, yj, zj, acc, negk, s_tab, lane_off);
   }
 #pragma unroll
   for (int c = 0; c < CA; ++c)
@@ -170,28 +210,14 @@ __global__ void __launch_bounds__(TPB, ESTEP_MINB_B) estep_rowsum_kernel(int M, 
     a0[q] = a1[q] = a2[q] = a3[q] = 0.0;
   }
   const double4* pack4 = reinterpret_cast<const double4*>(pack);
+  const bool safe = estep_safe_range(scal);
   for (int j0 = j_begin; j0 < j_end; j0 += TILE_COLS) {
     const int cnt = min(TILE_COLS, j_end - j0);
     __syncthreads();
     for (int t = threadIdx.x; t < 2 * cnt; t += TPB) xtile[t] = pack4[(size_t)j0 * 2 + t];
     __syncthreads();
-#pragma unroll 2
-    for (int t = 0; t < cnt; ++t) {
-      const double4 xa = xtile[2 * t];
-      const double4 xb = xtile[2 * t + 1];
-#pragma unroll
-      for (int q = 0; q < RB; ++q) {
-        const double dx = xa.x - yx[q], dy = xa.y - yy[q], dz = xa.z - yz[q];
-        double d2 = dx * dx;
-        d2 = fma(dy, dy, d2);
-        d2 = fma(dz, dz, d2);
-        const double k = gauss_exp2_tab(d2, negk, s_tab, lane_off);
-        a0[q] = fma(k, xa.w, a0[q]);
-        a1[q] = fma(k, xb.x, a1[q]);
-        a2[q] = fma(k, xb.y, a2[q]);
-        a3[q] = fma(k, xb.z, a3[q]);
-      }
-    }
+    if (safe) rowsum_tile<true>(cnt, xtile, yx, yy, yz, a0, a1, a2, a3, negk, s_tab, lane_off);
+    else rowsum_tile<false>(cnt, xtile, yx, yy, yz, a0, a1, a2, a3, negk, s_tab, lane_off);
   }
 #pragma unroll
   for (int q = 0; q < RB; ++q)

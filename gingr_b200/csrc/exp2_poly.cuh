@@ -82,6 +82,10 @@ __constant__ double GAUSS_C[8] = {GAUSS_EXP2_A1, GAUSS_EXP2_A2, GAUSS_EXP2_A3, G
 // range.  The zero is SELECTED (not a skipped accumulation): the reference evaluates 0 * (1 / 0) = NaN for a column
 // whose denominators vanish (CPD.scala:71-74), and that NaN must reach P1 / PX.
 // lane_off = (lane & 15) * 8; s_tab = the CTA's table (gauss_tab_fill).
+// SAFE: the caller guarantees 0 <= -negk64 * d2 < 2^31 - 2^18 for every pair of the launch (bounding boxes, see
+// estep_safe_range), so the high word of tmp cannot leave {0x43380000, 0x4337ffff} and ONE signed compare of the
+// low word decides validity -- two issue slots less per evaluation in a loop that is issue bound.
+template <bool SAFE>
 __device__ __forceinline__ double gauss_exp2_tab(double d2, double negk64, const unsigned int* s_tab, int lane_off) {
   const double SHIFT = GAUSS_C[5];
   const double tmp = fma(d2, negk64, SHIFT);
@@ -99,7 +103,7 @@ __device__ __forceinline__ double gauss_exp2_tab(double d2, double negk64, const
   const double s = T * r;
   const double v = fma(s, p, T);
   // n in [-1085, 0]  <=>  lo in [963 * 64, 2048 * 64]
-  const bool ok = (hi == 0x43380000) && ((unsigned)(lo - 963 * 64) <= 1085u * 64u);
+  const bool ok = SAFE ? (lo >= 963 * 64) : ((hi == 0x43380000) && ((unsigned)(lo - 963 * 64) <= 1085u * 64u));
   return __hiloint2double(ok ? __double2hiint(v) : 0, ok ? __double2loint(v) : 0);
 }
 

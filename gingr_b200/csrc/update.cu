@@ -116,12 +116,27 @@ __global__ void compact_gather_kernel(int M, int nranks, int Mmax, const double*
 }
 
 // ---- CPD scalars for the E-step from the state block --------------------------------------------
-__global__ void cpd_estep_scalars_kernel(const double* __restrict__ ds, double w, double ratio, double* scal) {
+__global__ void __launch_bounds__(256) cpd_estep_scalars_kernel(const double* __restrict__ ds, double w, double ratio,
+                                                                int n3, const double* __restrict__ fit,
+                                                                double target_maxabs, double* scal) {
+  // max |coordinate| of the current fit -> bound of the pair distances (scal[7], gauss_exp2_tab<SAFE>)
+  __shared__ double red[256];
+  double m = 0.0;
+  for (int k = threadIdx.x; k < n3; k += 256) m = fmax(m, fabs(fit[k]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
   const double sigma2 = ds[DS_SIGMA2];
   const double t = 2.0 * 3.14159265358979323846 * sigma2;
   scal[0] = sigma2;
   scal[1] = 1.0;
   scal[2] = w / (1.0 - w) * (t * sqrt(t)) * ratio;  // CPD.scala:69-70
+  const double s = red[0] + target_maxabs;
+  scal[7] = 3.0 * s * s;
 }
 
 // xpx total (fixed order) appended behind the row block for the all-reduce.  One CTA of 256 threads.
@@ -1178,7 +1193,8 @@ static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, u
     GINGR_TRY(validate_finite_enqueue(ctx, 1, g->ds.p + DS_SIGMA2, g->is.p + IS_FAIL_POST));
     if (tg->nonfinite) GINGR_TRY(validate_finite_enqueue(ctx, 3 * tg->N_total, tg->verts.p, g->is.p + IS_FAIL_POST));
     GINGR_TRY(aos_to_soa_enqueue(ctx, M, g->fit.p, g->estep.fit_soa.p));
-    cpd_estep_scalars_kernel<<<1, 1, 0, st>>>(g->ds.p, cfg.w, (double)M / (double)tg->N_total, g->estep.scal.p);
+    cpd_estep_scalars_kernel<<<1, 256, 0, st>>>(g->ds.p, cfg.w, (double)M / (double)tg->N_total, 3 * M, g->fit.p,
+                                                tg->maxabs, g->estep.scal.p);
     GINGR_LAUNCHED(ctx);
     if (tg->N > 0) {
       EstepEvents ee;
