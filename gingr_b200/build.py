@@ -21,7 +21,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
 
 # per-file extra flags: closest.cu must not contract a*b+c into FMA (bit-exact argmin vs the JVM's
 # individually rounded operations)
-EXTRA = {"closest.cu": ["-fmad=false"]}
+EXTRA = {"closest.cu": ["-fmad=false"], "grid.cu": ["-fmad=false"]}
 
 
 def sources():

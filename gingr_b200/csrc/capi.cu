@@ -9,6 +9,7 @@
 #include "closest.cuh"
 #include "common.cuh"
 #include "estep.cuh"
+#include "grid.cuh"
 #include "nccl_dl.cuh"
 #include "posterior.cuh"
 
@@ -152,6 +153,18 @@ int32_t gingr_target_upload(gingr_ctx* ctx, int32_t N, const double* pts, const 
       }
     GINGR_TRY(gingr::mesh_static_upload(ctx, N, pts, T, tri, &t->normals, &t->boundary));
   }
+  if (gingr::grid_wanted(N) && !t->nonfinite) {
+    gingr::VertexArray va;
+    va.p = t->aos.p;
+    t->pgrid = new gingr::SpatialGrid();
+    GINGR_TRY(t->pgrid->ensure(ctx, N, N, false));
+    GINGR_TRY(gingr::grid_build_points_enqueue(ctx, *t->pgrid, N, va));
+    if (T > 0) {
+      t->tgrid = new gingr::SpatialGrid();
+      GINGR_TRY(t->tgrid->ensure(ctx, N, T, true));
+      GINGR_TRY(gingr::grid_build_triangles_enqueue(ctx, *t->tgrid, N, va, T, t->tri.p));
+    }
+  }
   GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   *out = t;
   return GINGR_OK;
@@ -166,6 +179,8 @@ int32_t gingr_target_destroy(gingr_target* t) {
   t->tri.release();
   t->normals.release();
   t->boundary.release();
+  if (t->pgrid) { t->pgrid->release(); delete t->pgrid; }
+  if (t->tgrid) { t->tgrid->release(); delete t->tgrid; }
   delete t;
   return GINGR_OK;
 }
@@ -317,11 +332,15 @@ struct TemplateUpload {
   DevBuf<double> aos, soa, normals;
   DevBuf<int32_t> tri, off, adj;
   DevBuf<uint8_t> boundary;
-  void release() { aos.release(); soa.release(); normals.release(); tri.release(); off.release(); adj.release(); boundary.release(); }
+  gingr::SpatialGrid pgrid, tgrid;
+  void release() {
+    aos.release(); soa.release(); normals.release(); tri.release(); off.release(); adj.release(); boundary.release();
+    pgrid.release(); tgrid.release();
+  }
 };
 
 static int32_t upload_template(gingr_ctx* ctx, int M, const double* tpl, const int32_t* tpl_tri, int T, TemplateUpload* u,
-                               gingr::MeshView* view) {
+                               gingr::MeshView* view, bool want_pgrid) {
   cudaStream_t st = ctx->stream;
   GINGR_CUDA_TRY(ctx, u->aos.alloc((size_t)3 * M));
   GINGR_CUDA_TRY(ctx, u->soa.alloc((size_t)3 * M));
@@ -353,6 +372,20 @@ static int32_t upload_template(gingr_ctx* ctx, int M, const double* tpl, const i
     view->normals = u->normals.p;
     view->boundary = u->boundary.p;
   }
+  if (gingr::grid_wanted(M)) {
+    gingr::VertexArray va;
+    va.p = u->aos.p;
+    if (want_pgrid) {
+      GINGR_TRY(u->pgrid.ensure(ctx, M, M, false));
+      GINGR_TRY(gingr::grid_build_points_enqueue(ctx, u->pgrid, M, va));
+      view->pgrid = &u->pgrid;
+    }
+    if (T > 0) {
+      GINGR_TRY(u->tgrid.ensure(ctx, M, T, true));
+      GINGR_TRY(gingr::grid_build_triangles_enqueue(ctx, u->tgrid, M, va, T, u->tri.p));
+      view->tgrid = &u->tgrid;
+    }
+  }
   return GINGR_OK;
 }
 
@@ -365,6 +398,8 @@ static gingr::MeshView target_view(const gingr_target* t) {
   v.tri = t->tri.p;
   v.normals = t->normals.p;
   v.boundary = t->boundary.p;
+  v.pgrid = t->pgrid;
+  v.tgrid = t->tgrid;
   return v;
 }
 
@@ -378,7 +413,7 @@ int32_t gingr_icp_closest(gingr_ctx* ctx, const gingr_target* target, int32_t M,
   TemplateUpload up;
   gingr::MeshView tv;
   int32_t rc = ws.ensure(ctx, M, target->N_total, target->T, T);
-  if (rc >= 0) rc = upload_template(ctx, M, tpl, tpl_tri, T, &up, &tv);
+  if (rc >= 0) rc = upload_template(ctx, M, tpl, tpl_tri, T, &up, &tv, false);
   if (rc >= 0) rc = gingr::icp_correspondence_enqueue(ctx, ws, tv, target_view(target), method);
   cudaStream_t st = ctx->stream;
   cudaError_t e = cudaSuccess;
@@ -409,13 +444,13 @@ int32_t gingr_icp_closest_reversal(gingr_ctx* ctx, const gingr_target* target, i
   gingr::MeshView tv;
   DevBuf<int32_t> tid;
   int32_t rc = ws.ensure(ctx, N, M, T, target->T);
-  if (rc >= 0) rc = upload_template(ctx, M, tpl, tpl_tri, T, &up, &tv);
+  if (rc >= 0) rc = upload_template(ctx, M, tpl, tpl_tri, T, &up, &tv, true);
   // corr = closestPointCorrespondence(target, template): the roles are swapped (:38)
   if (rc >= 0) rc = gingr::icp_correspondence_enqueue(ctx, ws, target_view(target), tv, method);
   cudaStream_t st = ctx->stream;
   cudaError_t e = tid.alloc((size_t)N);
   // templateId = template.pointSet.findClosestPoint(p).id for the corresponding point p (:40)
-  if (rc >= 0 && e == cudaSuccess) rc = gingr::nn_vertex_enqueue(ctx, ws, N, ws.cp.p, M, up.soa.p, ws.d2.p, tid.p);
+  if (rc >= 0 && e == cudaSuccess) rc = gingr::nn_vertex_enqueue(ctx, ws, N, ws.cp.p, M, up.soa.p, ws.d2.p, tid.p, tv.pgrid, ws.qorder);
   if (rc >= 0) {
     if (tpl_id && e == cudaSuccess) e = cudaMemcpyAsync(tpl_id, tid.p, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, st);
     if (w && e == cudaSuccess) e = cudaMemcpyAsync(w, ws.w.p, (size_t)N, cudaMemcpyDeviceToHost, st);

@@ -16,7 +16,9 @@
 #include <vector>
 
 #include "closest.cuh"
+#include "closest_geom.cuh"
 #include "common.cuh"
+#include "grid.cuh"
 
 namespace gingr {
 
@@ -79,47 +81,6 @@ __global__ void nn_reduce_kernel(int M, int splits, const double* __restrict__ p
   }
   d2[i] = best;
   idx[i] = bi;
-}
-
-// ---------------------------------------------------------------------------------------------
-// closest point on a triangle (Ericson 5.1.5).  Same operation order as the oracle.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void closest_on_triangle(double px, double py, double pz, const double* a, const double* b,
-                                                    const double* c, double& ox, double& oy, double& oz) {
-  const double abx = b[0] - a[0], aby = b[1] - a[1], abz = b[2] - a[2];
-  const double acx = c[0] - a[0], acy = c[1] - a[1], acz = c[2] - a[2];
-  const double apx = px - a[0], apy = py - a[1], apz = pz - a[2];
-  const double d1 = abx * apx + aby * apy + abz * apz;
-  const double d2 = acx * apx + acy * apy + acz * apz;
-  if (d1 <= 0.0 && d2 <= 0.0) { ox = a[0]; oy = a[1]; oz = a[2]; return; }
-  const double bpx = px - b[0], bpy = py - b[1], bpz = pz - b[2];
-  const double d3 = abx * bpx + aby * bpy + abz * bpz;
-  const double d4 = acx * bpx + acy * bpy + acz * bpz;
-  if (d3 >= 0.0 && d4 <= d3) { ox = b[0]; oy = b[1]; oz = b[2]; return; }
-  const double vc = d1 * d4 - d3 * d2;
-  if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {
-    const double v = d1 / (d1 - d3);
-    ox = a[0] + v * abx; oy = a[1] + v * aby; oz = a[2] + v * abz; return;
-  }
-  const double cpx = px - c[0], cpy = py - c[1], cpz = pz - c[2];
-  const double d5 = abx * cpx + aby * cpy + abz * cpz;
-  const double d6 = acx * cpx + acy * cpy + acz * cpz;
-  if (d6 >= 0.0 && d5 <= d6) { ox = c[0]; oy = c[1]; oz = c[2]; return; }
-  const double vb = d5 * d2 - d1 * d6;
-  if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
-    const double w = d2 / (d2 - d6);
-    ox = a[0] + w * acx; oy = a[1] + w * acy; oz = a[2] + w * acz; return;
-  }
-  const double va = d3 * d6 - d5 * d4;
-  if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) {
-    const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
-    ox = b[0] + w * (c[0] - b[0]); oy = b[1] + w * (c[1] - b[1]); oz = b[2] + w * (c[2] - b[2]); return;
-  }
-  const double denom = 1.0 / (va + vb + vc);
-  const double v = vb * denom, w = vc * denom;
-  ox = a[0] + abx * v + acx * w;
-  oy = a[1] + aby * v + acy * w;
-  oz = a[2] + abz * v + acz * w;
 }
 
 // part: [splits][M] d2, tri ; [splits][M][3] cp
@@ -220,24 +181,8 @@ __global__ void __launch_bounds__(QT) line_mesh_kernel(int M, const double* __re
     __syncthreads();
     for (int t = 0; t < cnt; ++t) {
       if (SELF && (sv[t][0] == ii || sv[t][1] == ii || sv[t][2] == ii)) continue;
-      const double* a = &st[t][0];
-      const double e1x = st[t][3] - a[0], e1y = st[t][4] - a[1], e1z = st[t][5] - a[2];
-      const double e2x = st[t][6] - a[0], e2y = st[t][7] - a[1], e2z = st[t][8] - a[2];
-      const double hx = dy * e2z - dz * e2y, hy = dz * e2x - dx * e2z, hz = dx * e2y - dy * e2x;
-      const double det = e1x * hx + e1y * hy + e1z * hz;
-      if (det == 0.0) continue;
-      const double inv = 1.0 / det;
-      const double tx = ox - a[0], ty = oy - a[1], tz = oz - a[2];
-      const double u = (tx * hx + ty * hy + tz * hz) * inv;
-      if (u < 0.0 || u > 1.0) continue;
-      const double qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
-      const double vv = (dx * qx + dy * qy + dz * qz) * inv;
-      if (vv < 0.0 || u + vv > 1.0) continue;
-      const double s = (e2x * qx + e2y * qy + e2z * qz) * inv;
-      const double ix = ox + s * dx, iy = oy + s * dy, iz = oz + s * dz;
-      if (ix == ox && iy == oy && iz == oz) continue;
-      const double ex = ox - ix, ey = oy - iy, ez = oz - iz;
-      const double d = sqrt(ex * ex + ey * ey + ez * ez);
+      double d, ix, iy, iz;
+      if (!line_triangle_hit(ox, oy, oz, dx, dy, dz, &st[t][0], &st[t][3], &st[t][6], d, ix, iy, iz)) continue;
       if (d < best) {
         best = d;
         if (WITH_POINT) { bx = ix; by = iy; bz = iz; }
@@ -350,18 +295,38 @@ __global__ void gather_points_kernel(int M, const int32_t* __restrict__ idx, int
   out[3 * i + 2] = soa[2 * N + j];
 }
 
-// deterministic mean of sqrt(d2) (squared = 1) or of d2 itself (squared = 0): one block, fixed-order tree
-__global__ void mean_sqrt_kernel(int M, const double* __restrict__ d2, double* __restrict__ out, int squared = 1) {
+// deterministic mean of sqrt(d2) (squared = 1) or of d2 itself (squared = 0): fixed-order tree per block; large
+// inputs use MEAN_BLOCKS blocks whose partial sums the last stage adds in block order
+constexpr int MEAN_BLOCKS = 64;
+__global__ void __launch_bounds__(256) mean_sqrt_kernel(int M, const double* __restrict__ d2, double* __restrict__ out,
+                                                        int squared, int final_stage) {
   __shared__ double red[256];
   double s = 0.0;
-  for (int i = threadIdx.x; i < M; i += 256) s += squared ? sqrt(d2[i]) : d2[i];
+  if (final_stage == 2) {   // sum of the per-block partials (in d2), divided by M
+    for (int i = threadIdx.x; i < MEAN_BLOCKS; i += 256) s += d2[i];
+  } else {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < M; i += gridDim.x * 256) s += squared ? sqrt(d2[i]) : d2[i];
+  }
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[0] = red[0] / M;
+  if (threadIdx.x == 0) out[blockIdx.x] = final_stage ? red[0] / M : red[0];
+}
+
+static void mean_sqrt_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, int squared) {
+  cudaStream_t st = ctx->stream;
+  if (M <= 16384) {
+    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.d2.p, ws.mean_dist.p, squared, 1);
+    GINGR_LAUNCHED(ctx);
+  } else {
+    mean_sqrt_kernel<<<MEAN_BLOCKS, 256, 0, st>>>(M, ws.d2.p, ws.mean_part.p, squared, 0);
+    GINGR_LAUNCHED(ctx);
+    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.mean_part.p, ws.mean_dist.p, 0, 2);
+    GINGR_LAUNCHED(ctx);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -459,6 +424,11 @@ int32_t ClosestWorkspace::ensure(gingr_ctx* ctx, int nq, int n_search, int T_sea
   GINGR_CUDA_TRY(ctx, w.alloc((size_t)M));
   GINGR_CUDA_TRY(ctx, hit.alloc((size_t)M));
   GINGR_CUDA_TRY(ctx, mean_dist.alloc(1));
+  GINGR_CUDA_TRY(ctx, mean_part.alloc(MEAN_BLOCKS));
+  if (grid_wanted(std::max(n_search, std::max(T_search, T_query_mesh)))) {
+    if (!qorder) qorder = new SpatialGrid();
+    GINGR_TRY(qorder->ensure(ctx, nq, nq, false));
+  }
   return GINGR_OK;
 }
 
@@ -472,11 +442,15 @@ void ClosestWorkspace::release() {
   w.release();
   hit.release();
   mean_dist.release();
+  mean_part.release();
+  if (qorder) { qorder->release(); delete qorder; qorder = nullptr; }
 }
 
 // Nearest vertex (of a SoA point set) of arbitrary query points (AoS, device).
 int32_t nn_vertex_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, const double* d_q, int N,
-                          const double* d_pts_soa, double* d_d2, int32_t* d_idx) {
+                          const double* d_pts_soa, double* d_d2, int32_t* d_idx, const SpatialGrid* pgrid,
+                          const SpatialGrid* order) {
+  if (pgrid && pgrid->built) return grid_nn_enqueue(ctx, *pgrid, M, d_q, d_d2, d_idx, order);
   const int splits = std::min(ws.s_nn, std::max(1, ceil_div(N, PT)));
   nn_vertex_kernel<<<dim3(ceil_div(M, QT), splits), QT, 0, ctx->stream>>>(M, d_q, N, d_pts_soa, ws.part_d2.p,
                                                                           ws.part_idx.p);
@@ -495,29 +469,47 @@ int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const M
                                    int method) {
   cudaStream_t st = ctx->stream;
   const int M = tpl.n, N = tgt.n;
+  // any grid search ahead: sort the queries spatially once (a point grid over the template vertices)
+  const SpatialGrid* order = nullptr;
+  const bool any_grid = (tgt.pgrid && tgt.pgrid->built) || (tgt.tgrid && tgt.tgrid->built) || (tpl.tgrid && tpl.tgrid->built);
+  if (any_grid && ws.qorder && ws.qorder->cap_items >= M) {
+    VertexArray qa;
+    qa.p = tpl.aos;
+    GINGR_TRY(grid_build_points_enqueue(ctx, *ws.qorder, M, qa));
+    order = ws.qorder;
+  }
   if (method == GINGR_POINTCLOUD_CLOSEST_POINT) {
-    GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, tpl.aos, N, tgt.soa, ws.d2.p, ws.idx.p));
+    GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, tpl.aos, N, tgt.soa, ws.d2.p, ws.idx.p, tgt.pgrid, order));
     gather_points_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, ws.idx.p, N, tgt.soa, ws.cp.p);
     GINGR_LAUNCHED(ctx);
     GINGR_CUDA_TRY(ctx, cudaMemsetAsync(ws.w.p, 1, (size_t)M, st));
-    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.d2.p, ws.mean_dist.p);
-    GINGR_LAUNCHED(ctx);
+    mean_sqrt_enqueue(ctx, ws, M, 1);
     GINGR_CUDA_TRY(ctx, cudaGetLastError());
     return GINGR_OK;
   }
   if (tgt.T <= 0 || tpl.T <= 0 || !tpl.normals || !tgt.normals || !tgt.boundary || !tgt.aos)
     return gingr_fail(ctx, GINGR_ERR_ARG, "the mesh flavours of the ICP correspondence need template and target triangles");
   const int s_surf = std::min(ws.s_surf, std::max(1, ceil_div(tgt.T, TT)));
-  const int s_line = std::min(ws.s_line, std::max(1, ceil_div(tpl.T, TT)));
-  if (method == GINGR_TRIANGULAR_CLOSEST_POINT) {
+  int s_line = std::min(ws.s_line, std::max(1, ceil_div(tpl.T, TT)));
+  const bool tgt_grid = tgt.tgrid && tgt.tgrid->built, tpl_grid = tpl.tgrid && tpl.tgrid->built;
+  if (method == GINGR_TRIANGULAR_CLOSEST_POINT && tgt_grid) {
+    GINGR_TRY(grid_surface_enqueue(ctx, *tgt.tgrid, M, tpl.aos, tgt.aos, tgt.tri, ws.d2.p, nullptr, ws.cp.p, order));
+    mean_sqrt_enqueue(ctx, ws, M, 1);
+  } else if (method == GINGR_ALONG_NORMAL_CLOSEST_POINT && tgt_grid) {
+    GINGR_TRY(grid_line_enqueue(ctx, *tgt.tgrid, M, tpl.aos, tpl.normals, tgt.aos, tgt.tri, 0, ws.part_d2.p, ws.part_cp.p,
+                                order));
+    line_hit_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, 1, tpl.aos, ws.part_d2.p, ws.part_cp.p, ws.d2.p, ws.cp.p,
+                                                             ws.hit.p);
+    GINGR_LAUNCHED(ctx);
+    mean_sqrt_enqueue(ctx, ws, M, 0);  // distance += (p - closestPoint).norm (:128)
+  } else if (method == GINGR_TRIANGULAR_CLOSEST_POINT) {
     surface_kernel<<<dim3(ceil_div(M, QT), s_surf), QT, 0, st>>>(M, tpl.aos, N, tgt.soa, tgt.T, tgt.tri, ws.part_d2.p,
                                                                  ws.part_idx.p, ws.part_cp.p);
     GINGR_LAUNCHED(ctx);
     surface_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, s_surf, ws.part_d2.p, ws.part_idx.p, ws.part_cp.p,
                                                             ws.d2.p, nullptr, ws.cp.p);
     GINGR_LAUNCHED(ctx);
-    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.d2.p, ws.mean_dist.p);
-    GINGR_LAUNCHED(ctx);
+    mean_sqrt_enqueue(ctx, ws, M, 1);
   } else if (method == GINGR_ALONG_NORMAL_CLOSEST_POINT) {
     // nearest intersection of the line (p, n_p) with the target mesh (:105-110)
     const int s_hit = s_surf;
@@ -527,17 +519,21 @@ int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const M
     line_hit_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, s_hit, tpl.aos, ws.part_d2.p, ws.part_cp.p, ws.d2.p,
                                                              ws.cp.p, ws.hit.p);
     GINGR_LAUNCHED(ctx);
-    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.d2.p, ws.mean_dist.p, 0);  // distance += (p - closestPoint).norm (:128)
-    GINGR_LAUNCHED(ctx);
+    mean_sqrt_enqueue(ctx, ws, M, 0);  // distance += (p - closestPoint).norm (:128)
   } else {
     return gingr_fail(ctx, GINGR_ERR_ARG, "unknown ICP correspondence method");
   }
   // nearest target vertex of the corresponding point (:83 / :113); d2 of that search is not needed afterwards
-  GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, ws.cp.p, N, tgt.soa, ws.d2.p, ws.idx.p));
+  GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, ws.cp.p, N, tgt.soa, ws.d2.p, ws.idx.p, tgt.pgrid, order));
   // isClosestPointIntersecting on the template itself (:62-72)
-  line_mesh_kernel<true, true, false><<<dim3(ceil_div(M, QT), s_line), QT, 0, st>>>(M, tpl.aos, ws.cp.p, tpl.aos, tpl.T,
-                                                                                   tpl.tri, ws.part_d2.p, nullptr);
-  GINGR_LAUNCHED(ctx);
+  if (tpl_grid) {
+    GINGR_TRY(grid_line_enqueue(ctx, *tpl.tgrid, M, tpl.aos, ws.cp.p, tpl.aos, tpl.tri, 1, ws.part_d2.p, nullptr, order));
+    s_line = 1;
+  } else {
+    line_mesh_kernel<true, true, false><<<dim3(ceil_div(M, QT), s_line), QT, 0, st>>>(M, tpl.aos, ws.cp.p, tpl.aos, tpl.T,
+                                                                                     tpl.tri, ws.part_d2.p, nullptr);
+    GINGR_LAUNCHED(ctx);
+  }
   icp_weights_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, tpl.aos, ws.cp.p, ws.idx.p, tgt.boundary, tpl.normals,
                                                        tgt.normals, s_line, ws.part_d2.p,
                                                        method == GINGR_ALONG_NORMAL_CLOSEST_POINT ? ws.hit.p : nullptr,

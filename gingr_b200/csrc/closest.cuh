@@ -6,6 +6,8 @@
 
 namespace gingr {
 
+struct SpatialGrid;  // grid.cuh
+
 // A mesh as the correspondence kernels see it: device pointers, any of which may be null when the flavour does
 // not need it.  "template" = the mesh whose vertices are the queries, "target" = the mesh that is searched.
 struct MeshView {
@@ -16,6 +18,10 @@ struct MeshView {
   const int32_t* tri = nullptr;       // [3T]
   const double* normals = nullptr;    // [n][3] vertex normals of THIS geometry
   const uint8_t* boundary = nullptr;  // [n] pointIsOnBoundary
+  // optional uniform grids over THIS geometry (built by the owner, grid.cuh): when present the searches that scan
+  // this mesh run on the grid instead of the brute-force scan, with bit-identical results
+  const SpatialGrid* pgrid = nullptr;  // over the vertices
+  const SpatialGrid* tgrid = nullptr;  // over the triangles (needs aos)
 };
 
 struct ClosestWorkspace {
@@ -29,6 +35,8 @@ struct ClosestWorkspace {
   DevBuf<uint8_t> w;          // [nq]   0/1 weight
   DevBuf<uint8_t> hit;        // [nq]   along-normal: the line met the target
   DevBuf<double> mean_dist;   // [1]
+  DevBuf<double> mean_part;   // [64] per-block partial sums of the mean distance
+  SpatialGrid* qorder = nullptr;  // point grid over the queries = their spatial sort (grid searches only)
   // nq queries against a mesh of n_search vertices / T_search triangles; T_query_mesh triangles of the query mesh
   int32_t ensure(gingr_ctx* ctx, int nq, int n_search, int T_search, int T_query_mesh);
   void release();
@@ -41,7 +49,8 @@ int32_t mesh_static_upload(gingr_ctx* ctx, int n, const double* verts_aos_host, 
 int32_t vertex_normals_enqueue(gingr_ctx* ctx, int n, const double* d_verts_aos, const int32_t* d_tri,
                                const int32_t* d_adj_off, const int32_t* d_adj, double* d_normals);
 int32_t nn_vertex_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, const double* d_q, int N,
-                          const double* d_pts_soa, double* d_d2, int32_t* d_idx);
+                          const double* d_pts_soa, double* d_d2, int32_t* d_idx, const SpatialGrid* pgrid = nullptr,
+                          const SpatialGrid* order = nullptr);
 int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const MeshView& tpl, const MeshView& tgt,
                                    int method);
 int32_t reverse_fold_enqueue(gingr_ctx* ctx, int M, int N, const int32_t* d_tid, const uint8_t* d_w,

@@ -11,6 +11,7 @@
 #define GINGR_NUM_SMS_B200 148
 
 struct NcclApi;  // nccl_dl.cu
+namespace gingr { struct SpatialGrid; }  // grid.cuh
 
 struct gingr_ctx {
   int device = 0;
@@ -63,6 +64,9 @@ struct gingr_target {
   DevBuf<int32_t> tri;      // [3T]
   DevBuf<double> normals;   // [3][N_total]
   DevBuf<uint8_t> boundary; // [N_total]
+  // static uniform grids over the vertices / triangles (K2 at scale; null below the size where a scan wins)
+  gingr::SpatialGrid* pgrid = nullptr;
+  gingr::SpatialGrid* tgrid = nullptr;
 };
 
 struct gingr_model {

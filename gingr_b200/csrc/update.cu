@@ -32,6 +32,7 @@
 #include "closest.cuh"
 #include "common.cuh"
 #include "estep.cuh"
+#include "grid.cuh"
 #include "nccl_dl.cuh"
 #include "posterior.cuh"
 
@@ -581,6 +582,8 @@ struct gingr_registration {
   GramPlan gram;
   DevBuf<double> fit_normals;  // [M][3] vertex normals of the current fit (ICP mesh flavours)
   DevBuf<double> fit_soa;      // [3][M] (reversed ICP: the fit is the mesh that is searched)
+  SpatialGrid fit_pgrid, fit_tgrid;  // uniform grids over the moving fit, rebuilt every iteration (K2 at scale)
+  bool use_fit_pgrid = false, use_fit_tgrid = false;
   DevBuf<int32_t> rev_tid;     // [N] reversed ICP: template vertex each target vertex maps back to
   DevBuf<double> rev_cp, rev_wcnt;  // [M][3], [M] folded observations of the reversed direction
   DevBuf<double> rows_ext;     // [4 M + 8]  E-step rows + xPx (all-reduced together)
@@ -1018,6 +1021,21 @@ int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, cons
                     : g->closest.ensure(ctx, M, target->N_total, target->T, model->T);
     if (q < 0) rc = q;
     A(g->fit_normals.alloc((size_t)3 * M));
+    const bool mesh_flavour = cfg->correspondence_method != GINGR_POINTCLOUD_CLOSEST_POINT;
+    if (rc == GINGR_OK && grid_wanted(M)) {
+      // the fit is scanned by the self-intersection test of the mesh flavours (both directions) and, in the
+      // reversed direction, by the vertex / surface searches themselves
+      if (mesh_flavour && model->T > 0) {
+        q = g->fit_tgrid.ensure(ctx, M, model->T, true);
+        if (q < 0) rc = q;
+        g->use_fit_tgrid = true;
+      }
+      if (rev && rc == GINGR_OK) {
+        q = g->fit_pgrid.ensure(ctx, M, M, false);
+        if (q < 0) rc = q;
+        g->use_fit_pgrid = true;
+      }
+    }
     if (rev) {
       A(g->fit_soa.alloc((size_t)3 * M));
       A(g->rev_tid.alloc((size_t)target->N_total));
@@ -1065,6 +1083,7 @@ int32_t gingr_registration_destroy(gingr_registration* g) {
   g->lm_pid.release(); g->lml_pid.release(); g->lml_pts.release(); g->lml_cinv.release(); g->lml_A.release();
   g->lml_rows.release();
   g->estep.release(); g->closest.release(); g->gram.release();
+  g->fit_pgrid.release(); g->fit_tgrid.release();
   g->fit_normals.release(); g->fit_soa.release(); g->rev_tid.release(); g->rev_cp.release(); g->rev_wcnt.release();
   g->rows_ext.release(); g->Mx.release(); g->wrow.release(); g->u.release(); g->inst_a.release(); g->inst_b.release();
   g->newshape.release(); g->fit_local.release(); g->gathered.release(); g->fit.release(); g->vec.release();
@@ -1220,6 +1239,17 @@ static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, u
     }
     tv.n = tg->N_total; tv.aos = tg->aos.p; tv.soa = tg->verts.p; tv.T = tg->T; tv.tri = tg->tri.p;
     tv.normals = tg->normals.p; tv.boundary = tg->boundary.p;
+    tv.pgrid = tg->pgrid; tv.tgrid = tg->tgrid;
+    VertexArray fva;
+    fva.p = g->fit.p;
+    if (g->use_fit_tgrid) {
+      GINGR_TRY(grid_build_triangles_enqueue(ctx, g->fit_tgrid, M, fva, m->T, m->tri.p));
+      fv.tgrid = &g->fit_tgrid;
+    }
+    if (g->use_fit_pgrid) {
+      GINGR_TRY(grid_build_points_enqueue(ctx, g->fit_pgrid, M, fva));
+      fv.pgrid = &g->fit_pgrid;
+    }
     if (!cfg.reverse_correspondence_direction) {
       GINGR_TRY(icp_correspondence_enqueue(ctx, g->closest, fv, tv, cfg.correspondence_method));
       icp_cp = g->closest.cp.p;
@@ -1230,7 +1260,7 @@ static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, u
       fv.soa = g->fit_soa.p;
       GINGR_TRY(icp_correspondence_enqueue(ctx, g->closest, tv, fv, cfg.correspondence_method));
       GINGR_TRY(nn_vertex_enqueue(ctx, g->closest, tg->N_total, g->closest.cp.p, M, g->fit_soa.p, g->closest.d2.p,
-                                  g->rev_tid.p));
+                                  g->rev_tid.p, fv.pgrid, g->closest.qorder));
       GINGR_TRY(reverse_fold_enqueue(ctx, M, tg->N_total, g->rev_tid.p, g->closest.w.p, tg->aos.p, g->rev_cp.p,
                                      g->rev_wcnt.p));
       icp_cp = g->rev_cp.p;

@@ -7,6 +7,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gingr_b200/lib/variants
 EXTRA=""
 [ "$SRC" = "closest.cu" ] && EXTRA="-fmad=false"
+[ "$SRC" = "grid.cu" ] && EXTRA="-fmad=false"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v $EXTRA $FLAGS \
   -c gingr_b200/csrc/$SRC -o gingr_b200/lib/variants/${SRC%.cu}_$NAME.o 2> gingr_b200/lib/variants/${SRC%.cu}_$NAME.log
 OBJS=$(ls gingr_b200/lib/obj/*.o | grep -v "/${SRC%.cu}.o")
