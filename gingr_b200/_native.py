@@ -58,6 +58,21 @@ class GingrConfig(ctypes.Structure):
     ]
 
 
+class GingrMcmcSettings(ctypes.Structure):
+    """POD mirror of gingr_mcmc_settings (include/gingr_cuda.h)."""
+    _fields_ = [
+        ("random_mixture", c_double),
+        ("uncertainty", c_double),
+        ("evaluation_mode", c_int32),
+        ("reserved", c_int32),
+        ("rot_sdev", c_double * 3),
+        ("trans_sdev", c_double * 3),
+        ("shape_sdev", c_double * 3),
+    ]
+
+
+EVAL_MODEL_TO_TARGET, EVAL_TARGET_TO_MODEL, EVAL_SYMMETRIC = 0, 1, 2
+
 dp = POINTER(c_double)
 ip = POINTER(c_int32)
 bp = POINTER(c_uint8)
@@ -97,6 +112,13 @@ SIGNATURES = {
     "gingr_update_chain_sampled": (c_int32, [c_void_p, c_int32, c_uint64]),
     "gingr_update_batch": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_uint64]),
     "gingr_state_download": (c_int32, [c_void_p, POINTER(GingrState), dp, dp]),
+    "gingr_mcmc_configure": (c_int32, [c_void_p, POINTER(GingrMcmcSettings), ip, c_int32, ip, c_int32]),
+    "gingr_evaluate_log_value": (c_int32, [c_void_p, POINTER(GingrState), dp, dp]),
+    "gingr_log_transition_probability": (c_int32, [c_void_p, POINTER(GingrState), dp, POINTER(GingrState), dp, dp]),
+    "gingr_mcmc_chain": (c_int32, [c_void_p, c_int32, c_uint64]),
+    "gingr_mcmc_batch": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_uint64]),
+    "gingr_mcmc_stats": (c_int32, [c_void_p, dp, ip]),
+    "gingr_mcmc_best": (c_int32, [c_void_p, POINTER(GingrState), dp, dp]),
     "gingr_registration_set_profiling": (c_int32, [c_void_p, c_int32]),
     "gingr_registration_get_profile": (c_int32, [c_void_p, dp, ip]),
 }

@@ -22,7 +22,8 @@ from . import _native as nat
 from ._native import (ALGO_CPD, ALGO_ICP, NO_TRANSFORMS, POINTCLOUD_CLOSEST_POINT, RIGID_TRANSFORMS,
                       SIMILARITY_TRANSFORMS, STATUS_CONVERGED, STATUS_MAX_ITERATION,
                       STATUS_MODEL_FLEXIBILITY_ERROR, STATUS_NONE, TRIANGULAR_CLOSEST_POINT,
-                      ALONG_NORMAL_CLOSEST_POINT, GingrConfig, GingrError, GingrState)
+                      ALONG_NORMAL_CLOSEST_POINT, EVAL_MODEL_TO_TARGET, EVAL_SYMMETRIC, EVAL_TARGET_TO_MODEL,
+                      GingrConfig, GingrError, GingrMcmcSettings, GingrState)
 
 
 class Context:
@@ -462,6 +463,64 @@ class GingrAlgorithm:
                                                           nat.as_dp(fit)))
         return GeneralRegistrationState.from_pod(st, alpha, fit)
 
+    # ---- probabilistic registration (GingrAlgorithm.run with ProbabilisticSettings, :115-190) --------------------
+    def configureProbabilistic(self, settings: "ProbabilisticSettings"):
+        """Attach ProbabilisticSettings(IndependentPoints(...), randomMixture) to the registration."""
+        pod = settings.to_pod()
+        mids = None if settings.modelPointIds is None else nat.i32(settings.modelPointIds)
+        tids = None if settings.targetPointIds is None else nat.i32(settings.targetPointIds)
+        self.ctx.check(self.ctx._lib.gingr_mcmc_configure(self.handle, ctypes.byref(pod), nat.as_ip(mids),
+                                                          0 if mids is None else len(mids), nat.as_ip(tids),
+                                                          0 if tids is None else len(tids)))
+        self.probabilisticSettings = settings
+
+    def logValue(self, state: GeneralRegistrationState):
+        """(Prior, Distance) log values of the evaluators (Evaluator.scala:43-60); their sum is the product evaluator."""
+        st, alpha = state.to_pod()
+        out = np.zeros(2)
+        self.ctx.check(self.ctx._lib.gingr_evaluate_log_value(self.handle, ctypes.byref(st), nat.as_dp(alpha), nat.as_dp(out)))
+        return float(out[0]), float(out[1])
+
+    def logTransitionProbability(self, frm: GeneralRegistrationState, to: GeneralRegistrationState) -> float:
+        """GeneratorWrapperStochastic.logTransitionProbability (GeneratorWrapperStochastic.scala:42-63)."""
+        sf, af = frm.to_pod()
+        stt, at = to.to_pod()
+        out = np.zeros(1)
+        self.ctx.check(self.ctx._lib.gingr_log_transition_probability(self.handle, ctypes.byref(sf), nat.as_dp(af),
+                                                                      ctypes.byref(stt), nat.as_dp(at), nat.as_dp(out)))
+        return float(out[0])
+
+    def mcmcChain(self, iters: int, seed: int):
+        """`iters` Metropolis-Hastings steps from the device-resident state, on the device (gingr_mcmc_chain)."""
+        self.ctx.check(self.ctx._lib.gingr_mcmc_chain(self.handle, int(iters), int(seed)))
+
+    def mcmcStats(self):
+        values = np.zeros(16)
+        counts = np.zeros(32, dtype=np.int32)
+        self.ctx.check(self.ctx._lib.gingr_mcmc_stats(self.handle, nat.as_dp(values), nat.as_ip(counts)))
+        return values, counts
+
+    def mcmcBest(self) -> GeneralRegistrationState:
+        st = GingrState()
+        alpha = np.empty(self.model.rank)
+        fit = np.empty((self.model.M, 3))
+        self.ctx.check(self.ctx._lib.gingr_mcmc_best(self.handle, ctypes.byref(st), nat.as_dp(alpha), nat.as_dp(fit)))
+        return GeneralRegistrationState.from_pod(st, alpha, fit)
+
+    def runProbabilistic(self, initialState: GeneralRegistrationState, settings: "ProbabilisticSettings", seed: int = 0,
+                         iterations: Optional[int] = None) -> GeneralRegistrationState:
+        """GingrAlgorithm.run with probabilisticSettings (:115-175): maxIterations - 1 MH steps, returns the best sample
+        (:160-163) with status MaxIteration unless the chain ended in ModelFlexibilityError."""
+        self.configureProbabilistic(settings)
+        st, alpha = initialState.to_pod()
+        fit = np.empty((self.model.M, 3))
+        self.ctx.check(self.ctx._lib.gingr_initialize_state(self.handle, ctypes.byref(st), nat.as_dp(alpha), nat.as_dp(fit)))
+        steps = (self.config.maxIterations - 1) if iterations is None else int(iterations)
+        self.mcmcChain(max(steps, 0), seed)
+        best = self.mcmcBest()
+        if best.status == STATUS_NONE:
+            best = dataclasses.replace(best, status=STATUS_MAX_ITERATION)
+        return best
 
     def setProfiling(self, enable: bool):
         self.ctx.check(self.ctx._lib.gingr_registration_set_profiling(self.handle, int(enable)))
@@ -480,6 +539,40 @@ def update_batch(chains: Sequence[GingrAlgorithm], iters: int, probabilistic: bo
     ctx = chains[0].ctx
     arr = (ctypes.c_void_p * len(chains))(*[c.handle for c in chains])
     ctx.check(ctx._lib.gingr_update_batch(arr, len(chains), int(iters), int(probabilistic), int(seed)))
+
+
+def mcmc_batch(chains: Sequence[GingrAlgorithm], iters: int, seed: int = 0):
+    """`iters` MH steps of every chain (independent chains on one ctx; gingr_mcmc_batch); chain k uses seed + k."""
+    ctx = chains[0].ctx
+    arr = (ctypes.c_void_p * len(chains))(*[c.handle for c in chains])
+    ctx.check(ctx._lib.gingr_mcmc_batch(arr, len(chains), int(iters), int(seed)))
+
+
+@dataclass
+class ProbabilisticSettings:
+    """ProbabilisticSettings(IndependentPoints(state, uncertainty, mode, evaluatedPoints), randomMixture)
+    (GingrAlgorithm.scala:40-50, sampling/Evaluator.scala:43-60) with the proposal widths of Generator.DefaultRandom
+    (sampling/Generator.scala:27-83).  modelPointIds / targetPointIds stand in for the decimation of
+    numberOfPointsForComparison (None: all points)."""
+    uncertainty: float = 1.0
+    mode: int = EVAL_MODEL_TO_TARGET
+    randomMixture: float = 0.5
+    modelPointIds: Optional[np.ndarray] = None
+    targetPointIds: Optional[np.ndarray] = None
+    rotationSdev: Tuple[float, float, float] = (0.01, 0.01, 0.01)      # yaw, pitch, roll
+    translationSdev: Tuple[float, float, float] = (0.1, 0.1, 0.1)
+    shapeSteps: Tuple[float, float, float] = (1.0, 0.1, 0.01)
+
+    def to_pod(self) -> GingrMcmcSettings:
+        p = GingrMcmcSettings()
+        p.random_mixture = float(self.randomMixture)
+        p.uncertainty = float(self.uncertainty)
+        p.evaluation_mode = int(self.mode)
+        for k in range(3):
+            p.rot_sdev[k] = float(self.rotationSdev[k])
+            p.trans_sdev[k] = float(self.translationSdev[k])
+            p.shape_sdev[k] = float(self.shapeSteps[k])
+        return p
 
 
 class CpdRegistration(GingrAlgorithm):

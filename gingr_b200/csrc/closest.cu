@@ -543,6 +543,28 @@ int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const M
   return GINGR_OK;
 }
 
+// Squared distance of nq arbitrary points (AoS) to the surface of a mesh: closestPointOnSurface(pt) of
+// sampling/evaluators/IndependentPointDistanceEvaluator.scala:54-66, with the same kernels (and the same grid when the
+// mesh view carries one) as the TriangularClosestPoint correspondence.  Result in ws.d2 [nq]; ws.cp holds the points.
+int32_t surface_distance_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int nq, const double* d_q, const MeshView& mesh) {
+  cudaStream_t st = ctx->stream;
+  if (mesh.T <= 0 || !mesh.tri || !mesh.soa || !mesh.aos)
+    return gingr_fail(ctx, GINGR_ERR_ARG, "surface distance needs a triangle mesh (vertices AoS + SoA, triangles)");
+  if (mesh.tgrid && mesh.tgrid->built) {
+    GINGR_TRY(grid_surface_enqueue(ctx, *mesh.tgrid, nq, d_q, mesh.aos, mesh.tri, ws.d2.p, nullptr, ws.cp.p, nullptr));
+    return GINGR_OK;
+  }
+  const int s_surf = std::min(ws.s_surf, std::max(1, ceil_div(mesh.T, TT)));
+  surface_kernel<<<dim3(ceil_div(nq, QT), s_surf), QT, 0, st>>>(nq, d_q, mesh.n, mesh.soa, mesh.T, mesh.tri, ws.part_d2.p,
+                                                                ws.part_idx.p, ws.part_cp.p);
+  GINGR_LAUNCHED(ctx);
+  surface_reduce_kernel<<<ceil_div(nq, 128), 128, 0, st>>>(nq, s_surf, ws.part_d2.p, ws.part_idx.p, ws.part_cp.p, ws.d2.p,
+                                                           nullptr, ws.cp.p);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
 // closestPointCorrespondenceReversal (:34-45), second half: the observations (templateId_j, target point x_j, w_j)
 // of all target vertices j, folded per template vertex i in ascending j (deterministic, no atomics):
 //   wcnt_i = #{j : tid_j = i, w_j = 1},  cp_i = mean of those x_j   (wcnt_i / sigma2 and the mean reproduce the

@@ -53,6 +53,7 @@ int32_t nn_vertex_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, const dou
                           const SpatialGrid* order = nullptr);
 int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const MeshView& tpl, const MeshView& tgt,
                                    int method);
+int32_t surface_distance_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int nq, const double* d_q, const MeshView& mesh);
 int32_t reverse_fold_enqueue(gingr_ctx* ctx, int M, int N, const int32_t* d_tid, const uint8_t* d_w,
                              const double* d_target_aos, double* d_cp, double* d_wcnt);
 

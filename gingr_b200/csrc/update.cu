@@ -320,11 +320,11 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__global__ void add_normal_kernel(int r, uint64_t seed, const int* __restrict__ is, double* __restrict__ y) {
+__global__ void add_normal_kernel(int r, uint64_t seed, const int* __restrict__ counter, double* __restrict__ y) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;  // pair index: entries 2p, 2p + 1
   if (2 * p >= r) return;
   uint32_t x[4];
-  philox4x32_10((uint32_t)p, (uint32_t)is[IS_ITER], 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+  philox4x32_10((uint32_t)p, (uint32_t)counter[0], 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
   const double u1 = ((double)(x[0] >> 5) * 67108864.0 + (double)(x[1] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
   const double u2 = ((double)(x[2] >> 5) * 67108864.0 + (double)(x[3] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
   const double rad = sqrt(-2.0 * log(u1));
@@ -588,6 +588,10 @@ struct gingr_registration {
   DevBuf<double> rev_cp, rev_wcnt;  // [M][3], [M] folded observations of the reversed direction
   DevBuf<double> rows_ext;     // [4 M + 8]  E-step rows + xPx (all-reduced together)
   DevBuf<double> Mx;           // [(r + 8)][rp]  posterior matrix + rhs row
+  DevBuf<double> Mx_raw;       // [(r + 1)][rp]  copy of Mx and rhs before the factorisation (MCMC only, mcmc.cuh)
+  bool keep_raw = false;
+  const int* sample_counter = nullptr;  // device counter keyed into the posterior-sample stream (null: the iteration)
+  struct McmcState* mcmc = nullptr;  // Metropolis-Hastings chain state (mcmc.cuh), created by gingr_mcmc_configure
   DevBuf<double> wrow, u, inst_a, inst_b, newshape, fit_local, gathered, fit;
   DevBuf<double> vec;          // 8 * rp scratch vectors
   DevBuf<double> gt_part, sums_part, pro_part, pro_sums;
@@ -615,6 +619,7 @@ struct gingr_registration {
 
 static int32_t model_build_constants(gingr_ctx* ctx, gingr_model* m);
 static void drop_graph(gingr_registration* g);
+static void mcmc_release(gingr_registration* g);  // mcmc.cuh
 
 extern "C" {
 
@@ -1080,6 +1085,8 @@ int32_t gingr_registration_destroy(gingr_registration* g) {
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
   drop_graph(g);
+  mcmc_release(g);
+  g->Mx_raw.release();
   g->lm_pid.release(); g->lml_pid.release(); g->lml_pts.release(); g->lml_cinv.release(); g->lml_A.release();
   g->lml_rows.release();
   g->estep.release(); g->closest.release(); g->gram.release();
@@ -1191,7 +1198,12 @@ static int32_t evaluate_fit(gingr_registration* g, int off_s, int off_t, int off
   return gather_fit(ctx, m, g->fit_local.p, g->gathered.p, g->fit.p);
 }
 
-static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, uint64_t seed = 0) {
+// The iteration in two phases, so that the Metropolis-Hastings chain (mcmc.cuh) can keep the posterior of a state and
+// reuse it (scalismo's Memoize of cashedPosterior, GingrAlgorithm.scala:68):
+//   posterior phase  correspondence -> observations -> rhs, Gram -> Cholesky with the forward substitution; leaves
+//                    L and z = L^-1 rhs in g->Mx (and, if g->keep_raw, the unfactorised Mx in g->Mx_raw)
+//   update phase     (sample |) back solve -> alpha* -> Procrustes -> alpha_new -> commit -> fit
+static int32_t enqueue_posterior_phase(gingr_registration* g) {
   gingr_ctx* ctx = g->ctx;
   const gingr_model* m = g->model;
   const gingr_target* tg = g->target;
@@ -1295,10 +1307,26 @@ static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, u
   GINGR_TRY(gram_finish_enqueue(ctx, g->gram, g->gram.d_partial.p, m->sqrt_lambda.p, ctx->rank == 0 ? 1.0 : 0.0,
                                 use_lm ? g->Ll : 0, g->lml_rows.p, g->lml_A.p, rp, g->Mx.p));
   GINGR_TRY(comm_allreduce_sum(ctx, g->Mx.p, (size_t)(r + 1) * rp));
+  if (g->keep_raw)
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->Mx_raw.p, g->Mx.p, sizeof(double) * (size_t)(r + 1) * rp, cudaMemcpyDeviceToDevice, st));
   g->rec(8);
   GINGR_TRY(cholesky_enqueue(ctx, r, r + 1, g->Mx.p, rp, g->is.p + IS_INFO));
+  return GINGR_OK;
+}
+
+static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, uint64_t seed) {
+  gingr_ctx* ctx = g->ctx;
+  const gingr_model* m = g->model;
+  const gingr_config& cfg = g->cfg;
+  const int M = m->M, r = m->r, rp = m->rp, Ml = m->Ml, m0 = m->m0;
+  cudaStream_t st = ctx->stream;
+  double* vec = g->vec.p;
+  double* rhs = g->Mx.p + (size_t)r * rp;
+  (void)cfg;
   if (probabilistic) {  // posterior.sample() instead of posterior.mean (:211)
-    add_normal_kernel<<<ceil_div(ceil_div(r, 2), 128), 128, 0, st>>>(r, seed, g->is.p, rhs);
+    // counter of the Philox stream: the state's iteration (gingr_update) or the chain's MH step (mcmc.cuh)
+    add_normal_kernel<<<ceil_div(ceil_div(r, 2), 128), 128, 0, st>>>(r, seed, g->sample_counter ? g->sample_counter : g->is.p + IS_ITER,
+                                                                     rhs);
     GINGR_LAUNCHED(ctx);
   }
   GINGR_TRY(chol_backsolve_enqueue(ctx, r, g->Mx.p, rp, rhs, vec, g->flags.p));
@@ -1344,6 +1372,11 @@ static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, u
   if (g->profiling && g->prof_iters < gingr_registration::EV_MAX_ITERS) g->prof_iters++;
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
+}
+
+static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, uint64_t seed = 0) {
+  GINGR_TRY(enqueue_posterior_phase(g));
+  return enqueue_update_phase(g, probabilistic, seed);
 }
 
 static bool graphs_enabled(const gingr_ctx* ctx) {
@@ -1621,3 +1654,5 @@ int32_t gingr_state_download(gingr_registration* g, gingr_state* state_out, doub
 }
 
 }  // extern "C"
+
+#include "mcmc.cuh"

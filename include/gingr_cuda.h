@@ -233,6 +233,50 @@ GINGR_API int32_t gingr_update_batch(gingr_registration** regs, int32_t n, int32
 GINGR_API int32_t gingr_state_download(gingr_registration* reg, gingr_state* state_out, double* alpha_out,
                                        double* fit_out);
 
+/* ---- probabilistic registration: Metropolis-Hastings with the informed GiNGR proposal ---- */
+/* sampling/evaluators/IndependentPointDistanceEvaluator.scala:26-32 EvaluationMode */
+#define GINGR_EVAL_MODEL_TO_TARGET 0
+#define GINGR_EVAL_TARGET_TO_MODEL 1
+#define GINGR_EVAL_SYMMETRIC 2
+/* POD mirror of ProbabilisticSettings(IndependentPoints(state, uncertainty, mode, evaluatedPoints), randomMixture)
+ * (GingrAlgorithm.scala:40-50, sampling/Evaluator.scala:43-60) and of the defaults of Generator.DefaultRandom
+ * (sampling/Generator.scala:27-83). */
+typedef struct gingr_mcmc_settings {
+  double random_mixture;   /* weight of the random generators in MixtureProposal(rm *: random + (1 - rm) *: informed) */
+  double uncertainty;      /* sdev of the Gaussian point-distance likelihood */
+  int32_t evaluation_mode; /* GINGR_EVAL_* */
+  int32_t reserved;
+  double rot_sdev[3];      /* yaw (psi), pitch (theta), roll (phi); Generator.defaultRotation = 0.01 */
+  double trans_sdev[3];    /* x, y, z; Generator.defaultTranslation = 0.1 */
+  double shape_sdev[3];    /* RandomShape steps; default 1.0, 0.1, 0.01 */
+} gingr_mcmc_settings;
+/* Attach the probabilistic settings to a registration.  model_ids / target_ids: the comparison points of the distance
+ * evaluator (numberOfPointsForComparison; the reference decimates, the host passes the ids it wants), n = 0: all. */
+GINGR_API int32_t gingr_mcmc_configure(gingr_registration* reg, const gingr_mcmc_settings* settings,
+                                       const int32_t* model_ids, int32_t n_model_ids, const int32_t* target_ids,
+                                       int32_t n_target_ids);
+/* EvaluatorWrapper.logValue of a state (sampling/evaluators/EvaluatorWrapper.scala:23-33): out[0] = ModelEvaluator
+ * (ModelEvaluator.scala:25-32), out[1] = IndependentPointDistanceEvaluator (:54-78); the product evaluator is their sum. */
+GINGR_API int32_t gingr_evaluate_log_value(gingr_registration* reg, const gingr_state* state, const double* alpha,
+                                           double* out /*[2]*/);
+/* GeneratorWrapperStochastic.logTransitionProbability(from, to) (GeneratorWrapperStochastic.scala:42-63): log density of
+ * the informed proposal; -inf where the reference returns Double.NegativeInfinity. */
+GINGR_API int32_t gingr_log_transition_probability(gingr_registration* reg, const gingr_state* from,
+                                                   const double* from_alpha, const gingr_state* to,
+                                                   const double* to_alpha, double* out /*[1]*/);
+/* `iters` steps of scalismo's MetropolisHastings with generatorCombined (GingrAlgorithm.scala:177-190) and
+ * the evaluators above, starting at the device-resident state, entirely on the device: choice of the generator, informed
+ * or random proposal, posterior of the proposal (kept when accepted), both transition densities of the mixture, accept /
+ * reject, best-sample tracking.  Random numbers: Philox4x32-10, key = seed, counter = (index, MH step, purpose, 0). */
+GINGR_API int32_t gingr_mcmc_chain(gingr_registration* reg, int32_t iters, uint64_t seed);
+/* Independent chains batched on one GPU (BASELINE config 5); chain k uses seed + k. */
+GINGR_API int32_t gingr_mcmc_batch(gingr_registration** regs, int32_t n, int32_t iters, uint64_t seed);
+/* values[16] / counts[32]: see mcmc.cuh (log values of current / proposal / best, transition densities, accept counts per
+ * generator). */
+GINGR_API int32_t gingr_mcmc_stats(gingr_registration* reg, double* values /*[16]*/, int32_t* counts /*[32]*/);
+/* BestAndCurrentSampleLogger.currentBestSample (GingrAlgorithm.scala:160-163). */
+GINGR_API int32_t gingr_mcmc_best(gingr_registration* reg, gingr_state* state_out, double* alpha_out, double* fit_out);
+
 /* ---- measurement hooks (new; used by bench.py for the roofline numbers) ------------------------ */
 /* Per-phase device timing with CUDA events recorded on the ctx stream around the kernels of gingr_update /
  * gingr_update_chain.  ms[8]: 0 = E-step sweep A kernel, 1 = E-step sweep B kernel, 2 = Gram (DMMA) kernel,

@@ -620,8 +620,9 @@ def standard_normals(r: int, seed: int, iteration: int):
 RETRY_COUNTER_INIT = 10  # GingrAlgorithm.scala:69-70
 
 
-def update(algo, st: State, probabilistic: bool = False, seed: int = 0) -> State:
-    """GingrAlgorithm.update, literal.  api/GingrAlgorithm.scala:192-254"""
+def update(algo, st: State, probabilistic: bool = False, seed: int = 0, counter: Optional[int] = None) -> State:
+    """GingrAlgorithm.update, literal.  api/GingrAlgorithm.scala:192-254.  `counter`: second word of the Philox counter
+    of the posterior-sample stream (default: the state's iteration; the MH chain passes its step index)."""
     try:
         with np.errstate(all="ignore"):
             posed, c_post, Minv = compute_posterior_coefficients(algo, st)
@@ -640,7 +641,7 @@ def update(algo, st: State, probabilistic: bool = False, seed: int = 0) -> State
         # D^-1 U_s sqrt(s) z from svd(D Minv D); the same law is c + L^-T z with Mx = L L^T, which is the form
         # (and the z stream) libgingr_cuda documents -- identical distribution, different individual draws.
         L = np.linalg.cholesky(posed._last_Mx)
-        z = standard_normals(st.model.rank, seed, st.iteration)
+        z = standard_normals(st.model.rank, seed, st.iteration if counter is None else counter)
         c_post = c_post + np.linalg.solve(L.T, z)
     shapeproposal = posed.instance(c_post)                                # posterior.mean | sample  :211
     transformed_init = posed                                              # :212 (same transform)
@@ -671,10 +672,10 @@ def update(algo, st: State, probabilistic: bool = False, seed: int = 0) -> State
     return dataclasses.replace(new_state, sigma2=float(sigma2))
 
 
-def propose(algo, st: State, probabilistic: bool = False, seed: int = 0) -> State:
+def propose(algo, st: State, probabilistic: bool = False, seed: int = 0, counter: Optional[int] = None) -> State:
     """GingrGeneratorWrapper.propose: update, refresh fit, iteration += 1.
     api/sampling/generators/GingrGeneratorWrapper.scala:28-39"""
-    ns = update(algo, st, probabilistic, seed)
+    ns = update(algo, st, probabilistic, seed, counter)
     fit = model_instance_shape_pose_scale(ns.model, ns.params)
     return dataclasses.replace(ns, fit=fit, iteration=ns.iteration + 1)
 
@@ -702,3 +703,211 @@ def run(algo, initial: State, callback=None) -> State:
     if st.status == STATUS_NONE:
         st = dataclasses.replace(st, status=final_status)
     return st
+
+
+# ---------------------------------------------------------------------------------------------
+# Probabilistic registration: evaluators, proposal mixture, Metropolis-Hastings (api/sampling/*,
+# GingrAlgorithm.scala:115-190).  Literal restatement; scalismo / Breeze behaviour tagged [scalismo-recalled].
+# ---------------------------------------------------------------------------------------------
+EVAL_MODEL_TO_TARGET, EVAL_TARGET_TO_MODEL, EVAL_SYMMETRIC = 0, 1, 2   # IndependentPointDistanceEvaluator.scala:26-32
+LEAF_NAMES = ("informed", "rot_yaw", "rot_pitch", "rot_roll", "trans_x", "trans_y", "trans_z", "shape_0", "shape_1", "shape_2")
+
+
+@dataclass
+class McmcSettings:
+    """ProbabilisticSettings(IndependentPoints(state, uncertainty, mode, evaluatedPoints), randomMixture) and the
+    widths of Generator.DefaultRandom.  GingrAlgorithm.scala:40-50, sampling/Evaluator.scala:43-60, Generator.scala:27-83"""
+    uncertainty: float = 1.0
+    mode: int = EVAL_MODEL_TO_TARGET
+    random_mixture: float = 0.5
+    model_ids: Optional[np.ndarray] = None     # stand-in for decimate(numberOfPointsForComparison)
+    target_ids: Optional[np.ndarray] = None
+    rot_sdev: Tuple[float, float, float] = (0.01, 0.01, 0.01)     # yaw (psi), pitch (theta), roll (phi)
+    trans_sdev: Tuple[float, float, float] = (0.1, 0.1, 0.1)
+    shape_steps: Tuple[float, float, float] = (1.0, 0.1, 0.01)
+
+
+def gaussian_logpdf(x, mu, sd):
+    """Breeze Gaussian(mu, sd).logPdf / scalismo GaussianEvaluator.logDensity  [scalismo-recalled]"""
+    return -((x - mu) ** 2) / (2.0 * sd * sd) - np.log(sd * np.sqrt(2.0 * np.pi))
+
+
+def model_evaluator(alpha):
+    """ModelEvaluator.logValue: MultivariateNormalDistribution(0, I_r).logpdf(alpha).  ModelEvaluator.scala:25-32"""
+    a = np.asarray(alpha, dtype=float)
+    return float(-0.5 * (a @ a) - 0.5 * a.shape[0] * np.log(2.0 * np.pi))
+
+
+def distance_evaluator(settings: McmcSettings, st: State):
+    """IndependentPointDistanceEvaluator.computeLogValue.  IndependentPointDistanceEvaluator.scala:54-78"""
+    def m2t():
+        pts = st.fit if settings.model_ids is None else st.fit[np.asarray(settings.model_ids)]
+        _, d2, _ = closest_on_surface(pts, st.target, st.target_tri)
+        return float(np.sum(gaussian_logpdf(np.sqrt(d2), 0.0, settings.uncertainty)))
+
+    def t2m():
+        pts = st.target if settings.target_ids is None else st.target[np.asarray(settings.target_ids)]
+        _, d2, _ = closest_on_surface(pts, st.fit, st.model.tri)
+        return float(np.sum(gaussian_logpdf(np.sqrt(d2), 0.0, settings.uncertainty)))
+    if settings.mode == EVAL_MODEL_TO_TARGET:
+        return m2t()
+    if settings.mode == EVAL_TARGET_TO_MODEL:
+        return t2m()
+    return 0.5 * m2t() + 0.5 * t2m()
+
+
+def log_value(settings: McmcSettings, st: State):
+    """EvaluatorWrapper(probabilistic = true): ProductEvaluator(Prior, Distance) -> (prior, distance); the log value
+    is their sum.  sampling/Evaluator.scala:25-28, :49-59"""
+    return model_evaluator(st.params.shape), distance_evaluator(settings, st)
+
+
+def posterior_model(algo, st: State) -> Gpmm:
+    """cashedPosterior(state): model.transform(rigid).posterior(obs) as a full PointDistributionModel [A3]:
+    mean' + Phi' (sqrt(lambda) c), basis Phi' U_s, variance s with svd(D Minv D).  GingrAlgorithm.scala:281-302"""
+    posed, c, Minv = compute_posterior_coefficients(algo, st)
+    if not np.all(np.isfinite(c)):
+        raise FloatingPointError("posterior not finite")
+    D = np.sqrt(st.model.variance)
+    Sigma = D[:, None] * Minv * D[None, :]
+    U, s, _ = np.linalg.svd(Sigma)
+    return Gpmm(posed.ref, posed.mean + posed.basis @ (D * c), posed.basis @ U, s, posed.tri)
+
+
+def log_transition_informed(algo, frm: State, to: State) -> float:
+    """GeneratorWrapperStochastic.logTransitionProbability.  GeneratorWrapperStochastic.scala:42-63"""
+    try:
+        with np.errstate(all="ignore"):
+            posterior = posterior_model(algo, frm)
+    except (FloatingPointError, np.linalg.LinAlgError, ValueError):
+        return -np.inf                                                    # :44-45
+    if frm.step_length != 1.0:                                            # :47-51
+        comp = frm.params.shape + (to.params.shape - frm.params.shape) / frm.step_length
+        to_mesh = frm.model.instance(comp)
+    else:
+        to_mesh = frm.fit
+    try:
+        with np.errstate(all="ignore"):
+            projected = posterior.coefficients(to_mesh)                   # :53
+        v = float(-0.5 * (projected @ projected) - 0.5 * projected.shape[0] * np.log(2.0 * np.pi))   # gp.logpdf [A1]
+        return v if np.isfinite(v) else -np.inf
+    except (FloatingPointError, np.linalg.LinAlgError, ValueError):
+        return -np.inf                                                    # :57-60
+
+
+def leaf_weights(rho: float):
+    """Flattened weights of MixtureProposal(rho *: DefaultRandom + (1 - rho) *: informed).  Generator.scala:31-83,
+    GingrAlgorithm.scala:184-187 (scalismo normalises the weights of every mixture)."""
+    w = np.zeros(10)
+    w[0] = 1.0 - rho
+    w[1:4] = rho * 0.5 * 0.5 / 3.0
+    w[4:7] = rho * 0.5 * 0.5 / 3.0
+    w[7:10] = rho * 0.5 / 3.0
+    return w
+
+
+_EULER_SLOT = {1: 2, 2: 1, 3: 0}   # YawAxis -> psi, PitchAxis -> theta, RollAxis -> phi (RandomPoseUpdateProposal.scala:40-44)
+
+
+def mixture_log_transition(settings: McmcSettings, a: State, b: State, t_informed: float) -> float:
+    """MixtureProposal.logTransitionProbability(a, b) = log sum_k w_k exp(t_k) [scalismo-recalled A5] with the random
+    leaves of RandomPoseUpdateProposal.scala:47-63, :96-107 and RandomShapeUpdateProposal.scala:42-50."""
+    w = leaf_weights(settings.random_mixture)
+    pa, pb = a.params, b.params
+    scale_eq = pa.scale == pb.scale
+    trans_eq = bool(np.all(np.asarray(pa.translation) == np.asarray(pb.translation)))
+    rot_eq = tuple(pa.euler) == tuple(pb.euler)
+    shape_eq = bool(np.all(pa.shape == pb.shape))
+    with np.errstate(all="ignore"):
+        s = w[0] * np.exp(t_informed)
+        for k in range(3):
+            if scale_eq and trans_eq and shape_eq:
+                slot = _EULER_SLOT[1 + k]
+                s += w[1 + k] * np.exp(gaussian_logpdf(pb.euler[slot] - pa.euler[slot], 0.0, settings.rot_sdev[k]))
+            if scale_eq and rot_eq and shape_eq:
+                s += w[4 + k] * np.exp(gaussian_logpdf(pb.translation[k] - pa.translation[k], 0.0, settings.trans_sdev[k]))
+            if scale_eq and rot_eq and trans_eq:
+                sd = settings.shape_steps[k]
+                ss = float(np.sum((pb.shape - pa.shape) ** 2))
+                s += w[7 + k] * np.exp(-ss / (2.0 * sd * sd) - len(pa.shape) * np.log(sd * np.sqrt(2.0 * np.pi)))
+        return float(np.log(s))
+
+
+def _u53(a, b):
+    return ((int(a) >> 5) * 67108864.0 + (int(b) >> 6) + 0.5) / 9007199254740992.0
+
+
+def mcmc_uniforms(seed: int, step: int):
+    """(u_choice, u_accept) of MH step `step`: Philox counter (0, step, 1, 0)  (gingr_b200/csrc/mcmc.cuh)."""
+    x = philox4x32_10(np.array([0]), np.array([step]), np.array([1]), np.array([0]), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    return _u53(x[0][0], x[1][0]), _u53(x[2][0], x[3][0])
+
+
+def mcmc_normals(n: int, seed: int, step: int):
+    """Perturbation normals of the random proposals: Philox counter (pair, step, 2, 0), Box-Muller."""
+    npair = (n + 1) // 2
+    p = np.arange(npair, dtype=np.uint64)
+    zero = np.zeros(npair, dtype=np.uint64)
+    x0, x1, x2, x3 = philox4x32_10(p, zero + np.uint64(step), zero + np.uint64(2), zero, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u1 = ((x0 >> np.uint64(5)).astype(np.float64) * 67108864.0 + (x1 >> np.uint64(6)).astype(np.float64) + 0.5) / 9007199254740992.0
+    u2 = ((x2 >> np.uint64(5)).astype(np.float64) * 67108864.0 + (x3 >> np.uint64(6)).astype(np.float64) + 0.5) / 9007199254740992.0
+    rad = np.sqrt(-2.0 * np.log(u1))
+    ang = 6.283185307179586476925 * u2
+    z = np.empty(2 * npair)
+    z[0::2] = rad * np.cos(ang)
+    z[1::2] = rad * np.sin(ang)
+    return z[:n]
+
+
+def random_proposal(settings: McmcSettings, cur: State, leaf: int, seed: int, step: int) -> State:
+    """gingrPropose of the random generators + GingrGeneratorWrapper.propose (fit refresh, iteration + 1).
+    RandomPoseUpdateProposal.scala:37-47, :80-94; RandomShapeUpdateProposal.scala:32-40; GingrGeneratorWrapper.scala:28-39"""
+    p = cur.params
+    euler, trans, shape = list(p.euler), np.array(p.translation, dtype=float), p.shape.copy()
+    if 1 <= leaf <= 3:
+        euler[_EULER_SLOT[leaf]] += settings.rot_sdev[leaf - 1] * mcmc_normals(1, seed, step)[0]
+    elif 4 <= leaf <= 6:
+        trans[leaf - 4] += settings.trans_sdev[leaf - 4] * mcmc_normals(1, seed, step)[0]
+    else:
+        shape = shape + settings.shape_steps[leaf - 7] * mcmc_normals(len(shape), seed, step)
+    params = Params(p.scale, trans, tuple(euler), shape)
+    ns = dataclasses.replace(cur, params=params)
+    return dataclasses.replace(ns, fit=model_instance_shape_pose_scale(ns.model, params), iteration=cur.iteration + 1)
+
+
+def mcmc_step(algo, settings: McmcSettings, cur: State, lp_cur, step: int, seed: int):
+    """One step of scalismo MetropolisHastings [A5] with generatorCombined (GingrAlgorithm.scala:177-190).
+    Returns (state, (prior, distance) of it, info dict)."""
+    u_choice, u_accept = mcmc_uniforms(seed, step)
+    w = leaf_weights(settings.random_mixture)
+    leaf, acc = len(w) - 1, 0.0
+    for k in range(len(w)):
+        acc += w[k]
+        if u_choice < acc:
+            leaf = k
+            break
+    if w[leaf] <= 0.0:
+        leaf = 0
+    if leaf == 0:
+        prop = propose(algo, cur, True, seed, counter=step)               # GeneratorWrapperStochastic.gingrPropose
+    else:
+        prop = random_proposal(settings, cur, leaf, seed, step)
+    t_fw = log_transition_informed(algo, cur, prop)
+    t_bw = log_transition_informed(algo, prop, cur)
+    fw = mixture_log_transition(settings, cur, prop, t_fw)
+    bw = mixture_log_transition(settings, prop, cur, t_bw)
+    lp_prop = log_value(settings, prop)
+    info = {"leaf": leaf, "t_fw": t_fw, "t_bw": t_bw, "fw": fw, "bw": bw, "lp_prop": lp_prop, "u_accept": u_accept}
+    if cur.status == STATUS_MODEL_FLEXIBILITY_ERROR:
+        info["accept"] = False
+        return cur, lp_cur, info
+    if np.isnan(fw) or np.isnan(bw):
+        info["accept"] = False                                            # scalismo throws; the chain keeps its state here
+        return cur, lp_cur, info
+    ratio = -np.inf if (np.isneginf(fw) or np.isneginf(bw)) else fw - bw
+    with np.errstate(all="ignore"):
+        a = (lp_prop[0] + lp_prop[1]) - (lp_cur[0] + lp_cur[1]) - ratio
+        accept = bool(a > 0.0 or u_accept < np.exp(a))
+    info["a"] = a
+    info["accept"] = accept
+    return (prop, lp_prop, info) if accept else (cur, lp_cur, info)
