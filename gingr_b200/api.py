@@ -125,6 +125,34 @@ class Model:
         self.handle = h
         self.triangles = tri
 
+    def newReference(self, ref_points, triangles=None) -> "Model":
+        """model.newReference(newRef, NearestNeighborInterpolator()) (SimpleRegistrator.scala:90-92) on the device: the
+        new model's rows are gathered from the resident basis at the nearest old reference points."""
+        ref = nat.f64(ref_points).reshape(-1, 3)
+        tri = None if triangles is None else nat.i32(triangles).reshape(-1, 3)
+        h = ctypes.c_void_p()
+        self.ctx.check(self.ctx._lib.gingr_model_new_reference(self.ctx.handle, self.handle, ref.shape[0], nat.as_dp(ref),
+                                                               nat.as_ip(tri), 0 if tri is None else tri.shape[0],
+                                                               ctypes.byref(h)))
+        m = Model.__new__(Model)
+        m.ctx, m.M, m.rank, m.T, m.handle, m.triangles = self.ctx, ref.shape[0], self.rank, 0 if tri is None else tri.shape[0], h, tri
+        return m
+
+    def instance(self, parameters: "ModelFittingParameters") -> np.ndarray:
+        """ModelFittingParameters.modelInstanceShapePoseScale(model, parameters) (ModelFittingParameters.scala:130-143)."""
+        st = GingrState()
+        st.scale = float(parameters.scale)
+        for d in range(3):
+            st.translation[d] = float(parameters.translation[d])
+            st.euler[d] = float(parameters.euler[d])
+            st.center[d] = 0.0
+        st.rank = self.rank
+        alpha = nat.f64(parameters.shape)
+        fit = np.empty((self.M, 3))
+        self.ctx.check(self.ctx._lib.gingr_model_instance(self.ctx.handle, self.handle, ctypes.byref(st), nat.as_dp(alpha),
+                                                          nat.as_dp(fit)))
+        return fit
+
     def close(self):
         if getattr(self, "handle", None):
             self.ctx._lib.gingr_model_destroy(self.handle)
@@ -573,6 +601,55 @@ class ProbabilisticSettings:
             p.trans_sdev[k] = float(self.translationSdev[k])
             p.shape_sdev[k] = float(self.shapeSteps[k])
         return p
+
+
+class SimpleRegistrator:
+    """Host mirror of api/registration/SimpleRegistrator.scala:34-158 over device handles: run / runDecimated with the
+    hand-over of (pose, scale, shape) between resolution levels (examples/DemoMultiResolution.scala:39-47).  The
+    decimated reference and target meshes are the caller's (scalismo's quadric `decimate` is not part of the hot path);
+    the re-referenced model is built on the device from the resident basis (Model.newReference)."""
+
+    def __init__(self, ctx: Context, algorithm, config, model: Model, target: Target, evaluatorUncertainty: float = 1.0,
+                 evaluationMode: int = EVAL_MODEL_TO_TARGET):
+        self.ctx, self.algorithm, self.config, self.model, self.target = ctx, algorithm, config, model, target
+        self.evaluatorUncertainty, self.evaluationMode = evaluatorUncertainty, evaluationMode
+
+    def _run(self, model: Model, target: Target, generalState, globalTransformation, probabilistic, randomMixture, callback,
+             seed):
+        reg = self.algorithm(self.ctx, model, target, self.config)
+        try:
+            if generalState is not None:
+                # combineStates (:76-82): clearIteration, status None, then initializeState recomputes sigma2 from the config
+                g = dataclasses.replace(generalState, iteration=0, status=STATUS_NONE, globalTransformation=globalTransformation)
+                st = reg.initializeState(general=g)
+            else:
+                st = reg.initializeState(globalTransformation=globalTransformation)
+            if probabilistic:
+                settings = ProbabilisticSettings(uncertainty=self.evaluatorUncertainty, mode=self.evaluationMode,
+                                                 randomMixture=randomMixture)
+                final = reg.runProbabilistic(st, settings, seed=seed)
+            else:
+                final = reg.run(st, callback)
+        finally:
+            reg.close()
+        # "Final registration with full resolution meshes" (:152-157): the fit is re-evaluated on the full model
+        return dataclasses.replace(final, fit=self.model.instance(final.modelParameters))
+
+    def run(self, generalState=None, globalTransformation: int = RIGID_TRANSFORMS, probabilistic: bool = False,
+            randomMixture: float = 0.5, callback=None, seed: int = 0) -> GeneralRegistrationState:
+        return self._run(self.model, self.target, generalState, globalTransformation, probabilistic, randomMixture, callback, seed)
+
+    def runDecimated(self, decimatedReference, decimatedTarget, generalState=None,
+                     globalTransformation: int = RIGID_TRANSFORMS, probabilistic: bool = False, randomMixture: float = 0.5,
+                     callback=None, seed: int = 0) -> GeneralRegistrationState:
+        """decimatedReference / decimatedTarget: (points, triangles) of the decimated meshes (:84-106)."""
+        dm = self.model.newReference(*decimatedReference)
+        dt = Target(self.ctx, *decimatedTarget)
+        try:
+            return self._run(dm, dt, generalState, globalTransformation, probabilistic, randomMixture, callback, seed)
+        finally:
+            dm.close()
+            dt.close()
 
 
 class CpdRegistration(GingrAlgorithm):

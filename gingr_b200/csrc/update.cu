@@ -618,8 +618,43 @@ struct gingr_registration {
 };
 
 static int32_t model_build_constants(gingr_ctx* ctx, gingr_model* m);
+static int32_t model_upload_topology(gingr_ctx* ctx, gingr_model* m, const int32_t* tri, int T);
 static void drop_graph(gingr_registration* g);
 static void mcmc_release(gingr_registration* g);  // mcmc.cuh
+
+// reference triangles, vertex -> triangle adjacency and boundary flags of a model (ICP mesh flavours)
+static int32_t model_upload_topology(gingr_ctx* ctx, gingr_model* m, const int32_t* tri, int T) {
+  const int M = m->M;
+  cudaStream_t st = ctx->stream;
+  m->T = T;
+  if (T <= 0) return GINGR_OK;
+  for (int k = 0; k < 3 * T; ++k)
+    if (tri[k] < 0 || tri[k] >= M) return gingr_fail(ctx, GINGR_ERR_ARG, "model triangle index out of range");
+  std::vector<int32_t> off, adj;
+  std::vector<uint8_t> bflags;
+  build_vertex_adjacency(M, T, tri, &off, &adj);
+  compute_boundary_flags(M, T, tri, &bflags);
+  GINGR_CUDA_TRY(ctx, m->boundary.alloc((size_t)M));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->boundary.p, bflags.data(), (size_t)M, cudaMemcpyHostToDevice, st));
+  GINGR_CUDA_TRY(ctx, m->tri.alloc((size_t)3 * T));
+  GINGR_CUDA_TRY(ctx, m->adj_off.alloc(off.size()));
+  GINGR_CUDA_TRY(ctx, m->adj.alloc(adj.size()));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->tri.p, tri, sizeof(int32_t) * 3 * (size_t)T, cudaMemcpyHostToDevice, st));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->adj_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->adj.p, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice, st));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));   // off / adj / bflags are stack vectors
+  return GINGR_OK;
+}
+
+// new basis rows / mean of point i = those of old point idx[i]  (NearestNeighborInterpolator)
+__global__ void rereference_rows_kernel(int M2, int rp, const int32_t* __restrict__ idx, const double* __restrict__ phi,
+                                        const double* __restrict__ mean, double* __restrict__ phi2, double* __restrict__ mean2) {
+  const int row = blockIdx.x;          // 3 * i + d of the new model
+  const int i = row / 3, d = row % 3;
+  const size_t src = (size_t)3 * idx[i] + d;
+  for (int a = threadIdx.x; a < rp; a += blockDim.x) phi2[(size_t)row * rp + a] = phi[src * rp + a];
+  if (threadIdx.x == 0) mean2[row] = mean[src];
+}
 
 extern "C" {
 
@@ -665,26 +700,9 @@ int32_t gingr_model_upload(gingr_ctx* ctx, int32_t M, int32_t r, const double* r
     GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     tmp.release();
   }
-  m->T = T;
-  if (T > 0) {
-    for (int k = 0; k < 3 * T; ++k)
-      if (tri[k] < 0 || tri[k] >= M) {
-        delete m;
-        return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_model_upload: triangle index out of range");
-      }
-    std::vector<int32_t> off, adj;
-    std::vector<uint8_t> bflags;
-    build_vertex_adjacency(M, T, tri, &off, &adj);
-    compute_boundary_flags(M, T, tri, &bflags);
-    GINGR_CUDA_TRY(ctx, m->boundary.alloc((size_t)M));
-    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->boundary.p, bflags.data(), (size_t)M, cudaMemcpyHostToDevice, st));
-    GINGR_CUDA_TRY(ctx, m->tri.alloc((size_t)3 * T));
-    GINGR_CUDA_TRY(ctx, m->adj_off.alloc(off.size()));
-    GINGR_CUDA_TRY(ctx, m->adj.alloc(adj.size()));
-    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->tri.p, tri, sizeof(int32_t) * 3 * (size_t)T, cudaMemcpyHostToDevice, st));
-    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->adj_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
-    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(m->adj.p, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice, st));
-    GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  {
+    const int32_t rt = model_upload_topology(ctx, m, tri, T);
+    if (rt != GINGR_OK) { gingr_model_destroy(m); return rt; }
   }
   GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
   int32_t rc = model_build_constants(ctx, m);
@@ -710,6 +728,57 @@ int32_t gingr_model_destroy(gingr_model* m) {
   m->S.release();
   m->W0.release();
   delete m;
+  return GINGR_OK;
+}
+
+// model.newReference(newRef, NearestNeighborInterpolator()) (api/registration/SimpleRegistrator.scala:90-92; scalismo
+// semantics SURVEY.md A7): every new reference point takes the mean deformation and the three basis rows of its
+// NEAREST old reference point (exact argmin, lowest index on ties: the K2 vertex search); the variances are kept.  The
+// basis is no longer orthonormal afterwards, so the constants of the `coefficients` regression are rebuilt.
+int32_t gingr_model_new_reference(gingr_ctx* ctx, const gingr_model* model, int32_t M2, const double* new_ref,
+                                  const int32_t* tri, int32_t T, gingr_model** out) {
+  if (!ctx || !model || !out || !new_ref || M2 <= 0 || T < 0 || (T > 0 && !tri))
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_model_new_reference: bad argument");
+  if (ctx->nranks != 1) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "gingr_model_new_reference: single-GPU entry point (re-reference before sharding)");
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int M = model->M, r = model->r, rp = model->rp;
+  gingr_model* m = new gingr_model();
+  m->ctx = ctx;
+  m->M = M2; m->r = r; m->rp = rp; m->m0 = 0; m->Ml = M2;
+  DevBuf<double> old_soa, d2;
+  DevBuf<int32_t> idx;
+  ClosestWorkspace ws;
+  SpatialGrid pgrid;
+  int32_t rc = GINGR_OK;
+  auto A = [&](cudaError_t e) { if (e != cudaSuccess && rc == GINGR_OK) { gingr_set_error(ctx, cudaGetErrorString(e)); rc = GINGR_ERR_CUDA; } };
+  A(m->ref.alloc((size_t)3 * M2)); A(m->mean.alloc((size_t)3 * M2)); A(m->sqrt_lambda.alloc((size_t)rp));
+  A(m->phi.alloc((size_t)3 * M2 * rp));
+  A(old_soa.alloc((size_t)3 * M)); A(d2.alloc((size_t)M2)); A(idx.alloc((size_t)M2));
+  if (rc == GINGR_OK) rc = ws.ensure(ctx, M2, M, 0, 0);
+  if (rc == GINGR_OK) {
+    A(cudaMemcpyAsync(m->ref.p, new_ref, sizeof(double) * 3 * (size_t)M2, cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(m->sqrt_lambda.p, model->sqrt_lambda.p, sizeof(double) * rp, cudaMemcpyDeviceToDevice, st));
+  }
+  if (rc == GINGR_OK) rc = aos_to_soa_enqueue(ctx, M, model->ref.p, old_soa.p);
+  if (rc == GINGR_OK && grid_wanted(M)) {
+    VertexArray va;
+    va.p = model->ref.p;
+    rc = pgrid.ensure(ctx, M, M, false);
+    if (rc == GINGR_OK) rc = grid_build_points_enqueue(ctx, pgrid, M, va);
+  }
+  if (rc == GINGR_OK) rc = nn_vertex_enqueue(ctx, ws, M2, m->ref.p, M, old_soa.p, d2.p, idx.p, pgrid.built ? &pgrid : nullptr);
+  if (rc == GINGR_OK) {
+    rereference_rows_kernel<<<3 * M2, 128, 0, st>>>(M2, rp, idx.p, model->phi.p, model->mean.p, m->phi.p, m->mean.p);
+    GINGR_LAUNCHED(ctx);
+    A(cudaGetLastError());
+    A(cudaStreamSynchronize(st));
+  }
+  old_soa.release(); d2.release(); idx.release(); ws.release(); pgrid.release();
+  if (rc == GINGR_OK) rc = model_upload_topology(ctx, m, tri, T);
+  if (rc == GINGR_OK) rc = model_build_constants(ctx, m);
+  if (rc != GINGR_OK) { gingr_model_destroy(m); return rc; }
+  *out = m;
   return GINGR_OK;
 }
 

@@ -135,6 +135,15 @@ GINGR_API int32_t gingr_model_upload(gingr_ctx* ctx, int32_t M, int32_t r, const
                                      int64_t ld_basis, const double* variance /*[r]*/,
                                      const int32_t* tri /*[3T]*/, int32_t T, gingr_model** out);
 GINGR_API int32_t gingr_model_destroy(gingr_model* m);
+/* model.newReference(newRef, NearestNeighborInterpolator()) of SimpleRegistrator.decimateState
+ * (api/registration/SimpleRegistrator.scala:84-106; scalismo semantics SURVEY.md A7): every new reference point takes
+ * the mean deformation and basis rows of its nearest old reference point (exact argmin, ties -> lowest index), on the
+ * device, from the resident basis.  The decimated reference mesh itself (scalismo's quadric `decimate`) is the caller's.
+ * Used with gingr_target_upload of the decimated target to run the multi-resolution schedule of
+ * examples/DemoMultiResolution.scala:39-47 without re-uploading a basis. */
+GINGR_API int32_t gingr_model_new_reference(gingr_ctx* ctx, const gingr_model* model, int32_t M2,
+                                            const double* new_ref_pts /*[3 M2]*/, const int32_t* tri /*[3T]*/,
+                                            int32_t T, gingr_model** out);
 GINGR_API int32_t gingr_target_upload(gingr_ctx* ctx, int32_t N, const double* pts /*[3N]*/,
                                       const int32_t* tri /*[3T]*/, int32_t T, gingr_target** out);
 GINGR_API int32_t gingr_target_destroy(gingr_target* t);

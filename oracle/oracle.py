@@ -372,6 +372,13 @@ class Gpmm:
         basis = np.einsum("ab,mbk->mak", R, B).reshape(3 * self.M, self.rank)
         return Gpmm(ref, mean, basis, self.variance, self.tri)
 
+    def new_reference(self, new_ref, new_tri=None) -> "Gpmm":
+        """model.newReference(newRef, NearestNeighborInterpolator()) [scalismo-recalled A7]: mean deformation and basis
+        rows of the nearest old reference point (lowest index on ties).  SimpleRegistrator.scala:90-92"""
+        idx, _ = nearest_vertex(new_ref, self.ref)
+        rows = (3 * idx.astype(np.int64)[:, None] + np.arange(3)[None, :]).reshape(-1)
+        return Gpmm(_c(new_ref), self.mean[rows].copy(), self.basis[rows, :].copy(), self.variance, new_tri)
+
     def _regression(self, pids, values, cov_inv):
         """genericRegressionComputations  [A3].  values = y_i (displacements), cov_inv[n,3,3]."""
         pids = np.asarray(pids, dtype=np.int64)
