@@ -79,15 +79,17 @@ final class CudaSession(general: GeneralRegistrationState, cfg: MemorySegment =>
   private val aOut  = arena.allocate(JAVA_DOUBLE, rank.toLong)
   private val fit   = arena.allocate(JAVA_DOUBLE, 3L * M)
 
-  private def write(g: GeneralRegistrationState): Unit = {
+  private def write(g: GeneralRegistrationState): Unit = writeTo(g, stIn, aIn)
+
+  private def writeTo(g: GeneralRegistrationState, st: MemorySegment, alpha: MemorySegment): Unit = {
     val p = g.modelParameters
-    stIn.set(JAVA_DOUBLE, 0, p.scale.s)
+    st.set(JAVA_DOUBLE, 0, p.scale.s)
     val t = p.pose.translation; val e = p.pose.rotation.angles; val c = p.pose.rotation.center
-    Seq(t.x, t.y, t.z, e.phi, e.theta, e.psi, c.x, c.y, c.z).zipWithIndex.foreach { case (v, i) => stIn.set(JAVA_DOUBLE, 8L * (1 + i), v) }
-    stIn.set(JAVA_DOUBLE, 80, g.sigma2); stIn.set(JAVA_DOUBLE, 88, g.stepLength)
-    stIn.set(JAVA_INT, 96, g.globalTransformation match { case SimilarityTransforms => 0; case RigidTransforms => 1; case NoTransforms => 2 })
-    stIn.set(JAVA_INT, 100, g.iteration); stIn.set(JAVA_INT, 104, g.status.id); stIn.set(JAVA_INT, 108, rank)
-    MemorySegment.copy(p.shape.parameters.toArray, 0, aIn, JAVA_DOUBLE, 0, rank)
+    Seq(t.x, t.y, t.z, e.phi, e.theta, e.psi, c.x, c.y, c.z).zipWithIndex.foreach { case (v, i) => st.set(JAVA_DOUBLE, 8L * (1 + i), v) }
+    st.set(JAVA_DOUBLE, 80, g.sigma2); st.set(JAVA_DOUBLE, 88, g.stepLength)
+    st.set(JAVA_INT, 96, g.globalTransformation match { case SimilarityTransforms => 0; case RigidTransforms => 1; case NoTransforms => 2 })
+    st.set(JAVA_INT, 100, g.iteration); st.set(JAVA_INT, 104, g.status.id); st.set(JAVA_INT, 108, rank)
+    MemorySegment.copy(p.shape.parameters.toArray, 0, alpha, JAVA_DOUBLE, 0, rank)
   }
 
   private def read(g: GeneralRegistrationState, st: MemorySegment, alpha: MemorySegment): GeneralRegistrationState = {
@@ -112,6 +114,26 @@ final class CudaSession(general: GeneralRegistrationState, cfg: MemorySegment =>
   def update(g: GeneralRegistrationState, probabilistic: Boolean, seed: Long): GeneralRegistrationState = {
     write(g)
     check(update.invoke(reg, stIn, aIn, if (probabilistic) 1 else 0, seed, stOut, aOut, fit).asInstanceOf[Int], ctx)
+    read(g, stOut, aOut)
+  }
+
+  /** GeneratorWrapperStochastic.logTransitionProbability (GeneratorWrapperStochastic.scala:42-63) on the device. */
+  def logTransitionProbability(from: GeneralRegistrationState, to: GeneralRegistrationState): Double = {
+    write(from)                      // stIn / aIn
+    writeTo(to, stOut, aOut)         // the second state travels in the output segments
+    val out = arena.allocate(JAVA_DOUBLE)
+    check(logTransition.invoke(reg, stIn, aIn, stOut, aOut, out).asInstanceOf[Int], ctx)
+    out.get(JAVA_DOUBLE, 0)
+  }
+
+  /** ProbabilisticSettings -> gingr_mcmc_configure; then `steps` MH steps on the device and the best sample
+    * (GingrAlgorithm.run with probabilisticSettings, :115-175, without a host round trip per step). */
+  def runChain(g: GeneralRegistrationState, settings: MemorySegment, steps: Int, seed: Long): GeneralRegistrationState = {
+    check(mcmcConfigure.invoke(reg, settings, MemorySegment.NULL, 0, MemorySegment.NULL, 0).asInstanceOf[Int], ctx)
+    write(g)
+    check(initializeState.invoke(reg, stIn, aIn, fit).asInstanceOf[Int], ctx)
+    check(mcmcChain.invoke(reg, steps, seed).asInstanceOf[Int], ctx)
+    check(mcmcBest.invoke(reg, stOut, aOut, fit).asInstanceOf[Int], ctx)
     read(g, stOut, aOut)
   }
 
@@ -144,7 +166,21 @@ abstract class GingrAlgorithmCuda[C <: GingrConfig] extends GingrAlgorithm[CudaR
     probabilisticSettings: Option[ProbabilisticSettings[CudaRegistrationState[C]]],
     mixing: Option[ProposalGenerator[CudaRegistrationState[C]] with TransitionProbability[CudaRegistrationState[C]]]
   )(implicit rnd: Random): ProposalGenerator[CudaRegistrationState[C]] with TransitionProbability[CudaRegistrationState[C]] =
-    GeneratorWrapperDeterministic(update, name) // the stochastic wrapper needs the private CPU posterior (:186)
+    probabilisticSettings match {
+      case Some(setting) =>
+        // the informed generator of :186 without the private CPU posterior: proposal and transition density on the device
+        val informed = new GingrGeneratorWrapper[CudaRegistrationState[C]] {
+          override def gingrPropose(current: CudaRegistrationState[C]): CudaRegistrationState[C] = {
+            val n = update(current, true)
+            n.updateGeneral(n.general.updateGeneratedBy(name))
+          }
+          override def logTransitionProbability(from: CudaRegistrationState[C], to: CudaRegistrationState[C]): Double =
+            sessionFor(from).logTransitionProbability(from.general, to.general)
+        }
+        val mix = mixing.getOrElse(new Generator[CudaRegistrationState[C]]().DefaultRandom())
+        MixtureProposal(setting.randomMixture *: mix + (1.0 - setting.randomMixture) *: informed)
+      case _ => GeneratorWrapperDeterministic(update, name)
+    }
 }
 
 class CpdRegistrationCuda extends GingrAlgorithmCuda[CpdConfiguration] {

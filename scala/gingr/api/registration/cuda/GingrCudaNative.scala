@@ -65,6 +65,27 @@ object GingrCudaNative {
   val icpClosest     = fn("gingr_icp_closest", JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT,
                           ADDRESS, ADDRESS, ADDRESS, ADDRESS)
 
+  // probabilistic registration (SURVEY.md 8f-1) and multi-resolution hand-over (8f-2)
+  /** struct gingr_mcmc_settings: double x2, int32 x2, double x9 = 96 bytes. */
+  val MCMC_SETTINGS: StructLayout = MemoryLayout.structLayout(
+    JAVA_DOUBLE.withName("random_mixture"),
+    JAVA_DOUBLE.withName("uncertainty"),
+    JAVA_INT.withName("evaluation_mode"),
+    JAVA_INT.withName("reserved"),
+    MemoryLayout.sequenceLayout(3, JAVA_DOUBLE).withName("rot_sdev"),
+    MemoryLayout.sequenceLayout(3, JAVA_DOUBLE).withName("trans_sdev"),
+    MemoryLayout.sequenceLayout(3, JAVA_DOUBLE).withName("shape_sdev")
+  )
+  val mcmcConfigure  = fn("gingr_mcmc_configure", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT)
+  val evaluateLogValue = fn("gingr_evaluate_log_value", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
+  val logTransition  = fn("gingr_log_transition_probability", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
+  val mcmcChain      = fn("gingr_mcmc_chain", JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG)
+  val mcmcBatch      = fn("gingr_mcmc_batch", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_LONG)
+  val mcmcStats      = fn("gingr_mcmc_stats", JAVA_INT, ADDRESS, ADDRESS, ADDRESS)
+  val mcmcBest       = fn("gingr_mcmc_best", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
+  val stateDownload  = fn("gingr_state_download", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
+  val modelNewReference = fn("gingr_model_new_reference", JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS)
+
   def check(code: Int, ctx: MemorySegment): Int = {
     if (code < 0) {
       val msg = lastError.invoke(ctx).asInstanceOf[MemorySegment].reinterpret(4096).getString(0)
