@@ -35,6 +35,11 @@ constexpr int SP = NB + 1;  // shared pitch for the scalar kernels
 // The panel rows are solved one row per thread, the row held in registers (x[64]), right-looking so the 63
 // updates of a step are independent FMAs; L is read from shared memory as a broadcast.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+
 constexpr int PR = 128;  // panel rows (threads) per CTA
 constexpr size_t PANEL_SMEM = ((size_t)NB * SP + NB + (size_t)PR * SP) * sizeof(double);
 
@@ -81,14 +86,19 @@ __global__ void __launch_bounds__(PR) chol_panel_kernel(int nrows, int j0, int j
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i0 = j0 + jb + blockIdx.x * PR;
   const int cnt = max(0, min(PR, nrows - i0));
+  // All 96 loads of a thread are issued as asynchronous 8-byte copies before anything waits: the load phase was a
+  // quarter of the kernel (ncu: long-scoreboard stalls) when every global load stalled the scheduler's only warp in turn.
   for (int e = tid; e < NB * NB; e += PR) {
     const int i = e >> 6, k = e & 63;
-    sL[i * SP + k] = (i < jb && k <= i) ? A[(size_t)(j0 + i) * ld + j0 + k] : (i == k ? 1.0 : 0.0);
+    if (i < jb && k <= i) cp_async8(&sL[i * SP + k], &A[(size_t)(j0 + i) * ld + j0 + k]);
+    else sL[i * SP + k] = (i == k ? 1.0 : 0.0);
   }
   for (int e = tid; e < PR * NB; e += PR) {
     const int i = e >> 6, k = e & 63;
-    sX[i * SP + k] = (i < cnt && k < jb) ? A[(size_t)(i0 + i) * ld + j0 + k] : 0.0;
+    if (i < cnt && k < jb) cp_async8(&sX[i * SP + k], &A[(size_t)(i0 + i) * ld + j0 + k]);
+    else sX[i * SP + k] = 0.0;
   }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
   __syncthreads();
   // All four warps run the warp-level pieces redundantly and convergently (no divergent region around the
   // shuffles); only warp 0 stores.  h = 0: (L11, L21, A22 update), h = 1: L22 -- one copy of the unrolled code.

@@ -150,16 +150,25 @@ struct TriCells {
   bool too_big;
 };
 
-__device__ __forceinline__ TriCells triangle_cells(const GridParams& g, const double* __restrict__ va, int a, int b, int c) {
-  TriCells r;
+// bounding box of a triangle rounded OUTWARD to float: the 32-byte record the surface search rejects and
+// de-duplicates candidates with, and -- so that both agree exactly -- also what the cell ranges are derived from
+__device__ __forceinline__ void triangle_float_box(const double* __restrict__ va, int a, int b, int c, float4& lo, float4& hi) {
   const double* pa = va + 3 * (size_t)a; const double* pb = va + 3 * (size_t)b; const double* pc = va + 3 * (size_t)c;
+  lo = make_float4(__double2float_rd(fmin(pa[0], fmin(pb[0], pc[0]))), __double2float_rd(fmin(pa[1], fmin(pb[1], pc[1]))),
+                   __double2float_rd(fmin(pa[2], fmin(pb[2], pc[2]))), 0.f);
+  hi = make_float4(__double2float_ru(fmax(pa[0], fmax(pb[0], pc[0]))), __double2float_ru(fmax(pa[1], fmax(pb[1], pc[1]))),
+                   __double2float_ru(fmax(pa[2], fmax(pb[2], pc[2]))), 0.f);
+}
+
+__device__ __forceinline__ TriCells triangle_cells(const GridParams& g, const float4& lo, const float4& hi) {
+  TriCells r;
   const double m = g.margin;
-  r.x0 = cell_coord(fmin(pa[0], fmin(pb[0], pc[0])) - m, g.ox, g.inv_h, g.nx);
-  r.x1 = cell_coord(fmax(pa[0], fmax(pb[0], pc[0])) + m, g.ox, g.inv_h, g.nx);
-  r.y0 = cell_coord(fmin(pa[1], fmin(pb[1], pc[1])) - m, g.oy, g.inv_h, g.ny);
-  r.y1 = cell_coord(fmax(pa[1], fmax(pb[1], pc[1])) + m, g.oy, g.inv_h, g.ny);
-  r.z0 = cell_coord(fmin(pa[2], fmin(pb[2], pc[2])) - m, g.oz, g.inv_h, g.nz);
-  r.z1 = cell_coord(fmax(pa[2], fmax(pb[2], pc[2])) + m, g.oz, g.inv_h, g.nz);
+  r.x0 = cell_coord((double)lo.x - m, g.ox, g.inv_h, g.nx);
+  r.x1 = cell_coord((double)hi.x + m, g.ox, g.inv_h, g.nx);
+  r.y0 = cell_coord((double)lo.y - m, g.oy, g.inv_h, g.ny);
+  r.y1 = cell_coord((double)hi.y + m, g.oy, g.inv_h, g.ny);
+  r.z0 = cell_coord((double)lo.z - m, g.oz, g.inv_h, g.nz);
+  r.z1 = cell_coord((double)hi.z + m, g.oz, g.inv_h, g.nz);
   r.too_big = (long long)(r.x1 - r.x0 + 1) * (r.y1 - r.y0 + 1) * (r.z1 - r.z0 + 1) > MAX_TRI_CELLS;
   return r;
 }
@@ -173,18 +182,11 @@ __global__ void __launch_bounds__(256) grid_tri_kernel(int T, const double* __re
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (t >= T) return;
   const GridParams g = *gp;
-  if (PASS == 0) {
-    // bounding box of the triangle, rounded OUTWARD to float: a 32-byte quick reject for the surface search
-    const double* pa = verts_aos + 3 * (size_t)tri[3 * t];
-    const double* pb = verts_aos + 3 * (size_t)tri[3 * t + 1];
-    const double* pc = verts_aos + 3 * (size_t)tri[3 * t + 2];
-    tri_box[2 * t] = make_float4(__double2float_rd(fmin(pa[0], fmin(pb[0], pc[0]))), __double2float_rd(fmin(pa[1], fmin(pb[1], pc[1]))),
-                                 __double2float_rd(fmin(pa[2], fmin(pb[2], pc[2]))), 0.f);
-    tri_box[2 * t + 1] = make_float4(__double2float_ru(fmax(pa[0], fmax(pb[0], pc[0]))), __double2float_ru(fmax(pa[1], fmax(pb[1], pc[1]))),
-                                     __double2float_ru(fmax(pa[2], fmax(pb[2], pc[2]))), 0.f);
-  }
+  float4 blo, bhi;
+  triangle_float_box(verts_aos, tri[3 * t], tri[3 * t + 1], tri[3 * t + 2], blo, bhi);
+  if (PASS == 0) { tri_box[2 * t] = blo; tri_box[2 * t + 1] = bhi; }
   if (PASS == 1 && g.overflow) return;
-  const TriCells r = triangle_cells(g, verts_aos, tri[3 * t], tri[3 * t + 1], tri[3 * t + 2]);
+  const TriCells r = triangle_cells(g, blo, bhi);
   if (r.too_big) {
     if (PASS == 0) atomicExch(&gp->overflow, 1);
     return;
@@ -398,8 +400,8 @@ __device__ __forceinline__ double box_dist2(const GridParams& g, double qx, doub
 //   refine the fine cells around the candidate's own location (where()), which nearly always hold the true nearest
 //   ball   the proof: every cell whose box is not farther than the current best (which shrinks as candidates are
 //          evaluated) is visited, at the finest level where the ball spans at most 4096 cells.
-// visit(e0, e1) evaluates the entries [e0, e1) with (value, lowest index) selection; best() returns the current
-// best SQUARED distance.  Returns false when the caller must scan everything (no candidate near, or a ball too big).
+// visit(e0, e1, x, y, z, sh) evaluates the entries [e0, e1) of the level-sh/2 cell (x, y, z) (sh < 0: seed phase,
+// evaluate everything) with (value, lowest index) selection; best() returns the current best SQUARED distance.  Returns false when the caller must scan everything (no candidate near, or a ball too big).
 template <typename V, typename B, typename W>
 __device__ __forceinline__ bool grid_search(const GridParams& g, const int32_t* __restrict__ cell_start, double qx, double qy,
                                             double qz, V&& visit, B&& best, W&& where) {
@@ -457,7 +459,7 @@ __device__ __forceinline__ bool grid_search(const GridParams& g, const int32_t* 
           bx = ux; by = uy; bz = uz;
         }
         const int c = cell_index(g, bx, by, bz);
-        visit(cell_start[c], cell_start[c + 1]);
+        visit(cell_start[c], cell_start[c + 1], bx, by, bz, -1);
         seeded = true;
       }
     }
@@ -476,7 +478,7 @@ __device__ __forceinline__ bool grid_search(const GridParams& g, const int32_t* 
         for (int x = max(ux - 1, 0); x <= min(ux + 1, g.nx - 1); ++x) {
           const int c = cell_index(g, x, y, z);
           const int e0 = cell_start[c], e1 = cell_start[c + 1];
-          if (e1 > e0 && !(box_dist2(g, qx, qy, qz, x, y, z, g.h) > best())) visit(e0, e1);
+          if (e1 > e0 && !(box_dist2(g, qx, qy, qz, x, y, z, g.h) > best())) visit(e0, e1, x, y, z, 0);
         }
   }
   // ---- ball ---------------------------------------------------------------------------------------
@@ -498,7 +500,7 @@ __device__ __forceinline__ bool grid_search(const GridParams& g, const int32_t* 
           const int c = cell_index(g, x << sh, y << sh, z << sh);
           const int e0 = cell_start[c], e1 = cell_start[c + span];
           GSTAT(2, 1);
-          if (e1 > e0 && !(box_dist2(g, qx, qy, qz, x, y, z, hl) > best())) { GSTAT(3, 1); GSTAT(4, e1 - e0); visit(e0, e1); }
+          if (e1 > e0 && !(box_dist2(g, qx, qy, qz, x, y, z, hl) > best())) { GSTAT(3, 1); GSTAT(4, e1 - e0); visit(e0, e1, x, y, z, sh); }
         }
       }
     return true;
@@ -535,7 +537,7 @@ __global__ void __launch_bounds__(128) grid_nn_kernel(int M, const double4* __re
   if (isfinite(qx) && isfinite(qy) && isfinite(qz)) {
     const GridParams g = *gp;
     const bool done = grid_search(g, cell_start, qx, qy, qz,
-                                  [&](int e0, int e1) { for (int e = e0; e < e1; ++e) consider(e); },
+                                  [&](int e0, int e1, int, int, int, int) { for (int e = e0; e < e1; ++e) consider(e); },
                                   [&]() { return best; }, [&](double& x, double& y, double& z) { x = bpx; y = bpy; z = bpz; });
     if (!done) {
       best = INFINITY; bi = -1;
@@ -572,15 +574,22 @@ __global__ void __launch_bounds__(128) grid_surface_kernel(int M, const double4*
   const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
   double best = INFINITY, bx = 0, by = 0, bz = 0;
   int bt = -1;
-  auto consider = [&](int t) {
+  GridParams g;
+  auto consider = [&](int t, int x, int y, int z, int sh) {
     {
       // quick reject: the triangle lies inside its (outward rounded) box, so it cannot beat or tie the best when
-      // the box is strictly farther
+      // the box is strictly farther.  De-duplication: a triangle is entered in every cell its box overlaps; it is
+      // evaluated only in the cell that holds the point of its box nearest to the query -- that cell is one of its
+      // cells (same box, same monotone cell function as the build) and is never farther than the triangle itself, so
+      // the ball walk reaches it whenever the triangle can win.
       const float4 lo = tri_box[2 * t], hi = tri_box[2 * t + 1];
-      const double ex = fmax(0.0, fmax((double)lo.x - qx, qx - (double)hi.x));
-      const double ey = fmax(0.0, fmax((double)lo.y - qy, qy - (double)hi.y));
-      const double ez = fmax(0.0, fmax((double)lo.z - qz, qz - (double)hi.z));
+      const double px = fmin(fmax(qx, (double)lo.x), (double)hi.x), py = fmin(fmax(qy, (double)lo.y), (double)hi.y),
+                   pz = fmin(fmax(qz, (double)lo.z), (double)hi.z);
+      const double ex = qx - px, ey = qy - py, ez = qz - pz;
       if ((ex * ex + ey * ey + ez * ez) * (1.0 - 1e-12) > best) return;
+      if (sh >= 0 && ((cell_coord(px, g.ox, g.inv_h, g.nx) >> sh) != x || (cell_coord(py, g.oy, g.inv_h, g.ny) >> sh) != y ||
+                      (cell_coord(pz, g.oz, g.inv_h, g.nz) >> sh) != z))
+        return;
     }
     GSTAT(5, 1);
     const double* a = verts + 3 * (size_t)tri[3 * t];
@@ -594,16 +603,18 @@ __global__ void __launch_bounds__(128) grid_surface_kernel(int M, const double4*
     if (d < best || (d == best && t < bt)) { best = d; bt = t; bx = cx; by = cy; bz = cz; }
   };
   if (isfinite(qx) && isfinite(qy) && isfinite(qz)) {
-    const GridParams g = *gp;
+    g = *gp;
     bool done = false;
     if (!g.overflow) {
       done = grid_search(g, cell_start, qx, qy, qz,
-                         [&](int e0, int e1) { for (int e = e0; e < e1; ++e) consider(entries[e]); },
+                         [&](int e0, int e1, int x, int y, int z, int sh) {
+                           for (int e = e0; e < e1; ++e) consider(entries[e], x, y, z, sh);
+                         },
                          [&]() { return best; }, [&](double& x, double& y, double& z) { x = bx; y = by; z = bz; });
     }
     if (!done) {
       best = INFINITY; bt = -1; bx = by = bz = 0;
-      for (int t = 0; t < T; ++t) consider(t);
+      for (int t = 0; t < T; ++t) consider(t, 0, 0, 0, -1);
     }
   }
   d2[i] = best;
