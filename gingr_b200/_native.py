@@ -93,6 +93,8 @@ SIGNATURES = {
     "gingr_model_upload": (c_int32, [c_void_p, c_int32, c_int32, dp, dp, dp, c_int64, dp, ip, c_int32, vpp]),
     "gingr_model_destroy": (c_int32, [c_void_p]),
     "gingr_model_new_reference": (c_int32, [c_void_p, c_void_p, c_int32, dp, ip, c_int32, vpp]),
+    "gingr_gpmm_gaussian_mixture": (c_int32, [c_void_p, c_int32, dp, ip, c_int32, c_int32, dp, dp, c_double, c_int32, vpp, ip]),
+    "gingr_model_download": (c_int32, [c_void_p, c_void_p, ip, ip, dp, dp, dp, c_int64, dp]),
     "gingr_target_upload": (c_int32, [c_void_p, c_int32, dp, ip, c_int32, vpp]),
     "gingr_target_destroy": (c_int32, [c_void_p]),
     "gingr_cpd_estep": (c_int32, [c_void_p, c_void_p, c_int32, dp, c_double, c_double, dp, dp, dp]),

@@ -125,6 +125,34 @@ class Model:
         self.handle = h
         self.triangles = tri
 
+    @staticmethod
+    def gaussianMixture(ctx: Context, ref_points, triangles, sigmas, scalings, relativeTolerance: float = 0.01,
+                        maxRank: int = 0) -> "Model":
+        """GPMMTriangleMesh3D(reference, relativeTolerance).GaussianMixture(pars) (api/gpmm/GPMMHelper.scala:117-121;
+        .Gaussian(sigma, scaling) is the one-kernel case, :100-103) built on the device."""
+        ref = nat.f64(ref_points).reshape(-1, 3)
+        tri = None if triangles is None else nat.i32(triangles).reshape(-1, 3)
+        sg, sc = nat.f64(np.atleast_1d(sigmas)), nat.f64(np.atleast_1d(scalings))
+        assert sg.shape == sc.shape
+        h = ctypes.c_void_p()
+        rank = ctypes.c_int32()
+        ctx.check(ctx._lib.gingr_gpmm_gaussian_mixture(ctx.handle, ref.shape[0], nat.as_dp(ref), nat.as_ip(tri),
+                                                       0 if tri is None else tri.shape[0], len(sg), nat.as_dp(sg), nat.as_dp(sc),
+                                                       float(relativeTolerance), int(maxRank), ctypes.byref(h), ctypes.byref(rank)))
+        m = Model.__new__(Model)
+        m.ctx, m.M, m.rank, m.T, m.handle, m.triangles = ctx, ref.shape[0], int(rank.value), 0 if tri is None else tri.shape[0], h, tri
+        return m
+
+    def download(self):
+        """(reference points [M, 3], meanVector [3M], basisMatrix [3M, r], variance [r]) as scalismo stores them."""
+        ref = np.empty((self.M, 3))
+        mean = np.empty(3 * self.M)
+        basis = np.empty((3 * self.M, self.rank), order="F")
+        var = np.empty(self.rank)
+        self.ctx.check(self.ctx._lib.gingr_model_download(self.ctx.handle, self.handle, None, None, nat.as_dp(ref), nat.as_dp(mean),
+                                                          basis.ctypes.data_as(nat.dp), 3 * self.M, nat.as_dp(var)))
+        return ref, mean, basis, var
+
     def newReference(self, ref_points, triangles=None) -> "Model":
         """model.newReference(newRef, NearestNeighborInterpolator()) (SimpleRegistrator.scala:90-92) on the device: the
         new model's rows are gathered from the resident basis at the nearest old reference points."""

@@ -1725,3 +1725,4 @@ int32_t gingr_state_download(gingr_registration* g, gingr_state* state_out, doub
 }  // extern "C"
 
 #include "mcmc.cuh"
+#include "gpmm.cuh"

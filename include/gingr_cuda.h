@@ -144,6 +144,21 @@ GINGR_API int32_t gingr_model_destroy(gingr_model* m);
 GINGR_API int32_t gingr_model_new_reference(gingr_ctx* ctx, const gingr_model* model, int32_t M2,
                                             const double* new_ref_pts /*[3 M2]*/, const int32_t* tri /*[3T]*/,
                                             int32_t T, gingr_model** out);
+/* GPMM construction: GPMMTriangleMesh3D(reference, relativeTolerance).Gaussian(sigma, scaling) /
+ * .GaussianMixture(pars) (api/gpmm/GPMMHelper.scala:99-129) = GPMM.construct (:39-54) = scalismo
+ * LowRankGaussianProcess.approximateGPCholesky for DiagonalKernel(sum_q scaling_q GaussianKernel(sigma_q), 3):
+ * pivoted Cholesky until trace(residual) <= rel_tol * trace(K) (at most max_rank columns, 0 = no cap), then the KL basis
+ * (orthonormal columns, variances) -- all on the device; the mean is zero.  The basis is unique only up to rotations inside
+ * the (triple) eigenspaces: rank, variances and the covariance basis diag(variance) basis^T are what is defined. */
+GINGR_API int32_t gingr_gpmm_gaussian_mixture(gingr_ctx* ctx, int32_t M, const double* ref_pts /*[3M]*/,
+                                              const int32_t* tri /*[3T]*/, int32_t T, int32_t n_kernels,
+                                              const double* sigma /*[n]*/, const double* scaling /*[n]*/, double rel_tol,
+                                              int32_t max_rank, gingr_model** out, int32_t* rank_out);
+/* The model as scalismo stores it: meanVector, basisMatrix column-major with leading dimension ld_basis,
+ * variance.  Any output may be NULL (M_out / r_out give the sizes to allocate). */
+GINGR_API int32_t gingr_model_download(gingr_ctx* ctx, const gingr_model* model, int32_t* M_out, int32_t* r_out,
+                                       double* ref_pts /*[3M]*/, double* mean /*[3M]*/, double* basis, int64_t ld_basis,
+                                       double* variance /*[r]*/);
 GINGR_API int32_t gingr_target_upload(gingr_ctx* ctx, int32_t N, const double* pts /*[3N]*/,
                                       const int32_t* tri /*[3T]*/, int32_t T, gingr_target** out);
 GINGR_API int32_t gingr_target_destroy(gingr_target* t);

@@ -918,3 +918,80 @@ def mcmc_step(algo, settings: McmcSettings, cur: State, lp_cur, step: int, seed:
     info["a"] = a
     info["accept"] = accept
     return (prop, lp_prop, info) if accept else (cur, lp_cur, info)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPMM construction (api/gpmm/GPMMHelper.scala:39-54, :99-129; scalismo approximateGPCholesky [scalismo-recalled A7])
+# ---------------------------------------------------------------------------------------------
+def gaussian_mixture_kernel_matrix(pts, sigmas, scalings):
+    """Scalar kernel sum_q scaling_q exp(-|x - y|^2 / sigma_q^2)  (scalismo GaussianKernel: sigma^2, not 2 sigma^2)."""
+    p = _c(pts)
+    d2 = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1)
+    return sum(sc * np.exp(-d2 / (sg * sg)) for sg, sc in zip(np.atleast_1d(sigmas), np.atleast_1d(scalings)))
+
+
+def pivoted_cholesky(K, rel_tol, max_rank=None):
+    """scalismo PivotedCholesky.computeApproximateCholesky with RelativeTolerance, literal: columns are added while the
+    residual trace exceeds rel_tol * trace(K); the pivot is the first maximal residual diagonal."""
+    n = K.shape[0]
+    d = np.diag(K).astype(float).copy()
+    tol = rel_tol * d.sum()
+    cap = n if not max_rank else min(n, max_rank)
+    cols = []
+    done = np.zeros(n, dtype=bool)
+    tr = d.sum()
+    while len(cols) < cap and tr > tol:
+        dm = np.where(done, -np.inf, d)
+        p = int(np.argmax(dm))
+        if not dm[p] > 0.0:
+            cols.append(np.zeros(n))
+            done[p] = True
+        else:
+            piv = np.sqrt(dm[p])
+            col = K[:, p].astype(float).copy()
+            for c in cols:
+                col -= c * c[p]
+            col /= piv
+            col[done] = 0.0
+            col[p] = piv
+            done[p] = True
+            d = d - col * col
+            cols.append(col)
+        tr = float(d[~done].sum())
+    return np.stack(cols, axis=1) if cols else np.zeros((n, 0))
+
+
+def approximate_gp_cholesky(ref, sigmas, scalings, rel_tol=0.01, max_rank=None) -> "Gpmm":
+    """LowRankGaussianProcess.approximateGPCholesky for DiagonalKernel(scalar Gaussian mixture, 3), LITERAL: the
+    3M x 3M matrix K = Ks (x) I3 (row 3 i + d), pivoted Cholesky L, (V, s) = svd(L^T L), basis = L V s^-1/2, variance = s."""
+    Ks = gaussian_mixture_kernel_matrix(ref, sigmas, scalings)
+    K = np.kron(Ks, np.eye(3))
+    L = pivoted_cholesky(K, rel_tol, max_rank)
+    V, s, _ = np.linalg.svd(L.T @ L)
+    basis = L @ V / np.sqrt(s)[None, :]
+    return Gpmm(_c(ref), np.zeros(3 * len(ref)), basis, s, None), L
+
+
+def approximate_gp_cholesky_structured(ref, sigmas, scalings, rel_tol=0.01, max_rank=None):
+    """The same through the scalar M x M factorisation (what gingr_b200/csrc/gpmm.cuh does): returns (rank, L L^T as the
+    per-dimension scalar factors) -- dims < rank % 3 use one more scalar column."""
+    Ks = gaussian_mixture_kernel_matrix(ref, sigmas, scalings)
+    M = Ks.shape[0]
+    full_cap = 3 * M if not max_rank else min(3 * M, max_rank)
+    Ls = pivoted_cholesky(Ks, 0.0, min(M, (full_cap + 2) // 3))
+    # scalar traces T(k) before step k
+    T = [float(np.trace(Ks) - np.sum(Ls[:, :k] ** 2)) for k in range(Ls.shape[1] + 1)]
+    # residual of already chosen pivots is exactly zero in exact arithmetic; mirror the device (sum over not-done rows)
+    tol = rel_tol * 3.0 * T[0]
+    rank = None
+    for kk in range(Ls.shape[1]):
+        for c in range(3):
+            tr = 3.0 * T[kk] - c * (T[kk] - T[kk + 1])
+            if not tr > tol or 3 * kk + c >= full_cap:
+                rank = 3 * kk + c
+                break
+        if rank is not None:
+            break
+    if rank is None:
+        rank = min(3 * Ls.shape[1], full_cap)
+    return rank, Ls
