@@ -116,13 +116,28 @@ int64_t gingr_ctx_launch_count(const gingr_ctx* ctx) { return ctx ? ctx->launche
 // ---------------------------------------------------------------------------------------------
 // uploads
 // ---------------------------------------------------------------------------------------------
+static int32_t target_upload_into(gingr_ctx* ctx, gingr_target* t, int32_t N, const double* pts, const int32_t* tri, int32_t T);
+
 int32_t gingr_target_upload(gingr_ctx* ctx, int32_t N, const double* pts, const int32_t* tri, int32_t T,
                             gingr_target** out) {
   if (!ctx || !out || !pts || N <= 0 || T < 0 || (T > 0 && !tri))
     return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_target_upload: bad argument");
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (T > 0)
+    for (int k = 0; k < 3 * T; ++k)
+      if (tri[k] < 0 || tri[k] >= N) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_target_upload: triangle index out of range");
   gingr_target* t = new gingr_target();
   t->ctx = ctx;
+  const int32_t rc = target_upload_into(ctx, t, N, pts, tri, T);
+  if (rc != GINGR_OK) {
+    gingr_target_destroy(t);   // releases whatever was allocated before the failure
+    return rc;
+  }
+  *out = t;
+  return GINGR_OK;
+}
+
+static int32_t target_upload_into(gingr_ctx* ctx, gingr_target* t, int32_t N, const double* pts, const int32_t* tri, int32_t T) {
   t->N_total = N;
   for (size_t k = 0; k < (size_t)3 * N; ++k) {
     if (!(fabs(pts[k]) < INFINITY)) { t->nonfinite = true; break; }
@@ -146,11 +161,6 @@ int32_t gingr_target_upload(gingr_ctx* ctx, int32_t N, const double* pts, const 
   if (T > 0) {
     GINGR_CUDA_TRY(ctx, t->tri.alloc((size_t)3 * T));
     GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(t->tri.p, tri, sizeof(int32_t) * 3 * (size_t)T, cudaMemcpyHostToDevice, ctx->stream));
-    for (int k = 0; k < 3 * T; ++k)
-      if (tri[k] < 0 || tri[k] >= N) {
-        delete t;
-        return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_target_upload: triangle index out of range");
-      }
     GINGR_TRY(gingr::mesh_static_upload(ctx, N, pts, T, tri, &t->normals, &t->boundary));
   }
   if (gingr::grid_wanted(N) && !t->nonfinite) {
@@ -166,7 +176,6 @@ int32_t gingr_target_upload(gingr_ctx* ctx, int32_t N, const double* pts, const 
     }
   }
   GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  *out = t;
   return GINGR_OK;
 }
 

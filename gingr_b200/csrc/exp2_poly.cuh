@@ -107,4 +107,26 @@ __device__ __forceinline__ double gauss_exp2_tab(double d2, double negk64, const
   return __hiloint2double(ok ? __double2hiint(v) : 0, ok ? __double2loint(v) : 0);
 }
 
+// The same with the scaled argument u = d2 * negk64 already formed (expanded-distance path of estep.cu): the integer
+// part comes from one add against the shift constant, the remainder r = u - n is exact.  Range-guaranteed callers only
+// (0 <= -u < 2^31 - 2^18): one compare.
+__device__ __forceinline__ double gauss_exp2_tab_u(double u, const unsigned int* s_tab, int lane_off) {
+  const double SHIFT = GAUSS_C[5];
+  const double tmp = u + SHIFT;
+  const int lo = __double2loint(tmp);  // (2048 + n) * 64 + k
+  const double nf = tmp - SHIFT;
+  const double r = u - nf;
+  const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(s_tab) + (((lo << 7) & 0x1F80) | lane_off));
+  const double T = __hiloint2double((int)(((unsigned)lo << 14) + t.y), (int)t.x);
+  double p = GAUSS_C[4];
+  p = fma(p, r, GAUSS_C[3]);
+  p = fma(p, r, GAUSS_C[2]);
+  p = fma(p, r, GAUSS_C[1]);
+  p = fma(p, r, GAUSS_C[0]);
+  const double s = T * r;
+  const double v = fma(s, p, T);
+  const bool ok = lo >= 963 * 64;
+  return __hiloint2double(ok ? __double2hiint(v) : 0, ok ? __double2loint(v) : 0);
+}
+
 }  // namespace gingr

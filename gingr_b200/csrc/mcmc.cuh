@@ -751,18 +751,12 @@ int32_t gingr_mcmc_batch(gingr_registration** regs, int32_t n, int32_t iters, ui
     if (!regs[k]->state_valid) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_mcmc_batch: chain without device-resident state");
   }
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  constexpr int NS = 16;
-  static thread_local cudaStream_t pool[NS] = {nullptr};
-  static thread_local cudaEvent_t fork_ev = nullptr, join_ev[NS] = {nullptr};
-  static thread_local int pool_device = -1;
-  if (pool_device != ctx->device) {
-    for (int q = 0; q < NS; ++q) {
-      GINGR_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&pool[q], cudaStreamNonBlocking));
-      GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&join_ev[q], cudaEventDisableTiming));
-    }
-    GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
-    pool_device = ctx->device;
-  }
+  ChainStreamPool* sp = nullptr;
+  GINGR_TRY(chain_stream_pool(ctx, &sp));
+  constexpr int NS = ChainStreamPool::NS;
+  cudaStream_t* pool = sp->streams;
+  cudaEvent_t fork_ev = sp->fork_ev;
+  cudaEvent_t* join_ev = sp->join_ev;
   for (int k = 0; k < n; ++k) {
     if (!regs[k]->mcmc->primed) GINGR_TRY(mcmc_prime(regs[k]));
     GINGR_TRY(mcmc_capture(regs[k], seed + (uint64_t)k));

@@ -1609,6 +1609,29 @@ int32_t gingr_update_chain_sampled(gingr_registration* g, int32_t iters, uint64_
   return GINGR_OK;
 }
 
+// Pool of streams the batched entry points (gingr_update_batch, gingr_mcmc_batch) replay the chains' graphs on: one pool
+// per host thread and device, created on first use.
+struct ChainStreamPool {
+  static constexpr int NS = 16;
+  cudaStream_t streams[NS] = {nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev[NS] = {nullptr};
+  int device = -1;
+};
+
+static int32_t chain_stream_pool(gingr_ctx* ctx, ChainStreamPool** out) {
+  static thread_local ChainStreamPool pool;
+  if (pool.device != ctx->device) {
+    for (int q = 0; q < ChainStreamPool::NS; ++q) {
+      GINGR_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&pool.streams[q], cudaStreamNonBlocking));
+      GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&pool.join_ev[q], cudaEventDisableTiming));
+    }
+    GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&pool.fork_ev, cudaEventDisableTiming));
+    pool.device = ctx->device;
+  }
+  *out = &pool;
+  return GINGR_OK;
+}
+
 // Independent registrations / MCMC chains (SURVEY.md 8e "replicas only"; BASELINE config 5): every chain is its own
 // gingr_registration (own state and workspaces; model and target handles are shared), its iteration is one captured
 // CUDA graph, and the graphs of different chains are replayed round-robin on a small pool of streams so that the
@@ -1623,18 +1646,12 @@ int32_t gingr_update_batch(gingr_registration** regs, int32_t n, int32_t iters, 
   }
   if (ctx->nranks != 1) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "gingr_update_batch: chains are replicas, one ctx per GPU without a communicator");
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  constexpr int NS = 16;
-  static thread_local cudaStream_t pool[NS] = {nullptr};
-  static thread_local cudaEvent_t fork_ev = nullptr, join_ev[NS] = {nullptr};
-  static thread_local int pool_device = -1;
-  if (pool_device != ctx->device) {
-    for (int q = 0; q < NS; ++q) {
-      GINGR_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&pool[q], cudaStreamNonBlocking));
-      GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&join_ev[q], cudaEventDisableTiming));
-    }
-    GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
-    pool_device = ctx->device;
-  }
+  ChainStreamPool* sp = nullptr;
+  GINGR_TRY(chain_stream_pool(ctx, &sp));
+  constexpr int NS = ChainStreamPool::NS;
+  cudaStream_t* pool = sp->streams;
+  cudaEvent_t fork_ev = sp->fork_ev;
+  cudaEvent_t* join_ev = sp->join_ev;
   // capture (or re-key) every chain's graph on the ctx stream first: capture is not concurrent
   for (int k = 0; k < n; ++k) {
     gingr_registration* g = regs[k];
