@@ -29,14 +29,22 @@ namespace gingr {
 
 // tuning knobs (overridable with -D for experiments; the defaults are the measured best on B200)
 #ifndef ESTEP_CA
-#define ESTEP_CA 4
+#define ESTEP_CA 6
 #endif
 #ifndef ESTEP_RB
 #define ESTEP_RB 4
 #endif
 #ifndef ESTEP_MINB_A
-#define ESTEP_MINB_A 3
+#define ESTEP_MINB_A 2
 #endif
+#ifndef ESTEP_UNROLL_A
+#define ESTEP_UNROLL_A 1
+#endif
+#ifndef ESTEP_UNROLL_B
+#define ESTEP_UNROLL_B 1
+#endif
+#define ESTEP_PRAGMA(x) _Pragma(#x)
+#define ESTEP_UNROLL(n) ESTEP_PRAGMA(unroll n)
 #ifndef ESTEP_MINB_B
 #define ESTEP_MINB_B 2
 #endif
@@ -67,7 +75,7 @@ __device__ __forceinline__ bool estep_expand_ok(const double* __restrict__ scal)
 __device__ __forceinline__ void colsum_tile_expanded(int cnt, const double4* __restrict__ ytile, const double (&px)[CA],
                                                      const double (&py)[CA], const double (&pz)[CA], const double (&cx)[CA],
                                                      double (&acc)[CA], const unsigned int* s_tab, int lane_off) {
-#pragma unroll 2
+ESTEP_UNROLL(ESTEP_UNROLL_A)
   for (int t = 0; t < cnt; ++t) {
     const double4 y = ytile[t];
 #pragma unroll
@@ -86,7 +94,7 @@ __device__ __forceinline__ void rowsum_tile_expanded(int cnt, const double4* __r
                                                      const double (&yy)[RB], const double (&yz)[RB], const double (&cy)[RB],
                                                      double (&a0)[RB], double (&a1)[RB], double (&a2)[RB], double (&a3)[RB],
                                                      const unsigned int* s_tab, int lane_off) {
-#pragma unroll 2
+ESTEP_UNROLL(ESTEP_UNROLL_B)
   for (int t = 0; t < cnt; ++t) {
     const double4 xa = xtile[2 * t];
     const double4 xb = xtile[2 * t + 1];
