@@ -40,6 +40,14 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
 
+#ifdef CHOL_TIMING
+// tuning build only (tools/build_variant.sh timing chol.cu -DCHOL_TIMING): clock64 per phase of the panel kernel, block 0
+__device__ unsigned long long chol_timing[8];
+#define CT_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now = clock64(); atomicAdd(&chol_timing[k], (unsigned long long)(now - ct_last)); ct_last = now; } } while (0)
+#else
+#define CT_MARK(k) ((void)0)
+#endif
+
 constexpr int PR = 128;  // panel rows (threads) per CTA
 constexpr size_t PANEL_SMEM = ((size_t)NB * SP + NB + (size_t)PR * SP) * sizeof(double);
 
@@ -86,6 +94,9 @@ __global__ void __launch_bounds__(PR) chol_panel_kernel(int nrows, int j0, int j
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i0 = j0 + jb + blockIdx.x * PR;
   const int cnt = max(0, min(PR, nrows - i0));
+#ifdef CHOL_TIMING
+  long long ct_last = clock64();
+#endif
   // All 96 loads of a thread are issued as asynchronous 8-byte copies before anything waits: the load phase was a
   // quarter of the kernel (ncu: long-scoreboard stalls) when every global load stalled the scheduler's only warp in turn.
   for (int e = tid; e < NB * NB; e += PR) {
@@ -100,6 +111,7 @@ __global__ void __launch_bounds__(PR) chol_panel_kernel(int nrows, int j0, int j
   }
   asm volatile("cp.async.wait_all;\n" ::: "memory");
   __syncthreads();
+  CT_MARK(0);   // loads
   // All four warps run the warp-level pieces redundantly and convergently (no divergent region around the
   // shuffles); only warp 0 stores.  h = 0: (L11, L21, A22 update), h = 1: L22 -- one copy of the unrolled code.
   bool bad = false;
@@ -112,6 +124,7 @@ __global__ void __launch_bounds__(PR) chol_panel_kernel(int nrows, int j0, int j
     double invd = 0.0;
     bad = warp_chol32(a, lane, &invd) || bad;
     __syncthreads();  // every warp has read the block
+    CT_MARK(1);   // chol32
     if (warp == 0) {
 #pragma unroll
       for (int k = 0; k < 32; ++k)
@@ -126,6 +139,7 @@ __global__ void __launch_bounds__(PR) chol_panel_kernel(int nrows, int j0, int j
       for (int k = 0; k < 32; ++k) x[k] = sL[(32 + lane) * SP + k];
       row_trsm<32>(x, sL, sInvD);
       __syncthreads();
+      CT_MARK(2);   // trsm32
       if (warp == 0) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) sL[(32 + lane) * SP + k] = x[k];
@@ -149,6 +163,7 @@ __global__ void __launch_bounds__(PR) chol_panel_kernel(int nrows, int j0, int j
         }
       }
       __syncthreads();
+      CT_MARK(3);   // A22 update
     }
   }
   if (blockIdx.x == 0) {
@@ -158,6 +173,7 @@ __global__ void __launch_bounds__(PR) chol_panel_kernel(int nrows, int j0, int j
       if (i < jb && k <= i) A[(size_t)(j0 + i) * ld + j0 + k] = sL[i * SP + k];
     }
   }
+  CT_MARK(4);   // store of L
   if (cnt > 0) {
     double x[NB];
 #pragma unroll
@@ -167,10 +183,12 @@ __global__ void __launch_bounds__(PR) chol_panel_kernel(int nrows, int j0, int j
     for (int k = 0; k < NB; ++k) sX[tid * SP + k] = x[k];
   }
   __syncthreads();
+  CT_MARK(5);   // panel rows
   for (int e = tid; e < PR * NB; e += PR) {
     const int i = e >> 6, k = e & 63;
     if (i < cnt && k < jb) A[(size_t)(i0 + i) * ld + j0 + k] = sX[i * SP + k];
   }
+  CT_MARK(6);   // store of the panel
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -388,3 +406,15 @@ int32_t chol_backsolve_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld,
 }
 
 }  // namespace gingr
+
+#ifdef CHOL_TIMING
+extern "C" GINGR_API int32_t gingr_debug_chol_timing(unsigned long long* out, int32_t reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, gingr::chol_timing, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(gingr::chol_timing, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
