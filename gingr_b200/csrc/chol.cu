@@ -335,6 +335,30 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(int n, const double
   if (tid == 0) flags[k] = 1;
 }
 
+// n <= 64 (one block): plain right-looking back substitution by 64 threads -- the general kernel would spend 50 us
+// inverting the diagonal block with one thread per column, which only pays when it hides behind the flag waits.
+__global__ void __launch_bounds__(64) chol_backsolve_small_kernel(int n, const double* __restrict__ L, int ld,
+                                                                  const double* __restrict__ z, double* __restrict__ c) {
+  __shared__ double sLs[NB * SP];
+  __shared__ double acc[NB];
+  __shared__ double cj;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += 64) {
+    const int i = e >> 6, j = e & 63;
+    sLs[i * SP + j] = (i < n && j <= i) ? L[(size_t)i * ld + j] : 0.0;
+  }
+  acc[tid] = tid < n ? z[tid] : 0.0;
+  __syncthreads();
+  for (int j = n - 1; j >= 0; --j) {
+    if (tid == j) cj = acc[j] / sLs[j * SP + j];
+    __syncthreads();
+    const double v = cj;
+    if (tid < j) acc[tid] = fma(-sLs[j * SP + tid], v, acc[tid]);   // L^T[tid][j] = L[j][tid]
+    else if (tid == j) c[j] = v;
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -397,6 +421,12 @@ int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, 
 int32_t chol_backsolve_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld, const double* d_z, double* d_c,
                                int* d_flags) {
   const int nb = ceil_div(n, NB);
+  if (nb == 1) {
+    chol_backsolve_small_kernel<<<1, 64, 0, ctx->stream>>>(n, d_L, ld, d_z, d_c);
+    GINGR_LAUNCHED(ctx);
+    GINGR_CUDA_TRY(ctx, cudaGetLastError());
+    return GINGR_OK;
+  }
   if (nb > ctx->num_sms) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "rank too large for the sync-free back solve");
   GINGR_CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, sizeof(int) * nb, ctx->stream));
   chol_backsolve_kernel<<<nb, 256, 0, ctx->stream>>>(n, d_L, ld, d_z, d_c, d_flags);

@@ -406,7 +406,9 @@ int32_t mesh_static_upload(gingr_ctx* ctx, int n, const double* verts_aos_host, 
 static int pick_splits(const gingr_ctx* ctx, int M, int candidates, int tile) {
   const int qblocks = ceil_div(M, QT);
   const int want = ceil_div(ctx->num_sms * 4, qblocks);
-  return std::max(1, std::min(want, ceil_div(candidates, tile)));
+  // small candidate sets: ranges shorter than a shared-memory tile (down to a quarter) so that a 100-vertex problem
+  // is not a few CTAs looping over everything
+  return std::max(1, std::min(want, ceil_div(candidates, std::max(tile / 4, 8))));
 }
 
 int32_t ClosestWorkspace::ensure(gingr_ctx* ctx, int nq, int n_search, int T_search, int T_query_mesh) {
@@ -451,7 +453,7 @@ int32_t nn_vertex_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, const dou
                           const double* d_pts_soa, double* d_d2, int32_t* d_idx, const SpatialGrid* pgrid,
                           const SpatialGrid* order) {
   if (pgrid && pgrid->built) return grid_nn_enqueue(ctx, *pgrid, M, d_q, d_d2, d_idx, order);
-  const int splits = std::min(ws.s_nn, std::max(1, ceil_div(N, PT)));
+  const int splits = std::min(ws.s_nn, std::max(1, ceil_div(N, PT / 4)));
   nn_vertex_kernel<<<dim3(ceil_div(M, QT), splits), QT, 0, ctx->stream>>>(M, d_q, N, d_pts_soa, ws.part_d2.p,
                                                                           ws.part_idx.p);
   GINGR_LAUNCHED(ctx);
@@ -489,8 +491,8 @@ int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const M
   }
   if (tgt.T <= 0 || tpl.T <= 0 || !tpl.normals || !tgt.normals || !tgt.boundary || !tgt.aos)
     return gingr_fail(ctx, GINGR_ERR_ARG, "the mesh flavours of the ICP correspondence need template and target triangles");
-  const int s_surf = std::min(ws.s_surf, std::max(1, ceil_div(tgt.T, TT)));
-  int s_line = std::min(ws.s_line, std::max(1, ceil_div(tpl.T, TT)));
+  const int s_surf = std::min(ws.s_surf, std::max(1, ceil_div(tgt.T, TT / 4)));
+  int s_line = std::min(ws.s_line, std::max(1, ceil_div(tpl.T, TT / 4)));
   const bool tgt_grid = tgt.tgrid && tgt.tgrid->built, tpl_grid = tpl.tgrid && tpl.tgrid->built;
   if (method == GINGR_TRIANGULAR_CLOSEST_POINT && tgt_grid) {
     GINGR_TRY(grid_surface_enqueue(ctx, *tgt.tgrid, M, tpl.aos, tgt.aos, tgt.tri, ws.d2.p, nullptr, ws.cp.p, order));
@@ -554,7 +556,7 @@ int32_t surface_distance_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int nq, c
     GINGR_TRY(grid_surface_enqueue(ctx, *mesh.tgrid, nq, d_q, mesh.aos, mesh.tri, ws.d2.p, nullptr, ws.cp.p, nullptr));
     return GINGR_OK;
   }
-  const int s_surf = std::min(ws.s_surf, std::max(1, ceil_div(mesh.T, TT)));
+  const int s_surf = std::min(ws.s_surf, std::max(1, ceil_div(mesh.T, TT / 4)));
   surface_kernel<<<dim3(ceil_div(nq, QT), s_surf), QT, 0, st>>>(nq, d_q, mesh.n, mesh.soa, mesh.T, mesh.tri, ws.part_d2.p,
                                                                 ws.part_idx.p, ws.part_cp.p);
   GINGR_LAUNCHED(ctx);

@@ -331,7 +331,9 @@ __global__ void __launch_bounds__(256) gram_finish_kernel(int r, int rp, int ld_
   if (tb > ta) return;
   const int tile = ta * (ta + 1) / 2 + tb;
   const int s0 = tile_first[tile], s1 = tile_first[tile + 1];
-  for (int e = threadIdx.x; e < BT * BT; e += 256) {
+  // blockIdx.z slices the elements of the tile: a small matrix has few tiles and would otherwise be finished by a
+  // handful of latency-bound CTAs
+  for (int e = blockIdx.z * 256 + threadIdx.x; e < BT * BT; e += 256 * gridDim.z) {
     const int row = e / BT, col = e % BT;
     const int a = ta * BT + row, b = tb * BT + col;
     if (a >= r || b >= r || b > a) continue;
@@ -479,7 +481,9 @@ int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_ph
 int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_partial, const double* d_sqrt_lambda,
                             double add_identity, int L, const double* d_lm_rows, const double* d_lm_A, int ld_out,
                             double* d_out) {
-  gram_finish_kernel<<<dim3(plan.nt, plan.nt), 256, 0, ctx->stream>>>(plan.r, plan.rp, ld_out, d_partial,
+  const int tiles = plan.nt * (plan.nt + 1) / 2;
+  const int slices = std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
+  gram_finish_kernel<<<dim3(plan.nt, plan.nt, slices), 256, 0, ctx->stream>>>(plan.r, plan.rp, ld_out, d_partial,
                                                                       plan.d_tile_first.p, d_sqrt_lambda, add_identity,
                                                                       L, d_lm_rows, d_lm_A, d_out);
   GINGR_LAUNCHED(ctx);
