@@ -85,6 +85,30 @@ __device__ __forceinline__ void row_trsm(double (&x)[NC], const double* __restri
   }
 }
 
+// x <- x L^-T for ONE row by a whole warp (lane holds x[lane] and x[lane + 32]): the pivot element is scaled by its owner
+// and broadcast by a shuffle, every lane updates its two later elements.  64 short steps instead of the 2016 dependent
+// FMA + shared-memory loads of the thread-per-row form: used when a CTA has only a few rows (the right-hand-side row
+// of a small system).
+__device__ __forceinline__ void warp_row_trsm64(double* __restrict__ xrow /*shared, 64 values*/, const double* __restrict__ sLm,
+                                                const double* __restrict__ sInv, int lane) {
+  double x0 = xrow[lane], x1 = xrow[lane + 32];
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const double xj = __shfl_sync(0xffffffffu, x0 * sInv[j], j);
+    if (lane == j) x0 = xj;
+    else if (lane > j) x0 = fma(-xj, sLm[lane * SP + j], x0);
+    x1 = fma(-xj, sLm[(lane + 32) * SP + j], x1);
+  }
+#pragma unroll 8
+  for (int j = 32; j < 64; ++j) {
+    const double xj = __shfl_sync(0xffffffffu, x1 * sInv[j], j - 32);
+    if (lane + 32 == j) x1 = xj;
+    else if (lane + 32 > j) x1 = fma(-xj, sLm[(lane + 32) * SP + j], x1);
+  }
+  xrow[lane] = x0;
+  xrow[lane + 32] = x1;
+}
+
 __global__ void __launch_bounds__(PR) chol_panel_kernel(int nrows, int j0, int jb, double* __restrict__ A, int ld,
                                                         int* __restrict__ info) {
   extern __shared__ __align__(16) double psm[];
@@ -174,7 +198,9 @@ __global__ void __launch_bounds__(PR) chol_panel_kernel(int nrows, int j0, int j
     }
   }
   CT_MARK(4);   // store of L
-  if (cnt > 0) {
+  if (cnt > 0 && cnt <= 4) {
+    if (warp < cnt) warp_row_trsm64(sX + warp * SP, sL, sInvD, lane);   // a few rows: one warp per row
+  } else if (cnt > 0) {
     double x[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) x[k] = sX[tid * SP + k];
@@ -337,26 +363,36 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(int n, const double
 
 // n <= 64 (one block): plain right-looking back substitution by 64 threads -- the general kernel would spend 50 us
 // inverting the diagonal block with one thread per column, which only pays when it hides behind the flag waits.
-__global__ void __launch_bounds__(64) chol_backsolve_small_kernel(int n, const double* __restrict__ L, int ld,
+__global__ void __launch_bounds__(32) chol_backsolve_small_kernel(int n, const double* __restrict__ L, int ld,
                                                                   const double* __restrict__ z, double* __restrict__ c) {
   __shared__ double sLs[NB * SP];
-  __shared__ double acc[NB];
-  __shared__ double cj;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < NB * NB; e += 64) {
+  __shared__ double sinv[NB];
+  const int lane = threadIdx.x;
+  for (int e = lane; e < NB * NB; e += 32) {
     const int i = e >> 6, j = e & 63;
-    sLs[i * SP + j] = (i < n && j <= i) ? L[(size_t)i * ld + j] : 0.0;
+    sLs[i * SP + j] = (i < n && j <= i) ? L[(size_t)i * ld + j] : (i == j ? 1.0 : 0.0);
   }
-  acc[tid] = tid < n ? z[tid] : 0.0;
-  __syncthreads();
-  for (int j = n - 1; j >= 0; --j) {
-    if (tid == j) cj = acc[j] / sLs[j * SP + j];
-    __syncthreads();
-    const double v = cj;
-    if (tid < j) acc[tid] = fma(-sLs[j * SP + tid], v, acc[tid]);   // L^T[tid][j] = L[j][tid]
-    else if (tid == j) c[j] = v;
-    __syncthreads();
+  __syncwarp();
+  sinv[lane] = 1.0 / sLs[lane * SP + lane];
+  sinv[lane + 32] = 1.0 / sLs[(lane + 32) * SP + lane + 32];
+  __syncwarp();
+  // lane holds the running right-hand sides of unknowns lane and lane + 32; unknown j = L^T row j needs L[j][k], k < j
+  double a0 = lane < n ? z[lane] : 0.0, a1 = lane + 32 < n ? z[lane + 32] : 0.0;
+#pragma unroll 8
+  for (int j = 63; j >= 32; --j) {
+    const double cj = __shfl_sync(0xffffffffu, a1 * sinv[j], j - 32);
+    if (lane + 32 == j) a1 = cj;
+    else if (lane + 32 < j) a1 = fma(-sLs[j * SP + lane + 32], cj, a1);
+    a0 = fma(-sLs[j * SP + lane], cj, a0);
   }
+#pragma unroll 8
+  for (int j = 31; j >= 0; --j) {
+    const double cj = __shfl_sync(0xffffffffu, a0 * sinv[j], j);
+    if (lane == j) a0 = cj;
+    else if (lane < j) a0 = fma(-sLs[j * SP + lane], cj, a0);
+  }
+  if (lane < n) c[lane] = a0;
+  if (lane + 32 < n) c[lane + 32] = a1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -422,7 +458,7 @@ int32_t chol_backsolve_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld,
                                int* d_flags) {
   const int nb = ceil_div(n, NB);
   if (nb == 1) {
-    chol_backsolve_small_kernel<<<1, 64, 0, ctx->stream>>>(n, d_L, ld, d_z, d_c);
+    chol_backsolve_small_kernel<<<1, 32, 0, ctx->stream>>>(n, d_L, ld, d_z, d_c);
     GINGR_LAUNCHED(ctx);
     GINGR_CUDA_TRY(ctx, cudaGetLastError());
     return GINGR_OK;
