@@ -753,26 +753,12 @@ int32_t gingr_mcmc_batch(gingr_registration** regs, int32_t n, int32_t iters, ui
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   ChainStreamPool* sp = nullptr;
   GINGR_TRY(chain_stream_pool(ctx, &sp));
-  constexpr int NS = ChainStreamPool::NS;
-  cudaStream_t* pool = sp->streams;
-  cudaEvent_t fork_ev = sp->fork_ev;
-  cudaEvent_t* join_ev = sp->join_ev;
   for (int k = 0; k < n; ++k) {
     if (!regs[k]->mcmc->primed) GINGR_TRY(mcmc_prime(regs[k]));
     GINGR_TRY(mcmc_capture(regs[k], seed + (uint64_t)k));
   }
-  const int ns = std::min(NS, (int)n);
-  GINGR_CUDA_TRY(ctx, cudaEventRecord(fork_ev, ctx->stream));
-  for (int q = 0; q < ns; ++q) GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(pool[q], fork_ev, 0));
-  for (int it = 0; it < iters; ++it)
-    for (int k = 0; k < n; ++k) {
-      GINGR_CUDA_TRY(ctx, cudaGraphLaunch(regs[k]->mcmc->graph_exec, pool[k % ns]));
-      ctx->launches += regs[k]->mcmc->graph_launches;
-    }
-  for (int q = 0; q < ns; ++q) {
-    GINGR_CUDA_TRY(ctx, cudaEventRecord(join_ev[q], pool[q]));
-    GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, join_ev[q], 0));
-  }
+  GINGR_TRY(replay_chain_graphs(ctx, sp, n, iters, [&](int k) { return regs[k]->mcmc->graph_exec; }, [](int, cudaStream_t) {}));
+  for (int k = 0; k < n; ++k) ctx->launches += (int64_t)iters * regs[k]->mcmc->graph_launches;
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
 }

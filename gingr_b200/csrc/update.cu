@@ -1520,6 +1520,53 @@ static bool same_state(gingr_state a, const gingr_state& b) {
   return memcmp(&a, &b, sizeof(gingr_state)) == 0;
 }
 
+// Pool of streams the batched entry points (gingr_update_batch, gingr_mcmc_batch) replay the chains' graphs on: one pool
+// per host thread and device, created on first use.
+struct ChainStreamPool {
+  static constexpr int NS = 64;   // allocated; GINGR_BATCH_STREAMS (default 16) of them are used
+  cudaStream_t streams[NS] = {nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev[NS] = {nullptr};
+  int device = -1;
+  int used = 16;
+};
+
+static int32_t chain_stream_pool(gingr_ctx* ctx, ChainStreamPool** out) {
+  static thread_local ChainStreamPool pool;
+  if (pool.device != ctx->device) {
+    for (int q = 0; q < ChainStreamPool::NS; ++q) {
+      GINGR_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&pool.streams[q], cudaStreamNonBlocking));
+      GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&pool.join_ev[q], cudaEventDisableTiming));
+    }
+    GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&pool.fork_ev, cudaEventDisableTiming));
+    pool.device = ctx->device;
+    const char* e = getenv("GINGR_BATCH_STREAMS");
+    if (e && atoi(e) > 0) pool.used = std::min(atoi(e), (int)ChainStreamPool::NS);
+  }
+  *out = &pool;
+  return GINGR_OK;
+}
+
+// Replay `iters` times the graphs of n chains on the pool's streams (chain k always on stream k % ns, so its steps stay
+// ordered).  post(k, stream) enqueues what follows a chain's graph (may be empty).  Measured: the replay rate is bound by
+// the device-side launch processing of the graph nodes (about 0.5 us per kernel node), not by the host -- more streams
+// than 16 or several launching host threads do not raise it (profiles/r02_small_problems.md).
+template <typename G, typename P>
+static int32_t replay_chain_graphs(gingr_ctx* ctx, ChainStreamPool* sp, int n, int iters, G&& graph_of, P&& post) {
+  const int ns = std::min(sp->used, n);
+  GINGR_CUDA_TRY(ctx, cudaEventRecord(sp->fork_ev, ctx->stream));
+  for (int q = 0; q < ns; ++q) GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(sp->streams[q], sp->fork_ev, 0));
+  for (int it = 0; it < iters; ++it)
+    for (int k = 0; k < n; ++k) {
+      GINGR_CUDA_TRY(ctx, cudaGraphLaunch(graph_of(k), sp->streams[k % ns]));
+      post(k, sp->streams[k % ns]);
+    }
+  for (int q = 0; q < ns; ++q) {
+    GINGR_CUDA_TRY(ctx, cudaEventRecord(sp->join_ev[q], sp->streams[q]));
+    GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, sp->join_ev[q], 0));
+  }
+  return GINGR_OK;
+}
+
 extern "C" {
 
 int32_t gingr_initialize_state(gingr_registration* g, gingr_state* s, const double* alpha, double* fit_out) {
@@ -1609,29 +1656,6 @@ int32_t gingr_update_chain_sampled(gingr_registration* g, int32_t iters, uint64_
   return GINGR_OK;
 }
 
-// Pool of streams the batched entry points (gingr_update_batch, gingr_mcmc_batch) replay the chains' graphs on: one pool
-// per host thread and device, created on first use.
-struct ChainStreamPool {
-  static constexpr int NS = 16;
-  cudaStream_t streams[NS] = {nullptr};
-  cudaEvent_t fork_ev = nullptr, join_ev[NS] = {nullptr};
-  int device = -1;
-};
-
-static int32_t chain_stream_pool(gingr_ctx* ctx, ChainStreamPool** out) {
-  static thread_local ChainStreamPool pool;
-  if (pool.device != ctx->device) {
-    for (int q = 0; q < ChainStreamPool::NS; ++q) {
-      GINGR_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&pool.streams[q], cudaStreamNonBlocking));
-      GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&pool.join_ev[q], cudaEventDisableTiming));
-    }
-    GINGR_CUDA_TRY(ctx, cudaEventCreateWithFlags(&pool.fork_ev, cudaEventDisableTiming));
-    pool.device = ctx->device;
-  }
-  *out = &pool;
-  return GINGR_OK;
-}
-
 // Independent registrations / MCMC chains (SURVEY.md 8e "replicas only"; BASELINE config 5): every chain is its own
 // gingr_registration (own state and workspaces; model and target handles are shared), its iteration is one captured
 // CUDA graph, and the graphs of different chains are replayed round-robin on a small pool of streams so that the
@@ -1648,10 +1672,6 @@ int32_t gingr_update_batch(gingr_registration** regs, int32_t n, int32_t iters, 
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   ChainStreamPool* sp = nullptr;
   GINGR_TRY(chain_stream_pool(ctx, &sp));
-  constexpr int NS = ChainStreamPool::NS;
-  cudaStream_t* pool = sp->streams;
-  cudaEvent_t fork_ev = sp->fork_ev;
-  cudaEvent_t* join_ev = sp->join_ev;
   // capture (or re-key) every chain's graph on the ctx stream first: capture is not concurrent
   for (int k = 0; k < n; ++k) {
     gingr_registration* g = regs[k];
@@ -1674,21 +1694,9 @@ int32_t gingr_update_batch(gingr_registration** regs, int32_t n, int32_t iters, 
       g->graph_seed = sk;
     }
   }
-  const int ns = std::min(NS, (int)n);
-  GINGR_CUDA_TRY(ctx, cudaEventRecord(fork_ev, ctx->stream));
-  for (int q = 0; q < ns; ++q) GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(pool[q], fork_ev, 0));
-  for (int it = 0; it < iters; ++it)
-    for (int k = 0; k < n; ++k) {  // chain k always runs on stream k % ns: its iterations stay ordered
-      gingr_registration* g = regs[k];
-      cudaStream_t st = pool[k % ns];
-      GINGR_CUDA_TRY(ctx, cudaGraphLaunch(g->graph_exec, st));
-      bump_iteration_kernel<<<1, 1, 0, st>>>(g->is.p);
-      ctx->launches += g->graph_launches + 1;
-    }
-  for (int q = 0; q < ns; ++q) {
-    GINGR_CUDA_TRY(ctx, cudaEventRecord(join_ev[q], pool[q]));
-    GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, join_ev[q], 0));
-  }
+  GINGR_TRY(replay_chain_graphs(ctx, sp, n, iters, [&](int k) { return regs[k]->graph_exec; },
+                                [&](int k, cudaStream_t st) { bump_iteration_kernel<<<1, 1, 0, st>>>(regs[k]->is.p); }));
+  for (int k = 0; k < n; ++k) ctx->launches += (int64_t)iters * (regs[k]->graph_launches + 1);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
 }
