@@ -301,6 +301,29 @@ __global__ void __launch_bounds__(256) mcmc_decide_kernel(McmcDev p, int r, cons
   mi[MI_STEP] += 1;
 }
 
+// Several (conditional) copies in one launch: the replay rate of a chain's step graph is bound by its node count
+// (profiles/r02_small_problems.md), so the snapshot and the accept / reject / best-sample copies are one node each.
+// Segment q copies n 8-byte words when (flag == nullptr) or ((*flag != 0) == when).
+struct CopySegments {
+  static constexpr int MAXSEG = 12;
+  int count = 0;
+  const int* flag[MAXSEG];
+  int when[MAXSEG];
+  double* dst[MAXSEG];
+  const double* src[MAXSEG];
+  unsigned long long n[MAXSEG];
+  void add(const int* f, int w, void* d, const void* s_, size_t words) {
+    flag[count] = f; when[count] = w; dst[count] = (double*)d; src[count] = (const double*)s_; n[count] = words; ++count;
+  }
+};
+
+__global__ void __launch_bounds__(256) multi_copy_kernel(CopySegments seg) {
+  for (int q = 0; q < seg.count; ++q) {
+    if (seg.flag[q] && ((*seg.flag[q] != 0) != (seg.when[q] != 0))) continue;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < seg.n[q]; i += (size_t)gridDim.x * 256) seg.dst[q][i] = seg.src[q][i];
+  }
+}
+
 template <typename T>
 __global__ void cond_copy_kernel(const int* __restrict__ flag, int when, T* __restrict__ dst, const T* __restrict__ src, size_t n) {
   if ((*flag != 0) != (when != 0)) return;
@@ -508,19 +531,26 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
   const int M = m->M, r = m->r, rp = m->rp;
   cudaStream_t st = ctx->stream;
   const size_t fac_n = (size_t)(r + 1) * rp;
-  auto d2d = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st); };
-  // 1. snapshot of the current state
-  GINGR_CUDA_TRY(ctx, d2d(mc->s_ds.p, g->ds.p, sizeof(double) * DS_COUNT));
-  GINGR_CUDA_TRY(ctx, d2d(mc->s_is.p, g->is.p, sizeof(int) * IS_COUNT));
-  GINGR_CUDA_TRY(ctx, d2d(mc->s_alpha.p, g->alpha.p, sizeof(double) * r));
-  GINGR_CUDA_TRY(ctx, d2d(mc->s_fit.p, g->fit.p, sizeof(double) * 3 * (size_t)M));
-  GINGR_CUDA_TRY(ctx, d2d(mc->s_fac.p, g->Mx.p, sizeof(double) * fac_n));
+  // 1. snapshot of the current state (one node; the int block travels as 8 doubles)
+  static_assert(IS_COUNT % 2 == 0, "the int state block is copied as doubles");
+  {
+    CopySegments sg;
+    sg.add(nullptr, 0, mc->s_ds.p, g->ds.p, DS_COUNT);
+    sg.add(nullptr, 0, mc->s_is.p, g->is.p, IS_COUNT / 2);
+    sg.add(nullptr, 0, mc->s_alpha.p, g->alpha.p, r);
+    sg.add(nullptr, 0, mc->s_fit.p, g->fit.p, (size_t)3 * M);
+    sg.add(nullptr, 0, mc->s_fac.p, g->Mx.p, fac_n);
+    multi_copy_kernel<<<16, 256, 0, st>>>(sg);
+    GINGR_LAUNCHED(ctx);
+  }
   // 2. which generator of the mixture proposes
   mcmc_choose_kernel<<<1, 1, 0, st>>>(mc->dev, seed, mc->mi.p, mc->md.p);
   GINGR_LAUNCHED(ctx);
   // 3. the informed proposal update(current, probabilistic = true) from the kept posterior ...
   g->sample_counter = mc->mi.p + MI_STEP;
+  g->skip_fit_refresh = true;   // the fit is evaluated once, after the random override
   const int32_t rc = enqueue_update_phase(g, 1, seed);
+  g->skip_fit_refresh = false;
   g->sample_counter = nullptr;
   GINGR_TRY(rc);
   // 4. ... replaced by the chosen random leaf; iteration + 1; fit of the proposal
@@ -544,23 +574,28 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
   mcmc_decide_kernel<<<1, 256, 0, st>>>(mc->dev, r, mc->s_ds.p, mc->s_is.p, mc->s_alpha.p, g->ds.p, g->alpha.p, mc->md.p, mc->mi.p);
   GINGR_LAUNCHED(ctx);
   const int* acc = mc->mi.p + MI_ACCEPT;
-  const int cb = 32;
-  // reject: the working state returns to the snapshot
-  cond_copy_kernel<double><<<1, 128, 0, st>>>(acc, 0, g->ds.p, mc->s_ds.p, (size_t)DS_COUNT);
-  mcmc_restore_ints_kernel<<<1, 1, 0, st>>>(acc, g->is.p, mc->s_is.p);
-  cond_copy_kernel<double><<<ceil_div(r, 256), 256, 0, st>>>(acc, 0, g->alpha.p, mc->s_alpha.p, (size_t)r);
-  cond_copy_kernel<double><<<cb, 256, 0, st>>>(acc, 0, g->fit.p, mc->s_fit.p, (size_t)3 * M);
-  cond_copy_kernel<double><<<cb, 256, 0, st>>>(acc, 0, g->Mx.p, mc->s_fac.p, fac_n);
-  // accept: the proposal's posterior becomes the current one
-  cond_copy_kernel<double><<<cb, 256, 0, st>>>(acc, 1, mc->raw_cur.p, g->Mx_raw.p, fac_n);
-  cond_copy_kernel<double><<<ceil_div(r, 256), 256, 0, st>>>(acc, 1, mc->cm_cur.p, mc->cm_prop.p, (size_t)r);
-  // best sample
   const int* bu = mc->mi.p + MI_BEST_UPDATED;
-  cond_copy_kernel<double><<<1, 128, 0, st>>>(bu, 1, mc->best_ds.p, g->ds.p, (size_t)DS_COUNT);
+  // reject: the working state returns to the snapshot (ints by their own kernel: the retry counter stays);
+  // accept: the proposal's posterior becomes the current one; best sample (only ever an accepted proposal)
+  mcmc_restore_ints_kernel<<<1, 1, 0, st>>>(acc, g->is.p, mc->s_is.p);
+  GINGR_LAUNCHED(ctx);
+  {
+    CopySegments sg;
+    sg.add(acc, 0, g->ds.p, mc->s_ds.p, DS_COUNT);
+    sg.add(acc, 0, g->alpha.p, mc->s_alpha.p, r);
+    sg.add(acc, 0, g->fit.p, mc->s_fit.p, (size_t)3 * M);
+    sg.add(acc, 0, g->Mx.p, mc->s_fac.p, fac_n);
+    sg.add(acc, 1, mc->raw_cur.p, g->Mx_raw.p, fac_n);
+    sg.add(acc, 1, mc->cm_cur.p, mc->cm_prop.p, r);
+    sg.add(bu, 1, mc->best_ds.p, g->ds.p, DS_COUNT);
+    sg.add(bu, 1, mc->best_alpha.p, g->alpha.p, r);
+    sg.add(bu, 1, mc->best_fit.p, g->fit.p, (size_t)3 * M);
+    multi_copy_kernel<<<16, 256, 0, st>>>(sg);
+    GINGR_LAUNCHED(ctx);
+  }
+  // the best sample's int block: after the restore kernel (same stream order), an accepted proposal's ints are in g->is
   cond_copy_kernel<int><<<1, 32, 0, st>>>(bu, 1, mc->best_is.p, g->is.p, (size_t)IS_COUNT);
-  cond_copy_kernel<double><<<ceil_div(r, 256), 256, 0, st>>>(bu, 1, mc->best_alpha.p, g->alpha.p, (size_t)r);
-  cond_copy_kernel<double><<<cb, 256, 0, st>>>(bu, 1, mc->best_fit.p, g->fit.p, (size_t)3 * M);
-  ctx->launches += 11;
+  GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
 }

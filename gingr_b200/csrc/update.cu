@@ -590,6 +590,7 @@ struct gingr_registration {
   DevBuf<double> Mx;           // [(r + 8)][rp]  posterior matrix + rhs row
   DevBuf<double> Mx_raw;       // [(r + 1)][rp]  copy of Mx and rhs before the factorisation (MCMC only, mcmc.cuh)
   bool keep_raw = false;
+  bool skip_fit_refresh = false;        // MH step: the proposal's fit is evaluated after the random override
   const int* sample_counter = nullptr;  // device counter keyed into the posterior-sample stream (null: the iteration)
   struct McmcState* mcmc = nullptr;  // Metropolis-Hastings chain state (mcmc.cuh), created by gingr_mcmc_configure
   DevBuf<double> wrow, u, inst_a, inst_b, newshape, fit_local, gathered, fit;
@@ -1436,7 +1437,7 @@ static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, ui
   // ---- commit, refresh the fit ------------------------------------------------------------------------------------------
   finalize_kernel<<<1, 256, 0, st>>>(r, probabilistic, vec + 5 * rp, g->alpha.p, g->ds.p, g->is.p);
   GINGR_LAUNCHED(ctx);
-  GINGR_TRY(evaluate_fit(g, DS_SCALE, DS_T, DS_R2));
+  if (!g->skip_fit_refresh) GINGR_TRY(evaluate_fit(g, DS_SCALE, DS_T, DS_R2));
   g->rec(1);
   if (g->profiling && g->prof_iters < gingr_registration::EV_MAX_ITERS) g->prof_iters++;
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
