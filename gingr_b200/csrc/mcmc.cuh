@@ -384,6 +384,12 @@ static void mcmc_release(gingr_registration* g) {
   g->mcmc = nullptr;
 }
 
+// gingr_initialize_state / gingr_update / gingr_update_chain* / gingr_update_batch moved the device-resident state: the kept
+// posterior, log values and best sample of the chain no longer describe it, the next gingr_mcmc_chain starts afresh
+static void mcmc_invalidate(gingr_registration* g) {
+  if (g && g->mcmc) g->mcmc->primed = false;
+}
+
 static void mcmc_drop_graph(McmcState* mc) {
   if (mc->graph_exec) cudaGraphExecDestroy(mc->graph_exec);
   mc->graph_exec = nullptr;
@@ -503,6 +509,9 @@ static int32_t mcmc_prime(gingr_registration* g) {
   const int M = m->M, r = m->r, rp = m->rp;
   cudaStream_t st = ctx->stream;
   g->keep_raw = true;
+  // a new chain: step counter (the Philox stream position) and statistics start at zero
+  GINGR_CUDA_TRY(ctx, cudaMemsetAsync(mc->md.p, 0, sizeof(double) * MD_COUNT, st));
+  GINGR_CUDA_TRY(ctx, cudaMemsetAsync(mc->mi.p, 0, sizeof(int) * MI_COUNT, st));
   GINGR_TRY(enqueue_posterior_phase(g));
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(mc->raw_cur.p, g->Mx_raw.p, sizeof(double) * (size_t)(r + 1) * rp, cudaMemcpyDeviceToDevice, st));
   GINGR_TRY(enqueue_posterior_mean_coeffs(g, mc->cm_cur.p));
@@ -760,6 +769,7 @@ int32_t gingr_mcmc_chain(gingr_registration* g, int32_t iters, uint64_t seed) {
   McmcState* mc = g->mcmc;
   if (iters < 0) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_mcmc_chain: bad argument");
   if (!g->state_valid) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_mcmc_chain: no device-resident state (call gingr_initialize_state first)");
+  g->host_mirror_current = false;
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (!mc->primed) GINGR_TRY(mcmc_prime(g));
   const bool graph = graphs_enabled(ctx);
@@ -784,6 +794,7 @@ int32_t gingr_mcmc_batch(gingr_registration** regs, int32_t n, int32_t iters, ui
     if (!regs[k] || regs[k]->ctx != ctx) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_mcmc_batch: chains must share one ctx");
     GINGR_TRY(mcmc_check(regs[k], "gingr_mcmc_batch: bad argument"));
     if (!regs[k]->state_valid) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_mcmc_batch: chain without device-resident state");
+    regs[k]->host_mirror_current = false;
   }
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   ChainStreamPool* sp = nullptr;

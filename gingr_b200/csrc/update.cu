@@ -606,7 +606,8 @@ struct gingr_registration {
   int graph_prob = -1;
   uint64_t graph_seed = 0;
   int64_t graph_launches = 0;
-  bool state_valid = false;
+  bool state_valid = false;        // the device holds a consistent state (pose, alpha, fit)
+  bool host_mirror_current = false;  // ... and last_out / last_alpha are that state (false after device-resident chains)
   gingr_state last_out;
   std::vector<double> last_alpha;
   // profiling: per recorded iteration 14 events
@@ -621,7 +622,8 @@ struct gingr_registration {
 static int32_t model_build_constants(gingr_ctx* ctx, gingr_model* m);
 static int32_t model_upload_topology(gingr_ctx* ctx, gingr_model* m, const int32_t* tri, int T);
 static void drop_graph(gingr_registration* g);
-static void mcmc_release(gingr_registration* g);  // mcmc.cuh
+static void mcmc_release(gingr_registration* g);     // mcmc.cuh
+static void mcmc_invalidate(gingr_registration* g);  // mcmc.cuh: the device state changed outside the MH chain
 
 // reference triangles, vertex -> triangle adjacency and boundary flags of a model (ICP mesh flavours)
 static int32_t model_upload_topology(gingr_ctx* ctx, gingr_model* m, const int32_t* tri, int T) {
@@ -1572,6 +1574,7 @@ extern "C" {
 
 int32_t gingr_initialize_state(gingr_registration* g, gingr_state* s, const double* alpha, double* fit_out) {
   if (!g || !s || !alpha) return gingr_fail(g ? g->ctx : nullptr, GINGR_ERR_ARG, "gingr_initialize_state: bad argument");
+  mcmc_invalidate(g);
   gingr_ctx* ctx = g->ctx;
   const gingr_model* m = g->model;
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1599,6 +1602,7 @@ int32_t gingr_initialize_state(gingr_registration* g, gingr_state* s, const doub
   gingr_state tmp;
   GINGR_TRY(download_state(g, &tmp, nullptr, fit_out));
   g->last_out = *s;
+  g->host_mirror_current = true;
   g->last_alpha.assign(alpha, alpha + m->r);
   g->state_valid = true;
   return GINGR_OK;
@@ -1608,12 +1612,13 @@ int32_t gingr_update(gingr_registration* g, const gingr_state* state_in, const d
                      uint64_t seed, gingr_state* state_out, double* alpha_out, double* fit_out) {
   if (!g || !state_in || !alpha_in || !state_out || !alpha_out)
     return gingr_fail(g ? g->ctx : nullptr, GINGR_ERR_ARG, "gingr_update: bad argument");
+  mcmc_invalidate(g);
   gingr_ctx* ctx = g->ctx;
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const gingr_model* m = g->model;
   // Re-seed the device state unless the caller hands back exactly what the previous call returned
   // (then the device-resident fit is already the fit of this state).
-  const bool resume = g->state_valid && same_state(*state_in, g->last_out) &&
+  const bool resume = g->state_valid && g->host_mirror_current && same_state(*state_in, g->last_out) &&
                       memcmp(alpha_in, g->last_alpha.data(), sizeof(double) * m->r) == 0;
   if (!resume) {
     GINGR_TRY(upload_state(g, state_in, alpha_in));
@@ -1626,6 +1631,7 @@ int32_t gingr_update(gingr_registration* g, const gingr_state* state_in, const d
   GINGR_TRY(run_iteration(g, probabilistic != 0, seed));
   GINGR_TRY(download_state(g, state_out, alpha_out, fit_out));
   g->last_out = *state_out;
+  g->host_mirror_current = true;
   g->last_alpha.assign(alpha_out, alpha_out + m->r);
   g->state_valid = true;
   return GINGR_OK;
@@ -1635,6 +1641,8 @@ int32_t gingr_update_chain(gingr_registration* g, int32_t iters) {
   if (!g || iters < 0) return gingr_fail(g ? g->ctx : nullptr, GINGR_ERR_ARG, "gingr_update_chain: bad argument");
   gingr_ctx* ctx = g->ctx;
   if (!g->state_valid) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_chain: no device-resident state (call gingr_initialize_state / gingr_update first)");
+  mcmc_invalidate(g);
+  g->host_mirror_current = false;
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   for (int k = 0; k < iters; ++k) {
     GINGR_TRY(run_iteration(g, 0, 0));
@@ -1648,6 +1656,8 @@ int32_t gingr_update_chain_sampled(gingr_registration* g, int32_t iters, uint64_
   if (!g || iters < 0) return gingr_fail(g ? g->ctx : nullptr, GINGR_ERR_ARG, "gingr_update_chain_sampled: bad argument");
   gingr_ctx* ctx = g->ctx;
   if (!g->state_valid) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_chain_sampled: no device-resident state");
+  mcmc_invalidate(g);
+  g->host_mirror_current = false;
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   for (int k = 0; k < iters; ++k) {
     GINGR_TRY(run_iteration(g, 1, seed));  // the Philox counter carries the device iteration number
@@ -1668,6 +1678,8 @@ int32_t gingr_update_batch(gingr_registration** regs, int32_t n, int32_t iters, 
     if (!regs[k] || regs[k]->ctx != ctx) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_batch: chains must share one ctx");
     if (!regs[k]->state_valid) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_batch: chain without device-resident state");
     if (regs[k]->profiling) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_update_batch: profiling is per registration");
+    mcmc_invalidate(regs[k]);
+    regs[k]->host_mirror_current = false;
   }
   if (ctx->nranks != 1) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "gingr_update_batch: chains are replicas, one ctx per GPU without a communicator");
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1743,6 +1755,7 @@ int32_t gingr_state_download(gingr_registration* g, gingr_state* state_out, doub
   GINGR_CUDA_TRY(g->ctx, cudaSetDevice(g->ctx->device));
   GINGR_TRY(download_state(g, state_out, alpha_out, fit_out));
   g->last_out = *state_out;
+  g->host_mirror_current = true;
   if (alpha_out) g->last_alpha.assign(alpha_out, alpha_out + g->model->r);
   else g->state_valid = false;
   return GINGR_OK;

@@ -133,3 +133,30 @@ def test_posterior_with_zero_observations_and_duplicates(ctx, oracle):
     cov = np.eye(3)[None] * noise[:, None, None]
     c_ref, _ = m.posterior_coefficients(pids, pts, cov)
     assert np.max(np.abs(c - c_ref)) < 1e-9 * max(np.max(np.abs(c_ref)), 1e-9)
+
+
+def test_update_with_an_older_state_after_a_device_chain(ctx, oracle):
+    """After gingr_update_chain the device no longer holds the state the host last saw: handing that older state to
+    gingr_update must re-seed the device (not silently resume from the chain's end)."""
+    from gingr_b200 import api, synthetic
+    ref, tri = synthetic.sphere_mesh(120)
+    mean, basis, var = synthetic.make_gpmm(ref, 12, 1)
+    tv, tt = synthetic.sphere_mesh(130)
+    target = synthetic.make_target(tv, 0)
+    dm = api.Model(ctx, ref, mean, basis, var, tri)
+    dt = api.Target(ctx, target, tt)
+    a = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration(w=0.1))
+    b = api.CpdRegistration(ctx, dm, dt, api.CpdConfiguration(w=0.1))
+    st0 = a.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
+    b.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
+    a.updateChain(3)
+    got = a.propose(st0)
+    want = b.propose(st0)
+    assert np.array_equal(got.fit, want.fit) and got.sigma2 == want.sigma2
+    # and the downloaded end state of a chain can be continued
+    a.updateChain(2)
+    end = a.downloadState()
+    nxt = a.propose(end)
+    assert np.all(np.isfinite(nxt.fit)) and nxt.iteration == end.iteration + 1
+    for x in (a, b, dm, dt):
+        x.close()

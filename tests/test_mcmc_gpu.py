@@ -177,6 +177,34 @@ def test_run_probabilistic_returns_best_sample(ctx, oracle):
     reg.close()
 
 
+def test_chain_restarts_after_the_state_changed_outside_it(ctx, oracle):
+    """initializeState / update between two chains: the second chain must start from the new state (fresh posterior, log
+    values, best sample), exactly like a chain on a fresh registration."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 100, 110, 10, seed=2)
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    gs = api.ProbabilisticSettings(uncertainty=1.5, randomMixture=0.5)
+    cfg = api.IcpConfiguration(maxIterations=40, initialSigma=2.0, endSigma=0.5)
+    a = api.IcpRegistration(ctx, dm, dt, cfg)
+    a.configureProbabilistic(gs)
+    st0 = a.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
+    a.mcmcChain(6, 5)
+    st1 = a.propose(a.propose(st0))                      # deterministic updates in between (host state in / out)
+    a.mcmcChain(6, 9)
+    b = api.IcpRegistration(ctx, dm, dt, cfg)
+    b.configureProbabilistic(gs)
+    b.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
+    b.propose(b.propose(st0))
+    b.mcmcChain(6, 9)
+    sa, sb = a.downloadState(), b.downloadState()
+    assert np.array_equal(sa.fit, sb.fit) and np.array_equal(sa.modelParameters.shape, sb.modelParameters.shape)
+    va, ca = a.mcmcStats()
+    vb, cb = b.mcmcStats()
+    assert np.array_equal(va[:2], vb[:2]) and va[8] == vb[8]          # current and best log values
+    a.close(); b.close(); dm.close(); dt.close()
+
+
 def test_mcmc_argument_errors(ctx, oracle):
     from gingr_b200 import api
     reg, oalgo, ost, diag, keep = _setup(ctx, oracle, "icp", M=60, N=70, r=6)
