@@ -509,6 +509,7 @@ static int32_t mcmc_prime(gingr_registration* g) {
   const int M = m->M, r = m->r, rp = m->rp;
   cudaStream_t st = ctx->stream;
   g->keep_raw = true;
+  mcmc_drop_graph(mc);   // the captured step bakes in the state's stepLength (toMesh of the transition density)
   // a new chain: step counter (the Philox stream position) and statistics start at zero
   GINGR_CUDA_TRY(ctx, cudaMemsetAsync(mc->md.p, 0, sizeof(double) * MD_COUNT, st));
   GINGR_CUDA_TRY(ctx, cudaMemsetAsync(mc->mi.p, 0, sizeof(int) * MI_COUNT, st));
