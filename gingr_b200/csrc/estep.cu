@@ -58,7 +58,7 @@ constexpr int TILE_COLS = 256; // columns staged per shared-memory tile in sweep
 // scal[7] = upper bound of d2 from the coordinate ranges of both clouds (<= 0 / non-finite: unknown).
 __device__ __forceinline__ bool estep_safe_range(const double* __restrict__ scal) {
   const double sigma2 = scal[0], d2max = scal[7];
-  return sigma2 > 0.0 && d2max > 0.0 && d2max * (64.0 * 1.4426950408889634074 / (2.0 * sigma2)) < 2147221504.0;
+  return sigma2 > 0.0 && d2max > 0.0 && d2max * (GAUSS_SCALE * 1.4426950408889634074 / (2.0 * sigma2)) < 2146435072.0;
 }
 
 // Expanded-distance fast path: -k |x - y|^2 = (-k |x|^2) + (-k |y|^2) + (2 k x) . y  needs 1 add + 3 FMA per pair
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(TPB, ESTEP_MINB_A) estep_colsum_kernel(int M, 
   gauss_tab_fill(s_tab, threadIdx.x, TPB);
   const int lane_off = (threadIdx.x & 15) * 8;
   const double sigma2 = scal[0];
-  const double negk = -64.0 * 1.4426950408889634074 / (2.0 * sigma2);
+  const double negk = -GAUSS_SCALE * 1.4426950408889634074 / (2.0 * sigma2);
   const int rows_per_split = (M + gridDim.y - 1) / gridDim.y;
   const int i_begin = blockIdx.y * rows_per_split;
   const int i_end = min(M, i_begin + rows_per_split);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(TPB) estep_den_kernel(int N, int splits, const
     double4* o = reinterpret_cast<double4*>(pack + (size_t)j * 8);
     const double wb = w * GAUSS_BIAS_UNSCALE;  // sweep B multiplies 2^64 K by these
     if (estep_expand_ok(scal)) {   // layout of rowsum_tile_expanded
-      const double negk = -64.0 * 1.4426950408889634074 / (2.0 * scal[0]);
+      const double negk = -GAUSS_SCALE * 1.4426950408889634074 / (2.0 * scal[0]);
       o[0] = make_double4(-2.0 * negk * x, -2.0 * negk * y, -2.0 * negk * z, negk * (x * x + y * y + z * z));
       o[1] = make_double4(wb, wb * x, wb * y, wb * z);
     } else {
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(TPB, ESTEP_MINB_B) estep_rowsum_kernel(int M, 
   gauss_tab_fill(s_tab, threadIdx.x, TPB);
   const int lane_off = (threadIdx.x & 15) * 8;
   const double sigma2 = scal[0];
-  const double negk = -64.0 * 1.4426950408889634074 / (2.0 * sigma2);
+  const double negk = -GAUSS_SCALE * 1.4426950408889634074 / (2.0 * sigma2);
   const int cols_per_split = (N + gridDim.y - 1) / gridDim.y;
   const int j_begin = blockIdx.y * cols_per_split;
   const int j_end = min(N, j_begin + cols_per_split);

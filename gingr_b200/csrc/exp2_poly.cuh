@@ -54,20 +54,26 @@ __device__ __forceinline__ double gauss_exp2_biased(double d2, double negk) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Table variant (the one the E-step sweeps use): 2^x = 2^n * 2^(k/64) * 2^(r/64), x*64 = 64 n + k + r, |r| <= 1/2.
-//   tmp = fma(d2, negk64, SHIFT64)        low word = (2048 + n) * 64 + k          negk64 = -64 log2(e) / (2 sigma2)
+// Table variant (the one the E-step sweeps use), N = GAUSS_TAB_N = 256 entries (the names below say "64" for the scaled
+// quantities of the first, 64-entry version): 2^x = 2^n * 2^(k/N) * 2^(r/N), x*N = N n + k + r, |r| <= 1/2.
+//   tmp = fma(d2, negk64, SHIFT64)        low word = (2048 + n) * N + k          negk64 = -N log2(e) / (2 sigma2)
 //   r   = fma(d2, negk64, -(tmp - SHIFT64))
 //   T   = table[k] with its exponent field advanced by n + 64 in ONE integer multiply-add (the table's hi words
 //         are pre-adjusted, exp2_tab.cuh); the table lives in shared memory, replicated 16x so that the 16 lanes of
 //         a half warp hit 16 distinct bank pairs whatever their k (LDS.64 is served per half warp)
-//   K'  = T + (T r) q(r),  q = degree-4 Taylor tail (truncation 3.5e-17)
+//   K'  = T + (T r) q(r),  q = degree-3 Taylor tail of 2^(r/N) (truncation 3.8e-17 with N = 256)
 // 9 FP64 instructions (3 range reduction, 4 Horner, 1 mul, 1 fma) instead of 13, and 7 other instructions instead
 // of 12: the sweeps are bound by the FP64 pipe (2 cycles per warp instruction), so this is a direct 4/20 saving
 // per pair in sweep A and 4/23 in sweep B.
-constexpr int GAUSS_TAB_BYTES = 64 * 16 * 8;
+constexpr int GAUSS_TAB_BYTES = GAUSS_TAB_N * 16 * 8;
+constexpr double GAUSS_SCALE = (double)GAUSS_TAB_N;            // the scaled exponent is x * GAUSS_TAB_N
+constexpr int GAUSS_TAB_SHIFT = 20 - GAUSS_TAB_BITS;            // low word -> exponent field of the table's hi word
+constexpr int GAUSS_TAB_MASK = (GAUSS_TAB_N - 1) << 7;          // byte offset of row k (16 replicas x 8 bytes)
+constexpr int GAUSS_LO_MIN = 963 * GAUSS_TAB_N;                 // n >= -1085
+constexpr unsigned GAUSS_LO_SPAN = 1085u * GAUSS_TAB_N;
 
-__device__ __forceinline__ void gauss_tab_fill(unsigned int* s_tab /*[64*16*2]*/, int tid, int nthreads) {
-  for (int e = tid; e < 64 * 16; e += nthreads) {
+__device__ __forceinline__ void gauss_tab_fill(unsigned int* s_tab /*[N*16*2]*/, int tid, int nthreads) {
+  for (int e = tid; e < GAUSS_TAB_N * 16; e += nthreads) {
     s_tab[2 * e] = GAUSS_EXP2_TAB[e >> 4][0];
     s_tab[2 * e + 1] = GAUSS_EXP2_TAB[e >> 4][1];
   }
@@ -75,8 +81,8 @@ __device__ __forceinline__ void gauss_tab_fill(unsigned int* s_tab /*[64*16*2]*/
 
 // polynomial constants in constant memory: DFMA takes a c[bank][offset] operand directly, whereas 64-bit
 // immediates are re-materialised with UMOV pairs in the loop (3 extra issue slots per evaluation)
-__constant__ double GAUSS_C[8] = {GAUSS_EXP2_A1, GAUSS_EXP2_A2, GAUSS_EXP2_A3, GAUSS_EXP2_A4, GAUSS_EXP2_A5,
-                                  6755399441055744.0 + 131072.0 /* SHIFT = 1.5 * 2^52 + 2048 * 64 */, 0.0, 0.0};
+__constant__ double GAUSS_C[8] = {GAUSS_EXP2_A1, GAUSS_EXP2_A2, GAUSS_EXP2_A3, GAUSS_EXP2_A4, 0.0,
+                                  6755399441055744.0 + 2048.0 * GAUSS_TAB_N /* SHIFT = 1.5 * 2^52 + 2048 N */, 0.0, 0.0};
 
 // Returns K' = 2^64 * 2^(negk64 * d2 / 64), or exactly 0 when K underflows (n < -1085) or the argument is out of
 // range.  The zero is SELECTED (not a skipped accumulation): the reference evaluates 0 * (1 / 0) = NaN for a column
@@ -93,17 +99,16 @@ __device__ __forceinline__ double gauss_exp2_tab(double d2, double negk64, const
   const int hi = __double2hiint(tmp);
   const double nf = tmp - SHIFT;
   const double r = fma(d2, negk64, -nf);
-  const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(s_tab) + (((lo << 7) & 0x1F80) | lane_off));
-  const double T = __hiloint2double((int)(((unsigned)lo << 14) + t.y), (int)t.x);
-  double p = GAUSS_C[4];
-  p = fma(p, r, GAUSS_C[3]);
+  const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(s_tab) + (((lo << 7) & GAUSS_TAB_MASK) | lane_off));
+  const double T = __hiloint2double((int)(((unsigned)lo << GAUSS_TAB_SHIFT) + t.y), (int)t.x);
+  double p = GAUSS_C[3];
   p = fma(p, r, GAUSS_C[2]);
   p = fma(p, r, GAUSS_C[1]);
   p = fma(p, r, GAUSS_C[0]);
   const double s = T * r;
   const double v = fma(s, p, T);
   // n in [-1085, 0]  <=>  lo in [963 * 64, 2048 * 64]
-  const bool ok = SAFE ? (lo >= 963 * 64) : ((hi == 0x43380000) && ((unsigned)(lo - 963 * 64) <= 1085u * 64u));
+  const bool ok = SAFE ? (lo >= GAUSS_LO_MIN) : ((hi == 0x43380000) && ((unsigned)(lo - GAUSS_LO_MIN) <= GAUSS_LO_SPAN));
   return __hiloint2double(ok ? __double2hiint(v) : 0, ok ? __double2loint(v) : 0);
 }
 
@@ -116,16 +121,15 @@ __device__ __forceinline__ double gauss_exp2_tab_u(double u, const unsigned int*
   const int lo = __double2loint(tmp);  // (2048 + n) * 64 + k
   const double nf = tmp - SHIFT;
   const double r = u - nf;
-  const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(s_tab) + (((lo << 7) & 0x1F80) | lane_off));
-  const double T = __hiloint2double((int)(((unsigned)lo << 14) + t.y), (int)t.x);
-  double p = GAUSS_C[4];
-  p = fma(p, r, GAUSS_C[3]);
+  const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(s_tab) + (((lo << 7) & GAUSS_TAB_MASK) | lane_off));
+  const double T = __hiloint2double((int)(((unsigned)lo << GAUSS_TAB_SHIFT) + t.y), (int)t.x);
+  double p = GAUSS_C[3];
   p = fma(p, r, GAUSS_C[2]);
   p = fma(p, r, GAUSS_C[1]);
   p = fma(p, r, GAUSS_C[0]);
   const double s = T * r;
   const double v = fma(s, p, T);
-  const bool ok = lo >= 963 * 64;
+  const bool ok = lo >= GAUSS_LO_MIN;
   return __hiloint2double(ok ? __double2hiint(v) : 0, ok ? __double2loint(v) : 0);
 }
 
