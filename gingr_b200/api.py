@@ -597,6 +597,13 @@ def update_batch(chains: Sequence[GingrAlgorithm], iters: int, probabilistic: bo
     ctx.check(ctx._lib.gingr_update_batch(arr, len(chains), int(iters), int(probabilistic), int(seed)))
 
 
+def chain_range(n_chains: int, nranks: int, rank: int) -> Tuple[int, int]:
+    """(first, count) of the chains rank `rank` runs when n_chains independent chains are divided over nranks processes
+    (replicas only, no collective).  Chain k always uses seed + k, whichever rank runs it, so the division
+    does not change any chain."""
+    return shard_range(n_chains, nranks, rank)
+
+
 def mcmc_batch(chains: Sequence[GingrAlgorithm], iters: int, seed: int = 0):
     """`iters` MH steps of every chain (independent chains on one ctx; gingr_mcmc_batch); chain k uses seed + k."""
     ctx = chains[0].ctx

@@ -121,3 +121,75 @@ def test_multi_gpu_update_matches_oracle(world):
     sys.stdout.write(p.stdout[-4000:])
     sys.stderr.write(p.stderr[-4000:])
     assert p.returncode == 0 and "MGPU_PARITY_OK" in p.stdout
+
+
+def _gloo_chain_worker(rank, world, port, n_chains, steps, q):
+    """Replica-only division of independent MH chains (BASELINE config 5): every rank advances ITS chains with the
+    oracle's chain step (the device consumes the same Philox stream), results are gathered with gloo."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gingr_b200 import api, synthetic
+        from oracle import oracle
+        first, count = api.chain_range(n_chains, world, rank)
+        ref, tri = synthetic.sphere_mesh(40)
+        mean, basis, var = synthetic.make_gpmm(ref, 6, 1)
+        tv, tt = synthetic.sphere_mesh(45)
+        target = synthetic.make_target(tv, 0)
+        om = oracle.Gpmm(ref, mean, basis, var, tri)
+        settings = oracle.McmcSettings(uncertainty=1.5, random_mixture=0.5)
+        out = torch.zeros(n_chains, 3, dtype=torch.float64)
+        for k in range(first, first + count):
+            algo = oracle.IcpAlgorithm(oracle.IcpConfig(initial_sigma=2.0, end_sigma=0.5, max_iterations=20))
+            st = algo.initialize(oracle.initial_state(om, target, tt, global_transformation=oracle.RIGID_TRANSFORMS))
+            lp = oracle.log_value(settings, st)
+            acc = 0
+            for s in range(steps):
+                st, lp, info = oracle.mcmc_step(algo, settings, st, lp, s, seed=100 + k)
+                acc += int(info["accept"])
+            out[k] = torch.tensor([float(acc), lp[0] + lp[1], float(np.sum(st.params.shape))])
+        dist.all_reduce(out)          # every chain was written by exactly one rank
+        q.put((rank, first, count, out.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chain_range_partitions_every_chain_once():
+    from gingr_b200 import api
+    for n in (1, 7, 128, 1024, 1027):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for rank in range(world):
+                first, count = api.chain_range(n, world, rank)
+                seen.extend(range(first, first + count))
+            assert seen == list(range(n))
+            counts = [api.chain_range(n, world, r)[1] for r in range(world)]
+            assert max(counts) - min(counts) <= 1
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_divided_chains_equal_undivided_chains_gloo(world):
+    """The same chains, whichever rank runs them: world-size independence of config 5."""
+    import torch.multiprocessing as mp
+    from oracle import oracle
+    oracle.build()
+    n_chains, steps = 5, 3
+    ctxm = mp.get_context("spawn")
+    results = {}
+    for w in (1, world):
+        q = ctxm.Queue()
+        port = 29700 + 10 * w + (os.getpid() % 100)
+        procs = [ctxm.Process(target=_gloo_chain_worker, args=(k, w, port, n_chains, steps, q)) for k in range(w)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=240) for _ in range(w)]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        results[w] = res[0][3]
+        for r in res:
+            assert np.array_equal(r[3], res[0][3])
+    assert np.array_equal(results[1], results[world])
+    assert len(set(results[1][:, 2].tolist())) > 1          # different seeds, different chains

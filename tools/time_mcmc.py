@@ -22,8 +22,7 @@ if world > 1:
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n_total = n
-n = n_total // world + (1 if rank < n_total % world else 0)
-first_chain = rank * (n_total // world) + min(rank, n_total % world)
+first_chain, n = api.chain_range(n_total, world, rank)
 ctx = api.Context(local)
 ref, tri = synthetic.sphere_mesh(M)
 mean, basis, var = synthetic.make_gpmm(ref, r, 1)
