@@ -89,9 +89,9 @@ __global__ void grid_params_kernel(int n, int cap_cells, const double* __restric
     int nx, ny, nz;
     for (;;) {
       const double m = 1e-6 * h;
-      nx = (int)fmin(floor((ext[0] + 2.0 * m) / h) + 1.0, 2048.0);
-      ny = (int)fmin(floor((ext[1] + 2.0 * m) / h) + 1.0, 2048.0);
-      nz = (int)fmin(floor((ext[2] + 2.0 * m) / h) + 1.0, 2048.0);
+      nx = (int)fmin(floor((ext[0] + 2.0 * m) / h) + 1.0, 1023.0);
+      ny = (int)fmin(floor((ext[1] + 2.0 * m) / h) + 1.0, 1023.0);
+      nz = (int)fmin(floor((ext[2] + 2.0 * m) / h) + 1.0, 1023.0);
       const double padded = (double)((nx + 15) & ~15) * (double)((ny + 15) & ~15) * (double)((nz + 15) & ~15);
       if (padded <= (double)cap_cells &&
           (double)nx * h >= ext[0] + 2.0 * m && (double)ny * h >= ext[1] + 2.0 * m && (double)nz * h >= ext[2] + 2.0 * m)
@@ -551,6 +551,8 @@ __global__ void __launch_bounds__(128) grid_nn_kernel(int M, const double4* __re
 int32_t grid_nn_enqueue(gingr_ctx* ctx, const SpatialGrid& g, int M, const double* d_q, double* d_d2, int32_t* d_idx,
                         const SpatialGrid* order) {
   if (!g.built || g.triangles) return gingr_fail(ctx, GINGR_ERR_ARG, "grid_nn: point grid not built");
+  // thread per query: a candidate point is one distance evaluation, and the warp-per-query variant measured slower
+  // (far queries 1015 vs 696 us, near queries 287 vs 83 us at 100k) -- unlike the surface search below
   grid_nn_kernel<<<ceil_div(M, 128), 128, 0, ctx->stream>>>(M, order_ptr(order, M), d_q, g.n_items, g.params.p, g.cell_start.p, g.pts.p, d_d2, d_idx);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
@@ -622,9 +624,262 @@ __global__ void __launch_bounds__(128) grid_surface_kernel(int M, const double4*
   cp[3 * i] = bx; cp[3 * i + 1] = by; cp[3 * i + 2] = bz;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// closest point on the surface, one WARP per query.
+// The thread-per-query kernel above runs with 3-9 of 32 lanes active in its hot loops (profiles/r01s_ncu_grid_surface.md:
+// every lane walks its own cells and takes its own branches of the exact triangle evaluation).  Here the 32 lanes share
+// one query: cells of the seed cube / the refinement block / the ball are examined 32 at a time, the entries of a passing
+// cell are box-tested 32 at a time, the survivors are COMPACTED into a per-warp queue and evaluated exactly 32 at a time.
+// Same candidates' arithmetic, same conservative bounds, winners by (value, lowest triangle index) across lanes: the
+// results are bit-identical to the scans.
+// ---------------------------------------------------------------------------------------------
+constexpr int WQ_WARPS = 4;      // queries (warps) per CTA
+constexpr int WQ_CAP = 128;      // candidate queue per warp
+
+struct WarpBest {
+  double d, x, y, z;
+  int t;
+};
+
+__device__ __forceinline__ void warp_best_reduce(WarpBest& b) {
+  // lexicographic (d, t) minimum over the lanes, then the winner's point is broadcast
+  double d = b.d;
+  int t = b.t, who = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, d, o);
+    const int ot = __shfl_xor_sync(0xffffffffu, t, o);
+    const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+    if (od < d || (od == d && (unsigned)ot < (unsigned)t)) { d = od; t = ot; who = ow; }
+  }
+  b.d = d; b.t = t;
+  b.x = __shfl_sync(0xffffffffu, b.x, who);
+  b.y = __shfl_sync(0xffffffffu, b.y, who);
+  b.z = __shfl_sync(0xffffffffu, b.z, who);
+}
+
+__global__ void __launch_bounds__(WQ_WARPS * 32) grid_surface_warp_kernel(
+    int M, const double4* __restrict__ order, const double* __restrict__ q, int T, const GridParams* __restrict__ gp,
+    const int32_t* __restrict__ cell_start, const int32_t* __restrict__ entries, const float4* __restrict__ tri_box,
+    const double* __restrict__ verts /*AoS*/, const int32_t* __restrict__ tri, double* __restrict__ d2,
+    int32_t* __restrict__ tri_out, double* __restrict__ cp) {
+  __shared__ int s_queue[WQ_WARPS][WQ_CAP];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int slot = blockIdx.x * WQ_WARPS + w;
+  if (slot >= M) return;   // whole warps leave: no partial-warp collectives below
+  const int i = order ? (int)__double_as_longlong(order[slot].w) : slot;
+  const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+  int* queue = s_queue[w];
+  int qn = 0;   // warp-uniform
+  WarpBest best;   // warp-uniform after every flush
+  best.d = INFINITY; best.x = best.y = best.z = 0.0; best.t = 0x7fffffff;
+  const GridParams g = *gp;
+
+  // exact evaluation of the queued candidates, 32 at a time; the warp's best is re-established afterwards
+  auto flush = [&]() {
+    __syncwarp();
+    WarpBest mine = best;
+    for (int base = 0; base < qn; base += 32) {
+      const int k = base + lane;
+      if (k < qn) {
+        const int t = queue[k];
+        const double* a = verts + 3 * (size_t)tri[3 * t];
+        const double* b = verts + 3 * (size_t)tri[3 * t + 1];
+        const double* c = verts + 3 * (size_t)tri[3 * t + 2];
+        const double va[3] = {a[0], a[1], a[2]}, vb[3] = {b[0], b[1], b[2]}, vc[3] = {c[0], c[1], c[2]};
+        double cx, cy, cz;
+        closest_on_triangle(qx, qy, qz, va, vb, vc, cx, cy, cz);
+        const double dx = qx - cx, dy = qy - cy, dz = qz - cz;
+        const double d = dx * dx + dy * dy + dz * dz;
+        if (d < mine.d || (d == mine.d && (unsigned)t < (unsigned)mine.t)) { mine.d = d; mine.t = t; mine.x = cx; mine.y = cy; mine.z = cz; }
+      }
+    }
+    warp_best_reduce(mine);
+    best = mine;
+    qn = 0;
+    __syncwarp();
+  };
+  // box test (+ home-cell de-duplication for sh >= 0) of the triangles t = first + lane ... and compaction into the queue
+  auto offer = [&](bool valid, int t, int x, int y, int z, int sh) {
+    bool pass = false;
+    if (valid) {
+      const float4 lo = tri_box[2 * t], hi = tri_box[2 * t + 1];
+      const double px = fmin(fmax(qx, (double)lo.x), (double)hi.x), py = fmin(fmax(qy, (double)lo.y), (double)hi.y),
+                   pz = fmin(fmax(qz, (double)lo.z), (double)hi.z);
+      const double ex = qx - px, ey = qy - py, ez = qz - pz;
+      pass = !((ex * ex + ey * ey + ez * ez) * (1.0 - 1e-12) > best.d);
+      if (pass && sh >= 0)
+        pass = (cell_coord(px, g.ox, g.inv_h, g.nx) >> sh) == x && (cell_coord(py, g.oy, g.inv_h, g.ny) >> sh) == y &&
+               (cell_coord(pz, g.oz, g.inv_h, g.nz) >> sh) == z;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (pass) queue[qn + __popc(m & ((1u << lane) - 1u))] = t;
+    qn += __popc(m);
+    if (qn > WQ_CAP - 32) flush();
+  };
+  auto offer_entries = [&](int e0, int e1, int x, int y, int z, int sh) {
+    for (int base = e0; base < e1; base += 32) {
+      const int e = base + lane;
+      const bool valid = e < e1;
+      offer(valid, valid ? entries[e] : 0, x, y, z, sh);
+    }
+  };
+
+  bool done = false;
+  const bool finite_q = isfinite(qx) && isfinite(qy) && isfinite(qz);
+  if (finite_q && !g.overflow) {
+    const int fx = cell_coord(qx, g.ox, g.inv_h, g.nx), fy = cell_coord(qy, g.oy, g.inv_h, g.ny),
+              fz = cell_coord(qz, g.oz, g.inv_h, g.nz);
+    // ---- seed: nearest occupied cell in the cubes around the query's cell, level by level ------------------------
+    bool seeded = false;
+    for (int l = 0; l < LEVELS && !seeded; ++l) {
+      const int sh = 2 * l;
+      const int cx = fx >> sh, cy = fy >> sh, cz = fz >> sh;
+      const int nx = ((g.nx - 1) >> sh) + 1, ny = ((g.ny - 1) >> sh) + 1, nz = ((g.nz - 1) >> sh) + 1;
+      const double hl = g.h * (double)(1 << sh);
+      const int span = 1 << (3 * sh);
+      for (int k = 0; k <= K_LEVEL[l] && !seeded; ++k) {
+        const int side = 2 * k + 1, vol = side * side * side;
+        double bd = INFINITY;
+        int bc = 0x7fffffff;   // packed (z, y, x) of the lane's nearest occupied cell, 10 bits each
+        for (int c = lane; c < vol; c += 32) {
+          const int x = cx - k + c % side, y = cy - k + (c / side) % side, z = cz - k + c / (side * side);
+          if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) continue;
+          const int ci = cell_index(g, x << sh, y << sh, z << sh);
+          if (cell_start[ci + span] > cell_start[ci]) {
+            const double d = box_dist2(g, qx, qy, qz, x, y, z, hl);
+            const int pc = (z << 20) | (y << 10) | x;
+            if (d < bd || (d == bd && pc < bc)) { bd = d; bc = pc; }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+          const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+          if (od < bd || (od == bd && oc < bc)) { bd = od; bc = oc; }
+        }
+        if (bd < INFINITY) {
+          int bx = bc & 1023, by = (bc >> 10) & 1023, bz = bc >> 20;
+          for (int ll = l - 1; ll >= 0; --ll) {   // descend to the nearest occupied child, 64 children: 2 per lane
+            const int s2 = 2 * ll, sp2 = 1 << (3 * s2);
+            const double h2 = g.h * (double)(1 << s2);
+            double cd = INFINITY;
+            int cc = 0x7fffffff;
+            for (int c = lane; c < 64; c += 32) {
+              const int x = (bx << 2) + (c & 3), y = (by << 2) + ((c >> 2) & 3), z = (bz << 2) + (c >> 4);
+              const int ci = cell_index(g, x << s2, y << s2, z << s2);
+              if (cell_start[ci + sp2] > cell_start[ci]) {
+                const double d = box_dist2(g, qx, qy, qz, x, y, z, h2);
+                const int pc = (z << 20) | (y << 10) | x;
+                if (d < cd || (d == cd && pc < cc)) { cd = d; cc = pc; }
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const double od = __shfl_xor_sync(0xffffffffu, cd, o);
+              const int oc = __shfl_xor_sync(0xffffffffu, cc, o);
+              if (od < cd || (od == cd && oc < cc)) { cd = od; cc = oc; }
+            }
+            bx = cc & 1023; by = (cc >> 10) & 1023; bz = cc >> 20;
+          }
+          const int ci = cell_index(g, bx, by, bz);
+          offer_entries(cell_start[ci], cell_start[ci + 1], bx, by, bz, -1);
+          flush();
+          seeded = true;
+        }
+      }
+    }
+    if (seeded && best.d < INFINITY) {
+      // ---- refine: the 27 fine cells around the candidate's own location, twice -----------------------------------
+      for (int round = 0; round < 2; ++round) {
+        const int ux = cell_coord(best.x, g.ox, g.inv_h, g.nx), uy = cell_coord(best.y, g.oy, g.inv_h, g.ny),
+                  uz = cell_coord(best.z, g.oz, g.inv_h, g.nz);
+        int x = 0, y = 0, z = 0, e0 = 0, e1 = 0;
+        if (lane < 27) {
+          x = ux - 1 + lane % 3; y = uy - 1 + (lane / 3) % 3; z = uz - 1 + lane / 9;
+          if (x >= 0 && y >= 0 && z >= 0 && x < g.nx && y < g.ny && z < g.nz) {
+            const int c = cell_index(g, x, y, z);
+            e0 = cell_start[c]; e1 = cell_start[c + 1];
+            if (e1 > e0 && box_dist2(g, qx, qy, qz, x, y, z, g.h) > best.d) e1 = e0;
+          }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, e1 > e0);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          offer_entries(__shfl_sync(0xffffffffu, e0, src), __shfl_sync(0xffffffffu, e1, src), __shfl_sync(0xffffffffu, x, src),
+                        __shfl_sync(0xffffffffu, y, src), __shfl_sync(0xffffffffu, z, src), 0);
+        }
+        flush();
+      }
+      // ---- ball: every cell whose box is not farther than the best, at the finest level with <= 4096 cells ---------
+      const double R = sqrt(best.d) * (1.0 + 1e-12) + 2.0 * g.margin;
+      const int rx0 = max(cell_coord_raw(qx - R, g.ox, g.inv_h), 0), rx1 = min(cell_coord_raw(qx + R, g.ox, g.inv_h), g.nx - 1);
+      const int ry0 = max(cell_coord_raw(qy - R, g.oy, g.inv_h), 0), ry1 = min(cell_coord_raw(qy + R, g.oy, g.inv_h), g.ny - 1);
+      const int rz0 = max(cell_coord_raw(qz - R, g.oz, g.inv_h), 0), rz1 = min(cell_coord_raw(qz + R, g.oz, g.inv_h), g.nz - 1);
+      for (int l = 0; l < LEVELS && !done; ++l) {
+        const int sh = 2 * l;
+        const int x0 = rx0 >> sh, x1 = rx1 >> sh, y0 = ry0 >> sh, y1 = ry1 >> sh, z0 = rz0 >> sh, z1 = rz1 >> sh;
+        const int sx = x1 - x0 + 1, sy = y1 - y0 + 1, sz = z1 - z0 + 1;
+        if (sx < 1 || sy < 1 || sz < 1) { done = true; break; }   // cannot happen: the candidate lies inside the ball
+        if ((long long)sx * sy * sz > 4096) continue;
+        const int vol = sx * sy * sz;
+        const double hl = g.h * (double)(1 << sh);
+        const int span = 1 << (3 * sh);
+        for (int base = 0; base < vol; base += 32) {
+          const int c = base + lane;
+          int x = 0, y = 0, z = 0, e0 = 0, e1 = 0;
+          if (c < vol) {
+            x = x0 + c % sx; y = y0 + (c / sx) % sy; z = z0 + c / (sx * sy);
+            const int ci = cell_index(g, x << sh, y << sh, z << sh);
+            e0 = cell_start[ci]; e1 = cell_start[ci + span];
+            if (e1 > e0 && box_dist2(g, qx, qy, qz, x, y, z, hl) > best.d) e1 = e0;
+          }
+          unsigned m = __ballot_sync(0xffffffffu, e1 > e0);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            offer_entries(__shfl_sync(0xffffffffu, e0, src), __shfl_sync(0xffffffffu, e1, src), __shfl_sync(0xffffffffu, x, src),
+                          __shfl_sync(0xffffffffu, y, src), __shfl_sync(0xffffffffu, z, src), sh);
+          }
+        }
+        flush();
+        done = true;
+      }
+    }
+  }
+  if (finite_q && !done) {
+    // everything (overflowed grid, nothing near, ball too big): all triangles, 32 at a time
+    qn = 0;
+    best.d = INFINITY; best.x = best.y = best.z = 0.0; best.t = 0x7fffffff;
+    for (int base = 0; base < T; base += 32) offer(base + lane < T, base + lane, 0, 0, 0, -1);
+    flush();
+  }
+  if (lane == 0) {
+    d2[i] = best.d;
+    if (tri_out) tri_out[i] = best.t == 0x7fffffff ? -1 : best.t;
+    cp[3 * i] = best.x; cp[3 * i + 1] = best.y; cp[3 * i + 2] = best.z;
+  }
+}
+
+
+static bool warp_search_wanted() {
+  const char* e = getenv("GINGR_K2_WARP");   // 0: thread-per-query surface search (A/B measurements); default: warp-per-query
+  return !(e && *e && atoi(e) == 0);
+}
+
 int32_t grid_surface_enqueue(gingr_ctx* ctx, const SpatialGrid& g, int M, const double* d_q, const double* d_verts_aos,
                              const int32_t* d_tri, double* d_d2, int32_t* d_tri_out, double* d_cp, const SpatialGrid* order) {
   if (!g.built || !g.triangles) return gingr_fail(ctx, GINGR_ERR_ARG, "grid_surface: triangle grid not built");
+  if (warp_search_wanted()) {
+    grid_surface_warp_kernel<<<ceil_div(M, WQ_WARPS), WQ_WARPS * 32, 0, ctx->stream>>>(
+        M, order_ptr(order, M), d_q, g.n_items, g.params.p, g.cell_start.p, g.entries.p, g.tri_box.p, d_verts_aos, d_tri, d_d2,
+        d_tri_out, d_cp);
+    GINGR_LAUNCHED(ctx);
+    GINGR_CUDA_TRY(ctx, cudaGetLastError());
+    return GINGR_OK;
+  }
   grid_surface_kernel<<<ceil_div(M, 128), 128, 0, ctx->stream>>>(M, order_ptr(order, M), d_q, g.n_items, g.params.p, g.cell_start.p, g.entries.p,
                                                                  g.tri_box.p, d_verts_aos, d_tri, d_d2, d_tri_out, d_cp);
   GINGR_LAUNCHED(ctx);
