@@ -33,14 +33,17 @@ int32_t chol_backsolve_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld,
 
 // ---- vecops.cu -----------------------------------------------------------------------------------
 // out_q[k] = sum_a phi[k][a] v_q[a],  q < nvec (1 or 2), k < rows
+// d_scale (optional): the vectors are multiplied elementwise by it while they are staged (instance(alpha) = Phi (sqrt(lambda) alpha))
 int32_t gemv_rows_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_phi, int nvec, const double* d_v0,
-                          const double* d_v1, double* d_out0, double* d_out1);
+                          const double* d_v1, double* d_out0, double* d_out1, const double* d_scale = nullptr);
 // out[a] = scale[a] * sum_k phi[k][a] u[k]   (scale may be null).  d_part: >= gemvT_splits(ctx, rows) * rp doubles
 int gemvT_splits(const gingr_ctx* ctx, int rows);
 int32_t gemvT_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_phi, const double* d_u,
                       const double* d_scale, double* d_part, double* d_out);
 // y[a] = sum_b A[a][b] x[b]  for a dense r x r row-major matrix (pitch ld)
-int32_t dense_matvec_enqueue(gingr_ctx* ctx, int r, const double* d_A, int ld, const double* d_x, double* d_y);
+// d_flag_in / d_flag_out (optional): set to 1 when x / y holds a non-finite value
+int32_t dense_matvec_enqueue(gingr_ctx* ctx, int r, const double* d_A, int ld, const double* d_x, double* d_y,
+                             int* d_flag_in = nullptr, int* d_flag_out = nullptr);
 // B[c][r] = A[r][c]  (n x n, pitches lda / ldb)
 int32_t transpose_enqueue(gingr_ctx* ctx, int n, const double* d_A, int lda, double* d_B, int ldb);
 

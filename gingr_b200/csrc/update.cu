@@ -469,8 +469,8 @@ __device__ double det3(const double* A) {
 // Umeyama about the origin (LandmarkRegistration.{rigid,similarity}3DLandmarkRegistration, SURVEY.md A4;
 // GingrAlgorithm.scala:227-231, :260-279) and the Euler round trips of the state update (:239-243,
 // GeneralRegistrationState.scala:83-87).  sums: [0] sum |x - mux|^2, [1..9] sum (y - muy)(x - mux)^T
-__global__ void procrustes_solve_kernel(int M, const double* __restrict__ sums, double* __restrict__ ds,
-                                        const int* __restrict__ is) {
+__device__ void procrustes_solve_dev(int M, const double* __restrict__ sums, double* __restrict__ ds,
+                                     const int* __restrict__ is) {
   const int gt = is[IS_GT];
   double R1[9], t[3], c = 1.0;
   if (gt == GINGR_NO_TRANSFORMS) {
@@ -498,6 +498,34 @@ __global__ void procrustes_solve_kernel(int M, const double* __restrict__ sums, 
   for (int i = 0; i < 3; ++i) { ds[DS_NEW_T + i] = t[i]; ds[DS_NEW_EULER + i] = e2[i]; }
   for (int i = 0; i < 9; ++i) ds[DS_R1 + i] = R1[i];
   euler_to_matrix_dev(e2[0], e2[1], e2[2], ds + DS_R2);
+}
+
+__global__ void procrustes_solve_kernel(int M, const double* __restrict__ sums, double* __restrict__ ds,
+                                        const int* __restrict__ is) {
+  procrustes_solve_dev(M, sums, ds, is);
+}
+
+// single rank: sum of the block partials (block order, as procrustes_reduce_kernel) followed by what consumes them:
+// the means after pass 0, the rotation / translation / scale after pass 1
+__global__ void procrustes_reduce_then_kernel(int pass, int nblocks, int M, const double* __restrict__ part,
+                                              double* __restrict__ sums /*[16]*/, double* __restrict__ ds,
+                                              const int* __restrict__ is) {
+  const int q = threadIdx.x;
+  if (q < 10) {
+    double s = 0.0;
+    for (int k = 0; k < nblocks; ++k) s += part[k * 16 + q];
+    sums[q] = s;
+  }
+  __syncwarp();
+  if (q != 0) return;
+  if (pass == 0) {
+    for (int d = 0; d < 3; ++d) {
+      ds[DS_MUX + d] = sums[d] / M;
+      ds[DS_MUY + d] = sums[3 + d] / M;
+    }
+  } else {
+    procrustes_solve_dev(M, sums, ds, is);
+  }
 }
 
 // u_i = R1^T (newshape_i - (R1 (ref + mean)_i + t_new))  for the second `coefficients` call (:234-237)
@@ -837,14 +865,8 @@ namespace gingr {
 // instance coefficients -> local mesh rows: out[3 Ml] = Phi_local (sqrt_lambda * alpha) for 1 or 2 alphas
 static int32_t instance_rows(gingr_ctx* ctx, const gingr_model* m, double* d_vec_scratch, int nvec, const double* d_alpha0,
                              const double* d_alpha1, double* d_out0, double* d_out1) {
-  const int r = m->r, rp = m->rp;
-  scale_vec_kernel<<<ceil_div(r, 256), 256, 0, ctx->stream>>>(r, m->sqrt_lambda.p, d_alpha0, d_vec_scratch);
-  GINGR_LAUNCHED(ctx);
-  if (nvec > 1) {
-    scale_vec_kernel<<<ceil_div(r, 256), 256, 0, ctx->stream>>>(r, m->sqrt_lambda.p, d_alpha1, d_vec_scratch + rp);
-    GINGR_LAUNCHED(ctx);
-  }
-  return gemv_rows_enqueue(ctx, 3 * m->Ml, r, rp, m->phi.p, nvec, d_vec_scratch, d_vec_scratch + rp, d_out0, d_out1);
+  (void)d_vec_scratch;   // sqrt(lambda) * alpha is formed while the vectors are staged in the row pass
+  return gemv_rows_enqueue(ctx, 3 * m->Ml, m->r, m->rp, m->phi.p, nvec, d_alpha0, d_alpha1, d_out0, d_out1, m->sqrt_lambda.p);
 }
 
 // local fit rows -> full fit on every rank
@@ -1264,9 +1286,11 @@ static int32_t evaluate_fit(gingr_registration* g, int off_s, int off_t, int off
   GINGR_TRY(instance_rows(ctx, m, g->vec.p + 6 * m->rp, 1, g->alpha.p, nullptr, g->inst_a.p, nullptr));
   if (m->Ml > 0) {
     fit_from_instance_kernel<<<ceil_div(m->Ml, 256), 256, 0, ctx->stream>>>(m->m0, m->Ml, m->ref.p, m->mean.p, g->inst_a.p,
-                                                                            g->ds.p, off_s, off_t, off_R, g->fit_local.p);
+                                                                            g->ds.p, off_s, off_t, off_R,
+                                                                            ctx->nranks == 1 ? g->fit.p : g->fit_local.p);
     GINGR_LAUNCHED(ctx);
   }
+  if (ctx->nranks == 1) return GINGR_OK;   // one rank owns every row: the fit was written in place
   return gather_fit(ctx, m, g->fit_local.p, g->gathered.p, g->fit.p);
 }
 
@@ -1403,10 +1427,9 @@ static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, ui
   }
   GINGR_TRY(chol_backsolve_enqueue(ctx, r, g->Mx.p, rp, rhs, vec, g->flags.p));
   g->rec(9);
-  check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, vec, g->is.p + IS_FAIL_POST);
-  GINGR_LAUNCHED(ctx);
   // ---- alpha* = coefficients(posterior mean) = W0 S c ; combine ---------------------------------------------
-  GINGR_TRY(dense_matvec_enqueue(ctx, r, m->S.p, rp, vec, vec + rp));
+  // (a non-finite c is flagged by the first product, a non-finite alpha_new by the last: no separate launches)
+  GINGR_TRY(dense_matvec_enqueue(ctx, r, m->S.p, rp, vec, vec + rp, g->is.p + IS_FAIL_POST, nullptr));
   GINGR_TRY(dense_matvec_enqueue(ctx, r, m->W0.p, rp, vec + rp, vec + 2 * rp));
   combine_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, g->alpha.p, vec + 2 * rp, g->ds.p, vec + 3 * rp);
   GINGR_LAUNCHED(ctx);
@@ -1416,16 +1439,20 @@ static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, ui
   for (int pass = 0; pass < 2; ++pass) {
     procrustes_sums_kernel<<<pblocks, 256, 0, st>>>(pass, m0, Ml, m->ref.p, m->mean.p, g->inst_a.p, g->inst_b.p, g->ds.p,
                                                     g->newshape.p, g->pro_part.p);
-    procrustes_reduce_kernel<<<1, 32, 0, st>>>(pblocks, 10, g->pro_part.p, g->pro_sums.p);
-    ctx->launches += 2;
-    GINGR_TRY(comm_allreduce_sum(ctx, g->pro_sums.p, 16));
-    if (pass == 0) {
-      procrustes_means_kernel<<<1, 1, 0, st>>>(M, g->pro_sums.p, g->ds.p);
+    GINGR_LAUNCHED(ctx);
+    if (ctx->nranks == 1) {
+      // one rank: the block partials are summed (same fixed order) by the kernel that consumes the sums
+      procrustes_reduce_then_kernel<<<1, 32, 0, st>>>(pass, pblocks, M, g->pro_part.p, g->pro_sums.p, g->ds.p, g->is.p);
+      GINGR_LAUNCHED(ctx);
+    } else {
+      procrustes_reduce_kernel<<<1, 32, 0, st>>>(pblocks, 10, g->pro_part.p, g->pro_sums.p);
+      GINGR_LAUNCHED(ctx);
+      GINGR_TRY(comm_allreduce_sum(ctx, g->pro_sums.p, 16));
+      if (pass == 0) procrustes_means_kernel<<<1, 1, 0, st>>>(M, g->pro_sums.p, g->ds.p);
+      else procrustes_solve_kernel<<<1, 1, 0, st>>>(M, g->pro_sums.p, g->ds.p, g->is.p);
       GINGR_LAUNCHED(ctx);
     }
   }
-  procrustes_solve_kernel<<<1, 1, 0, st>>>(M, g->pro_sums.p, g->ds.p, g->is.p);
-  GINGR_LAUNCHED(ctx);
   // ---- alpha_new = transformedModel.coefficients(newshape) ---------------------------------------------------------
   if (Ml > 0) {
     coeff_residual_kernel<<<ceil_div(Ml, 256), 256, 0, st>>>(m0, Ml, g->newshape.p, m->ref.p, m->mean.p, g->ds.p, g->u.p);
@@ -1433,9 +1460,7 @@ static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, ui
   }
   GINGR_TRY(gemvT_enqueue(ctx, 3 * Ml, r, rp, m->phi.p, g->u.p, m->sqrt_lambda.p, g->gt_part.p, vec + 4 * rp));
   GINGR_TRY(comm_allreduce_sum(ctx, vec + 4 * rp, (size_t)r));
-  GINGR_TRY(dense_matvec_enqueue(ctx, r, m->W0.p, rp, vec + 4 * rp, vec + 5 * rp));
-  check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, vec + 5 * rp, g->is.p + IS_FAIL_COEF);
-  GINGR_LAUNCHED(ctx);
+  GINGR_TRY(dense_matvec_enqueue(ctx, r, m->W0.p, rp, vec + 4 * rp, vec + 5 * rp, nullptr, g->is.p + IS_FAIL_COEF));
   // ---- commit, refresh the fit ------------------------------------------------------------------------------------------
   finalize_kernel<<<1, 256, 0, st>>>(r, probabilistic, vec + 5 * rp, g->alpha.p, g->ds.p, g->is.p);
   GINGR_LAUNCHED(ctx);

@@ -17,11 +17,13 @@ namespace gingr {
 template <int NVEC>
 __global__ void __launch_bounds__(256) gemv_rows_kernel(int rows, int r, int rp, const double* __restrict__ phi,
                                                         const double* __restrict__ v0, const double* __restrict__ v1,
+                                                        const double* __restrict__ scale /*may be null*/,
                                                         double* __restrict__ out0, double* __restrict__ out1) {
   extern __shared__ double sv[];  // [NVEC][r]
   for (int a = threadIdx.x; a < r; a += 256) {
-    sv[a] = v0[a];
-    if (NVEC > 1) sv[r + a] = v1[a];
+    const double sc = scale ? scale[a] : 1.0;   // instance(alpha): v = sqrt(lambda) * alpha, folded into the staging
+    sv[a] = scale ? sc * v0[a] : v0[a];
+    if (NVEC > 1) sv[r + a] = scale ? sc * v1[a] : v1[a];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -92,16 +94,27 @@ __global__ void gemvT_reduce_kernel(int r, int rp, int splits, const double* __r
 }
 
 __global__ void __launch_bounds__(256) dense_matvec_kernel(int r, const double* __restrict__ A, int ld,
-                                                           const double* __restrict__ x, double* __restrict__ y) {
+                                                           const double* __restrict__ x, double* __restrict__ y,
+                                                           int* __restrict__ flag_in, int* __restrict__ flag_out) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * 256 + threadIdx.x) >> 5;
   if (row >= r) return;
   const double* p = A + (size_t)row * ld;
   double s = 0.0;
-  for (int b = lane; b < r; b += 32) s = fma(p[b], x[b], s);
+  bool bad_in = false;
+  for (int b = lane; b < r; b += 32) {
+    const double xb = x[b];
+    bad_in = bad_in || !(fabs(xb) < INFINITY);
+    s = fma(p[b], xb, s);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) y[row] = s;
+  // optional finiteness flags of the operand / the result (what separate check_finite launches did)
+  if (flag_in && row == 0 && bad_in) *flag_in = 1;
+  if (lane == 0) {
+    y[row] = s;
+    if (flag_out && !(fabs(s) < INFINITY)) *flag_out = 1;
+  }
 }
 
 __global__ void transpose_kernel(int n, const double* __restrict__ A, int lda, double* __restrict__ B, int ldb) {
@@ -167,7 +180,7 @@ int32_t add_vectors_enqueue(gingr_ctx* ctx, int n, const double* d_a, const doub
 
 // ---------------------------------------------------------------------------------------------
 int32_t gemv_rows_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_phi, int nvec, const double* d_v0,
-                          const double* d_v1, double* d_out0, double* d_out1) {
+                          const double* d_v1, double* d_out0, double* d_out1, const double* d_scale) {
   if (rows <= 0) return GINGR_OK;
   const int blocks = std::max(1, std::min(ctx->num_sms * 4, ceil_div(rows, 8)));
   const size_t smem = (size_t)nvec * r * sizeof(double);
@@ -184,9 +197,9 @@ int32_t gemv_rows_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double*
     if (smem > 200 * 1024) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "rank too large for gemv_rows shared memory");
   }
   if (nvec == 1)
-    gemv_rows_kernel<1><<<blocks, 256, smem, ctx->stream>>>(rows, r, rp, d_phi, d_v0, d_v0, d_out0, d_out0);
+    gemv_rows_kernel<1><<<blocks, 256, smem, ctx->stream>>>(rows, r, rp, d_phi, d_v0, d_v0, d_scale, d_out0, d_out0);
   else
-    gemv_rows_kernel<2><<<blocks, 256, smem, ctx->stream>>>(rows, r, rp, d_phi, d_v0, d_v1, d_out0, d_out1);
+    gemv_rows_kernel<2><<<blocks, 256, smem, ctx->stream>>>(rows, r, rp, d_phi, d_v0, d_v1, d_scale, d_out0, d_out1);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
@@ -212,8 +225,9 @@ int32_t gemvT_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_p
   return GINGR_OK;
 }
 
-int32_t dense_matvec_enqueue(gingr_ctx* ctx, int r, const double* d_A, int ld, const double* d_x, double* d_y) {
-  dense_matvec_kernel<<<ceil_div(r * 32, 256), 256, 0, ctx->stream>>>(r, d_A, ld, d_x, d_y);
+int32_t dense_matvec_enqueue(gingr_ctx* ctx, int r, const double* d_A, int ld, const double* d_x, double* d_y,
+                             int* d_flag_in, int* d_flag_out) {
+  dense_matvec_kernel<<<ceil_div(r * 32, 256), 256, 0, ctx->stream>>>(r, d_A, ld, d_x, d_y, d_flag_in, d_flag_out);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
