@@ -36,7 +36,8 @@ enum { LEAF_INFORMED = 0, LEAF_ROT_YAW = 1, LEAF_ROT_PITCH = 2, LEAF_ROT_ROLL = 
        LEAF_TRANS_Z = 6, LEAF_SHAPE_0 = 7, LEAF_SHAPE_1 = 8, LEAF_SHAPE_2 = 9, LEAF_COUNT = 10 };
 // doubles of the chain
 enum { MD_LP_CUR = 0 /*prior, distance*/, MD_LP_PROP = 2, MD_TINF_FW = 4, MD_TINF_BW = 5, MD_U_ACCEPT = 6, MD_A = 7,
-       MD_LP_BEST = 8, MD_FW = 9, MD_BW = 10, MD_COUNT = 16 };
+       MD_LP_BEST = 8, MD_FW = 9, MD_BW = 10, MD_TINF_CUR = 11 /*informed density of the current state (stepLength = 1)*/,
+       MD_COUNT = 16 };
 // ints of the chain
 enum { MI_STEP = 0, MI_LEAF = 1, MI_ACCEPT = 2, MI_ACCEPTED = 3, MI_BEST_UPDATED = 4, MI_NAN = 5, MI_INFO2 = 6,
        MI_PROPOSED = 8 /*[LEAF_COUNT]*/, MI_ACCEPTED_LEAF = 18 /*[LEAF_COUNT]*/, MI_COUNT = 32 };
@@ -248,7 +249,7 @@ __device__ double mixture_log_transition(const McmcDev& p, int r, const double* 
   return log(s);
 }
 
-__global__ void __launch_bounds__(256) mcmc_decide_kernel(McmcDev p, int r, const double* __restrict__ s_ds, const int* __restrict__ s_is,
+__global__ void __launch_bounds__(256) mcmc_decide_kernel(McmcDev p, int r, int fw_cached, const double* __restrict__ s_ds, const int* __restrict__ s_is,
                                                           const double* __restrict__ s_alpha, const double* __restrict__ ds,
                                                           const double* __restrict__ alpha, double* __restrict__ md,
                                                           int* __restrict__ mi) {
@@ -270,6 +271,9 @@ __global__ void __launch_bounds__(256) mcmc_decide_kernel(McmcDev p, int r, cons
   }
   if (threadIdx.x != 0) return;
   const bool shape_equal = neq[0] == 0;
+  // stepLength = 1: logTransitionProbability(from, to) only looks at `from` (its fit projected on its own posterior), so
+  // the density of the current state is the one computed when it was proposed (scalismo memoises the posterior alike)
+  if (fw_cached) md[MD_TINF_FW] = md[MD_TINF_CUR];
   const double fw = mixture_log_transition(p, r, s_ds, s_alpha, ds, alpha, md[MD_TINF_FW], red[0], shape_equal);
   const double bw = mixture_log_transition(p, r, ds, alpha, s_ds, s_alpha, md[MD_TINF_BW], red[0], shape_equal);
   md[MD_FW] = fw;
@@ -292,6 +296,7 @@ __global__ void __launch_bounds__(256) mcmc_decide_kernel(McmcDev p, int r, cons
     mi[MI_ACCEPTED_LEAF + mi[MI_LEAF]] += 1;
     md[MD_LP_CUR] = md[MD_LP_PROP];
     md[MD_LP_CUR + 1] = md[MD_LP_PROP + 1];
+    md[MD_TINF_CUR] = md[MD_TINF_BW];
   }
   // BestAndCurrentSampleLogger: the chain state of this iteration (proposal if accepted, else current) vs the best
   const double lp_now = accept ? lp_prop : lp_cur;
@@ -517,6 +522,8 @@ static int32_t mcmc_prime(gingr_registration* g) {
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(mc->raw_cur.p, g->Mx_raw.p, sizeof(double) * (size_t)(r + 1) * rp, cudaMemcpyDeviceToDevice, st));
   GINGR_TRY(enqueue_posterior_mean_coeffs(g, mc->cm_cur.p));
   GINGR_TRY(enqueue_log_value(g, g->fit.p, g->alpha.p, mc->md.p + MD_LP_CUR));
+  if (g->last_out.step_length == 1.0)   // the informed density of the start state (fit on its own posterior)
+    GINGR_TRY(enqueue_log_transition(g, g->Mx_raw.p, mc->cm_cur.p, g->ds.p, g->is.p, g->fit.p, mc->md.p + MD_TINF_CUR));
   // best = current
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(mc->best_ds.p, g->ds.p, sizeof(double) * DS_COUNT, cudaMemcpyDeviceToDevice, st));
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(mc->best_is.p, g->is.p, sizeof(int) * IS_COUNT, cudaMemcpyDeviceToDevice, st));
@@ -573,15 +580,18 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
   GINGR_TRY(enqueue_posterior_mean_coeffs(g, mc->cm_prop.p));
   // 6. informed transition densities, both directions
   const double step_length = g->last_out.step_length;
+  const bool fw_cached = step_length == 1.0;   // MD_TINF_CUR holds it (mcmc_prime / the accepting step)
   const double* to_mesh = nullptr;
-  GINGR_TRY(enqueue_to_mesh(g, step_length, mc->s_fit.p, mc->s_alpha.p, g->alpha.p, &to_mesh));
-  GINGR_TRY(enqueue_log_transition(g, mc->raw_cur.p, mc->cm_cur.p, mc->s_ds.p, mc->s_is.p, to_mesh, mc->md.p + MD_TINF_FW));
+  if (!fw_cached) {
+    GINGR_TRY(enqueue_to_mesh(g, step_length, mc->s_fit.p, mc->s_alpha.p, g->alpha.p, &to_mesh));
+    GINGR_TRY(enqueue_log_transition(g, mc->raw_cur.p, mc->cm_cur.p, mc->s_ds.p, mc->s_is.p, to_mesh, mc->md.p + MD_TINF_FW));
+  }
   GINGR_TRY(enqueue_to_mesh(g, step_length, g->fit.p, g->alpha.p, mc->s_alpha.p, &to_mesh));
   GINGR_TRY(enqueue_log_transition(g, g->Mx_raw.p, mc->cm_prop.p, g->ds.p, g->is.p, to_mesh, mc->md.p + MD_TINF_BW));
   // 7. evaluators of the proposal
   GINGR_TRY(enqueue_log_value(g, g->fit.p, g->alpha.p, mc->md.p + MD_LP_PROP));
   // 8. accept / reject
-  mcmc_decide_kernel<<<1, 256, 0, st>>>(mc->dev, r, mc->s_ds.p, mc->s_is.p, mc->s_alpha.p, g->ds.p, g->alpha.p, mc->md.p, mc->mi.p);
+  mcmc_decide_kernel<<<1, 256, 0, st>>>(mc->dev, r, fw_cached ? 1 : 0, mc->s_ds.p, mc->s_is.p, mc->s_alpha.p, g->ds.p, g->alpha.p, mc->md.p, mc->mi.p);
   GINGR_LAUNCHED(ctx);
   const int* acc = mc->mi.p + MI_ACCEPT;
   const int* bu = mc->mi.p + MI_BEST_UPDATED;
