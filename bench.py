@@ -324,7 +324,10 @@ def run_ours(args):
                     "peak": dfma_peak, "unit": "TFLOP/s", "frac": estep_tf / dfma_peak, "traffic": tr_estep,
                     "ms": t_a + t_b, "algorithmic_flop": estep_flop,
                     "algorithmic_bytes": 24.0 * (M + n_local) + 8.0 * (4 * M + n_local),
-                    "peak_source": "FP64_PEAKS.json dfma_tflops_sustained (measured, tools/fp64_peaks.cu)"}
+                    "peak_source": "FP64_PEAKS.json dfma_tflops_sustained (measured, tools/fp64_peaks.cu)",
+                    "note": "achieved = SURVEY 8(d) ALGORITHMIC count (71 flop per pair, exp = 22) / time; the kernels issue 14 + 17 "
+                            "FP64 instructions per pair (expanded-distance path, table-driven 2^x), ncu FP64 pipe active 78-79 % "
+                            "(profiles/r02_ncu_top_kernels.md)"}
         rl_gram = {"kernel": "gram_ws_kernel (K3, DMMA.8x8x4, warp-specialised, cp.async.bulk)", "bound": "tensor",
                    "achieved": gram_tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": gram_tf / dmma_peak,
                    "traffic": traffic.get("gram_ws_kernel"), "ms": t_g, "algorithmic_flop": gram_flop,
