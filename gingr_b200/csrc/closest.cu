@@ -13,6 +13,7 @@
 // The searches are tiled brute force (queries in registers, candidates staged through shared memory),
 // FP64-pipe bound at 8 M N flop for the vertex search.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "closest.cuh"
@@ -597,9 +598,90 @@ __global__ void __launch_bounds__(128) reverse_fold_kernel(int M, int N, const i
   }
 }
 
+// ---- the same fold in O(N + M) for large problems: lists of the target vertices per template vertex (integer atomics, then
+// each list sorted ascending), summed in ascending j -- the order of the scan above, so the result is bit-identical
+__global__ void rfold_count_kernel(int N, int M, const int32_t* __restrict__ tid, const uint8_t* __restrict__ w,
+                                   int32_t* __restrict__ cnt) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N && w[j] && tid[j] >= 0 && tid[j] < M) atomicAdd(&cnt[tid[j]], 1);
+}
+
+// exclusive scan of cnt[0..M) into start[0..M] by one CTA (M up to a few million: each thread owns a contiguous chunk)
+__global__ void __launch_bounds__(1024) rfold_scan_kernel(int M, const int32_t* __restrict__ cnt, int32_t* __restrict__ start,
+                                                          int32_t* __restrict__ fill) {
+  __shared__ int sh[1024];
+  const int per = (M + 1023) / 1024;
+  const int b0 = threadIdx.x * per, b1 = min(M, b0 + per);
+  int s = 0;
+  for (int i = b0; i < b1; ++i) s += cnt[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = sh[threadIdx.x] - s;
+  for (int i = b0; i < b1; ++i) {
+    start[i] = run;
+    fill[i] = 0;
+    run += cnt[i];
+  }
+  if (threadIdx.x == 1023) start[M] = sh[1023];
+}
+
+__global__ void rfold_scatter_kernel(int N, int M, const int32_t* __restrict__ tid, const uint8_t* __restrict__ w,
+                                     const int32_t* __restrict__ start, int32_t* __restrict__ fill, int32_t* __restrict__ list) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N && w[j] && tid[j] >= 0 && tid[j] < M) list[start[tid[j]] + atomicAdd(&fill[tid[j]], 1)] = j;
+}
+
+__global__ void rfold_sum_kernel(int M, const int32_t* __restrict__ start, int32_t* __restrict__ list,
+                                 const double* __restrict__ x /*AoS target points*/, double* __restrict__ cp,
+                                 double* __restrict__ wcnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int b = start[i], e = start[i + 1];
+  for (int a = b + 1; a < e; ++a) {   // insertion sort: the lists are short (N / M on average)
+    const int v = list[a];
+    int k = a - 1;
+    while (k >= b && list[k] > v) { list[k + 1] = list[k]; --k; }
+    list[k + 1] = v;
+  }
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  for (int a = b; a < e; ++a) {
+    const int j = list[a];
+    sx += x[3 * j]; sy += x[3 * j + 1]; sz += x[3 * j + 2];
+  }
+  const int cnt = e - b;
+  wcnt[i] = (double)cnt;
+  const double inv = cnt > 0 ? 1.0 / (double)cnt : 0.0;
+  cp[3 * i] = sx * inv; cp[3 * i + 1] = sy * inv; cp[3 * i + 2] = sz * inv;
+}
+
 int32_t reverse_fold_enqueue(gingr_ctx* ctx, int M, int N, const int32_t* d_tid, const uint8_t* d_w,
-                             const double* d_target_aos, double* d_cp, double* d_wcnt) {
-  reverse_fold_kernel<<<ceil_div(M, 128), 128, 0, ctx->stream>>>(M, N, d_tid, d_w, d_target_aos, d_cp, d_wcnt);
+                             const double* d_target_aos, double* d_cp, double* d_wcnt, int32_t* d_scratch) {
+  cudaStream_t st = ctx->stream;
+  const char* env = getenv("GINGR_RFOLD_LIST");   // 0 / 1: force the scan / the list form (tests); default: by size
+  const int forced = (env && *env) ? atoi(env) : -1;
+  const bool lists = forced >= 0 ? forced != 0 : (long long)M * (long long)N > (1LL << 24);
+  if (d_scratch && lists) {
+    // scratch: cnt [M], start [M + 1], fill [M], list [N]
+    int32_t* cnt = d_scratch;
+    int32_t* start = cnt + M;
+    int32_t* fill = start + M + 1;
+    int32_t* list = fill + M;
+    GINGR_CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)M, st));
+    rfold_count_kernel<<<ceil_div(N, 256), 256, 0, st>>>(N, M, d_tid, d_w, cnt);
+    rfold_scan_kernel<<<1, 1024, 0, st>>>(M, cnt, start, fill);
+    rfold_scatter_kernel<<<ceil_div(N, 256), 256, 0, st>>>(N, M, d_tid, d_w, start, fill, list);
+    rfold_sum_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, start, list, d_target_aos, d_cp, d_wcnt);
+    ctx->launches += 4;
+    GINGR_CUDA_TRY(ctx, cudaGetLastError());
+    return GINGR_OK;
+  }
+  reverse_fold_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, N, d_tid, d_w, d_target_aos, d_cp, d_wcnt);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

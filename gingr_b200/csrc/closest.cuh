@@ -54,7 +54,8 @@ int32_t nn_vertex_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, const dou
 int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const MeshView& tpl, const MeshView& tgt,
                                    int method);
 int32_t surface_distance_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int nq, const double* d_q, const MeshView& mesh);
+// d_scratch (optional): 3 M + N + 1 ints; with it, large problems (M N > 2^24) take the O(N + M) list form (same result)
 int32_t reverse_fold_enqueue(gingr_ctx* ctx, int M, int N, const int32_t* d_tid, const uint8_t* d_w,
-                             const double* d_target_aos, double* d_cp, double* d_wcnt);
+                             const double* d_target_aos, double* d_cp, double* d_wcnt, int32_t* d_scratch = nullptr);
 
 }  // namespace gingr

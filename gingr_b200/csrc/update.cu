@@ -614,6 +614,7 @@ struct gingr_registration {
   bool use_fit_pgrid = false, use_fit_tgrid = false;
   DevBuf<int32_t> rev_tid;     // [N] reversed ICP: template vertex each target vertex maps back to
   DevBuf<double> rev_cp, rev_wcnt;  // [M][3], [M] folded observations of the reversed direction
+  DevBuf<int32_t> rev_scratch;      // [3 M + N + 1] lists of the O(N + M) fold (large problems)
   DevBuf<double> rows_ext;     // [4 M + 8]  E-step rows + xPx (all-reduced together)
   DevBuf<double> Mx;           // [(r + 8)][rp]  posterior matrix + rhs row
   DevBuf<double> Mx_raw;       // [(r + 1)][rp]  copy of Mx and rhs before the factorisation (MCMC only, mcmc.cuh)
@@ -1140,6 +1141,7 @@ int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, cons
       A(g->rev_tid.alloc((size_t)target->N_total));
       A(g->rev_cp.alloc((size_t)3 * M));
       A(g->rev_wcnt.alloc((size_t)M));
+      A(g->rev_scratch.alloc((size_t)3 * M + target->N_total + 1));
     }
   }
   if (rc == GINGR_OK) { int32_t q = g->gram.build(ctx, 3 * Ml, r, rp); if (q < 0) rc = q; }
@@ -1185,7 +1187,7 @@ int32_t gingr_registration_destroy(gingr_registration* g) {
   g->lml_rows.release();
   g->estep.release(); g->closest.release(); g->gram.release();
   g->fit_pgrid.release(); g->fit_tgrid.release();
-  g->fit_normals.release(); g->fit_soa.release(); g->rev_tid.release(); g->rev_cp.release(); g->rev_wcnt.release();
+  g->fit_normals.release(); g->fit_soa.release(); g->rev_tid.release(); g->rev_cp.release(); g->rev_wcnt.release(); g->rev_scratch.release();
   g->rows_ext.release(); g->Mx.release(); g->wrow.release(); g->u.release(); g->inst_a.release(); g->inst_b.release();
   g->newshape.release(); g->fit_local.release(); g->gathered.release(); g->fit.release(); g->vec.release();
   g->gt_part.release(); g->sums_part.release(); g->pro_part.release(); g->pro_sums.release();
@@ -1370,7 +1372,7 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
       GINGR_TRY(nn_vertex_enqueue(ctx, g->closest, tg->N_total, g->closest.cp.p, M, g->fit_soa.p, g->closest.d2.p,
                                   g->rev_tid.p, fv.pgrid, g->closest.qorder));
       GINGR_TRY(reverse_fold_enqueue(ctx, M, tg->N_total, g->rev_tid.p, g->closest.w.p, tg->aos.p, g->rev_cp.p,
-                                     g->rev_wcnt.p));
+                                     g->rev_wcnt.p, g->rev_scratch.p));
       icp_cp = g->rev_cp.p;
       icp_wcnt = g->rev_wcnt.p;
     }

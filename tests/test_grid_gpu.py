@@ -219,3 +219,33 @@ def test_icp_update_with_grids_is_bit_identical(ctx, method, reverse):
     a, b = _both(run)
     _assert_identical(a, b)
     assert np.all(np.isfinite(b[2]))
+
+
+@pytest.mark.parametrize("method", ["TRIANGULAR_CLOSEST_POINT", "POINTCLOUD_CLOSEST_POINT"])
+def test_reversed_fold_by_lists_equals_the_scan(ctx, method):
+    """closestPointCorrespondenceReversal: the O(N + M) list form of the per-template-vertex fold (large problems) gives the
+    bits of the O(M N) scan (GINGR_RFOLD_LIST forces either)."""
+    from gingr_b200 import api, synthetic
+    M, N, r = 1200, 2600, 24
+    ref, tri = synthetic.sphere_mesh(M)
+    mean, basis, var = synthetic.make_gpmm(ref, r, 1)
+    tv, tt = synthetic.sphere_mesh(N)
+    target = synthetic.make_target(tv, 0)
+    outs = []
+    for forced in ("0", "1"):
+        os.environ["GINGR_RFOLD_LIST"] = forced
+        try:
+            model = api.Model(ctx, ref, mean, basis, var, tri)
+            tgt = api.Target(ctx, target, tt)
+            cfg = api.IcpConfiguration(initialSigma=2.0, endSigma=0.5, reverseCorrespondenceDirection=True,
+                                       correspondenceMethod=getattr(api, method))
+            reg = api.IcpRegistration(ctx, model, tgt, cfg)
+            reg.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
+            reg.updateChain(3)
+            st = reg.downloadState()
+            outs.append((st.fit, st.modelParameters.shape, np.array([st.sigma2])))
+            reg.close(); model.close(); tgt.close()
+        finally:
+            os.environ.pop("GINGR_RFOLD_LIST", None)
+    _assert_identical(outs[0], outs[1])
+    assert np.all(np.isfinite(outs[1][0]))

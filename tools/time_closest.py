@@ -26,7 +26,8 @@ for method in ("POINTCLOUD_CLOSEST_POINT", "TRIANGULAR_CLOSEST_POINT", "ALONG_NO
         os.environ["GINGR_K2_GRID"] = str(grid)
         model = api.Model(ctx, ref, mean, basis, var, tri)
         tgt = api.Target(ctx, target, tt)
-        cfg = api.IcpConfiguration(maxIterations=10 ** 6, initialSigma=1.0, endSigma=1.0, correspondenceMethod=getattr(api, method))
+        cfg = api.IcpConfiguration(maxIterations=10 ** 6, initialSigma=1.0, endSigma=1.0, correspondenceMethod=getattr(api, method),
+                                   reverseCorrespondenceDirection=os.environ.get("K2_REVERSE") == "1")
         reg = api.IcpRegistration(ctx, model, tgt, cfg)
         reg.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
         reg.updateChain(1)
