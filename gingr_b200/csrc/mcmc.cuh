@@ -77,7 +77,8 @@ __host__ __device__ inline void leaf_weights(double rho, double* w) {
 // (RandomPoseUpdateProposal.scala:40-44); DS_EULER holds (phi, theta, psi)
 __host__ __device__ inline int leaf_euler_slot(int leaf) { return leaf == LEAF_ROT_YAW ? 2 : leaf == LEAF_ROT_PITCH ? 1 : 0; }
 
-__global__ void mcmc_choose_kernel(McmcDev p, uint64_t seed, int* __restrict__ mi, double* __restrict__ md) {
+// which generator of the mixture proposes (flattened leaves, Generator.scala:31-83) and the uniform of the accept test
+__device__ void mcmc_choose(const McmcDev& p, uint64_t seed, int* __restrict__ mi, double* __restrict__ md) {
   uint32_t x[4];
   philox4x32_10(0u, (uint32_t)mi[MI_STEP], 1u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
   const double uc = u53(x[0], x[1]);
@@ -100,9 +101,12 @@ __global__ void mcmc_choose_kernel(McmcDev p, uint64_t seed, int* __restrict__ m
 __global__ void __launch_bounds__(256) mcmc_random_override_kernel(McmcDev p, uint64_t seed, int r, const int* __restrict__ mi,
                                                                    const double* __restrict__ s_ds, const int* __restrict__ s_is,
                                                                    const double* __restrict__ s_alpha, double* __restrict__ ds,
-                                                                   int* __restrict__ is, double* __restrict__ alpha) {
-  const int leaf = mi[MI_LEAF];
-  const uint32_t step = (uint32_t)mi[MI_STEP];
+                                                                   int* __restrict__ is, double* __restrict__ alpha,
+                                                                   int* mi_rw, double* __restrict__ md) {
+  if (threadIdx.x == 0) mcmc_choose(p, seed, mi_rw, md);   // the informed update before this kernel does not depend on it
+  __syncthreads();
+  const int leaf = mi_rw[MI_LEAF];
+  const uint32_t step = (uint32_t)mi_rw[MI_STEP];
   if (leaf != LEAF_INFORMED) {
     if (threadIdx.x == 0) {
       ds[DS_SCALE] = s_ds[DS_SCALE];
@@ -127,20 +131,6 @@ __global__ void __launch_bounds__(256) mcmc_random_override_kernel(McmcDev p, ui
 }
 
 // ---- evaluators ---------------------------------------------------------------------------------------------
-// ModelEvaluator: log N(alpha; 0, I_r)
-__global__ void __launch_bounds__(256) mcmc_prior_kernel(int r, const double* __restrict__ alpha, double* __restrict__ out) {
-  __shared__ double red[256];
-  double s = 0.0;
-  for (int a = threadIdx.x; a < r; a += 256) s += alpha[a] * alpha[a];
-  red[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[0] = -0.5 * red[0] - 0.5 * (double)r * LOG_2PI;
-}
-
 __global__ void gather_aos_kernel(int n, const int32_t* __restrict__ ids, const double* __restrict__ src, double* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -151,8 +141,21 @@ __global__ void gather_aos_kernel(int n, const int32_t* __restrict__ ids, const 
 // sum_i logPdf_{N(0, sd)}(sqrt(d2_i)) = sum_i (-d2_i / (2 sd^2) - log(sd sqrt(2 pi)))   (Breeze Gaussian.logPdf);
 // one block, fixed-order tree; out[0] (accumulate ? += : =) weight * sum
 __global__ void __launch_bounds__(256) mcmc_distance_logpdf_kernel(int n, const double* __restrict__ d2, double sd, double weight,
-                                                                   int accumulate, double* __restrict__ out) {
+                                                                   int accumulate, double* __restrict__ out, int r,
+                                                                   const double* __restrict__ alpha /*null: no prior*/) {
   __shared__ double red[256];
+  if (alpha) {   // ModelEvaluator of the same state in the same launch: out[-1] = log N(alpha; 0, I_r)
+    double sa = 0.0;
+    for (int a = threadIdx.x; a < r; a += 256) sa += alpha[a] * alpha[a];
+    red[threadIdx.x] = sa;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[-1] = -0.5 * red[0] - 0.5 * (double)r * LOG_2PI;
+    __syncthreads();
+  }
   const double lognorm = log(sd * 2.5066282746310005024157652848110);
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) {
@@ -183,8 +186,10 @@ __global__ void mcmc_residual_kernel(int M, const double* __restrict__ mesh, con
 
 // B[a][b] = S[a][b] + eps * Mx[a][b] (a, b < r);  row r: rhs = b_proj - S c
 __global__ void mcmc_build_system_kernel(int r, int rp, const double* __restrict__ S, const double* __restrict__ Mx, double eps,
-                                         const double* __restrict__ bproj, const double* __restrict__ Sc, double* __restrict__ B) {
+                                         const double* __restrict__ bproj, const double* __restrict__ Sc, double* __restrict__ B,
+                                         int* __restrict__ info2) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e == 0) info2[0] = 0;   // the factorisation that follows reports a failed pivot here
   if (e >= (r + 1) * rp) return;
   const int a = e / rp, b = e % rp;
   if (a < r) B[e] = b < r ? S[(size_t)a * rp + b] + eps * Mx[(size_t)a * rp + b] : 0.0;
@@ -337,10 +342,15 @@ __global__ void cond_copy_kernel(const int* __restrict__ flag, int when, T* __re
 
 // on reject the working state returns to the snapshot, except the retry counter, which belongs to the algorithm
 // instance and not to the state (GingrAlgorithm.scala:70)
-__global__ void mcmc_restore_ints_kernel(const int* __restrict__ flag, int* __restrict__ is, const int* __restrict__ s_is) {
-  if (*flag != 0) return;
-  for (int k = 0; k < IS_COUNT; ++k)
-    if (k != IS_RETRY) is[k] = s_is[k];
+// ... and the best sample's int block when the accepted proposal is the new best (one launch for both int blocks)
+__global__ void mcmc_restore_ints_kernel(const int* __restrict__ flag, int* __restrict__ is, const int* __restrict__ s_is,
+                                         const int* __restrict__ best_flag, int* __restrict__ best_is) {
+  if (*flag == 0) {
+    for (int k = 0; k < IS_COUNT; ++k)
+      if (k != IS_RETRY) is[k] = s_is[k];
+  }
+  if (*best_flag != 0)
+    for (int k = 0; k < IS_COUNT; ++k) best_is[k] = is[k];
 }
 
 }  // namespace gingr
@@ -409,8 +419,6 @@ static int32_t enqueue_log_value(gingr_registration* g, const double* d_fit, con
   const gingr_target* tg = g->target;
   cudaStream_t st = ctx->stream;
   const int M = m->M, N = tg->N_total;
-  mcmc_prior_kernel<<<1, 256, 0, st>>>(m->r, d_alpha, d_out);
-  GINGR_LAUNCHED(ctx);
   const int mode = mc->cfg.evaluation_mode;
   const double sd = mc->cfg.uncertainty;
   int acc = 0;
@@ -427,7 +435,7 @@ static int32_t enqueue_log_value(gingr_registration* g, const double* d_fit, con
     tv.n = N; tv.aos = tg->aos.p; tv.soa = tg->verts.p; tv.T = tg->T; tv.tri = tg->tri.p; tv.tgrid = tg->tgrid;
     GINGR_TRY(surface_distance_enqueue(ctx, mc->ws_m2t, nq, q, tv));
     mcmc_distance_logpdf_kernel<<<1, 256, 0, st>>>(nq, mc->ws_m2t.d2.p, sd, mode == GINGR_EVAL_SYMMETRIC ? 0.5 : 1.0, acc,
-                                                   d_out + 1);
+                                                   d_out + 1, m->r, d_alpha);
     GINGR_LAUNCHED(ctx);
     acc = 1;
   }
@@ -446,7 +454,7 @@ static int32_t enqueue_log_value(gingr_registration* g, const double* d_fit, con
     }
     GINGR_TRY(surface_distance_enqueue(ctx, mc->ws_t2m, nq, q, fv));
     mcmc_distance_logpdf_kernel<<<1, 256, 0, st>>>(nq, mc->ws_t2m.d2.p, sd, mode == GINGR_EVAL_SYMMETRIC ? 0.5 : 1.0, acc,
-                                                   d_out + 1);
+                                                   d_out + 1, m->r, acc ? nullptr : d_alpha);
     GINGR_LAUNCHED(ctx);
   }
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
@@ -469,9 +477,9 @@ static int32_t enqueue_log_transition(gingr_registration* g, const double* d_raw
   GINGR_LAUNCHED(ctx);
   GINGR_TRY(gemvT_enqueue(ctx, 3 * M, r, rp, m->phi.p, mc->u3m.p, m->sqrt_lambda.p, g->gt_part.p, v));
   GINGR_TRY(dense_matvec_enqueue(ctx, r, m->S.p, rp, d_cmean, v + rp));
-  mcmc_build_system_kernel<<<ceil_div((r + 1) * rp, 256), 256, 0, st>>>(r, rp, m->S.p, d_raw, 1e-5, v, v + rp, mc->sys.p);
+  mcmc_build_system_kernel<<<ceil_div((r + 1) * rp, 256), 256, 0, st>>>(r, rp, m->S.p, d_raw, 1e-5, v, v + rp, mc->sys.p,
+                                                                        mc->mi.p + MI_INFO2);
   GINGR_LAUNCHED(ctx);
-  GINGR_CUDA_TRY(ctx, cudaMemsetAsync(mc->mi.p + MI_INFO2, 0, sizeof(int), st));
   GINGR_TRY(cholesky_enqueue(ctx, r, r + 1, mc->sys.p, rp, mc->mi.p + MI_INFO2));
   GINGR_TRY(chol_backsolve_enqueue(ctx, r, mc->sys.p, rp, mc->sys.p + (size_t)r * rp, v + 2 * rp, g->flags.p));
   GINGR_TRY(dense_matvec_enqueue(ctx, r, d_raw, rp, v + 2 * rp, v + 3 * rp));
@@ -560,9 +568,6 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
     multi_copy_kernel<<<16, 256, 0, st>>>(sg);
     GINGR_LAUNCHED(ctx);
   }
-  // 2. which generator of the mixture proposes
-  mcmc_choose_kernel<<<1, 1, 0, st>>>(mc->dev, seed, mc->mi.p, mc->md.p);
-  GINGR_LAUNCHED(ctx);
   // 3. the informed proposal update(current, probabilistic = true) from the kept posterior ...
   g->sample_counter = mc->mi.p + MI_STEP;
   g->skip_fit_refresh = true;   // the fit is evaluated once, after the random override
@@ -572,7 +577,7 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
   GINGR_TRY(rc);
   // 4. ... replaced by the chosen random leaf; iteration + 1; fit of the proposal
   mcmc_random_override_kernel<<<1, 256, 0, st>>>(mc->dev, seed, r, mc->mi.p, mc->s_ds.p, mc->s_is.p, mc->s_alpha.p, g->ds.p,
-                                                 g->is.p, g->alpha.p);
+                                                 g->is.p, g->alpha.p, mc->mi.p, mc->md.p);
   GINGR_LAUNCHED(ctx);
   GINGR_TRY(evaluate_fit(g, DS_SCALE, DS_T, DS_R2));
   // 5. posterior of the proposal (kept if accepted: the reference memoises it for the next update)
@@ -597,7 +602,7 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
   const int* bu = mc->mi.p + MI_BEST_UPDATED;
   // reject: the working state returns to the snapshot (ints by their own kernel: the retry counter stays);
   // accept: the proposal's posterior becomes the current one; best sample (only ever an accepted proposal)
-  mcmc_restore_ints_kernel<<<1, 1, 0, st>>>(acc, g->is.p, mc->s_is.p);
+  mcmc_restore_ints_kernel<<<1, 1, 0, st>>>(acc, g->is.p, mc->s_is.p, bu, mc->best_is.p);
   GINGR_LAUNCHED(ctx);
   {
     CopySegments sg;
@@ -613,9 +618,6 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
     multi_copy_kernel<<<16, 256, 0, st>>>(sg);
     GINGR_LAUNCHED(ctx);
   }
-  // the best sample's int block: after the restore kernel (same stream order), an accepted proposal's ints are in g->is
-  cond_copy_kernel<int><<<1, 32, 0, st>>>(bu, 1, mc->best_is.p, g->is.p, (size_t)IS_COUNT);
-  GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
 }
