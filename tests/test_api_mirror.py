@@ -1,0 +1,113 @@
+"""The Python mirror of the reference's configuration / state classes (gingr_b200/api.py): names and DEFAULTS must be the
+reference's (checked against the Scala sources when the reference tree is mounted), and the POD round trips are lossless.
+No GPU."""
+import dataclasses
+import os
+import re
+
+import numpy as np
+import pytest
+
+REF = "/root/reference/src/main/scala/gingr"
+needs_reference = pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not mounted (GPU box)")
+
+
+def _case_class_defaults(path, name):
+    """{field: default literal} of `case class name(...)` in a Scala file (fields with a default only)."""
+    src = open(path).read()
+    start = src.index("case class " + name)
+    depth, i = 0, src.index("(", start)
+    j = i
+    while True:
+        if src[j] == "(":
+            depth += 1
+        elif src[j] == ")":
+            depth -= 1
+            if depth == 0:
+                break
+        j += 1
+    body = src[i + 1:j]
+    out = {}
+    for m in re.finditer(r"(?:override val\s+)?(\w+)\s*:\s*[^=,()]+(?:\[[^\]]*\])?\s*=\s*([^,\n]+)", body):
+        out[m.group(1)] = m.group(2).strip()
+    return out
+
+
+def _num(s):
+    return float(s.replace("1e-10", "1e-10"))
+
+
+@needs_reference
+def test_configuration_defaults_are_the_references():
+    from gingr_b200 import api
+    cpd = _case_class_defaults(os.path.join(REF, "api/registration/config/CPD.scala"), "CpdConfiguration")
+    c = api.CpdConfiguration()
+    assert int(cpd["maxIterations"]) == c.maxIterations and _num(cpd["threshold"]) == c.threshold
+    assert cpd["useLandmarkCorrespondence"] == "true" and c.useLandmarkCorrespondence is True
+    assert cpd["initialSigma"] == "None" and c.initialSigma is None
+    assert _num(cpd["w"]) == c.w and _num(cpd["lambda"]) == c.lambda_
+    icp = _case_class_defaults(os.path.join(REF, "api/registration/config/ICP.scala"), "IcpConfiguration")
+    k = api.IcpConfiguration()
+    assert int(icp["maxIterations"]) == k.maxIterations and _num(icp["threshold"]) == k.threshold
+    assert _num(icp["initialSigma"]) == k.initialSigma and _num(icp["endSigma"]) == k.endSigma
+    assert icp["reverseCorrespondenceDirection"] == "false" and k.reverseCorrespondenceDirection is False
+    assert icp["correspondenceMethod"] == "TriangularClosestPoint" and k.correspondenceMethod == api.TRIANGULAR_CLOSEST_POINT
+    assert k.sigmaStep == (k.initialSigma - k.endSigma) / k.maxIterations                      # ICP.scala:65
+    gs = _case_class_defaults(os.path.join(REF, "api/GeneralRegistrationState.scala"), "GeneralRegistrationState")
+    s = api.GeneralRegistrationState(api.ModelFittingParameters(1.0, np.zeros(3), (0.0, 0.0, 0.0), np.zeros(2)), np.zeros((1, 3)))
+    assert _num(gs["sigma2"]) == s.sigma2 and _num(gs["stepLength"]) == s.stepLength
+    assert gs["globalTransformation"] == "RigidTransforms" and s.globalTransformation == api.RIGID_TRANSFORMS
+    assert int(gs["iteration"]) == s.iteration and gs["status"] == "FittingStatuses.None" and s.status == api.STATUS_NONE
+    ps = _case_class_defaults(os.path.join(REF, "api/GingrAlgorithm.scala"), "ProbabilisticSettings")
+    assert _num(ps["randomMixture"]) == api.ProbabilisticSettings().randomMixture
+    gen = open(os.path.join(REF, "api/sampling/Generator.scala")).read()
+    assert "defaultTranslation = 0.1" in gen and "defaultRotation = 0.01" in gen and "Seq(1.0, 0.1, 0.01)" in gen
+    p = api.ProbabilisticSettings()
+    assert p.translationSdev == (0.1, 0.1, 0.1) and p.rotationSdev == (0.01, 0.01, 0.01) and p.shapeSteps == (1.0, 0.1, 0.01)
+
+
+@needs_reference
+def test_enumerations_follow_the_reference_order():
+    from gingr_b200 import api
+    fs = open(os.path.join(REF, "api/FittingStatuses.scala")).read()
+    order = re.search(r"val\s+(\w+)\s*,\s*(\w+)\s*,\s*(\w+)\s*,\s*(\w+)\s*=\s*Value", fs)
+    assert order and [x for x in order.groups()] == ["None", "MaxIteration", "Converged", "ModelFlexibilityError"]
+    assert (api.STATUS_NONE, api.STATUS_MAX_ITERATION, api.STATUS_CONVERGED, api.STATUS_MODEL_FLEXIBILITY_ERROR) == (0, 1, 2, 3)
+    icp = open(os.path.join(REF, "api/registration/config/ICP.scala")).read()
+    names = re.findall(r"case object (\w+ClosestPoint) extends ICPCorrespondenceMethod", icp)
+    assert set(names) == {"TriangularClosestPoint", "AlongNormalClosestPoint", "PointcloudClosestPoint"}
+    modes = open(os.path.join(REF, "api/sampling/evaluators/IndependentPointDistanceEvaluator.scala")).read()
+    assert re.findall(r"case object (\w+) extends EvaluationMode", modes) == ["ModelToTargetEvaluation", "TargetToModelEvaluation", "SymmetricEvaluation"]
+    assert (api.EVAL_MODEL_TO_TARGET, api.EVAL_TARGET_TO_MODEL, api.EVAL_SYMMETRIC) == (0, 1, 2)
+
+
+def test_state_and_config_pod_round_trips():
+    from gingr_b200 import api
+    pars = api.ModelFittingParameters(1.25, np.array([1.0, -2.0, 3.5]), (0.1, -0.2, 0.3), np.linspace(-1, 1, 7))
+    st = api.GeneralRegistrationState(pars, np.zeros((4, 3)), sigma2=2.5, globalTransformation=api.SIMILARITY_TRANSFORMS,
+                                      stepLength=0.5, generatedBy="x", iteration=7, status=api.STATUS_CONVERGED)
+    pod, alpha = st.to_pod()
+    assert pod.rank == 7 and pod.iteration == 7 and pod.status == api.STATUS_CONVERGED and pod.sigma2 == 2.5
+    assert tuple(pod.center) == (0.0, 0.0, 0.0) and pod.step_length == 0.5
+    back = api.GeneralRegistrationState.from_pod(pod, alpha, st.fit, "x")
+    assert back.modelParameters.scale == 1.25 and tuple(back.modelParameters.euler) == (0.1, -0.2, 0.3)
+    assert np.array_equal(back.modelParameters.translation, pars.translation) and np.array_equal(back.modelParameters.shape, pars.shape)
+    assert (back.sigma2, back.stepLength, back.iteration, back.status, back.globalTransformation) == (2.5, 0.5, 7, api.STATUS_CONVERGED, api.SIMILARITY_TRANSFORMS)
+    c = api.CpdConfiguration(maxIterations=33, w=0.2, lambda_=2.0, initialSigma=4.0, useLandmarkCorrespondence=False).to_pod()
+    assert (c.algorithm, c.max_iterations, c.w, c.lambda_, c.has_initial_sigma, c.initial_sigma, c.use_landmark_correspondence) == (api.ALGO_CPD, 33, 0.2, 2.0, 1, 4.0, 0)
+    assert api.CpdConfiguration().to_pod().has_initial_sigma == 0
+    k = api.IcpConfiguration(initialSigma=9.0, endSigma=3.0, reverseCorrespondenceDirection=True,
+                             correspondenceMethod=api.ALONG_NORMAL_CLOSEST_POINT).to_pod()
+    assert (k.algorithm, k.initial_sigma, k.end_sigma, k.reverse_correspondence_direction, k.correspondence_method) == (api.ALGO_ICP, 9.0, 3.0, 1, api.ALONG_NORMAL_CLOSEST_POINT)
+    m = api.ProbabilisticSettings(uncertainty=2.0, mode=api.EVAL_SYMMETRIC, randomMixture=0.25, shapeSteps=(2.0, 0.2, 0.02)).to_pod()
+    assert (m.uncertainty, m.evaluation_mode, m.random_mixture, tuple(m.shape_sdev)) == (2.0, 2, 0.25, (2.0, 0.2, 0.02))
+
+
+def test_convergence_closures_match_the_reference():
+    from gingr_b200 import api
+    a = api.GeneralRegistrationState(api.ModelFittingParameters(1.0, np.zeros(3), (0, 0, 0), np.zeros(1)), np.zeros((1, 3)), sigma2=1.0)
+    b = dataclasses.replace(a, sigma2=1.0 + 5e-11)
+    c = dataclasses.replace(a, sigma2=1.1)
+    cpd, icp = api.CpdConfiguration(), api.IcpConfiguration()
+    assert cpd.converged(a, b, cpd.threshold) and not cpd.converged(a, c, cpd.threshold)      # CPD.scala:106-110
+    assert not icp.converged(a, a, icp.threshold)                                             # ICP.scala:57-58: never
