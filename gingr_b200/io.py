@@ -359,3 +359,107 @@ def read_mesh(path: str) -> Tuple[np.ndarray, np.ndarray]:
     if low.endswith(".ply"):
         return read_ply(path)
     raise ValueError(f"unsupported mesh format: {path}")
+
+
+# ---------------------------------------------------------------------------------------------
+# Statistical model file (the cached GPMM of examples/DemoHelper/DemoDatasetLoader.scala:40-53)
+# ---------------------------------------------------------------------------------------------
+# The reference caches its low-rank models through scalismo's StatisticalModelIO as "<name>_dec-<n>_<kernel>_<pars>.h5.json".
+# That container is defined inside scalismo 1.0-RC1 (build.sbt:40), which is not in the reference tree, and the tree
+# holds no sample file, so its byte layout cannot be pinned here: NOT interchangeable with scalismo's reader until
+# checked against a real file.  What is kept is the statismo group / dataset naming the format descends from
+# (/representer/points [3, M], /representer/cells [3, T], /model/mean [3M], /model/pcaBasis [3M, r] orthonormal,
+# /model/pcaVariance [r], /model/noiseVariance) inside a JSON document, with every dataset stored as
+# {"dtype", "shape", "base64"} of little-endian row-major data.  Doubles are stored as doubles (scalismo narrows to
+# float32), so a reloaded model is bit-identical to the one that was written.
+MODEL_FILE_FORMAT = "gingr_b200.statistical_model.v1"
+
+
+def _dataset(a: np.ndarray, dtype: str) -> dict:
+    import base64
+    arr = np.ascontiguousarray(np.asarray(a).astype(dtype, copy=False))
+    return {"dtype": dtype, "shape": list(arr.shape), "base64": base64.b64encode(arr.tobytes()).decode("ascii")}
+
+
+def _from_dataset(d: dict) -> np.ndarray:
+    import base64
+    arr = np.frombuffer(base64.b64decode(d["base64"]), dtype=d["dtype"])
+    shape = tuple(int(s) for s in d["shape"])
+    if arr.size != int(np.prod(shape, dtype=np.int64)):
+        raise ValueError("statistical model file: dataset size does not match its shape")
+    return arr.reshape(shape).copy()
+
+
+def model_file_name(name: str, decimate: Optional[int], kernel_name: str, printpars: str) -> str:
+    """File name of the cached model, DemoDatasetLoader.scala:46-47 (kernel names / parameter strings:
+    simple/SimpleModels.scala:25-52, e.g. GaussKernel(50, 70) -> ("Gauss", "50.0_70.0"))."""
+    dec = "full" if decimate is None else str(int(decimate))
+    return f"{name}_dec-{dec}_{kernel_name}_{printpars}.h5.json"
+
+
+def gauss_kernel_printpars(scaling: float, sigma: float) -> str:
+    """GaussKernel.printpars (SimpleModels.scala:37-40): scaling.toString + "_" + sigma.toString."""
+    return f"{float(scaling)!r}_{float(sigma)!r}"
+
+
+def write_statistical_model(path: str, reference_points, triangles, mean, basis, variance, noise_variance: float = 0.0) -> None:
+    """StatisticalModelIO.writeStatisticalTriangleMeshModel3D's role (DemoDatasetLoader.scala:51); see the layout note above."""
+    ref = np.asarray(reference_points, dtype=np.float64).reshape(-1, 3)
+    m = ref.shape[0]
+    mean = np.asarray(mean, dtype=np.float64).reshape(-1)
+    basis = np.asarray(basis, dtype=np.float64)
+    variance = np.asarray(variance, dtype=np.float64).reshape(-1)
+    if mean.shape[0] != 3 * m or basis.shape != (3 * m, variance.shape[0]):
+        raise ValueError("statistical model: mean must be [3M], basis [3M, r], variance [r]")
+    tri = np.zeros((0, 3), np.int32) if triangles is None else np.asarray(triangles, dtype=np.int32).reshape(-1, 3)
+    if tri.size and (tri.min() < 0 or tri.max() >= m):
+        raise ValueError("statistical model: triangle index out of range")
+    doc = {
+        "format": MODEL_FILE_FORMAT,
+        "version": {"majorVersion": 0, "minorVersion": 9},
+        "representer": {"name": "gingr_b200", "datasetType": "POLYGON_MESH",
+                        "points": _dataset(ref.T, "<f8"), "cells": _dataset(tri.T, "<i4")},
+        "model": {"mean": _dataset(mean, "<f8"), "pcaBasis": _dataset(basis, "<f8"),
+                  "pcaVariance": _dataset(variance, "<f8"), "noiseVariance": float(noise_variance)},
+    }
+    with open(path, "w") as f:
+        json.dump(doc, f)
+
+
+def read_statistical_model(path: str):
+    """-> (reference points [M, 3], triangles [T, 3] int32, mean [3M], basis [3M, r], variance [r]).  Raises (the
+    reference's Try fails, DemoDatasetLoader.scala:48) on a missing, foreign or inconsistent file."""
+    with open(path) as f:
+        doc = json.load(f)
+    if not isinstance(doc, dict) or doc.get("format") != MODEL_FILE_FORMAT:
+        raise ValueError(f"{path}: not a {MODEL_FILE_FORMAT} file")
+    ref = _from_dataset(doc["representer"]["points"]).T.copy()
+    tri = _from_dataset(doc["representer"]["cells"]).T.astype(np.int32).copy()
+    mean = _from_dataset(doc["model"]["mean"])
+    basis = _from_dataset(doc["model"]["pcaBasis"])
+    var = _from_dataset(doc["model"]["pcaVariance"])
+    m = ref.shape[0]
+    if ref.ndim != 2 or ref.shape[1] != 3 or mean.shape != (3 * m,) or basis.shape != (3 * m, var.shape[0]):
+        raise ValueError(f"{path}: inconsistent dataset shapes")
+    if tri.size and (tri.min() < 0 or tri.max() >= m):
+        raise ValueError(f"{path}: triangle index out of range")
+    return ref, tri, mean, basis, var
+
+
+def load_or_create_gauss_model(ctx, directory: str, name: str, reference_points, triangles, scaling: float, sigma: float,
+                               decimate: Optional[int] = None, relativeTolerance: float = 0.01):
+    """DataSetLoader.model(decimate, GaussKernel(scaling, sigma), ...) (DemoDatasetLoader.scala:40-53): read the cached
+    model when its file exists, else build it ON THE DEVICE (Model.gaussianMixture) and write the file.  The caller
+    passes the (already decimated) reference; -> gingr_b200.api.Model."""
+    import os
+    from . import api
+    path = os.path.join(directory, model_file_name(name, decimate, "Gauss", gauss_kernel_printpars(scaling, sigma)))
+    try:
+        ref, tri, mean, basis, var = read_statistical_model(path)
+        return api.Model(ctx, ref, mean, basis, var, tri if tri.size else None)
+    except (OSError, ValueError, KeyError):
+        pass
+    model = api.Model.gaussianMixture(ctx, reference_points, triangles, [sigma], [scaling], relativeTolerance=relativeTolerance)
+    ref, mean, basis, var = model.download()
+    write_statistical_model(path, ref, triangles, mean, basis, var)
+    return model

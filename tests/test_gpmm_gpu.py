@@ -84,3 +84,24 @@ def test_gpmm_argument_errors(ctx):
         api.Model.gaussianMixture(ctx, ref, tri, [1.0] * 9, [1.0] * 9)
     with pytest.raises(api.GingrError):
         api.Model.gaussianMixture(ctx, ref, tri, [10.0], [1.0], relativeTolerance=1.5)      # nothing left
+
+
+def test_model_cache_builds_once_then_reloads_identically(ctx, tmp_path):
+    """DataSetLoader.model (DemoDatasetLoader.scala:40-53): first call builds on the device and writes the file, the
+    second reads it; both models are bit-identical on the device, and a corrupt file is rebuilt."""
+    import os
+    from gingr_b200 import io
+    ref, tri = _ref(120)
+    a = io.load_or_create_gauss_model(ctx, str(tmp_path), "blob", ref, tri, scaling=50.0, sigma=70.0, decimate=120)
+    path = os.path.join(str(tmp_path), "blob_dec-120_Gauss_50.0_70.0.h5.json")
+    assert os.path.isfile(path)
+    stamp = os.stat(path).st_mtime_ns
+    b = io.load_or_create_gauss_model(ctx, str(tmp_path), "blob", ref, tri, scaling=50.0, sigma=70.0, decimate=120)
+    assert os.stat(path).st_mtime_ns == stamp and b.rank == a.rank and b.T == a.T
+    for x, y in zip(a.download(), b.download()):
+        assert np.array_equal(x, y)
+    with open(path, "w") as f:
+        f.write("{")
+    c = io.load_or_create_gauss_model(ctx, str(tmp_path), "blob", ref, tri, scaling=50.0, sigma=70.0, decimate=120)
+    assert c.rank == a.rank and io.read_statistical_model(path)[4].shape == (a.rank,)
+    a.close(); b.close(); c.close()

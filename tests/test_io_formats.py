@@ -121,3 +121,42 @@ def test_reference_example_files():
     tl = io.read_landmarks(os.path.join(REF_DATA, "femur", "femur_target.json"))
     pids, pts, covs = io.landmark_correspondences(lm, tl, v)
     assert len(pids) == 6 and np.all(covs == np.eye(3))
+
+
+def test_statistical_model_file_round_trip(tmp_path):
+    """The cached-GPMM file (DemoDatasetLoader.scala:40-53 role): lossless round trip, reference file naming, and the
+    reference's Try semantics (any unreadable / foreign / inconsistent file reads as 'absent')."""
+    from gingr_b200 import io
+    rng = np.random.default_rng(5)
+    v, t = _tetra()
+    basis, _ = np.linalg.qr(rng.normal(size=(12, 5)))
+    var = np.sort(rng.uniform(0.1, 9.0, 5))[::-1].copy()
+    mean = rng.normal(size=12)
+    p = str(tmp_path / io.model_file_name("femur", 100, "Gauss", io.gauss_kernel_printpars(50, 70)))
+    assert os.path.basename(p) == "femur_dec-100_Gauss_50.0_70.0.h5.json"                     # DemoDatasetLoader.scala:47
+    assert io.model_file_name("bunny", None, "GaussMix", "") == "bunny_dec-full_GaussMix_.h5.json"
+    io.write_statistical_model(p, v, t, mean, basis, var)
+    ref, tri, m2, b2, v2 = io.read_statistical_model(p)
+    assert np.array_equal(ref, v) and np.array_equal(tri, t) and tri.dtype == np.int32
+    assert np.array_equal(m2, mean) and np.array_equal(b2, basis) and np.array_equal(v2, var)   # bit-exact, f64 kept
+    doc = json.load(open(p))
+    assert doc["representer"]["points"]["shape"] == [3, 4] and doc["representer"]["cells"]["shape"] == [3, 4]
+    assert doc["model"]["pcaBasis"]["shape"] == [12, 5] and doc["model"]["noiseVariance"] == 0.0
+    # point cloud model (no cells)
+    q = str(tmp_path / "cloud.h5.json")
+    io.write_statistical_model(q, v, None, mean, basis, var)
+    assert io.read_statistical_model(q)[1].shape == (0, 3)
+    # failures
+    with pytest.raises(OSError):
+        io.read_statistical_model(str(tmp_path / "missing.h5.json"))
+    (tmp_path / "foreign.h5.json").write_text(json.dumps({"format": "something else"}))
+    with pytest.raises(ValueError):
+        io.read_statistical_model(str(tmp_path / "foreign.h5.json"))
+    doc["model"]["pcaVariance"]["shape"] = [4]
+    (tmp_path / "bad.h5.json").write_text(json.dumps(doc))
+    with pytest.raises(ValueError):
+        io.read_statistical_model(str(tmp_path / "bad.h5.json"))
+    with pytest.raises(ValueError):
+        io.write_statistical_model(q, v, t, mean[:-1], basis, var)
+    with pytest.raises(ValueError):
+        io.write_statistical_model(q, v, t + 1, mean, basis, var)
