@@ -90,6 +90,34 @@ object GingrCudaNative {
                                ADDRESS, ADDRESS, JAVA_DOUBLE, JAVA_INT, ADDRESS, ADDRESS)
   val modelDownload  = fn("gingr_model_download", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS)
 
+  // the remaining entry points of include/gingr_cuda.h (every exported function has a handle here; tests/test_scala_shim.py
+  // checks names, arity and argument classes against the header)
+  val version        = fn("gingr_version", JAVA_INT)
+  val ctxStream      = fn("gingr_ctx_stream", ADDRESS, ADDRESS)
+  val ctxSynchronize = fn("gingr_ctx_synchronize", JAVA_INT, ADDRESS)
+  val ctxLaunchCount = fn("gingr_ctx_launch_count", JAVA_LONG, ADDRESS)
+  val commUniqueId   = fn("gingr_comm_unique_id", JAVA_INT, ADDRESS)
+  val commInit       = fn("gingr_comm_init", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS)
+  // other/algorithms/cpd/BCPD.scala:167-184, :200-209 (nu, nu', N-hat, x-hat in one call)
+  val bcpdEstep      = fn("gingr_bcpd_estep", JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_DOUBLE, JAVA_DOUBLE,
+                          JAVA_DOUBLE, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
+  // CPD.scala:81-90 computeInitialSigma2
+  val cpdInitialSigma2 = fn("gingr_cpd_initial_sigma2", JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS)
+  // ClosestPointRegistrator.scala:34-45 closestPointCorrespondenceReversal
+  val icpClosestReversal = fn("gingr_icp_closest_reversal", JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT,
+                              ADDRESS, ADDRESS, ADDRESS)
+  // GingrAlgorithm.scala:281-302 (model.transform(rigid).posterior(observations), mean only), :215 / :236 (coefficients), :93-95 (instance)
+  val posteriorMean  = fn("gingr_posterior_mean", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT,
+                          ADDRESS, ADDRESS, ADDRESS)
+  val coefficients   = fn("gingr_coefficients", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
+  val modelInstance  = fn("gingr_model_instance", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
+  // device-resident loops: `iters` x update() without the host round trip (GingrAlgorithm.run's deterministic branch, :179-189)
+  val updateChain    = fn("gingr_update_chain", JAVA_INT, ADDRESS, JAVA_INT)
+  val updateChainSampled = fn("gingr_update_chain_sampled", JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG)
+  val updateBatch    = fn("gingr_update_batch", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_LONG)
+  val setProfiling   = fn("gingr_registration_set_profiling", JAVA_INT, ADDRESS, JAVA_INT)
+  val getProfile     = fn("gingr_registration_get_profile", JAVA_INT, ADDRESS, ADDRESS, ADDRESS)
+
   def check(code: Int, ctx: MemorySegment): Int = {
     if (code < 0) {
       val msg = lastError.invoke(ctx).asInstanceOf[MemorySegment].reinterpret(4096).getString(0)
