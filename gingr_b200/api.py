@@ -143,6 +143,13 @@ class Model:
         m.ctx, m.M, m.rank, m.T, m.handle, m.triangles = ctx, ref.shape[0], int(rank.value), 0 if tri is None else tri.shape[0], h, tri
         return m
 
+    @staticmethod
+    def automaticGaussian(ctx: Context, ref_points, triangles, relativeTolerance: float = 0.01, maxRank: int = 0) -> "Model":
+        """GPMMTriangleMesh3D(reference, relativeTolerance).AutomaticGaussian() (api/gpmm/GPMMHelper.scala:119-129): the
+        two-kernel mixture (maxDist/4, maxDist/8) + (maxDist/8, maxDist/16) with maxDist the largest point distance."""
+        d = maximum_point_distance(ref_points)
+        return Model.gaussianMixture(ctx, ref_points, triangles, [d / 4.0, d / 8.0], [d / 8.0, d / 16.0], relativeTolerance, maxRank)
+
     def download(self):
         """(reference points [M, 3], meanVector [3M], basisMatrix [3M, r], variance [r]) as scalismo stores them."""
         ref = np.empty((self.M, 3))
@@ -196,6 +203,34 @@ class Model:
 # ---------------------------------------------------------------------------------------------
 # kernel-level operators
 # ---------------------------------------------------------------------------------------------
+def _max_pair_distance(a: np.ndarray, b: np.ndarray) -> float:
+    best = 0.0
+    step = max(1, (1 << 22) // max(1, b.shape[0]))
+    for i0 in range(0, a.shape[0], step):
+        d = a[i0:i0 + step, None, :] - b[None, :, :]
+        best = max(best, float(np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2]).max()))
+    return best
+
+
+def maximum_point_distance(points, brute_force_limit: int = 2048) -> float:
+    """PointSetHelper.maximumPointDistance (api/gpmm/GPMMHelper.scala:76-81): max over all pairs of (p1 - p2).norm, the
+    reference's O(M^2) loop ("TODO: compute faster for large pointsets").  The maximum is attained between two vertices
+    of the convex hull, so above brute_force_limit points only hull vertices are paired; the distances themselves are
+    formed exactly as EuclideanVector3D.norm does (sqrt(x*x + y*y + z*z) of the component differences), so the value is
+    the reference's bit for bit.  Host side (once per model construction)."""
+    p = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(-1, 3))
+    if p.shape[0] > brute_force_limit:
+        try:
+            from scipy.spatial import ConvexHull, QhullError
+            try:
+                p = p[ConvexHull(p).vertices]
+            except QhullError:      # degenerate (flat) point sets: pair everything
+                pass
+        except ImportError:
+            pass
+    return _max_pair_distance(p, p)
+
+
 def cpd_estep(ctx: Context, target: Target, fit, sigma2: float, w: float):
     """P1[M], Pt1[N_local], PX[M,3] of CpdRegistrationState.P (CPD.scala:54-75) without forming P."""
     fit = nat.f64(fit).reshape(-1, 3)
@@ -636,6 +671,46 @@ class ProbabilisticSettings:
             p.trans_sdev[k] = float(self.translationSdev[k])
             p.shape_sdev[k] = float(self.shapeSteps[k])
         return p
+
+
+def _scala_double(x: float) -> str:
+    """Double.toString as the JVM prints it for the magnitudes kernel parameters take (1e-3 <= |x| < 1e7: plain decimal
+    with at least one fraction digit, which is Python's repr)."""
+    return repr(float(x))
+
+
+@dataclass(frozen=True)
+class GaussKernel:
+    """simple/SimpleModels.scala:37-40."""
+    scaling: float
+    sigma: float
+    name = "Gauss"
+
+    @property
+    def printpars(self) -> str:
+        return _scala_double(self.scaling) + "_" + _scala_double(self.sigma)
+
+
+@dataclass(frozen=True)
+class GaussMixKernel:
+    """simple/SimpleModels.scala:41-44 (AutomaticGaussian)."""
+    name = "GaussMix"
+    printpars = ""
+
+
+class SimpleTriangleModels3D:
+    """simple/SimpleModels.scala:54-77 for the Gaussian families (the kernels the demos load: femur Gauss(50, 70), bunny
+    Gauss(20, 40), DemoDatasetLoader.scala:113-114, :146-147).  The Laplacian, dot-product and mirror kernels are not
+    on the path SURVEY.md 8 scopes and are refused rather than approximated."""
+
+    @staticmethod
+    def create(ctx: Context, reference_points, triangles, kernelSelect, relativeTolerance: float = 0.01) -> Model:
+        if isinstance(kernelSelect, GaussKernel):
+            return Model.gaussianMixture(ctx, reference_points, triangles, [kernelSelect.sigma], [kernelSelect.scaling],
+                                         relativeTolerance)
+        if isinstance(kernelSelect, GaussMixKernel):
+            return Model.automaticGaussian(ctx, reference_points, triangles, relativeTolerance)
+        raise NotImplementedError(f"kernel {type(kernelSelect).__name__} is outside the device GPMM builder (Gaussian families only)")
 
 
 class SimpleRegistrator:

@@ -446,20 +446,28 @@ def read_statistical_model(path: str):
     return ref, tri, mean, basis, var
 
 
-def load_or_create_gauss_model(ctx, directory: str, name: str, reference_points, triangles, scaling: float, sigma: float,
-                               decimate: Optional[int] = None, relativeTolerance: float = 0.01):
-    """DataSetLoader.model(decimate, GaussKernel(scaling, sigma), ...) (DemoDatasetLoader.scala:40-53): read the cached
-    model when its file exists, else build it ON THE DEVICE (Model.gaussianMixture) and write the file.  The caller
-    passes the (already decimated) reference; -> gingr_b200.api.Model."""
+def load_or_create_model(ctx, directory: str, name: str, reference_points, triangles, kernelSelect,
+                         decimate: Optional[int] = None, relativeTolerance: float = 0.01):
+    """DataSetLoader.model(decimate, kernelSelect, ...) (DemoDatasetLoader.scala:40-53): read the cached model when its
+    file exists, else build it ON THE DEVICE (api.SimpleTriangleModels3D.create) and write the file.  The caller passes
+    the (already decimated) reference; kernelSelect is api.GaussKernel / api.GaussMixKernel; -> gingr_b200.api.Model."""
     import os
     from . import api
-    path = os.path.join(directory, model_file_name(name, decimate, "Gauss", gauss_kernel_printpars(scaling, sigma)))
+    path = os.path.join(directory, model_file_name(name, decimate, kernelSelect.name, kernelSelect.printpars))
     try:
         ref, tri, mean, basis, var = read_statistical_model(path)
         return api.Model(ctx, ref, mean, basis, var, tri if tri.size else None)
     except (OSError, ValueError, KeyError):
         pass
-    model = api.Model.gaussianMixture(ctx, reference_points, triangles, [sigma], [scaling], relativeTolerance=relativeTolerance)
+    model = api.SimpleTriangleModels3D.create(ctx, reference_points, triangles, kernelSelect, relativeTolerance)
     ref, mean, basis, var = model.download()
     write_statistical_model(path, ref, triangles, mean, basis, var)
     return model
+
+
+def load_or_create_gauss_model(ctx, directory: str, name: str, reference_points, triangles, scaling: float, sigma: float,
+                               decimate: Optional[int] = None, relativeTolerance: float = 0.01):
+    """load_or_create_model with GaussKernel(scaling, sigma)."""
+    from . import api
+    return load_or_create_model(ctx, directory, name, reference_points, triangles, api.GaussKernel(scaling, sigma), decimate,
+                                relativeTolerance)

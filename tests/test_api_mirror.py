@@ -111,3 +111,22 @@ def test_convergence_closures_match_the_reference():
     cpd, icp = api.CpdConfiguration(), api.IcpConfiguration()
     assert cpd.converged(a, b, cpd.threshold) and not cpd.converged(a, c, cpd.threshold)      # CPD.scala:106-110
     assert not icp.converged(a, a, icp.threshold)                                             # ICP.scala:57-58: never
+
+
+def test_maximum_point_distance_is_the_brute_force_value():
+    """PointSetHelper.maximumPointDistance (GPMMHelper.scala:76-81): hull pairing above the limit must give the literal
+    all-pairs maximum bit for bit -- also for points all on the hull, flat sets and duplicated points."""
+    from gingr_b200 import api
+    rng = np.random.default_rng(3)
+    sphere = rng.normal(size=(2500, 3))
+    sphere /= np.linalg.norm(sphere, axis=1)[:, None]
+    flat = np.c_[rng.normal(size=(2500, 2)), np.zeros(2500)]
+    blob = rng.normal(size=(3000, 3)) * [30.0, 10.0, 5.0]
+    dup = np.repeat(blob[:1500], 2, axis=0)
+    for pts in (sphere, flat, blob, dup):
+        lit = api.maximum_point_distance(pts, brute_force_limit=10 ** 9)
+        assert api.maximum_point_distance(pts, brute_force_limit=16) == lit
+        i, j = rng.integers(0, len(pts), 2)
+        assert lit >= np.linalg.norm(pts[i] - pts[j]) * (1 - 1e-15)
+    tiny = np.array([[0.0, 0, 0], [3.0, 4.0, 0.0]])
+    assert api.maximum_point_distance(tiny) == 5.0 and api.maximum_point_distance(tiny[:1]) == 0.0

@@ -105,3 +105,33 @@ def test_model_cache_builds_once_then_reloads_identically(ctx, tmp_path):
     c = io.load_or_create_gauss_model(ctx, str(tmp_path), "blob", ref, tri, scaling=50.0, sigma=70.0, decimate=120)
     assert c.rank == a.rank and io.read_statistical_model(path)[4].shape == (a.rank,)
     a.close(); b.close(); c.close()
+
+
+def test_automatic_gaussian_is_the_two_kernel_mixture(ctx):
+    """AutomaticGaussian (GPMMHelper.scala:119-129) = GaussianMixture((d/4, d/8), (d/8, d/16)), d = largest point distance."""
+    from gingr_b200 import api
+    ref, tri = _ref(200)
+    d = max(float(np.linalg.norm(a - b)) for a in ref for b in ref)
+    assert abs(api.maximum_point_distance(ref) - d) <= 1e-13 * d
+    d = api.maximum_point_distance(ref)
+    a = api.Model.automaticGaussian(ctx, ref, tri, 0.05)
+    b = api.Model.gaussianMixture(ctx, ref, tri, [d / 4.0, d / 8.0], [d / 8.0, d / 16.0], 0.05)
+    assert a.rank == b.rank and a.rank > 3
+    for x, y in zip(a.download(), b.download()):
+        assert np.array_equal(x, y)
+    a.close(); b.close()
+
+
+def test_model_cache_with_the_automatic_mixture(ctx, tmp_path):
+    import os
+    from gingr_b200 import api, io
+    ref, tri = _ref(90)
+    a = io.load_or_create_model(ctx, str(tmp_path), "blob", ref, tri, api.GaussMixKernel(), relativeTolerance=0.05)
+    assert os.path.isfile(os.path.join(str(tmp_path), "blob_dec-full_GaussMix_.h5.json"))
+    b = io.load_or_create_model(ctx, str(tmp_path), "blob", ref, tri, api.GaussMixKernel(), relativeTolerance=0.05)
+    assert a.rank == b.rank
+    for x, y in zip(a.download(), b.download()):
+        assert np.array_equal(x, y)
+    with pytest.raises(NotImplementedError):
+        api.SimpleTriangleModels3D.create(ctx, ref, tri, object())
+    a.close(); b.close()
