@@ -77,3 +77,8 @@ def test_struct_layouts_match_the_ctypes_mirrors():
             assert off == getattr(mirror, [f[0] for f in mirror._fields_][names.index(fname)]).offset, (layout, fname)
             off += size[kind] * n
         assert off == ctypes.sizeof(mirror), (layout, off, ctypes.sizeof(mirror))
+
+
+def test_integration_notes_name_every_entry_point():
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert [n for n in _header_prototypes() if n not in doc] == []
