@@ -598,16 +598,57 @@ class GingrAlgorithm:
         self.ctx.check(self.ctx._lib.gingr_mcmc_best(self.handle, ctypes.byref(st), nat.as_dp(alpha), nat.as_dp(fit)))
         return GeneralRegistrationState.from_pod(st, alpha, fit)
 
+    def generatorNames(self, settings: "ProbabilisticSettings"):
+        """generatedBy of the ten leaves of generatorCombined (GingrAlgorithm.scala:177-190, sampling/Generator.scala:31-83),
+        in the order of the device's leaf index (mcmcStats counts[1])."""
+        r, t, sh = settings.rotationSdev, settings.translationSdev, settings.shapeSteps
+        return ([self.name] + [f"Rotation{a}-{float(v)!r}" for a, v in zip(("Yaw", "Pitch", "Roll"), r)] +
+                [f"Translation{a}-{float(v)!r}" for a, v in zip("XYZ", t)] + [f"RandomShape-{float(v)!r}" for v in sh])
+
     def runProbabilistic(self, initialState: GeneralRegistrationState, settings: "ProbabilisticSettings", seed: int = 0,
-                         iterations: Optional[int] = None) -> GeneralRegistrationState:
+                         iterations: Optional[int] = None, acceptRejectLogger=None, callBackLogger=None) -> GeneralRegistrationState:
         """GingrAlgorithm.run with probabilisticSettings (:115-175): maxIterations - 1 MH steps, returns the best sample
-        (:160-163) with status MaxIteration unless the chain ended in ModelFlexibilityError."""
+        (:160-163) with status MaxIteration unless the chain ended in ModelFlexibilityError.
+
+        Without loggers the whole chain runs on the device in one call.  With an acceptRejectLogger (io.JSONStateLogger:
+        accept(state, values) / reject(state, values)) or a callBackLogger (callable(state), ChainStateLogger.logState)
+        the same chain -- same seed, same draws, same decisions -- is advanced one step per call and read back after
+        each step, as scalismo's logged iterator does (:126-134).  A rejected proposal is logged with its generator name
+        and log values; its scale (the only parameter jsonLogFormat keeps for a rejected sample) is the current
+        state's, which differs from the proposal's only for a rejected informed SimilarityTransforms step."""
         self.configureProbabilistic(settings)
+        logged = acceptRejectLogger is not None or callBackLogger is not None
+        # the evaluators depend on the parameters only; evaluated BEFORE initializeState because gingr_evaluate_log_value
+        # replaces the device-resident state the chain starts from
+        lp0 = dict(zip(("Prior", "Distance"), self.logValue(initialState))) if acceptRejectLogger is not None else None
         st, alpha = initialState.to_pod()
         fit = np.empty((self.model.M, 3))
         self.ctx.check(self.ctx._lib.gingr_initialize_state(self.handle, ctypes.byref(st), nat.as_dp(alpha), nat.as_dp(fit)))
-        steps = (self.config.maxIterations - 1) if iterations is None else int(iterations)
-        self.mcmcChain(max(steps, 0), seed)
+        steps = max((self.config.maxIterations - 1) if iterations is None else int(iterations), 0)
+        if not logged:
+            self.mcmcChain(steps, seed)
+        else:
+            names = self.generatorNames(settings)
+            current = dataclasses.replace(GeneralRegistrationState.from_pod(st, alpha, fit), generatedBy=initialState.generatedBy)
+            if acceptRejectLogger is not None:                         # :126 the initial state is logged as accepted
+                acceptRejectLogger.accept(current, lp0)
+            if callBackLogger is not None:
+                callBackLogger(current)
+            for _ in range(steps):
+                self.mcmcChain(1, seed)
+                values, counts = self.mcmcStats()
+                lp = {"Prior": float(values[2]), "Distance": float(values[3])}
+                name = names[int(counts[1])]
+                if counts[2]:
+                    current = dataclasses.replace(self.downloadState(), generatedBy=name)
+                    if acceptRejectLogger is not None:
+                        acceptRejectLogger.accept(current, lp)
+                elif acceptRejectLogger is not None:
+                    acceptRejectLogger.reject(dataclasses.replace(current, generatedBy=name), lp)
+                if callBackLogger is not None:
+                    callBackLogger(current)
+                if current.status == STATUS_MODEL_FLEXIBILITY_ERROR:   # :150-153 the chain stops at an error state
+                    break
         best = self.mcmcBest()
         if best.status == STATUS_NONE:
             best = dataclasses.replace(best, status=STATUS_MAX_ITERATION)

@@ -95,28 +95,55 @@ class JSONStateLogger:
         self.rejected = 0
         self.generatedBy = set()
 
-    def _values(self, state) -> Dict[str, float]:
-        ev = dict(self.evaluate(state)) if self.evaluate is not None else {}
+    def _values(self, state, values=None) -> Dict[str, float]:
+        if values is not None:
+            ev = {k: float(v) for k, v in values.items()}
+        else:
+            ev = dict(self.evaluate(state)) if self.evaluate is not None else {}
         ev["product"] = float(sum(ev.values()))
         return ev
 
     def _now(self) -> str:
         return datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S")
 
-    def accept(self, state) -> None:
+    def accept(self, state, values=None) -> None:
+        """values: the evaluators' log values when the caller already holds them (the device chain does), else
+        evaluate(state) is called."""
         p = state.modelParameters
         self.generatedBy.add(state.generatedBy)
-        self.log.append(JsonLogRecord(self.accepted + self.rejected, state.generatedBy, self._values(state), True,
+        self.log.append(JsonLogRecord(self.accepted + self.rejected, state.generatedBy, self._values(state, values), True,
                                       [float(v) for v in p.shape], [float(v) for v in p.translation],
                                       [float(v) for v in p.euler], [0.0, 0.0, 0.0], float(p.scale), self._now()))
         self.accepted += 1
 
-    def reject(self, state) -> None:
+    def reject(self, state, values=None) -> None:
         p = state.modelParameters
         self.generatedBy.add(state.generatedBy)
-        self.log.append(JsonLogRecord(self.accepted + self.rejected, state.generatedBy, self._values(state), False,
+        self.log.append(JsonLogRecord(self.accepted + self.rejected, state.generatedBy, self._values(state, values), False,
                                       [], [], [], [], float(p.scale), self._now()))
         self.rejected += 1
+
+    # acceptance statistics (JSONStateLogger.scala:86, :142-147, :186-196)
+    @property
+    def totalSamples(self) -> int:
+        return self.accepted + self.rejected
+
+    @property
+    def percentRejected(self) -> float:
+        """rejected / total rounded HALF_UP to two decimals (:142-145)."""
+        import decimal
+        if self.totalSamples == 0:
+            return float("nan")
+        q = decimal.Decimal(repr(self.rejected / self.totalSamples)).quantize(decimal.Decimal("0.01"), rounding=decimal.ROUND_HALF_UP)
+        return float(q)
+
+    @property
+    def percentAccepted(self) -> float:
+        return 1.0 - self.percentRejected
+
+    def percentAcceptedOfType(self, name: str, last: Optional[int] = None) -> float:
+        recs = [r for r in (self.log if last is None else self.log[-last:]) if r.name == name]
+        return sum(1 for r in recs if r.status) / len(recs) if recs else float("nan")
 
     def to_json(self) -> list:
         return [r.__dict__.copy() for r in self.log]

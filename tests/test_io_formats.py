@@ -1,5 +1,6 @@
 """Wire / disk formats (gingr_b200/io.py): round trips, the reference's JSON layouts, and -- when
 the reference tree is mounted -- its own example files (the femur fixtures of tests/golden were generated from them)."""
+import dataclasses
 import json
 import os
 
@@ -160,3 +161,22 @@ def test_statistical_model_file_round_trip(tmp_path):
         io.write_statistical_model(q, v, t, mean[:-1], basis, var)
     with pytest.raises(ValueError):
         io.write_statistical_model(q, v, t + 1, mean, basis, var)
+
+
+def test_logger_statistics_and_precomputed_values():
+    from gingr_b200 import api, io
+    lg = io.JSONStateLogger()
+    p = api.ModelFittingParameters(1.0, np.zeros(3), (0.0, 0.0, 0.0), np.arange(3.0))
+    s = api.GeneralRegistrationState(p, np.zeros((1, 3)), generatedBy="CPD")
+    lg.accept(s, {"Prior": -1.5, "Distance": -2.0})
+    lg.reject(dataclasses.replace(s, generatedBy="RandomShape-0.1"), {"Prior": -3.0, "Distance": -4.0})
+    lg.reject(dataclasses.replace(s, generatedBy="CPD"), {"Prior": -3.0, "Distance": -4.0})
+    assert lg.totalSamples == 3 and lg.log[0].logvalue == {"Prior": -1.5, "Distance": -2.0, "product": -3.5}
+    assert lg.log[1].modelParameters == [] and lg.log[1].name == "RandomShape-0.1" and not lg.log[1].status
+    assert lg.percentRejected == 0.67 and abs(lg.percentAccepted - 0.33) < 1e-12       # 2/3 -> 0.67 (HALF_UP, two decimals)
+    assert lg.percentAcceptedOfType("CPD") == 0.5 and lg.percentAcceptedOfType("RandomShape-0.1") == 0.0
+    assert lg.percentAcceptedOfType("CPD", last=1) == 0.0
+    lg2 = io.JSONStateLogger()
+    for k in range(8):
+        (lg2.reject if k == 0 else lg2.accept)(s, {})
+    assert lg2.percentRejected == 0.13                                                  # 0.125 rounds half UP

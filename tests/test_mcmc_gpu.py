@@ -220,3 +220,41 @@ def test_mcmc_argument_errors(ctx, oracle):
     with pytest.raises(api.GingrError):
         reg.mcmcChain(1, 0)                                          # no device-resident state yet
     reg.close()
+
+
+def test_logged_probabilistic_run_is_the_same_chain(ctx, oracle, tmp_path):
+    """run(..., acceptRejectLogger, callBackLogger, probabilisticSettings) (GingrAlgorithm.scala:115-175): the logged,
+    step-by-step run makes the decisions of the one-call device chain; the JSON log carries one record per sample
+    (the initial state first, accepted), generator names of Generator.DefaultRandom, and the proposal's log values."""
+    from gingr_b200 import api, io
+    gs = api.ProbabilisticSettings(uncertainty=1.5, randomMixture=0.5)
+    reg, _, _, _, keep = _setup(ctx, oracle, "icp", M=100, N=110, r=10)
+    st0 = reg.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
+    plain = reg.runProbabilistic(st0, gs, seed=9, iterations=25)
+    _, counts_plain = reg.mcmcStats()
+    logger = io.JSONStateLogger(path=str(tmp_path / "log.json"))
+    seen = []
+    logged = reg.runProbabilistic(st0, gs, seed=9, iterations=25, acceptRejectLogger=logger, callBackLogger=seen.append)
+    values, counts = reg.mcmcStats()
+    assert np.array_equal(counts, counts_plain)
+    assert np.array_equal(logged.fit, plain.fit) and np.array_equal(logged.modelParameters.shape, plain.modelParameters.shape)
+    assert logger.totalSamples == 26 and len(seen) == 26
+    assert logger.accepted == 1 + counts[3] and logger.rejected == 25 - counts[3]
+    names = reg.generatorNames(gs)
+    assert names == ["ICP", "RotationYaw-0.01", "RotationPitch-0.01", "RotationRoll-0.01", "TranslationX-0.1", "TranslationY-0.1",
+                     "TranslationZ-0.1", "RandomShape-1.0", "RandomShape-0.1", "RandomShape-0.01"]
+    for leaf, name in enumerate(names):
+        recs = [r for r in logger.log[1:] if r.name == name]
+        assert len(recs) == counts[8 + leaf] and sum(r.status for r in recs) == counts[18 + leaf]
+    # accepted records hold the state the chain moved to; its log values are the evaluators' at that state
+    last = max(k for k, r in enumerate(logger.log) if r.status)
+    cur = seen[-1]
+    assert logger.log[last].modelParameters == [float(v) for v in cur.modelParameters.shape]
+    pr, di = reg.logValue(cur)
+    lv = logger.log[last].logvalue
+    assert abs(lv["Prior"] - pr) <= 1e-9 * abs(pr) and abs(lv["Distance"] - di) <= 1e-9 * abs(di)
+    assert abs(lv["product"] - (lv["Prior"] + lv["Distance"])) == 0.0
+    logger.write()
+    back = io.JSONStateLogger.load(logger.path)
+    assert len(back) == 26 and back[0].status and back[0].index == 0
+    reg.close()
