@@ -761,9 +761,11 @@ class SimpleRegistrator:
     the re-referenced model is built on the device from the resident basis (Model.newReference)."""
 
     def __init__(self, ctx: Context, algorithm, config, model: Model, target: Target, evaluatorUncertainty: float = 1.0,
-                 evaluationMode: int = EVAL_MODEL_TO_TARGET):
+                 evaluationMode: int = EVAL_MODEL_TO_TARGET, logFileFittingParameters: Optional[str] = None):
         self.ctx, self.algorithm, self.config, self.model, self.target = ctx, algorithm, config, model, target
         self.evaluatorUncertainty, self.evaluationMode = evaluatorUncertainty, evaluationMode
+        self.logFileFittingParameters = logFileFittingParameters
+        self.jsonLogger = None       # the JSONStateLogger of the last logged probabilistic run (:139)
 
     def _run(self, model: Model, target: Target, generalState, globalTransformation, probabilistic, randomMixture, callback,
              seed):
@@ -778,7 +780,17 @@ class SimpleRegistrator:
             if probabilistic:
                 settings = ProbabilisticSettings(uncertainty=self.evaluatorUncertainty, mode=self.evaluationMode,
                                                  randomMixture=randomMixture)
-                final = reg.runProbabilistic(st, settings, seed=seed)
+                # The reference always attaches a JSONStateLogger here (:139-145).  The log costs one host round trip per
+                # MH step, so it is kept only when somebody reads it: a log file or a callback was asked for; otherwise
+                # the whole chain stays on the device.
+                if self.logFileFittingParameters is not None or callback is not None:
+                    from .io import JSONStateLogger
+                    self.jsonLogger = JSONStateLogger(path=self.logFileFittingParameters)
+                    final = reg.runProbabilistic(st, settings, seed=seed, acceptRejectLogger=self.jsonLogger, callBackLogger=callback)
+                    if self.logFileFittingParameters is not None:
+                        self.jsonLogger.write()                                                    # writeLog (:150)
+                else:
+                    final = reg.runProbabilistic(st, settings, seed=seed)
             else:
                 final = reg.run(st, callback)
         finally:

@@ -130,3 +130,64 @@ def test_maximum_point_distance_is_the_brute_force_value():
         assert lit >= np.linalg.norm(pts[i] - pts[j]) * (1 - 1e-15)
     tiny = np.array([[0.0, 0, 0], [3.0, 4.0, 0.0]])
     assert api.maximum_point_distance(tiny) == 5.0 and api.maximum_point_distance(tiny[:1]) == 0.0
+
+
+def test_simple_registrator_attaches_the_json_logger_when_asked(tmp_path):
+    """SimpleRegistrator.run (SimpleRegistrator.scala:127-158): probabilistic runs carry a JSONStateLogger that is written
+    to logFileFittingParameters, the callback is the chain-state logger, and the returned fit is the FULL model's
+    instance.  Wiring only (fake registration object, no device)."""
+    from gingr_b200 import api, io
+    pars = api.ModelFittingParameters(1.0, np.zeros(3), (0.0, 0.0, 0.0), np.arange(2.0))
+    st = api.GeneralRegistrationState(pars, np.zeros((2, 3)))
+    calls = {}
+
+    class FakeReg:
+        def __init__(self, ctx, model, target, config):
+            self.config = config
+
+        def initializeState(self, general=None, globalTransformation=None):
+            calls["init"] = (general, globalTransformation)
+            return st
+
+        def runProbabilistic(self, state, settings, seed=0, acceptRejectLogger=None, callBackLogger=None):
+            calls["settings"] = settings
+            calls["loggers"] = (acceptRejectLogger, callBackLogger)
+            if acceptRejectLogger is not None:
+                acceptRejectLogger.accept(state, {"Prior": -1.0, "Distance": -2.0})
+                acceptRejectLogger.reject(dataclasses.replace(state, generatedBy="CPD"), {"Prior": -3.0, "Distance": -4.0})
+            if callBackLogger is not None:
+                callBackLogger(state)
+            return dataclasses.replace(state, status=api.STATUS_MAX_ITERATION)
+
+        def run(self, state, callback=None):
+            calls["det"] = callback
+            return dataclasses.replace(state, status=api.STATUS_CONVERGED)
+
+        def close(self):
+            calls["closed"] = calls.get("closed", 0) + 1
+
+    class FakeModel:
+        def instance(self, p):
+            return np.full((5, 3), 7.0)
+
+    log = str(tmp_path / "fit.json")
+    sr = api.SimpleRegistrator(None, FakeReg, api.CpdConfiguration(), FakeModel(), None, evaluatorUncertainty=2.0,
+                               evaluationMode=api.EVAL_SYMMETRIC, logFileFittingParameters=log)
+    seen = []
+    out = sr.run(probabilistic=True, randomMixture=0.25, callback=seen.append, seed=3)
+    assert out.fit.shape == (5, 3) and out.status == api.STATUS_MAX_ITERATION and calls["closed"] == 1
+    s = calls["settings"]
+    assert (s.uncertainty, s.mode, s.randomMixture) == (2.0, api.EVAL_SYMMETRIC, 0.25)
+    assert calls["loggers"][0] is sr.jsonLogger and len(seen) == 1
+    recs = io.JSONStateLogger.load(log)
+    assert [r.status for r in recs] == [True, False] and recs[1].name == "CPD" and recs[0].logvalue["product"] == -3.0
+    # no log file, no callback: the chain is left on the device (no per-step logger)
+    sr2 = api.SimpleRegistrator(None, FakeReg, api.CpdConfiguration(), FakeModel(), None)
+    sr2.run(probabilistic=True)
+    assert calls["loggers"] == (None, None) and sr2.jsonLogger is None
+    # deterministic: callback goes to run(), and a handed-over state is re-initialised with iteration 0 / status None
+    g = dataclasses.replace(st, iteration=9, status=api.STATUS_CONVERGED)
+    out = sr2.run(generalState=g, globalTransformation=api.SIMILARITY_TRANSFORMS, callback=seen.append)
+    assert calls["det"] is not None and out.status == api.STATUS_CONVERGED
+    assert calls["init"][0].iteration == 0 and calls["init"][0].status == api.STATUS_NONE
+    assert calls["init"][0].globalTransformation == api.SIMILARITY_TRANSFORMS
