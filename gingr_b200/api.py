@@ -124,6 +124,7 @@ class Model:
                                               nat.as_ip(tri), self.T, ctypes.byref(h)))
         self.handle = h
         self.triangles = tri
+        self.reference = ref.copy()      # host copy of model.reference.pointSet (landmark look-up, file export)
 
     @staticmethod
     def gaussianMixture(ctx: Context, ref_points, triangles, sigmas, scalings, relativeTolerance: float = 0.01,
@@ -141,6 +142,7 @@ class Model:
                                                        float(relativeTolerance), int(maxRank), ctypes.byref(h), ctypes.byref(rank)))
         m = Model.__new__(Model)
         m.ctx, m.M, m.rank, m.T, m.handle, m.triangles = ctx, ref.shape[0], int(rank.value), 0 if tri is None else tri.shape[0], h, tri
+        m.reference = ref.copy()
         return m
 
     @staticmethod
@@ -171,6 +173,7 @@ class Model:
                                                                ctypes.byref(h)))
         m = Model.__new__(Model)
         m.ctx, m.M, m.rank, m.T, m.handle, m.triangles = self.ctx, ref.shape[0], self.rank, 0 if tri is None else tri.shape[0], h, tri
+        m.reference = ref.copy()
         return m
 
     def instance(self, parameters: "ModelFittingParameters") -> np.ndarray:
@@ -761,25 +764,56 @@ class SimpleRegistrator:
     the re-referenced model is built on the device from the resident basis (Model.newReference)."""
 
     def __init__(self, ctx: Context, algorithm, config, model: Model, target: Target, evaluatorUncertainty: float = 1.0,
-                 evaluationMode: int = EVAL_MODEL_TO_TARGET, logFileFittingParameters: Optional[str] = None):
+                 evaluationMode: int = EVAL_MODEL_TO_TARGET, logFileFittingParameters: Optional[str] = None,
+                 initialModelParameterTransform=None, modelLandmarks=None, targetLandmarks=None,
+                 evaluatedPoints: Optional[int] = None):
+        """initialModelParameterTransform: (rotation matrix [3, 3], translation [3]) of the TranslationAfterRotation the
+        initial pose is taken from (GeneralRegistrationState.scala:143-157); modelLandmarks / targetLandmarks: io.Landmark
+        lists, matched by id on the reference of the model a run uses (:43-62, :111-122); evaluatedPoints: the evaluator's
+        numberOfPointsForComparison (IndependentPointDistanceEvaluator.scala:39-47)."""
         self.ctx, self.algorithm, self.config, self.model, self.target = ctx, algorithm, config, model, target
         self.evaluatorUncertainty, self.evaluationMode = evaluatorUncertainty, evaluationMode
         self.logFileFittingParameters = logFileFittingParameters
+        self.initialModelParameterTransform = initialModelParameterTransform
+        self.modelLandmarks, self.targetLandmarks = modelLandmarks, targetLandmarks
+        self.evaluatedPoints = evaluatedPoints
         self.jsonLogger = None       # the JSONStateLogger of the last logged probabilistic run (:139)
+
+    def _evaluated_point_ids(self, model: Model, target: Target):
+        """The evaluator's point subsets for evaluatedPoints = n.  Kept from the reference: the MODEL ids are those of the
+        decimated instance used as ids of the full mesh, i.e. simply the first n ids (IndependentPointDistanceEvaluator
+        .scala:46-47, :50).  Substituted: the target points are every (N / n)-th target vertex instead of the vertices
+        of scalismo's quadric decimation."""
+        if self.evaluatedPoints is None:
+            return None, None
+        n = int(self.evaluatedPoints)
+        mids = np.arange(min(n, model.M), dtype=np.int32)
+        N = target.N
+        tids = np.unique(np.floor(np.arange(min(n, N)) * (N / min(n, N))).astype(np.int32))
+        return mids, tids
 
     def _run(self, model: Model, target: Target, generalState, globalTransformation, probabilistic, randomMixture, callback,
              seed):
         reg = self.algorithm(self.ctx, model, target, self.config)
         try:
+            if self.modelLandmarks and self.targetLandmarks:
+                from .io import landmark_correspondences
+                pids, pts, covs = landmark_correspondences(self.modelLandmarks, self.targetLandmarks, model.reference)
+                if len(pids):
+                    reg.setLandmarks(pids, pts, covs)
             if generalState is not None:
                 # combineStates (:76-82): clearIteration, status None, then initializeState recomputes sigma2 from the config
                 g = dataclasses.replace(generalState, iteration=0, status=STATUS_NONE, globalTransformation=globalTransformation)
                 st = reg.initializeState(general=g)
+            elif self.initialModelParameterTransform is not None:
+                rot, trans = self.initialModelParameterTransform
+                st = reg.initializeState(globalTransformation=globalTransformation, rotation=rot, translation=trans)
             else:
                 st = reg.initializeState(globalTransformation=globalTransformation)
             if probabilistic:
+                mids, tids = self._evaluated_point_ids(model, target)
                 settings = ProbabilisticSettings(uncertainty=self.evaluatorUncertainty, mode=self.evaluationMode,
-                                                 randomMixture=randomMixture)
+                                                 randomMixture=randomMixture, modelPointIds=mids, targetPointIds=tids)
                 # The reference always attaches a JSONStateLogger here (:139-145).  The log costs one host round trip per
                 # MH step, so it is kept only when somebody reads it: a log file or a callback was asked for; otherwise
                 # the whole chain stays on the device.
@@ -813,6 +847,26 @@ class SimpleRegistrator:
         finally:
             dm.close()
             dt.close()
+
+
+class GingrInterface:
+    """simple/GingrInterface.scala:20-64: the model / target / landmarks / evaluator options once, then .CPD(config) or
+    .ICP(config) -> SimpleRegistrator."""
+
+    def __init__(self, ctx: Context, model: Model, target: Target, initialModelParameterTransform=None, modelLandmarks=None,
+                 targetLandmarks=None, evaluatorUncertainty: float = 1.0, evaluatedPoints: Optional[int] = None,
+                 evaluationMode: int = EVAL_MODEL_TO_TARGET, logFileFittingParameters: Optional[str] = None):
+        self.ctx, self.model, self.target = ctx, model, target
+        self._options = dict(evaluatorUncertainty=evaluatorUncertainty, evaluationMode=evaluationMode,
+                             logFileFittingParameters=logFileFittingParameters,
+                             initialModelParameterTransform=initialModelParameterTransform, modelLandmarks=modelLandmarks,
+                             targetLandmarks=targetLandmarks, evaluatedPoints=evaluatedPoints)
+
+    def CPD(self, config: Optional["CpdConfiguration"] = None) -> "SimpleRegistrator":
+        return SimpleRegistrator(self.ctx, CpdRegistration, config or CpdConfiguration(), self.model, self.target, **self._options)
+
+    def ICP(self, config: Optional["IcpConfiguration"] = None) -> "SimpleRegistrator":
+        return SimpleRegistrator(self.ctx, IcpRegistration, config or IcpConfiguration(), self.model, self.target, **self._options)
 
 
 class CpdRegistration(GingrAlgorithm):

@@ -191,3 +191,71 @@ def test_simple_registrator_attaches_the_json_logger_when_asked(tmp_path):
     assert calls["det"] is not None and out.status == api.STATUS_CONVERGED
     assert calls["init"][0].iteration == 0 and calls["init"][0].status == api.STATUS_NONE
     assert calls["init"][0].globalTransformation == api.SIMILARITY_TRANSFORMS
+
+
+def test_gingr_interface_options_reach_the_registration(monkeypatch):
+    """simple/GingrInterface.scala:20-64 -> SimpleRegistrator: landmarks are resolved on the run model's reference, the
+    initial transform seeds the pose, evaluatedPoints becomes the evaluator's point subsets."""
+    from gingr_b200 import api, io
+    calls = {}
+    pars = api.ModelFittingParameters(1.0, np.zeros(3), (0.0, 0.0, 0.0), np.zeros(2))
+    st = api.GeneralRegistrationState(pars, np.zeros((2, 3)))
+
+    class FakeReg:
+        name = "CPD"
+
+        def __init__(self, ctx, model, target, config):
+            calls["config"] = config
+
+        def setLandmarks(self, pids, points, cov=None):
+            calls["lm"] = (np.asarray(pids), np.asarray(points), np.asarray(cov))
+
+        def initializeState(self, general=None, globalTransformation=None, rotation=None, translation=None):
+            calls["init"] = (general, globalTransformation, rotation, translation)
+            return st
+
+        def runProbabilistic(self, state, settings, seed=0, acceptRejectLogger=None, callBackLogger=None):
+            calls["settings"] = settings
+            return state
+
+        def run(self, state, callback=None):
+            return state
+
+        def close(self):
+            pass
+
+    class FakeModel:
+        M = 10
+        reference = np.array([[float(k), 0.0, 0.0] for k in range(10)])
+
+        def instance(self, p):
+            return np.zeros((10, 3))
+
+    class FakeTarget:
+        N = 1000
+
+    monkeypatch.setattr(api, "CpdRegistration", FakeReg)
+    monkeypatch.setattr(api, "IcpRegistration", FakeReg)
+    cov = np.diag([1.0, 2.0, 3.0])
+    mlm = [io.Landmark("A", np.array([2.2, 0.1, 0.0]), cov), io.Landmark("B", np.array([7.6, 0.0, 0.0]), None),
+           io.Landmark("only-model", np.zeros(3), None)]
+    tlm = [io.Landmark("B", np.array([1.0, 1.0, 1.0]), None), io.Landmark("A", np.array([5.0, 5.0, 5.0]), None)]
+    R = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    gi = api.GingrInterface(None, FakeModel(), FakeTarget(), initialModelParameterTransform=(R, [1.0, 2.0, 3.0]),
+                            modelLandmarks=mlm, targetLandmarks=tlm, evaluatorUncertainty=3.0, evaluatedPoints=4,
+                            evaluationMode=api.EVAL_TARGET_TO_MODEL)
+    sr = gi.CPD(api.CpdConfiguration(w=0.2))
+    assert isinstance(sr, api.SimpleRegistrator) and calls == {}
+    sr.run(probabilistic=True, randomMixture=0.1)
+    assert calls["config"].w == 0.2
+    pids, pts, covs = calls["lm"]
+    assert list(pids) == [2, 8] and np.array_equal(pts, [[5.0, 5.0, 5.0], [1.0, 1.0, 1.0]])     # matched by id, nearest reference vertex
+    assert np.array_equal(covs[0], cov) and np.array_equal(covs[1], np.eye(3))
+    assert calls["init"][0] is None and calls["init"][2] is R and list(calls["init"][3]) == [1.0, 2.0, 3.0]
+    s = calls["settings"]
+    assert (s.uncertainty, s.mode, s.randomMixture) == (3.0, api.EVAL_TARGET_TO_MODEL, 0.1)
+    assert list(s.modelPointIds) == [0, 1, 2, 3] and list(s.targetPointIds) == [0, 250, 500, 750]
+    # a handed-over state wins over the initial transform (combineStates, SimpleRegistrator.scala:76-82)
+    gi.ICP().run(generalState=st)
+    assert calls["init"][0] is not None and calls["init"][2] is None
+    assert isinstance(calls["config"], api.IcpConfiguration)
