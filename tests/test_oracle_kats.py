@@ -256,3 +256,62 @@ def test_posterior_sample_has_covariance_minv(oracle):
     L = np.linalg.cholesky(Mx)
     S = np.linalg.solve(L.T, np.eye(12))
     np.testing.assert_allclose(S @ S.T, oracle.breeze_pinv(Mx), rtol=1e-10, atol=1e-12)
+
+
+def test_posterior_equals_dense_gaussian_conditioning(oracle):
+    """Independent of the low-rank algebra the oracle restates [A3]: the GP the model describes has covariance
+    K = Phi diag(lambda) Phi^T over all 3M coordinates; conditioning it on noisy observations of some points with the
+    textbook dense formula  mean' = mu + K_xo (K_oo + Sigma)^-1 (y - mu_o),  K' = K - K_xo (K_oo + Sigma)^-1 K_ox  must give
+    the mean the oracle's coefficient vector produces and the covariance D Minv D spans (posterior_model's SVD form)."""
+    rng = np.random.default_rng(11)
+    m = _small_model(oracle, M=40, r=9, seed=3)
+    pids = rng.choice(m.M, size=17, replace=False)
+    A = rng.normal(size=(len(pids), 3, 3))
+    cov = A @ np.transpose(A, (0, 2, 1)) + 0.05 * np.eye(3)[None]             # full 3x3 noise per observation
+    y_pts = m.ref[pids] + m.mean.reshape(-1, 3)[pids] + rng.normal(size=(len(pids), 3)) * 3.0
+    c, Minv = m.posterior_coefficients(pids, y_pts, cov)
+    D = np.sqrt(m.variance)
+    low_rank_mean = m.mean + m.basis @ (D * c)
+    K = (m.basis * m.variance) @ m.basis.T
+    rows = (3 * pids[:, None] + np.arange(3)[None, :]).ravel()
+    S = np.zeros((len(rows), len(rows)))
+    for k in range(len(pids)):
+        S[3 * k:3 * k + 3, 3 * k:3 * k + 3] = cov[k]
+    resid = (y_pts - m.ref[pids]).ravel() - m.mean[rows]
+    G = np.linalg.solve(K[np.ix_(rows, rows)] + S, np.eye(len(rows)))
+    dense_mean = m.mean + K[:, rows] @ (G @ resid)
+    assert np.max(np.abs(low_rank_mean - dense_mean)) < 1e-9 * np.max(np.abs(dense_mean))
+    dense_cov = K - K[:, rows] @ G @ K[rows, :]
+    low_rank_cov = m.basis @ (D[:, None] * Minv * D[None, :]) @ m.basis.T
+    assert np.max(np.abs(low_rank_cov - dense_cov)) < 1e-9 * np.max(np.abs(K))
+
+
+def test_closest_on_triangle_against_constrained_least_squares(oracle):
+    """Independent of the region walk: the closest point of a triangle is the minimiser of |a + u e1 + v e2 - q|^2 over
+    u, v >= 0, u + v <= 1, a convex QP solved here by enumerating its KKT candidates in closed form (interior stationary
+    point, the three edge projections clamped to [0, 1]) -- random, skinny and near-degenerate triangles."""
+    rng = np.random.default_rng(21)
+    worst = 0.0
+    for trial in range(300):
+        a, b, c = rng.normal(size=(3, 3)) * rng.choice([1.0, 1e-3, 50.0])
+        if trial % 5 == 0:
+            c = a + (b - a) * rng.uniform(0.2, 0.8) + 1e-4 * rng.normal(size=3)      # sliver
+        q = rng.normal(size=3) * rng.choice([0.5, 5.0, 100.0])
+        cands = []
+        e1, e2 = b - a, c - a
+        Gm = np.array([[e1 @ e1, e1 @ e2], [e1 @ e2, e2 @ e2]])
+        if abs(np.linalg.det(Gm)) > 1e-300:
+            u, v = np.linalg.solve(Gm, np.array([e1 @ (q - a), e2 @ (q - a)]))
+            if u >= 0 and v >= 0 and u + v <= 1:
+                cands.append(a + u * e1 + v * e2)
+        for p0, p1 in ((a, b), (b, c), (c, a)):
+            d = p1 - p0
+            s = np.clip(d @ (q - p0) / (d @ d), 0.0, 1.0)
+            cands.append(p0 + s * d)
+        best = min(np.linalg.norm(q - x) for x in cands)
+        cp, d2, _ = oracle.closest_on_surface(q[None], np.array([a, b, c]), np.array([[0, 1, 2]], dtype=np.int32))
+        got = np.linalg.norm(q - cp[0])
+        scale = max(best, np.linalg.norm(b - a), 1e-12)
+        worst = max(worst, abs(got - best) / scale)
+        assert abs(np.sqrt(d2[0]) - got) <= 1e-12 * scale
+    assert worst < 1e-9, worst
