@@ -315,3 +315,35 @@ def test_closest_on_triangle_against_constrained_least_squares(oracle):
         worst = max(worst, abs(got - best) / scale)
         assert abs(np.sqrt(d2[0]) - got) <= 1e-12 * scale
     assert worst < 1e-9, worst
+
+
+def test_umeyama_is_the_least_squares_optimum_on_noisy_pairs(oracle):
+    """Independent of the SVD recipe: on NOISY correspondences the rigid result must be the minimiser of
+    sum |R x + t - y|^2 over rotations (checked against scipy's Kabsch implementation and by perturbation), and the
+    similarity scale the minimiser of the same residual in s for the returned R."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(8)
+    X = _cloud(80, 5)
+    R0 = oracle.euler_to_matrix(-0.4, 0.25, 0.6)
+    Y = 1.3 * (X @ R0.T) + np.array([2.0, -1.0, 0.5]) + 0.3 * rng.normal(size=X.shape)
+
+    def resid(R, t, s):
+        return float(np.sum((s * (X @ R.T) + t - Y) ** 2))
+    R, t, s = oracle.umeyama(X, Y, False)
+    assert s == 1.0 and abs(np.linalg.det(R) - 1.0) < 1e-12
+    Rk, _ = Rotation.align_vectors(Y - Y.mean(0), X - X.mean(0))
+    np.testing.assert_allclose(R, Rk.as_matrix(), atol=1e-9)
+    np.testing.assert_allclose(t, Y.mean(0) - R @ X.mean(0), atol=1e-12)
+    base = resid(R, t, 1.0)
+    for _ in range(20):
+        dR = Rotation.from_rotvec(1e-3 * rng.normal(size=3)).as_matrix()
+        assert resid(dR @ R, Y.mean(0) - dR @ R @ X.mean(0), 1.0) >= base - 1e-9
+    R, t, s = oracle.umeyama(X, Y, True)
+    Xc, Yc = X - X.mean(0), Y - Y.mean(0)
+    s_opt = np.sum(Yc * (Xc @ R.T)) / np.sum(Xc * Xc)                # d/ds of the residual = 0
+    assert abs(s - s_opt) < 1e-12 and abs(s - 1.3) < 0.05
+    np.testing.assert_allclose(t, Y.mean(0) - s * (R @ X.mean(0)), atol=1e-12)
+    # reflection case: the data prefer an improper map; the result must still be a rotation
+    Yr = X * np.array([1.0, 1.0, -1.0]) + 0.01 * rng.normal(size=X.shape)
+    Rr, _, _ = oracle.umeyama(X, Yr, False)
+    assert abs(np.linalg.det(Rr) - 1.0) < 1e-12
