@@ -347,3 +347,36 @@ def test_umeyama_is_the_least_squares_optimum_on_noisy_pairs(oracle):
     Yr = X * np.array([1.0, 1.0, -1.0]) + 0.01 * rng.normal(size=X.shape)
     Rr, _, _ = oracle.umeyama(X, Yr, False)
     assert abs(np.linalg.det(Rr) - 1.0) < 1e-12
+
+
+def test_line_mesh_nearest_against_linear_solves(oracle):
+    """Independent of Moeller-Trumbore: for every triangle solve  a + u (b - a) + v (c - a) = p + s d  as a 3x3 linear
+    system; an intersection is 0 <= u, v, u + v <= 1 (s of either sign: the line is infinite), the answer the nearest
+    one that is not p itself.  Queries off the mesh, so the 'drop points == p' rule plays no role here."""
+    from gingr_b200 import synthetic
+    rng = np.random.default_rng(31)
+    v, tri = synthetic.sphere_mesh(120)
+    p = rng.normal(size=(40, 3)) * 60.0                         # inside, outside and far outside the radius-100 sphere
+    p[::4] *= 4.0
+    d = rng.normal(size=p.shape)
+    dist, hit = oracle.line_mesh_nearest(p, d, v, tri)
+    for i in range(len(p)):
+        best, bh = np.inf, p[i]
+        for t in tri:
+            a, b, c = v[t]
+            A = np.column_stack([b - a, c - a, -d[i]])
+            if abs(np.linalg.det(A)) < 1e-12:
+                continue
+            u, w, s = np.linalg.solve(A, p[i] - a)
+            if u >= 0 and w >= 0 and u + w <= 1:
+                x = p[i] + s * d[i]
+                if np.linalg.norm(x - p[i]) < best:
+                    best, bh = np.linalg.norm(x - p[i]), x
+        if np.isinf(best):
+            assert np.isinf(dist[i])
+        else:
+            assert abs(dist[i] - best) <= 1e-9 * max(best, 1.0), (i, dist[i], best)
+            assert np.linalg.norm(hit[i] - bh) <= 1e-8 * max(best, 1.0)
+    inside = np.linalg.norm(p, axis=1) < 90.0
+    assert inside.any() and np.all(np.isfinite(dist[inside]))      # a line through an interior point always hits a closed mesh
+    assert np.isinf(dist).any()                                    # and some far lines miss it
