@@ -380,3 +380,27 @@ def test_line_mesh_nearest_against_linear_solves(oracle):
     inside = np.linalg.norm(p, axis=1) < 90.0
     assert inside.any() and np.all(np.isfinite(dist[inside]))      # a line through an interior point always hits a closed mesh
     assert np.isinf(dist).any()                                    # and some far lines miss it
+
+
+@pytest.mark.parametrize("sigma2,w", [(25.0, 0.1), (1.0, 0.0), (400.0, 0.5)])
+def test_estep_reductions_against_extended_precision(oracle, sigma2, w):
+    """Independent evaluation of P1, P^T 1 and P X in 80-bit arithmetic (numpy longdouble) straight from the definition
+    (CPD.scala:54-75), both oracle variants: the FP64 restatement is within 1e-12 relative of it."""
+    if np.finfo(np.longdouble).eps >= np.finfo(np.float64).eps:
+        pytest.skip("no extended precision on this platform")
+    rng = np.random.default_rng(17)
+    M, N = 70, 90
+    fit = rng.normal(size=(M, 3)) * 20.0
+    tgt = fit[rng.integers(0, M, N)] + rng.normal(size=(N, 3)) * np.sqrt(sigma2)
+    L = np.longdouble
+    f, t = fit.astype(L), tgt.astype(L)
+    d2 = ((t[None, :, :] - f[:, None, :]) ** 2).sum(-1)
+    K = np.exp(-d2 / (L(2) * L(sigma2)))
+    c = (L(2) * L(np.pi) * L(sigma2)) ** (L(3) / L(2)) * L(w) / (L(1) - L(w)) * L(M) / L(N)
+    P = K / (K.sum(0) + c)[None, :]
+    P1, Pt1, PX = P.sum(1), P.sum(0), P @ t
+    for fast in (False, True):
+        g1, gt1, gx = oracle.cpd_estep(fit, tgt, sigma2, w, fast=fast)
+        assert np.max(np.abs(g1 - P1) / P1.max()) < 1e-12
+        assert np.max(np.abs(gt1 - Pt1)) < 1e-12
+        assert np.max(np.abs(gx - PX)) < 1e-12 * float(np.max(np.abs(PX)))
