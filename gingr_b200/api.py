@@ -760,8 +760,9 @@ class SimpleTriangleModels3D:
 class SimpleRegistrator:
     """Host mirror of api/registration/SimpleRegistrator.scala:34-158 over device handles: run / runDecimated with the
     hand-over of (pose, scale, shape) between resolution levels (examples/DemoMultiResolution.scala:39-47).  The
-    decimated reference and target meshes are the caller's (scalismo's quadric `decimate` is not part of the hot path);
-    the re-referenced model is built on the device from the resident basis (Model.newReference)."""
+    decimated reference and target meshes are the caller's, or come from gingr_b200.decimate when point counts are given
+    (scalismo's quadric `decimate` lives in scalismo; SURVEY.md 8c states the substitution); the re-referenced model is
+    built on the device from the resident basis (Model.newReference)."""
 
     def __init__(self, ctx: Context, algorithm, config, model: Model, target: Target, evaluatorUncertainty: float = 1.0,
                  evaluationMode: int = EVAL_MODEL_TO_TARGET, logFileFittingParameters: Optional[str] = None,
@@ -839,7 +840,16 @@ class SimpleRegistrator:
     def runDecimated(self, decimatedReference, decimatedTarget, generalState=None,
                      globalTransformation: int = RIGID_TRANSFORMS, probabilistic: bool = False, randomMixture: float = 0.5,
                      callback=None, seed: int = 0) -> GeneralRegistrationState:
-        """decimatedReference / decimatedTarget: (points, triangles) of the decimated meshes (:84-106)."""
+        """decimateState + run (:58-70, :84-106).  decimatedReference / decimatedTarget: either the number of points, as in
+        the reference (runDecimated(modelPoints, targetPoints, ...)) -- the meshes are then decimated by
+        gingr_b200.decimate (shortest-edge collapse, the stated stand-in for scalismo's quadric decimate) -- or the
+        (points, triangles) of meshes the caller decimated."""
+        if isinstance(decimatedReference, (int, np.integer)):
+            from .decimate import decimate
+            decimatedReference = decimate(self.model.reference, self.model.triangles, int(decimatedReference))
+        if isinstance(decimatedTarget, (int, np.integer)):
+            from .decimate import decimate
+            decimatedTarget = decimate(self.target.points, self.target.triangles, int(decimatedTarget))
         dm = self.model.newReference(*decimatedReference)
         dt = Target(self.ctx, *decimatedTarget)
         try:

@@ -259,3 +259,58 @@ def test_gingr_interface_options_reach_the_registration(monkeypatch):
     gi.ICP().run(generalState=st)
     assert calls["init"][0] is not None and calls["init"][2] is None
     assert isinstance(calls["config"], api.IcpConfiguration)
+
+
+def test_run_decimated_accepts_point_counts(monkeypatch):
+    """runDecimated(modelPoints, targetPoints, ...) (SimpleRegistrator.scala:58-70): integer arguments decimate the model's
+    reference and the target on the host, then re-reference / upload; tuples are taken as given."""
+    from gingr_b200 import api, synthetic
+    made = {}
+    rv, rt = synthetic.sphere_mesh(400)
+    tv, tt = synthetic.sphere_mesh(500)
+
+    class FakeModel:
+        M, reference, triangles = 400, rv, rt
+
+        def newReference(self, pts, tri=None):
+            made["ref"] = (np.asarray(pts), np.asarray(tri))
+            return self
+
+        def instance(self, p):
+            return np.zeros((400, 3))
+
+        def close(self):
+            made["model_closed"] = True
+
+    class FakeTarget:
+        def __init__(self, ctx=None, pts=tv, tri=tt):
+            self.points, self.triangles, self.N = np.asarray(pts), np.asarray(tri), len(pts)
+            made.setdefault("targets", []).append(self)
+
+        def close(self):
+            made["target_closed"] = True
+
+    pars = api.ModelFittingParameters(1.0, np.zeros(3), (0.0, 0.0, 0.0), np.zeros(2))
+    st = api.GeneralRegistrationState(pars, np.zeros((2, 3)))
+
+    class FakeReg:
+        def __init__(self, ctx, model, target, config):
+            made["run_target"] = target
+
+        def initializeState(self, general=None, globalTransformation=None):
+            return st
+
+        def run(self, state, callback=None):
+            return state
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(api, "Target", FakeTarget)
+    sr = api.SimpleRegistrator(None, FakeReg, api.CpdConfiguration(), FakeModel(), FakeTarget())
+    sr.runDecimated(60, 80)
+    assert made["ref"][0].shape == (60, 3) and made["ref"][1].max() == 59
+    assert made["run_target"].N == 80 and made["run_target"] is not sr.target
+    assert made["model_closed"] and made["target_closed"]
+    sr.runDecimated((rv[:50], None), (tv[:70], None))
+    assert made["ref"][0].shape == (50, 3) and made["run_target"].N == 70
