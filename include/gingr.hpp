@@ -174,6 +174,36 @@ struct IcpConfiguration {
   }
 };
 
+// sampling/evaluators/IndependentPointDistanceEvaluator.scala:26-32
+enum class EvaluationMode : int32_t { ModelToTargetEvaluation = GINGR_EVAL_MODEL_TO_TARGET,
+                                      TargetToModelEvaluation = GINGR_EVAL_TARGET_TO_MODEL, SymmetricEvaluation = GINGR_EVAL_SYMMETRIC };
+
+// ProbabilisticSettings(IndependentPoints(state, uncertainty, mode, evaluatedPoints), randomMixture)
+// (api/GingrAlgorithm.scala:40-50, sampling/Evaluator.scala:43-60) with the widths of Generator.DefaultRandom
+// (sampling/Generator.scala:27-83).  Empty id lists: all points are compared.
+struct ProbabilisticSettings {
+  double uncertainty = 1.0;
+  EvaluationMode mode = EvaluationMode::ModelToTargetEvaluation;
+  double randomMixture = 0.5;
+  std::vector<int32_t> modelPointIds, targetPointIds;
+  std::array<double, 3> rotationSdev{0.01, 0.01, 0.01};    // yaw, pitch, roll
+  std::array<double, 3> translationSdev{0.1, 0.1, 0.1};
+  std::array<double, 3> shapeSteps{1.0, 0.1, 0.01};
+
+  gingr_mcmc_settings toPod() const {
+    gingr_mcmc_settings m{};
+    m.random_mixture = randomMixture;
+    m.uncertainty = uncertainty;
+    m.evaluation_mode = static_cast<int32_t>(mode);
+    for (int d = 0; d < 3; ++d) {
+      m.rot_sdev[d] = rotationSdev[d];
+      m.trans_sdev[d] = translationSdev[d];
+      m.shape_sdev[d] = shapeSteps[d];
+    }
+    return m;
+  }
+};
+
 // scalismo PointDistributionModel on the device
 class Model {
  public:
@@ -330,9 +360,48 @@ class GingrAlgorithm {
     return state;
   }
 
+  // ---- probabilistic registration (GingrAlgorithm.run with ProbabilisticSettings, :115-190) ----
+  void configureProbabilistic(const ProbabilisticSettings& s) {
+    const gingr_mcmc_settings pod = s.toPod();
+    ctx_->check(gingr_mcmc_configure(h_, &pod, s.modelPointIds.empty() ? nullptr : s.modelPointIds.data(),
+                                     static_cast<int32_t>(s.modelPointIds.size()),
+                                     s.targetPointIds.empty() ? nullptr : s.targetPointIds.data(),
+                                     static_cast<int32_t>(s.targetPointIds.size())));
+  }
+  // (Prior, Distance) log values of the evaluators (sampling/Evaluator.scala:43-60); their sum is the product evaluator.
+  // Replaces the device-resident state: call before initializeState, not between it and a chain.
+  std::pair<double, double> logValue(const State& state) const {
+    const gingr_state pod = state.toPod();
+    double out[2] = {0.0, 0.0};
+    ctx_->check(gingr_evaluate_log_value(h_, &pod, state.modelParameters.shape.data(), out));
+    return {out[0], out[1]};
+  }
+  // `iters` Metropolis-Hastings steps on the device from the device-resident state (initializeState / update first)
+  void mcmcChain(int iters, uint64_t seed) { ctx_->check(gingr_mcmc_chain(h_, iters, seed)); }
+  State downloadState() const { return download(&gingr_state_download); }
+  State mcmcBest() const { return download(&gingr_mcmc_best); }
+  // run(...) with probabilisticSettings: maxIterations - 1 steps, the best sample is returned (:160-171)
+  State runProbabilistic(const State& initial, const ProbabilisticSettings& settings, uint64_t seed = 0) {
+    configureProbabilistic(settings);
+    initializeState(initial);
+    mcmcChain(config_.maxIterations > 1 ? config_.maxIterations - 1 : 0, seed);
+    State best = mcmcBest();
+    if (best.status == FittingStatus::None) best.status = FittingStatus::MaxIteration;
+    return best;
+  }
+
   gingr_registration* handle() const { return h_; }
 
  private:
+  State download(int32_t (*fn)(gingr_registration*, gingr_state*, double*, double*)) const {
+    State s;
+    gingr_state pod{};
+    s.modelParameters.shape.resize(model_->rank());
+    s.fit.resize(static_cast<size_t>(3) * model_->points());
+    ctx_->check(fn(h_, &pod, s.modelParameters.shape.data(), s.fit.data()));
+    s.fromPod(pod);
+    return s;
+  }
   const Context* ctx_;
   const Model* model_;
   Config config_;

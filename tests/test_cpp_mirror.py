@@ -34,6 +34,9 @@ def test_defaults_and_pod_conversion_match_the_python_mirror(built_library, tmp_
     src.write_text(r'''
 #include <cstdio>
 #include "gingr.hpp"
+// explicit instantiation: every member of both algorithm classes must compile, not only the ones used below
+template class gingr::GingrAlgorithm<gingr::CpdConfiguration>;
+template class gingr::GingrAlgorithm<gingr::IcpConfiguration>;
 int main() {
   gingr::CpdConfiguration c; gingr::IcpConfiguration k; gingr::GeneralRegistrationState s;
   s.modelParameters.shape = {0.5, -1.5, 2.0}; s.modelParameters.euler = {0.1, 0.2, 0.3}; s.iteration = 7; s.sigma2 = 2.5;
@@ -50,6 +53,9 @@ int main() {
               p.rank, p.iteration, p.sigma2, p.euler[2], back.iteration, (int)back.globalTransformation,
               cp.algorithm, cp.has_initial_sigma, kp.algorithm, kp.has_initial_sigma, kp.initial_sigma,
               gingr::CpdConfiguration::name, gingr::IcpConfiguration::name, sizeof(gingr_state), sizeof(gingr_config));
+  gingr::ProbabilisticSettings ps; const gingr_mcmc_settings mp = ps.toPod();
+  std::fprintf(stderr, "%.17g %.17g %d %.17g %.17g %.17g %.17g %zu\n", mp.random_mixture, mp.uncertainty, mp.evaluation_mode,
+               mp.rot_sdev[0], mp.trans_sdev[2], mp.shape_sdev[0], mp.shape_sdev[2], sizeof(gingr_mcmc_settings));
   gingr::CpdConfiguration c2; c2.initialSigma = 4.0;
   return (c2.toPod().has_initial_sigma == 1 && c2.toPod().initial_sigma == 4.0 && !k.converged(s, s, 1.0) &&
           c.converged(s, back, 1e-10) ) ? 0 : 3;
@@ -70,6 +76,11 @@ int main() {
     assert got["cfg"] == [api.ALGO_CPD, 0, api.ALGO_ICP, 1, 100.0]
     assert got["names"] == ["CPD", "ICP"]
     assert got["sizes"] == [ctypes.sizeof(nat.GingrState), ctypes.sizeof(nat.GingrConfig)]
+    ps = api.ProbabilisticSettings()
+    vals = p.stderr.split()
+    assert [float(v) for v in vals[:2]] == [ps.randomMixture, ps.uncertainty] and int(vals[2]) == ps.mode
+    assert [float(v) for v in vals[3:7]] == [ps.rotationSdev[0], ps.translationSdev[2], ps.shapeSteps[0], ps.shapeSteps[2]]
+    assert int(vals[7]) == ctypes.sizeof(nat.GingrMcmcSettings)
 
 
 def test_cpp_demo_links_and_fails_loudly_without_a_device(built_library, tmp_path):
