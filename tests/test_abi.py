@@ -64,3 +64,25 @@ def test_product_does_not_import_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle|libgingr_oracle|oracle/", txt, flags=re.M):
                     bad.append(os.path.join(root, f))
     assert not bad, bad
+
+
+def test_header_is_plain_c99():
+    """The boundary is a C ABI: the header must compile as strict C99 (no C++-isms), and the struct sizes the C compiler
+    sees are the ones the ctypes mirrors use."""
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from gingr_b200 import _native as nat
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        with open(src, "w") as f:
+            f.write('#include <stdio.h>\n#include "gingr_cuda.h"\nint main(void) { printf("%u %u %u\\n", (unsigned)sizeof(gingr_state), '
+                    '(unsigned)sizeof(gingr_config), (unsigned)sizeof(gingr_mcmc_settings)); return 0; }\n')
+        exe = os.path.join(d, "t")
+        p = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                            src, "-o", exe], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(nat.GingrState), ctypes.sizeof(nat.GingrConfig), ctypes.sizeof(nat.GingrMcmcSettings)]
