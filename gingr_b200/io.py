@@ -259,12 +259,18 @@ def read_stl(path: str) -> Tuple[np.ndarray, np.ndarray]:
         if len(raw) == 84 + 50 * nt:
             rec = np.frombuffer(raw, dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]), count=nt, offset=84)
             return _merge_vertices(rec["v"])
-    text = raw.decode("ascii", errors="strict")
+    try:
+        text = raw.decode("ascii", errors="strict")
+    except UnicodeDecodeError:
+        text = ""
     if not text.lstrip().startswith("solid"):
         raise ValueError(f"{path}: neither a binary STL (size mismatch) nor an ASCII STL")
     vals = [ln.split()[1:4] for ln in text.splitlines() if ln.strip().startswith("vertex")]
-    corners = np.asarray(vals, dtype=np.float32)
-    if corners.size == 0 or corners.shape[0] % 3 != 0:
+    try:
+        corners = np.asarray(vals, dtype=np.float32)
+    except ValueError:
+        raise ValueError(f"{path}: malformed ASCII STL (vertex records)")
+    if corners.size == 0 or corners.ndim != 2 or corners.shape[1] != 3 or corners.shape[0] % 3 != 0:
         raise ValueError(f"{path}: malformed ASCII STL")
     return _merge_vertices(corners.reshape(-1, 3, 3))
 
@@ -292,7 +298,21 @@ _PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short":
 
 def read_ply(path: str) -> Tuple[np.ndarray, np.ndarray]:
     """PLY (ascii, binary_little_endian or binary_big_endian) with a vertex element (x, y, z + any other scalar
-    properties) and a face element with one list property of triangles -> (vertices float64, triangles int32)."""
+    properties) and a face element with one list property of triangles -> (vertices float64, triangles int32).
+    A truncated, inconsistent or non-triangle file raises ValueError (scalismo's MeshIO returns a failed Try)."""
+    try:
+        verts, tris = _read_ply(path)
+    except (IndexError, KeyError, UnicodeDecodeError) as e:
+        raise ValueError(f"{path}: malformed PLY ({type(e).__name__}: {e})")
+    if verts is None:
+        raise ValueError(f"{path}: no vertex element")
+    tris = np.zeros((0, 3), dtype=np.int32) if tris is None else tris
+    if tris.size and (tris.min() < 0 or tris.max() >= verts.shape[0]):
+        raise ValueError(f"{path}: face index out of range")
+    return verts, tris
+
+
+def _read_ply(path: str):
     with open(path, "rb") as f:
         raw = f.read()
     end = raw.find(b"end_header")
@@ -331,7 +351,11 @@ def read_ply(path: str) -> Tuple[np.ndarray, np.ndarray]:
                 for r in rows:
                     if int(r[0]) != 3:
                         raise ValueError(f"{path}: only triangle faces are supported")
+                    if len(r) < 4:
+                        raise ValueError(f"{path}: truncated face record")
                 tris = np.asarray([[int(v) for v in r[1:4]] for r in rows], dtype=np.int32).reshape(-1, 3)
+            if len(rows) != el["count"] or any(len(r) == 0 for r in rows):
+                raise ValueError(f"{path}: element {el['name']} has fewer records than its header says")
         return verts, tris
     bo = "<" if fmt == "binary_little_endian" else ">"
     off = 0
@@ -353,9 +377,7 @@ def read_ply(path: str) -> Tuple[np.ndarray, np.ndarray]:
             off += dt.itemsize * el["count"]
             if el["name"] == "face":
                 tris = arr["v"].astype(np.int32)
-    if verts is None:
-        raise ValueError(f"{path}: no vertex element")
-    return verts, (np.zeros((0, 3), dtype=np.int32) if tris is None else tris)
+    return verts, tris
 
 
 def write_ply(path: str, vertices, triangles, binary: bool = True) -> None:

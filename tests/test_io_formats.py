@@ -180,3 +180,36 @@ def test_logger_statistics_and_precomputed_values():
     for k in range(8):
         (lg2.reject if k == 0 else lg2.accept)(s, {})
     assert lg2.percentRejected == 0.13                                                  # 0.125 rounds half UP
+
+
+def test_malformed_mesh_files_raise_value_error(tmp_path):
+    """MeshIO.readMesh returns a failed Try on unreadable files; here every malformed file is a ValueError (never an
+    IndexError / UnicodeDecodeError, never a mesh with dangling indices)."""
+    from gingr_b200 import io
+    hdr = (b"ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+           b"element face 1\nproperty list uchar int vertex_indices\nend_header\n")
+    cases = {
+        "empty.stl": b"",
+        "garbage.stl": bytes(range(256)) * 3,
+        "truncated.stl": b"\0" * 80 + (5).to_bytes(4, "little") + b"\0" * 60,
+        "ragged.stl": b"solid x\nfacet normal 0 0 1\nouter loop\nvertex 0 0 0\nvertex 1 0\nvertex 0 1 0\nendloop\nendfacet\nendsolid x\n",
+        "two_corners.stl": b"solid x\nvertex 0 0 0\nvertex 1 0 0\nendsolid x\n",
+        "empty.ply": b"",
+        "header_only.ply": b"ply\nformat ascii 1.0\n",
+        "short_body.ply": hdr + b"0 0 0\n1 0 0\n",
+        "short_face.ply": hdr + b"0 0 0\n1 0 0\n0 1 0\n3 0 1\n",
+        "dangling_index.ply": hdr + b"0 0 0\n1 0 0\n0 1 0\n3 0 1 7\n",
+        "quad.ply": hdr.replace(b"vertex 3", b"vertex 4") + b"0 0 0\n1 0 0\n1 1 0\n0 1 0\n4 0 1 2 3\n",
+        "binary_truncated.ply": hdr.replace(b"ascii", b"binary_little_endian") + b"\0" * 20,
+        "unknown_format.ply": hdr.replace(b"ascii", b"binary_middle_endian") + b"\0" * 64,
+        "mesh.obj": b"v 0 0 0\n",
+    }
+    for name, data in cases.items():
+        p = tmp_path / name
+        p.write_bytes(data)
+        with pytest.raises(ValueError):
+            io.read_mesh(str(p))
+    good = tmp_path / "ok.ply"
+    good.write_bytes(hdr + b"0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n")
+    v, t = io.read_mesh(str(good))
+    assert v.shape == (3, 3) and t.tolist() == [[0, 1, 2]]
