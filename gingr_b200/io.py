@@ -193,15 +193,25 @@ def read_landmarks(path: str) -> List[Landmark]:
     """scalismo LandmarkIO.readLandmarksJson3D layout."""
     with open(path) as f:
         data = json.load(f)
+    if not isinstance(data, list):
+        raise ValueError(f"{path}: a landmark file is a JSON array")
     out = []
     for d in data:
-        cov = None
-        u = d.get("uncertainty")
-        if u is not None:
-            sd = np.asarray(u["stddevs"], dtype=float)
-            pcs = np.asarray(u["pcvectors"], dtype=float)      # rows = principal axes
-            cov = pcs.T @ np.diag(sd ** 2) @ pcs
-        out.append(Landmark(str(d["id"]), np.asarray(d["coordinates"], dtype=float), cov))
+        try:
+            cov = None
+            u = d.get("uncertainty")
+            if u is not None:
+                sd = np.asarray(u["stddevs"], dtype=float)
+                pcs = np.asarray(u["pcvectors"], dtype=float)      # rows = principal axes
+                if sd.shape != (3,) or pcs.shape != (3, 3):
+                    raise ValueError("uncertainty needs 3 stddevs and 3 x 3 pcvectors")
+                cov = pcs.T @ np.diag(sd ** 2) @ pcs
+            point = np.asarray(d["coordinates"], dtype=float)
+            if point.shape != (3,):
+                raise ValueError("coordinates need 3 components")
+            out.append(Landmark(str(d["id"]), point, cov))
+        except (KeyError, TypeError, AttributeError) as e:
+            raise ValueError(f"{path}: not a scalismo landmark record ({type(e).__name__}: {e})")
     return out
 
 

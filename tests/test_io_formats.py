@@ -213,3 +213,19 @@ def test_malformed_mesh_files_raise_value_error(tmp_path):
     good.write_bytes(hdr + b"0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n")
     v, t = io.read_mesh(str(good))
     assert v.shape == (3, 3) and t.tolist() == [[0, 1, 2]]
+
+
+def test_malformed_landmark_files_raise_value_error(tmp_path):
+    from gingr_b200 import io
+    bad = ['{"id": "A"}', '[{"id": "A"}]', '[{"id": "A", "coordinates": [1, 2]}]', '[3]',
+           '[{"id": "A", "coordinates": [1, 2, 3], "uncertainty": {"stddevs": [1, 2], "pcvectors": [[1, 0, 0], [0, 1, 0], [0, 0, 1]]}}]',
+           '[{"id": "A", "coordinates": [1, 2, 3], "uncertainty": {"stddevs": [1, 2, 3]}}]']
+    for k, text in enumerate(bad):
+        p = tmp_path / f"lm{k}.json"
+        p.write_text(text)
+        with pytest.raises(ValueError):
+            io.read_landmarks(str(p))
+    ok = tmp_path / "ok.json"
+    ok.write_text('[{"id": "A", "coordinates": [1, 2, 3], "uncertainty": {"stddevs": [1, 2, 3], "pcvectors": [[0, 1, 0], [1, 0, 0], [0, 0, 1]]}}]')
+    lm = io.read_landmarks(str(ok))[0]
+    assert lm.id == "A" and np.allclose(np.diag(lm.covariance), [4.0, 1.0, 9.0])
