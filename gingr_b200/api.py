@@ -114,7 +114,8 @@ class Model:
         var = nat.f64(variance).reshape(-1)
         self.rank = var.shape[0]
         basis = np.asarray(basis, dtype=np.float64)
-        assert basis.shape == (3 * self.M, self.rank), basis.shape
+        if mean.shape != (3 * self.M,) or basis.shape != (3 * self.M, self.rank):
+            raise ValueError(f"model arrays: mean must be [3M], basis [3M, r]; got {mean.shape}, {basis.shape} for M = {self.M}, r = {self.rank}")
         basis_f = np.asfortranarray(basis)   # Breeze column-major layout; ld = 3M
         tri = None if triangles is None else nat.i32(triangles).reshape(-1, 3)
         self.T = 0 if tri is None else tri.shape[0]
@@ -134,7 +135,8 @@ class Model:
         ref = nat.f64(ref_points).reshape(-1, 3)
         tri = None if triangles is None else nat.i32(triangles).reshape(-1, 3)
         sg, sc = nat.f64(np.atleast_1d(sigmas)), nat.f64(np.atleast_1d(scalings))
-        assert sg.shape == sc.shape
+        if sg.shape != sc.shape or sg.ndim != 1:
+            raise ValueError("gaussianMixture: one scaling per sigma")
         h = ctypes.c_void_p()
         rank = ctypes.c_int32()
         ctx.check(ctx._lib.gingr_gpmm_gaussian_mixture(ctx.handle, ref.shape[0], nat.as_dp(ref), nat.as_ip(tri),

@@ -314,3 +314,14 @@ def test_run_decimated_accepts_point_counts(monkeypatch):
     assert made["model_closed"] and made["target_closed"]
     sr.runDecimated((rv[:50], None), (tv[:70], None))
     assert made["ref"][0].shape == (50, 3) and made["run_target"].N == 70
+
+
+def test_model_constructor_rejects_inconsistent_arrays_before_touching_the_library():
+    from gingr_b200 import api
+    ref = np.zeros((4, 3))
+    with pytest.raises(ValueError):
+        api.Model(None, ref, np.zeros(12), np.zeros((11, 2)), np.ones(2))          # basis rows != 3M
+    with pytest.raises(ValueError):
+        api.Model(None, ref, np.zeros(9), np.zeros((12, 2)), np.ones(2))           # mean length != 3M
+    with pytest.raises(ValueError):
+        api.Model.gaussianMixture(None, ref, None, [1.0, 2.0], [1.0])
