@@ -1,5 +1,6 @@
 """The drop-in boundary: libgingr_cuda.so loads, exports every symbol include/gingr_cuda.h declares, the
 ctypes table covers the header, and the product fails loudly (no CPU fallback) without a GPU."""
+import pathlib
 import ctypes
 import os
 import re
@@ -10,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def header_functions():
-    src = open(os.path.join(ROOT, "include", "gingr_cuda.h")).read()
+    src = pathlib.Path(os.path.join(ROOT, "include", "gingr_cuda.h")).read_text()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return re.findall(r"GINGR_API\s+[\w\s\*]+?\b(gingr_\w+)\s*\(", src)
 
@@ -60,7 +61,7 @@ def test_product_does_not_import_oracle():
     for root, _, files in os.walk(os.path.join(ROOT, "gingr_b200")):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
-                txt = open(os.path.join(root, f), errors="ignore").read()
+                txt = pathlib.Path(os.path.join(root, f)).read_text(errors="ignore")
                 if re.search(r"^\s*(from|import)\s+oracle|libgingr_oracle|oracle/", txt, flags=re.M):
                     bad.append(os.path.join(root, f))
     assert not bad, bad

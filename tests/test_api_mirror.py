@@ -1,6 +1,7 @@
 """The Python mirror of the reference's configuration / state classes (gingr_b200/api.py): names and DEFAULTS must be the
 reference's (checked against the Scala sources when the reference tree is mounted), and the POD round trips are lossless.
 No GPU."""
+import pathlib
 import dataclasses
 import os
 import re
@@ -14,7 +15,7 @@ needs_reference = pytest.mark.skipif(not os.path.isdir(REF), reason="reference s
 
 def _case_class_defaults(path, name):
     """{field: default literal} of `case class name(...)` in a Scala file (fields with a default only)."""
-    src = open(path).read()
+    src = pathlib.Path(path).read_text()
     start = src.index("case class " + name)
     depth, i = 0, src.index("(", start)
     j = i
@@ -60,7 +61,7 @@ def test_configuration_defaults_are_the_references():
     assert int(gs["iteration"]) == s.iteration and gs["status"] == "FittingStatuses.None" and s.status == api.STATUS_NONE
     ps = _case_class_defaults(os.path.join(REF, "api/GingrAlgorithm.scala"), "ProbabilisticSettings")
     assert _num(ps["randomMixture"]) == api.ProbabilisticSettings().randomMixture
-    gen = open(os.path.join(REF, "api/sampling/Generator.scala")).read()
+    gen = pathlib.Path(os.path.join(REF, "api/sampling/Generator.scala")).read_text()
     assert "defaultTranslation = 0.1" in gen and "defaultRotation = 0.01" in gen and "Seq(1.0, 0.1, 0.01)" in gen
     p = api.ProbabilisticSettings()
     assert p.translationSdev == (0.1, 0.1, 0.1) and p.rotationSdev == (0.01, 0.01, 0.01) and p.shapeSteps == (1.0, 0.1, 0.01)
@@ -69,14 +70,14 @@ def test_configuration_defaults_are_the_references():
 @needs_reference
 def test_enumerations_follow_the_reference_order():
     from gingr_b200 import api
-    fs = open(os.path.join(REF, "api/FittingStatuses.scala")).read()
+    fs = pathlib.Path(os.path.join(REF, "api/FittingStatuses.scala")).read_text()
     order = re.search(r"val\s+(\w+)\s*,\s*(\w+)\s*,\s*(\w+)\s*,\s*(\w+)\s*=\s*Value", fs)
     assert order and [x for x in order.groups()] == ["None", "MaxIteration", "Converged", "ModelFlexibilityError"]
     assert (api.STATUS_NONE, api.STATUS_MAX_ITERATION, api.STATUS_CONVERGED, api.STATUS_MODEL_FLEXIBILITY_ERROR) == (0, 1, 2, 3)
-    icp = open(os.path.join(REF, "api/registration/config/ICP.scala")).read()
+    icp = pathlib.Path(os.path.join(REF, "api/registration/config/ICP.scala")).read_text()
     names = re.findall(r"case object (\w+ClosestPoint) extends ICPCorrespondenceMethod", icp)
     assert set(names) == {"TriangularClosestPoint", "AlongNormalClosestPoint", "PointcloudClosestPoint"}
-    modes = open(os.path.join(REF, "api/sampling/evaluators/IndependentPointDistanceEvaluator.scala")).read()
+    modes = pathlib.Path(os.path.join(REF, "api/sampling/evaluators/IndependentPointDistanceEvaluator.scala")).read_text()
     assert re.findall(r"case object (\w+) extends EvaluationMode", modes) == ["ModelToTargetEvaluation", "TargetToModelEvaluation", "SymmetricEvaluation"]
     assert (api.EVAL_MODEL_TO_TARGET, api.EVAL_TARGET_TO_MODEL, api.EVAL_SYMMETRIC) == (0, 1, 2)
 

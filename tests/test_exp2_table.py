@@ -2,6 +2,7 @@
 table against an independent high-precision evaluation, and a BIT-EXACT emulation of the device routine (IEEE adds, FMAs
 through exact rationals, the integer exponent insertion) against the exact value over the whole argument range -- the
 accuracy claim of DESIGN.md for K1 without needing the device.  No GPU."""
+import pathlib
 import os
 import re
 import struct
@@ -16,7 +17,7 @@ NBIAS, KBIAS = 2048, 64
 
 
 def _parse():
-    src = open(os.path.join(ROOT, "gingr_b200", "csrc", "exp2_tab.cuh")).read()
+    src = pathlib.Path(os.path.join(ROOT, "gingr_b200", "csrc", "exp2_tab.cuh")).read_text()
     n = int(re.search(r"GAUSS_TAB_N = (\d+)", src).group(1))
     bits = int(re.search(r"GAUSS_TAB_BITS = (\d+)", src).group(1))
     rows = [(int(a, 16), int(b, 16)) for a, b in re.findall(r"\{0x([0-9a-f]{8})u, 0x([0-9a-f]{8})u\}", src)]

@@ -1,5 +1,6 @@
 """Wire / disk formats (gingr_b200/io.py): round trips, the reference's JSON layouts, and -- when
 the reference tree is mounted -- its own example files (the femur fixtures of tests/golden were generated from them)."""
+import pathlib
 import dataclasses
 import json
 import os
@@ -44,7 +45,7 @@ def test_json_state_logger_records(tmp_path):
     lg.reject(st)
     lg.accept(st)
     lg.write()
-    raw = json.load(open(tmp_path / "log.json"))
+    raw = json.loads(pathlib.Path(tmp_path / "log.json").read_text())
     assert [r["index"] for r in raw] == [0, 1, 2] and [r["status"] for r in raw] == [True, False, True]
     assert set(raw[0]) == {"index", "name", "logvalue", "status", "modelParameters", "translation", "rotation",
                            "rotationCenter", "scaling", "datetime"}                       # jsonLogFormat :36-47
@@ -96,11 +97,11 @@ def test_stl_round_trip_merges_vertices(tmp_path):
         "facet normal 0 0 0\n outer loop\n" + "".join(f"  vertex {p[0]} {p[1]} {p[2]}\n" for p in v[tri]) + " endloop\nendfacet\n"
         for tri in t) + "endsolid s\n"
     g = str(tmp_path / "a.stl")
-    open(g, "w").write(ascii_stl)
+    pathlib.Path(g).write_text(ascii_stl)
     v3, t3 = io.read_stl(g)
     assert np.array_equal(v3[t3], v[t])
     with pytest.raises(ValueError):
-        open(g, "wb").write(b"garbage" * 20)
+        pathlib.Path(g).write_bytes(b"garbage" * 20)
         io.read_stl(g)
 
 
@@ -140,7 +141,7 @@ def test_statistical_model_file_round_trip(tmp_path):
     ref, tri, m2, b2, v2 = io.read_statistical_model(p)
     assert np.array_equal(ref, v) and np.array_equal(tri, t) and tri.dtype == np.int32
     assert np.array_equal(m2, mean) and np.array_equal(b2, basis) and np.array_equal(v2, var)   # bit-exact, f64 kept
-    doc = json.load(open(p))
+    doc = json.loads(pathlib.Path(p).read_text())
     assert doc["representer"]["points"]["shape"] == [3, 4] and doc["representer"]["cells"]["shape"] == [3, 4]
     assert doc["model"]["pcaBasis"]["shape"] == [12, 5] and doc["model"]["noiseVariance"] == 0.0
     # point cloud model (no cells)

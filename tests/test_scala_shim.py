@@ -3,6 +3,7 @@ here (no JVM), so it is checked textually against include/gingr_cuda.h: every ex
 and each handle's FunctionDescriptor has the header's arity and argument classes (int32 -> JAVA_INT, 64-bit integers ->
 JAVA_LONG, double -> JAVA_DOUBLE, any pointer or array parameter -> ADDRESS).  The struct layouts are checked against
 the ctypes mirrors (sizes and field order).  No GPU."""
+import pathlib
 import ctypes
 import os
 import re
@@ -13,7 +14,7 @@ SHIM = os.path.join(ROOT, "scala", "gingr", "api", "registration", "cuda", "Ging
 
 
 def _header_prototypes():
-    h = open(HEADER).read()
+    h = pathlib.Path(HEADER).read_text()
     h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
     h = re.sub(r"//[^\n]*", "", h)
     out = {}
@@ -33,7 +34,7 @@ def _klass(decl: str) -> str:
 
 
 def _shim_handles():
-    s = open(SHIM).read()
+    s = pathlib.Path(SHIM).read_text()
     out = {}
     for m in re.finditer(r'fn\(\s*"(gingr_\w+)"\s*,([^)]*)\)', s):
         toks = [t.strip() for t in m.group(2).replace("\n", " ").split(",") if t.strip()]
@@ -80,5 +81,5 @@ def test_struct_layouts_match_the_ctypes_mirrors():
 
 
 def test_integration_notes_name_every_entry_point():
-    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    doc = pathlib.Path(os.path.join(ROOT, "INTEGRATION.md")).read_text()
     assert [n for n in _header_prototypes() if n not in doc] == []
