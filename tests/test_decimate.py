@@ -83,3 +83,30 @@ def test_point_cloud_and_edge_cases():
         decimate.decimate(v, t, 0)
     with pytest.raises(ValueError):
         decimate.decimate(v, t + 50, 10)
+
+
+def test_torus_keeps_its_genus():
+    """A closed surface of genus 1: V - E + F stays 0, every edge stays in two triangles, no fold-over against the input
+    normals (checked through the signed volume, which must keep its sign and most of its size)."""
+    from gingr_b200 import decimate
+    nu, nv, R, r = 60, 24, 10.0, 3.0
+    u, v = np.meshgrid(np.arange(nu) * 2 * np.pi / nu, np.arange(nv) * 2 * np.pi / nv, indexing="ij")
+    pts = np.c_[((R + r * np.cos(v)) * np.cos(u)).ravel(), ((R + r * np.cos(v)) * np.sin(u)).ravel(), (r * np.sin(v)).ravel()]
+    tri = []
+    for i in range(nu):
+        for j in range(nv):
+            a, b = i * nv + j, ((i + 1) % nu) * nv + j
+            c, d = i * nv + (j + 1) % nv, ((i + 1) % nu) * nv + (j + 1) % nv
+            tri += [[a, b, c], [b, d, c]]
+    tri = np.array(tri, dtype=np.int32)
+
+    def volume(p, t):
+        return float(np.einsum("ij,ij->i", p[t[:, 0]], np.cross(p[t[:, 1]], p[t[:, 2]])).sum() / 6.0)
+    v0 = volume(pts, tri)
+    for n in (600, 250):
+        dv, dt = decimate.decimate(pts, tri, n)
+        cnt = _edge_counts(dt)
+        assert len(dv) == n and np.all(cnt == 2)
+        assert len(dv) - len(cnt) + len(dt) == 0                       # Euler characteristic of a torus
+        v1 = volume(dv, dt)
+        assert np.sign(v1) == np.sign(v0) and 0.8 * abs(v0) < abs(v1) <= abs(v0) * 1.001
