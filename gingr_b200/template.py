@@ -20,10 +20,11 @@ from . import api
 from .rotation import euler_to_matrix, matrix_to_euler
 
 
-def umeyama(X: np.ndarray, Y: np.ndarray, similarity: bool) -> Tuple[np.ndarray, np.ndarray, float]:
+def umeyama(X: np.ndarray, Y: np.ndarray, similarity: bool, euler_round_trip: bool = True) -> Tuple[np.ndarray, np.ndarray, float]:
     """scalismo LandmarkRegistration.{rigid, similarity}3DLandmarkRegistration about the origin, as called from
-    GingrAlgorithm.scala:260-279 [scalismo-recalled, SURVEY A4]: x -> s R x + t minimising the squared residual; the
-    rotation goes through its Euler angles and back, as the state stores it (GeneralRegistrationState.scala:83-87)."""
+    GingrAlgorithm.scala:260-279 [scalismo-recalled, SURVEY A4]: x -> s R x + t minimising the squared residual; with
+    euler_round_trip the rotation goes through its Euler angles and back, as the state stores it
+    (GeneralRegistrationState.scala:83-87)."""
     n = X.shape[0]
     mx, my = X.mean(axis=0), Y.mean(axis=0)
     Xc, Yc = X - mx, Y - my
@@ -36,7 +37,8 @@ def umeyama(X: np.ndarray, Y: np.ndarray, similarity: bool) -> Tuple[np.ndarray,
     R = U @ J @ Vt
     s = float(np.trace(np.diag(D) @ J) / var_x) if similarity else 1.0
     t = my - s * (R @ mx)
-    R = euler_to_matrix(*matrix_to_euler(R))
+    if euler_round_trip:
+        R = euler_to_matrix(*matrix_to_euler(R))
     return R, t, s
 
 
