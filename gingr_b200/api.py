@@ -154,6 +154,16 @@ class Model:
         d = maximum_point_distance(ref_points)
         return Model.gaussianMixture(ctx, ref_points, triangles, [d / 4.0, d / 8.0], [d / 8.0, d / 16.0], relativeTolerance, maxRank)
 
+    @staticmethod
+    def automaticGPMMfromTemplate(ctx: Context, ref_points, triangles, relativeTolerance: float = 0.1, maxRank: int = 0) -> "Model":
+        """GPMMHelper.automaticGPMMfromTemplate (api/registration/utils/GPMMHelper.scala:38-68): three Gaussian kernels from
+        the largest point distance d and the smallest nearest-neighbour distance e: (sigma, scaling) = (d/4, d/8),
+        (d/8, d/16), (5e, 5e/2); relativeTolerance 0.1."""
+        d = maximum_point_distance(ref_points)
+        e = minimum_point_distance(ref_points)
+        sig = [d / 4.0, d / 8.0, e * 5.0]
+        return Model.gaussianMixture(ctx, ref_points, triangles, sig, [v / 2.0 for v in sig], relativeTolerance, maxRank)
+
     def download(self):
         """(reference points [M, 3], meanVector [3M], basisMatrix [3M, r], variance [r]) as scalismo stores them."""
         ref = np.empty((self.M, 3))
@@ -234,6 +244,32 @@ def maximum_point_distance(points, brute_force_limit: int = 2048) -> float:
         except ImportError:
             pass
     return _max_pair_distance(p, p)
+
+
+def minimum_point_distance(points) -> float:
+    """PointSetHelper.minimumPointDistance (api/gpmm/GPMMHelper.scala:83-85, registration/utils/GPMMHelper.scala:35-37): the
+    smallest distance from a point to its nearest OTHER point (0 when the set holds duplicates).  Neighbour candidates come
+    from a KD-tree; the distances are re-formed as EuclideanVector3D.norm does, so the value is the brute-force one."""
+    p = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(-1, 3))
+    n = p.shape[0]
+    if n < 2:
+        raise ValueError("minimum point distance needs two points")
+    try:
+        from scipy.spatial import cKDTree
+        k = min(4, n)
+        _, nb = cKDTree(p).query(p, k=k)                         # self + the next k - 1 candidates
+        nb = nb[:, 1:] if k > 1 else nb
+        d = p[:, None, :] - p[nb]
+        cand = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2])
+        return float(cand.min())
+    except ImportError:
+        best = np.inf
+        for i0 in range(0, n, 1024):
+            d = p[i0:i0 + 1024, None, :] - p[None, :, :]
+            dist = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2])
+            dist[np.arange(dist.shape[0]), np.arange(i0, i0 + dist.shape[0])] = np.inf
+            best = min(best, float(dist.min()))
+        return best
 
 
 def cpd_estep(ctx: Context, target: Target, fit, sigma2: float, w: float):

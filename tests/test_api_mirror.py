@@ -326,3 +326,26 @@ def test_model_constructor_rejects_inconsistent_arrays_before_touching_the_libra
         api.Model(None, ref, np.zeros(9), np.zeros((12, 2)), np.ones(2))           # mean length != 3M
     with pytest.raises(ValueError):
         api.Model.gaussianMixture(None, ref, None, [1.0, 2.0], [1.0])
+
+
+def test_minimum_point_distance_and_the_automatic_template_model(monkeypatch):
+    """minimumPointDistance is the brute-force value; automaticGPMMfromTemplate (registration/utils/GPMMHelper.scala:38-68)
+    passes the reference's three (sigma, scaling) pairs and relativeTolerance 0.1 to the device builder."""
+    from gingr_b200 import api
+    rng = np.random.default_rng(6)
+    for pts in (rng.normal(size=(700, 3)) * 20.0, np.c_[rng.normal(size=(500, 2)), np.zeros(500)], rng.uniform(size=(5, 3))):
+        d = np.sqrt(((pts[:, None] - pts[None]) ** 2).sum(-1))
+        np.fill_diagonal(d, np.inf)
+        got = api.minimum_point_distance(pts)
+        assert abs(got - d.min()) <= 1e-15 * d.min()
+    dup = np.r_[pts, pts[:1]]
+    assert api.minimum_point_distance(dup) == 0.0
+    with pytest.raises(ValueError):
+        api.minimum_point_distance(pts[:1])
+    seen = {}
+    monkeypatch.setattr(api.Model, "gaussianMixture", staticmethod(lambda ctx, ref, tri, sig, sc, tol, cap=0: seen.update(sig=sig, sc=sc, tol=tol)))
+    ref = rng.normal(size=(300, 3)) * 10.0
+    api.Model.automaticGPMMfromTemplate(None, ref, None)
+    dmax, dmin = api.maximum_point_distance(ref), api.minimum_point_distance(ref)
+    assert seen["sig"] == [dmax / 4.0, dmax / 8.0, dmin * 5.0] and seen["sc"] == [dmax / 8.0, dmax / 16.0, dmin * 2.5]
+    assert seen["tol"] == 0.1
