@@ -83,3 +83,42 @@ def test_struct_layouts_match_the_ctypes_mirrors():
 def test_integration_notes_name_every_entry_point():
     doc = pathlib.Path(os.path.join(ROOT, "INTEGRATION.md")).read_text()
     assert [n for n in _header_prototypes() if n not in doc] == []
+
+
+def _call_sites(src):
+    """(handle name, number of arguments) of every `<handle>.invoke(...)` in a Scala source."""
+    out = []
+    for m in re.finditer(r"\b(\w+)\.invoke\(", src):
+        i, depth, args, cur = m.end(), 1, 0, ""
+        while depth:
+            ch = src[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+                if depth == 0:
+                    break
+            elif ch == "," and depth == 1:
+                args += 1
+                cur = ""
+                i += 1
+                continue
+            cur += ch
+            i += 1
+        out.append((m.group(1), args + (1 if cur.strip() else 0)))
+    return out
+
+
+def test_scala_call_sites_pass_the_declared_number_of_arguments():
+    """CpdRegistrationCuda.scala calls the handles of GingrCudaNative.scala: every call site must pass as many arguments as
+    the handle's FunctionDescriptor (and hence the C prototype) has parameters."""
+    shim_src, handles = _shim_handles()
+    by_val = {}
+    for m in re.finditer(r'val\s+(\w+)\s*=\s*fn\(\s*"(gingr_\w+)"', shim_src):
+        by_val[m.group(1)] = m.group(2)
+    user = pathlib.Path(os.path.join(os.path.dirname(SHIM), "CpdRegistrationCuda.scala")).read_text()
+    sites = _call_sites(user) + [s for s in _call_sites(shim_src) if s[0] in by_val]
+    assert len(sites) >= 15
+    for name, nargs in sites:
+        assert name in by_val, f"{name}.invoke: no such handle"
+        assert nargs == len(handles[by_val[name]][1]), (name, nargs, handles[by_val[name]][1])
