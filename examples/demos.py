@@ -6,6 +6,7 @@ results printed instead of shown.  Needs a B200 and the built library (python -m
     python examples/demos.py icp      --data ...  [--log chain.json]
     python examples/demos.py multires --data ...                                   # bunny: CPD 100 -> CPD 500 -> ICP 1000
     python examples/demos.py landmarks --data ...                                  # femur with / without landmarks
+    python examples/demos.py posterior --data ... --log chain.json                 # DemoPosteriorVisualizationFemur: variance maps
     python examples/demos.py cpd                                                   # no --data: a synthetic sphere pair
 
 Substitutions: meshes are decimated by gingr_b200.decimate instead of scalismo's quadric decimation; the
@@ -141,9 +142,40 @@ def demo_landmarks(args):
     print_status("with landmarks", res, t0, ctx, model, ds)
 
 
+def demo_posterior(args):
+    """DemoICP's probabilistic run with its JSON log, then examples/DemoPosteriorVisualizationFemur.scala:10-28: thin the
+    chain after a burn-in, turn the samples into shapes and reduce them to per-vertex variance maps (no UI: the maps are
+    written as .npy next to the log)."""
+    from gingr_b200 import api, helper, io
+    ctx = api.Context(0)
+    ds = load_dataset("femur" if args.data else "synthetic", args.data)
+    model, target = build(ctx, ds, args.cache)
+    log_path = args.log or "targetFittingICP.json"
+    gi = api.GingrInterface(ctx, model, target, evaluatorUncertainty=5.0, logFileFittingParameters=log_path)
+    cfg = api.IcpConfiguration(maxIterations=args.samples, initialSigma=1.0, endSigma=1.0)
+    t0 = time.time()
+    best = gi.ICP(cfg).runDecimated(100, 100, globalTransformation=api.NO_TRANSFORMS, probabilistic=True, seed=args.seed)
+    print_status("probabilistic (best sample)", best, t0, ctx, model, ds)
+    full_log = io.JSONStateLogger.load(log_path)
+    burn_in = min(100, len(full_log) // 4)
+    samples = helper.samples_from_log(full_log, takeEveryN=max(1, len(full_log) // 40), total=10000, burnIn=burn_in)
+    print(f"Number of samples from log: {len(samples)}/{len(full_log) - burn_in}")
+    shapes = helper.log_samples_to_shapes(model, [r for r, _ in samples])
+    best_pars = helper.record_to_parameters(helper.best_record([r for r in full_log if r.status]))
+    best_shape = model.instance(best_pars)
+    total = helper.distance_map_total(shapes)
+    normal = helper.distance_map_normal(shapes, model.triangles) if model.triangles is not None else total
+    base = os.path.splitext(log_path)[0]
+    np.save(base + "_variance_total.npy", total)
+    np.save(base + "_variance_normal.npy", normal)
+    np.save(base + "_best_shape.npy", best_shape)
+    print(f"posterior variance per vertex: total mean {total.mean():.4g} max {total.max():.4g}; along normals mean "
+          f"{normal.mean():.4g} max {normal.max():.4g}; written to {base}_variance_*.npy")
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    ap.add_argument("demo", choices=["cpd", "icp", "multires", "landmarks"])
+    ap.add_argument("demo", choices=["cpd", "icp", "multires", "landmarks", "posterior"])
     ap.add_argument("--data", default=None, help="the reference's examples/data directory (default: synthetic spheres)")
     ap.add_argument("--cache", default=None, help="directory for the cached model files (DemoDatasetLoader.model)")
     ap.add_argument("--log", default=None, help="JSON state log of the probabilistic run (logFileFittingParameters)")
@@ -154,6 +186,8 @@ def main(argv=None):
         demo_cpd_or_icp(args, args.demo)
     elif args.demo == "multires":
         demo_multires(args)
+    elif args.demo == "posterior":
+        demo_posterior(args)
     else:
         demo_landmarks(args)
 
