@@ -9,4 +9,5 @@
   synthetic, rotation   seeded synthetic workloads, Euler-angle conventions
 
 Nothing here computes on the CPU what the library computes: without the built library and a B200 every device call raises.
-The CPU oracle lives outside the package (oracle/) and is imported by tests, smoke() and bench.py's CPU baseline only."""
+The CPU restatement used as test oracle lives outside the package and is imported by tests, smoke() and bench.py's CPU
+baseline only."""
