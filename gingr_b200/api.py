@@ -407,6 +407,18 @@ class GeneralRegistrationState:
     iteration: int = 0
     status: int = STATUS_NONE
 
+    def statusText(self) -> str:
+        """The sentence printStatus() prints (GeneralRegistrationState.scala:104-114)."""
+        n = self.iteration + 1
+        return {STATUS_NONE: "Initial state - no iterations performed!",
+                STATUS_CONVERGED: f"Fitting converged after {n} accepted iterations!",
+                STATUS_MAX_ITERATION: f"Fitting finished the MaxIterations with ({n}) accepted iterations!",
+                STATUS_MODEL_FLEXIBILITY_ERROR: f"Model not flexible enough to compute posterior model - finished after {n} accepted iterations!",
+                }[self.status]
+
+    def printStatus(self) -> None:
+        print(self.statusText())
+
     def to_pod(self) -> Tuple[GingrState, np.ndarray]:
         p = self.modelParameters
         st = GingrState()

@@ -349,3 +349,19 @@ def test_minimum_point_distance_and_the_automatic_template_model(monkeypatch):
     dmax, dmin = api.maximum_point_distance(ref), api.minimum_point_distance(ref)
     assert seen["sig"] == [dmax / 4.0, dmax / 8.0, dmin * 5.0] and seen["sc"] == [dmax / 8.0, dmax / 16.0, dmin * 2.5]
     assert seen["tol"] == 0.1
+
+
+def test_print_status_sentences(capsys):
+    from gingr_b200 import api
+    p = api.ModelFittingParameters(1.0, np.zeros(3), (0.0, 0.0, 0.0), np.zeros(1))
+    s = api.GeneralRegistrationState(p, np.zeros((1, 3)), iteration=4)
+    assert s.statusText() == "Initial state - no iterations performed!"
+    assert dataclasses.replace(s, status=api.STATUS_CONVERGED).statusText() == "Fitting converged after 5 accepted iterations!"
+    assert dataclasses.replace(s, status=api.STATUS_MAX_ITERATION).statusText() == "Fitting finished the MaxIterations with (5) accepted iterations!"
+    dataclasses.replace(s, status=api.STATUS_MODEL_FLEXIBILITY_ERROR).printStatus()
+    assert capsys.readouterr().out == "Model not flexible enough to compute posterior model - finished after 5 accepted iterations!\n"
+    if os.path.isdir(REF):
+        src = pathlib.Path(os.path.join(REF, "api/GeneralRegistrationState.scala")).read_text()
+        for frag in ("Initial state - no iterations performed!", "Fitting converged after ", "Fitting finished the MaxIterations with (",
+                     "Model not flexible enough to compute posterior model - finished after "):
+            assert frag in src
