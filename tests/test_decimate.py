@@ -110,3 +110,24 @@ def test_torus_keeps_its_genus():
         assert len(dv) - len(cnt) + len(dt) == 0                       # Euler characteristic of a torus
         v1 = volume(dv, dt)
         assert np.sign(v1) == np.sign(v0) and 0.8 * abs(v0) < abs(v1) <= abs(v0) * 1.001
+
+
+def test_arbitrary_triangle_soups_never_break_the_decimator():
+    """Non-manifold edges, duplicated vertices, degenerate and repeated triangles, isolated vertices: the output is always a
+    valid (possibly undecimated) mesh over a subset of the input vertices."""
+    from gingr_b200 import decimate
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        n, T = int(rng.integers(4, 40)), int(rng.integers(1, 80))
+        v = rng.normal(size=(n, 3))
+        if trial % 3 == 0:
+            v = np.round(v, 0)
+        t = rng.integers(0, n, size=(T, 3)).astype(np.int32)
+        if trial % 4:
+            t = t[(t[:, 0] != t[:, 1]) & (t[:, 1] != t[:, 2]) & (t[:, 0] != t[:, 2])]
+        if len(t) == 0:
+            continue
+        dv, dt = decimate.decimate(v, t, int(rng.integers(1, n + 2)))
+        assert len(dv) <= n and np.all(np.isfinite(dv))
+        assert dt.size == 0 or (dt.min() >= 0 and dt.max() < len(dv))
+        assert all(any((v == q).all(1)) for q in dv)
