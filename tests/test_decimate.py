@@ -131,3 +131,31 @@ def test_arbitrary_triangle_soups_never_break_the_decimator():
         assert len(dv) <= n and np.all(np.isfinite(dv))
         assert dt.size == 0 or (dt.min() >= 0 and dt.max() < len(dv))
         assert all(any((v == q).all(1)) for q in dv)
+
+
+def test_native_twin_equals_the_python_specification():
+    """csrc_host/decimate.cpp against decimate._collapse: same kept vertices and the same triangles, bit for bit, on closed,
+    open, genus-1 and arbitrary inputs."""
+    from gingr_b200 import decimate, synthetic
+    lib = decimate._native_lib()
+    if lib is None:
+        pytest.skip("no host C++ compiler")
+    cases = []
+    v, t = synthetic.sphere_mesh(1500)
+    cases += [(v * np.array([1.0, 0.7, 1.6]), t, 200), (v, t, 37)]
+    sv, st = _sheet(25)
+    cases += [(sv, st, 120)]
+    rng = np.random.default_rng(4)
+    for _ in range(60):
+        n = int(rng.integers(5, 40))
+        tv = np.round(rng.normal(size=(n, 3)), int(rng.integers(0, 3)))
+        tt = rng.integers(0, n, size=(int(rng.integers(2, 90)), 3)).astype(np.int32)
+        tt = tt[(tt[:, 0] != tt[:, 1]) & (tt[:, 1] != tt[:, 2]) & (tt[:, 0] != tt[:, 2])]
+        if len(tt):
+            cases.append((tv, tt, int(rng.integers(1, n))))
+    for pts, tri, n in cases:
+        p = np.ascontiguousarray(pts, dtype=np.float64)
+        tr = np.ascontiguousarray(tri, dtype=np.int32)
+        a = decimate._collapse_native(lib, p, tr, n)
+        b = decimate._collapse(p, tr, n)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (len(p), len(tr), n)
