@@ -833,14 +833,15 @@ class SimpleRegistrator:
     def _evaluated_point_ids(self, model: Model, target: Target):
         """The evaluator's point subsets for evaluatedPoints = n.  Kept from the reference: the MODEL ids are those of the
         decimated instance used as ids of the full mesh, i.e. simply the first n ids (IndependentPointDistanceEvaluator
-        .scala:46-47, :50).  Substituted: the target points are every (N / n)-th target vertex instead of the vertices
-        of scalismo's quadric decimation."""
+        .scala:46-47, :50).  Substituted: the target points are about n target vertices spread evenly over the target
+        (one per occupied cell of a uniform grid, decimate.decimate_points) instead of the vertices of scalismo's quadric
+        decimation."""
         if self.evaluatedPoints is None:
             return None, None
+        from .decimate import decimate_points
         n = int(self.evaluatedPoints)
         mids = np.arange(min(n, model.M), dtype=np.int32)
-        N = target.N
-        tids = np.unique(np.floor(np.arange(min(n, N)) * (N / min(n, N))).astype(np.int32))
+        tids = decimate_points(target.points, n).astype(np.int32)
         return mids, tids
 
     def _run(self, model: Model, target: Target, generalState, globalTransformation, probabilistic, randomMixture, callback,

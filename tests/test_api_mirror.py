@@ -234,6 +234,7 @@ def test_gingr_interface_options_reach_the_registration(monkeypatch):
 
     class FakeTarget:
         N = 1000
+        points = np.random.default_rng(0).uniform(size=(1000, 3)) * 50.0
 
     monkeypatch.setattr(api, "CpdRegistration", FakeReg)
     monkeypatch.setattr(api, "IcpRegistration", FakeReg)
@@ -255,7 +256,9 @@ def test_gingr_interface_options_reach_the_registration(monkeypatch):
     assert calls["init"][0] is None and calls["init"][2] is R and list(calls["init"][3]) == [1.0, 2.0, 3.0]
     s = calls["settings"]
     assert (s.uncertainty, s.mode, s.randomMixture) == (3.0, api.EVAL_TARGET_TO_MODEL, 0.1)
-    assert list(s.modelPointIds) == [0, 1, 2, 3] and list(s.targetPointIds) == [0, 250, 500, 750]
+    assert list(s.modelPointIds) == [0, 1, 2, 3]
+    tids = np.asarray(s.targetPointIds)
+    assert tids.dtype == np.int32 and 2 <= len(tids) <= 8 and np.all(np.diff(tids) > 0) and tids.max() < 1000
     # a handed-over state wins over the initial transform (combineStates, SimpleRegistrator.scala:76-82)
     gi.ICP().run(generalState=st)
     assert calls["init"][0] is not None and calls["init"][2] is None
