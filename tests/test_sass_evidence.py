@@ -1,0 +1,75 @@
+"""What the compiled library contains, checked on the CPU from its SASS (cuobjdump): the design claims of DESIGN.md that can
+be read off the machine code -- the Gram kernel runs on the FP64 tensor pipe (DMMA.8x8x4) fed by the TMA engine (UBLKCP)
+through mbarriers (SYNCS), the trailing Cholesky update is DMMA too, the E-step sweeps are pure DFMA with the table look-up
+in shared memory and no local-memory spill, and every kernel is built for sm_100a.  No GPU."""
+import collections
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "gingr_b200", "lib", "libgingr_cuda.so")
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="no cuobjdump")
+
+
+@pytest.fixture(scope="module")
+def kernels():
+    if not os.path.exists(LIB):
+        from gingr_b200 import build
+        build.build()
+    out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"arch = (sm_\w+)", out))
+    table = {}
+    for block in re.split(r"\n\s*Function : ", out)[1:]:
+        name = block.split("\n", 1)[0].strip()
+        c = collections.Counter(re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*(?:\.[A-Z0-9_x]+)*)", block, flags=re.M))
+        table[name] = c
+    return archs, table
+
+
+def _find(table, fragment):
+    hits = [k for k in table if fragment in k]
+    assert hits, fragment
+    return hits
+
+
+def _count(counter, prefix):
+    return sum(v for k, v in counter.items() if k == prefix or k.startswith(prefix + "."))
+
+
+def test_everything_is_built_for_sm_100a(kernels):
+    archs, table = kernels
+    assert archs == {"sm_100a"}, archs
+    assert len(table) >= 80
+
+
+def test_gram_kernel_is_dmma_fed_by_tma_through_mbarriers(kernels):
+    _, table = kernels
+    for name in _find(table, "gram_ws_kernel"):
+        c = table[name]
+        assert _count(c, "DMMA") >= 256 and any(k.startswith("DMMA.8x8x4") for k in c)
+        assert _count(c, "UBLKCP") >= 1                      # cp.async.bulk: the TMA engine moves the operand rows
+        assert _count(c, "SYNCS") >= 4                       # mbarrier arrive / try_wait on the full and empty rings
+        assert _count(c, "DFMA") == 0 and _count(c, "LDL") == 0 and _count(c, "STL") == 0
+    for name in _find(table, "chol_syrk_kernel"):
+        assert _count(table[name], "DMMA") >= 32 and _count(table[name], "LDL") == 0
+
+
+def test_estep_sweeps_are_spill_free_dfma_with_the_table_in_shared_memory(kernels):
+    _, table = kernels
+    for frag in ("estep_colsum_kernel", "estep_rowsum_kernel"):
+        for name in _find(table, frag):
+            c = table[name]
+            assert _count(c, "DFMA") >= 300 and _count(c, "LDS") >= 30
+            assert _count(c, "LDL") == 0 and _count(c, "STL") == 0          # no local-memory traffic in the hot loops
+            assert _count(c, "DMMA") == 0
+
+
+def test_cholesky_panel_factorises_in_registers_with_shuffles(kernels):
+    _, table = kernels
+    for name in _find(table, "chol_panel_kernel"):
+        c = table[name]
+        assert _count(c, "SHFL") >= 500 and _count(c, "DFMA") >= 1000 and _count(c, "LDL") == 0 and _count(c, "STL") == 0
