@@ -7,6 +7,7 @@ results printed instead of shown.  Needs a B200 and the built library (python -m
     python examples/demos.py multires --data ...                                   # bunny: CPD 100 -> CPD 500 -> ICP 1000
     python examples/demos.py landmarks --data ...                                  # femur with / without landmarks
     python examples/demos.py posterior --data ... --log chain.json                 # DemoPosteriorVisualizationFemur: variance maps
+    python examples/demos.py gpmm --data ... --cache models/                       # Create{Femur, Bunny}GPMM: build + cache the models
     python examples/demos.py cpd                                                   # no --data: a synthetic sphere pair
 
 Substitutions: meshes are decimated by gingr_b200.decimate instead of scalismo's quadric decimation; the
@@ -142,6 +143,20 @@ def demo_landmarks(args):
     print_status("with landmarks", res, t0, ctx, model, ds)
 
 
+def demo_gpmm(args):
+    """examples/Create{Femur, Bunny}GPMM.scala: build the data set's Gaussian-kernel model on the device and leave it in the
+    cache directory (the file DataSetLoader.model looks for), then report its leading variances."""
+    from gingr_b200 import api
+    ctx = api.Context(0)
+    for name in (("femur", "bunny") if args.data else ("synthetic",)):
+        ds = load_dataset(name, args.data)
+        model, target = build(ctx, ds, args.cache or ".")
+        _, _, _, var = model.download()
+        print(f"{ds['name']}: leading standard deviations {np.sqrt(var[:5]).round(3).tolist()}, last {float(np.sqrt(var[-1])):.4g}")
+        target.close()
+        model.close()
+
+
 def demo_posterior(args):
     """DemoICP's probabilistic run with its JSON log, then examples/DemoPosteriorVisualizationFemur.scala:10-28: thin the
     chain after a burn-in, turn the samples into shapes and reduce them to per-vertex variance maps (no UI: the maps are
@@ -175,7 +190,7 @@ def demo_posterior(args):
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    ap.add_argument("demo", choices=["cpd", "icp", "multires", "landmarks", "posterior"])
+    ap.add_argument("demo", choices=["cpd", "icp", "multires", "landmarks", "posterior", "gpmm"])
     ap.add_argument("--data", default=None, help="the reference's examples/data directory (default: synthetic spheres)")
     ap.add_argument("--cache", default=None, help="directory for the cached model files (DemoDatasetLoader.model)")
     ap.add_argument("--log", default=None, help="JSON state log of the probabilistic run (logFileFittingParameters)")
@@ -188,6 +203,8 @@ def main(argv=None):
         demo_multires(args)
     elif args.demo == "posterior":
         demo_posterior(args)
+    elif args.demo == "gpmm":
+        demo_gpmm(args)
     else:
         demo_landmarks(args)
 
