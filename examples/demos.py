@@ -121,7 +121,8 @@ def demo_multires(args):
     print_status("medium (CPD 500)", medium, t0, ctx, model, ds)
     t0 = time.time()
     fine = gi.ICP(api.IcpConfiguration(maxIterations=100, initialSigma=2.0, endSigma=0.01)).runDecimated(
-        1000, 1000, generalState=medium, globalTransformation=api.NO_TRANSFORMS)
+        1000, 1000, generalState=medium, globalTransformation=api.NO_TRANSFORMS)   # argument ignored as in the reference: the
+    # handed-over state keeps its RigidTransforms (SimpleRegistrator.scala:93-95)
     print_status("fine (ICP 1000)", fine, t0, ctx, model, ds)
 
 

@@ -72,7 +72,7 @@ def _literal(oracle, Ypts, Xpts, w, lam, gamma, k, G, max_iteration, tolerance=1
 
 @pytest.mark.parametrize("w", [0.0, 0.2])
 def test_bcpd_equals_the_literal_statements(oracle, monkeypatch, w):
-    from gingr_b200 import textbook_bcpd
+    import textbook_bcpd
     _install(monkeypatch, oracle)
     rng = np.random.default_rng(9)
     Y = rng.normal(size=(24, 3)) * 2.0
@@ -97,7 +97,7 @@ def test_bcpd_equals_the_literal_statements(oracle, monkeypatch, w):
 
 
 def test_bcpd_requirements(oracle, monkeypatch):
-    from gingr_b200 import textbook_bcpd
+    import textbook_bcpd
     _install(monkeypatch, oracle)
     Y = np.random.default_rng(0).normal(size=(6, 3))
     G = np.eye(6)

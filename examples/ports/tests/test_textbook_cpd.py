@@ -68,7 +68,7 @@ def _literal(kind, X, Y0, G, lam, w, max_iteration, tolerance=0.001):
 @pytest.mark.parametrize("kind,w,iters", [("rigid", 0.0, 25), ("rigid", 0.2, 25), ("affine", 0.1, 25), ("nonrigid", 0.0, 8),
                                           ("nonrigid", 0.3, 8)])
 def test_variants_equal_the_literal_statements(oracle, monkeypatch, kind, w, iters):
-    from gingr_b200 import textbook_cpd
+    import textbook_cpd
     _install(monkeypatch, oracle)
     rng = np.random.default_rng(5)
     Y0 = rng.normal(size=(40, 3)) * 2.0
@@ -89,7 +89,7 @@ def test_variants_equal_the_literal_statements(oracle, monkeypatch, kind, w, ite
 
 
 def test_factory_requirements_and_kernel_matrix(oracle, monkeypatch):
-    from gingr_b200 import textbook_cpd
+    import textbook_cpd
     _install(monkeypatch, oracle)
     Y = np.random.default_rng(0).normal(size=(12, 3))
     for bad in (dict(w=1.5), dict(w=-0.1), dict(beta=0.0), dict(lambda_=0.0)):

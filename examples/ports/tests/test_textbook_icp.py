@@ -43,7 +43,7 @@ def _literal(oracle, template, target, similarity, max_iteration, tolerance=0.00
 
 @pytest.mark.parametrize("registrator", ["rigid", "similarity"])
 def test_rigid_icp_equals_the_literal_loop(oracle, monkeypatch, registrator):
-    from gingr_b200 import textbook_icp
+    import textbook_icp
     _install(monkeypatch, oracle)
     rng = np.random.default_rng(3)
     tpl = rng.normal(size=(120, 3)) * np.array([10.0, 6.0, 3.0])

@@ -74,7 +74,7 @@ def _literal_A(task, template, cp, w, alpha, beta, gamma):
 
 @pytest.mark.parametrize("variant", ["T", "A"])
 def test_nicp_iterations_equal_dense_least_squares(oracle, monkeypatch, variant):
-    from gingr_b200 import textbook_nicp
+    import textbook_nicp
     _install(monkeypatch, oracle)
     tpl, tgt, tl, sl = _meshes()
     cls = textbook_nicp.NonRigidOptimalStepICP_T if variant == "T" else textbook_nicp.NonRigidOptimalStepICP_A

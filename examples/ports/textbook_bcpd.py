@@ -14,7 +14,7 @@ from typing import Tuple
 
 import numpy as np
 
-from . import api
+from gingr_b200 import api
 
 DIM = 3
 

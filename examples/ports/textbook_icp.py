@@ -10,8 +10,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import api
-from .template import umeyama
+from gingr_b200 import api
+from gingr_b200.template import umeyama
 
 
 class RigidICP:

@@ -14,7 +14,7 @@ from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import api
+from gingr_b200 import api
 
 DIM = 3
 DEFAULT_ALPHA = [10.0] * 11          # NonRigidOptimalStepICP.scala:61-63

@@ -4,7 +4,6 @@
   _native, api     ctypes binding and the mirror of the reference's classes (configurations, state, CpdRegistration,
                    IcpRegistration, SimpleRegistrator, GingrInterface, ProbabilisticSettings, Model, Target)
   template         the reference's TemplateRegistration extension point (user closures, regression on the device)
-  textbook_*       the comparison algorithms of gingr/other (CPD variants, BCPD, rigid ICP, N-ICP) over the device kernels
   io, helper       wire / disk formats, state-log consumers;  comparison: mesh distances;  decimate: mesh decimation
   synthetic, rotation   seeded synthetic workloads, Euler-angle conventions
 

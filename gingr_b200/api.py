@@ -195,9 +195,11 @@ class Model:
         for d in range(3):
             st.translation[d] = float(parameters.translation[d])
             st.euler[d] = float(parameters.euler[d])
-            st.center[d] = 0.0
+            st.center[d] = float(parameters.center[d])
         st.rank = self.rank
         alpha = nat.f64(parameters.shape)
+        if alpha.shape != (self.rank,):
+            raise ValueError(f"shape coefficients have shape {alpha.shape}, the model has rank {self.rank}")
         fit = np.empty((self.M, 3))
         self.ctx.check(self.ctx._lib.gingr_model_instance(self.ctx.handle, self.handle, ctypes.byref(st), nat.as_dp(alpha),
                                                           nat.as_dp(fit)))
@@ -346,6 +348,11 @@ def posterior_mean(ctx: Context, model: Model, R, t, pids, points, noise):
     pts = nat.f64(points).reshape(-1, 3)
     noise = nat.f64(noise)
     kind = 0 if noise.ndim == 1 else 1
+    n = pids.shape[0]
+    if pids.ndim != 1 or pts.shape[0] != n:
+        raise ValueError(f"{n} point ids but {pts.shape[0]} points")
+    if noise.shape not in ((n,), (n, 3, 3)):
+        raise ValueError(f"noise must have shape ({n},) or ({n}, 3, 3), got {noise.shape}")
     c = np.empty(model.rank)
     mesh = np.empty((model.M, 3))
     code = ctx.check(ctx._lib.gingr_posterior_mean(ctx.handle, model.handle, nat.as_dp(R), nat.as_dp(t),
@@ -361,6 +368,8 @@ def coefficients(ctx: Context, model: Model, R, t, mesh_points):
     R = nat.f64(R).reshape(3, 3)
     t = nat.f64(t).reshape(3)
     mesh = nat.f64(mesh_points).reshape(-1, 3)
+    if mesh.shape[0] != model.M:
+        raise ValueError(f"mesh has {mesh.shape[0]} points, the model has {model.M}")
     c = np.empty(model.rank)
     code = ctx.check(ctx._lib.gingr_coefficients(ctx.handle, model.handle, nat.as_dp(R), nat.as_dp(t),
                                                  nat.as_dp(mesh), nat.as_dp(c)))
@@ -854,8 +863,10 @@ class SimpleRegistrator:
                 if len(pids):
                     reg.setLandmarks(pids, pts, covs)
             if generalState is not None:
-                # combineStates (:76-82): clearIteration, status None, then initializeState recomputes sigma2 from the config
-                g = dataclasses.replace(generalState, iteration=0, status=STATUS_NONE, globalTransformation=globalTransformation)
+                # combineStates (:76-82): clearIteration, status None, then initializeState recomputes sigma2 from the config.
+                # The state keeps ITS OWN globalTransformation: the reference ignores the call argument whenever a
+                # generalState is given (:93-95, :135-137)
+                g = dataclasses.replace(generalState, iteration=0, status=STATUS_NONE)
                 st = reg.initializeState(general=g)
             elif self.initialModelParameterTransform is not None:
                 rot, trans = self.initialModelParameterTransform

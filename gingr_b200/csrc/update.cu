@@ -1060,6 +1060,9 @@ int32_t gingr_model_instance(gingr_ctx* ctx, const gingr_model* model, const gin
                              double* fit) {
   if (!ctx || !model || !stt || !alpha || !fit) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_model_instance: bad argument");
   if (ctx->nranks != 1) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "gingr_model_instance: single-GPU entry point");
+  if (stt->rank != model->r) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_model_instance: state rank does not match the model rank");
+  if (stt->center[0] != 0.0 || stt->center[1] != 0.0 || stt->center[2] != 0.0)
+    return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "rotation centre must be the origin (GeneralRegistrationState.scala:147)");
   const gingr_model* m = model;
   const int M = m->M, r = m->r, rp = m->rp;
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));

@@ -107,12 +107,23 @@ def _native_lib():
                 if cxx is None:
                     raise OSError("no host C++ compiler")
                 os.makedirs(os.path.dirname(so), exist_ok=True)
-                subprocess.run([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", src, "-o", so], check=True,
-                               capture_output=True)
+                # several processes (ranks, pytest-xdist) may get here at once: build to a private name, rename atomically
+                tmp = f"{so}.{os.getpid()}.tmp"
+                try:
+                    subprocess.run([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", src, "-o", tmp],
+                                   check=True, capture_output=True)
+                    os.replace(tmp, so)
+                finally:
+                    if os.path.exists(tmp):
+                        os.remove(tmp)
             lib = ctypes.CDLL(so)
             lib.gingr_host_decimate.restype = ctypes.c_int32
             _NATIVE = lib
-        except (OSError, subprocess.CalledProcessError):
+        except (OSError, subprocess.CalledProcessError) as e:
+            if os.environ.get("GINGR_HOST_NATIVE", "1") != "0":
+                import warnings
+                warnings.warn(f"gingr_b200.decimate: native helper unavailable ({e}); using the Python specification "
+                              "(identical result, slower)")
             _NATIVE = False
     return _NATIVE or None
 

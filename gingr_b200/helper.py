@@ -17,8 +17,11 @@ def record_to_parameters(record: JsonLogRecord):
     from .api import ModelFittingParameters
     if len(record.rotation) != 3 or len(record.rotationCenter) != 3:
         raise ValueError("requirement failed: the log record has no pose (a rejected sample)")
+    # the centre travels with the parameters; the device refuses a non-zero one (GiNGR always rotates about the origin,
+    # GeneralRegistrationState.scala:147) instead of silently re-posing the shape
     return ModelFittingParameters(float(record.scaling), np.asarray(record.translation, dtype=np.float64),
-                                  tuple(float(v) for v in record.rotation), np.asarray(record.modelParameters, dtype=np.float64))
+                                  tuple(float(v) for v in record.rotation), np.asarray(record.modelParameters, dtype=np.float64),
+                                  np.asarray(record.rotationCenter, dtype=np.float64))
 
 
 def best_record(log: Sequence[JsonLogRecord]) -> JsonLogRecord:

@@ -113,7 +113,8 @@ class JSONStateLogger:
         self.generatedBy.add(state.generatedBy)
         self.log.append(JsonLogRecord(self.accepted + self.rejected, state.generatedBy, self._values(state, values), True,
                                       [float(v) for v in p.shape], [float(v) for v in p.translation],
-                                      [float(v) for v in p.euler], [0.0, 0.0, 0.0], float(p.scale), self._now()))
+                                      [float(v) for v in p.euler], [float(v) for v in getattr(p, "center", (0.0, 0.0, 0.0))],
+                                      float(p.scale), self._now()))
         self.accepted += 1
 
     def reject(self, state, values=None) -> None:

@@ -191,6 +191,11 @@ def test_simple_registrator_attaches_the_json_logger_when_asked(tmp_path):
     out = sr2.run(generalState=g, globalTransformation=api.SIMILARITY_TRANSFORMS, callback=seen.append)
     assert calls["det"] is not None and out.status == api.STATUS_CONVERGED
     assert calls["init"][0].iteration == 0 and calls["init"][0].status == api.STATUS_NONE
+    # the hand-over keeps the state's OWN transformation type; the call argument is ignored when a generalState is given
+    # (SimpleRegistrator.scala:76-82, :93-95, :135-137)
+    assert calls["init"][0].globalTransformation == st.globalTransformation != api.SIMILARITY_TRANSFORMS
+    gs = dataclasses.replace(st, globalTransformation=api.SIMILARITY_TRANSFORMS)
+    sr2.run(generalState=gs)                                   # default argument RIGID must not overwrite SIMILARITY
     assert calls["init"][0].globalTransformation == api.SIMILARITY_TRANSFORMS
 
 
