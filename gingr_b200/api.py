@@ -363,6 +363,30 @@ def posterior_mean(ctx: Context, model: Model, R, t, pids, points, noise):
     return c, mesh
 
 
+def spd_solve(ctx: Context, A, B=None, reps: int = 1):
+    """The on-device r x r Cholesky solve of the regression (scalismo: Minv = pinv(Mx); c = Minv * rhs).
+    A: [n, n] symmetric positive definite; B: [nrhs, n] right-hand sides as rows (or None).
+    -> dict(L=[n, n] lower factor, Y=[nrhs, n] rows L^-1 b_q, x=[n] A^-1 b_0 (None without B), ms=device time of one
+    factorisation + back substitution).  Raises FloatingPointError when A is not positive definite."""
+    A = nat.f64(A)
+    n = A.shape[0]
+    if A.shape != (n, n):
+        raise ValueError(f"A must be square, got {A.shape}")
+    nrhs = 0
+    if B is not None:
+        B = nat.f64(B).reshape(-1, n)
+        nrhs = B.shape[0]
+    L = np.empty((n, n))
+    Y = np.empty((nrhs, n))
+    x = np.empty(n) if nrhs else None
+    ms = ctypes.c_double()
+    code = ctx.check(ctx._lib.gingr_spd_solve(ctx.handle, n, nat.as_dp(A), nrhs, nat.as_dp(B), nat.as_dp(L), nat.as_dp(Y),
+                                              nat.as_dp(x), int(reps), ctypes.byref(ms)))
+    if code == nat.GINGR_MODEL_FLEXIBILITY:
+        raise FloatingPointError("matrix not positive definite (ModelFlexibilityError)")
+    return dict(L=L, Y=Y, x=x, ms=float(ms.value))
+
+
 def coefficients(ctx: Context, model: Model, R, t, mesh_points):
     """model.transform(R, t).coefficients(mesh) (GingrAlgorithm.scala:215, :236)."""
     R = nat.f64(R).reshape(3, 3)

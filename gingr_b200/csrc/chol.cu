@@ -398,7 +398,9 @@ __global__ void __launch_bounds__(32) chol_backsolve_small_kernel(int n, const d
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, int* d_info) {
+int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, int* d_info, CholWs* ws) {
+  static const int env_df = [] { const char* e = getenv("GINGR_CHOL_DF"); return e ? atoi(e) : 1; }();
+  if (ws != nullptr && env_df != 0) return cholesky_df_enqueue(ctx, n, nrows, d_A, ld, d_info, *ws);
   static thread_local int attr_device = -1;  // once per device (and host thread): not a stream operation
   if (attr_device != ctx->device) {
     GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(chol_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -480,7 +480,7 @@ static int32_t enqueue_log_transition(gingr_registration* g, const double* d_raw
   mcmc_build_system_kernel<<<ceil_div((r + 1) * rp, 256), 256, 0, st>>>(r, rp, m->S.p, d_raw, 1e-5, v, v + rp, mc->sys.p,
                                                                         mc->mi.p + MI_INFO2);
   GINGR_LAUNCHED(ctx);
-  GINGR_TRY(cholesky_enqueue(ctx, r, r + 1, mc->sys.p, rp, mc->mi.p + MI_INFO2));
+  GINGR_TRY(cholesky_enqueue(ctx, r, r + 1, mc->sys.p, rp, mc->mi.p + MI_INFO2, &g->cholws));
   GINGR_TRY(chol_backsolve_enqueue(ctx, r, mc->sys.p, rp, mc->sys.p + (size_t)r * rp, v + 2 * rp, g->flags.p));
   GINGR_TRY(dense_matvec_enqueue(ctx, r, d_raw, rp, v + 2 * rp, v + 3 * rp));
   mcmc_quadform_kernel<<<1, 256, 0, st>>>(r, v + 2 * rp, v + 3 * rp, d_from_is, mc->mi.p + MI_INFO2, d_out);

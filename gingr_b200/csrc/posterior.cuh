@@ -26,7 +26,18 @@ int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_part
 // matrix with nrows >= n rows.  The extra rows i >= n are carried through the panel solves, so on return
 // row n + q holds  L^-1 b_q  for the right-hand side b_q that was stored there (forward substitution for free).
 // d_info[0] is set to 1 if a non-positive / non-finite pivot appears (matrix not SPD).
-int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, int* d_info);
+// Workspace of the data-flow factorisation (chol_df.cu): tile tickets / flags and the inverses of the diagonal blocks.
+// One per concurrent factorisation (a registration owns one); alloc() outside stream capture.
+struct CholWs {
+  DevBuf<int> sync;
+  DevBuf<double> linv;
+  int cap_n = 0, cap_nrows = 0;
+  int32_t alloc(gingr_ctx* ctx, int n, int nrows);
+  void release();
+};
+// ws == nullptr (or GINGR_CHOL_DF=0): the kernel-per-step form of chol.cu; else one persistent data-flow kernel.
+int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, int* d_info, CholWs* ws = nullptr);
+int32_t cholesky_df_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, int* d_info, CholWs& ws);
 // c = L^-T z  (sync-free multi-CTA backward substitution).  d_flags: >= ceil(n/64) ints of scratch.
 int32_t chol_backsolve_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld, const double* d_z, double* d_c,
                                int* d_flags);

@@ -627,6 +627,7 @@ struct gingr_registration {
   DevBuf<double> gt_part, sums_part, pro_part, pro_sums;
   DevBuf<double> ds;
   DevBuf<int> is, flags;
+  CholWs cholws;               // tickets / flags / diagonal-block inverses of the data-flow Cholesky (chol_df.cu)
   DevBuf<double> alpha;
   int retry_counter = RETRY_COUNTER_INIT;  // mirror of the device counter, refreshed by download_state
   // One iteration captured as a CUDA graph: the ~100-launch sequence of a small registration (C1-C3 sizes) is
@@ -836,7 +837,9 @@ static int32_t model_build_constants(gingr_ctx* ctx, gingr_model* m) {
   GINGR_CUDA_TRY(ctx, info.alloc(4));
   GINGR_CUDA_TRY(ctx, cudaMemsetAsync(info.p, 0, sizeof(int) * 4, ctx->stream));
   GINGR_TRY(build_regression_system_enqueue(ctx, r, rp, m->S.p, 1e-5, B.p));
-  GINGR_TRY(cholesky_enqueue(ctx, r, 2 * r, B.p, rp, info.p));
+  CholWs cws;
+  GINGR_TRY(cws.alloc(ctx, r, 2 * r));
+  GINGR_TRY(cholesky_enqueue(ctx, r, 2 * r, B.p, rp, info.p, &cws));
   // W0 = Rm Rm^T = Gram of Rm^T
   GINGR_CUDA_TRY(ctx, cudaMemsetAsync(Rt.p, 0, sizeof(double) * r * rp, ctx->stream));
   GINGR_TRY(transpose_enqueue(ctx, r, B.p + (size_t)r * rp, rp, Rt.p, rp));
@@ -853,6 +856,7 @@ static int32_t model_build_constants(gingr_ctx* ctx, gingr_model* m) {
   B.release();
   Rt.release();
   info.release();
+  cws.release();
   if (h_info != 0) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_model_upload: basis/variance not finite (1e-5 I + S not SPD)");
   m->has_regression_constants = true;
   return GINGR_OK;
@@ -891,8 +895,9 @@ struct PosteriorScratch {
   GramPlan gram;
   DevBuf<double> Mx, wrow, u, vec, gt_part, inst, fit_local, gathered, fit, ds;
   DevBuf<int> is, flags;
+  gingr::CholWs cholws;
   void release() {
-    gram.release();
+    gram.release(); cholws.release();
     Mx.release(); wrow.release(); u.release(); vec.release(); gt_part.release(); inst.release();
     fit_local.release(); gathered.release(); fit.release(); ds.release(); is.release(); flags.release();
   }
@@ -970,6 +975,7 @@ int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model, const dou
   PM_TRY(s.ds.alloc(DS_COUNT));
   PM_TRY(s.is.alloc(IS_COUNT));
   PM_TRY(s.flags.alloc(256));
+  if ((rc = s.cholws.alloc(ctx, r, r + 1)) < 0) return fail(rc);
   PM_TRY(cudaMemsetAsync(s.Mx.p, 0, sizeof(double) * (size_t)(r + 8) * rp, st));
   PM_TRY(cudaMemsetAsync(s.is.p, 0, sizeof(int) * IS_COUNT, st));
   PM_TRY(cudaMemcpyAsync(s.wrow.p, wrow.data(), sizeof(double) * 3 * M, cudaMemcpyHostToDevice, st));
@@ -996,7 +1002,7 @@ int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model, const dou
   }
   if ((rc = gram_partials_enqueue(ctx, s.gram, m->phi.p, s.wrow.p)) < 0) return fail(rc);
   if ((rc = gram_finish_enqueue(ctx, s.gram, s.gram.d_partial.p, m->sqrt_lambda.p, 1.0, L, d_lrows.p, d_lA.p, rp, s.Mx.p)) < 0) return fail(rc);
-  if ((rc = cholesky_enqueue(ctx, r, r + 1, s.Mx.p, rp, s.is.p + IS_INFO)) < 0) return fail(rc);
+  if ((rc = cholesky_enqueue(ctx, r, r + 1, s.Mx.p, rp, s.is.p + IS_INFO, &s.cholws)) < 0) return fail(rc);
   double* c = s.vec.p;
   if ((rc = chol_backsolve_enqueue(ctx, r, s.Mx.p, rp, rhs, c, s.flags.p)) < 0) return fail(rc);
   check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, c, s.is.p + IS_FAIL_POST);
@@ -1054,6 +1060,63 @@ int32_t gingr_coefficients(gingr_ctx* ctx, const gingr_model* model, const doubl
 #undef CO_TRY
   rel();
   return hflag ? GINGR_MODEL_FLEXIBILITY : GINGR_OK;
+}
+
+int32_t gingr_spd_solve(gingr_ctx* ctx, int32_t n, const double* A, int32_t nrhs, const double* B, double* L_out,
+                        double* Y_out, double* x_out, int32_t reps, double* ms_out) {
+  if (!ctx || !A || n < 1 || nrhs < 0 || (nrhs > 0 && !B) || (x_out && nrhs < 1) || reps < 1)
+    return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_spd_solve: bad argument");
+  GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int np = (n + 7) / 8 * 8, nrows = n + nrhs;
+  DevBuf<double> in, work, x;
+  DevBuf<int> info, flags;
+  CholWs ws;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t st = ctx->stream;
+  auto rel = [&]() { in.release(); work.release(); x.release(); info.release(); flags.release(); ws.release();
+                     if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); };
+#define SS_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { gingr_set_error(ctx, cudaGetErrorString(_e)); cudaStreamSynchronize(st); rel(); return GINGR_ERR_CUDA; } } while (0)
+  SS_TRY(in.alloc((size_t)nrows * np)); SS_TRY(work.alloc((size_t)(nrows + 8) * np)); SS_TRY(x.alloc(np));
+  SS_TRY(info.alloc(4)); SS_TRY(flags.alloc((size_t)ceil_div(n, 64) + 8));
+  int32_t rc = ws.alloc(ctx, n, nrows);
+  if (rc < 0) { rel(); return rc; }
+  SS_TRY(cudaEventCreate(&e0)); SS_TRY(cudaEventCreate(&e1));
+  SS_TRY(cudaMemsetAsync(in.p, 0, sizeof(double) * (size_t)nrows * np, st));
+  SS_TRY(cudaMemcpy2DAsync(in.p, sizeof(double) * np, A, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice, st));
+  if (nrhs > 0)
+    SS_TRY(cudaMemcpy2DAsync(in.p + (size_t)n * np, sizeof(double) * np, B, sizeof(double) * n, sizeof(double) * n, nrhs,
+                             cudaMemcpyHostToDevice, st));
+  SS_TRY(cudaMemsetAsync(info.p, 0, sizeof(int) * 4, st));
+  float ms_total = 0.f;
+  for (int it = 0; it < reps; ++it) {
+    SS_TRY(cudaMemcpyAsync(work.p, in.p, sizeof(double) * (size_t)nrows * np, cudaMemcpyDeviceToDevice, st));
+    SS_TRY(cudaEventRecord(e0, st));
+    rc = cholesky_enqueue(ctx, n, nrows, work.p, np, info.p, &ws);
+    if (rc >= 0 && nrhs > 0) rc = chol_backsolve_enqueue(ctx, n, work.p, np, work.p + (size_t)n * np, x.p, flags.p);
+    if (rc < 0) { cudaStreamSynchronize(st); rel(); return rc; }
+    SS_TRY(cudaEventRecord(e1, st));
+    SS_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    SS_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    ms_total += ms;
+  }
+  if (ms_out) *ms_out = (double)ms_total / reps;
+  int h_info = 0;
+  SS_TRY(cudaMemcpyAsync(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (L_out) {
+    SS_TRY(cudaMemcpy2DAsync(L_out, sizeof(double) * n, work.p, sizeof(double) * np, sizeof(double) * n, n, cudaMemcpyDeviceToHost, st));
+  }
+  if (Y_out && nrhs > 0)
+    SS_TRY(cudaMemcpy2DAsync(Y_out, sizeof(double) * n, work.p + (size_t)n * np, sizeof(double) * np, sizeof(double) * n, nrhs,
+                             cudaMemcpyDeviceToHost, st));
+  if (x_out) SS_TRY(cudaMemcpyAsync(x_out, x.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  SS_TRY(cudaStreamSynchronize(st));
+#undef SS_TRY
+  rel();
+  if (L_out)
+    for (int i = 0; i < n; ++i)
+      for (int k = i + 1; k < n; ++k) L_out[(size_t)i * n + k] = 0.0;
+  return h_info ? GINGR_MODEL_FLEXIBILITY : GINGR_OK;
 }
 
 int32_t gingr_model_instance(gingr_ctx* ctx, const gingr_model* model, const gingr_state* stt, const double* alpha,
@@ -1160,6 +1223,7 @@ int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, cons
   A(g->pro_part.alloc((size_t)16 * ceil_div(std::max(Ml, 1), 256)));
   A(g->pro_sums.alloc(32));
   A(g->ds.alloc(DS_COUNT)); A(g->is.alloc(IS_COUNT)); A(g->flags.alloc(256));
+  if (rc == GINGR_OK) { int32_t q = g->cholws.alloc(ctx, r, r + 1); if (q < 0) rc = q; }
   A(g->alpha.alloc((size_t)rp));
   if (rc == GINGR_OK) {
     A(cudaMemsetAsync(g->Mx.p, 0, sizeof(double) * (size_t)(r + 8) * rp, ctx->stream));
@@ -1194,7 +1258,7 @@ int32_t gingr_registration_destroy(gingr_registration* g) {
   g->rows_ext.release(); g->Mx.release(); g->wrow.release(); g->u.release(); g->inst_a.release(); g->inst_b.release();
   g->newshape.release(); g->fit_local.release(); g->gathered.release(); g->fit.release(); g->vec.release();
   g->gt_part.release(); g->sums_part.release(); g->pro_part.release(); g->pro_sums.release();
-  g->ds.release(); g->is.release(); g->flags.release(); g->alpha.release();
+  g->ds.release(); g->is.release(); g->flags.release(); g->alpha.release(); g->cholws.release();
   for (auto& e : g->events) cudaEventDestroy(e);
   delete g;
   return GINGR_OK;
@@ -1411,7 +1475,7 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
   if (g->keep_raw)
     GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->Mx_raw.p, g->Mx.p, sizeof(double) * (size_t)(r + 1) * rp, cudaMemcpyDeviceToDevice, st));
   g->rec(8);
-  GINGR_TRY(cholesky_enqueue(ctx, r, r + 1, g->Mx.p, rp, g->is.p + IS_INFO));
+  GINGR_TRY(cholesky_enqueue(ctx, r, r + 1, g->Mx.p, rp, g->is.p + IS_INFO, &g->cholws));
   return GINGR_OK;
 }
 

@@ -211,6 +211,16 @@ GINGR_API int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model,
  * all M points with noise 1e-5 * I3. */
 GINGR_API int32_t gingr_coefficients(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t,
                                      const double* mesh_pts /*[3M]*/, double* coeffs /*[r]*/);
+/* Kernel-level entry of the r x r solve inside the regression -- scalismo's `Minv = pinv(Mx); c = Minv * rhs`
+ * (call sites GingrAlgorithm.scala:300, :215, :236) -- as the on-device Cholesky the iteration uses.
+ * A[n*n] row-major symmetric positive definite (only the lower triangle is read); B[nrhs*n]: right-hand sides as rows.
+ * Outputs (each may be NULL): L_out[n*n] the factor (lower, row-major, strict upper part zero); Y_out[nrhs*n] the rows
+ * L^-1 b_q (forward substitution, carried through the factorisation); x_out[n] = A^-1 b_0 (needs nrhs >= 1).
+ * reps >= 1 factorisations are run back to back on the same input; ms_out (may be NULL) receives the device time of
+ * ONE factorisation + back substitution (CUDA events on the library's stream).
+ * Returns GINGR_MODEL_FLEXIBILITY when A is not positive definite / not finite. */
+GINGR_API int32_t gingr_spd_solve(gingr_ctx* ctx, int32_t n, const double* A, int32_t nrhs, const double* B,
+                                  double* L_out, double* Y_out, double* x_out, int32_t reps, double* ms_out);
 /* Replaces ModelFittingParameters.modelInstanceShapePoseScale (ModelFittingParameters.scala:130-143):
  * fit = s * (R * instance(alpha) + t). */
 GINGR_API int32_t gingr_model_instance(gingr_ctx* ctx, const gingr_model* model, const gingr_state* st,

@@ -110,6 +110,9 @@ object GingrCudaNative {
   val posteriorMean  = fn("gingr_posterior_mean", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT,
                           ADDRESS, ADDRESS, ADDRESS)
   val coefficients   = fn("gingr_coefficients", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
+  // the r x r solve of the regression alone (pinv(Mx) * rhs as a Cholesky solve): A, nrhs rows of B -> L, L^-1 B^T rows, A^-1 b_0
+  val spdSolve       = fn("gingr_spd_solve", JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT,
+                          ADDRESS)
   val modelInstance  = fn("gingr_model_instance", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
   // device-resident loops: `iters` x update() without the host round trip (GingrAlgorithm.run's deterministic branch, :179-189)
   val updateChain    = fn("gingr_update_chain", JAVA_INT, ADDRESS, JAVA_INT)
