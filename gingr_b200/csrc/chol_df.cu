@@ -6,18 +6,18 @@
 // (r^3/3 = 2.7 GFLOP at r = 2000 is 0.1 ms of DMMA): the previous form (one panel kernel + one or two trailing-update
 // kernels per 64-column step, 32 dependent steps of ~47 us) is replaced by a tile data-flow:
 //
-//   * the lower triangle is cut into 64 x 64 tiles; tiles are handed out in column-major order by an atomic counter
-//     to a persistent grid (one CTA per SM); a CTA that owns tile (i, j) keeps its accumulator in registers,
-//     subtracts X_ik X_jk^T (DMMA.8x8x4) for every k < j as soon as the two operand tiles are flagged final
-//     (left-looking, operands double-buffered through cp.async), then
-//   * diagonal tile: factorises the 64 x 64 block inside the CTA (two in-register 32 x 32 warp factorisations that
-//     eliminate TWO columns per dependent rsqrt, the off-diagonal block by substitution, everything else as small
-//     products), also forms L_jj^-1, publishes both and raises the tile's flag;
-//   * off-diagonal tile: waits for L_jj^-1 and finishes with X_ij = A_ij L_jj^-T as a (triangular) DMMA product --
-//     no substitution outside the diagonal tiles.
-//   Because a CTA only ever waits for tiles with a smaller ticket, and every ticket that was drawn belongs to a
-//   running CTA, the spin waits cannot deadlock whatever else occupies the GPU.  No launch boundary, no grid-wide
-//   barrier: between two diagonal factorisations the critical path is  flag -> one tile product -> flag.
+//   * the lower triangle is cut into 64 x 64 tiles; TASKS are handed out in a topological order by an atomic ticket
+//     counter to a persistent grid (one CTA of 8 warps per SM).  A task keeps its accumulators in registers and
+//     subtracts X_ik X_jk^T (DMMA.8x8x4) for every k as soon as the two operand tiles are flagged final (left-looking,
+//     operands double-buffered through cp.async);
+//   * task T(i, j) (off-diagonal tile): waits for Z_j = L_jj^-1 and finishes with X_ij = A_ij Z_j^T as a (triangular)
+//     DMMA product -- no substitution anywhere outside the diagonal blocks;
+//   * task D(j) owns the diagonal tile (j, j) AND the tile (j, j-1) left of it: when Z_{j-1} appears it forms X_{j,j-1},
+//     keeps it in shared memory, applies the last update to the diagonal tile, factorises the 64 x 64 block inside
+//     the CTA (see potrf64), publishes Z_j and raises the flag.  Between two diagonal factorisations the critical
+//     path is therefore  flag -> one triangular tile product -> one tile product -- with no trip through global memory;
+//   * a CTA only ever waits for tasks with a smaller ticket, and every ticket that was drawn belongs to a running
+//     CTA, so the spin waits cannot deadlock whatever else occupies the GPU.  No launch boundary, no grid-wide barrier.
 //
 // Rows below the square part (right-hand sides stored as extra rows) ride along, which performs the forward
 // substitution L^-1 b inside the factorisation (as chol.cu's kernels did).
@@ -34,11 +34,11 @@ namespace {
 
 constexpr int TB = 64;                 // tile edge
 constexpr int TP = TB + 4;             // shared pitch, == 4 (mod 16): conflict-free DMMA fragment loads
-constexpr int DF_THREADS = 128;
+constexpr int DF_THREADS = 256;
 constexpr int TILE_DOUBLES = TB * TP;  // 4352
-// shared memory: 5 tile buffers (2 stages x 2 operands + the tile's own input), diag(L) and the sub-diagonal entries
-// L[2s+1][2s] of the in-CTA factorisation
-constexpr size_t DF_SMEM = (size_t)(5 * TILE_DOUBLES + TB + 32) * sizeof(double) + 64;
+// shared memory: 6 tile buffers (2 stages x 2 operands + the two input tiles of a diagonal task), diag(L), the
+// sub-diagonal entries L[2s+1][2s] and the step flags of the in-CTA factorisation
+constexpr size_t DF_SMEM = (size_t)(6 * TILE_DOUBLES + TB + 32 + 32) * sizeof(double) + 64;
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -54,6 +54,8 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// barrier of the two warps (64 threads) that own the pivot columns of a factorisation step
+__device__ __forceinline__ void bar_pair(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -63,19 +65,23 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 #ifdef DF_TIMING
 // tuning build only (tools/build_variant.sh dft chol_df.cu -DDF_TIMING): per tile 8 globaltimer stamps (ns) and, for
-// diagonal tiles, 8 clock64 phase stamps of the in-CTA factorisation; read with gingr_debug_chol_df_timing
+// diagonal tiles, clock64 phase stamps of the in-CTA factorisation; read with gingr_debug_chol_df_timing
 __device__ unsigned long long df_stamps[64 * 64 * 16];
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define DF_STAMP(tile, k) do { if (threadIdx.x == 0 && (tile) < 64 * 64) df_stamps[(tile) * 16 + (k)] = gtime(); } while (0)
 #define DF_CLOCK(tile, k) do { if (threadIdx.x == 0 && (tile) < 64 * 64) df_stamps[(tile) * 16 + 8 + (k)] = (unsigned long long)clock64(); } while (0)
+// per-step profile of the in-CTA factorisation of tile 0 (lane 0 of the warp that executes the marked code)
+__device__ long long potrf_prof[32 * 8];
+#define PF_MARK(s, k) do { if ((threadIdx.x & 31) == 0 && tile_id == 0) potrf_prof[(s) * 8 + (k)] = clock64(); } while (0)
 #else
+#define PF_MARK(s, k) ((void)0)
 #define DF_STAMP(tile, k) ((void)0)
 #define DF_CLOCK(tile, k) ((void)0)
 #endif
 
 struct DfParams {
   double* A;
-  int ld, n, nrows, nb, nbr, ntiles;
+  int ld, n, nrows, nb, nbr, ntasks;
   int* sync;      // [0] ticket counter, [1] finished CTAs, [2 ...] flags[nbr][nb]
   double* linv;   // [nb][64][64] inverses of the diagonal blocks
   int* info;
@@ -93,359 +99,301 @@ __device__ __forceinline__ void load_tile_async(double* s, const double* __restr
   }
 }
 
-// acc += I K^T over the 64 columns of the two shared tiles (warp tile 32 x 32: acc[i][j] = rows wm*32+i*8+g, cols wn*32+j*8+2t)
-__device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], const double* __restrict__ sI,
+// Warp tile of the 8 warps: 16 rows x 32 columns; acc[i][j] = rows wm*16 + i*8 + g, columns wn*32 + j*8 + 2t (+1).
+// acc += I K^T over the 64 columns of the two shared tiles
+__device__ __forceinline__ void mma_tile(double (&acc)[2][4][2], const double* __restrict__ sI,
                                          const double* __restrict__ sK, int wm, int wn, int g, int t) {
 #pragma unroll 4
   for (int c4 = 0; c4 < TB / 4; ++c4) {
-    double af[4], bf[4];
+    double af[2], bf[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) af[i] = sI[(wm * 32 + i * 8 + g) * TP + c4 * 4 + t];
+    for (int i = 0; i < 2; ++i) af[i] = sI[(wm * 16 + i * 8 + g) * TP + c4 * 4 + t];
 #pragma unroll
     for (int j = 0; j < 4; ++j) bf[j] = sK[(wn * 32 + j * 8 + g) * TP + c4 * 4 + t];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
   }
 }
 
+// diagonal task: accV += I K^T and (unless this warp sits in the unused upper-right quarter) accS += I I^T
+__device__ __forceinline__ void mma_tile2(double (&accV)[2][4][2], double (&accS)[2][4][2], const double* __restrict__ sI,
+                                          const double* __restrict__ sK, bool doS, int wm, int wn, int g, int t) {
+#pragma unroll 2
+  for (int c4 = 0; c4 < TB / 4; ++c4) {
+    double af[2], bk[4], bi[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) af[i] = sI[(wm * 16 + i * 8 + g) * TP + c4 * 4 + t];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bk[j] = sK[(wn * 32 + j * 8 + g) * TP + c4 * 4 + t];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(accV[i][j][0], accV[i][j][1], af[i], bk[j]);
+    if (doS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bi[j] = sI[(wn * 32 + j * 8 + g) * TP + c4 * 4 + t];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(accS[i][j][0], accS[i][j][1], af[i], bi[j]);
+    }
+  }
+}
+
 // X = V Z^T with Z lower triangular (Z = L^-1): column c of X only needs k <= c, so a fragment column block jj stops at
 // k4 < wn*8 + jj*2 + 2
-__device__ __forceinline__ void mma_tile_lower(double (&acc)[4][4][2], const double* __restrict__ sI,
+__device__ __forceinline__ void mma_tile_lower(double (&acc)[2][4][2], const double* __restrict__ sI,
                                                const double* __restrict__ sK, int wm, int wn, int g, int t) {
 #pragma unroll 2
   for (int c4 = 0; c4 < TB / 4; ++c4) {
     if (c4 >= wn * 8 + 8) break;
-    double af[4], bf[4];
+    double af[2], bf[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) af[i] = sI[(wm * 32 + i * 8 + g) * TP + c4 * 4 + t];
+    for (int i = 0; i < 2; ++i) af[i] = sI[(wm * 16 + i * 8 + g) * TP + c4 * 4 + t];
 #pragma unroll
     for (int j = 0; j < 4; ++j) bf[j] = sK[(wn * 32 + j * 8 + g) * TP + c4 * 4 + t];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (c4 < wn * 8 + j * 2 + 2) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int i = 0; i < 2; ++i) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// In-CTA factorisation of a 64 x 64 block, L AND L^-1 in one pass (all 128 threads).
-//
-// What bounds it (tools/lat_bench.cu on a B200): a DFMA issues once per ~6 cycles from a single warp (8 cycles dependent),
-// a 64-bit shuffle costs 26, a shared-memory exchange 35, the branch-free rsqrt 49.  So (1) the trailing updates must be
-// spread over all four warps, and (2) the dependent chain pivot -> rsqrt -> scale -> exchange -> update is walked as few
-// times as possible.  Layout: lane holds rows `lane` and `lane + 32`; warp g holds the column PAIRS 4 lp + g (lp < 8), i.e.
-// 32 matrix entries per thread in registers.  Step s eliminates the columns j = 2 s and j + 1 at once: with p = a_jj,
-// q = a_{j+1,j}, t = a_{j+1,j+1} the second pivot is det / p, det = p t - q^2, so rsqrt(p) and rsqrt(det) are independent
-// (one chain per TWO columns; det loses what t - (q rs)^2 loses).  The scaled columns go through shared memory (G2, one
-// double2 per row and step), one CTA barrier per step, and every thread updates its own 2 x 16 entries.
-// L^-1 rides along for free: a row that has been eliminated (row j after its pivot step) continues as row j of the identity
-// appended below the block -- rows below the square part receive X = I L^-T under exactly the same column operations, and
-// row m of the identity is zero before step m/2 -- so every thread always carries two ACTIVE rows, and at the end
-//   G2[r][s] = (L[r][2s], L[r][2s+1])  for r > 2s + 1,      G2[r][s] = (Z[2s][r], Z[2s+1][r])  for r <= 2s + 1   (Z = L^-1)
-// with L[2s+1][2s] in sSub[s] and the diagonal of L in sDiag.
-// The chain is executed by all warps on their own registers (no divergent block around it, so that ptxas can interleave it
-// with the updates); only the owner warp of the pair stores.
-// ---------------------------------------------------------------------------------------------
-constexpr int G2P = 33;   // double2 pitch of G2: 132 words == 4 (mod 32), conflict-free LDS.128 down a column
-
-__device__ __forceinline__ double rsq_nr(double d) {   // MUFU.RSQ64H seed + one cubic step: rsqrt() without its slow-path branch
-  double y0;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
-  const double e = fma(-d * y0, y0, 1.0);
-  const double h = fma(e, 0.375, 0.5);
-  return fma(y0 * e, h, y0);
-}
-
-// sT: the block (lower triangle, pitch TP, identity-padded beyond the valid part).  On return G2 / sDiag / sSub hold L and
-// Z = L^-1 as described above (read them with potrf_L / potrf_Z).  Returns true if a pivot was not positive and finite.
-__device__ __forceinline__ double potrf_L(const double2* __restrict__ G2, const double* __restrict__ sDiag,
-                                          const double* __restrict__ sSub, int r, int c) {   // r >= c
-  if (r == c) return sDiag[c];
-  if (r == c + 1 && !(c & 1)) return sSub[c >> 1];
-  const double2 v = G2[r * G2P + (c >> 1)];
-  return (c & 1) ? v.y : v.x;
-}
-__device__ __forceinline__ double potrf_Z(const double2* __restrict__ G2, int c, int k) {   // Z[c][k], zero for k > c
-  if (k > c) return 0.0;
-  const double2 v = G2[k * G2P + (c >> 1)];
-  return (c & 1) ? v.y : v.x;
-}
-__device__ __forceinline__ bool potrf64(const double* __restrict__ sT, double2* __restrict__ G2, double* __restrict__ sDiag,
-                                        double* __restrict__ sSub, int tid, int tile_id) {
-  const int lane = tid & 31, g = tid >> 5;
-  (void)tile_id;
-  DF_CLOCK(tile_id, 0);
-  double a0[16], a1[16];   // rows lane / lane + 32, columns 2 (4 lp + g) + e at index 2 lp + e
-#pragma unroll
-  for (int lp = 0; lp < 8; ++lp)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = 2 * (4 * lp + g) + e;
-      a0[2 * lp + e] = (col <= lane) ? sT[lane * TP + col] : 0.0;
-      a1[2 * lp + e] = (col <= lane + 32) ? sT[(lane + 32) * TP + col] : 0.0;
-    }
-  bool bad = false;
-#pragma unroll
-  for (int s = 0; s < 32; ++s) {
-    const int lp0 = s >> 2, go = s & 3;        // local index and owner warp of the pair
-    const int j = 2 * s, hf = j >> 5, pl = j & 31;
-    // ---- the chain: pivot block -> two independent rsqrt -> scaled columns of both rows ----------------------
-    const double v0 = hf ? a1[2 * lp0] : a0[2 * lp0];
-    const double v1 = hf ? a1[2 * lp0 + 1] : a0[2 * lp0 + 1];
-    const double p = __shfl_sync(0xffffffffu, v0, pl);
-    const double q = __shfl_sync(0xffffffffu, v0, pl + 1);
-    const double t = __shfl_sync(0xffffffffu, v1, pl + 1);
-    const double det = fma(p, t, -q * q);
-    const double rs1 = rsq_nr(p), rsd = rsq_nr(det);
-    const double sp = p * rs1;         // L[j][j]
-    const double l21 = q * rs1;        // L[j+1][j]
-    const double i22 = rsd * sp;       // 1 / L[j+1][j+1]
-    double f0a = a0[2 * lp0] * rs1, f0b = a1[2 * lp0] * rs1;
-    double f1a = fma(-f0a, l21, a0[2 * lp0 + 1]) * i22, f1b = fma(-f0b, l21, a1[2 * lp0 + 1]) * i22;
-    // rows j and j + 1 turn into rows of the appended identity: their factors are those of e_j and e_{j+1}
-    const bool sw0 = (lane == pl), sw1 = (lane == pl + 1);
-    if (hf == 0) {
-      if (sw0) { f0a = rs1; f1a = -rs1 * l21 * i22; }
-      if (sw1) { f0a = 0.0; f1a = i22; }
-    } else {
-      if (sw0) { f0b = rs1; f1b = -rs1 * l21 * i22; }
-      if (sw1) { f0b = 0.0; f1b = i22; }
-    }
-    if (g == go) {
-      if (!(p > 0.0) || !(p < INFINITY) || !(det > 0.0) || !(det < INFINITY)) bad = true;
-      G2[lane * G2P + s] = make_double2(f0a, f1a);
-      G2[(lane + 32) * G2P + s] = make_double2(f0b, f1b);
-      if (lane == 0) {
-        sDiag[j] = sp;
-        sDiag[j + 1] = fma(-l21, l21, t) * i22;
-        sSub[s] = l21;
-      }
-    }
-    __syncthreads();
-    if (s == 31) break;
-    // ---- trailing update of the own pairs > s (rows that just switched restart from zero) ------------------
-    const double2 Fa = G2[lane * G2P + s], Fb = G2[(lane + 32) * G2P + s];
-    const bool za = (hf == 0) && (sw0 || sw1), zb = (hf == 1) && (sw0 || sw1);
-#pragma unroll
-    for (int lp = lp0; lp < 8; ++lp) {
-      if (lp > lp0 || g > go) {
-        const int P = 4 * lp + g;
-        const double2 c0 = G2[(2 * P) * G2P + s], c1 = G2[(2 * P + 1) * G2P + s];
-        const double x0 = za ? 0.0 : a0[2 * lp], x1 = za ? 0.0 : a0[2 * lp + 1];
-        const double y0 = zb ? 0.0 : a1[2 * lp], y1 = zb ? 0.0 : a1[2 * lp + 1];
-        a0[2 * lp] = fma(-Fa.y, c0.y, fma(-Fa.x, c0.x, x0));
-        a0[2 * lp + 1] = fma(-Fa.y, c1.y, fma(-Fa.x, c1.x, x1));
-        a1[2 * lp] = fma(-Fb.y, c0.y, fma(-Fb.x, c0.x, y0));
-        a1[2 * lp + 1] = fma(-Fb.y, c1.y, fma(-Fb.x, c1.x, y1));
-      }
-    }
-  }
-  DF_CLOCK(tile_id, 1);
-  return __syncthreads_or(bad ? 1 : 0) != 0;
-}
-
+#include "chol_potrf.cuh"
 
 __global__ void __launch_bounds__(DF_THREADS, 1) chol_df_kernel(DfParams P) {
   extern __shared__ __align__(16) double dsm[];
-  double* buf0 = dsm;                       // stage 0, row operand   | potrf: Z = L^-1        | trsm: Z
-  double* buf1 = dsm + TILE_DOUBLES;        // stage 0, column operand| potrf: extra rows
-  double* buf2 = dsm + 2 * TILE_DOUBLES;    // stage 1, row operand   | potrf: column exchange G2
-  double* buf3 = dsm + 3 * TILE_DOUBLES;    // stage 1, column operand
-  double* sA0 = dsm + 4 * TILE_DOUBLES;     // the tile's own input, later its updated value / L
-  double* sDiag = dsm + 5 * TILE_DOUBLES;   // [64]
-  double* sSub = sDiag + TB;                // [32]
-  __shared__ int s_tile, s_pre[2];
+  double* bufI0 = dsm;                       // stage 0, row operand    | X_{j,j-1} of a diagonal task
+  double* bufK0 = dsm + TILE_DOUBLES;        // stage 0, column operand | Z of the finishing product
+  double* bufI1 = dsm + 2 * TILE_DOUBLES;    // stage 1, row operand    | potrf: factor exchange G2
+  double* bufK1 = dsm + 3 * TILE_DOUBLES;    // stage 1, column operand | potrf: rows below the square part
+  double* sV0 = dsm + 4 * TILE_DOUBLES;      // input / updated value of the off-diagonal tile
+  double* sA0 = dsm + 5 * TILE_DOUBLES;      // input / updated value of the diagonal tile (diagonal tasks)
+  double* sDiag = dsm + 6 * TILE_DOUBLES;    // [64]
+  double* sSub = sDiag + TB;                 // [32]
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sSub + 32);   // [32] step barriers of potrf64
+  __shared__ int s_task, s_pre[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
+  // warp tile: 16 rows x 32 columns.  wm = warp & 3 puts one left-half and one right-half warp on every SM sub-partition
+  // (warp % 4): the triangular products give the right half 2.6x the work of the left one
+  const int wm = warp & 3, wn = warp >> 2, g = lane >> 2, t = lane & 3;
   int* flags = P.sync + 2;
   const double* __restrict__ A = P.A;
-  const int ld = P.ld;
+  const int ld = P.ld, nb = P.nb;
+  if (tid < 32) mbar_init(&sBar[tid], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  unsigned potrf_calls = 0;   // the loop-top barrier orders the initialisation before the first use
 
   for (;;) {
-    __syncthreads();   // s_tile / shared buffers of the previous tile are free
-    if (tid == 0) s_tile = atomicAdd(&P.sync[0], 1);
+    __syncthreads();   // s_task / shared buffers of the previous task are free
+    if (tid == 0) s_task = atomicAdd(&P.sync[0], 1);
     __syncthreads();
-    int tt = s_tile;
-    if (tt >= P.ntiles) break;
+    int tt = s_task;
+    if (tt >= P.ntasks) break;
+    // ---- ticket -> task.  Column j: D(j) first, then T(i, j) for the rows i that no diagonal task owns -------------
     int j = 0;
-    while (tt >= P.nbr - j) { tt -= P.nbr - j; ++j; }
-    const int i = j + tt;
-    const int i0 = i * TB, j0 = j * TB;
-    const int jb = min(TB, P.n - j0);              // valid columns of this block column
-    const int rcnt = min(TB, P.nrows - i0);        // valid rows of this tile
-    const bool diag = (i == j);
-    const int tile_id = i * P.nb + j;
+    for (;;) {
+      const int cnt = (P.nbr - j - 1) + (j + 1 >= nb ? 1 : 0);
+      if (tt < cnt) break;
+      tt -= cnt;
+      ++j;
+    }
+    const bool isD = (tt == 0);
+    const int rb = isD ? j : ((j + 1 >= nb) ? j + tt : j + 1 + tt);   // row block of the task
+    const int cb = isD ? j - 1 : j;                                    // column block of its off-diagonal tile (-1: none)
+    const bool hasV = cb >= 0;
+    const int r0 = rb * TB;
+    const int rcnt = min(TB, P.nrows - r0);                            // valid rows
+    const int vb = hasV ? min(TB, P.n - cb * TB) : 0;                  // valid columns of the off-diagonal tile
+    const int tile_id = rb * nb + (isD ? j : cb);
     (void)tile_id;
     DF_STAMP(tile_id, 0);
 
-    // the tile's own input (its group completes long before it is needed)
-    load_tile_async(sA0, A, ld, i0, j0, rcnt, tid);
+    // the task's own input tiles (their group completes long before it is needed)
+    if (hasV) load_tile_async(sV0, A, ld, r0, cb * TB, rcnt, tid);
+    if (isD) load_tile_async(sA0, A, ld, r0, r0, rcnt, tid);
     cp_async_commit();
 
-    double acc[4][4][2];
+    double accV[2][4][2], accS[2][4][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+      for (int b = 0; b < 4; ++b) accV[a][b][0] = accV[a][b][1] = accS[a][b][0] = accS[a][b][1] = 0.0;
+    const bool doS = isD && !(wm < 2 && wn == 1);   // the upper-right quarter of a diagonal tile is never used
 
-    // ---- left-looking updates: S = sum_k X_ik X_jk^T ------------------------------------------------------
-    if (j > 0) {
+    // ---- left-looking updates over k < cb: V += X_{rb,k} X_{cb,k}^T, diagonal task also S += X_{rb,k} X_{rb,k}^T ----
+    if (cb > 0) {
+      const int* fI = flags + rb * nb;
+      const int* fK = flags + cb * nb;
       if (tid == 0) {
-        while (ld_acquire(&flags[i * P.nb + 0]) == 0) {}
-        if (!diag) while (ld_acquire(&flags[j * P.nb + 0]) == 0) {}
+        while (ld_acquire(fI) == 0) {}
+        while (ld_acquire(fK) == 0) {}
       }
       __syncthreads();
-      load_tile_async(buf0, A, ld, i0, 0, rcnt, tid);
-      if (!diag) load_tile_async(buf1, A, ld, j0, 0, TB, tid);
+      load_tile_async(bufI0, A, ld, r0, 0, rcnt, tid);
+      load_tile_async(bufK0, A, ld, cb * TB, 0, TB, tid);
       cp_async_commit();
-      for (int k = 0; k < j; ++k) {
+      for (int k = 0; k < cb; ++k) {
         const int st = k & 1;
-        double* sI = st ? buf2 : buf0;
-        double* sK = diag ? sI : (st ? buf3 : buf1);
-        const bool more = (k + 1 < j);
+        const double* sI = st ? bufI1 : bufI0;
+        const double* sK = st ? bufK1 : bufK0;
+        const bool more = (k + 1 < cb);
         if (tid == 0) {
           int pre = 0;
-          if (more) pre = (ld_acquire(&flags[i * P.nb + k + 1]) != 0) && (diag || ld_acquire(&flags[j * P.nb + k + 1]) != 0);
+          if (more) pre = (ld_acquire(fI + k + 1) != 0) && (ld_acquire(fK + k + 1) != 0);
           s_pre[st] = pre;        // two slots: a slow reader of step k cannot see the value of step k + 1
         }
         cp_async_wait_all();
         __syncthreads();          // stage k landed; every thread is past the product of step k - 1; s_pre visible
         const bool pre = s_pre[st] != 0;
         if (more && pre) {
-          load_tile_async(st ? buf0 : buf2, A, ld, i0, (k + 1) * TB, rcnt, tid);
-          if (!diag) load_tile_async(st ? buf1 : buf3, A, ld, j0, (k + 1) * TB, TB, tid);
+          load_tile_async(st ? bufI0 : bufI1, A, ld, r0, (k + 1) * TB, rcnt, tid);
+          load_tile_async(st ? bufK0 : bufK1, A, ld, cb * TB, (k + 1) * TB, TB, tid);
           cp_async_commit();
         }
-        if (!(diag && wm == 0 && wn == 1)) mma_tile(acc, sI, sK, wm, wn, g, t);   // the upper-right quarter of a diagonal tile is never used
+        if (isD) mma_tile2(accV, accS, sI, sK, doS, wm, wn, g, t);
+        else mma_tile(accV, sI, sK, wm, wn, g, t);
         if (more && !pre) {
           if (tid == 0) {
-            while (ld_acquire(&flags[i * P.nb + k + 1]) == 0) {}
-            if (!diag) while (ld_acquire(&flags[j * P.nb + k + 1]) == 0) {}
+            while (ld_acquire(fI + k + 1) == 0) {}
+            while (ld_acquire(fK + k + 1) == 0) {}
           }
           __syncthreads();
-          load_tile_async(st ? buf0 : buf2, A, ld, i0, (k + 1) * TB, rcnt, tid);
-          if (!diag) load_tile_async(st ? buf1 : buf3, A, ld, j0, (k + 1) * TB, TB, tid);
+          load_tile_async(st ? bufI0 : bufI1, A, ld, r0, (k + 1) * TB, rcnt, tid);
+          load_tile_async(st ? bufK0 : bufK1, A, ld, cb * TB, (k + 1) * TB, TB, tid);
           cp_async_commit();
         }
       }
     }
     cp_async_wait_all();
-    __syncthreads();   // sA0 landed; the stage buffers are free
+    __syncthreads();   // the input tiles landed; the stage buffers are free
     DF_STAMP(tile_id, 1);
 
-    // ---- sA0 <- A0 - S, masked to the valid part ---------------------------------------------------------------
+    if (hasV) {
+      // ---- sV0 <- A - V (masked to the valid part);  X = sV0 Z^T with Z = L_cb^-1 ------------------------------------
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int row = wm * 32 + a * 8 + g, col = wn * 32 + b * 8 + 2 * t;
-        double2* p = reinterpret_cast<double2*>(sA0 + row * TP + col);
-        double2 v = *p;
-        v.x = (row < rcnt && col < jb) ? v.x - acc[a][b][0] : 0.0;
-        v.y = (row < rcnt && col + 1 < jb) ? v.y - acc[a][b][1] : 0.0;
-        *p = v;
-      }
-    __syncthreads();
-
-    if (diag) {
-      // rows >= jb of a diagonal tile lie below the square part (right-hand sides): set them aside, pad with identity
-      const int ecnt = rcnt - jb;     // > 0 only in the last block column
-      if (jb < TB) {
-        for (int e = tid; e < TB * TB; e += DF_THREADS) {
-          const int r = e >> 6, c = e & 63;
-          if (r >= jb) {
-            buf1[r * TP + c] = sA0[r * TP + c];
-            sA0[r * TP + c] = (r == c) ? 1.0 : 0.0;
-          }
+        for (int b = 0; b < 4; ++b) {
+          const int row = wm * 16 + a * 8 + g, col = wn * 32 + b * 8 + 2 * t;
+          double2* p = reinterpret_cast<double2*>(sV0 + row * TP + col);
+          double2 v = *p;
+          v.x = (row < rcnt && col < vb) ? v.x - accV[a][b][0] : 0.0;
+          v.y = (row < rcnt && col + 1 < vb) ? v.y - accV[a][b][1] : 0.0;
+          *p = v;
+          accV[a][b][0] = accV[a][b][1] = 0.0;
         }
-        __syncthreads();
-      }
-      DF_STAMP(tile_id, 2);
-      const double2* G2 = reinterpret_cast<const double2*>(buf2);
-      const bool bad = potrf64(sA0, reinterpret_cast<double2*>(buf2), sDiag, sSub, tid, tile_id);
-      DF_STAMP(tile_id, 3);
-      if (bad && tid == 0) P.info[0] = 1;
-      // publish Z = L^-1 first: it is all the waiting tiles of this block column need
-      double* Z = P.linv + (size_t)j * TB * TB;
-#pragma unroll 4
-      for (int e = tid; e < TB * (TB / 2); e += DF_THREADS) {
-        const int c = e >> 5, k = (e & 31) * 2;
-        *reinterpret_cast<double2*>(Z + c * TB + k) = make_double2(potrf_Z(G2, c, k), potrf_Z(G2, c, k + 1));
-      }
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        st_release(&flags[i * P.nb + j], 1);
-      }
-      DF_STAMP(tile_id, 4);
-      // ... then L and the solved extra rows, which nothing inside this kernel reads (a diagonal tile is never an operand)
-      for (int e = tid; e < TB * TB; e += DF_THREADS) {
-        const int r = e >> 6, c = e & 63;
-        if (r < jb && c <= r) P.A[(size_t)(i0 + r) * ld + j0 + c] = potrf_L(G2, sDiag, sSub, r, c);
-      }
-      if (ecnt > 0) {
-        for (int e = tid; e < ecnt * TB; e += DF_THREADS) {
-          const int r = jb + (e >> 6), c = e & 63;
-          if (c < jb) {
-            const double* er = buf1 + r * TP;
-            double s0 = 0.0;
-            for (int k = 0; k <= c; ++k) s0 = fma(er[k], potrf_Z(G2, c, k), s0);
-            P.A[(size_t)(i0 + r) * ld + j0 + c] = s0;
-          }
-        }
-      }
-      continue;   // the flag is up already
-    } else {
-      // X = V Z^T with Z = L_jj^-1
-      if (tid == 0) while (ld_acquire(&flags[j * P.nb + j]) == 0) {}
+      if (tid == 0) while (ld_acquire(&flags[cb * nb + cb]) == 0) {}
       __syncthreads();
       DF_STAMP(tile_id, 2);
       {
-        const double* Z = P.linv + (size_t)j * TB * TB;
+        const double* Z = P.linv + (size_t)cb * TB * TB;
 #pragma unroll 4
         for (int e = tid; e < TB * (TB / 2); e += DF_THREADS) {
           const int r = e >> 5, c = (e & 31) * 2;
-          cp_async16(buf0 + r * TP + c, Z + r * TB + c);
+          cp_async16(bufK0 + r * TP + c, Z + r * TB + c);
         }
         cp_async_commit();
       }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
       cp_async_wait_all();
       __syncthreads();
-      mma_tile_lower(acc, sA0, buf0, wm, wn, g, t);
+      mma_tile_lower(accV, sV0, bufK0, wm, wn, g, t);
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const int row = wm * 32 + a * 8 + g, col = wn * 32 + b * 8 + 2 * t;
+          const int row = wm * 16 + a * 8 + g, col = wn * 32 + b * 8 + 2 * t;
+          if (isD) *reinterpret_cast<double2*>(bufI0 + row * TP + col) = make_double2(accV[a][b][0], accV[a][b][1]);
           if (row < rcnt) {
-            double* p = P.A + (size_t)(i0 + row) * ld + j0 + col;
-            if (col + 1 < jb) *reinterpret_cast<double2*>(p) = make_double2(acc[a][b][0], acc[a][b][1]);
-            else if (col < jb) p[0] = acc[a][b][0];
+            double* p = P.A + (size_t)(r0 + row) * ld + cb * TB + col;
+            if (col + 1 < vb) *reinterpret_cast<double2*>(p) = make_double2(accV[a][b][0], accV[a][b][1]);
+            else if (col < vb) p[0] = accV[a][b][0];
           }
         }
+      __syncthreads();   // every thread's stores are issued; X is complete in shared memory (diagonal task)
+      if (tid == DF_THREADS - 1) {   // the last warp pays for the fence, not the warp that leads the diagonal factorisation
+        __threadfence();
+        st_release(&flags[rb * nb + cb], 1);
+      }
+      DF_STAMP(tile_id, 3);
+      if (!isD) continue;
+      // the last update of the diagonal tile, with X_{j,j-1} straight from shared memory
+      if (doS) mma_tile(accS, bufI0, bufI0, wm, wn, g, t);
     }
-    __syncthreads();   // every thread's stores are issued
-    if (tid == 0) {
-      __threadfence();
-      st_release(&flags[i * P.nb + j], 1);
+
+    // ---- diagonal task: sA0 <- A_jj - S, factorise, publish --------------------------------------------------------
+    const int jb = min(TB, P.n - r0);      // valid columns of this block column
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int row = wm * 16 + a * 8 + g, col = wn * 32 + b * 8 + 2 * t;
+        double2* p = reinterpret_cast<double2*>(sA0 + row * TP + col);
+        double2 v = *p;
+        v.x = (row < rcnt && col < jb) ? v.x - accS[a][b][0] : 0.0;
+        v.y = (row < rcnt && col + 1 < jb) ? v.y - accS[a][b][1] : 0.0;
+        *p = v;
+      }
+    __syncthreads();
+    // rows >= jb of a diagonal tile lie below the square part (right-hand sides): set them aside, pad with identity
+    const int ecnt = rcnt - jb;     // > 0 only in the last block column
+    if (jb < TB) {
+      for (int e = tid; e < TB * TB; e += DF_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        if (r >= jb) {
+          bufK1[r * TP + c] = sA0[r * TP + c];
+          sA0[r * TP + c] = (r == c) ? 1.0 : 0.0;
+        }
+      }
+      __syncthreads();
     }
     DF_STAMP(tile_id, 4);
+    const double2* G2 = reinterpret_cast<const double2*>(bufI1);
+    const bool bad = potrf64(sA0, reinterpret_cast<double2*>(bufI1), sDiag, sSub, sBar, potrf_calls & 1u, tid, tile_id);
+    ++potrf_calls;
+    DF_STAMP(tile_id, 5);
+    if (bad && tid == 0) P.info[0] = 1;
+    // publish Z = L^-1 first: it is all the waiting tasks of this block column need
+    double* Z = P.linv + (size_t)j * TB * TB;
+#pragma unroll 4
+    for (int e = tid; e < TB * (TB / 2); e += DF_THREADS) {
+      const int c = e >> 5, k = (e & 31) * 2;
+      *reinterpret_cast<double2*>(Z + c * TB + k) = make_double2(potrf_Z(G2, c, k), potrf_Z(G2, c, k + 1));
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      st_release(&flags[j * nb + j], 1);
+    }
+    DF_STAMP(tile_id, 6);
+    // ... then L and the solved extra rows, which nothing inside this kernel reads (a diagonal tile is never an operand)
+    for (int e = tid; e < TB * TB; e += DF_THREADS) {
+      const int r = e >> 6, c = e & 63;
+      if (r < jb && c <= r) P.A[(size_t)(r0 + r) * ld + r0 + c] = potrf_L(G2, sDiag, sSub, r, c);
+    }
+    if (ecnt > 0) {
+      for (int e = tid; e < ecnt * TB; e += DF_THREADS) {
+        const int r = jb + (e >> 6), c = e & 63;
+        if (c < jb) {
+          const double* er = bufK1 + r * TP;
+          double s0 = 0.0;
+          for (int k = 0; k <= c; ++k) s0 = fma(er[k], potrf_Z(G2, c, k), s0);
+          P.A[(size_t)(r0 + r) * ld + r0 + c] = s0;
+        }
+      }
+    }
   }
   // ---- the last CTA out resets the tickets and flags for the next launch (no memset node in the captured graph) ----
   __shared__ int s_last;
   if (tid == 0) s_last = (atomicAdd(&P.sync[1], 1) == (int)gridDim.x - 1);
   __syncthreads();
   if (s_last) {
-    for (int e = tid; e < P.nbr * P.nb; e += DF_THREADS) flags[e] = 0;
+    for (int e = tid; e < P.nbr * nb; e += DF_THREADS) flags[e] = 0;
     if (tid == 0) { P.sync[0] = 0; P.sync[1] = 0; }
   }
 }
@@ -484,15 +432,15 @@ int32_t cholesky_df_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int l
   P.nrows = nrows;
   P.nb = ceil_div(n, TB);
   P.nbr = ceil_div(nrows, TB);
-  P.ntiles = 0;
-  for (int j = 0; j < P.nb; ++j) P.ntiles += P.nbr - j;
+  P.ntasks = 0;   // per block column: the diagonal task + the rows no diagonal task owns
+  for (int j = 0; j < P.nb; ++j) P.ntasks += (P.nbr - j - 1) + (j + 1 >= P.nb ? 1 : 0);
   if ((size_t)(2 + (size_t)P.nb * P.nbr) > ws.sync.n || (size_t)P.nb * TB * TB > ws.linv.n)
     return gingr_fail(ctx, GINGR_ERR_ARG, "cholesky: workspace too small");
   if ((ld & 1) != 0 || (((uintptr_t)d_A) & 15) != 0) return gingr_fail(ctx, GINGR_ERR_ARG, "cholesky: matrix must be 16-byte aligned with an even pitch");
   P.sync = ws.sync.p;
   P.linv = ws.linv.p;
   P.info = d_info;
-  const int grid = std::min(P.ntiles, ctx->num_sms);
+  const int grid = std::min(P.ntasks, ctx->num_sms);
   chol_df_kernel<<<grid, DF_THREADS, DF_SMEM, ctx->stream>>>(P);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
@@ -502,6 +450,11 @@ int32_t cholesky_df_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int l
 }  // namespace gingr
 
 #ifdef DF_TIMING
+extern "C" GINGR_API int32_t gingr_debug_potrf_profile(long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, gingr::potrf_prof, sizeof(long long) * 32 * 8);
+  return 0;
+}
 extern "C" GINGR_API int32_t gingr_debug_chol_df_timing(unsigned long long* out, int32_t count) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, gingr::df_stamps, sizeof(unsigned long long) * (size_t)count);

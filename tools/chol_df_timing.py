@@ -21,16 +21,21 @@ t0 = st[0 * nb + 0, 0]
 rows = []
 for j in range(nb):
     d = st[j * nb + j]
-    ph = (d[9:11] - d[8:10]).tolist()
-    row = {"j": j, "start_us": (d[0] - t0) / 1e3, "updates_done_us": (d[1] - t0) / 1e3, "potrf_us": (d[3] - d[2]) / 1e3,
-           "flag_us": (d[4] - t0) / 1e3, "potrf_cycles": ph}
-    if j + 1 < nbr:
-        e = st[(j + 1) * nb + j]
-        row["below"] = {"start_us": (e[0] - t0) / 1e3, "updates_done_us": (e[1] - t0) / 1e3, "gotZ_us": (e[2] - t0) / 1e3, "flag_us": (e[4] - t0) / 1e3}
-    rows.append(row)
+    rows.append({"j": j, "start_us": (d[0] - t0) / 1e3, "updates_done_us": (d[1] - t0) / 1e3, "gotZprev_us": (d[2] - t0) / 1e3 if j else None,
+                 "Xflag_us": (d[3] - t0) / 1e3 if j else None, "potrf_start_us": (d[4] - t0) / 1e3, "potrf_us": (d[5] - d[4]) / 1e3,
+                 "flag_us": (d[6] - t0) / 1e3, "potrf_cycles": int(d[9] - d[8])})
 steps = [rows[k + 1]["flag_us"] - rows[k]["flag_us"] for k in range(nb - 1)]
 print(json.dumps({"n": n, "ms": o["ms"], "step_us_mean": float(np.mean(steps)) if steps else None,
                   "potrf_us_mean": float(np.mean([r["potrf_us"] for r in rows])),
-                  "phases_cycles_mean(elimination, unpack)": np.mean([r["potrf_cycles"] for r in rows], axis=0).round(0).tolist()}))
+                  "potrf_cycles_mean": float(np.mean([r["potrf_cycles"] for r in rows]))}))
 for r in rows[:4] + rows[-3:]:
     print(json.dumps(r))
+
+if hasattr(ctx._lib, "gingr_debug_potrf_profile"):
+    pb = (ctypes.c_longlong * (32 * 8))()
+    ctx._lib.gingr_debug_potrf_profile(pb)
+    pf = np.array(pb, dtype=np.int64).reshape(32, 8)
+    base = pf[0, 0]
+    print("potrf profile of tile 0, cycles since the first chain start: owner chain start / factors ready / released | next owner: acquired / pivot pair updated")
+    for s in range(0, 32):
+        print(s, (pf[s, :5] - base).tolist())
