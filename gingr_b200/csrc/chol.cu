@@ -457,8 +457,10 @@ int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, 
 }
 
 int32_t chol_backsolve_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld, const double* d_z, double* d_c,
-                               int* d_flags) {
+                               int* d_flags, CholWs* ws) {
   const int nb = ceil_div(n, NB);
+  static const int env_df = [] { const char* e = getenv("GINGR_CHOL_DF"); return e ? atoi(e) : 1; }();
+  if (ws != nullptr && env_df != 0 && nb > 1) return chol_backsolve_z_enqueue(ctx, n, d_L, ld, d_z, d_c, *ws);
   if (nb == 1) {
     chol_backsolve_small_kernel<<<1, 32, 0, ctx->stream>>>(n, d_L, ld, d_z, d_c);
     GINGR_LAUNCHED(ctx);

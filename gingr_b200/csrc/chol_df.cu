@@ -398,6 +398,90 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_df_kernel(DfParams P) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward substitution  L^T c = z  with the published inverses Z_k = L_kk^-1 of the factorisation above: one CTA per
+// 64-block, blocks become ready from the last one up.  CTA k accumulates  z_k - sum_{i>k} L_ik^T c_i  as the c_i appear
+// and finishes with c_k = Z_k^T acc.  Everything the critical step needs is in shared memory BEFORE its flag arrives:
+// Z_k, and the L_ik blocks stream through a two-deep cp.async ring one block ahead of the flags, so between two flags
+// there is one 64 x 64 mat-vec from shared memory, one more with Z_k^T, a fence and the flag (chol.cu's kernel inverted
+// its diagonal block itself and read every L_ik from global memory after the flag: 5.6 us per block, now ~2).
+// flags: nb + 1 ints, zero on entry; the last CTA out zeroes them again.
+// ---------------------------------------------------------------------------------------------
+constexpr int BS_THREADS = 256;
+constexpr size_t BS_SMEM = (size_t)(3 * TB * TB + TB + 4 * TB + TB) * sizeof(double);
+
+__global__ void __launch_bounds__(BS_THREADS) chol_backsolve_z_kernel(int n, const double* __restrict__ L, int ld,
+                                                                      const double* __restrict__ z, double* __restrict__ c,
+                                                                      const double* __restrict__ linv, int* flags) {
+  extern __shared__ __align__(16) double bsm[];
+  double* sZ = bsm;                    // [64][64] Z_k
+  double* sLb = bsm + TB * TB;         // [2][64][64] L_ik ring
+  double* sc = bsm + 3 * TB * TB;      // [64] c_i
+  double* sacc = sc + TB;              // [4][64] partial sums
+  double* acc = sacc + 4 * TB;         // [64]
+  const int nb = (n + TB - 1) / TB;
+  const int k = nb - 1 - (int)blockIdx.x;   // first CTAs own the last blocks (solved first)
+  const int tid = threadIdx.x, col = tid & 63, part = tid >> 6;
+  const int k0 = k * TB, kcnt = min(TB, n - k0);
+  auto load_block = [&](double* dst, int i) {   // rows of block i, columns of block k (k < i: all 64 columns exist)
+    const int i0 = i * TB, icnt = min(TB, n - i0);
+#pragma unroll 4
+    for (int e = tid; e < TB * (TB / 2); e += BS_THREADS) {
+      const int r = e >> 5, cc = (e & 31) * 2;
+      if (r < icnt) cp_async16(dst + r * TB + cc, L + (size_t)(i0 + r) * ld + k0 + cc);
+      else *reinterpret_cast<double2*>(dst + r * TB + cc) = make_double2(0.0, 0.0);
+    }
+  };
+  {
+    const double* Z = linv + (size_t)k * TB * TB;
+#pragma unroll 4
+    for (int e = tid; e < TB * (TB / 2); e += BS_THREADS) cp_async16(sZ + 2 * e, Z + 2 * e);
+  }
+  if (k + 1 < nb) load_block(sLb, nb - 1);
+  cp_async_commit();
+  if (tid < TB) acc[tid] = tid < kcnt ? z[k0 + tid] : 0.0;
+  double s = 0.0;
+  for (int i = nb - 1; i > k; --i) {
+    const int st = (nb - 1 - i) & 1;
+    if (i - 1 > k) load_block(sLb + (st ^ 1) * TB * TB, i - 1);   // the ring slot was last read two steps ago (barriers below)
+    cp_async_commit();
+    if (tid == 0) while (ld_acquire(&flags[i]) == 0) {}
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    __syncthreads();
+    const int i0 = i * TB;
+    if (tid < TB) sc[tid] = (i0 + tid < n) ? __ldcg(c + i0 + tid) : 0.0;
+    __syncthreads();
+    const double* Lb = sLb + st * TB * TB;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) s = fma(Lb[(part * 16 + rr) * TB + col], sc[part * 16 + rr], s);
+  }
+  cp_async_wait_all();
+  sacc[part * TB + col] = s;
+  __syncthreads();
+  if (tid < TB) acc[tid] -= (sacc[tid] + sacc[TB + tid]) + (sacc[2 * TB + tid] + sacc[3 * TB + tid]);
+  __syncthreads();
+  // c_k = Z_k^T acc :  c[j] = sum_{i >= j} Z[i][j] acc[i]   (4 partial sums per output)
+  {
+    double t = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const int i = part * 16 + rr;
+      t = fma(sZ[i * TB + col], acc[i], t);     // Z is lower triangular with zeros above the diagonal
+    }
+    sacc[part * TB + col] = t;
+  }
+  __syncthreads();
+  if (tid < kcnt) c[k0 + tid] = (sacc[tid] + sacc[TB + tid]) + (sacc[2 * TB + tid] + sacc[3 * TB + tid]);
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    st_release(&flags[k], 1);
+    if (atomicAdd(&flags[nb], 1) == nb - 1) {   // last CTA out: every flag has been read for the last time
+      for (int e = 0; e <= nb; ++e) flags[e] = 0;
+    }
+  }
+}
+
 }  // namespace
 
 int32_t CholWs::alloc(gingr_ctx* ctx, int n, int nrows) {
@@ -408,6 +492,10 @@ int32_t CholWs::alloc(gingr_ctx* ctx, int n, int nrows) {
     GINGR_CUDA_TRY(ctx, cudaMemsetAsync(sync.p, 0, sizeof(int) * ns, ctx->stream));
   }
   GINGR_CUDA_TRY(ctx, linv.alloc((size_t)nb * TB * TB));
+  if (bsync.n < (size_t)nb + 1) {
+    GINGR_CUDA_TRY(ctx, bsync.alloc((size_t)nb + 1));
+    GINGR_CUDA_TRY(ctx, cudaMemsetAsync(bsync.p, 0, sizeof(int) * ((size_t)nb + 1), ctx->stream));
+  }
   cap_n = std::max(cap_n, n);
   cap_nrows = std::max(cap_nrows, nrows);
   return GINGR_OK;
@@ -416,6 +504,7 @@ int32_t CholWs::alloc(gingr_ctx* ctx, int n, int nrows) {
 void CholWs::release() {
   sync.release();
   linv.release();
+  bsync.release();
   cap_n = cap_nrows = 0;
 }
 
@@ -442,6 +531,21 @@ int32_t cholesky_df_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int l
   P.info = d_info;
   const int grid = std::min(P.ntasks, ctx->num_sms);
   chol_df_kernel<<<grid, DF_THREADS, DF_SMEM, ctx->stream>>>(P);
+  GINGR_LAUNCHED(ctx);
+  GINGR_CUDA_TRY(ctx, cudaGetLastError());
+  return GINGR_OK;
+}
+
+int32_t chol_backsolve_z_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld, const double* d_z, double* d_c, CholWs& ws) {
+  static thread_local int attr_device = -1;
+  if (attr_device != ctx->device) {
+    GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(chol_backsolve_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM));
+    attr_device = ctx->device;
+  }
+  const int nb = ceil_div(n, TB);
+  if ((size_t)nb + 1 > ws.bsync.n || (size_t)nb * TB * TB > ws.linv.n) return gingr_fail(ctx, GINGR_ERR_ARG, "back solve: workspace too small");
+  if (nb > ctx->num_sms) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "rank too large for the sync-free back solve");
+  chol_backsolve_z_kernel<<<nb, BS_THREADS, BS_SMEM, ctx->stream>>>(n, d_L, ld, d_z, d_c, ws.linv.p, ws.bsync.p);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

@@ -29,7 +29,7 @@ int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_part
 // Workspace of the data-flow factorisation (chol_df.cu): tile tickets / flags and the inverses of the diagonal blocks.
 // One per concurrent factorisation (a registration owns one); alloc() outside stream capture.
 struct CholWs {
-  DevBuf<int> sync;
+  DevBuf<int> sync, bsync;   // factorisation tickets / flags; flags of the back substitution
   DevBuf<double> linv;
   int cap_n = 0, cap_nrows = 0;
   int32_t alloc(gingr_ctx* ctx, int n, int nrows);
@@ -39,8 +39,11 @@ struct CholWs {
 int32_t cholesky_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, int* d_info, CholWs* ws = nullptr);
 int32_t cholesky_df_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int ld, int* d_info, CholWs& ws);
 // c = L^-T z  (sync-free multi-CTA backward substitution).  d_flags: >= ceil(n/64) ints of scratch.
+// ws (optional): the workspace the factor was computed with by the data-flow kernel -- the back substitution then uses
+// the published inverses of the diagonal blocks (chol_df.cu); GINGR_CHOL_DF=0 or ws == nullptr: chol.cu's kernel.
 int32_t chol_backsolve_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld, const double* d_z, double* d_c,
-                               int* d_flags);
+                               int* d_flags, CholWs* ws = nullptr);
+int32_t chol_backsolve_z_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld, const double* d_z, double* d_c, CholWs& ws);
 
 // ---- vecops.cu -----------------------------------------------------------------------------------
 // out_q[k] = sum_a phi[k][a] v_q[a],  q < nvec (1 or 2), k < rows

@@ -1004,7 +1004,7 @@ int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model, const dou
   if ((rc = gram_finish_enqueue(ctx, s.gram, s.gram.d_partial.p, m->sqrt_lambda.p, 1.0, L, d_lrows.p, d_lA.p, rp, s.Mx.p)) < 0) return fail(rc);
   if ((rc = cholesky_enqueue(ctx, r, r + 1, s.Mx.p, rp, s.is.p + IS_INFO, &s.cholws)) < 0) return fail(rc);
   double* c = s.vec.p;
-  if ((rc = chol_backsolve_enqueue(ctx, r, s.Mx.p, rp, rhs, c, s.flags.p)) < 0) return fail(rc);
+  if ((rc = chol_backsolve_enqueue(ctx, r, s.Mx.p, rp, rhs, c, s.flags.p, &s.cholws)) < 0) return fail(rc);
   check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, c, s.is.p + IS_FAIL_POST);
   GINGR_LAUNCHED(ctx);
   if (mean_pts) {
@@ -1092,7 +1092,7 @@ int32_t gingr_spd_solve(gingr_ctx* ctx, int32_t n, const double* A, int32_t nrhs
     SS_TRY(cudaMemcpyAsync(work.p, in.p, sizeof(double) * (size_t)nrows * np, cudaMemcpyDeviceToDevice, st));
     SS_TRY(cudaEventRecord(e0, st));
     rc = cholesky_enqueue(ctx, n, nrows, work.p, np, info.p, &ws);
-    if (rc >= 0 && nrhs > 0) rc = chol_backsolve_enqueue(ctx, n, work.p, np, work.p + (size_t)n * np, x.p, flags.p);
+    if (rc >= 0 && nrhs > 0) rc = chol_backsolve_enqueue(ctx, n, work.p, np, work.p + (size_t)n * np, x.p, flags.p, &ws);
     if (rc < 0) { cudaStreamSynchronize(st); rel(); return rc; }
     SS_TRY(cudaEventRecord(e1, st));
     SS_TRY(cudaEventSynchronize(e1));
@@ -1479,7 +1479,9 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
   return GINGR_OK;
 }
 
-static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, uint64_t seed) {
+// fresh_factor: g->Mx was factorised by the posterior phase right before (its block inverses still sit in g->cholws); the
+// MH chain calls this on a KEPT factor that was copied around since, and then takes chol.cu's back substitution
+static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, uint64_t seed, bool fresh_factor = false) {
   gingr_ctx* ctx = g->ctx;
   const gingr_model* m = g->model;
   const gingr_config& cfg = g->cfg;
@@ -1494,7 +1496,7 @@ static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, ui
                                                                      rhs);
     GINGR_LAUNCHED(ctx);
   }
-  GINGR_TRY(chol_backsolve_enqueue(ctx, r, g->Mx.p, rp, rhs, vec, g->flags.p));
+  GINGR_TRY(chol_backsolve_enqueue(ctx, r, g->Mx.p, rp, rhs, vec, g->flags.p, fresh_factor ? &g->cholws : nullptr));
   g->rec(9);
   // ---- alpha* = coefficients(posterior mean) = W0 S c ; combine ---------------------------------------------
   // (a non-finite c is flagged by the first product, a non-finite alpha_new by the last: no separate launches)
@@ -1542,7 +1544,7 @@ static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, ui
 
 static int32_t enqueue_iteration(gingr_registration* g, int probabilistic = 0, uint64_t seed = 0) {
   GINGR_TRY(enqueue_posterior_phase(g));
-  return enqueue_update_phase(g, probabilistic, seed);
+  return enqueue_update_phase(g, probabilistic, seed, true);
 }
 
 static bool graphs_enabled(const gingr_ctx* ctx) {
