@@ -16,19 +16,34 @@ library, so scaling is STRONG (total work fixed).  Prints one JSON line (rank 0)
   roofline  dominant kernel, timed live with CUDA events recorded around it on the library's stream, in an
             event-instrumented pass of the same chain right after the timed one (the timed chain replays the captured
             iteration graph, which cannot carry per-iteration events).
-  cpu_baseline  the CPU oracle (port of the reference path, NOT the JVM) on this box's cores on a bounded sample.
+  parity    the first iterations of the seeded chain re-played and compared with the cached oracle values
+            (tests/golden/c4_chain_oracle.npz, oracle/fast.py); the run fails if any exceeds 1e-6.
+  cpu_baseline  the CPU oracle (port of the reference path, NOT the JVM) on this box's cores: ONE real update() of the
+            same workload (bounded sample = 1 iteration), N = 1 only.
+  secondary the other named configurations of BASELINE.json (C1, C3, C5) and the ICP iteration at 200k points with the K2
+            roofline (bench_secondary.py).
 
 --impl reference times the CPU port as the main line (the JVM reference cannot run here: no JVM, scalismo /
-Breeze jars absent).
+Breeze jars absent): real update() iterations of the oracle (oracle/fast.py: the algorithmic-minimum form,
+pinned to the literal restatement by tests/test_oracle_fast.py) on the SAME workload, all host cores, --steps / --warmup
+honoured, wall clock -- no sampling, no extrapolation.
 """
 from __future__ import annotations
 
+import os
+import sys
+
+# The CPU legs use every host core.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently turn the
+# reference arm into a one-core run: undo that BEFORE numpy / OpenBLAS / libgomp read the environment.
+_CPU_CORES = os.cpu_count() or 1
+if "--impl" in sys.argv and "reference" in sys.argv:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_CPU_CORES)
+
 import argparse
 import json
-import os
 import statistics
 import subprocess
-import sys
 import tempfile
 import threading
 import time
@@ -135,49 +150,47 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU port (oracle) timing -- only the cpu_baseline / --impl reference legs touch oracle/
 # ---------------------------------------------------------------------------------------------------
-def cpu_iteration_seconds(name: str, budget_s: float = 20.0):
-    """Seconds per update() of the CPU port in algorithmic-minimum mode (one streaming E-step, one weighted
-    Gram, SVD pseudo-inverse, two projections), measured on bounded samples and scaled by the exact work ratio:
-    E-step on a column subsample (cost is linear in N), Gram on a row subsample (linear in 3M), the r x r algebra
-    at full size."""
+def _use_all_cores():
+    """All host cores for the C oracle (OpenMP) and for numpy / scipy BLAS, whatever the environment said at start-up."""
     from oracle import oracle
     oracle.build()
+    oracle.set_num_threads(_CPU_CORES)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=_CPU_CORES)
+    except Exception:
+        pass
+    return oracle.num_threads()
+
+
+def cpu_oracle_chain(name: str, warmup: int, steps: int, initial_sigma2=None, budget_s: float = 1e9):
+    """Real update() iterations of the CPU port on the workload `name`: -> (seconds per timed iteration (list), cores,
+    description, final state).  Model constants (Q^T Q and its factor: once per model, like the model upload on the GPU
+    side) and the initial state are built outside the timed iterations.  Stops early only if budget_s is exceeded."""
+    from oracle import fast, oracle
+    cores = _use_all_cores()
     M, N, r, _ = WORKLOADS[name]
     ref, mean, basis, var, target = make_inputs(name)
-    cores = oracle.num_threads()
-    sample = {}
-    # E-step: choose N_s so that the sample takes a few seconds (~ 2 * M * N_s exp at ~1e8/s/core)
-    n_s = int(min(N, max(256, 3.0 * 1e8 * cores / (2.0 * M))))
-    fit = ref + mean.reshape(-1, 3)
-    t0 = time.perf_counter()
-    P1, Pt1, PX = oracle.cpd_estep(fit, target[:n_s], 25.0, W_OUTLIER, fast=True)
-    t_e = (time.perf_counter() - t0) * (N / n_s)
-    sample["estep"] = f"{M}x{n_s} of {M}x{N} pairs"
-    # Gram: rows subsample
-    m_s = int(min(M, max(64, 2.0e10 * 1.0 / (2.0 * 3 * r * r))))
-    rows = 3 * m_s
-    Q = basis[:rows] * np.sqrt(var)[None, :]
-    wts = np.repeat(np.random.default_rng(0).uniform(0.5, 2.0, m_s), 3)
-    t0 = time.perf_counter()
-    Mx = (Q * wts[:, None]).T @ Q + np.eye(r)
-    t_g = (time.perf_counter() - t0) * (M / m_s)
-    sample["gram"] = f"{rows}x{r} of {3 * M}x{r} rows"
-    # r x r algebra at full size: pinv (SVD) as Breeze does, plus the matrix-vector products
-    t0 = time.perf_counter()
-    Minv = oracle.breeze_pinv(Mx)
-    c = Minv @ np.ones(r)
-    t_s = time.perf_counter() - t0
-    # HBM-like passes: 3 basis passes (rhs, instances, projection) -- measured on the row subsample
-    t0 = time.perf_counter()
-    v = Q @ c
-    q = Q.T @ v
-    v2 = Q @ q
-    t_p = (time.perf_counter() - t0) * (M / m_s)
-    total = t_e + t_g + t_s + t_p
-    return total, cores, ("update() of the CPU port (C oracle + numpy/OpenBLAS), algorithmic-minimum mode; "
-                          f"E-step sampled on {sample['estep']}, Gram and basis passes on {sample['gram']}, each scaled by "
-                          f"the exact work ratio; r x r pseudo-inverse at full size; parts: estep {t_e:.2f}s gram {t_g:.2f}s "
-                          f"pinv {t_s:.2f}s passes {t_p:.2f}s")
+    om = oracle.Gpmm(ref, mean, basis, var, None)
+    fm = fast.FastCpdModel(om)
+    algo = oracle.CpdAlgorithm(oracle.CpdConfig(w=W_OUTLIER, initial_sigma=initial_sigma2), literal=False)
+    st = algo.initialize(oracle.initial_state(om, target, None, global_transformation=oracle.RIGID_TRANSFORMS))
+    t_start = time.perf_counter()
+    secs = []
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        st = fast.propose(fm, algo, st)
+        dt = time.perf_counter() - t0
+        if st.status == oracle.STATUS_MODEL_FLEXIBILITY_ERROR:
+            raise SystemExit("bench.py: the CPU port reported ModelFlexibilityError")
+        if k >= warmup:
+            secs.append(dt)
+        if time.perf_counter() - t_start > budget_s and len(secs) >= 1:
+            break
+    note = (f"{len(secs)} real update() + fit refresh of the CPU port (oracle/fast.py: C/OpenMP streaming E-step, BLAS dsyrk Gram, "
+            f"Cholesky, 5 basis passes) on the full workload M={M} N={N} rank={r}, {cores} threads, wall clock per iteration; "
+            "no sampling, no extrapolation")
+    return secs, cores, note, st
 
 
 def run_reference(args):
@@ -186,32 +199,61 @@ def run_reference(args):
         return 0
     name = args.workload
     M, N, r, desc = WORKLOADS[name]
-    steps = max(1, args.steps)
-    vals = []
-    note = ""
-    cores = 1
-    for k in range(args.warmup + steps):
-        # each step is one bounded-sample measurement; keep the whole run within a few minutes
-        if k >= 1 and time.time() - run_reference.t0 > 150:
-            break
-        sec, cores, note = cpu_iteration_seconds(name)
-        if k >= min(args.warmup, 1):
-            vals.append(1.0 / sec)
-    v = statistics.median(vals)
+    secs, cores, note, st = cpu_oracle_chain(name, args.warmup, args.steps, budget_s=args.ref_budget_s)
+    sec = statistics.mean(secs)
+    v = 1.0 / sec
     line = {
         "impl": "reference", "metric": "GiNGR update() iterations/s", "value": v, "unit": "iterations/s",
-        "n_gpus": args.gpus, "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 / v,
+        "n_gpus": args.gpus, "steps": len(secs), "warmup": args.warmup, "ms_per_step": 1e3 * sec,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "M": M, "N": N, "rank": r, "w": W_OUTLIER, "note": "CPU port of the reference path (no JVM in this image)"},
+        "config": {"workload": desc, "M": M, "N": N, "rank": r, "w": W_OUTLIER, "algorithm": "CPD",
+                   "note": "CPU port of the reference path (no JVM in this image), every iteration a real update() on the full workload"},
         "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": note},
         "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "final_sigma2": st.sigma2,
+        "seconds_per_iteration": {"min": min(secs), "max": max(secs)},
     }
     print(json.dumps(line))
     return 0
 
 
-run_reference.t0 = time.time()
+# ---------------------------------------------------------------------------------------------------
+# parity of the timed configuration against the cached oracle chain
+# ---------------------------------------------------------------------------------------------------
+GOLDEN_C4 = os.path.join(ROOT, "tests", "golden", "c4_chain_oracle.npz")
+PARITY_TOL = 1e-6
+
+
+def chain_parity(reg, api, ref, iterations=None):
+    """Re-play the first iterations of the seeded C4 chain from the initial state and compare every component with the
+    cached oracle values (tests/golden/make_c4_golden.py): coefficients relative to max |alpha|, fit relative to the mesh
+    diagonal, sigma2 relative.  Returns the parity record (all ranks hold the full state after an iteration)."""
+    g = np.load(GOLDEN_C4)
+    n_it = g["alpha"].shape[0] if iterations is None else min(iterations, g["alpha"].shape[0])
+    diag = float(np.linalg.norm(ref.max(0) - ref.min(0)))
+    st = reg.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
+    rec = {"against": "tests/golden/c4_chain_oracle.npz (oracle/fast.py, generated by tests/golden/make_c4_golden.py)",
+           "iterations": int(n_it), "tolerance": PARITY_TOL,
+           "sigma2_initial_rel_err": abs(st.sigma2 - float(g["sigma2"][0])) / float(g["sigma2"][0])}
+    worst = rec["sigma2_initial_rel_err"]
+    e_a = e_f = e_s = e_t = 0.0
+    for k in range(n_it):
+        st = reg.propose(st)
+        if st.status == api.STATUS_MODEL_FLEXIBILITY_ERROR:
+            raise SystemExit("bench.py: ModelFlexibilityError while re-playing the golden chain")
+        a = g["alpha"][k]
+        e_a = max(e_a, float(np.max(np.abs(st.modelParameters.shape - a)) / max(np.max(np.abs(a)), 1e-300)))
+        e_f = max(e_f, float(np.max(np.abs(st.fit[g["fit_idx"]] - g["fit_sub"][k])) / diag),
+                  float(np.max(np.abs(st.fit.sum(axis=0) - g["fit_sum"][k])) / (diag * st.fit.shape[0])))
+        e_s = max(e_s, abs(st.sigma2 - float(g["sigma2"][k + 1])) / float(g["sigma2"][k + 1]))
+        e_t = max(e_t, float(np.max(np.abs(st.modelParameters.translation - g["translation"][k])) / diag),
+                  float(np.max(np.abs(np.array(st.modelParameters.euler) - g["euler"][k]))))
+    rec.update({"alpha_rel_err": e_a, "fit_rel_err": e_f, "sigma2_rel_err": e_s, "pose_err": e_t})
+    worst = max(worst, e_a, e_f, e_s, e_t)
+    rec["max_rel_err"] = worst
+    rec["ok"] = bool(worst < PARITY_TOL)
+    return rec
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -252,6 +294,11 @@ def run_ours(args):
     # The timed region replays the captured iteration graph (the product path).  The per-kernel times of the
     # roofline come from a second, event-instrumented pass of the same chain right after it (events cannot live
     # inside the replayed graph); its total is reported as phases_ms.iteration next to ms_per_step.
+    parity = None
+    if name == "c4" and os.path.exists(GOLDEN_C4):
+        parity = chain_parity(reg, api, ref)
+        if not parity["ok"]:
+            raise SystemExit(f"bench.py: parity against the cached oracle chain FAILED: {json.dumps(parity)}")
     state0 = reg.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
     reg.updateChain(max(args.warmup, 3))
     barrier()
@@ -298,6 +345,32 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_chain, ms_e2e = float(t[0]), float(t[1])
 
+    # ---- secondary entries: the other named configurations (short; C5 on every rank, the rest at N = 1) -------------
+    secondary = None
+    if name == "c4" and not args.no_secondary:
+        import bench_secondary as bs
+        reg.close()
+        reg = None
+        model.close()
+        secondary = {}
+        barrier()
+        c5 = bs.c5_mcmc(ctx, world, rank)
+        agg = torch.tensor([float(c5["chains"] * c5["steps"]), float(c5["accepted"]), float(c5["launches"])], dtype=torch.float64, device="cuda")
+        tmax = torch.tensor([c5["seconds"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(agg)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        secondary["c5_mcmc"] = {
+            "workload": "1024 independent Metropolis-Hastings chains of the C1 size (ICP proposal + random pose / shape proposals, "
+                        "evaluators, accept / reject on the device), divided among the GPUs (replicas, no collective)",
+            "gpus": world, "chains": 1024, "mh_steps_per_chain": c5["steps"], "chain_steps_per_s": float(agg[0]) / float(tmax[0]),
+            "chain_steps_per_s_per_gpu": float(agg[0]) / float(tmax[0]) / world, "acceptance_rate": float(agg[1]) / (1024 * (c5["steps"] + 3)),
+            "launches_per_chain_step": float(agg[2]) / float(agg[0]), "finite": c5["finite"]}
+        if world == 1:
+            secondary["c1_icp"] = bs.c1_icp(ctx)
+            secondary["c3_multiresolution"] = bs.c3_pipeline(ctx)
+            secondary["icp_200k"] = bs.icp_200k(ctx, ROOT)
+
     if rank == 0:
         peaks = load_peaks()
         fp = peaks.get("FP64_PEAKS.json", {})
@@ -337,8 +410,8 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                sec, cores, note = cpu_iteration_seconds(name)
-                cpu = {"value": 1.0 / sec, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": note}
+                secs, cores, note, _ = cpu_oracle_chain(name, 0, 1, initial_sigma2=state0.sigma2)
+                cpu = {"value": 1.0 / secs[0], "unit": "iterations/s", "cores": cores, "kind": "port", "sample": note}
             except Exception as ex:  # the oracle is test infrastructure: its absence must not fail the bench
                 cpu = {"value": None, "unit": "iterations/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
         h2d = 112 + 8 * r
@@ -361,9 +434,12 @@ def run_ours(args):
                           "iteration": t_it},
             "cpu_baseline": cpu,
             "final_sigma2": final.sigma2,
+            "parity": parity,
+            "secondary": secondary,
         }
         print(json.dumps(line))
-    reg.close()
+    if reg is not None:
+        reg.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -377,6 +453,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C1 / C3 / C5 / ICP-200k entries")
+    ap.add_argument("--ref-budget-s", type=float, default=900.0,
+                    help="--impl reference: stop after this many seconds of iterations (the completed count is reported)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
