@@ -104,6 +104,7 @@ SIGNATURES = {
     "gingr_icp_closest": (c_int32, [c_void_p, c_void_p, c_int32, dp, ip, c_int32, c_int32, ip, dp, bp, dp]),
     "gingr_icp_closest_reversal": (c_int32, [c_void_p, c_void_p, c_int32, dp, ip, c_int32, c_int32, ip, bp, dp]),
     "gingr_posterior_mean": (c_int32, [c_void_p, c_void_p, dp, dp, c_int32, ip, dp, c_int32, dp, dp, dp]),
+    "gingr_posterior_covariance": (c_int32, [c_void_p, c_void_p, dp, dp, c_int32, ip, dp, c_int32, dp, dp]),
     "gingr_coefficients": (c_int32, [c_void_p, c_void_p, dp, dp, dp, dp]),
     "gingr_spd_solve": (c_int32, [c_void_p, c_int32, dp, c_int32, dp, dp, dp, dp, c_int32, dp]),
     "gingr_model_instance": (c_int32, [c_void_p, c_void_p, POINTER(GingrState), dp, dp]),

@@ -363,6 +363,27 @@ def posterior_mean(ctx: Context, model: Model, R, t, pids, points, noise):
     return c, mesh
 
 
+def posterior_covariance(ctx: Context, model: Model, R, t, pids, points, noise) -> np.ndarray:
+    """Covariance of model.transform(R, t).posterior(obs) at the mesh points -> [M, 3, 3]
+    (GingrAlgorithm.scala:300; the quantity helper/PosteriorHelper.scala:26-80 colour-maps).  Arguments as posterior_mean."""
+    R = nat.f64(R).reshape(3, 3)
+    t = nat.f64(t).reshape(3)
+    pids = nat.i32(pids)
+    pts = nat.f64(points).reshape(-1, 3)
+    noise = nat.f64(noise)
+    n = pids.shape[0]
+    if pids.ndim != 1 or pts.shape[0] != n:
+        raise ValueError(f"{n} point ids but {pts.shape[0]} points")
+    if noise.shape not in ((n,), (n, 3, 3)):
+        raise ValueError(f"noise must have shape ({n},) or ({n}, 3, 3), got {noise.shape}")
+    cov = np.empty((model.M, 3, 3))
+    code = ctx.check(ctx._lib.gingr_posterior_covariance(ctx.handle, model.handle, nat.as_dp(R), nat.as_dp(t), n, nat.as_ip(pids),
+                                                         nat.as_dp(pts), 0 if noise.ndim == 1 else 1, nat.as_dp(noise), nat.as_dp(cov)))
+    if code == nat.GINGR_MODEL_FLEXIBILITY:
+        raise FloatingPointError("posterior failed (ModelFlexibilityError)")
+    return cov
+
+
 def spd_solve(ctx: Context, A, B=None, reps: int = 1):
     """The on-device r x r Cholesky solve of the regression (scalismo: Minv = pinv(Mx); c = Minv * rhs).
     A: [n, n] symmetric positive definite; B: [nrhs, n] right-hand sides as rows (or None).

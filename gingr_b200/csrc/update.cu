@@ -903,12 +903,50 @@ struct PosteriorScratch {
   }
 };
 
-extern "C" {
+namespace gingr {
+// rows r + 1 + k of the system <- row k of Q = Phi diag(sqrt(lambda)): riding through the factorisation as extra rows they
+// come out as Q_k L^-T, whose 3 x 3 Gram blocks are the posterior covariances at the mesh points
+__global__ void posterior_cov_rows_kernel(int rows, int r, int rp, const double* __restrict__ phi,
+                                          const double* __restrict__ sqrt_lambda, double* __restrict__ out) {
+  const int k = blockIdx.y;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < rp; c += gridDim.x * blockDim.x)
+    out[(size_t)k * rp + c] = c < r ? phi[(size_t)k * rp + c] * sqrt_lambda[c] : 0.0;
+}
+// cov_i = R (X_i X_i^T) R^T with X_i the three solved rows of vertex i; one warp per vertex
+__global__ void __launch_bounds__(256) posterior_cov_kernel(int M, int r, int rp, const double* __restrict__ X,
+                                                            const double* __restrict__ ds, double* __restrict__ cov) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= M) return;
+  const double* x0 = X + (size_t)(3 * i) * rp;
+  const double* x1 = x0 + rp;
+  const double* x2 = x1 + rp;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int c = lane; c < r; c += 32) {
+    const double a = x0[c], b = x1[c], d = x2[c];
+    s[0] = fma(a, a, s[0]); s[1] = fma(a, b, s[1]); s[2] = fma(a, d, s[2]);
+    s[3] = fma(b, b, s[3]); s[4] = fma(b, d, s[4]); s[5] = fma(d, d, s[5]);
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+  if (lane == 0) {
+    const double C[9] = {s[0], s[1], s[2], s[1], s[3], s[4], s[2], s[4], s[5]};
+    const double* R = ds + DS_R;
+    double T[9];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) T[3 * a + b] = R[3 * a] * C[b] + R[3 * a + 1] * C[3 + b] + R[3 * a + 2] * C[6 + b];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+        cov[(size_t)9 * i + 3 * a + b] = T[3 * a] * R[3 * b] + T[3 * a + 1] * R[3 * b + 1] + T[3 * a + 2] * R[3 * b + 2];
+  }
+}
+}  // namespace gingr
 
-// ---- K3 kernel-level entry points -----------------------------------------------------------------
-int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t, int32_t n,
-                             const int32_t* pid, const double* points, int32_t noise_kind, const double* noise,
-                             double* coeffs, double* mean_pts) {
+// the regression of model.transform(R, t).posterior(obs): coefficients, mean mesh and (optionally) the covariance blocks
+static int32_t posterior_core(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t, int32_t n,
+                              const int32_t* pid, const double* points, int32_t noise_kind, const double* noise,
+                              double* coeffs, double* mean_pts, double* cov_pts) {
   if (!ctx || !model || !R || !t || n < 0 || (n > 0 && (!pid || !points || !noise)) || noise_kind < 0 || noise_kind > 1)
     return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_posterior_mean: bad argument");
   if (ctx->nranks != 1) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "gingr_posterior_mean: single-GPU entry point");
@@ -965,7 +1003,8 @@ int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model, const dou
   DevBuf<int32_t> d_lpid;
   DevBuf<double> d_lpts, d_lcinv, d_lA, d_lrows;
 #define PM_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { gingr_set_error(ctx, cudaGetErrorString(_e)); s.release(); d_lpid.release(); d_lpts.release(); d_lcinv.release(); d_lA.release(); d_lrows.release(); return GINGR_ERR_CUDA; } } while (0)
-  PM_TRY(s.Mx.alloc((size_t)(r + 8) * rp));
+  const int xrows = cov_pts ? 3 * M : 0;       // rows of Q carried through the factorisation for the covariance
+  PM_TRY(s.Mx.alloc((size_t)(r + 8 + xrows) * rp));
   PM_TRY(s.wrow.alloc((size_t)3 * M));
   PM_TRY(s.u.alloc((size_t)3 * M));
   PM_TRY(s.vec.alloc((size_t)8 * rp));
@@ -975,7 +1014,7 @@ int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model, const dou
   PM_TRY(s.ds.alloc(DS_COUNT));
   PM_TRY(s.is.alloc(IS_COUNT));
   PM_TRY(s.flags.alloc(256));
-  if ((rc = s.cholws.alloc(ctx, r, r + 1)) < 0) return fail(rc);
+  if ((rc = s.cholws.alloc(ctx, r, r + 1 + xrows)) < 0) return fail(rc);
   PM_TRY(cudaMemsetAsync(s.Mx.p, 0, sizeof(double) * (size_t)(r + 8) * rp, st));
   PM_TRY(cudaMemsetAsync(s.is.p, 0, sizeof(int) * IS_COUNT, st));
   PM_TRY(cudaMemcpyAsync(s.wrow.p, wrow.data(), sizeof(double) * 3 * M, cudaMemcpyHostToDevice, st));
@@ -1002,7 +1041,12 @@ int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model, const dou
   }
   if ((rc = gram_partials_enqueue(ctx, s.gram, m->phi.p, s.wrow.p)) < 0) return fail(rc);
   if ((rc = gram_finish_enqueue(ctx, s.gram, s.gram.d_partial.p, m->sqrt_lambda.p, 1.0, L, d_lrows.p, d_lA.p, rp, s.Mx.p)) < 0) return fail(rc);
-  if ((rc = cholesky_enqueue(ctx, r, r + 1, s.Mx.p, rp, s.is.p + IS_INFO, &s.cholws)) < 0) return fail(rc);
+  if (xrows > 0) {
+    gingr::posterior_cov_rows_kernel<<<dim3(ceil_div(rp, 256), xrows), 256, 0, st>>>(xrows, r, rp, m->phi.p, m->sqrt_lambda.p,
+                                                                                 s.Mx.p + (size_t)(r + 1) * rp);
+    GINGR_LAUNCHED(ctx);
+  }
+  if ((rc = cholesky_enqueue(ctx, r, r + 1 + xrows, s.Mx.p, rp, s.is.p + IS_INFO, &s.cholws)) < 0) return fail(rc);
   double* c = s.vec.p;
   if ((rc = chol_backsolve_enqueue(ctx, r, s.Mx.p, rp, rhs, c, s.flags.p, &s.cholws)) < 0) return fail(rc);
   check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, c, s.is.p + IS_FAIL_POST);
@@ -1014,14 +1058,38 @@ int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model, const dou
     GINGR_LAUNCHED(ctx);
     PM_TRY(cudaMemcpyAsync(mean_pts, s.fit_local.p, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, st));
   }
+  DevBuf<double> d_cov;
+  if (cov_pts) {
+    if (d_cov.alloc((size_t)9 * M) != cudaSuccess) return fail(gingr_fail(ctx, GINGR_ERR_CUDA, "out of device memory"));
+    gingr::posterior_cov_kernel<<<ceil_div(M, 8), 256, 0, st>>>(M, r, rp, s.Mx.p + (size_t)(r + 1) * rp, s.ds.p, d_cov.p);
+    GINGR_LAUNCHED(ctx);
+    cudaMemcpyAsync(cov_pts, d_cov.p, sizeof(double) * 9 * M, cudaMemcpyDeviceToHost, st);
+  }
   int his[IS_COUNT];
   if (coeffs) PM_TRY(cudaMemcpyAsync(coeffs, c, sizeof(double) * r, cudaMemcpyDeviceToHost, st));
   PM_TRY(cudaMemcpyAsync(his, s.is.p, sizeof(int) * IS_COUNT, cudaMemcpyDeviceToHost, st));
   PM_TRY(cudaStreamSynchronize(st));
 #undef PM_TRY
   s.release();
+  d_cov.release();
   d_lpid.release(); d_lpts.release(); d_lcinv.release(); d_lA.release(); d_lrows.release();
   return (his[IS_INFO] || his[IS_FAIL_POST]) ? GINGR_MODEL_FLEXIBILITY : GINGR_OK;
+}
+
+extern "C" {
+
+// ---- K3 kernel-level entry points -----------------------------------------------------------------
+int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t, int32_t n,
+                             const int32_t* pid, const double* points, int32_t noise_kind, const double* noise,
+                             double* coeffs, double* mean_pts) {
+  return posterior_core(ctx, model, R, t, n, pid, points, noise_kind, noise, coeffs, mean_pts, nullptr);
+}
+
+int32_t gingr_posterior_covariance(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t, int32_t n,
+                                   const int32_t* pid, const double* points, int32_t noise_kind, const double* noise,
+                                   double* cov_pts) {
+  if (!cov_pts) return gingr_fail(ctx, GINGR_ERR_ARG, "gingr_posterior_covariance: bad argument");
+  return posterior_core(ctx, model, R, t, n, pid, points, noise_kind, noise, nullptr, nullptr, cov_pts);
 }
 
 int32_t gingr_coefficients(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t,

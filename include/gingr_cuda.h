@@ -207,6 +207,14 @@ GINGR_API int32_t gingr_posterior_mean(gingr_ctx* ctx, const gingr_model* model,
                                        int32_t n, const int32_t* pid, const double* points /*[3n]*/,
                                        int32_t noise_kind, const double* noise, double* coeffs /*[r]*/,
                                        double* mean_pts /*[3M]*/);
+/* The COVARIANCE of the same posterior at the mesh points: scalismo's `posterior` (GingrAlgorithm.scala:300) returns a
+ * model whose covariance helper/PosteriorHelper.scala:26-80 turns into per-vertex variance maps; here
+ *   cov_i = R Phi_i D Mx^-1 D Phi_i^T R^T   (3 x 3, row-major, cov[9 i ..]),  Mx = Q^T L^-1 Q + I  as above,
+ * evaluated exactly: the rows of Q = Phi D ride through the Cholesky factorisation as extra rows (Q_i L^-T), their
+ * 3 x 3 Gram blocks are the covariances.  Same observation arguments as gingr_posterior_mean. */
+GINGR_API int32_t gingr_posterior_covariance(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t,
+                                             int32_t n, const int32_t* pid, const double* points /*[3n]*/,
+                                             int32_t noise_kind, const double* noise, double* cov_pts /*[9M]*/);
 /* Replaces model.transform(rigid).coefficients(mesh) (GingrAlgorithm.scala:215, :236): regression on
  * all M points with noise 1e-5 * I3. */
 GINGR_API int32_t gingr_coefficients(gingr_ctx* ctx, const gingr_model* model, const double* R, const double* t,

@@ -109,6 +109,9 @@ object GingrCudaNative {
   // GingrAlgorithm.scala:281-302 (model.transform(rigid).posterior(observations), mean only), :215 / :236 (coefficients), :93-95 (instance)
   val posteriorMean  = fn("gingr_posterior_mean", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT,
                           ADDRESS, ADDRESS, ADDRESS)
+  // per-vertex 3 x 3 covariance of the same posterior (what PosteriorHelper colour-maps)
+  val posteriorCov   = fn("gingr_posterior_covariance", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT,
+                          ADDRESS, ADDRESS)
   val coefficients   = fn("gingr_coefficients", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
   // the r x r solve of the regression alone (pinv(Mx) * rhs as a Cholesky solve): A, nrhs rows of B -> L, L^-1 B^T rows, A^-1 b_0
   val spdSolve       = fn("gingr_spd_solve", JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT,

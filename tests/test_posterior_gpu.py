@@ -173,3 +173,36 @@ def test_gram_more_tiles_than_sms(ctx, oracle):
     c_ref, _ = m.posterior_coefficients(pids, obs, np.eye(3)[None] * noise[:, None, None])
     diag = np.linalg.norm(ref.max(0) - ref.min(0))
     assert np.max(np.abs(mesh - m.instance(c_ref))) < 1e-9 * diag
+
+
+@pytest.mark.parametrize("M,r,full", [(60, 12, False), (300, 130, False), (120, 40, True), (700, 200, False)])
+def test_posterior_covariance_at_the_mesh_points(ctx, oracle, M, r, full):
+    """gingr_posterior_covariance: cov_i = R Phi_i D Mx^-1 D Phi_i^T R^T against the oracle's dense form
+    Q'_i Minv Q'_i^T with Minv = pinv(Mx) of the literal regression (scalismo posterior; what
+    helper/PosteriorHelper.scala:26-80 visualises).  Tolerance 1e-9 of the largest prior variance."""
+    from gingr_b200 import api
+    m = _model(oracle, M, r, seed=5)
+    dm = _upload(ctx, m)
+    rng = np.random.default_rng(8)
+    R, t = oracle.euler_to_matrix(0.25, -0.15, 0.1), np.array([2.0, -1.0, 0.5])
+    posed = m.transform(R, t)
+    pids = rng.permutation(M)[: max(3, M // 2)].astype(np.int32)
+    obs = posed.instance(rng.normal(size=r))[pids] + rng.normal(scale=0.3, size=(len(pids), 3))
+    if full:
+        A = rng.normal(size=(len(pids), 3, 3))
+        noise = A @ np.transpose(A, (0, 2, 1)) + 0.1 * np.eye(3)
+        cov_obs = noise
+    else:
+        noise = rng.uniform(0.05, 5.0, size=len(pids))
+        cov_obs = np.eye(3)[None] * noise[:, None, None]
+    got = api.posterior_covariance(ctx, dm, R, t, pids, obs, noise)
+    _, Minv = posed.posterior_coefficients(pids, obs, cov_obs)
+    Q = (posed.basis * np.sqrt(posed.variance)[None, :]).reshape(M, 3, r)
+    ref = np.einsum("mak,kl,mbl->mab", Q, Minv, Q)
+    prior = np.einsum("mak,mak->m", Q, Q).max()
+    assert got.shape == (M, 3, 3)
+    assert np.max(np.abs(got - ref)) < 1e-9 * prior
+    assert np.max(np.abs(got - np.transpose(got, (0, 2, 1)))) < 1e-12 * prior     # symmetric
+    # observed vertices are more certain than the prior, unobserved ones never less certain than observed neighbours' floor
+    tr_post, tr_prior = np.trace(got, axis1=1, axis2=2), np.einsum("mak,mak->m", Q, Q)
+    assert np.all(tr_post <= tr_prior * (1 + 1e-12)) and np.all(tr_post > 0)
