@@ -354,7 +354,11 @@ def run_ours(args):
         model.close()
         secondary = {}
         barrier()
-        c5 = bs.c5_mcmc(ctx, world, rank)
+        # independent chains need a context that is not part of a communicator (gingr_mcmc_configure: replicas only)
+        ctx5 = api.Context(local_rank) if world > 1 else ctx
+        c5 = bs.c5_mcmc(ctx5, world, rank)
+        if ctx5 is not ctx:
+            ctx5.close()
         agg = torch.tensor([float(c5["chains"] * c5["steps"]), float(c5["accepted"]), float(c5["launches"])], dtype=torch.float64, device="cuda")
         tmax = torch.tensor([c5["seconds"]], dtype=torch.float64, device="cuda")
         if world > 1:
