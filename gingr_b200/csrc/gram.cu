@@ -178,6 +178,13 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_streamk_kernel(int rows,
 //             cp.async.bulk (global -> shared, 1 KB, completes on the mbarrier) per operand row
 //   empty[s]  count 8 : one arrive per consumer warp after its last fragment load of the stage
 // ---------------------------------------------------------------------------------------------
+// Measured and NOT kept (round 2): skipping the fragments a tile does not need -- above the diagonal of the 16 diagonal
+// tiles, past rank r in the last tile row (2000 -> 2048 padding), together 10 % of the DMMA slots -- with cyclic column
+// fragments per warp (so that the four sub-partitions stay balanced on a diagonal tile) and a cost-weighted schedule.
+// The masked loop itself is free (7.74 ms with every mask full, 7.72 ms for the cyclic mapping alone, against 7.75 ms),
+// but as soon as fragments are really skipped the kernel takes 8.99 ms with the equal-chunk schedule and 14.1 ms with the
+// weighted one: the CTAs of the cheaper tiles run ahead of the lockstep in which all CTAs walk the chunk index together,
+// and the 512 KB strip of Phi that every tile shares per chunk no longer meets its readers in L2.
 constexpr int GRAM_WS_THREADS = 256 + 32;
 constexpr size_t GRAM_WS_SMEM = GRAM_SMEM + 2 * STAGES * sizeof(unsigned long long);
 
