@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(QT) line_mesh_kernel(int M, const double* __re
                                                        const double* __restrict__ other /*AoS*/,
                                                        const double* __restrict__ mesh /*AoS vertices*/, int T,
                                                        const int32_t* __restrict__ tri,
-                                                       double* __restrict__ part_min, double* __restrict__ part_pt) {
+                                                       double* __restrict__ part_min, double* __restrict__ part_pt,
+                                                       int q0 = 0 /*vertex id of query 0 (SELF: a query range of the mesh)*/) {
   __shared__ double st[TT][9];
   __shared__ int32_t sv[TT][3];
   const int i = blockIdx.x * QT + threadIdx.x;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(QT) line_mesh_kernel(int M, const double* __re
     }
     __syncthreads();
     for (int t = 0; t < cnt; ++t) {
-      if (SELF && (sv[t][0] == ii || sv[t][1] == ii || sv[t][2] == ii)) continue;
+      if (SELF && (sv[t][0] == q0 + ii || sv[t][1] == q0 + ii || sv[t][2] == q0 + ii)) continue;
       double d, ix, iy, iz;
       if (!line_triangle_hit(ox, oy, oz, dx, dy, dz, &st[t][0], &st[t][3], &st[t][6], d, ix, iy, iz)) continue;
       if (d < best) {
@@ -317,13 +318,15 @@ __global__ void __launch_bounds__(256) mean_sqrt_kernel(int M, const double* __r
   if (threadIdx.x == 0) out[blockIdx.x] = final_stage ? red[0] / M : red[0];
 }
 
-static void mean_sqrt_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, int squared) {
+static void mean_sqrt_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, int squared, const double* d_d2 = nullptr) {
   cudaStream_t st = ctx->stream;
+  if (!d_d2) d_d2 = ws.d2.p;
+  if (M <= 0) return;
   if (M <= 16384) {
-    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.d2.p, ws.mean_dist.p, squared, 1);
+    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, d_d2, ws.mean_dist.p, squared, 1);
     GINGR_LAUNCHED(ctx);
   } else {
-    mean_sqrt_kernel<<<MEAN_BLOCKS, 256, 0, st>>>(M, ws.d2.p, ws.mean_part.p, squared, 0);
+    mean_sqrt_kernel<<<MEAN_BLOCKS, 256, 0, st>>>(M, d_d2, ws.mean_part.p, squared, 0);
     GINGR_LAUNCHED(ctx);
     mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.mean_part.p, ws.mean_dist.p, 0, 2);
     GINGR_LAUNCHED(ctx);
@@ -426,6 +429,9 @@ int32_t ClosestWorkspace::ensure(gingr_ctx* ctx, int nq, int n_search, int T_sea
   GINGR_CUDA_TRY(ctx, cp.alloc((size_t)3 * M));
   GINGR_CUDA_TRY(ctx, w.alloc((size_t)M));
   GINGR_CUDA_TRY(ctx, hit.alloc((size_t)M));
+  // a rank that searches only a query range never writes the other entries: keep them defined (weight 0, point 0)
+  GINGR_CUDA_TRY(ctx, cudaMemsetAsync(w.p, 0, (size_t)M, ctx->stream));
+  GINGR_CUDA_TRY(ctx, cudaMemsetAsync(cp.p, 0, sizeof(double) * 3 * (size_t)M, ctx->stream));
   GINGR_CUDA_TRY(ctx, mean_dist.alloc(1));
   GINGR_CUDA_TRY(ctx, mean_part.alloc(MEAN_BLOCKS));
   if (grid_wanted(std::max(n_search, std::max(T_search, T_query_mesh)))) {
@@ -469,24 +475,36 @@ int32_t nn_vertex_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, const dou
 // the mesh flavours); tgt.soa, (tgt.aos, tgt.tri, tgt.normals, tgt.boundary for the mesh flavours).
 // Results for the tpl.n template vertices in ws.idx (nearest target vertex) / ws.cp / ws.w / ws.mean_dist.
 int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const MeshView& tpl, const MeshView& tgt,
-                                   int method) {
+                                   int method, int q0, int qn) {
   cudaStream_t st = ctx->stream;
-  const int M = tpl.n, N = tgt.n;
+  // Query range [q0, q0 + qn) of the template vertices (K2 splits the QUERIES across the GPUs; a rank
+  // searches the vertices of its own basis shard, whose observation rows are the only ones it needs -- no gather).
+  // All per-query outputs keep their global index; the template MESH (self-intersection test) stays whole.
+  if (qn < 0) { q0 = 0; qn = tpl.n; }
+  const int M = qn, N = tgt.n;
+  if (M == 0) return GINGR_OK;
+  const double* q_aos = tpl.aos + (size_t)3 * q0;
+  const double* q_nrm = tpl.normals ? tpl.normals + (size_t)3 * q0 : nullptr;
+  double* o_d2 = ws.d2.p + q0;
+  int32_t* o_idx = ws.idx.p + q0;
+  double* o_cp = ws.cp.p + (size_t)3 * q0;
+  uint8_t* o_w = ws.w.p + q0;
+  uint8_t* o_hit = ws.hit.p + q0;
   // any grid search ahead: sort the queries spatially once (a point grid over the template vertices)
   const SpatialGrid* order = nullptr;
   const bool any_grid = (tgt.pgrid && tgt.pgrid->built) || (tgt.tgrid && tgt.tgrid->built) || (tpl.tgrid && tpl.tgrid->built);
   if (any_grid && ws.qorder && ws.qorder->cap_items >= M) {
     VertexArray qa;
-    qa.p = tpl.aos;
+    qa.p = q_aos;
     GINGR_TRY(grid_build_points_enqueue(ctx, *ws.qorder, M, qa));
     order = ws.qorder;
   }
   if (method == GINGR_POINTCLOUD_CLOSEST_POINT) {
-    GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, tpl.aos, N, tgt.soa, ws.d2.p, ws.idx.p, tgt.pgrid, order));
-    gather_points_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, ws.idx.p, N, tgt.soa, ws.cp.p);
+    GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, q_aos, N, tgt.soa, o_d2, o_idx, tgt.pgrid, order));
+    gather_points_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, o_idx, N, tgt.soa, o_cp);
     GINGR_LAUNCHED(ctx);
-    GINGR_CUDA_TRY(ctx, cudaMemsetAsync(ws.w.p, 1, (size_t)M, st));
-    mean_sqrt_enqueue(ctx, ws, M, 1);
+    GINGR_CUDA_TRY(ctx, cudaMemsetAsync(o_w, 1, (size_t)M, st));
+    mean_sqrt_enqueue(ctx, ws, M, 1, o_d2);
     GINGR_CUDA_TRY(ctx, cudaGetLastError());
     return GINGR_OK;
   }
@@ -496,51 +514,48 @@ int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const M
   int s_line = std::min(ws.s_line, std::max(1, ceil_div(tpl.T, TT / 4)));
   const bool tgt_grid = tgt.tgrid && tgt.tgrid->built, tpl_grid = tpl.tgrid && tpl.tgrid->built;
   if (method == GINGR_TRIANGULAR_CLOSEST_POINT && tgt_grid) {
-    GINGR_TRY(grid_surface_enqueue(ctx, *tgt.tgrid, M, tpl.aos, tgt.aos, tgt.tri, ws.d2.p, nullptr, ws.cp.p, order));
-    mean_sqrt_enqueue(ctx, ws, M, 1);
+    GINGR_TRY(grid_surface_enqueue(ctx, *tgt.tgrid, M, q_aos, tgt.aos, tgt.tri, o_d2, nullptr, o_cp, order));
+    mean_sqrt_enqueue(ctx, ws, M, 1, o_d2);
   } else if (method == GINGR_ALONG_NORMAL_CLOSEST_POINT && tgt_grid) {
-    GINGR_TRY(grid_line_enqueue(ctx, *tgt.tgrid, M, tpl.aos, tpl.normals, tgt.aos, tgt.tri, 0, ws.part_d2.p, ws.part_cp.p,
+    GINGR_TRY(grid_line_enqueue(ctx, *tgt.tgrid, M, q_aos, q_nrm, tgt.aos, tgt.tri, 0, ws.part_d2.p, ws.part_cp.p,
                                 order));
-    line_hit_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, 1, tpl.aos, ws.part_d2.p, ws.part_cp.p, ws.d2.p, ws.cp.p,
-                                                             ws.hit.p);
+    line_hit_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, 1, q_aos, ws.part_d2.p, ws.part_cp.p, o_d2, o_cp, o_hit);
     GINGR_LAUNCHED(ctx);
-    mean_sqrt_enqueue(ctx, ws, M, 0);  // distance += (p - closestPoint).norm (:128)
+    mean_sqrt_enqueue(ctx, ws, M, 0, o_d2);  // distance += (p - closestPoint).norm (:128)
   } else if (method == GINGR_TRIANGULAR_CLOSEST_POINT) {
-    surface_kernel<<<dim3(ceil_div(M, QT), s_surf), QT, 0, st>>>(M, tpl.aos, N, tgt.soa, tgt.T, tgt.tri, ws.part_d2.p,
+    surface_kernel<<<dim3(ceil_div(M, QT), s_surf), QT, 0, st>>>(M, q_aos, N, tgt.soa, tgt.T, tgt.tri, ws.part_d2.p,
                                                                  ws.part_idx.p, ws.part_cp.p);
     GINGR_LAUNCHED(ctx);
     surface_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, s_surf, ws.part_d2.p, ws.part_idx.p, ws.part_cp.p,
-                                                            ws.d2.p, nullptr, ws.cp.p);
+                                                            o_d2, nullptr, o_cp);
     GINGR_LAUNCHED(ctx);
-    mean_sqrt_enqueue(ctx, ws, M, 1);
+    mean_sqrt_enqueue(ctx, ws, M, 1, o_d2);
   } else if (method == GINGR_ALONG_NORMAL_CLOSEST_POINT) {
     // nearest intersection of the line (p, n_p) with the target mesh (:105-110)
     const int s_hit = s_surf;
     line_mesh_kernel<false, false, true><<<dim3(ceil_div(M, QT), s_hit), QT, 0, st>>>(
-        M, tpl.aos, tpl.normals, tgt.aos, tgt.T, tgt.tri, ws.part_d2.p, ws.part_cp.p);
+        M, q_aos, q_nrm, tgt.aos, tgt.T, tgt.tri, ws.part_d2.p, ws.part_cp.p);
     GINGR_LAUNCHED(ctx);
-    line_hit_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, s_hit, tpl.aos, ws.part_d2.p, ws.part_cp.p, ws.d2.p,
-                                                             ws.cp.p, ws.hit.p);
+    line_hit_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, s_hit, q_aos, ws.part_d2.p, ws.part_cp.p, o_d2, o_cp, o_hit);
     GINGR_LAUNCHED(ctx);
-    mean_sqrt_enqueue(ctx, ws, M, 0);  // distance += (p - closestPoint).norm (:128)
+    mean_sqrt_enqueue(ctx, ws, M, 0, o_d2);  // distance += (p - closestPoint).norm (:128)
   } else {
     return gingr_fail(ctx, GINGR_ERR_ARG, "unknown ICP correspondence method");
   }
   // nearest target vertex of the corresponding point (:83 / :113); d2 of that search is not needed afterwards
-  GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, ws.cp.p, N, tgt.soa, ws.d2.p, ws.idx.p, tgt.pgrid, order));
-  // isClosestPointIntersecting on the template itself (:62-72)
+  GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, o_cp, N, tgt.soa, o_d2, o_idx, tgt.pgrid, order));
+  // isClosestPointIntersecting on the template itself (:62-72): the lines of the query range against the WHOLE template
   if (tpl_grid) {
-    GINGR_TRY(grid_line_enqueue(ctx, *tpl.tgrid, M, tpl.aos, ws.cp.p, tpl.aos, tpl.tri, 1, ws.part_d2.p, nullptr, order));
+    GINGR_TRY(grid_line_enqueue(ctx, *tpl.tgrid, M, q_aos, o_cp, tpl.aos, tpl.tri, 1, ws.part_d2.p, nullptr, order, q0));
     s_line = 1;
   } else {
-    line_mesh_kernel<true, true, false><<<dim3(ceil_div(M, QT), s_line), QT, 0, st>>>(M, tpl.aos, ws.cp.p, tpl.aos, tpl.T,
-                                                                                     tpl.tri, ws.part_d2.p, nullptr);
+    line_mesh_kernel<true, true, false><<<dim3(ceil_div(M, QT), s_line), QT, 0, st>>>(M, q_aos, o_cp, tpl.aos, tpl.T,
+                                                                                     tpl.tri, ws.part_d2.p, nullptr, q0);
     GINGR_LAUNCHED(ctx);
   }
-  icp_weights_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, tpl.aos, ws.cp.p, ws.idx.p, tgt.boundary, tpl.normals,
-                                                       tgt.normals, s_line, ws.part_d2.p,
-                                                       method == GINGR_ALONG_NORMAL_CLOSEST_POINT ? ws.hit.p : nullptr,
-                                                       ws.w.p);
+  icp_weights_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, q_aos, o_cp, o_idx, tgt.boundary, q_nrm, tgt.normals, s_line,
+                                                       ws.part_d2.p,
+                                                       method == GINGR_ALONG_NORMAL_CLOSEST_POINT ? o_hit : nullptr, o_w);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

@@ -51,8 +51,9 @@ int32_t vertex_normals_enqueue(gingr_ctx* ctx, int n, const double* d_verts_aos,
 int32_t nn_vertex_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, const double* d_q, int N,
                           const double* d_pts_soa, double* d_d2, int32_t* d_idx, const SpatialGrid* pgrid = nullptr,
                           const SpatialGrid* order = nullptr);
+// q0 / qn: query range [q0, q0 + qn) of the template vertices (qn < 0: all).  Per-query outputs keep their global index.
 int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const MeshView& tpl, const MeshView& tgt,
-                                   int method);
+                                   int method, int q0 = 0, int qn = -1);
 int32_t surface_distance_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int nq, const double* d_q, const MeshView& mesh);
 // d_scratch (optional): 3 M + N + 1 ints; with it, large problems (M N > 2^24) take the O(N + M) list form (same result)
 int32_t reverse_fold_enqueue(gingr_ctx* ctx, int M, int N, const int32_t* d_tid, const uint8_t* d_w,

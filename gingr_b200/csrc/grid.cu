@@ -897,7 +897,7 @@ __global__ void __launch_bounds__(128) grid_line_kernel(int M, const double4* __
                                                         const int32_t* __restrict__ entries,
                                                         const double* __restrict__ mesh /*AoS*/,
                                                         const int32_t* __restrict__ tri, double* __restrict__ out_min,
-                                                        double* __restrict__ out_pt) {
+                                                        double* __restrict__ out_pt, int q0) {
   const int slot = blockIdx.x * 128 + threadIdx.x;
   if (slot >= M) return;
   const int i = order ? (int)__double_as_longlong(order[slot].w) : slot;   // spatially sorted queries: coherent warps
@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(128) grid_line_kernel(int M, const double4* __
   int bt = 0x7fffffff;
   auto consider = [&](int t) {
     const int v0 = tri[3 * t], v1 = tri[3 * t + 1], v2 = tri[3 * t + 2];
-    if (SELF && (v0 == i || v1 == i || v2 == i)) return;
+    if (SELF && (v0 == q0 + i || v1 == q0 + i || v2 == q0 + i)) return;   // q0: vertex id of query 0 (query range of the mesh)
     const double* a = mesh + 3 * (size_t)v0;
     const double* b = mesh + 3 * (size_t)v1;
     const double* c = mesh + 3 * (size_t)v2;
@@ -978,14 +978,14 @@ __global__ void __launch_bounds__(128) grid_line_kernel(int M, const double4* __
 
 int32_t grid_line_enqueue(gingr_ctx* ctx, const SpatialGrid& g, int M, const double* d_o, const double* d_other,
                           const double* d_mesh_aos, const int32_t* d_tri, int self, double* d_min, double* d_pt,
-                          const SpatialGrid* order) {
+                          const SpatialGrid* order, int q0) {
   if (!g.built || !g.triangles) return gingr_fail(ctx, GINGR_ERR_ARG, "grid_line: triangle grid not built");
   if (self)
     grid_line_kernel<true><<<ceil_div(M, 128), 128, 0, ctx->stream>>>(M, order_ptr(order, M), d_o, d_other, g.n_items, g.params.p, g.cell_start.p,
-                                                                      g.entries.p, d_mesh_aos, d_tri, d_min, d_pt);
+                                                                      g.entries.p, d_mesh_aos, d_tri, d_min, d_pt, q0);
   else
     grid_line_kernel<false><<<ceil_div(M, 128), 128, 0, ctx->stream>>>(M, order_ptr(order, M), d_o, d_other, g.n_items, g.params.p, g.cell_start.p,
-                                                                       g.entries.p, d_mesh_aos, d_tri, d_min, d_pt);
+                                                                       g.entries.p, d_mesh_aos, d_tri, d_min, d_pt, q0);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

@@ -68,6 +68,6 @@ int32_t grid_surface_enqueue(gingr_ctx* ctx, const SpatialGrid& g, int M, const 
 //   self == 0: d = other (the vertex normal), unbounded march in both directions, hit point returned
 int32_t grid_line_enqueue(gingr_ctx* ctx, const SpatialGrid& g, int M, const double* d_o, const double* d_other,
                           const double* d_mesh_aos, const int32_t* d_tri, int self, double* d_min, double* d_pt,
-                          const SpatialGrid* order = nullptr);
+                          const SpatialGrid* order = nullptr, int q0 = 0 /*self: vertex id of query 0*/);
 
 }  // namespace gingr

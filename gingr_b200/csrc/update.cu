@@ -1496,7 +1496,12 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
       fv.pgrid = &g->fit_pgrid;
     }
     if (!cfg.reverse_correspondence_direction) {
-      GINGR_TRY(icp_correspondence_enqueue(ctx, g->closest, fv, tv, cfg.correspondence_method));
+      // several ranks: every rank searches only the vertices of its own basis shard [m0, m0 + Ml) -- the queries are
+      // split across the GPUs (ClosestPointRegistrator.scala:74-131), and since a rank's observation rows ARE
+      // those vertices nothing has to be gathered.  (The reversed direction folds target queries onto template vertices
+      // and stays replicated.)
+      if (ctx->nranks > 1) GINGR_TRY(icp_correspondence_enqueue(ctx, g->closest, fv, tv, cfg.correspondence_method, m0, Ml));
+      else GINGR_TRY(icp_correspondence_enqueue(ctx, g->closest, fv, tv, cfg.correspondence_method));
       icp_cp = g->closest.cp.p;
     } else {
       // closestPointCorrespondenceReversal (ClosestPointRegistrator.scala:34-45): search from the target to the fit,

@@ -41,12 +41,17 @@ def main():
     diag = float(np.linalg.norm(ref.max(0) - ref.min(0)))
     ok = True
     results = {}
-    for name in ("cpd", "icp"):
+    ICP_METHODS = {"icp": api.TRIANGULAR_CLOSEST_POINT, "icp_pointcloud": api.POINTCLOUD_CLOSEST_POINT,
+                   "icp_normal": api.ALONG_NORMAL_CLOSEST_POINT, "icp_reversed": api.TRIANGULAR_CLOSEST_POINT}
+    NAMES = ("cpd",) + tuple(ICP_METHODS)   # the ICP flavours split their QUERIES across the ranks (reversed: replicated)
+    for name in NAMES:
         if name == "cpd":
             reg = api.CpdRegistration(ctx, model, tgt, api.CpdConfiguration(w=0.1))
             reg.setLandmarks([3, 250], target[[5, 300]], None)
         else:
-            reg = api.IcpRegistration(ctx, model, tgt, api.IcpConfiguration(initialSigma=2.0, endSigma=0.5))
+            reg = api.IcpRegistration(ctx, model, tgt, api.IcpConfiguration(initialSigma=2.0, endSigma=0.5,
+                                                                            correspondenceMethod=ICP_METHODS[name],
+                                                                            reverseCorrespondenceDirection=(name == "icp_reversed")))
         st = reg.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
         for _ in range(3):
             st = reg.propose(st)
@@ -65,14 +70,17 @@ def main():
         from oracle import oracle
         oracle.build()
         om = oracle.Gpmm(ref, mean, basis, var, tri)
-        for name in ("cpd", "icp"):
+        OMETHOD = {"icp": oracle.METHOD_TRIANGULAR, "icp_pointcloud": oracle.METHOD_POINTCLOUD, "icp_normal": oracle.METHOD_ALONG_NORMAL,
+                   "icp_reversed": oracle.METHOD_TRIANGULAR}
+        for name in NAMES:
             if name == "cpd":
                 algo = oracle.CpdAlgorithm(oracle.CpdConfig(w=0.1))
                 lm = oracle.Landmarks(np.array([3, 250], dtype=np.int32), target[[5, 300]], np.tile(np.eye(3), (2, 1, 1)))
                 ost = algo.initialize(oracle.initial_state(om, target, tt, global_transformation=oracle.RIGID_TRANSFORMS,
                                                            landmarks=lm))
             else:
-                algo = oracle.IcpAlgorithm(oracle.IcpConfig(initial_sigma=2.0, end_sigma=0.5))
+                algo = oracle.IcpAlgorithm(oracle.IcpConfig(initial_sigma=2.0, end_sigma=0.5, method=OMETHOD[name],
+                                                            reverse=(name == "icp_reversed")))
                 ost = algo.initialize(oracle.initial_state(om, target, tt, global_transformation=oracle.RIGID_TRANSFORMS))
             for _ in range(3):
                 ost = oracle.propose(algo, ost)

@@ -117,10 +117,12 @@ def test_multi_gpu_update_matches_oracle(world):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    sys.stdout.write(p.stdout[-4000:])
-    sys.stderr.write(p.stderr[-4000:])
-    assert p.returncode == 0 and "MGPU_PARITY_OK" in p.stdout
+    # exact scans and the uniform grids of the K2 search (the grids are otherwise only used from 8192 vertices up)
+    for grid in ("0", "1"):
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, GINGR_K2_GRID=grid))
+        sys.stdout.write(p.stdout[-4000:])
+        sys.stderr.write(p.stderr[-4000:])
+        assert p.returncode == 0 and "MGPU_PARITY_OK" in p.stdout, f"GINGR_K2_GRID={grid}"
 
 
 def _gloo_chain_worker(rank, world, port, n_chains, steps, q):
