@@ -354,11 +354,11 @@ __global__ void __launch_bounds__(256) procrustes_sums_kernel(int pass, int m0, 
                                                               const double* __restrict__ ds,
                                                               double* __restrict__ newshape /*[3 Ml]*/,
                                                               double* __restrict__ part /*[blocks][16]*/) {
-  __shared__ double red[10][8];
+  __shared__ double red[16][8];
   const int i = blockIdx.x * 256 + threadIdx.x;
-  double v[10];
+  double v[16];
 #pragma unroll
-  for (int q = 0; q < 10; ++q) v[q] = 0.0;
+  for (int q = 0; q < 16; ++q) v[q] = 0.0;
   if (i < Ml) {
     const int gi = m0 + i;
     const double* R = ds + DS_R;
@@ -371,6 +371,21 @@ __global__ void __launch_bounds__(256) procrustes_sums_kernel(int pass, int m0, 
     if (pass == 0) {
       newshape[3 * i] = Y0; newshape[3 * i + 1] = Y1; newshape[3 * i + 2] = Y2;
       v[0] = X0; v[1] = X1; v[2] = X2; v[3] = Y0; v[4] = Y1; v[5] = Y2;
+    } else if (pass == 2) {
+      // several ranks: ONE pass and one all-reduce.  Moments about fixed points every rank knows -- p0 = (ref + mean) of
+      // vertex 0 for x, its posed image q0 = R p0 + t for y -- so that centring them afterwards cancels nothing that
+      // matters (the shifted coordinates are of the size of the shape, wherever it sits).
+      newshape[3 * i] = Y0; newshape[3 * i + 1] = Y1; newshape[3 * i + 2] = Y2;
+      const double p0x = ref[0] + mean[0], p0y = ref[1] + mean[1], p0z = ref[2] + mean[2];
+      const double x0 = X0 - p0x, x1 = X1 - p0y, x2 = X2 - p0z;
+      const double y0 = Y0 - (R[0] * p0x + R[1] * p0y + R[2] * p0z + ds[DS_T]);
+      const double y1 = Y1 - (R[3] * p0x + R[4] * p0y + R[5] * p0z + ds[DS_T + 1]);
+      const double y2 = Y2 - (R[6] * p0x + R[7] * p0y + R[8] * p0z + ds[DS_T + 2]);
+      v[0] = x0 * x0 + x1 * x1 + x2 * x2;
+      v[1] = y0 * x0; v[2] = y0 * x1; v[3] = y0 * x2;
+      v[4] = y1 * x0; v[5] = y1 * x1; v[6] = y1 * x2;
+      v[7] = y2 * x0; v[8] = y2 * x1; v[9] = y2 * x2;
+      v[10] = x0; v[11] = x1; v[12] = x2; v[13] = y0; v[14] = y1; v[15] = y2;
     } else {
       const double x0 = X0 - ds[DS_MUX], x1 = X1 - ds[DS_MUX + 1], x2 = X2 - ds[DS_MUX + 2];
       const double y0 = Y0 - ds[DS_MUY], y1 = Y1 - ds[DS_MUY + 1], y2 = Y2 - ds[DS_MUY + 2];
@@ -381,13 +396,13 @@ __global__ void __launch_bounds__(256) procrustes_sums_kernel(int pass, int m0, 
     }
   }
 #pragma unroll
-  for (int q = 0; q < 10; ++q) {
+  for (int q = 0; q < 16; ++q) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
     if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v[q];
   }
   __syncthreads();
-  if (threadIdx.x < 10) {
+  if (threadIdx.x < 16) {
     double s = 0.0;
     for (int k = 0; k < 8; ++k) s += red[threadIdx.x][k];
     part[blockIdx.x * 16 + threadIdx.x] = s;
@@ -502,6 +517,26 @@ __device__ void procrustes_solve_dev(int M, const double* __restrict__ sums, dou
 
 __global__ void procrustes_solve_kernel(int M, const double* __restrict__ sums, double* __restrict__ ds,
                                         const int* __restrict__ is) {
+  procrustes_solve_dev(M, sums, ds, is);
+}
+
+// several ranks: the all-reduced shifted moments of the single pass (pass 2 of procrustes_sums_kernel) -> means and
+// centred sums, then the same solve
+__global__ void procrustes_moments_solve_kernel(int M, double* __restrict__ sums /*[16]*/, const double* __restrict__ ref,
+                                                const double* __restrict__ mean, double* __restrict__ ds,
+                                                const int* __restrict__ is) {
+  const double* R = ds + DS_R;
+  const double p0[3] = {ref[0] + mean[0], ref[1] + mean[1], ref[2] + mean[2]};
+  double mx[3], my[3];
+  for (int d = 0; d < 3; ++d) {
+    mx[d] = sums[10 + d] / M;
+    my[d] = sums[13 + d] / M;
+    ds[DS_MUX + d] = mx[d] + p0[d];
+    ds[DS_MUY + d] = my[d] + (R[3 * d] * p0[0] + R[3 * d + 1] * p0[1] + R[3 * d + 2] * p0[2] + ds[DS_T + d]);
+  }
+  sums[0] -= M * (mx[0] * mx[0] + mx[1] * mx[1] + mx[2] * mx[2]);
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) sums[1 + 3 * a + b] -= M * my[a] * mx[b];
   procrustes_solve_dev(M, sums, ds, is);
 }
 
@@ -1580,22 +1615,26 @@ static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, ui
   // ---- instances, Procrustes -----------------------------------------------------------------------------------
   GINGR_TRY(instance_rows(ctx, m, vec + 6 * rp, 2, g->alpha.p, vec + 3 * rp, g->inst_a.p, g->inst_b.p));
   const int pblocks = ceil_div(std::max(Ml, 1), 256);
-  for (int pass = 0; pass < 2; ++pass) {
-    procrustes_sums_kernel<<<pblocks, 256, 0, st>>>(pass, m0, Ml, m->ref.p, m->mean.p, g->inst_a.p, g->inst_b.p, g->ds.p,
-                                                    g->newshape.p, g->pro_part.p);
-    GINGR_LAUNCHED(ctx);
-    if (ctx->nranks == 1) {
+  if (ctx->nranks == 1) {
+    for (int pass = 0; pass < 2; ++pass) {
+      procrustes_sums_kernel<<<pblocks, 256, 0, st>>>(pass, m0, Ml, m->ref.p, m->mean.p, g->inst_a.p, g->inst_b.p, g->ds.p,
+                                                      g->newshape.p, g->pro_part.p);
+      GINGR_LAUNCHED(ctx);
       // one rank: the block partials are summed (same fixed order) by the kernel that consumes the sums
       procrustes_reduce_then_kernel<<<1, 32, 0, st>>>(pass, pblocks, M, g->pro_part.p, g->pro_sums.p, g->ds.p, g->is.p);
       GINGR_LAUNCHED(ctx);
-    } else {
-      procrustes_reduce_kernel<<<1, 32, 0, st>>>(pblocks, 10, g->pro_part.p, g->pro_sums.p);
-      GINGR_LAUNCHED(ctx);
-      GINGR_TRY(comm_allreduce_sum(ctx, g->pro_sums.p, 16));
-      if (pass == 0) procrustes_means_kernel<<<1, 1, 0, st>>>(M, g->pro_sums.p, g->ds.p);
-      else procrustes_solve_kernel<<<1, 1, 0, st>>>(M, g->pro_sums.p, g->ds.p, g->is.p);
-      GINGR_LAUNCHED(ctx);
     }
+  } else {
+    // several ranks: one pass of shifted moments and ONE all-reduce of 16 doubles (two latency-bound all-reduces and the
+    // second pass over the shard before)
+    procrustes_sums_kernel<<<pblocks, 256, 0, st>>>(2, m0, Ml, m->ref.p, m->mean.p, g->inst_a.p, g->inst_b.p, g->ds.p,
+                                                    g->newshape.p, g->pro_part.p);
+    GINGR_LAUNCHED(ctx);
+    procrustes_reduce_kernel<<<1, 32, 0, st>>>(Ml > 0 ? pblocks : 0, 16, g->pro_part.p, g->pro_sums.p);
+    GINGR_LAUNCHED(ctx);
+    GINGR_TRY(comm_allreduce_sum(ctx, g->pro_sums.p, 16));
+    procrustes_moments_solve_kernel<<<1, 1, 0, st>>>(M, g->pro_sums.p, m->ref.p, m->mean.p, g->ds.p, g->is.p);
+    GINGR_LAUNCHED(ctx);
   }
   // ---- alpha_new = transformedModel.coefficients(newshape) ---------------------------------------------------------
   if (Ml > 0) {
