@@ -652,6 +652,7 @@ struct gingr_registration {
   DevBuf<int32_t> rev_scratch;      // [3 M + N + 1] lists of the O(N + M) fold (large problems)
   DevBuf<double> rows_ext;     // [4 M + 8]  E-step rows + xPx (all-reduced together)
   DevBuf<double> Mx;           // [(r + 8)][rp]  posterior matrix + rhs row
+  DevBuf<double> Mx_packed;    // several ranks: lower tiles of the partial posterior matrix + rhs, all-reduced as one buffer
   DevBuf<double> Mx_raw;       // [(r + 1)][rp]  copy of Mx and rhs before the factorisation (MCMC only, mcmc.cuh)
   bool keep_raw = false;
   bool skip_fit_refresh = false;        // MH step: the proposal's fit is evaluated after the random override
@@ -1316,6 +1317,7 @@ int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, cons
   if (rc == GINGR_OK) { int32_t q = g->gram.build(ctx, 3 * Ml, r, rp); if (q < 0) rc = q; }
   A(g->rows_ext.alloc((size_t)4 * M + 8));
   A(g->Mx.alloc((size_t)(r + 8) * rp));
+  if (ctx->nranks > 1) A(g->Mx_packed.alloc(gram_packed_doubles(g->gram) + rp));
   A(g->wrow.alloc((size_t)3 * Mmax)); A(g->u.alloc((size_t)3 * Mmax));
   A(g->inst_a.alloc((size_t)3 * Mmax)); A(g->inst_b.alloc((size_t)3 * Mmax));
   A(g->newshape.alloc((size_t)3 * Mmax)); A(g->fit_local.alloc((size_t)3 * Mmax));
@@ -1330,6 +1332,7 @@ int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, cons
   A(g->alpha.alloc((size_t)rp));
   if (rc == GINGR_OK) {
     A(cudaMemsetAsync(g->Mx.p, 0, sizeof(double) * (size_t)(r + 8) * rp, ctx->stream));
+    if (g->Mx_packed.p) A(cudaMemsetAsync(g->Mx_packed.p, 0, sizeof(double) * g->Mx_packed.n, ctx->stream));   // unused slots stay 0
     A(cudaMemsetAsync(g->fit_local.p, 0, sizeof(double) * 3 * Mmax, ctx->stream));
     A(cudaMemsetAsync(g->ds.p, 0, sizeof(double) * DS_COUNT, ctx->stream));
     A(cudaMemsetAsync(g->is.p, 0, sizeof(int) * IS_COUNT, ctx->stream));
@@ -1353,6 +1356,7 @@ int32_t gingr_registration_destroy(gingr_registration* g) {
   drop_graph(g);
   mcmc_release(g);
   g->Mx_raw.release();
+  g->Mx_packed.release();
   g->lm_pid.release(); g->lml_pid.release(); g->lml_pts.release(); g->lml_cinv.release(); g->lml_A.release();
   g->lml_rows.release();
   g->estep.release(); g->closest.release(); g->gram.release();
@@ -1566,7 +1570,11 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
                                  cfg.end_sigma, g->ds.p);
   GINGR_LAUNCHED(ctx);
   // ---- posterior: rhs, Gram, Cholesky --------------------------------------------------------------------
-  double* rhs = g->Mx.p + (size_t)r * rp;
+  // several ranks: the partial matrix is written as packed lower tiles with the rhs behind them, so that ONE all-reduce of
+  // half the bytes of the (r + 1) x rp rectangle combines both; it is unpacked into g->Mx afterwards
+  const bool packed = ctx->nranks > 1;
+  const size_t packed_n = packed ? gram_packed_doubles(g->gram) : 0;
+  double* rhs = packed ? g->Mx_packed.p + packed_n : g->Mx.p + (size_t)r * rp;
   GINGR_TRY(gemvT_enqueue(ctx, 3 * Ml, r, rp, m->phi.p, g->u.p, m->sqrt_lambda.p, g->gt_part.p, rhs));
   const bool use_lm = cfg.use_landmark_correspondence && g->Ll > 0;
   if (use_lm) {
@@ -1577,9 +1585,16 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
   }
   GINGR_TRY(gram_partials_enqueue(ctx, g->gram, m->phi.p, g->wrow.p, g->ev(6) ? *g->ev(6) : nullptr,
                                   g->ev(7) ? *g->ev(7) : nullptr));
-  GINGR_TRY(gram_finish_enqueue(ctx, g->gram, g->gram.d_partial.p, m->sqrt_lambda.p, ctx->rank == 0 ? 1.0 : 0.0,
-                                use_lm ? g->Ll : 0, g->lml_rows.p, g->lml_A.p, rp, g->Mx.p));
-  GINGR_TRY(comm_allreduce_sum(ctx, g->Mx.p, (size_t)(r + 1) * rp));
+  if (packed) {
+    GINGR_TRY(gram_finish_enqueue(ctx, g->gram, g->gram.d_partial.p, m->sqrt_lambda.p, ctx->rank == 0 ? 1.0 : 0.0,
+                                  use_lm ? g->Ll : 0, g->lml_rows.p, g->lml_A.p, rp, g->Mx_packed.p, true));
+    GINGR_TRY(comm_allreduce_sum(ctx, g->Mx_packed.p, packed_n + (size_t)r));
+    GINGR_TRY(gram_unpack_enqueue(ctx, g->gram, g->Mx_packed.p, rp, g->Mx.p));
+    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->Mx.p + (size_t)r * rp, rhs, sizeof(double) * r, cudaMemcpyDeviceToDevice, st));
+  } else {
+    GINGR_TRY(gram_finish_enqueue(ctx, g->gram, g->gram.d_partial.p, m->sqrt_lambda.p, 1.0, use_lm ? g->Ll : 0, g->lml_rows.p,
+                                  g->lml_A.p, rp, g->Mx.p));
+  }
   if (g->keep_raw)
     GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->Mx_raw.p, g->Mx.p, sizeof(double) * (size_t)(r + 1) * rp, cudaMemcpyDeviceToDevice, st));
   g->rec(8);
