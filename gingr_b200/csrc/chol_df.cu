@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(BS_THREADS) chol_backsolve_z_kernel(int n, con
   double s = 0.0;
   for (int i = nb - 1; i > k; --i) {
     const int st = (nb - 1 - i) & 1;
-    if (i - 1 > k) load_block(sLb + (st ^ 1) * TB * TB, i - 1);   // the ring slot was last read two steps ago (barriers below)
+    __syncthreads();   // the other ring slot was read by the products of the previous step: every thread is past them
+    if (i - 1 > k) load_block(sLb + (st ^ 1) * TB * TB, i - 1);
     cp_async_commit();
     if (tid == 0) while (ld_acquire(&flags[i]) == 0) {}
     asm volatile("cp.async.wait_group 1;\n" ::: "memory");
