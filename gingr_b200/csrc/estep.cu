@@ -326,15 +326,20 @@ __global__ void __launch_bounds__(TPB, ESTEP_MINB_B) estep_rowsum_kernel(int M, 
 __global__ void __launch_bounds__(TPB) estep_rowreduce_kernel(int M, int splits, const double* __restrict__ part,
                                                               const double* __restrict__ rowf,
                                                               double* __restrict__ out) {
-  const int i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= M) return;
+  // one thread per (quantity q, row i): 4 M threads instead of M (the M-thread form ran at 7 % occupancy: 51 us at
+  // M = 20 000); two interleaved partial sums over the splits, fixed order
+  const int idx = blockIdx.x * TPB + threadIdx.x;
+  if (idx >= 4 * M) return;
+  const int q = idx / M, i = idx - q * M;
   const double f = rowf ? rowf[i] : 1.0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    double s = 0.0;
-    for (int k = 0; k < splits; ++k) s += part[((size_t)k * 4 + q) * M + i];
-    out[(size_t)q * M + i] = f * s;
+  double s0 = 0.0, s1 = 0.0;
+  int k = 0;
+  for (; k + 1 < splits; k += 2) {
+    s0 += part[((size_t)k * 4 + q) * M + i];
+    s1 += part[((size_t)(k + 1) * 4 + q) * M + i];
   }
+  if (k < splits) s0 += part[((size_t)k * 4 + q) * M + i];
+  out[(size_t)q * M + i] = f * (s0 + s1);
 }
 
 // sets *flag when any of the n doubles is NaN / Inf (the E-step kernels assume finite input, exp2_poly.cuh)
@@ -519,7 +524,7 @@ int32_t estep_enqueue(gingr_ctx* ctx, EstepWorkspace& ws, int M, int N, const do
                                                                         ws.rowpart.p);
   if (ev) cudaEventRecord(ev->b1, st);
   GINGR_LAUNCHED(ctx);
-  estep_rowreduce_kernel<<<ceil_div(M, TPB), TPB, 0, st>>>(M, p.col_splits, ws.rowpart.p, rowf, ws.rows.p);
+  estep_rowreduce_kernel<<<ceil_div(4 * M, TPB), TPB, 0, st>>>(M, p.col_splits, ws.rowpart.p, rowf, ws.rows.p);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256) gram_finish_kernel(int r, int rp, int ld_
                                                           double add_identity, int L,
                                                           const double* __restrict__ lm_rows,
                                                           const double* __restrict__ lm_A, double* __restrict__ out,
-                                                          int packed) {
+                                                          int packed /*1: packed lower tiles, 2: matrix without the mirror*/) {
   const int ta = blockIdx.y, tb = blockIdx.x;
   if (tb > ta) return;
   const int tile = ta * (ta + 1) / 2 + tb;
@@ -358,12 +358,12 @@ __global__ void __launch_bounds__(256) gram_finish_kernel(int r, int rp, int ld_
     }
     const double da = sqrt_lambda ? sqrt_lambda[a] : 1.0, db = sqrt_lambda ? sqrt_lambda[b] : 1.0;
     const double v = da * s * db;
-    if (packed) {   // lower tiles back to back (what a multi-rank iteration all-reduces: half of the full rectangle)
+    if (packed == 1) {   // lower tiles back to back (what a multi-rank iteration all-reduces: half of the full rectangle)
       out[(size_t)tile * BT * BT + e] = v + (a == b ? add_identity : 0.0);
       continue;
     }
     out[(size_t)a * ld_out + b] = v + (a == b ? add_identity : 0.0);
-    if (a != b) out[(size_t)b * ld_out + a] = v;
+    if (a != b && packed != 2) out[(size_t)b * ld_out + a] = v;   // the mirror is a column-wise (uncoalesced) write
   }
 }
 
@@ -490,7 +490,7 @@ int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_ph
 }
 
 // out[r x r] (pitch ld_out) = add_identity I + D (sum of partial tiles + landmark blocks) D
-// out (both triangles, pitch ld_out) <- the lower tiles of a packed buffer [tile][128][128] (tile = ta (ta + 1) / 2 + tb)
+// out (LOWER triangle, pitch ld_out) <- the lower tiles of a packed buffer [tile][128][128] (tile = ta (ta + 1) / 2 + tb)
 __global__ void __launch_bounds__(256) gram_unpack_kernel(int r, int ld_out, const double* __restrict__ packed,
                                                           double* __restrict__ out) {
   const int ta = blockIdx.y, tb = blockIdx.x;
@@ -500,9 +500,7 @@ __global__ void __launch_bounds__(256) gram_unpack_kernel(int r, int ld_out, con
     const int row = e / BT, col = e % BT;
     const int a = ta * BT + row, b = tb * BT + col;
     if (a >= r || b >= r || b > a) continue;
-    const double v = packed[(size_t)tile * BT * BT + e];
-    out[(size_t)a * ld_out + b] = v;
-    if (a != b) out[(size_t)b * ld_out + a] = v;
+    out[(size_t)a * ld_out + b] = packed[(size_t)tile * BT * BT + e];   // lower triangle: all the factorisation reads
   }
 }
 
@@ -519,12 +517,12 @@ int32_t gram_unpack_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_pack
 
 int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_partial, const double* d_sqrt_lambda,
                             double add_identity, int L, const double* d_lm_rows, const double* d_lm_A, int ld_out,
-                            double* d_out, bool packed) {
+                            double* d_out, bool packed, bool lower_only) {
   const int tiles = plan.nt * (plan.nt + 1) / 2;
   const int slices = std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
   gram_finish_kernel<<<dim3(plan.nt, plan.nt, slices), 256, 0, ctx->stream>>>(plan.r, plan.rp, ld_out, d_partial,
                                                                       plan.d_tile_first.p, d_sqrt_lambda, add_identity,
-                                                                      L, d_lm_rows, d_lm_A, d_out, packed ? 1 : 0);
+                                                                      L, d_lm_rows, d_lm_A, d_out, packed ? 1 : (lower_only ? 2 : 0));
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

@@ -18,10 +18,12 @@ struct GramPlan {
 int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_phi, const double* d_wrow,
                               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 // packed: d_out receives the lower tiles back to back ([tile][128][128], gram_packed_doubles) instead of the r x r matrix --
-// what a multi-rank iteration all-reduces (half the bytes); gram_unpack_enqueue then writes both triangles of the matrix.
+// what a multi-rank iteration all-reduces (half the bytes); gram_unpack_enqueue then writes the lower triangle of the matrix.
 int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_partial, const double* d_sqrt_lambda,
                             double add_identity, int L, const double* d_lm_rows, const double* d_lm_A, int ld_out,
-                            double* d_out, bool packed = false);
+                            double* d_out, bool packed = false, bool lower_only = false);
+// lower_only: the strict upper triangle is not written (the Cholesky factorisation reads the lower one only; the mirror
+// is a column-wise write that costs as much as the rest of the kernel)
 size_t gram_packed_doubles(const GramPlan& plan);
 int32_t gram_unpack_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_packed, int ld_out, double* d_out);
 

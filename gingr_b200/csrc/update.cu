@@ -117,19 +117,30 @@ __global__ void compact_gather_kernel(int M, int nranks, int Mmax, const double*
 }
 
 // ---- CPD scalars for the E-step from the state block --------------------------------------------
-__global__ void __launch_bounds__(256) cpd_estep_scalars_kernel(const double* __restrict__ ds, double w, double ratio,
-                                                                int n3, const double* __restrict__ fit,
-                                                                double target_maxabs, double* scal) {
+__global__ void __launch_bounds__(1024) cpd_estep_scalars_kernel(const double* __restrict__ ds, double w, double ratio,
+                                                                 int n3, const double* __restrict__ fit,
+                                                                 double target_maxabs, double* scal) {
   // max |coordinate| of the current fit -> bound of the pair distances (scal[7], gauss_exp2_tab<SAFE>)
-  __shared__ double red[256];
-  double m = 0.0;
-  for (int k = threadIdx.x; k < n3; k += 256) m = fmax(m, fabs(fit[k]));
-  red[threadIdx.x] = m;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
-    __syncthreads();
+  __shared__ double red[32];
+  double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+  int k = threadIdx.x;
+  for (; k + 3072 < n3; k += 4096) {
+    m0 = fmax(m0, fabs(fit[k]));
+    m1 = fmax(m1, fabs(fit[k + 1024]));
+    m2 = fmax(m2, fabs(fit[k + 2048]));
+    m3 = fmax(m3, fabs(fit[k + 3072]));
   }
+  for (; k < n3; k += 1024) m0 = fmax(m0, fabs(fit[k]));
+  double m = fmax(fmax(m0, m1), fmax(m2, m3));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  m = red[threadIdx.x];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  red[0] = m;
   if (threadIdx.x != 0) return;
   const double sigma2 = ds[DS_SIGMA2];
   const double t = 2.0 * 3.14159265358979323846 * sigma2;
@@ -235,16 +246,26 @@ __global__ void __launch_bounds__(256) obs_kernel(ObsArgs a, const double* __res
 // sigma2 hook: CPD (xPx - 2 trPXY + yPy) / (3 Np) (CPD.scala:133-147); ICP linear anneal (ICP.scala:96-99)
 __global__ void sigma2_kernel(int algo, int nblocks, const double* __restrict__ sums_part, const double* __restrict__ xpx,
                               double sigma_step, double end_sigma, double* __restrict__ ds) {
+  // one warp: lane l adds the block partials l, l + 32, ... in order, then a fixed shuffle tree (deterministic)
+  const int lane = threadIdx.x;
   if (algo == GINGR_ALGO_CPD) {
     double np = 0.0, ypy = 0.0, tr = 0.0;
-    for (int k = 0; k < nblocks; ++k) {
+    for (int k = lane; k < nblocks; k += 32) {
       np += sums_part[3 * k];
       ypy += sums_part[3 * k + 1];
       tr += sums_part[3 * k + 2];
     }
-    ds[DS_NP] = np; ds[DS_XPX] = xpx[0]; ds[DS_YPY] = ypy; ds[DS_TRPXY] = tr;
-    ds[DS_NEW_SIGMA2] = (xpx[0] - 2.0 * tr + ypy) / (np * 3.0);
-  } else {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      np += __shfl_xor_sync(0xffffffffu, np, o);
+      ypy += __shfl_xor_sync(0xffffffffu, ypy, o);
+      tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    }
+    if (lane == 0) {
+      ds[DS_NP] = np; ds[DS_XPX] = xpx[0]; ds[DS_YPY] = ypy; ds[DS_TRPXY] = tr;
+      ds[DS_NEW_SIGMA2] = (xpx[0] - 2.0 * tr + ypy) / (np * 3.0);
+    }
+  } else if (lane == 0) {
     ds[DS_NEW_SIGMA2] = fmax(ds[DS_SIGMA2] - sigma_step, end_sigma);
   }
 }
@@ -546,10 +567,13 @@ __global__ void procrustes_reduce_then_kernel(int pass, int nblocks, int M, cons
                                               double* __restrict__ sums /*[16]*/, double* __restrict__ ds,
                                               const int* __restrict__ is) {
   const int q = threadIdx.x;
-  if (q < 10) {
+  // lane l adds the blocks l, l + 32, ... of every quantity in order, then a fixed shuffle tree (deterministic)
+  for (int c = 0; c < 10; ++c) {
     double s = 0.0;
-    for (int k = 0; k < nblocks; ++k) s += part[k * 16 + q];
-    sums[q] = s;
+    for (int k = q; k < nblocks; k += 32) s += part[k * 16 + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (q == 0) sums[c] = s;
   }
   __syncwarp();
   if (q != 0) return;
@@ -1076,7 +1100,7 @@ static int32_t posterior_core(gingr_ctx* ctx, const gingr_model* model, const do
     ctx->launches += 3;
   }
   if ((rc = gram_partials_enqueue(ctx, s.gram, m->phi.p, s.wrow.p)) < 0) return fail(rc);
-  if ((rc = gram_finish_enqueue(ctx, s.gram, s.gram.d_partial.p, m->sqrt_lambda.p, 1.0, L, d_lrows.p, d_lA.p, rp, s.Mx.p)) < 0) return fail(rc);
+  if ((rc = gram_finish_enqueue(ctx, s.gram, s.gram.d_partial.p, m->sqrt_lambda.p, 1.0, L, d_lrows.p, d_lA.p, rp, s.Mx.p, false, true)) < 0) return fail(rc);
   if (xrows > 0) {
     gingr::posterior_cov_rows_kernel<<<dim3(ceil_div(rp, 256), xrows), 256, 0, st>>>(xrows, r, rp, m->phi.p, m->sqrt_lambda.p,
                                                                                  s.Mx.p + (size_t)(r + 1) * rp);
@@ -1496,7 +1520,7 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
     GINGR_TRY(validate_finite_enqueue(ctx, 1, g->ds.p + DS_SIGMA2, g->is.p + IS_FAIL_POST));
     if (tg->nonfinite) GINGR_TRY(validate_finite_enqueue(ctx, 3 * tg->N_total, tg->verts.p, g->is.p + IS_FAIL_POST));
     GINGR_TRY(aos_to_soa_enqueue(ctx, M, g->fit.p, g->estep.fit_soa.p));
-    cpd_estep_scalars_kernel<<<1, 256, 0, st>>>(g->ds.p, cfg.w, (double)M / (double)tg->N_total, 3 * M, g->fit.p,
+    cpd_estep_scalars_kernel<<<1, 1024, 0, st>>>(g->ds.p, cfg.w, (double)M / (double)tg->N_total, 3 * M, g->fit.p,
                                                 tg->maxabs, g->estep.scal.p);
     GINGR_LAUNCHED(ctx);
     if (tg->N > 0) {
@@ -1566,7 +1590,7 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
                                       g->lm_pid.p, g->ds.p, g->is.p, g->wrow.p, g->u.p, g->sums_part.p);
   GINGR_LAUNCHED(ctx);
   const double sigma_step = cfg.algorithm == GINGR_ALGO_ICP ? (cfg.initial_sigma - cfg.end_sigma) / (double)cfg.max_iterations : 0.0;
-  sigma2_kernel<<<1, 1, 0, st>>>(cfg.algorithm, oblocks, g->sums_part.p, g->rows_ext.p + (size_t)4 * M, sigma_step,
+  sigma2_kernel<<<1, 32, 0, st>>>(cfg.algorithm, oblocks, g->sums_part.p, g->rows_ext.p + (size_t)4 * M, sigma_step,
                                  cfg.end_sigma, g->ds.p);
   GINGR_LAUNCHED(ctx);
   // ---- posterior: rhs, Gram, Cholesky --------------------------------------------------------------------
@@ -1592,8 +1616,9 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
     GINGR_TRY(gram_unpack_enqueue(ctx, g->gram, g->Mx_packed.p, rp, g->Mx.p));
     GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->Mx.p + (size_t)r * rp, rhs, sizeof(double) * r, cudaMemcpyDeviceToDevice, st));
   } else {
+    // the upper triangle is only read from the kept copy of the MH chain (mcmc.cuh: dense products with the raw matrix)
     GINGR_TRY(gram_finish_enqueue(ctx, g->gram, g->gram.d_partial.p, m->sqrt_lambda.p, 1.0, use_lm ? g->Ll : 0, g->lml_rows.p,
-                                  g->lml_A.p, rp, g->Mx.p));
+                                  g->lml_A.p, rp, g->Mx.p, false, !g->keep_raw));
   }
   if (g->keep_raw)
     GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->Mx_raw.p, g->Mx.p, sizeof(double) * (size_t)(r + 1) * rp, cudaMemcpyDeviceToDevice, st));
