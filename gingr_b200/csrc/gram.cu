@@ -213,6 +213,7 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
 
 __global__ void __launch_bounds__(GRAM_WS_THREADS, 1) gram_ws_kernel(int rows, int rp, const double* __restrict__ phi,
                                                                      const double* __restrict__ wrow,
+                                                                     const double* __restrict__ resid, int r,
                                                                      const GramSegment* __restrict__ segs,
                                                                      const int* __restrict__ seg_begin,
                                                                      double* __restrict__ partial) {
@@ -239,6 +240,10 @@ __global__ void __launch_bounds__(GRAM_WS_THREADS, 1) gram_ws_kernel(int rows, i
       const int a0 = sg.ta * BT, b0 = sg.tb * BT;
       const bool diag = sg.ta == sg.tb;
       const unsigned bytes_a = (unsigned)(min(BT, rp - a0) * 8), bytes_b = diag ? 0u : (unsigned)(min(BT, rp - b0) * 8);
+      // rhs for free: in the last tile row the first column of the A panel past the bulk copy (global index rp: the
+      // copy also brings the zero padding [r, rp) of Phi) carries the residual of the row, so that output row rp of those
+      // tiles is  sum_k resid_k w_k Phi[k][.]  = Phi^T W resid
+      const int rcol = (resid != nullptr && rp - a0 > 0 && rp - a0 < BT) ? rp - a0 : -1;
       for (int ch = sg.c0; ch < sg.c1; ++ch, ++it) {
         const int stage = it % STAGES;
         const int krow = ch * BK + lane;                 // this lane's row of the chunk
@@ -250,6 +255,8 @@ __global__ void __launch_bounds__(GRAM_WS_THREADS, 1) gram_ws_kernel(int rows, i
         sW[stage * BK + lane] = wv;
         if (!rok) {  // rows past the end of Phi contribute zero (the tail chunk only)
           for (int c = 0; c < BT; ++c) { dA[c] = 0.0; if (!diag) dB[c] = 0.0; }
+        } else if (rcol >= 0) {
+          dA[rcol] = resid[krow];
         }
         const int valid = min(BK, rows - ch * BK);
         const unsigned full_bar = bar0 + 8 * stage;
@@ -334,11 +341,25 @@ __global__ void __launch_bounds__(256) gram_finish_kernel(int r, int rp, int ld_
                                                           double add_identity, int L,
                                                           const double* __restrict__ lm_rows,
                                                           const double* __restrict__ lm_A, double* __restrict__ out,
-                                                          int packed /*1: packed lower tiles, 2: matrix without the mirror*/) {
+                                                          int packed /*1: packed lower tiles, 2: matrix without the mirror*/,
+                                                          int rhs_row /*1: row rp of the last tile row holds Phi^T W resid*/) {
   const int ta = blockIdx.y, tb = blockIdx.x;
   if (tb > ta) return;
   const int tile = ta * (ta + 1) / 2 + tb;
   const int s0 = tile_first[tile], s1 = tile_first[tile + 1];
+  if (rhs_row && ta == (int)gridDim.y - 1) {
+    // the rhs that rode along (gram_ws_kernel): out[r][b] = sqrt_lambda[b] * sum of the partials, no identity, no mirror
+    const int row = rp - ta * BT;
+    for (int col = blockIdx.z * 256 + threadIdx.x; col < BT; col += 256 * gridDim.z) {
+      const int b = tb * BT + col, e = row * BT + col;
+      if (b >= r) continue;
+      double s = 0.0;
+      for (int k = s0; k < s1; ++k) s += partial[(size_t)k * BT * BT + e];
+      const double v = (sqrt_lambda ? sqrt_lambda[b] : 1.0) * s;
+      if (packed == 1) out[(size_t)tile * BT * BT + e] = v;
+      else out[(size_t)r * ld_out + b] = v;
+    }
+  }
   // blockIdx.z slices the elements of the tile: a small matrix has few tiles and would otherwise be finished by a
   // handful of latency-bound CTAs
   for (int e = blockIdx.z * 256 + threadIdx.x; e < BT * BT; e += 256 * gridDim.z) {
@@ -467,14 +488,22 @@ void GramPlan::release() {
 }
 
 // partial tiles of G = Phi^T diag(wrow) Phi  (wrow may be null)
+bool gram_rhs_fusable(const GramPlan& plan) {
+  static const int use_ws = [] { const char* e = getenv("GINGR_GRAM_WS"); return e ? atoi(e) : 1; }();
+  static const int fuse = [] { const char* e = getenv("GINGR_GRAM_RHS"); return e ? atoi(e) : 1; }();
+  // the same answer on every rank (a rank without rows just contributes zero partials)
+  return fuse && use_ws && GRAM_WARPS_M == 2 && (plan.rp % BT) != 0;
+}
+
 int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_phi, const double* d_wrow,
-                              cudaEvent_t ev0, cudaEvent_t ev1) {
+                              cudaEvent_t ev0, cudaEvent_t ev1, const double* d_resid) {
+  if (d_resid && !gram_rhs_fusable(plan)) return gingr_fail(ctx, GINGR_ERR_ARG, "gram: the rhs cannot ride along for this rank");
   if (ev0) cudaEventRecord(ev0, ctx->stream);
   if (plan.rows > 0 && plan.nsegs > 0) {
     static const int use_ws = [] { const char* e = getenv("GINGR_GRAM_WS"); return e ? atoi(e) : 1; }();
     if (use_ws && GRAM_WARPS_M == 2)
       gram_ws_kernel<<<plan.ncta, GRAM_WS_THREADS, GRAM_WS_SMEM, ctx->stream>>>(
-          plan.rows, plan.rp, d_phi, d_wrow, reinterpret_cast<const GramSegment*>(plan.d_segs.p), plan.d_seg_begin.p,
+          plan.rows, plan.rp, d_phi, d_wrow, d_resid, plan.r, reinterpret_cast<const GramSegment*>(plan.d_segs.p), plan.d_seg_begin.p,
           plan.d_partial.p);
     else
       gram_streamk_kernel<<<plan.ncta, GRAM_THREADS, GRAM_SMEM, ctx->stream>>>(
@@ -491,8 +520,8 @@ int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_ph
 
 // out[r x r] (pitch ld_out) = add_identity I + D (sum of partial tiles + landmark blocks) D
 // out (LOWER triangle, pitch ld_out) <- the lower tiles of a packed buffer [tile][128][128] (tile = ta (ta + 1) / 2 + tb)
-__global__ void __launch_bounds__(256) gram_unpack_kernel(int r, int ld_out, const double* __restrict__ packed,
-                                                          double* __restrict__ out) {
+__global__ void __launch_bounds__(256) gram_unpack_kernel(int r, int rp, int ld_out, const double* __restrict__ packed,
+                                                          double* __restrict__ out, int rhs_row) {
   const int ta = blockIdx.y, tb = blockIdx.x;
   if (tb > ta) return;
   const int tile = ta * (ta + 1) / 2 + tb;
@@ -502,14 +531,21 @@ __global__ void __launch_bounds__(256) gram_unpack_kernel(int r, int ld_out, con
     if (a >= r || b >= r || b > a) continue;
     out[(size_t)a * ld_out + b] = packed[(size_t)tile * BT * BT + e];   // lower triangle: all the factorisation reads
   }
+  if (rhs_row && ta == (int)gridDim.y - 1) {
+    const int row = rp - ta * BT;
+    for (int col = blockIdx.z * 256 + threadIdx.x; col < BT; col += 256 * gridDim.z) {
+      const int b = tb * BT + col;
+      if (b < r) out[(size_t)r * ld_out + b] = packed[(size_t)tile * BT * BT + row * BT + col];
+    }
+  }
 }
 
 size_t gram_packed_doubles(const GramPlan& plan) { return (size_t)(plan.nt * (plan.nt + 1) / 2) * BT * BT; }
 
-int32_t gram_unpack_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_packed, int ld_out, double* d_out) {
+int32_t gram_unpack_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_packed, int ld_out, double* d_out, bool rhs_row) {
   const int tiles = plan.nt * (plan.nt + 1) / 2;
   const int slices = std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
-  gram_unpack_kernel<<<dim3(plan.nt, plan.nt, slices), 256, 0, ctx->stream>>>(plan.r, ld_out, d_packed, d_out);
+  gram_unpack_kernel<<<dim3(plan.nt, plan.nt, slices), 256, 0, ctx->stream>>>(plan.r, plan.rp, ld_out, d_packed, d_out, rhs_row ? 1 : 0);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
@@ -517,12 +553,13 @@ int32_t gram_unpack_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_pack
 
 int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_partial, const double* d_sqrt_lambda,
                             double add_identity, int L, const double* d_lm_rows, const double* d_lm_A, int ld_out,
-                            double* d_out, bool packed, bool lower_only) {
+                            double* d_out, bool packed, bool lower_only, bool rhs_row) {
   const int tiles = plan.nt * (plan.nt + 1) / 2;
   const int slices = std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
   gram_finish_kernel<<<dim3(plan.nt, plan.nt, slices), 256, 0, ctx->stream>>>(plan.r, plan.rp, ld_out, d_partial,
                                                                       plan.d_tile_first.p, d_sqrt_lambda, add_identity,
-                                                                      L, d_lm_rows, d_lm_A, d_out, packed ? 1 : (lower_only ? 2 : 0));
+                                                                      L, d_lm_rows, d_lm_A, d_out, packed ? 1 : (lower_only ? 2 : 0),
+                                                                      rhs_row ? 1 : 0);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

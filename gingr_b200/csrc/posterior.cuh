@@ -15,17 +15,22 @@ struct GramPlan {
   int32_t build(gingr_ctx* ctx, int rows, int r, int rp);
   void release();
 };
+// d_resid (optional, needs gram_rhs_fusable): per-row residuals c_k; row r of the last tile row then comes out as
+// sum_k c_k w_k Phi[k][.] = Phi^T W c -- the right-hand side of the regression without a pass of its own over Phi
+// (finish / unpack with rhs_row = true emit it as row r of the matrix)
+bool gram_rhs_fusable(const GramPlan& plan);
 int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_phi, const double* d_wrow,
-                              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+                              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, const double* d_resid = nullptr);
 // packed: d_out receives the lower tiles back to back ([tile][128][128], gram_packed_doubles) instead of the r x r matrix --
 // what a multi-rank iteration all-reduces (half the bytes); gram_unpack_enqueue then writes the lower triangle of the matrix.
 int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_partial, const double* d_sqrt_lambda,
                             double add_identity, int L, const double* d_lm_rows, const double* d_lm_A, int ld_out,
-                            double* d_out, bool packed = false, bool lower_only = false);
+                            double* d_out, bool packed = false, bool lower_only = false, bool rhs_row = false);
 // lower_only: the strict upper triangle is not written (the Cholesky factorisation reads the lower one only; the mirror
 // is a column-wise write that costs as much as the rest of the kernel)
 size_t gram_packed_doubles(const GramPlan& plan);
-int32_t gram_unpack_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_packed, int ld_out, double* d_out);
+int32_t gram_unpack_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_packed, int ld_out, double* d_out,
+                            bool rhs_row = false);
 
 // ---- chol.cu -------------------------------------------------------------------------------------
 // In-place blocked Cholesky A = L L^T of the leading n x n block (lower triangle, row-major, pitch ld) of a

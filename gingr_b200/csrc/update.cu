@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(256) obs_kernel(ObsArgs a, const double* __res
                                                   const double* __restrict__ ref, const double* __restrict__ mean,
                                                   const int32_t* __restrict__ lm_pid, const double* __restrict__ ds,
                                                   int* __restrict__ is, double* __restrict__ wrow,
-                                                  double* __restrict__ u, double* __restrict__ sums_part /*[blocks][3]*/) {
+                                                  double* __restrict__ u, double* __restrict__ sums_part /*[blocks][3]*/,
+                                                  double* __restrict__ resid /*[3 Ml] unweighted R^T residual, may be null*/) {
   __shared__ double red[3][8];
   const int i = blockIdx.x * 256 + threadIdx.x;
   double sP1 = 0.0, sY = 0.0, sT = 0.0;
@@ -222,9 +223,12 @@ __global__ void __launch_bounds__(256) obs_kernel(ObsArgs a, const double* __res
       double rz = pz - (R[6] * bx + R[7] * by + R[8] * bz + ds[DS_T + 2]);
       if (wt == 0.0) { rx = ry = rz = 0.0; }  // dropped observation: contributes nothing (and no 0 * NaN)
       wrow[3 * li] = wrow[3 * li + 1] = wrow[3 * li + 2] = wt;
-      u[3 * li] = wt * (R[0] * rx + R[3] * ry + R[6] * rz);
-      u[3 * li + 1] = wt * (R[1] * rx + R[4] * ry + R[7] * rz);
-      u[3 * li + 2] = wt * (R[2] * rx + R[5] * ry + R[8] * rz);
+      const double q0 = R[0] * rx + R[3] * ry + R[6] * rz, q1 = R[1] * rx + R[4] * ry + R[7] * rz,
+                   q2 = R[2] * rx + R[5] * ry + R[8] * rz;
+      u[3 * li] = wt * q0;
+      u[3 * li + 1] = wt * q1;
+      u[3 * li + 2] = wt * q2;
+      if (resid) { resid[3 * li] = q0; resid[3 * li + 1] = q1; resid[3 * li + 2] = q2; }   // the Gram applies the weight itself
     }
   }
   // block sums (fixed order)
@@ -682,7 +686,7 @@ struct gingr_registration {
   bool skip_fit_refresh = false;        // MH step: the proposal's fit is evaluated after the random override
   const int* sample_counter = nullptr;  // device counter keyed into the posterior-sample stream (null: the iteration)
   struct McmcState* mcmc = nullptr;  // Metropolis-Hastings chain state (mcmc.cuh), created by gingr_mcmc_configure
-  DevBuf<double> wrow, u, inst_a, inst_b, newshape, fit_local, gathered, fit;
+  DevBuf<double> wrow, u, resid, inst_a, inst_b, newshape, fit_local, gathered, fit;
   DevBuf<double> vec;          // 8 * rp scratch vectors
   DevBuf<double> gt_part, sums_part, pro_part, pro_sums;
   DevBuf<double> ds;
@@ -1342,7 +1346,7 @@ int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, cons
   A(g->rows_ext.alloc((size_t)4 * M + 8));
   A(g->Mx.alloc((size_t)(r + 8) * rp));
   if (ctx->nranks > 1) A(g->Mx_packed.alloc(gram_packed_doubles(g->gram) + rp));
-  A(g->wrow.alloc((size_t)3 * Mmax)); A(g->u.alloc((size_t)3 * Mmax));
+  A(g->wrow.alloc((size_t)3 * Mmax)); A(g->u.alloc((size_t)3 * Mmax)); A(g->resid.alloc((size_t)3 * Mmax));
   A(g->inst_a.alloc((size_t)3 * Mmax)); A(g->inst_b.alloc((size_t)3 * Mmax));
   A(g->newshape.alloc((size_t)3 * Mmax)); A(g->fit_local.alloc((size_t)3 * Mmax));
   A(g->gathered.alloc((size_t)3 * Mmax * ctx->nranks)); A(g->fit.alloc((size_t)3 * M));
@@ -1386,7 +1390,7 @@ int32_t gingr_registration_destroy(gingr_registration* g) {
   g->estep.release(); g->closest.release(); g->gram.release();
   g->fit_pgrid.release(); g->fit_tgrid.release();
   g->fit_normals.release(); g->fit_soa.release(); g->rev_tid.release(); g->rev_cp.release(); g->rev_wcnt.release(); g->rev_scratch.release();
-  g->rows_ext.release(); g->Mx.release(); g->wrow.release(); g->u.release(); g->inst_a.release(); g->inst_b.release();
+  g->rows_ext.release(); g->Mx.release(); g->wrow.release(); g->u.release(); g->resid.release(); g->inst_a.release(); g->inst_b.release();
   g->newshape.release(); g->fit_local.release(); g->gathered.release(); g->fit.release(); g->vec.release();
   g->gt_part.release(); g->sums_part.release(); g->pro_part.release(); g->pro_sums.release();
   g->ds.release(); g->is.release(); g->flags.release(); g->alpha.release(); g->cholws.release();
@@ -1586,8 +1590,14 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
   oa.algo = cfg.algorithm; oa.M = M; oa.m0 = m0; oa.Ml = Ml; oa.use_lm = cfg.use_landmark_correspondence && g->L > 0;
   oa.L = g->L; oa.lambda = cfg.lambda;
   const int oblocks = ceil_div(M, 256);
+  // the right-hand side D Phi^T W resid rides along in the Gram (no pass of its own over Phi) unless landmarks add their
+  // own terms to it or the rank is a multiple of the tile edge (no spare column in the last tile row)
+  const bool use_lm = cfg.use_landmark_correspondence && g->Ll > 0;
+  const bool any_lm = cfg.use_landmark_correspondence && g->L > 0;
+  const bool rhs_fused = !any_lm && gram_rhs_fusable(g->gram);
   obs_kernel<<<oblocks, 256, 0, st>>>(oa, g->rows_ext.p, icp_cp, g->closest.w.p, icp_wcnt, g->fit.p, m->ref.p, m->mean.p,
-                                      g->lm_pid.p, g->ds.p, g->is.p, g->wrow.p, g->u.p, g->sums_part.p);
+                                      g->lm_pid.p, g->ds.p, g->is.p, g->wrow.p, g->u.p, g->sums_part.p,
+                                      rhs_fused ? g->resid.p : nullptr);
   GINGR_LAUNCHED(ctx);
   const double sigma_step = cfg.algorithm == GINGR_ALGO_ICP ? (cfg.initial_sigma - cfg.end_sigma) / (double)cfg.max_iterations : 0.0;
   sigma2_kernel<<<1, 32, 0, st>>>(cfg.algorithm, oblocks, g->sums_part.p, g->rows_ext.p + (size_t)4 * M, sigma_step,
@@ -1599,8 +1609,7 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
   const bool packed = ctx->nranks > 1;
   const size_t packed_n = packed ? gram_packed_doubles(g->gram) : 0;
   double* rhs = packed ? g->Mx_packed.p + packed_n : g->Mx.p + (size_t)r * rp;
-  GINGR_TRY(gemvT_enqueue(ctx, 3 * Ml, r, rp, m->phi.p, g->u.p, m->sqrt_lambda.p, g->gt_part.p, rhs));
-  const bool use_lm = cfg.use_landmark_correspondence && g->Ll > 0;
+  if (!rhs_fused) GINGR_TRY(gemvT_enqueue(ctx, 3 * Ml, r, rp, m->phi.p, g->u.p, m->sqrt_lambda.p, g->gt_part.p, rhs));
   if (use_lm) {
     landmark_prepare_kernel<<<ceil_div(g->Ll, 64), 64, 0, st>>>(g->Ll, g->lml_cinv.p, g->ds.p, g->lml_A.p);
     landmark_rhs_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, rp, g->Ll, g->lml_pid.p, g->lml_pts.p, g->lml_A.p, g->lml_rows.p,
@@ -1608,17 +1617,18 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
     ctx->launches += 2;
   }
   GINGR_TRY(gram_partials_enqueue(ctx, g->gram, m->phi.p, g->wrow.p, g->ev(6) ? *g->ev(6) : nullptr,
-                                  g->ev(7) ? *g->ev(7) : nullptr));
+                                  g->ev(7) ? *g->ev(7) : nullptr, rhs_fused ? g->resid.p : nullptr));
   if (packed) {
     GINGR_TRY(gram_finish_enqueue(ctx, g->gram, g->gram.d_partial.p, m->sqrt_lambda.p, ctx->rank == 0 ? 1.0 : 0.0,
-                                  use_lm ? g->Ll : 0, g->lml_rows.p, g->lml_A.p, rp, g->Mx_packed.p, true));
-    GINGR_TRY(comm_allreduce_sum(ctx, g->Mx_packed.p, packed_n + (size_t)r));
-    GINGR_TRY(gram_unpack_enqueue(ctx, g->gram, g->Mx_packed.p, rp, g->Mx.p));
-    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->Mx.p + (size_t)r * rp, rhs, sizeof(double) * r, cudaMemcpyDeviceToDevice, st));
+                                  use_lm ? g->Ll : 0, g->lml_rows.p, g->lml_A.p, rp, g->Mx_packed.p, true, false, rhs_fused));
+    GINGR_TRY(comm_allreduce_sum(ctx, g->Mx_packed.p, packed_n + (rhs_fused ? 0 : (size_t)r)));
+    GINGR_TRY(gram_unpack_enqueue(ctx, g->gram, g->Mx_packed.p, rp, g->Mx.p, rhs_fused));
+    if (!rhs_fused)
+      GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->Mx.p + (size_t)r * rp, rhs, sizeof(double) * r, cudaMemcpyDeviceToDevice, st));
   } else {
     // the upper triangle is only read from the kept copy of the MH chain (mcmc.cuh: dense products with the raw matrix)
     GINGR_TRY(gram_finish_enqueue(ctx, g->gram, g->gram.d_partial.p, m->sqrt_lambda.p, 1.0, use_lm ? g->Ll : 0, g->lml_rows.p,
-                                  g->lml_A.p, rp, g->Mx.p, false, !g->keep_raw));
+                                  g->lml_A.p, rp, g->Mx.p, false, !g->keep_raw, rhs_fused));
   }
   if (g->keep_raw)
     GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->Mx_raw.p, g->Mx.p, sizeof(double) * (size_t)(r + 1) * rp, cudaMemcpyDeviceToDevice, st));
