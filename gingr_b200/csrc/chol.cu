@@ -16,7 +16,7 @@
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "batch.cuh"
 #include "posterior.cuh"
 
 namespace gingr {
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(int n, const double
 
 // n <= 64 (one block): plain right-looking back substitution by 64 threads -- the general kernel would spend 50 us
 // inverting the diagonal block with one thread per column, which only pays when it hides behind the flag waits.
-__global__ void __launch_bounds__(32) chol_backsolve_small_kernel(int n, const double* __restrict__ L, int ld,
+GINGR_KERNEL((32), chol_backsolve_small_kernel, int n, const double* __restrict__ L, int ld,
                                                                   const double* __restrict__ z, double* __restrict__ c) {
   __shared__ double sLs[NB * SP];
   __shared__ double sinv[NB];
@@ -462,7 +462,7 @@ int32_t chol_backsolve_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld,
   static const int env_df = [] { const char* e = getenv("GINGR_CHOL_DF"); return e ? atoi(e) : 1; }();
   if (ws != nullptr && env_df != 0 && nb > 1) return chol_backsolve_z_enqueue(ctx, n, d_L, ld, d_z, d_c, *ws);
   if (nb == 1) {
-    chol_backsolve_small_kernel<<<1, 32, 0, ctx->stream>>>(n, d_L, ld, d_z, d_c);
+    GINGR_LAUNCH(ctx, chol_backsolve_small_kernel, 1, 32, 0, ctx->stream, n, d_L, ld, d_z, d_c);
     GINGR_LAUNCHED(ctx);
     GINGR_CUDA_TRY(ctx, cudaGetLastError());
     return GINGR_OK;

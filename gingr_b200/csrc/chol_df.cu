@@ -25,7 +25,7 @@
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "batch.cuh"
 #include "posterior.cuh"
 
 namespace gingr {
@@ -166,7 +166,7 @@ __device__ __forceinline__ void mma_tile_lower(double (&acc)[2][4][2], const dou
 
 #include "chol_potrf.cuh"
 
-__global__ void __launch_bounds__(DF_THREADS, 1) chol_df_kernel(DfParams P) {
+GINGR_KERNEL((DF_THREADS, 1), chol_df_kernel, DfParams P) {
   extern __shared__ __align__(16) double dsm[];
   double* bufI0 = dsm;                       // stage 0, row operand    | X_{j,j-1} of a diagonal task
   double* bufK0 = dsm + TILE_DOUBLES;        // stage 0, column operand | Z of the finishing product
@@ -531,7 +531,7 @@ int32_t cholesky_df_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int l
   P.linv = ws.linv.p;
   P.info = d_info;
   const int grid = std::min(P.ntasks, ctx->num_sms);
-  chol_df_kernel<<<grid, DF_THREADS, DF_SMEM, ctx->stream>>>(P);
+  GINGR_LAUNCH(ctx, chol_df_kernel, grid, DF_THREADS, DF_SMEM, ctx->stream, P);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

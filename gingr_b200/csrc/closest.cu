@@ -18,7 +18,7 @@
 
 #include "closest.cuh"
 #include "closest_geom.cuh"
-#include "common.cuh"
+#include "batch.cuh"
 #include "grid.cuh"
 
 namespace gingr {
@@ -30,7 +30,7 @@ constexpr int TT = 64;     // candidate triangles per shared-memory tile
 // ---------------------------------------------------------------------------------------------
 // nearest vertex
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(QT) nn_vertex_kernel(int M, const double* __restrict__ q /*AoS [M][3]*/, int N,
+GINGR_KERNEL((QT), nn_vertex_kernel, int M, const double* __restrict__ q /*AoS [M][3]*/, int N,
                                                        const double* __restrict__ pts /*SoA [3][N]*/,
                                                        double* __restrict__ part_d2, int32_t* __restrict__ part_idx) {
   __shared__ double sx[PT], sy[PT], sz[PT];
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(QT) nn_vertex_kernel(int M, const double* __re
   }
 }
 
-__global__ void nn_reduce_kernel(int M, int splits, const double* __restrict__ part_d2,
+GINGR_KERNEL_NB(nn_reduce_kernel, int M, int splits, const double* __restrict__ part_d2,
                                  const int32_t* __restrict__ part_idx, double* __restrict__ d2,
                                  int32_t* __restrict__ idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,7 +85,7 @@ __global__ void nn_reduce_kernel(int M, int splits, const double* __restrict__ p
 }
 
 // part: [splits][M] d2, tri ; [splits][M][3] cp
-__global__ void __launch_bounds__(QT) surface_kernel(int M, const double* __restrict__ q, int N,
+GINGR_KERNEL((QT), surface_kernel, int M, const double* __restrict__ q, int N,
                                                      const double* __restrict__ verts /*SoA [3][N]*/, int T,
                                                      const int32_t* __restrict__ tri, double* __restrict__ part_d2,
                                                      int32_t* __restrict__ part_tri, double* __restrict__ part_cp) {
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(QT) surface_kernel(int M, const double* __rest
   }
 }
 
-__global__ void surface_reduce_kernel(int M, int splits, const double* __restrict__ part_d2,
+GINGR_KERNEL_NB(surface_reduce_kernel, int M, int splits, const double* __restrict__ part_d2,
                                       const int32_t* __restrict__ part_tri, const double* __restrict__ part_cp,
                                       double* __restrict__ d2, int32_t* __restrict__ tri_out,
                                       double* __restrict__ cp) {
@@ -154,13 +154,11 @@ __global__ void surface_reduce_kernel(int M, int splits, const double* __restric
 //                                         the hit point itself is needed (WITH_POINT = true)
 // DIFF = true: the direction is o - other[i] (computed in registers), else other[i] is the direction.
 // ---------------------------------------------------------------------------------------------
-template <bool SELF, bool DIFF, bool WITH_POINT>
-__global__ void __launch_bounds__(QT) line_mesh_kernel(int M, const double* __restrict__ o /*AoS*/,
-                                                       const double* __restrict__ other /*AoS*/,
-                                                       const double* __restrict__ mesh /*AoS vertices*/, int T,
-                                                       const int32_t* __restrict__ tri,
-                                                       double* __restrict__ part_min, double* __restrict__ part_pt,
-                                                       int q0 = 0 /*vertex id of query 0 (SELF: a query range of the mesh)*/) {
+GINGR_KERNEL_T((bool SELF, bool DIFF, bool WITH_POINT), (SELF, DIFF, WITH_POINT), (QT), line_mesh_kernel, int M,
+               const double* __restrict__ o /*AoS*/, const double* __restrict__ other /*AoS*/,
+               const double* __restrict__ mesh /*AoS vertices*/, int T, const int32_t* __restrict__ tri,
+               double* __restrict__ part_min, double* __restrict__ part_pt,
+               int q0 /*vertex id of query 0 (SELF: a query range of the mesh)*/) {
   __shared__ double st[TT][9];
   __shared__ int32_t sv[TT][3];
   const int i = blockIdx.x * QT + threadIdx.x;
@@ -204,7 +202,7 @@ __global__ void __launch_bounds__(QT) line_mesh_kernel(int M, const double* __re
 
 // nearest hit over the triangle-range splits (lowest range first on ties); no hit: dist = 0, point = o, hit = 0
 // (ClosestPointRegistrator.scala:127 "return p to avoid influencing the distance measure")
-__global__ void line_hit_reduce_kernel(int M, int splits, const double* __restrict__ o,
+GINGR_KERNEL_NB(line_hit_reduce_kernel, int M, int splits, const double* __restrict__ o,
                                        const double* __restrict__ part_min, const double* __restrict__ part_pt,
                                        double* __restrict__ dist, double* __restrict__ pt, uint8_t* __restrict__ hit) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,7 +229,7 @@ __global__ void line_hit_reduce_kernel(int M, int splits, const double* __restri
 // vertex normals from a CSR vertex -> triangle adjacency (ascending triangle ids = the accumulation
 // order of a triangle-ordered scatter).  verts AoS [n][3]; normals AoS [n][3].   SURVEY.md A6
 // ---------------------------------------------------------------------------------------------
-__global__ void vertex_normals_kernel(int n, const double* __restrict__ v, const int32_t* __restrict__ tri,
+GINGR_KERNEL_NB(vertex_normals_kernel, int n, const double* __restrict__ v, const int32_t* __restrict__ tri,
                                       const int32_t* __restrict__ adj_off, const int32_t* __restrict__ adj,
                                       double* __restrict__ normals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,7 +258,7 @@ __global__ void vertex_normals_kernel(int n, const double* __restrict__ v, const
 
 // w = 0 if target vertex on boundary, else 0 if normals opposite, else 0 if intersecting, else 1
 // (ClosestPointRegistrator.scala:84-90).  min_part: [splits][M]
-__global__ void icp_weights_kernel(int M, const double* __restrict__ p, const double* __restrict__ cp,
+GINGR_KERNEL_NB(icp_weights_kernel, int M, const double* __restrict__ p, const double* __restrict__ cp,
                                    const int32_t* __restrict__ idx, const uint8_t* __restrict__ tgt_boundary,
                                    const double* __restrict__ n_tpl /*AoS*/, const double* __restrict__ n_tgt /*AoS*/,
                                    int splits, const double* __restrict__ min_part,
@@ -287,7 +285,7 @@ __global__ void icp_weights_kernel(int M, const double* __restrict__ p, const do
   w[i] = out;
 }
 
-__global__ void gather_points_kernel(int M, const int32_t* __restrict__ idx, int N, const double* __restrict__ soa,
+GINGR_KERNEL_NB(gather_points_kernel, int M, const int32_t* __restrict__ idx, int N, const double* __restrict__ soa,
                                      double* __restrict__ out /*AoS*/) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
@@ -300,7 +298,7 @@ __global__ void gather_points_kernel(int M, const int32_t* __restrict__ idx, int
 // deterministic mean of sqrt(d2) (squared = 1) or of d2 itself (squared = 0): fixed-order tree per block; large
 // inputs use MEAN_BLOCKS blocks whose partial sums the last stage adds in block order
 constexpr int MEAN_BLOCKS = 64;
-__global__ void __launch_bounds__(256) mean_sqrt_kernel(int M, const double* __restrict__ d2, double* __restrict__ out,
+GINGR_KERNEL((256), mean_sqrt_kernel, int M, const double* __restrict__ d2, double* __restrict__ out,
                                                         int squared, int final_stage) {
   __shared__ double red[256];
   double s = 0.0;
@@ -323,12 +321,12 @@ static void mean_sqrt_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, int s
   if (!d_d2) d_d2 = ws.d2.p;
   if (M <= 0) return;
   if (M <= 16384) {
-    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, d_d2, ws.mean_dist.p, squared, 1);
+    GINGR_LAUNCH(ctx, mean_sqrt_kernel, 1, 256, 0, st, M, d_d2, ws.mean_dist.p, squared, 1);
     GINGR_LAUNCHED(ctx);
   } else {
-    mean_sqrt_kernel<<<MEAN_BLOCKS, 256, 0, st>>>(M, d_d2, ws.mean_part.p, squared, 0);
+    GINGR_LAUNCH(ctx, mean_sqrt_kernel, MEAN_BLOCKS, 256, 0, st, M, d_d2, ws.mean_part.p, squared, 0);
     GINGR_LAUNCHED(ctx);
-    mean_sqrt_kernel<<<1, 256, 0, st>>>(M, ws.mean_part.p, ws.mean_dist.p, 0, 2);
+    GINGR_LAUNCH(ctx, mean_sqrt_kernel, 1, 256, 0, st, M, ws.mean_part.p, ws.mean_dist.p, 0, 2);
     GINGR_LAUNCHED(ctx);
   }
 }
@@ -371,7 +369,7 @@ void compute_boundary_flags(int n, int T, const int32_t* tri, std::vector<uint8_
 
 int32_t vertex_normals_enqueue(gingr_ctx* ctx, int n, const double* d_verts_aos, const int32_t* d_tri,
                                const int32_t* d_adj_off, const int32_t* d_adj, double* d_normals) {
-  vertex_normals_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(n, d_verts_aos, d_tri, d_adj_off, d_adj, d_normals);
+  GINGR_LAUNCH(ctx, vertex_normals_kernel, ceil_div(n, 128), 128, 0, ctx->stream, n, d_verts_aos, d_tri, d_adj_off, d_adj, d_normals);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
@@ -461,10 +459,10 @@ int32_t nn_vertex_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int M, const dou
                           const SpatialGrid* order) {
   if (pgrid && pgrid->built) return grid_nn_enqueue(ctx, *pgrid, M, d_q, d_d2, d_idx, order);
   const int splits = std::min(ws.s_nn, std::max(1, ceil_div(N, PT / 4)));
-  nn_vertex_kernel<<<dim3(ceil_div(M, QT), splits), QT, 0, ctx->stream>>>(M, d_q, N, d_pts_soa, ws.part_d2.p,
+  GINGR_LAUNCH(ctx, nn_vertex_kernel, dim3(ceil_div(M, QT), splits), QT, 0, ctx->stream, M, d_q, N, d_pts_soa, ws.part_d2.p,
                                                                           ws.part_idx.p);
   GINGR_LAUNCHED(ctx);
-  nn_reduce_kernel<<<ceil_div(M, 128), 128, 0, ctx->stream>>>(M, splits, ws.part_d2.p, ws.part_idx.p, d_d2, d_idx);
+  GINGR_LAUNCH(ctx, nn_reduce_kernel, ceil_div(M, 128), 128, 0, ctx->stream, M, splits, ws.part_d2.p, ws.part_idx.p, d_d2, d_idx);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
@@ -501,9 +499,9 @@ int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const M
   }
   if (method == GINGR_POINTCLOUD_CLOSEST_POINT) {
     GINGR_TRY(nn_vertex_enqueue(ctx, ws, M, q_aos, N, tgt.soa, o_d2, o_idx, tgt.pgrid, order));
-    gather_points_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, o_idx, N, tgt.soa, o_cp);
+    GINGR_LAUNCH(ctx, gather_points_kernel, ceil_div(M, 128), 128, 0, st, M, o_idx, N, tgt.soa, o_cp);
     GINGR_LAUNCHED(ctx);
-    GINGR_CUDA_TRY(ctx, cudaMemsetAsync(o_w, 1, (size_t)M, st));
+    GINGR_CUDA_TRY(ctx, gingr_fill_bytes(ctx, o_w, 1, (size_t)M, st));
     mean_sqrt_enqueue(ctx, ws, M, 1, o_d2);
     GINGR_CUDA_TRY(ctx, cudaGetLastError());
     return GINGR_OK;
@@ -519,24 +517,24 @@ int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const M
   } else if (method == GINGR_ALONG_NORMAL_CLOSEST_POINT && tgt_grid) {
     GINGR_TRY(grid_line_enqueue(ctx, *tgt.tgrid, M, q_aos, q_nrm, tgt.aos, tgt.tri, 0, ws.part_d2.p, ws.part_cp.p,
                                 order));
-    line_hit_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, 1, q_aos, ws.part_d2.p, ws.part_cp.p, o_d2, o_cp, o_hit);
+    GINGR_LAUNCH(ctx, line_hit_reduce_kernel, ceil_div(M, 128), 128, 0, st, M, 1, q_aos, ws.part_d2.p, ws.part_cp.p, o_d2, o_cp, o_hit);
     GINGR_LAUNCHED(ctx);
     mean_sqrt_enqueue(ctx, ws, M, 0, o_d2);  // distance += (p - closestPoint).norm (:128)
   } else if (method == GINGR_TRIANGULAR_CLOSEST_POINT) {
-    surface_kernel<<<dim3(ceil_div(M, QT), s_surf), QT, 0, st>>>(M, q_aos, N, tgt.soa, tgt.T, tgt.tri, ws.part_d2.p,
+    GINGR_LAUNCH(ctx, surface_kernel, dim3(ceil_div(M, QT), s_surf), QT, 0, st, M, q_aos, N, tgt.soa, tgt.T, tgt.tri, ws.part_d2.p,
                                                                  ws.part_idx.p, ws.part_cp.p);
     GINGR_LAUNCHED(ctx);
-    surface_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, s_surf, ws.part_d2.p, ws.part_idx.p, ws.part_cp.p,
+    GINGR_LAUNCH(ctx, surface_reduce_kernel, ceil_div(M, 128), 128, 0, st, M, s_surf, ws.part_d2.p, ws.part_idx.p, ws.part_cp.p,
                                                             o_d2, nullptr, o_cp);
     GINGR_LAUNCHED(ctx);
     mean_sqrt_enqueue(ctx, ws, M, 1, o_d2);
   } else if (method == GINGR_ALONG_NORMAL_CLOSEST_POINT) {
     // nearest intersection of the line (p, n_p) with the target mesh (:105-110)
     const int s_hit = s_surf;
-    line_mesh_kernel<false, false, true><<<dim3(ceil_div(M, QT), s_hit), QT, 0, st>>>(
-        M, q_aos, q_nrm, tgt.aos, tgt.T, tgt.tri, ws.part_d2.p, ws.part_cp.p);
+    GINGR_LAUNCH_T(ctx, line_mesh_kernel, (false, false, true), dim3(ceil_div(M, QT), s_hit), QT, 0, st, M, q_aos, q_nrm, tgt.aos,
+                   tgt.T, tgt.tri, ws.part_d2.p, ws.part_cp.p, 0);
     GINGR_LAUNCHED(ctx);
-    line_hit_reduce_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, s_hit, q_aos, ws.part_d2.p, ws.part_cp.p, o_d2, o_cp, o_hit);
+    GINGR_LAUNCH(ctx, line_hit_reduce_kernel, ceil_div(M, 128), 128, 0, st, M, s_hit, q_aos, ws.part_d2.p, ws.part_cp.p, o_d2, o_cp, o_hit);
     GINGR_LAUNCHED(ctx);
     mean_sqrt_enqueue(ctx, ws, M, 0, o_d2);  // distance += (p - closestPoint).norm (:128)
   } else {
@@ -549,11 +547,11 @@ int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const M
     GINGR_TRY(grid_line_enqueue(ctx, *tpl.tgrid, M, q_aos, o_cp, tpl.aos, tpl.tri, 1, ws.part_d2.p, nullptr, order, q0));
     s_line = 1;
   } else {
-    line_mesh_kernel<true, true, false><<<dim3(ceil_div(M, QT), s_line), QT, 0, st>>>(M, q_aos, o_cp, tpl.aos, tpl.T,
-                                                                                     tpl.tri, ws.part_d2.p, nullptr, q0);
+    GINGR_LAUNCH_T(ctx, line_mesh_kernel, (true, true, false), dim3(ceil_div(M, QT), s_line), QT, 0, st, M, q_aos, o_cp, tpl.aos,
+                   tpl.T, tpl.tri, ws.part_d2.p, nullptr, q0);
     GINGR_LAUNCHED(ctx);
   }
-  icp_weights_kernel<<<ceil_div(M, 128), 128, 0, st>>>(M, q_aos, o_cp, o_idx, tgt.boundary, q_nrm, tgt.normals, s_line,
+  GINGR_LAUNCH(ctx, icp_weights_kernel, ceil_div(M, 128), 128, 0, st, M, q_aos, o_cp, o_idx, tgt.boundary, q_nrm, tgt.normals, s_line,
                                                        ws.part_d2.p,
                                                        method == GINGR_ALONG_NORMAL_CLOSEST_POINT ? o_hit : nullptr, o_w);
   GINGR_LAUNCHED(ctx);
@@ -573,10 +571,10 @@ int32_t surface_distance_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int nq, c
     return GINGR_OK;
   }
   const int s_surf = std::min(ws.s_surf, std::max(1, ceil_div(mesh.T, TT / 4)));
-  surface_kernel<<<dim3(ceil_div(nq, QT), s_surf), QT, 0, st>>>(nq, d_q, mesh.n, mesh.soa, mesh.T, mesh.tri, ws.part_d2.p,
+  GINGR_LAUNCH(ctx, surface_kernel, dim3(ceil_div(nq, QT), s_surf), QT, 0, st, nq, d_q, mesh.n, mesh.soa, mesh.T, mesh.tri, ws.part_d2.p,
                                                                 ws.part_idx.p, ws.part_cp.p);
   GINGR_LAUNCHED(ctx);
-  surface_reduce_kernel<<<ceil_div(nq, 128), 128, 0, st>>>(nq, s_surf, ws.part_d2.p, ws.part_idx.p, ws.part_cp.p, ws.d2.p,
+  GINGR_LAUNCH(ctx, surface_reduce_kernel, ceil_div(nq, 128), 128, 0, st, nq, s_surf, ws.part_d2.p, ws.part_idx.p, ws.part_cp.p, ws.d2.p,
                                                            nullptr, ws.cp.p);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());

@@ -11,6 +11,7 @@
 #define GINGR_NUM_SMS_B200 148
 
 struct NcclApi;  // nccl_dl.cu
+struct LaunchRecorder;  // batch.cuh
 namespace gingr { struct SpatialGrid; }  // grid.cuh
 
 struct gingr_ctx {
@@ -21,6 +22,7 @@ struct gingr_ctx {
   std::vector<cudaEvent_t> chol_events;  // 2 per block step, created on first use
   std::string last_error;
   int64_t launches = 0;
+  LaunchRecorder* rec = nullptr;       // while set, batch-aware launches are recorded instead of issued (batch.cuh)
   // multi-GPU
   int nranks = 1, rank = 0;
   void* nccl_comm = nullptr;

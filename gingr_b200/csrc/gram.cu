@@ -25,7 +25,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
+#include "batch.cuh"
 #include "posterior.cuh"
 
 namespace gingr {
@@ -211,7 +211,7 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(GRAM_WS_THREADS, 1) gram_ws_kernel(int rows, int rp, const double* __restrict__ phi,
+GINGR_KERNEL((GRAM_WS_THREADS, 1), gram_ws_kernel, int rows, int rp, const double* __restrict__ phi,
                                                                      const double* __restrict__ wrow,
                                                                      const double* __restrict__ resid, int r,
                                                                      const GramSegment* __restrict__ segs,
@@ -335,22 +335,23 @@ __global__ void __launch_bounds__(GRAM_WS_THREADS, 1) gram_ws_kernel(int rows, i
 // Sum the partial tiles in slot order and emit  out = add_identity * I + D (G + LM) D  (both triangles).
 // tile_first[t] .. tile_first[t+1] are the slots of lower-triangular tile t (t = ta (ta+1)/2 + tb).
 // Landmark term: LM[a][b] = sum_l sum_{d,e} phi_l[d][a] A_l[d][e] phi_l[e][b]  with lm_rows [L][3][rp], lm_A [L][9].
-__global__ void __launch_bounds__(256) gram_finish_kernel(int r, int rp, int ld_out, const double* __restrict__ partial,
+GINGR_KERNEL((256), gram_finish_kernel, int r, int rp, int ld_out, const double* __restrict__ partial,
                                                           const int* __restrict__ tile_first,
                                                           const double* __restrict__ sqrt_lambda,
                                                           double add_identity, int L,
                                                           const double* __restrict__ lm_rows,
                                                           const double* __restrict__ lm_A, double* __restrict__ out,
                                                           int packed /*1: packed lower tiles, 2: matrix without the mirror*/,
-                                                          int rhs_row /*1: row rp of the last tile row holds Phi^T W resid*/) {
-  const int ta = blockIdx.y, tb = blockIdx.x;
+                                                          int rhs_row /*1: row rp of the last tile row holds Phi^T W resid*/,
+             int nt, int slices /*grid (nt, nt * slices): blockIdx.z is left to the batched form (batch.cuh)*/) {
+  const int ta = blockIdx.y % nt, tb = blockIdx.x, slice = blockIdx.y / nt;
   if (tb > ta) return;
   const int tile = ta * (ta + 1) / 2 + tb;
   const int s0 = tile_first[tile], s1 = tile_first[tile + 1];
-  if (rhs_row && ta == (int)gridDim.y - 1) {
+  if (rhs_row && ta == nt - 1) {
     // the rhs that rode along (gram_ws_kernel): out[r][b] = sqrt_lambda[b] * sum of the partials, no identity, no mirror
     const int row = rp - ta * BT;
-    for (int col = blockIdx.z * 256 + threadIdx.x; col < BT; col += 256 * gridDim.z) {
+    for (int col = slice * 256 + threadIdx.x; col < BT; col += 256 * slices) {
       const int b = tb * BT + col, e = row * BT + col;
       if (b >= r) continue;
       double s = 0.0;
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(256) gram_finish_kernel(int r, int rp, int ld_
   }
   // blockIdx.z slices the elements of the tile: a small matrix has few tiles and would otherwise be finished by a
   // handful of latency-bound CTAs
-  for (int e = blockIdx.z * 256 + threadIdx.x; e < BT * BT; e += 256 * gridDim.z) {
+  for (int e = slice * 256 + threadIdx.x; e < BT * BT; e += 256 * slices) {
     const int row = e / BT, col = e % BT;
     const int a = ta * BT + row, b = tb * BT + col;
     if (a >= r || b >= r || b > a) continue;
@@ -391,14 +392,14 @@ __global__ void __launch_bounds__(256) gram_finish_kernel(int r, int rp, int ld_
 // ---------------------------------------------------------------------------------------------
 // host side: static stream-K schedule
 // ---------------------------------------------------------------------------------------------
-int32_t GramPlan::build(gingr_ctx* ctx, int rows_, int r_, int rp_) {
+int32_t GramPlan::build(gingr_ctx* ctx, int rows_, int r_, int rp_, int max_cta) {
   rows = rows_;
   r = r_;
   rp = rp_;
   nt = ceil_div(r, BT);
   ntiles = nt * (nt + 1) / 2;
   nchunks = std::max(1, ceil_div(rows, BK));
-  ncta = ctx->num_sms;
+  ncta = max_cta > 0 ? std::min(ctx->num_sms, max_cta) : ctx->num_sms;
   const int n = ncta, K = nchunks;
   std::vector<std::pair<int, int>> tile_ab(ntiles);
   for (int a = 0, k = 0; a < nt; ++a)
@@ -502,7 +503,7 @@ int32_t gram_partials_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_ph
   if (plan.rows > 0 && plan.nsegs > 0) {
     static const int use_ws = [] { const char* e = getenv("GINGR_GRAM_WS"); return e ? atoi(e) : 1; }();
     if (use_ws && GRAM_WARPS_M == 2)
-      gram_ws_kernel<<<plan.ncta, GRAM_WS_THREADS, GRAM_WS_SMEM, ctx->stream>>>(
+      GINGR_LAUNCH(ctx, gram_ws_kernel, plan.ncta, GRAM_WS_THREADS, GRAM_WS_SMEM, ctx->stream, 
           plan.rows, plan.rp, d_phi, d_wrow, d_resid, plan.r, reinterpret_cast<const GramSegment*>(plan.d_segs.p), plan.d_seg_begin.p,
           plan.d_partial.p);
     else
@@ -556,10 +557,10 @@ int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_part
                             double* d_out, bool packed, bool lower_only, bool rhs_row) {
   const int tiles = plan.nt * (plan.nt + 1) / 2;
   const int slices = std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
-  gram_finish_kernel<<<dim3(plan.nt, plan.nt, slices), 256, 0, ctx->stream>>>(plan.r, plan.rp, ld_out, d_partial,
+  GINGR_LAUNCH(ctx, gram_finish_kernel, dim3(plan.nt, plan.nt * slices), 256, 0, ctx->stream, plan.r, plan.rp, ld_out, d_partial,
                                                                       plan.d_tile_first.p, d_sqrt_lambda, add_identity,
                                                                       L, d_lm_rows, d_lm_A, d_out, packed ? 1 : (lower_only ? 2 : 0),
-                                                                      rhs_row ? 1 : 0);
+                                                                      rhs_row ? 1 : 0, plan.nt, slices);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

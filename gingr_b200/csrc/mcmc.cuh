@@ -98,7 +98,7 @@ __device__ void mcmc_choose(const McmcDev& p, uint64_t seed, int* __restrict__ m
 
 // the chosen random leaf replaces the informed proposal: all parameters of the current state (snapshot) with one
 // Gaussian perturbation; sigma2 and status are those of the current state (the random generators do not touch them)
-__global__ void __launch_bounds__(256) mcmc_random_override_kernel(McmcDev p, uint64_t seed, int r, const int* __restrict__ mi,
+GINGR_KERNEL((256), mcmc_random_override_kernel, McmcDev p, uint64_t seed, int r, const int* __restrict__ mi,
                                                                    const double* __restrict__ s_ds, const int* __restrict__ s_is,
                                                                    const double* __restrict__ s_alpha, double* __restrict__ ds,
                                                                    int* __restrict__ is, double* __restrict__ alpha,
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) mcmc_random_override_kernel(McmcDev p, ui
 }
 
 // ---- evaluators ---------------------------------------------------------------------------------------------
-__global__ void gather_aos_kernel(int n, const int32_t* __restrict__ ids, const double* __restrict__ src, double* __restrict__ dst) {
+GINGR_KERNEL_NB(gather_aos_kernel, int n, const int32_t* __restrict__ ids, const double* __restrict__ src, double* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int j = ids ? ids[i] : i;
@@ -140,7 +140,7 @@ __global__ void gather_aos_kernel(int n, const int32_t* __restrict__ ids, const 
 
 // sum_i logPdf_{N(0, sd)}(sqrt(d2_i)) = sum_i (-d2_i / (2 sd^2) - log(sd sqrt(2 pi)))   (Breeze Gaussian.logPdf);
 // one block, fixed-order tree; out[0] (accumulate ? += : =) weight * sum
-__global__ void __launch_bounds__(256) mcmc_distance_logpdf_kernel(int n, const double* __restrict__ d2, double sd, double weight,
+GINGR_KERNEL((256), mcmc_distance_logpdf_kernel, int n, const double* __restrict__ d2, double sd, double weight,
                                                                    int accumulate, double* __restrict__ out, int r,
                                                                    const double* __restrict__ alpha /*null: no prior*/) {
   __shared__ double red[256];
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) mcmc_distance_logpdf_kernel(int n, const 
 
 // ---- informed transition density ---------------------------------------------------------------------------------
 // u_i = R^T (mesh_i - t) - ref_i - mean_i     (residual of `mesh` against the posed model mean, rotated back)
-__global__ void mcmc_residual_kernel(int M, const double* __restrict__ mesh, const double* __restrict__ ref,
+GINGR_KERNEL_NB(mcmc_residual_kernel, int M, const double* __restrict__ mesh, const double* __restrict__ ref,
                                      const double* __restrict__ mean, const double* __restrict__ R, const double* __restrict__ t,
                                      double* __restrict__ u) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,7 +185,7 @@ __global__ void mcmc_residual_kernel(int M, const double* __restrict__ mesh, con
 }
 
 // B[a][b] = S[a][b] + eps * Mx[a][b] (a, b < r);  row r: rhs = b_proj - S c
-__global__ void mcmc_build_system_kernel(int r, int rp, const double* __restrict__ S, const double* __restrict__ Mx, double eps,
+GINGR_KERNEL_NB(mcmc_build_system_kernel, int r, int rp, const double* __restrict__ S, const double* __restrict__ Mx, double eps,
                                          const double* __restrict__ bproj, const double* __restrict__ Sc, double* __restrict__ B,
                                          int* __restrict__ info2) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,7 +198,7 @@ __global__ void mcmc_build_system_kernel(int r, int rp, const double* __restrict
 
 // out = -0.5 u^T (Mx u) - r/2 log(2 pi), or -inf when the posterior of `from` failed / the solve failed / not finite
 // (GeneratorWrapperStochastic.scala:44-45, :58-60)
-__global__ void __launch_bounds__(256) mcmc_quadform_kernel(int r, const double* __restrict__ u, const double* __restrict__ Mxu,
+GINGR_KERNEL((256), mcmc_quadform_kernel, int r, const double* __restrict__ u, const double* __restrict__ Mxu,
                                                             const int* __restrict__ from_is, const int* __restrict__ info2,
                                                             double* __restrict__ out) {
   __shared__ double red[256];
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) mcmc_quadform_kernel(int r, const double*
 }
 
 // alpha_comp = from + (to - from) / stepLength   (GeneratorWrapperStochastic.scala:48-50)
-__global__ void mcmc_compensate_kernel(int r, const double* __restrict__ from, const double* __restrict__ to, double step,
+GINGR_KERNEL_NB(mcmc_compensate_kernel, int r, const double* __restrict__ from, const double* __restrict__ to, double step,
                                        double* __restrict__ out) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a < r) out[a] = from[a] + (to[a] - from[a]) / step;
@@ -254,7 +254,7 @@ __device__ double mixture_log_transition(const McmcDev& p, int r, const double* 
   return log(s);
 }
 
-__global__ void __launch_bounds__(256) mcmc_decide_kernel(McmcDev p, int r, int fw_cached, const double* __restrict__ s_ds, const int* __restrict__ s_is,
+GINGR_KERNEL((256), mcmc_decide_kernel, McmcDev p, int r, int fw_cached, const double* __restrict__ s_ds, const int* __restrict__ s_is,
                                                           const double* __restrict__ s_alpha, const double* __restrict__ ds,
                                                           const double* __restrict__ alpha, double* __restrict__ md,
                                                           int* __restrict__ mi) {
@@ -327,7 +327,7 @@ struct CopySegments {
   }
 };
 
-__global__ void __launch_bounds__(256) multi_copy_kernel(CopySegments seg) {
+GINGR_KERNEL((256), multi_copy_kernel, CopySegments seg) {
   for (int q = 0; q < seg.count; ++q) {
     if (seg.flag[q] && ((*seg.flag[q] != 0) != (seg.when[q] != 0))) continue;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < seg.n[q]; i += (size_t)gridDim.x * 256) seg.dst[q][i] = seg.src[q][i];
@@ -343,7 +343,7 @@ __global__ void cond_copy_kernel(const int* __restrict__ flag, int when, T* __re
 // on reject the working state returns to the snapshot, except the retry counter, which belongs to the algorithm
 // instance and not to the state (GingrAlgorithm.scala:70)
 // ... and the best sample's int block when the accepted proposal is the new best (one launch for both int blocks)
-__global__ void mcmc_restore_ints_kernel(const int* __restrict__ flag, int* __restrict__ is, const int* __restrict__ s_is,
+GINGR_KERNEL_NB(mcmc_restore_ints_kernel, const int* __restrict__ flag, int* __restrict__ is, const int* __restrict__ s_is,
                                          const int* __restrict__ best_flag, int* __restrict__ best_is) {
   if (*flag == 0) {
     for (int k = 0; k < IS_COUNT; ++k)
@@ -392,8 +392,11 @@ struct McmcState {
 
 using namespace gingr;
 
+static uint64_t g_mcmc_epoch = 1;   // bumped whenever a chain's buffers or configuration go away: batched plans are stale
+
 static void mcmc_release(gingr_registration* g) {
   if (!g->mcmc) return;
+  ++g_mcmc_epoch;   // declared below: a batched plan that names this chain is stale
   g->mcmc->release();
   delete g->mcmc;
   g->mcmc = nullptr;
@@ -427,14 +430,14 @@ static int32_t enqueue_log_value(gingr_registration* g, const double* d_fit, con
     const int nq = mc->n_model_ids > 0 ? mc->n_model_ids : M;
     const double* q = d_fit;
     if (mc->n_model_ids > 0) {
-      gather_aos_kernel<<<ceil_div(nq, 256), 256, 0, st>>>(nq, mc->model_ids.p, d_fit, mc->q_pts.p);
+      GINGR_LAUNCH(ctx, gather_aos_kernel, ceil_div(nq, 256), 256, 0, st, nq, mc->model_ids.p, d_fit, mc->q_pts.p);
       GINGR_LAUNCHED(ctx);
       q = mc->q_pts.p;
     }
     MeshView tv;
     tv.n = N; tv.aos = tg->aos.p; tv.soa = tg->verts.p; tv.T = tg->T; tv.tri = tg->tri.p; tv.tgrid = tg->tgrid;
     GINGR_TRY(surface_distance_enqueue(ctx, mc->ws_m2t, nq, q, tv));
-    mcmc_distance_logpdf_kernel<<<1, 256, 0, st>>>(nq, mc->ws_m2t.d2.p, sd, mode == GINGR_EVAL_SYMMETRIC ? 0.5 : 1.0, acc,
+    GINGR_LAUNCH(ctx, mcmc_distance_logpdf_kernel, 1, 256, 0, st, nq, mc->ws_m2t.d2.p, sd, mode == GINGR_EVAL_SYMMETRIC ? 0.5 : 1.0, acc,
                                                    d_out + 1, m->r, d_alpha);
     GINGR_LAUNCHED(ctx);
     acc = 1;
@@ -453,7 +456,7 @@ static int32_t enqueue_log_value(gingr_registration* g, const double* d_fit, con
       fv.tgrid = &mc->fit_tgrid;
     }
     GINGR_TRY(surface_distance_enqueue(ctx, mc->ws_t2m, nq, q, fv));
-    mcmc_distance_logpdf_kernel<<<1, 256, 0, st>>>(nq, mc->ws_t2m.d2.p, sd, mode == GINGR_EVAL_SYMMETRIC ? 0.5 : 1.0, acc,
+    GINGR_LAUNCH(ctx, mcmc_distance_logpdf_kernel, 1, 256, 0, st, nq, mc->ws_t2m.d2.p, sd, mode == GINGR_EVAL_SYMMETRIC ? 0.5 : 1.0, acc,
                                                    d_out + 1, m->r, acc ? nullptr : d_alpha);
     GINGR_LAUNCHED(ctx);
   }
@@ -472,18 +475,18 @@ static int32_t enqueue_log_transition(gingr_registration* g, const double* d_raw
   const int M = m->M, r = m->r, rp = m->rp;
   cudaStream_t st = ctx->stream;
   double* v = mc->vecs.p;   // [0] b_proj  [1] S c  [2] u  [3] Mx u
-  mcmc_residual_kernel<<<ceil_div(M, 256), 256, 0, st>>>(M, d_to_mesh, m->ref.p, m->mean.p, d_from_ds + DS_R, d_from_ds + DS_T,
+  GINGR_LAUNCH(ctx, mcmc_residual_kernel, ceil_div(M, 256), 256, 0, st, M, d_to_mesh, m->ref.p, m->mean.p, d_from_ds + DS_R, d_from_ds + DS_T,
                                                          mc->u3m.p);
   GINGR_LAUNCHED(ctx);
   GINGR_TRY(gemvT_enqueue(ctx, 3 * M, r, rp, m->phi.p, mc->u3m.p, m->sqrt_lambda.p, g->gt_part.p, v));
   GINGR_TRY(dense_matvec_enqueue(ctx, r, m->S.p, rp, d_cmean, v + rp));
-  mcmc_build_system_kernel<<<ceil_div((r + 1) * rp, 256), 256, 0, st>>>(r, rp, m->S.p, d_raw, 1e-5, v, v + rp, mc->sys.p,
+  GINGR_LAUNCH(ctx, mcmc_build_system_kernel, ceil_div((r + 1) * rp, 256), 256, 0, st, r, rp, m->S.p, d_raw, 1e-5, v, v + rp, mc->sys.p,
                                                                         mc->mi.p + MI_INFO2);
   GINGR_LAUNCHED(ctx);
   GINGR_TRY(cholesky_enqueue(ctx, r, r + 1, mc->sys.p, rp, mc->mi.p + MI_INFO2, &g->cholws));
   GINGR_TRY(chol_backsolve_enqueue(ctx, r, mc->sys.p, rp, mc->sys.p + (size_t)r * rp, v + 2 * rp, g->flags.p));
   GINGR_TRY(dense_matvec_enqueue(ctx, r, d_raw, rp, v + 2 * rp, v + 3 * rp));
-  mcmc_quadform_kernel<<<1, 256, 0, st>>>(r, v + 2 * rp, v + 3 * rp, d_from_is, mc->mi.p + MI_INFO2, d_out);
+  GINGR_LAUNCH(ctx, mcmc_quadform_kernel, 1, 256, 0, st, r, v + 2 * rp, v + 3 * rp, d_from_is, mc->mi.p + MI_INFO2, d_out);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
@@ -499,7 +502,7 @@ static int32_t enqueue_to_mesh(gingr_registration* g, double step_length, const 
   const gingr_model* m = g->model;
   const int M = m->M, r = m->r, rp = m->rp;
   double* v = mc->vecs.p;
-  mcmc_compensate_kernel<<<ceil_div(r, 256), 256, 0, ctx->stream>>>(r, d_from_alpha, d_to_alpha, step_length, v + 4 * rp);
+  GINGR_LAUNCH(ctx, mcmc_compensate_kernel, ceil_div(r, 256), 256, 0, ctx->stream, r, d_from_alpha, d_to_alpha, step_length, v + 4 * rp);
   GINGR_LAUNCHED(ctx);
   GINGR_TRY(instance_rows(ctx, m, v + 5 * rp, 1, v + 4 * rp, nullptr, mc->inst.p, nullptr));
   add_vectors_enqueue(ctx, 3 * M, m->ref.p, m->mean.p, mc->u3m.p);
@@ -565,7 +568,7 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
     sg.add(nullptr, 0, mc->s_alpha.p, g->alpha.p, r);
     sg.add(nullptr, 0, mc->s_fit.p, g->fit.p, (size_t)3 * M);
     sg.add(nullptr, 0, mc->s_fac.p, g->Mx.p, fac_n);
-    multi_copy_kernel<<<16, 256, 0, st>>>(sg);
+    GINGR_LAUNCH(ctx, multi_copy_kernel, 16, 256, 0, st, sg);
     GINGR_LAUNCHED(ctx);
   }
   // 3. the informed proposal update(current, probabilistic = true) from the kept posterior ...
@@ -576,7 +579,7 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
   g->sample_counter = nullptr;
   GINGR_TRY(rc);
   // 4. ... replaced by the chosen random leaf; iteration + 1; fit of the proposal
-  mcmc_random_override_kernel<<<1, 256, 0, st>>>(mc->dev, seed, r, mc->mi.p, mc->s_ds.p, mc->s_is.p, mc->s_alpha.p, g->ds.p,
+  GINGR_LAUNCH(ctx, mcmc_random_override_kernel, 1, 256, 0, st, mc->dev, seed, r, mc->mi.p, mc->s_ds.p, mc->s_is.p, mc->s_alpha.p, g->ds.p,
                                                  g->is.p, g->alpha.p, mc->mi.p, mc->md.p);
   GINGR_LAUNCHED(ctx);
   GINGR_TRY(evaluate_fit(g, DS_SCALE, DS_T, DS_R2));
@@ -596,13 +599,13 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
   // 7. evaluators of the proposal
   GINGR_TRY(enqueue_log_value(g, g->fit.p, g->alpha.p, mc->md.p + MD_LP_PROP));
   // 8. accept / reject
-  mcmc_decide_kernel<<<1, 256, 0, st>>>(mc->dev, r, fw_cached ? 1 : 0, mc->s_ds.p, mc->s_is.p, mc->s_alpha.p, g->ds.p, g->alpha.p, mc->md.p, mc->mi.p);
+  GINGR_LAUNCH(ctx, mcmc_decide_kernel, 1, 256, 0, st, mc->dev, r, fw_cached ? 1 : 0, mc->s_ds.p, mc->s_is.p, mc->s_alpha.p, g->ds.p, g->alpha.p, mc->md.p, mc->mi.p);
   GINGR_LAUNCHED(ctx);
   const int* acc = mc->mi.p + MI_ACCEPT;
   const int* bu = mc->mi.p + MI_BEST_UPDATED;
   // reject: the working state returns to the snapshot (ints by their own kernel: the retry counter stays);
   // accept: the proposal's posterior becomes the current one; best sample (only ever an accepted proposal)
-  mcmc_restore_ints_kernel<<<1, 1, 0, st>>>(acc, g->is.p, mc->s_is.p, bu, mc->best_is.p);
+  GINGR_LAUNCH(ctx, mcmc_restore_ints_kernel, 1, 1, 0, st, acc, g->is.p, mc->s_is.p, bu, mc->best_is.p);
   GINGR_LAUNCHED(ctx);
   {
     CopySegments sg;
@@ -615,7 +618,7 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
     sg.add(bu, 1, mc->best_ds.p, g->ds.p, DS_COUNT);
     sg.add(bu, 1, mc->best_alpha.p, g->alpha.p, r);
     sg.add(bu, 1, mc->best_fit.p, g->fit.p, (size_t)3 * M);
-    multi_copy_kernel<<<16, 256, 0, st>>>(sg);
+    GINGR_LAUNCH(ctx, multi_copy_kernel, 16, 256, 0, st, sg);
     GINGR_LAUNCHED(ctx);
   }
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
@@ -715,7 +718,7 @@ int32_t gingr_mcmc_configure(gingr_registration* g, const gingr_mcmc_settings* s
       GINGR_CUDA_TRY(ctx, mc->target_ids.alloc(n_target_ids));
       GINGR_CUDA_TRY(ctx, mc->target_sub.alloc((size_t)3 * n_target_ids));
       GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(mc->target_ids.p, target_ids, sizeof(int32_t) * n_target_ids, cudaMemcpyHostToDevice, st));
-      gather_aos_kernel<<<ceil_div(n_target_ids, 256), 256, 0, st>>>(n_target_ids, mc->target_ids.p, tg->aos.p, mc->target_sub.p);
+      GINGR_LAUNCH(ctx, gather_aos_kernel, ceil_div(n_target_ids, 256), 256, 0, st, n_target_ids, mc->target_ids.p, tg->aos.p, mc->target_sub.p);
       GINGR_LAUNCHED(ctx);
     }
     if (grid_wanted(M)) {
@@ -798,8 +801,140 @@ int32_t gingr_mcmc_chain(gingr_registration* g, int32_t iters, uint64_t seed) {
   return GINGR_OK;
 }
 
-// Independent chains batched on one GPU (BASELINE config 5): chain k uses seed + k; the captured step graphs are
-// replayed round-robin on a pool of streams, as gingr_update_batch does.
+// ---- the MH step of many chains as ONE kernel sequence (batch.cuh) ------------------------------------------------------
+// Every chain's step is recorded (arguments only, nothing is launched), the sequences are checked to be the same launch
+// for launch, the argument tuples go to the device as [launch][chain] arrays and the batched forms of the kernels are
+// captured as one graph: blockIdx.z = chain.  The plan is kept until the set of chains, the seed or a chain's configuration
+// changes.
+struct McmcBatchPlan {
+  std::vector<gingr_registration*> regs;
+  std::vector<double> step_lengths;
+  uint64_t seed = 0, epoch = 0;
+  int device = -1;
+  bool unsupported = false;     // a launch / copy on the path is not batch-aware, or the chains differ: per-chain graphs
+  int nlaunch = 0;
+  DevBuf<unsigned char> d_args;
+  cudaGraphExec_t exec = nullptr;
+  void drop() {
+    if (exec) cudaGraphExecDestroy(exec);
+    exec = nullptr;
+    regs.clear();
+    step_lengths.clear();
+    unsupported = false;
+    nlaunch = 0;
+  }
+};
+
+static bool mcmc_batch_plan_current(const McmcBatchPlan& bp, gingr_ctx* ctx, gingr_registration** regs, int n, uint64_t seed) {
+  if (bp.epoch != g_mcmc_epoch || bp.device != ctx->device || bp.seed != seed || (int)bp.regs.size() != n) return false;
+  for (int k = 0; k < n; ++k)
+    if (bp.regs[k] != regs[k] || bp.step_lengths[k] != regs[k]->last_out.step_length) return false;
+  return true;
+}
+
+static int32_t mcmc_batch_plan_build(gingr_ctx* ctx, gingr_registration** regs, int n, uint64_t seed, McmcBatchPlan& bp) {
+  bp.drop();
+  bp.epoch = g_mcmc_epoch;
+  bp.device = ctx->device;
+  bp.seed = seed;
+  bp.regs.assign(regs, regs + n);
+  for (int k = 0; k < n; ++k) bp.step_lengths.push_back(regs[k]->last_out.step_length);
+  cudaStream_t st = ctx->stream;
+  // a chain's Gram on few CTAs: with n chains in one launch the machine is filled by the chains, and the empty CTAs of
+  // the 148-wide schedule would each still cost a slot with 200 KB of shared memory
+  const int cap = std::max(1, (2 * ctx->num_sms) / n);
+  for (int k = 0; k < n; ++k) {
+    gingr_registration* g = regs[k];
+    if (g->gram.ncta > cap) {
+      GINGR_TRY(g->gram.build(ctx, g->gram.rows, g->gram.r, g->gram.rp, cap));
+      drop_graph(g);
+      mcmc_drop_graph(g->mcmc);
+      g->mcmc->primed = false;   // the kept posterior was formed in the other summation order
+    }
+  }
+  for (int k = 0; k < n; ++k)
+    if (!regs[k]->mcmc->primed) GINGR_TRY(mcmc_prime(regs[k]));
+  // 1. record: inside a capture, so that whatever is not batch-aware is caught in the discarded graph instead of running
+  std::vector<LaunchRecorder> rec((size_t)n);
+  const int64_t l0 = ctx->launches;
+  GINGR_CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int32_t rc = GINGR_OK;
+  for (int k = 0; k < n && rc >= 0; ++k) {
+    ctx->rec = &rec[k];
+    rc = enqueue_mcmc_step(regs[k], seed + (uint64_t)k);
+  }
+  ctx->rec = nullptr;
+  ctx->launches = l0;
+  cudaGraph_t stray = nullptr;
+  const cudaError_t ec = cudaStreamEndCapture(st, &stray);
+  size_t stray_nodes = 0;
+  if (stray) {
+    cudaGraphGetNodes(stray, nullptr, &stray_nodes);
+    cudaGraphDestroy(stray);
+  }
+  if (rc < 0) return rc;
+  GINGR_CUDA_TRY(ctx, ec);
+  // 2. the same sequence for every chain?
+  bool same = stray_nodes == 0 && !rec[0].recs.empty();
+  const std::vector<LaunchRecord>& r0 = rec[0].recs;
+  for (int k = 1; k < n && same; ++k) {
+    const std::vector<LaunchRecord>& rk = rec[k].recs;
+    same = rk.size() == r0.size();
+    for (size_t i = 0; i < r0.size() && same; ++i)
+      same = rk[i].fn == r0[i].fn && rk[i].arg_bytes == r0[i].arg_bytes && rk[i].smem == r0[i].smem &&
+             rk[i].grid.x == r0[i].grid.x && rk[i].grid.y == r0[i].grid.y && rk[i].grid.z == r0[i].grid.z &&
+             rk[i].block.x == r0[i].block.x && rk[i].block.y == r0[i].block.y && rk[i].block.z == r0[i].block.z;
+  }
+  for (size_t i = 0; i < r0.size() && same; ++i) same = r0[i].grid.z == 1;
+  if (!same) {
+    if (getenv("GINGR_MCMC_BATCH_VERBOSE"))
+      fprintf(stderr, "gingr_mcmc_batch: not batchable (%zu stray stream operations, %zu recorded launches): per-chain graphs\n",
+              stray_nodes, r0.size());
+    bp.unsupported = true;
+    return GINGR_OK;
+  }
+  // 3. argument arrays [launch][chain]
+  std::vector<size_t> off(r0.size());
+  size_t total = 0;
+  for (size_t i = 0; i < r0.size(); ++i) {
+    off[i] = total;
+    total += ((size_t)r0[i].arg_bytes * n + 255) / 256 * 256;
+  }
+  std::vector<unsigned char> h(total, 0);
+  for (size_t i = 0; i < r0.size(); ++i)
+    for (int k = 0; k < n; ++k)
+      memcpy(h.data() + off[i] + (size_t)k * r0[i].arg_bytes, rec[k].args.data() + rec[k].recs[i].arg_off, r0[i].arg_bytes);
+  GINGR_CUDA_TRY(ctx, bp.d_args.alloc(total));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(bp.d_args.p, h.data(), total, cudaMemcpyHostToDevice, st));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  // 4. the batched sequence as one graph
+  for (size_t i = 0; i < r0.size(); ++i)
+    if (r0[i].smem > 48 * 1024)
+      GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(r0[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r0[i].smem));
+  GINGR_CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  cudaError_t el = cudaSuccess;
+  for (size_t i = 0; i < r0.size() && el == cudaSuccess; ++i) {
+    const void* p = bp.d_args.p + off[i];
+    void* params[1] = {(void*)&p};
+    el = cudaLaunchKernel(r0[i].fn, dim3(r0[i].grid.x, r0[i].grid.y, (unsigned)n), r0[i].block, params, r0[i].smem, st);
+  }
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+  if (el != cudaSuccess || e2 != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    GINGR_CUDA_TRY(ctx, el);
+    GINGR_CUDA_TRY(ctx, e2);
+  }
+  const cudaError_t e3 = cudaGraphInstantiate(&bp.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  GINGR_CUDA_TRY(ctx, e3);
+  bp.nlaunch = (int)r0.size();
+  return GINGR_OK;
+}
+
+// Independent chains batched on one GPU (BASELINE config 5): chain k uses seed + k.  The chains' steps run as one
+// batched kernel sequence (blockIdx.z = chain; GINGR_MCMC_BATCHED=0 or a step that is not batchable: the captured
+// per-chain step graphs replayed round-robin on a pool of streams, as gingr_update_batch does).
 int32_t gingr_mcmc_batch(gingr_registration** regs, int32_t n, int32_t iters, uint64_t seed) {
   if (!regs || n <= 0 || iters < 0) return gingr_fail(nullptr, GINGR_ERR_ARG, "gingr_mcmc_batch: bad argument");
   gingr_ctx* ctx = regs[0] ? regs[0]->ctx : nullptr;
@@ -810,6 +945,21 @@ int32_t gingr_mcmc_batch(gingr_registration** regs, int32_t n, int32_t iters, ui
     regs[k]->host_mirror_current = false;
   }
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  static const int batched = [] { const char* e = getenv("GINGR_MCMC_BATCHED"); return e ? atoi(e) : 1; }();
+  if (batched && n >= 2 && n <= 65535 && graphs_enabled(ctx)) {
+    static thread_local McmcBatchPlan bp;
+    if (!mcmc_batch_plan_current(bp, ctx, regs, n, seed)) {
+      const int32_t rc = mcmc_batch_plan_build(ctx, regs, n, seed, bp);
+      if (rc < 0) { bp.drop(); return rc; }
+    }
+    if (!bp.unsupported) {
+      for (int k = 0; k < n; ++k)
+        if (!regs[k]->mcmc->primed) GINGR_TRY(mcmc_prime(regs[k]));
+      for (int it = 0; it < iters; ++it) GINGR_CUDA_TRY(ctx, cudaGraphLaunch(bp.exec, ctx->stream));
+      ctx->launches += (int64_t)iters * bp.nlaunch;
+      return GINGR_OK;
+    }
+  }
   ChainStreamPool* sp = nullptr;
   GINGR_TRY(chain_stream_pool(ctx, &sp));
   for (int k = 0; k < n; ++k) {

@@ -12,7 +12,8 @@ struct GramPlan {
   DevBuf<int> d_seg_begin;   // [ncta + 1]
   DevBuf<int> d_tile_first;  // [ntiles + 1]
   DevBuf<double> d_partial;  // [nsegs][128][128]
-  int32_t build(gingr_ctx* ctx, int rows, int r, int rp);
+  // max_cta > 0 caps the CTAs of the schedule (many chains batched in one launch: a chain's Gram on few CTAs, batch.cuh)
+  int32_t build(gingr_ctx* ctx, int rows, int r, int rp, int max_cta = 0);
   void release();
 };
 // d_resid (optional, needs gram_rhs_fusable): per-row residuals c_k; row r of the last tile row then comes out as

@@ -30,7 +30,7 @@
 #include <vector>
 
 #include "closest.cuh"
-#include "common.cuh"
+#include "batch.cuh"
 #include "estep.cuh"
 #include "grid.cuh"
 #include "nccl_dl.cuh"
@@ -70,7 +70,7 @@ __device__ __forceinline__ void matrix_to_euler_dev(const double* R, double* e) 
   }
 }
 
-__global__ void pose_kernel(double* ds, int* is) {
+GINGR_KERNEL_NB(pose_kernel, double* ds, int* is) {
   euler_to_matrix_dev(ds[DS_EULER], ds[DS_EULER + 1], ds[DS_EULER + 2], ds + DS_R);
   is[IS_INFO] = 0;
   is[IS_FAIL_POST] = 0;
@@ -79,7 +79,7 @@ __global__ void pose_kernel(double* ds, int* is) {
 
 // fit_i = s (R (ref_i + mean_i + a_i) + t)  for the local point range [m0, m0 + Ml); a: [3 Ml] local.
 // pose offsets select which (scale, t, R) of the state block to use.
-__global__ void fit_from_instance_kernel(int m0, int Ml, const double* __restrict__ ref, const double* __restrict__ mean,
+GINGR_KERNEL_NB(fit_from_instance_kernel, int m0, int Ml, const double* __restrict__ ref, const double* __restrict__ mean,
                                          const double* __restrict__ a, const double* __restrict__ ds, int off_s,
                                          int off_t, int off_R, double* __restrict__ out /*[3 Ml] local*/) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,7 +96,7 @@ __global__ void fit_from_instance_kernel(int m0, int Ml, const double* __restric
 }
 
 // v[a] = sqrt_lambda[a] * alpha[a]
-__global__ void scale_vec_kernel(int r, const double* __restrict__ sl, const double* __restrict__ alpha,
+GINGR_KERNEL_NB(scale_vec_kernel, int r, const double* __restrict__ sl, const double* __restrict__ alpha,
                                  double* __restrict__ out) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a < r) out[a] = sl[a] * alpha[a];
@@ -176,7 +176,7 @@ struct ObsArgs {
   double lambda;
 };
 
-__global__ void __launch_bounds__(256) obs_kernel(ObsArgs a, const double* __restrict__ rows /*[4][M] CPD*/,
+GINGR_KERNEL((256), obs_kernel, ObsArgs a, const double* __restrict__ rows /*[4][M] CPD*/,
                                                   const double* __restrict__ cp /*[M][3] ICP*/,
                                                   const uint8_t* __restrict__ w01,
                                                   const double* __restrict__ wcnt /*reversed ICP, else null*/,
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) obs_kernel(ObsArgs a, const double* __res
 }
 
 // sigma2 hook: CPD (xPx - 2 trPXY + yPy) / (3 Np) (CPD.scala:133-147); ICP linear anneal (ICP.scala:96-99)
-__global__ void sigma2_kernel(int algo, int nblocks, const double* __restrict__ sums_part, const double* __restrict__ xpx,
+GINGR_KERNEL_NB(sigma2_kernel, int algo, int nblocks, const double* __restrict__ sums_part, const double* __restrict__ xpx,
                               double sigma_step, double end_sigma, double* __restrict__ ds) {
   // one warp: lane l adds the block partials l, l + 32, ... in order, then a fixed shuffle tree (deterministic)
   const int lane = threadIdx.x;
@@ -276,7 +276,7 @@ __global__ void sigma2_kernel(int algo, int nblocks, const double* __restrict__ 
 
 // ---- landmarks ------------------------------------------------------------------------------------
 // A_l = R^T C_l^-1 R ; rhs += D Phi_l^T A_l R^T (y_l - (R (ref + mean)_pid + t))   for local landmarks
-__global__ void landmark_prepare_kernel(int L, const double* __restrict__ cinv, const double* __restrict__ ds,
+GINGR_KERNEL_NB(landmark_prepare_kernel, int L, const double* __restrict__ cinv, const double* __restrict__ ds,
                                         double* __restrict__ A) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= L) return;
@@ -289,7 +289,7 @@ __global__ void landmark_prepare_kernel(int L, const double* __restrict__ cinv, 
     for (int j = 0; j < 3; ++j) A[9 * l + 3 * i + j] = R[i] * T[j] + R[3 + i] * T[3 + j] + R[6 + i] * T[6 + j];
 }
 
-__global__ void landmark_rhs_kernel(int r, int rp, int L, const int32_t* __restrict__ pid,
+GINGR_KERNEL_NB(landmark_rhs_kernel, int r, int rp, int L, const int32_t* __restrict__ pid,
                                     const double* __restrict__ pts, const double* __restrict__ A,
                                     const double* __restrict__ lm_rows, const double* __restrict__ ref,
                                     const double* __restrict__ mean, const double* __restrict__ sl,
@@ -316,7 +316,7 @@ __global__ void landmark_rhs_kernel(int r, int rp, int L, const int32_t* __restr
 }
 
 // gather the 3 basis rows of each landmark vertex: lm_rows [L][3][rp]
-__global__ void gather_rows_kernel(int L, int rp, int m0, const int32_t* __restrict__ pid, const double* __restrict__ phi,
+GINGR_KERNEL_NB(gather_rows_kernel, int L, int rp, int m0, const int32_t* __restrict__ pid, const double* __restrict__ phi,
                                    double* __restrict__ out) {
   const int l = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -345,7 +345,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__global__ void add_normal_kernel(int r, uint64_t seed, const int* __restrict__ counter, double* __restrict__ y) {
+GINGR_KERNEL_NB(add_normal_kernel, int r, uint64_t seed, const int* __restrict__ counter, double* __restrict__ y) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;  // pair index: entries 2p, 2p + 1
   if (2 * p >= r) return;
   uint32_t x[4];
@@ -359,13 +359,13 @@ __global__ void add_normal_kernel(int r, uint64_t seed, const int* __restrict__ 
 }
 
 // ---- small vector kernels -------------------------------------------------------------------------
-__global__ void check_finite_kernel(int n, const double* __restrict__ v, int* __restrict__ flag) {
+GINGR_KERNEL_NB(check_finite_kernel, int n, const double* __restrict__ v, int* __restrict__ flag) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a < n && !(fabs(v[a]) < INFINITY)) *flag = 1;
 }
 
 // alpha_c = alpha + (alpha* - alpha) * stepLength   (GingrAlgorithm.scala:218-220)
-__global__ void combine_kernel(int r, const double* __restrict__ alpha, const double* __restrict__ astar,
+GINGR_KERNEL_NB(combine_kernel, int r, const double* __restrict__ alpha, const double* __restrict__ astar,
                                const double* __restrict__ ds, double* __restrict__ out) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a < r) out[a] = alpha[a] + (astar[a] - alpha[a]) * ds[DS_STEP];
@@ -373,7 +373,7 @@ __global__ void combine_kernel(int r, const double* __restrict__ alpha, const do
 
 // X_i = ref + mean + a (currentFitNoTransform, :224), Y_i = R (ref + mean + b) + t (newshape, :222), local points.
 // pass 0: partial sums of X and Y ; pass 1: centred sums |X - mux|^2 and (Y - muy)(X - mux)^T.
-__global__ void __launch_bounds__(256) procrustes_sums_kernel(int pass, int m0, int Ml, const double* __restrict__ ref,
+GINGR_KERNEL((256), procrustes_sums_kernel, int pass, int m0, int Ml, const double* __restrict__ ref,
                                                               const double* __restrict__ mean,
                                                               const double* __restrict__ a, const double* __restrict__ b,
                                                               const double* __restrict__ ds,
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(256) procrustes_sums_kernel(int pass, int m0, 
   }
 }
 
-__global__ void procrustes_reduce_kernel(int nblocks, int count, const double* __restrict__ part,
+GINGR_KERNEL_NB(procrustes_reduce_kernel, int nblocks, int count, const double* __restrict__ part,
                                          double* __restrict__ out /*[16]*/) {
   const int q = threadIdx.x;
   if (q >= count) return;
@@ -443,7 +443,7 @@ __global__ void procrustes_reduce_kernel(int nblocks, int count, const double* _
   out[q] = s;
 }
 
-__global__ void procrustes_means_kernel(int M, const double* __restrict__ sums, double* __restrict__ ds) {
+GINGR_KERNEL_NB(procrustes_means_kernel, int M, const double* __restrict__ sums, double* __restrict__ ds) {
   for (int d = 0; d < 3; ++d) {
     ds[DS_MUX + d] = sums[d] / M;
     ds[DS_MUY + d] = sums[3 + d] / M;
@@ -540,14 +540,14 @@ __device__ void procrustes_solve_dev(int M, const double* __restrict__ sums, dou
   euler_to_matrix_dev(e2[0], e2[1], e2[2], ds + DS_R2);
 }
 
-__global__ void procrustes_solve_kernel(int M, const double* __restrict__ sums, double* __restrict__ ds,
+GINGR_KERNEL_NB(procrustes_solve_kernel, int M, const double* __restrict__ sums, double* __restrict__ ds,
                                         const int* __restrict__ is) {
   procrustes_solve_dev(M, sums, ds, is);
 }
 
 // several ranks: the all-reduced shifted moments of the single pass (pass 2 of procrustes_sums_kernel) -> means and
 // centred sums, then the same solve
-__global__ void procrustes_moments_solve_kernel(int M, double* __restrict__ sums /*[16]*/, const double* __restrict__ ref,
+GINGR_KERNEL_NB(procrustes_moments_solve_kernel, int M, double* __restrict__ sums /*[16]*/, const double* __restrict__ ref,
                                                 const double* __restrict__ mean, double* __restrict__ ds,
                                                 const int* __restrict__ is) {
   const double* R = ds + DS_R;
@@ -567,7 +567,7 @@ __global__ void procrustes_moments_solve_kernel(int M, double* __restrict__ sums
 
 // single rank: sum of the block partials (block order, as procrustes_reduce_kernel) followed by what consumes them:
 // the means after pass 0, the rotation / translation / scale after pass 1
-__global__ void procrustes_reduce_then_kernel(int pass, int nblocks, int M, const double* __restrict__ part,
+GINGR_KERNEL_NB(procrustes_reduce_then_kernel, int pass, int nblocks, int M, const double* __restrict__ part,
                                               double* __restrict__ sums /*[16]*/, double* __restrict__ ds,
                                               const int* __restrict__ is) {
   const int q = threadIdx.x;
@@ -592,7 +592,7 @@ __global__ void procrustes_reduce_then_kernel(int pass, int nblocks, int M, cons
 }
 
 // u_i = R1^T (newshape_i - (R1 (ref + mean)_i + t_new))  for the second `coefficients` call (:234-237)
-__global__ void coeff_residual_kernel(int m0, int Ml, const double* __restrict__ newshape, const double* __restrict__ ref,
+GINGR_KERNEL_NB(coeff_residual_kernel, int m0, int Ml, const double* __restrict__ newshape, const double* __restrict__ ref,
                                       const double* __restrict__ mean, const double* __restrict__ ds,
                                       double* __restrict__ u) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -612,7 +612,7 @@ __global__ void coeff_residual_kernel(int m0, int Ml, const double* __restrict__
 // replaced; a failed posterior leaves the state unchanged (status ModelFlexibilityError if iteration > 0; in the
 // probabilistic branch only once the retry counter of :69-70 has run out), a
 // failed `coefficients` sets ModelFlexibilityError.  DS_R2 is left holding the rotation of the committed state.
-__global__ void finalize_kernel(int r, int probabilistic, const double* __restrict__ alpha_new, double* __restrict__ alpha,
+GINGR_KERNEL_NB(finalize_kernel, int r, int probabilistic, const double* __restrict__ alpha_new, double* __restrict__ alpha,
                                 double* __restrict__ ds, int* __restrict__ is) {
   __shared__ int mode;  // 0 commit, 1 keep
   if (threadIdx.x == 0) {
@@ -643,9 +643,9 @@ __global__ void finalize_kernel(int r, int probabilistic, const double* __restri
     for (int a = threadIdx.x; a < r; a += blockDim.x) alpha[a] = alpha_new[a];
 }
 
-__global__ void bump_iteration_kernel(int* is) { is[IS_ITER] += 1; }
+GINGR_KERNEL_NB(bump_iteration_kernel, int* is) { is[IS_ITER] += 1; }
 
-__global__ void set_iteration_kernel(int* is, int iteration, int status) {
+GINGR_KERNEL_NB(set_iteration_kernel, int* is, int iteration, int status) {
   is[IS_ITER] = iteration;
   is[IS_STATUS] = status;
 }
@@ -1097,9 +1097,9 @@ static int32_t posterior_core(gingr_ctx* ctx, const gingr_model* model, const do
     PM_TRY(cudaMemcpyAsync(d_lpid.p, lpid.data(), sizeof(int32_t) * L, cudaMemcpyHostToDevice, st));
     PM_TRY(cudaMemcpyAsync(d_lpts.p, lpts.data(), sizeof(double) * 3 * L, cudaMemcpyHostToDevice, st));
     PM_TRY(cudaMemcpyAsync(d_lcinv.p, lcinv.data(), sizeof(double) * 9 * L, cudaMemcpyHostToDevice, st));
-    gather_rows_kernel<<<dim3(ceil_div(3 * rp, 256), L), 256, 0, st>>>(L, rp, 0, d_lpid.p, m->phi.p, d_lrows.p);
-    landmark_prepare_kernel<<<ceil_div(L, 64), 64, 0, st>>>(L, d_lcinv.p, s.ds.p, d_lA.p);
-    landmark_rhs_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, rp, L, d_lpid.p, d_lpts.p, d_lA.p, d_lrows.p, m->ref.p,
+    GINGR_LAUNCH(ctx, gather_rows_kernel, dim3(ceil_div(3 * rp, 256), L), 256, 0, st, L, rp, 0, d_lpid.p, m->phi.p, d_lrows.p);
+    GINGR_LAUNCH(ctx, landmark_prepare_kernel, ceil_div(L, 64), 64, 0, st, L, d_lcinv.p, s.ds.p, d_lA.p);
+    GINGR_LAUNCH(ctx, landmark_rhs_kernel, ceil_div(r, 256), 256, 0, st, r, rp, L, d_lpid.p, d_lpts.p, d_lA.p, d_lrows.p, m->ref.p,
                                                           m->mean.p, m->sqrt_lambda.p, s.ds.p, rhs);
     ctx->launches += 3;
   }
@@ -1113,11 +1113,11 @@ static int32_t posterior_core(gingr_ctx* ctx, const gingr_model* model, const do
   if ((rc = cholesky_enqueue(ctx, r, r + 1 + xrows, s.Mx.p, rp, s.is.p + IS_INFO, &s.cholws)) < 0) return fail(rc);
   double* c = s.vec.p;
   if ((rc = chol_backsolve_enqueue(ctx, r, s.Mx.p, rp, rhs, c, s.flags.p, &s.cholws)) < 0) return fail(rc);
-  check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, c, s.is.p + IS_FAIL_POST);
+  GINGR_LAUNCH(ctx, check_finite_kernel, ceil_div(r, 256), 256, 0, st, r, c, s.is.p + IS_FAIL_POST);
   GINGR_LAUNCHED(ctx);
   if (mean_pts) {
     if ((rc = instance_rows(ctx, m, s.vec.p + 2 * rp, 1, c, nullptr, s.inst.p, nullptr)) < 0) return fail(rc);
-    fit_from_instance_kernel<<<ceil_div(M, 256), 256, 0, st>>>(0, M, m->ref.p, m->mean.p, s.inst.p, s.ds.p, DS_SCALE, DS_T,
+    GINGR_LAUNCH(ctx, fit_from_instance_kernel, ceil_div(M, 256), 256, 0, st, 0, M, m->ref.p, m->mean.p, s.inst.p, s.ds.p, DS_SCALE, DS_T,
                                                                DS_R, s.fit_local.p);
     GINGR_LAUNCHED(ctx);
     PM_TRY(cudaMemcpyAsync(mean_pts, s.fit_local.p, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, st));
@@ -1178,12 +1178,12 @@ int32_t gingr_coefficients(gingr_ctx* ctx, const gingr_model* model, const doubl
   CO_TRY(cudaMemcpyAsync(ds.p, hds, sizeof(hds), cudaMemcpyHostToDevice, st));
   CO_TRY(cudaMemcpyAsync(mesh.p, mesh_pts, sizeof(double) * 3 * M, cudaMemcpyHostToDevice, st));
   CO_TRY(cudaMemsetAsync(flag.p, 0, sizeof(int) * 4, st));
-  coeff_residual_kernel<<<ceil_div(M, 256), 256, 0, st>>>(0, M, mesh.p, m->ref.p, m->mean.p, ds.p, u.p);
+  GINGR_LAUNCH(ctx, coeff_residual_kernel, ceil_div(M, 256), 256, 0, st, 0, M, mesh.p, m->ref.p, m->mean.p, ds.p, u.p);
   GINGR_LAUNCHED(ctx);
   int32_t rc = gemvT_enqueue(ctx, 3 * M, r, rp, m->phi.p, u.p, m->sqrt_lambda.p, part.p, vec.p);
   if (rc >= 0) rc = dense_matvec_enqueue(ctx, r, m->W0.p, rp, vec.p, vec.p + rp);
   if (rc < 0) { cudaStreamSynchronize(st); rel(); return rc; }
-  check_finite_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, vec.p + rp, flag.p);
+  GINGR_LAUNCH(ctx, check_finite_kernel, ceil_div(r, 256), 256, 0, st, r, vec.p + rp, flag.p);
   GINGR_LAUNCHED(ctx);
   int hflag = 0;
   CO_TRY(cudaMemcpyAsync(coeffs, vec.p + rp, sizeof(double) * r, cudaMemcpyDeviceToHost, st));
@@ -1274,11 +1274,11 @@ int32_t gingr_model_instance(gingr_ctx* ctx, const gingr_model* model, const gin
   for (int d = 0; d < 3; ++d) { hds[DS_T + d] = stt->translation[d]; hds[DS_EULER + d] = stt->euler[d]; }
   MI_TRY(cudaMemcpyAsync(ds.p, hds, sizeof(hds), cudaMemcpyHostToDevice, st));
   MI_TRY(cudaMemcpyAsync(vec.p, alpha, sizeof(double) * r, cudaMemcpyHostToDevice, st));
-  pose_kernel<<<1, 1, 0, st>>>(ds.p, is.p);
+  GINGR_LAUNCH(ctx, pose_kernel, 1, 1, 0, st, ds.p, is.p);
   GINGR_LAUNCHED(ctx);
   int32_t rc = instance_rows(ctx, m, vec.p + rp, 1, vec.p, nullptr, inst.p, nullptr);
   if (rc < 0) { cudaStreamSynchronize(st); rel(); return rc; }
-  fit_from_instance_kernel<<<ceil_div(M, 256), 256, 0, st>>>(0, M, m->ref.p, m->mean.p, inst.p, ds.p, DS_SCALE, DS_T, DS_R,
+  GINGR_LAUNCH(ctx, fit_from_instance_kernel, ceil_div(M, 256), 256, 0, st, 0, M, m->ref.p, m->mean.p, inst.p, ds.p, DS_SCALE, DS_T, DS_R,
                                                              out.p);
   GINGR_LAUNCHED(ctx);
   MI_TRY(cudaMemcpyAsync(fit, out.p, sizeof(double) * 3 * M, cudaMemcpyDeviceToHost, st));
@@ -1436,7 +1436,7 @@ int32_t gingr_registration_set_landmarks(gingr_registration* g, int32_t L, const
     GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->lml_pid.p, lpid.data(), sizeof(int32_t) * Ll, cudaMemcpyHostToDevice, st));
     GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->lml_pts.p, lpts.data(), sizeof(double) * 3 * Ll, cudaMemcpyHostToDevice, st));
     GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->lml_cinv.p, lcinv.data(), sizeof(double) * 9 * Ll, cudaMemcpyHostToDevice, st));
-    gather_rows_kernel<<<dim3(ceil_div(3 * m->rp, 256), Ll), 256, 0, st>>>(Ll, m->rp, m->m0, g->lml_pid.p, m->phi.p,
+    GINGR_LAUNCH(ctx, gather_rows_kernel, dim3(ceil_div(3 * m->rp, 256), Ll), 256, 0, st, Ll, m->rp, m->m0, g->lml_pid.p, m->phi.p,
                                                                           g->lml_rows.p);
     GINGR_LAUNCHED(ctx);
   }
@@ -1478,7 +1478,7 @@ static int32_t upload_state(gingr_registration* g, const gingr_state* s, const d
   }
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->ds.p, h, sizeof(double) * DS_COUNT, cudaMemcpyHostToDevice, ctx->stream));
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->is.p, hi, sizeof(int) * IS_COUNT, cudaMemcpyHostToDevice, ctx->stream));
-  pose_kernel<<<1, 1, 0, ctx->stream>>>(g->ds.p, g->is.p);
+  GINGR_LAUNCH(ctx, pose_kernel, 1, 1, 0, ctx->stream, g->ds.p, g->is.p);
   GINGR_LAUNCHED(ctx);
   return GINGR_OK;
 }
@@ -1489,7 +1489,7 @@ static int32_t evaluate_fit(gingr_registration* g, int off_s, int off_t, int off
   const gingr_model* m = g->model;
   GINGR_TRY(instance_rows(ctx, m, g->vec.p + 6 * m->rp, 1, g->alpha.p, nullptr, g->inst_a.p, nullptr));
   if (m->Ml > 0) {
-    fit_from_instance_kernel<<<ceil_div(m->Ml, 256), 256, 0, ctx->stream>>>(m->m0, m->Ml, m->ref.p, m->mean.p, g->inst_a.p,
+    GINGR_LAUNCH(ctx, fit_from_instance_kernel, ceil_div(m->Ml, 256), 256, 0, ctx->stream, m->m0, m->Ml, m->ref.p, m->mean.p, g->inst_a.p,
                                                                             g->ds.p, off_s, off_t, off_R,
                                                                             ctx->nranks == 1 ? g->fit.p : g->fit_local.p);
     GINGR_LAUNCHED(ctx);
@@ -1513,7 +1513,7 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
   double* vec = g->vec.p;  // [0] c_post  [1] S c  [2] alpha*  [3] alpha_c  [4] q  [5] alpha_new  [6,7] scaled scratch
   // events: 0/1 iteration, 2..5 E-step sweeps, 6/7 Gram, 8/9 Cholesky + back solve, 10/11 closest point, 12/13 unused
   g->rec(0);
-  pose_kernel<<<1, 1, 0, st>>>(g->ds.p, g->is.p);
+  GINGR_LAUNCH(ctx, pose_kernel, 1, 1, 0, st, g->ds.p, g->is.p);
   GINGR_LAUNCHED(ctx);
   // ---- correspondence -------------------------------------------------------------------------------
   const double* icp_cp = nullptr;
@@ -1595,12 +1595,12 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
   const bool use_lm = cfg.use_landmark_correspondence && g->Ll > 0;
   const bool any_lm = cfg.use_landmark_correspondence && g->L > 0;
   const bool rhs_fused = !any_lm && gram_rhs_fusable(g->gram);
-  obs_kernel<<<oblocks, 256, 0, st>>>(oa, g->rows_ext.p, icp_cp, g->closest.w.p, icp_wcnt, g->fit.p, m->ref.p, m->mean.p,
+  GINGR_LAUNCH(ctx, obs_kernel, oblocks, 256, 0, st, oa, g->rows_ext.p, icp_cp, g->closest.w.p, icp_wcnt, g->fit.p, m->ref.p, m->mean.p,
                                       g->lm_pid.p, g->ds.p, g->is.p, g->wrow.p, g->u.p, g->sums_part.p,
                                       rhs_fused ? g->resid.p : nullptr);
   GINGR_LAUNCHED(ctx);
   const double sigma_step = cfg.algorithm == GINGR_ALGO_ICP ? (cfg.initial_sigma - cfg.end_sigma) / (double)cfg.max_iterations : 0.0;
-  sigma2_kernel<<<1, 32, 0, st>>>(cfg.algorithm, oblocks, g->sums_part.p, g->rows_ext.p + (size_t)4 * M, sigma_step,
+  GINGR_LAUNCH(ctx, sigma2_kernel, 1, 32, 0, st, cfg.algorithm, oblocks, g->sums_part.p, g->rows_ext.p + (size_t)4 * M, sigma_step,
                                  cfg.end_sigma, g->ds.p);
   GINGR_LAUNCHED(ctx);
   // ---- posterior: rhs, Gram, Cholesky --------------------------------------------------------------------
@@ -1611,8 +1611,8 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
   double* rhs = packed ? g->Mx_packed.p + packed_n : g->Mx.p + (size_t)r * rp;
   if (!rhs_fused) GINGR_TRY(gemvT_enqueue(ctx, 3 * Ml, r, rp, m->phi.p, g->u.p, m->sqrt_lambda.p, g->gt_part.p, rhs));
   if (use_lm) {
-    landmark_prepare_kernel<<<ceil_div(g->Ll, 64), 64, 0, st>>>(g->Ll, g->lml_cinv.p, g->ds.p, g->lml_A.p);
-    landmark_rhs_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, rp, g->Ll, g->lml_pid.p, g->lml_pts.p, g->lml_A.p, g->lml_rows.p,
+    GINGR_LAUNCH(ctx, landmark_prepare_kernel, ceil_div(g->Ll, 64), 64, 0, st, g->Ll, g->lml_cinv.p, g->ds.p, g->lml_A.p);
+    GINGR_LAUNCH(ctx, landmark_rhs_kernel, ceil_div(r, 256), 256, 0, st, r, rp, g->Ll, g->lml_pid.p, g->lml_pts.p, g->lml_A.p, g->lml_rows.p,
                                                           m->ref.p, m->mean.p, m->sqrt_lambda.p, g->ds.p, rhs);
     ctx->launches += 2;
   }
@@ -1631,7 +1631,7 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
                                   g->lml_A.p, rp, g->Mx.p, false, !g->keep_raw, rhs_fused));
   }
   if (g->keep_raw)
-    GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->Mx_raw.p, g->Mx.p, sizeof(double) * (size_t)(r + 1) * rp, cudaMemcpyDeviceToDevice, st));
+    GINGR_CUDA_TRY(ctx, gingr_copy_d2d(ctx, g->Mx_raw.p, g->Mx.p, sizeof(double) * (size_t)(r + 1) * rp, st));
   g->rec(8);
   GINGR_TRY(cholesky_enqueue(ctx, r, r + 1, g->Mx.p, rp, g->is.p + IS_INFO, &g->cholws));
   return GINGR_OK;
@@ -1650,7 +1650,7 @@ static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, ui
   (void)cfg;
   if (probabilistic) {  // posterior.sample() instead of posterior.mean (:211)
     // counter of the Philox stream: the state's iteration (gingr_update) or the chain's MH step (mcmc.cuh)
-    add_normal_kernel<<<ceil_div(ceil_div(r, 2), 128), 128, 0, st>>>(r, seed, g->sample_counter ? g->sample_counter : g->is.p + IS_ITER,
+    GINGR_LAUNCH(ctx, add_normal_kernel, ceil_div(ceil_div(r, 2), 128), 128, 0, st, r, seed, g->sample_counter ? g->sample_counter : g->is.p + IS_ITER,
                                                                      rhs);
     GINGR_LAUNCHED(ctx);
   }
@@ -1660,42 +1660,42 @@ static int32_t enqueue_update_phase(gingr_registration* g, int probabilistic, ui
   // (a non-finite c is flagged by the first product, a non-finite alpha_new by the last: no separate launches)
   GINGR_TRY(dense_matvec_enqueue(ctx, r, m->S.p, rp, vec, vec + rp, g->is.p + IS_FAIL_POST, nullptr));
   GINGR_TRY(dense_matvec_enqueue(ctx, r, m->W0.p, rp, vec + rp, vec + 2 * rp));
-  combine_kernel<<<ceil_div(r, 256), 256, 0, st>>>(r, g->alpha.p, vec + 2 * rp, g->ds.p, vec + 3 * rp);
+  GINGR_LAUNCH(ctx, combine_kernel, ceil_div(r, 256), 256, 0, st, r, g->alpha.p, vec + 2 * rp, g->ds.p, vec + 3 * rp);
   GINGR_LAUNCHED(ctx);
   // ---- instances, Procrustes -----------------------------------------------------------------------------------
   GINGR_TRY(instance_rows(ctx, m, vec + 6 * rp, 2, g->alpha.p, vec + 3 * rp, g->inst_a.p, g->inst_b.p));
   const int pblocks = ceil_div(std::max(Ml, 1), 256);
   if (ctx->nranks == 1) {
     for (int pass = 0; pass < 2; ++pass) {
-      procrustes_sums_kernel<<<pblocks, 256, 0, st>>>(pass, m0, Ml, m->ref.p, m->mean.p, g->inst_a.p, g->inst_b.p, g->ds.p,
+      GINGR_LAUNCH(ctx, procrustes_sums_kernel, pblocks, 256, 0, st, pass, m0, Ml, m->ref.p, m->mean.p, g->inst_a.p, g->inst_b.p, g->ds.p,
                                                       g->newshape.p, g->pro_part.p);
       GINGR_LAUNCHED(ctx);
       // one rank: the block partials are summed (same fixed order) by the kernel that consumes the sums
-      procrustes_reduce_then_kernel<<<1, 32, 0, st>>>(pass, pblocks, M, g->pro_part.p, g->pro_sums.p, g->ds.p, g->is.p);
+      GINGR_LAUNCH(ctx, procrustes_reduce_then_kernel, 1, 32, 0, st, pass, pblocks, M, g->pro_part.p, g->pro_sums.p, g->ds.p, g->is.p);
       GINGR_LAUNCHED(ctx);
     }
   } else {
     // several ranks: one pass of shifted moments and ONE all-reduce of 16 doubles (two latency-bound all-reduces and the
     // second pass over the shard before)
-    procrustes_sums_kernel<<<pblocks, 256, 0, st>>>(2, m0, Ml, m->ref.p, m->mean.p, g->inst_a.p, g->inst_b.p, g->ds.p,
+    GINGR_LAUNCH(ctx, procrustes_sums_kernel, pblocks, 256, 0, st, 2, m0, Ml, m->ref.p, m->mean.p, g->inst_a.p, g->inst_b.p, g->ds.p,
                                                     g->newshape.p, g->pro_part.p);
     GINGR_LAUNCHED(ctx);
-    procrustes_reduce_kernel<<<1, 32, 0, st>>>(Ml > 0 ? pblocks : 0, 16, g->pro_part.p, g->pro_sums.p);
+    GINGR_LAUNCH(ctx, procrustes_reduce_kernel, 1, 32, 0, st, Ml > 0 ? pblocks : 0, 16, g->pro_part.p, g->pro_sums.p);
     GINGR_LAUNCHED(ctx);
     GINGR_TRY(comm_allreduce_sum(ctx, g->pro_sums.p, 16));
-    procrustes_moments_solve_kernel<<<1, 1, 0, st>>>(M, g->pro_sums.p, m->ref.p, m->mean.p, g->ds.p, g->is.p);
+    GINGR_LAUNCH(ctx, procrustes_moments_solve_kernel, 1, 1, 0, st, M, g->pro_sums.p, m->ref.p, m->mean.p, g->ds.p, g->is.p);
     GINGR_LAUNCHED(ctx);
   }
   // ---- alpha_new = transformedModel.coefficients(newshape) ---------------------------------------------------------
   if (Ml > 0) {
-    coeff_residual_kernel<<<ceil_div(Ml, 256), 256, 0, st>>>(m0, Ml, g->newshape.p, m->ref.p, m->mean.p, g->ds.p, g->u.p);
+    GINGR_LAUNCH(ctx, coeff_residual_kernel, ceil_div(Ml, 256), 256, 0, st, m0, Ml, g->newshape.p, m->ref.p, m->mean.p, g->ds.p, g->u.p);
     GINGR_LAUNCHED(ctx);
   }
   GINGR_TRY(gemvT_enqueue(ctx, 3 * Ml, r, rp, m->phi.p, g->u.p, m->sqrt_lambda.p, g->gt_part.p, vec + 4 * rp));
   GINGR_TRY(comm_allreduce_sum(ctx, vec + 4 * rp, (size_t)r));
   GINGR_TRY(dense_matvec_enqueue(ctx, r, m->W0.p, rp, vec + 4 * rp, vec + 5 * rp, nullptr, g->is.p + IS_FAIL_COEF));
   // ---- commit, refresh the fit ------------------------------------------------------------------------------------------
-  finalize_kernel<<<1, 256, 0, st>>>(r, probabilistic, vec + 5 * rp, g->alpha.p, g->ds.p, g->is.p);
+  GINGR_LAUNCH(ctx, finalize_kernel, 1, 256, 0, st, r, probabilistic, vec + 5 * rp, g->alpha.p, g->ds.p, g->is.p);
   GINGR_LAUNCHED(ctx);
   if (!g->skip_fit_refresh) GINGR_TRY(evaluate_fit(g, DS_SCALE, DS_T, DS_R2));
   g->rec(1);
@@ -1882,7 +1882,7 @@ int32_t gingr_update(gingr_registration* g, const gingr_state* state_in, const d
     GINGR_TRY(upload_state(g, state_in, alpha_in));
     GINGR_TRY(evaluate_fit(g, DS_SCALE, DS_T, DS_R));
   } else {
-    set_iteration_kernel<<<1, 1, 0, ctx->stream>>>(g->is.p, state_in->iteration, state_in->status);
+    GINGR_LAUNCH(ctx, set_iteration_kernel, 1, 1, 0, ctx->stream, g->is.p, state_in->iteration, state_in->status);
     GINGR_LAUNCHED(ctx);
   }
   g->state_valid = false;
@@ -1904,7 +1904,7 @@ int32_t gingr_update_chain(gingr_registration* g, int32_t iters) {
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   for (int k = 0; k < iters; ++k) {
     GINGR_TRY(run_iteration(g, 0, 0));
-    bump_iteration_kernel<<<1, 1, 0, ctx->stream>>>(g->is.p);  // GingrGeneratorWrapper.propose: updateIteration()
+    GINGR_LAUNCH(ctx, bump_iteration_kernel, 1, 1, 0, ctx->stream, g->is.p);  // GingrGeneratorWrapper.propose: updateIteration()
     GINGR_LAUNCHED(ctx);
   }
   return GINGR_OK;
@@ -1919,7 +1919,7 @@ int32_t gingr_update_chain_sampled(gingr_registration* g, int32_t iters, uint64_
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   for (int k = 0; k < iters; ++k) {
     GINGR_TRY(run_iteration(g, 1, seed));  // the Philox counter carries the device iteration number
-    bump_iteration_kernel<<<1, 1, 0, ctx->stream>>>(g->is.p);
+    GINGR_LAUNCH(ctx, bump_iteration_kernel, 1, 1, 0, ctx->stream, g->is.p);
     GINGR_LAUNCHED(ctx);
   }
   return GINGR_OK;
@@ -1966,7 +1966,7 @@ int32_t gingr_update_batch(gingr_registration** regs, int32_t n, int32_t iters, 
     }
   }
   GINGR_TRY(replay_chain_graphs(ctx, sp, n, iters, [&](int k) { return regs[k]->graph_exec; },
-                                [&](int k, cudaStream_t st) { bump_iteration_kernel<<<1, 1, 0, st>>>(regs[k]->is.p); }));
+                                [&](int k, cudaStream_t st) { GINGR_LAUNCH(ctx, bump_iteration_kernel, 1, 1, 0, st, regs[k]->is.p); }));
   for (int k = 0; k < n; ++k) ctx->launches += (int64_t)iters * (regs[k]->graph_launches + 1);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

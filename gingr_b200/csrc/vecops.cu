@@ -9,16 +9,14 @@
 // Both read Phi (8 * 3M * r bytes) exactly once; Phi is row-major [3M][rp] so both are fully coalesced.
 #include <algorithm>
 
-#include "common.cuh"
+#include "batch.cuh"
 #include "posterior.cuh"
 
 namespace gingr {
 
-template <int NVEC>
-__global__ void __launch_bounds__(256) gemv_rows_kernel(int rows, int r, int rp, const double* __restrict__ phi,
-                                                        const double* __restrict__ v0, const double* __restrict__ v1,
-                                                        const double* __restrict__ scale /*may be null*/,
-                                                        double* __restrict__ out0, double* __restrict__ out1) {
+GINGR_KERNEL_T((int NVEC), (NVEC), (256), gemv_rows_kernel, int rows, int r, int rp, const double* __restrict__ phi,
+               const double* __restrict__ v0, const double* __restrict__ v1, const double* __restrict__ scale /*may be null*/,
+               double* __restrict__ out0, double* __restrict__ out1) {
   extern __shared__ double sv[];  // [NVEC][r]
   for (int a = threadIdx.x; a < r; a += 256) {
     const double sc = scale ? scale[a] : 1.0;   // instance(alpha): v = sqrt(lambda) * alpha, folded into the staging
@@ -62,7 +60,7 @@ static int gemvT_rows_per_cta(const gingr_ctx* ctx, int rows) {
   return std::max(16, std::min(GT_ROWS, (want + 3) / 4 * 4));
 }
 
-__global__ void __launch_bounds__(256) gemvT_kernel(int rows, int rp, int rows_per_cta, const double* __restrict__ phi,
+GINGR_KERNEL((256), gemvT_kernel, int rows, int rp, int rows_per_cta, const double* __restrict__ phi,
                                                     const double* __restrict__ u, double* __restrict__ part) {
   __shared__ double su[GT_ROWS];
   const int k0 = blockIdx.y * rows_per_cta;
@@ -87,7 +85,7 @@ __global__ void __launch_bounds__(256) gemvT_kernel(int rows, int rp, int rows_p
 // Sum of the `splits` partial vectors, fixed order (deterministic).  A CTA owns 32 columns; 8 groups of threads walk the
 // splits interleaved and are combined through shared memory: the one-thread-per-column form walked ~300 strided loads in a
 // dependent add chain from 8 CTAs (35 us at rank 2000, more than the streaming pass it follows on 8 GPUs).
-__global__ void __launch_bounds__(256) gemvT_reduce_kernel(int r, int rp, int splits, const double* __restrict__ part,
+GINGR_KERNEL((256), gemvT_reduce_kernel, int r, int rp, int splits, const double* __restrict__ part,
                                                            const double* __restrict__ scale, double* __restrict__ out) {
   __shared__ double sp[8][33];
   const int c = threadIdx.x & 31, q = threadIdx.x >> 5;
@@ -111,7 +109,7 @@ __global__ void __launch_bounds__(256) gemvT_reduce_kernel(int r, int rp, int sp
 
 // y = A x for a dense r x r row-major matrix: one warp per row, four independent accumulators per lane (the
 // one-accumulator form ran at 1.7 TB/s on a matrix that mostly sits in L2)
-__global__ void __launch_bounds__(256) dense_matvec_kernel(int r, const double* __restrict__ A, int ld,
+GINGR_KERNEL((256), dense_matvec_kernel, int r, const double* __restrict__ A, int ld,
                                                            const double* __restrict__ x, double* __restrict__ y,
                                                            int* __restrict__ flag_in, int* __restrict__ flag_out) {
   const int lane = threadIdx.x & 31;
@@ -169,7 +167,7 @@ __global__ void slab_transpose_kernel(int rows, int nc, const double* __restrict
     if (jo < nc && k0 + q < rows) dst[(size_t)(k0 + q) * ld_dst + jo] = tile[threadIdx.x][q];
 }
 
-__global__ void build_regression_system_kernel(int r, int rp, const double* __restrict__ S, double eps,
+GINGR_KERNEL_NB(build_regression_system_kernel, int r, int rp, const double* __restrict__ S, double eps,
                                                double* __restrict__ B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int a = blockIdx.y;
@@ -178,7 +176,7 @@ __global__ void build_regression_system_kernel(int r, int rp, const double* __re
   B[(size_t)(r + a) * rp + b] = a == b ? 1.0 : 0.0;
 }
 
-__global__ void add_vectors_kernel(int n, const double* __restrict__ a, const double* __restrict__ b,
+GINGR_KERNEL_NB(add_vectors_kernel, int n, const double* __restrict__ a, const double* __restrict__ b,
                                    double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + b[i];
@@ -193,14 +191,14 @@ int32_t slab_transpose_enqueue(gingr_ctx* ctx, int rows, int nc, const double* d
 }
 
 int32_t build_regression_system_enqueue(gingr_ctx* ctx, int r, int rp, const double* d_S, double eps, double* d_B) {
-  build_regression_system_kernel<<<dim3(ceil_div(rp, 256), r), 256, 0, ctx->stream>>>(r, rp, d_S, eps, d_B);
+  GINGR_LAUNCH(ctx, build_regression_system_kernel, dim3(ceil_div(rp, 256), r), 256, 0, ctx->stream, r, rp, d_S, eps, d_B);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
 }
 
 int32_t add_vectors_enqueue(gingr_ctx* ctx, int n, const double* d_a, const double* d_b, double* d_out) {
-  add_vectors_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, d_a, d_b, d_out);
+  GINGR_LAUNCH(ctx, add_vectors_kernel, ceil_div(n, 256), 256, 0, ctx->stream, n, d_a, d_b, d_out);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
@@ -225,9 +223,9 @@ int32_t gemv_rows_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double*
     if (smem > 200 * 1024) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "rank too large for gemv_rows shared memory");
   }
   if (nvec == 1)
-    gemv_rows_kernel<1><<<blocks, 256, smem, ctx->stream>>>(rows, r, rp, d_phi, d_v0, d_v0, d_scale, d_out0, d_out0);
+    GINGR_LAUNCH_T(ctx, gemv_rows_kernel, (1), blocks, 256, smem, ctx->stream, rows, r, rp, d_phi, d_v0, d_v0, d_scale, d_out0, d_out0);
   else
-    gemv_rows_kernel<2><<<blocks, 256, smem, ctx->stream>>>(rows, r, rp, d_phi, d_v0, d_v1, d_scale, d_out0, d_out1);
+    GINGR_LAUNCH_T(ctx, gemv_rows_kernel, (2), blocks, 256, smem, ctx->stream, rows, r, rp, d_phi, d_v0, d_v1, d_scale, d_out0, d_out1);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
@@ -241,13 +239,13 @@ int32_t gemvT_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_p
                       const double* d_scale, double* d_part, double* d_out) {
   const int splits = gemvT_splits(ctx, rows);
   if (rows > 0) {
-    gemvT_kernel<<<dim3(ceil_div(rp, 256), splits), 256, 0, ctx->stream>>>(rows, rp, gemvT_rows_per_cta(ctx, rows), d_phi,
+    GINGR_LAUNCH(ctx, gemvT_kernel, dim3(ceil_div(rp, 256), splits), 256, 0, ctx->stream, rows, rp, gemvT_rows_per_cta(ctx, rows), d_phi,
                                                                            d_u, d_part);
     GINGR_LAUNCHED(ctx);
   } else {
     GINGR_CUDA_TRY(ctx, cudaMemsetAsync(d_part, 0, sizeof(double) * rp, ctx->stream));
   }
-  gemvT_reduce_kernel<<<ceil_div(r, 32), 256, 0, ctx->stream>>>(r, rp, splits, d_part, d_scale, d_out);
+  GINGR_LAUNCH(ctx, gemvT_reduce_kernel, ceil_div(r, 32), 256, 0, ctx->stream, r, rp, splits, d_part, d_scale, d_out);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
@@ -255,7 +253,7 @@ int32_t gemvT_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_p
 
 int32_t dense_matvec_enqueue(gingr_ctx* ctx, int r, const double* d_A, int ld, const double* d_x, double* d_y,
                              int* d_flag_in, int* d_flag_out) {
-  dense_matvec_kernel<<<ceil_div(r * 32, 256), 256, 0, ctx->stream>>>(r, d_A, ld, d_x, d_y, d_flag_in, d_flag_out);
+  GINGR_LAUNCH(ctx, dense_matvec_kernel, ceil_div(r * 32, 256), 256, 0, ctx->stream, r, d_A, ld, d_x, d_y, d_flag_in, d_flag_out);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

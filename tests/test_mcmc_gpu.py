@@ -162,6 +162,54 @@ def test_chain_in_one_call_equals_single_steps_and_batch(ctx, oracle):
         c.close()
 
 
+@pytest.mark.parametrize("algo,step_length", [("icp", 1.0), ("icp", 0.5)])
+def test_many_chains_run_as_one_batched_kernel_sequence(ctx, oracle, algo, step_length):
+    """gingr_mcmc_batch with many chains: one launch per step of the kernel sequence serves all chains (batch.cuh,
+    blockIdx.z = chain).  Same chains as solo runs with seed + k -- the Gram of a batched chain runs on fewer CTAs (another
+    summation order), so values agree to rounding (1e-9 relative) and the decisions coincide."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 100, 110, 10, seed=3)
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    gs = api.ProbabilisticSettings(uncertainty=1.5, randomMixture=0.5)
+
+    def chain():
+        reg = api.IcpRegistration(ctx, dm, dt, api.IcpConfiguration(maxIterations=40, initialSigma=2.0, endSigma=0.5))
+        reg.configureProbabilistic(gs)
+        pars = api.ModelFittingParameters(1.0, np.zeros(3), (0.0, 0.0, 0.0), np.zeros(dm.rank))
+        reg.initializeState(general=api.GeneralRegistrationState(pars, np.zeros((dm.M, 3)), globalTransformation=api.RIGID_TRANSFORMS,
+                                                                 stepLength=step_length))
+        return reg
+    n, iters = 48, 6
+    chains = [chain() for _ in range(n)]
+    api.mcmc_batch(chains, 1, seed=500)
+    ctx.synchronize()
+    l0 = ctx.launch_count
+    api.mcmc_batch(chains, iters - 1, seed=500)
+    ctx.synchronize()
+    per_step = (ctx.launch_count - l0) / (iters - 1)
+    assert per_step < 100, f"{per_step} launches per MH step of {n} chains: the batched sequence did not run"
+    for k in (0, 1, 7, n - 1):
+        solo = chain()
+        solo.mcmcChain(iters, 500 + k)
+        v1, c1 = chains[k].mcmcStats()
+        v2, c2 = solo.mcmcStats()
+        assert np.array_equal(c1, c2), (k, c1, c2)
+        np.testing.assert_allclose(v1, v2, rtol=1e-9, atol=1e-9)
+        s1, s2 = chains[k].downloadState(), solo.downloadState()
+        np.testing.assert_allclose(s1.fit, s2.fit, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(s1.modelParameters.shape, s2.modelParameters.shape, rtol=1e-8, atol=1e-9)
+        b1, b2 = chains[k].mcmcBest(), solo.mcmcBest()
+        np.testing.assert_allclose(b1.fit, b2.fit, rtol=1e-9, atol=1e-9)
+        solo.close()
+    # the plan is reused; a different seed rebuilds it
+    api.mcmc_batch(chains, 2, seed=900)
+    ctx.synchronize()
+    assert all(np.all(np.isfinite(c.downloadState().fit)) for c in chains[:4])
+    for c in chains:
+        c.close()
+
+
 def test_run_probabilistic_returns_best_sample(ctx, oracle):
     from gingr_b200 import api
     reg, oalgo, ost, diag, keep = _setup(ctx, oracle, "icp", M=100, N=110, r=10)
