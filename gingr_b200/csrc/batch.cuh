@@ -43,12 +43,16 @@ struct LaunchRecorder {
 };
 
 template <typename F> struct gingr_args_of;
-template <typename... A> struct gingr_args_of<void (*)(A...)> { using type = cuda::std::tuple<A...>; };
+// by-value kernel parameters; a body may take a large struct as `const T&` and then reads it in place (parameter bank of
+// the single form -- __grid_constant__ --, the argument array of the batched form) instead of copying it to local memory
+template <typename T> struct gingr_decay { using type = T; };
+template <typename T> struct gingr_decay<const T&> { using type = T; };
+template <typename... A> struct gingr_args_of<void (*)(A...)> { using type = cuda::std::tuple<typename gingr_decay<A>::type...>; };
 
 #define GINGR_KERNEL_IMPL(bounds_attr, name, ...)                                                                       \
   static __device__ __forceinline__ void name##_body(__VA_ARGS__);                                                      \
   using name##_args = typename gingr_args_of<decltype(&name##_body)>::type;                                             \
-  __global__ void bounds_attr name(const name##_args a) { cuda::std::apply(name##_body, a); }                           \
+  __global__ void bounds_attr name(const __grid_constant__ name##_args a) { cuda::std::apply(name##_body, a); }         \
   __global__ void bounds_attr name##_batched(const name##_args* __restrict__ a) { cuda::std::apply(name##_body, a[blockIdx.z]); } \
   static __device__ __forceinline__ void name##_body(__VA_ARGS__)
 
@@ -62,7 +66,8 @@ template <typename... A> struct gingr_args_of<void (*)(A...)> { using type = cud
   template <GINGR_UNPAREN tdecl> static __device__ __forceinline__ void name##_body(__VA_ARGS__);                       \
   template <GINGR_UNPAREN tdecl>                                                                                        \
   using name##_args = typename gingr_args_of<decltype(&name##_body<GINGR_UNPAREN targs>)>::type;                        \
-  template <GINGR_UNPAREN tdecl> __global__ void __launch_bounds__ bounds name(const name##_args<GINGR_UNPAREN targs> a) { \
+  template <GINGR_UNPAREN tdecl>                                                                                        \
+  __global__ void __launch_bounds__ bounds name(const __grid_constant__ name##_args<GINGR_UNPAREN targs> a) {           \
     cuda::std::apply(name##_body<GINGR_UNPAREN targs>, a);                                                              \
   }                                                                                                                     \
   template <GINGR_UNPAREN tdecl>                                                                                        \

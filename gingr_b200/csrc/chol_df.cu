@@ -166,7 +166,7 @@ __device__ __forceinline__ void mma_tile_lower(double (&acc)[2][4][2], const dou
 
 #include "chol_potrf.cuh"
 
-GINGR_KERNEL((DF_THREADS, 1), chol_df_kernel, DfParams P) {
+GINGR_KERNEL((DF_THREADS, 1), chol_df_kernel, const DfParams& P) {
   extern __shared__ __align__(16) double dsm[];
   double* bufI0 = dsm;                       // stage 0, row operand    | X_{j,j-1} of a diagonal task
   double* bufK0 = dsm + TILE_DOUBLES;        // stage 0, column operand | Z of the finishing product

@@ -291,6 +291,9 @@ GINGR_KERNEL((GRAM_WS_THREADS, 1), gram_ws_kernel, int rows, int rp, const doubl
   for (int si = s_first; si < s_last; ++si) {
     const GramSegment sg = segs[si];
     const bool diag = sg.ta == sg.tb;
+    // a warp whose 64 x 32 piece lies past the matrix (rank far below the tile edge: the small problems of batched chains;
+    // row rp may carry the rhs) only keeps the pipeline's barriers moving; the finish never reads its part of the tile
+    const bool idle = sg.ta * BT + wm * 64 > rp || sg.tb * BT + wn * 32 >= rp;
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -299,6 +302,11 @@ GINGR_KERNEL((GRAM_WS_THREADS, 1), gram_ws_kernel, int rows, int rp, const doubl
     for (int ch = sg.c0; ch < sg.c1; ++ch, ++it) {
       const int stage = it % STAGES;
       mbar_wait(bar0 + 8 * stage, (it / STAGES) & 1);
+      if (idle) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8 * (STAGES + stage));
+        continue;
+      }
       const double* tA = sA + (size_t)stage * BK * PITCH + wm * 64 + g;
       const double* tB = (diag ? sA : sB) + (size_t)stage * BK * PITCH + wn * 32 + g;
       const double* tW = sW + stage * BK;
@@ -321,6 +329,7 @@ GINGR_KERNEL((GRAM_WS_THREADS, 1), gram_ws_kernel, int rows, int rp, const doubl
           for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
     }
+    if (idle) continue;
     double* out = partial + (size_t)sg.slot * BT * BT;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -545,7 +554,8 @@ size_t gram_packed_doubles(const GramPlan& plan) { return (size_t)(plan.nt * (pl
 
 int32_t gram_unpack_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_packed, int ld_out, double* d_out, bool rhs_row) {
   const int tiles = plan.nt * (plan.nt + 1) / 2;
-  const int slices = std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
+  // (chains batched in one launch fill the machine by themselves: batch.cuh)
+  const int slices = ctx->rec ? 1 : std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
   gram_unpack_kernel<<<dim3(plan.nt, plan.nt, slices), 256, 0, ctx->stream>>>(plan.r, plan.rp, ld_out, d_packed, d_out, rhs_row ? 1 : 0);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());

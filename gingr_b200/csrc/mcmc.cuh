@@ -98,7 +98,7 @@ __device__ void mcmc_choose(const McmcDev& p, uint64_t seed, int* __restrict__ m
 
 // the chosen random leaf replaces the informed proposal: all parameters of the current state (snapshot) with one
 // Gaussian perturbation; sigma2 and status are those of the current state (the random generators do not touch them)
-GINGR_KERNEL((256), mcmc_random_override_kernel, McmcDev p, uint64_t seed, int r, const int* __restrict__ mi,
+GINGR_KERNEL((256), mcmc_random_override_kernel, const McmcDev& p, uint64_t seed, int r, const int* __restrict__ mi,
                                                                    const double* __restrict__ s_ds, const int* __restrict__ s_is,
                                                                    const double* __restrict__ s_alpha, double* __restrict__ ds,
                                                                    int* __restrict__ is, double* __restrict__ alpha,
@@ -254,7 +254,7 @@ __device__ double mixture_log_transition(const McmcDev& p, int r, const double* 
   return log(s);
 }
 
-GINGR_KERNEL((256), mcmc_decide_kernel, McmcDev p, int r, int fw_cached, const double* __restrict__ s_ds, const int* __restrict__ s_is,
+GINGR_KERNEL((256), mcmc_decide_kernel, const McmcDev& p, int r, int fw_cached, const double* __restrict__ s_ds, const int* __restrict__ s_is,
                                                           const double* __restrict__ s_alpha, const double* __restrict__ ds,
                                                           const double* __restrict__ alpha, double* __restrict__ md,
                                                           int* __restrict__ mi) {
@@ -327,7 +327,7 @@ struct CopySegments {
   }
 };
 
-GINGR_KERNEL((256), multi_copy_kernel, CopySegments seg) {
+GINGR_KERNEL((256), multi_copy_kernel, const CopySegments& seg) {
   for (int q = 0; q < seg.count; ++q) {
     if (seg.flag[q] && ((*seg.flag[q] != 0) != (seg.when[q] != 0))) continue;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < seg.n[q]; i += (size_t)gridDim.x * 256) seg.dst[q][i] = seg.src[q][i];

@@ -176,7 +176,7 @@ struct ObsArgs {
   double lambda;
 };
 
-GINGR_KERNEL((256), obs_kernel, ObsArgs a, const double* __restrict__ rows /*[4][M] CPD*/,
+GINGR_KERNEL((256), obs_kernel, const ObsArgs& a, const double* __restrict__ rows /*[4][M] CPD*/,
                                                   const double* __restrict__ cp /*[M][3] ICP*/,
                                                   const uint8_t* __restrict__ w01,
                                                   const double* __restrict__ wcnt /*reversed ICP, else null*/,

@@ -208,7 +208,8 @@ int32_t add_vectors_enqueue(gingr_ctx* ctx, int n, const double* d_a, const doub
 int32_t gemv_rows_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_phi, int nvec, const double* d_v0,
                           const double* d_v1, double* d_out0, double* d_out1, const double* d_scale) {
   if (rows <= 0) return GINGR_OK;
-  const int blocks = std::max(1, std::min(ctx->num_sms * 4, ceil_div(rows, 8)));
+  // one row per warp; four when many chains share the launch (batch.cuh) -- a row's dot product does not depend on it
+  const int blocks = std::max(1, std::min(ctx->num_sms * 4, ceil_div(rows, ctx->rec ? 32 : 8)));
   const size_t smem = (size_t)nvec * r * sizeof(double);
   if (smem > 48 * 1024) {
     static bool set1 = false, set2 = false;
