@@ -423,6 +423,7 @@ int32_t ClosestWorkspace::ensure(gingr_ctx* ctx, int nq, int n_search, int T_sea
   GINGR_CUDA_TRY(ctx, part_idx.alloc((size_t)smax * M));
   GINGR_CUDA_TRY(ctx, part_cp.alloc((size_t)3 * std::max(s_surf, s_line) * M));
   GINGR_CUDA_TRY(ctx, d2.alloc((size_t)M));
+  GINGR_CUDA_TRY(ctx, surf_d2.alloc((size_t)M));
   GINGR_CUDA_TRY(ctx, idx.alloc((size_t)M));
   GINGR_CUDA_TRY(ctx, cp.alloc((size_t)3 * M));
   GINGR_CUDA_TRY(ctx, w.alloc((size_t)M));
@@ -444,6 +445,7 @@ void ClosestWorkspace::release() {
   part_idx.release();
   part_cp.release();
   d2.release();
+  surf_d2.release();
   idx.release();
   cp.release();
   w.release();
@@ -511,9 +513,10 @@ int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const M
   const int s_surf = std::min(ws.s_surf, std::max(1, ceil_div(tgt.T, TT / 4)));
   int s_line = std::min(ws.s_line, std::max(1, ceil_div(tpl.T, TT / 4)));
   const bool tgt_grid = tgt.tgrid && tgt.tgrid->built, tpl_grid = tpl.tgrid && tpl.tgrid->built;
+  double* o_sd2 = ws.surf_d2.p + q0;   // not o_d2: the nearest-vertex search below reuses that
   if (method == GINGR_TRIANGULAR_CLOSEST_POINT && tgt_grid) {
-    GINGR_TRY(grid_surface_enqueue(ctx, *tgt.tgrid, M, q_aos, tgt.aos, tgt.tri, o_d2, nullptr, o_cp, order));
-    mean_sqrt_enqueue(ctx, ws, M, 1, o_d2);
+    GINGR_TRY(grid_surface_enqueue(ctx, *tgt.tgrid, M, q_aos, tgt.aos, tgt.tri, o_sd2, nullptr, o_cp, order));
+    mean_sqrt_enqueue(ctx, ws, M, 1, o_sd2);
   } else if (method == GINGR_ALONG_NORMAL_CLOSEST_POINT && tgt_grid) {
     GINGR_TRY(grid_line_enqueue(ctx, *tgt.tgrid, M, q_aos, q_nrm, tgt.aos, tgt.tri, 0, ws.part_d2.p, ws.part_cp.p,
                                 order));
@@ -525,9 +528,9 @@ int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const M
                                                                  ws.part_idx.p, ws.part_cp.p);
     GINGR_LAUNCHED(ctx);
     GINGR_LAUNCH(ctx, surface_reduce_kernel, ceil_div(M, 128), 128, 0, st, M, s_surf, ws.part_d2.p, ws.part_idx.p, ws.part_cp.p,
-                                                            o_d2, nullptr, o_cp);
+                                                            o_sd2, nullptr, o_cp);
     GINGR_LAUNCHED(ctx);
-    mean_sqrt_enqueue(ctx, ws, M, 1, o_d2);
+    mean_sqrt_enqueue(ctx, ws, M, 1, o_sd2);
   } else if (method == GINGR_ALONG_NORMAL_CLOSEST_POINT) {
     // nearest intersection of the line (p, n_p) with the target mesh (:105-110)
     const int s_hit = s_surf;

@@ -30,6 +30,8 @@ struct ClosestWorkspace {
   DevBuf<int32_t> part_idx;   // [smax][nq]
   DevBuf<double> part_cp;     // [max(s_surf, s_line)][nq][3]
   DevBuf<double> d2;          // [nq]
+  DevBuf<double> surf_d2;     // [nq]   triangular flavour: squared distance to the target surface, kept after the search
+                              //        (the point-distance evaluator of an MH step asks for exactly these, mcmc.cuh)
   DevBuf<int32_t> idx;        // [nq]   nearest target vertex
   DevBuf<double> cp;          // [nq][3] corresponding point
   DevBuf<uint8_t> w;          // [nq]   0/1 weight

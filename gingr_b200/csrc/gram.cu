@@ -554,8 +554,7 @@ size_t gram_packed_doubles(const GramPlan& plan) { return (size_t)(plan.nt * (pl
 
 int32_t gram_unpack_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_packed, int ld_out, double* d_out, bool rhs_row) {
   const int tiles = plan.nt * (plan.nt + 1) / 2;
-  // (chains batched in one launch fill the machine by themselves: batch.cuh)
-  const int slices = ctx->rec ? 1 : std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
+  const int slices = std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
   gram_unpack_kernel<<<dim3(plan.nt, plan.nt, slices), 256, 0, ctx->stream>>>(plan.r, plan.rp, ld_out, d_packed, d_out, rhs_row ? 1 : 0);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
@@ -566,7 +565,8 @@ int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_part
                             double add_identity, int L, const double* d_lm_rows, const double* d_lm_A, int ld_out,
                             double* d_out, bool packed, bool lower_only, bool rhs_row) {
   const int tiles = plan.nt * (plan.nt + 1) / 2;
-  const int slices = std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
+  // (chains batched in one launch fill the machine by themselves: batch.cuh)
+  const int slices = ctx->rec ? 1 : std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
   GINGR_LAUNCH(ctx, gram_finish_kernel, dim3(plan.nt, plan.nt * slices), 256, 0, ctx->stream, plan.r, plan.rp, ld_out, d_partial,
                                                                       plan.d_tile_first.p, d_sqrt_lambda, add_identity,
                                                                       L, d_lm_rows, d_lm_A, d_out, packed ? 1 : (lower_only ? 2 : 0),

@@ -415,7 +415,10 @@ static void mcmc_drop_graph(McmcState* mc) {
 
 // EvaluatorWrapper.logValue pieces of the state in the working buffers (fit, alpha): out[0] = ModelEvaluator,
 // out[1] = IndependentPointDistanceEvaluator
-static int32_t enqueue_log_value(gingr_registration* g, const double* d_fit, const double* d_alpha, double* d_out) {
+// d_surface_d2 (optional): squared distances of ALL points of d_fit to the target surface when a correspondence search on
+// the same points has just produced them (ClosestWorkspace::surf_d2) -- the same scan is then not run a second time
+static int32_t enqueue_log_value(gingr_registration* g, const double* d_fit, const double* d_alpha, double* d_out,
+                                 const double* d_surface_d2 = nullptr) {
   gingr_ctx* ctx = g->ctx;
   McmcState* mc = g->mcmc;
   const gingr_model* m = g->model;
@@ -434,10 +437,15 @@ static int32_t enqueue_log_value(gingr_registration* g, const double* d_fit, con
       GINGR_LAUNCHED(ctx);
       q = mc->q_pts.p;
     }
-    MeshView tv;
-    tv.n = N; tv.aos = tg->aos.p; tv.soa = tg->verts.p; tv.T = tg->T; tv.tri = tg->tri.p; tv.tgrid = tg->tgrid;
-    GINGR_TRY(surface_distance_enqueue(ctx, mc->ws_m2t, nq, q, tv));
-    GINGR_LAUNCH(ctx, mcmc_distance_logpdf_kernel, 1, 256, 0, st, nq, mc->ws_m2t.d2.p, sd, mode == GINGR_EVAL_SYMMETRIC ? 0.5 : 1.0, acc,
+    const double* d2 = mc->ws_m2t.d2.p;
+    if (d_surface_d2 && mc->n_model_ids == 0) {
+      d2 = d_surface_d2;
+    } else {
+      MeshView tv;
+      tv.n = N; tv.aos = tg->aos.p; tv.soa = tg->verts.p; tv.T = tg->T; tv.tri = tg->tri.p; tv.tgrid = tg->tgrid;
+      GINGR_TRY(surface_distance_enqueue(ctx, mc->ws_m2t, nq, q, tv));
+    }
+    GINGR_LAUNCH(ctx, mcmc_distance_logpdf_kernel, 1, 256, 0, st, nq, d2, sd, mode == GINGR_EVAL_SYMMETRIC ? 0.5 : 1.0, acc,
                                                    d_out + 1, m->r, d_alpha);
     GINGR_LAUNCHED(ctx);
     acc = 1;
@@ -517,6 +525,16 @@ static int32_t enqueue_posterior_mean_coeffs(gingr_registration* g, double* d_ou
   return chol_backsolve_enqueue(g->ctx, m->r, g->Mx.p, m->rp, g->Mx.p + (size_t)m->r * m->rp, d_out, g->flags.p);
 }
 
+// the surface distances the posterior phase of g->fit left behind, when its correspondence search was the triangular
+// closest point of the fit's vertices on the target (the evaluator's own query)
+static const double* posterior_surface_d2(const gingr_registration* g) {
+  const gingr_config& cfg = g->cfg;
+  return (cfg.algorithm == GINGR_ALGO_ICP && cfg.correspondence_method == GINGR_TRIANGULAR_CLOSEST_POINT &&
+          !cfg.reverse_correspondence_direction && g->ctx->nranks == 1)
+             ? g->closest.surf_d2.p
+             : nullptr;
+}
+
 // Posterior + evaluators of the device-resident state: the chain starts from it.
 static int32_t mcmc_prime(gingr_registration* g) {
   gingr_ctx* ctx = g->ctx;
@@ -532,7 +550,7 @@ static int32_t mcmc_prime(gingr_registration* g) {
   GINGR_TRY(enqueue_posterior_phase(g));
   GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(mc->raw_cur.p, g->Mx_raw.p, sizeof(double) * (size_t)(r + 1) * rp, cudaMemcpyDeviceToDevice, st));
   GINGR_TRY(enqueue_posterior_mean_coeffs(g, mc->cm_cur.p));
-  GINGR_TRY(enqueue_log_value(g, g->fit.p, g->alpha.p, mc->md.p + MD_LP_CUR));
+  GINGR_TRY(enqueue_log_value(g, g->fit.p, g->alpha.p, mc->md.p + MD_LP_CUR, posterior_surface_d2(g)));
   if (g->last_out.step_length == 1.0)   // the informed density of the start state (fit on its own posterior)
     GINGR_TRY(enqueue_log_transition(g, g->Mx_raw.p, mc->cm_cur.p, g->ds.p, g->is.p, g->fit.p, mc->md.p + MD_TINF_CUR));
   // best = current
@@ -596,8 +614,8 @@ static int32_t enqueue_mcmc_step(gingr_registration* g, uint64_t seed) {
   }
   GINGR_TRY(enqueue_to_mesh(g, step_length, g->fit.p, g->alpha.p, mc->s_alpha.p, &to_mesh));
   GINGR_TRY(enqueue_log_transition(g, g->Mx_raw.p, mc->cm_prop.p, g->ds.p, g->is.p, to_mesh, mc->md.p + MD_TINF_BW));
-  // 7. evaluators of the proposal
-  GINGR_TRY(enqueue_log_value(g, g->fit.p, g->alpha.p, mc->md.p + MD_LP_PROP));
+  // 7. evaluators of the proposal (its posterior phase, step 5, searched the same points)
+  GINGR_TRY(enqueue_log_value(g, g->fit.p, g->alpha.p, mc->md.p + MD_LP_PROP, posterior_surface_d2(g)));
   // 8. accept / reject
   GINGR_LAUNCH(ctx, mcmc_decide_kernel, 1, 256, 0, st, mc->dev, r, fw_cached ? 1 : 0, mc->s_ds.p, mc->s_is.p, mc->s_alpha.p, g->ds.p, g->alpha.p, mc->md.p, mc->mi.p);
   GINGR_LAUNCHED(ctx);
