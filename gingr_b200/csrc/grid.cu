@@ -26,10 +26,12 @@ namespace gingr {
 
 #ifdef GINGR_GRID_STATS
 // tuning build only (tools/build_variant.sh stats grid.cu -DGINGR_GRID_STATS): event counters of the searches
-__device__ unsigned long long grid_stats[8];
+__device__ unsigned long long grid_stats[24];   // 0-7 thread-per-query searches, 8-23 the warp-per-query surface search
 #define GSTAT(k, n) atomicAdd(&grid_stats[k], (unsigned long long)(n))
+#define GSTATW(k, n) do { if ((threadIdx.x & 31) == 0) atomicAdd(&grid_stats[8 + (k)], (unsigned long long)(n)); } while (0)
 #else
 #define GSTAT(k, n) ((void)0)
+#define GSTATW(k, n) ((void)0)
 #endif
 
 constexpr int BB_BLOCKS = 128;
@@ -659,11 +661,14 @@ __device__ __forceinline__ void warp_best_reduce(WarpBest& b) {
   b.z = __shfl_sync(0xffffffffu, b.z, who);
 }
 
-__global__ void __launch_bounds__(WQ_WARPS * 32) grid_surface_warp_kernel(
+#ifndef WQ_MINB
+#define WQ_MINB 4   // 128 registers (a few spills in the cell walks); 3 (168, none) measured 11 % slower, 5 and 6 the same as 4
+#endif
+__global__ void __launch_bounds__(WQ_WARPS * 32, WQ_MINB) grid_surface_warp_kernel(
     int M, const double4* __restrict__ order, const double* __restrict__ q, int T, const GridParams* __restrict__ gp,
     const int32_t* __restrict__ cell_start, const int32_t* __restrict__ entries, const float4* __restrict__ tri_box,
     const double* __restrict__ verts /*AoS*/, const int32_t* __restrict__ tri, double* __restrict__ d2,
-    int32_t* __restrict__ tri_out, double* __restrict__ cp) {
+    int32_t* __restrict__ tri_out, double* __restrict__ cp, int descend /*GINGR_K2_DESCEND, A/B measurements*/) {
   __shared__ int s_queue[WQ_WARPS][WQ_CAP];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int slot = blockIdx.x * WQ_WARPS + w;
@@ -677,8 +682,12 @@ __global__ void __launch_bounds__(WQ_WARPS * 32) grid_surface_warp_kernel(
   const GridParams g = *gp;
 
   // exact evaluation of the queued candidates, 32 at a time; the warp's best is re-established afterwards
+  int phase = 0;   // statistics only: 0 seed, 1 refine, 2 ball
+  (void)phase;
+  GSTATW(0, 1);
   auto flush = [&]() {
     __syncwarp();
+    GSTATW(8, 1); GSTATW(7, qn);
     WarpBest mine = best;
     for (int base = 0; base < qn; base += 32) {
       const int k = base + lane;
@@ -719,10 +728,54 @@ __global__ void __launch_bounds__(WQ_WARPS * 32) grid_surface_warp_kernel(
     if (qn > WQ_CAP - 32) flush();
   };
   auto offer_entries = [&](int e0, int e1, int x, int y, int z, int sh) {
+    GSTATW(phase == 0 ? 2 : (phase == 1 ? 3 : 6), e1 - e0);
     for (int base = e0; base < e1; base += 32) {
       const int e = base + lane;
       const bool valid = e < e1;
       offer(valid, valid ? entries[e] : 0, x, y, z, sh);
+    }
+  };
+
+  int u1x = -9, u1y = -9, u1z = -9, u2x = -9, u2y = -9, u2z = -9;   // centres of the two refinement blocks (fine cells)
+  auto refined = [&](int x, int y, int z) {
+    return (abs(x - u1x) <= 1 && abs(y - u1y) <= 1 && abs(z - u1z) <= 1) || (abs(x - u2x) <= 1 && abs(y - u2y) <= 1 && abs(z - u2z) <= 1);
+  };
+  // a coarse cell of the ball walk that passed its box test: its 64 children (nested 4 x 4 x 4 blocking: contiguous in
+  // cell_start), two per lane, are box-tested themselves and only the passing fine cells offer their entries -- a far
+  // query's ball touches the surface in a cap that is a few FINE cells wide, a coarse cell holds ~16 occupied ones
+  auto walk_fine = [&](int ci, int x, int y, int z) {   // (x, y, z) at level 1 (edge 4h), ci = index of its first fine cell
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int c = lane + 32 * half;
+      const int xx = (x << 2) | (c & 3), yy = (y << 2) | ((c >> 2) & 3), zz = (z << 2) | (c >> 4);
+      int e0 = cell_start[ci + c], e1 = cell_start[ci + c + 1];
+      if (e1 > e0 && (refined(xx, yy, zz) || box_dist2(g, qx, qy, qz, xx, yy, zz, g.h) > best.d)) e1 = e0;
+      unsigned m = __ballot_sync(0xffffffffu, e1 > e0);
+      GSTATW(10, __popc(m));
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        offer_entries(__shfl_sync(0xffffffffu, e0, src), __shfl_sync(0xffffffffu, e1, src), __shfl_sync(0xffffffffu, xx, src),
+                      __shfl_sync(0xffffffffu, yy, src), __shfl_sync(0xffffffffu, zz, src), 0);
+      }
+    }
+  };
+  auto walk_mid = [&](int ci, int x, int y, int z) {    // (x, y, z) at level 2 (edge 16h): children at level 1
+    const double h1 = g.h * 4.0;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int c = lane + 32 * half;
+      const int xx = (x << 2) | (c & 3), yy = (y << 2) | ((c >> 2) & 3), zz = (z << 2) | (c >> 4);
+      const int cc = ci + (c << 6);
+      bool pass = cell_start[cc + 64] > cell_start[cc];
+      if (pass && box_dist2(g, qx, qy, qz, xx, yy, zz, h1) > best.d) pass = false;
+      unsigned m = __ballot_sync(0xffffffffu, pass);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        walk_fine(__shfl_sync(0xffffffffu, cc, src), __shfl_sync(0xffffffffu, xx, src), __shfl_sync(0xffffffffu, yy, src),
+                  __shfl_sync(0xffffffffu, zz, src));
+      }
     }
   };
 
@@ -741,6 +794,7 @@ __global__ void __launch_bounds__(WQ_WARPS * 32) grid_surface_warp_kernel(
       const int span = 1 << (3 * sh);
       for (int k = 0; k <= K_LEVEL[l] && !seeded; ++k) {
         const int side = 2 * k + 1, vol = side * side * side;
+        GSTATW(1, vol);
         double bd = INFINITY;
         int bc = 0x7fffffff;   // packed (z, y, x) of the lane's nearest occupied cell, 10 bits each
         for (int c = lane; c < vol; c += 32) {
@@ -792,13 +846,21 @@ __global__ void __launch_bounds__(WQ_WARPS * 32) grid_surface_warp_kernel(
     }
     if (seeded && best.d < INFINITY) {
       // ---- refine: the 27 fine cells around the candidate's own location, twice -----------------------------------
+      // A cell examined here has had all the triangles it is the home cell of offered against a bound that was not
+      // tighter than any later one: the second round and the ball walk below skip the cells of the earlier blocks
+      // (their survivors would only be evaluated a second time).
+      phase = 1;
       for (int round = 0; round < 2; ++round) {
         const int ux = cell_coord(best.x, g.ox, g.inv_h, g.nx), uy = cell_coord(best.y, g.oy, g.inv_h, g.ny),
                   uz = cell_coord(best.z, g.oz, g.inv_h, g.nz);
+        if (round == 0) { u1x = ux; u1y = uy; u1z = uz; }
+        u2x = ux; u2y = uy; u2z = uz;
+        if (round == 1 && ux == u1x && uy == u1y && uz == u1z) break;
         int x = 0, y = 0, z = 0, e0 = 0, e1 = 0;
         if (lane < 27) {
           x = ux - 1 + lane % 3; y = uy - 1 + (lane / 3) % 3; z = uz - 1 + lane / 9;
-          if (x >= 0 && y >= 0 && z >= 0 && x < g.nx && y < g.ny && z < g.nz) {
+          const bool seen = round == 1 && abs(x - u1x) <= 1 && abs(y - u1y) <= 1 && abs(z - u1z) <= 1;
+          if (!seen && x >= 0 && y >= 0 && z >= 0 && x < g.nx && y < g.ny && z < g.nz) {
             const int c = cell_index(g, x, y, z);
             e0 = cell_start[c]; e1 = cell_start[c + 1];
             if (e1 > e0 && box_dist2(g, qx, qy, qz, x, y, z, g.h) > best.d) e1 = e0;
@@ -825,23 +887,38 @@ __global__ void __launch_bounds__(WQ_WARPS * 32) grid_surface_warp_kernel(
         if (sx < 1 || sy < 1 || sz < 1) { done = true; break; }   // cannot happen: the candidate lies inside the ball
         if ((long long)sx * sy * sz > 4096) continue;
         const int vol = sx * sy * sz;
+        phase = 2;
+        GSTATW(4, vol); GSTATW(9, l);
         const double hl = g.h * (double)(1 << sh);
         const int span = 1 << (3 * sh);
+        // c -> (x, y, z) without integer divisions: c < 4096, so the float quotients (error < 1e-3 / n, the fraction of
+        // (c + 0.5) / n is at least 0.5 / n from an integer) floor to the exact values
+        const int sxy = sx * sy;
+        const float inv_sx = 1.0f / (float)sx, inv_sxy = 1.0f / (float)sxy;
         for (int base = 0; base < vol; base += 32) {
           const int c = base + lane;
           int x = 0, y = 0, z = 0, e0 = 0, e1 = 0;
           if (c < vol) {
-            x = x0 + c % sx; y = y0 + (c / sx) % sy; z = z0 + c / (sx * sy);
+            const int zc = (int)(((float)c + 0.5f) * inv_sxy), rem = c - zc * sxy, yc = (int)(((float)rem + 0.5f) * inv_sx);
+            x = x0 + rem - yc * sx; y = y0 + yc; z = z0 + zc;
             const int ci = cell_index(g, x << sh, y << sh, z << sh);
             e0 = cell_start[ci]; e1 = cell_start[ci + span];
-            if (e1 > e0 && box_dist2(g, qx, qy, qz, x, y, z, hl) > best.d) e1 = e0;
+            if (e1 > e0 && ((l == 0 && refined(x, y, z)) || box_dist2(g, qx, qy, qz, x, y, z, hl) > best.d)) e1 = e0;
           }
+          int ci0 = 0;
+          if (c < vol) ci0 = cell_index(g, x << sh, y << sh, z << sh);
           unsigned m = __ballot_sync(0xffffffffu, e1 > e0);
+          GSTATW(5, __popc(m));
           while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;
-            offer_entries(__shfl_sync(0xffffffffu, e0, src), __shfl_sync(0xffffffffu, e1, src), __shfl_sync(0xffffffffu, x, src),
-                          __shfl_sync(0xffffffffu, y, src), __shfl_sync(0xffffffffu, z, src), sh);
+            const int xs = __shfl_sync(0xffffffffu, x, src), ys = __shfl_sync(0xffffffffu, y, src), zs = __shfl_sync(0xffffffffu, z, src);
+            if (l == 0 || !descend)
+              offer_entries(__shfl_sync(0xffffffffu, e0, src), __shfl_sync(0xffffffffu, e1, src), xs, ys, zs, sh);
+            else if (l == 1)
+              walk_fine(__shfl_sync(0xffffffffu, ci0, src), xs, ys, zs);
+            else
+              walk_mid(__shfl_sync(0xffffffffu, ci0, src), xs, ys, zs);
           }
         }
         flush();
@@ -873,9 +950,10 @@ int32_t grid_surface_enqueue(gingr_ctx* ctx, const SpatialGrid& g, int M, const 
                              const int32_t* d_tri, double* d_d2, int32_t* d_tri_out, double* d_cp, const SpatialGrid* order) {
   if (!g.built || !g.triangles) return gingr_fail(ctx, GINGR_ERR_ARG, "grid_surface: triangle grid not built");
   if (warp_search_wanted()) {
+    static const int descend = [] { const char* e = getenv("GINGR_K2_DESCEND"); return e ? atoi(e) : 1; }();
     grid_surface_warp_kernel<<<ceil_div(M, WQ_WARPS), WQ_WARPS * 32, 0, ctx->stream>>>(
         M, order_ptr(order, M), d_q, g.n_items, g.params.p, g.cell_start.p, g.entries.p, g.tri_box.p, d_verts_aos, d_tri, d_d2,
-        d_tri_out, d_cp);
+        d_tri_out, d_cp, descend);
     GINGR_LAUNCHED(ctx);
     GINGR_CUDA_TRY(ctx, cudaGetLastError());
     return GINGR_OK;
@@ -996,9 +1074,9 @@ int32_t grid_line_enqueue(gingr_ctx* ctx, const SpatialGrid& g, int M, const dou
 #ifdef GINGR_GRID_STATS
 extern "C" GINGR_API int32_t gingr_debug_grid_stats(unsigned long long* out, int32_t reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, gingr::grid_stats, sizeof(unsigned long long) * 8);
+  cudaMemcpyFromSymbol(out, gingr::grid_stats, sizeof(unsigned long long) * 24);
   if (reset) {
-    unsigned long long z[8] = {0};
+    unsigned long long z[24] = {0};
     cudaMemcpyToSymbol(gingr::grid_stats, z, sizeof(z));
   }
   return 0;
