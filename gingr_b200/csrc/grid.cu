@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256) grid_bbox_kernel(int n, VertexArray v, do
   if (threadIdx.x < 6) part[blockIdx.x * 6 + threadIdx.x] = red[threadIdx.x][0];
 }
 
-__global__ void grid_params_kernel(int n, int cap_cells, const double* __restrict__ part, GridParams* __restrict__ gp) {
+__global__ void grid_params_kernel(int n, int cap_cells, const double* __restrict__ part, GridParams* __restrict__ gp,
+                                   double cell_scale /*cell edge = cell_scale * diagonal / sqrt(n)*/) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int b = 0; b < BB_BLOCKS; ++b)
@@ -87,7 +88,7 @@ __global__ void grid_params_kernel(int n, int cap_cells, const double* __restric
     g.h = 1.0; g.inv_h = 1.0; g.margin = 0.0;
     g.nx = g.ny = g.nz = 1;
   } else {
-    double h = 2.0 * diag / sqrt((double)(n > 0 ? n : 1));
+    double h = cell_scale * diag / sqrt((double)(n > 0 ? n : 1));
     int nx, ny, nz;
     for (;;) {
       const double m = 1e-6 * h;
@@ -329,7 +330,8 @@ static int32_t grid_common_head(gingr_ctx* ctx, SpatialGrid& g, int n, VertexArr
   cudaStream_t st = ctx->stream;
   grid_bbox_kernel<<<BB_BLOCKS, 256, 0, st>>>(n, v, g.bbox_part.p);
   GINGR_LAUNCHED(ctx);
-  grid_params_kernel<<<1, 32, 0, st>>>(n, g.cap_cells, g.bbox_part.p, g.params.p);
+  static const double cell_scale = [] { const char* e = getenv("GINGR_K2_CELL_SCALE"); return e && atof(e) > 0.0 ? atof(e) : 2.0; }();
+  grid_params_kernel<<<1, 32, 0, st>>>(n, g.cap_cells, g.bbox_part.p, g.params.p, cell_scale);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaMemsetAsync(g.fill.p, 0, sizeof(int32_t) * ((size_t)g.cap_cells + 1), st));
   return GINGR_OK;
