@@ -422,7 +422,21 @@ int32_t GramPlan::build(gingr_ctx* ctx, int rows_, int r_, int rp_, int max_cta)
   if (rem > 0) {
     // last round: rem main CTAs take chunks [0, K1) of their tile, the other n - rem CTAs share the bottom
     // slabs [K1, K) of all rem tiles; every CTA ends up with ~ rem K / n chunks
-    const int K1 = (int)((int64_t)K * rem / n);
+    // equal chunk counts would leave the n - rem tail CTAs late: each of their ~rem / (n - rem) + 1 pieces costs a
+    // pipeline refill and a 128 KB partial tile on top of its chunks (about 0.75 chunk times, from the phase times of the
+    // 8-GPU iteration: 235 chunks per tile, 12 tail CTAs with 11-12 pieces each).  K1 minimises the later of the two.
+    int K1 = (int)((int64_t)K * rem / n);
+    {
+      const double ov = 0.75, pieces = (double)rem / (n - rem) + 1.0;
+      double best_t = 1e300;
+      int best_k = K1;
+      for (int k = std::max(0, K1 - 2); k <= std::min(K, K1 + 8); ++k) {
+        const double t_main = k > 0 ? k + ov : 0.0, t_tail = (double)rem * (K - k) / (n - rem) + (K - k > 0 ? ov * pieces : 0.0);
+        const double t = std::max(t_main, t_tail);
+        if (t < best_t) { best_t = t; best_k = k; }
+      }
+      K1 = best_k;
+    }
     const int base_tile = full_rounds * n;
     for (int c = 0; c < rem; ++c)
       if (K1 > 0) list.push_back({c, base_tile + c, 0, K1});
@@ -554,7 +568,7 @@ size_t gram_packed_doubles(const GramPlan& plan) { return (size_t)(plan.nt * (pl
 
 int32_t gram_unpack_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_packed, int ld_out, double* d_out, bool rhs_row) {
   const int tiles = plan.nt * (plan.nt + 1) / 2;
-  const int slices = std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
+  const int slices = std::max(1, std::min(64, (8 * ctx->num_sms) / std::max(tiles, 1)));
   gram_unpack_kernel<<<dim3(plan.nt, plan.nt, slices), 256, 0, ctx->stream>>>(plan.r, plan.rp, ld_out, d_packed, d_out, rhs_row ? 1 : 0);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
@@ -566,7 +580,8 @@ int32_t gram_finish_enqueue(gingr_ctx* ctx, GramPlan& plan, const double* d_part
                             double* d_out, bool packed, bool lower_only, bool rhs_row) {
   const int tiles = plan.nt * (plan.nt + 1) / 2;
   // (chains batched in one launch fill the machine by themselves: batch.cuh)
-  const int slices = ctx->rec ? 1 : std::max(1, std::min(64, (2 * ctx->num_sms) / std::max(tiles, 1)));
+  // ~8 CTAs per SM: the kernel is a latency-bound stream of a few dependent loads per element
+  const int slices = ctx->rec ? 1 : std::max(1, std::min(64, (8 * ctx->num_sms) / std::max(tiles, 1)));
   GINGR_LAUNCH(ctx, gram_finish_kernel, dim3(plan.nt, plan.nt * slices), 256, 0, ctx->stream, plan.r, plan.rp, ld_out, d_partial,
                                                                       plan.d_tile_first.p, d_sqrt_lambda, add_identity,
                                                                       L, d_lm_rows, d_lm_A, d_out, packed ? 1 : (lower_only ? 2 : 0),

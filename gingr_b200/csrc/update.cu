@@ -116,39 +116,49 @@ __global__ void compact_gather_kernel(int M, int nranks, int Mmax, const double*
   fit[e] = gathered[(size_t)rk * 3 * Mmax + 3 * (i - start) + d];
 }
 
-// ---- CPD scalars for the E-step from the state block --------------------------------------------
-__global__ void __launch_bounds__(1024) cpd_estep_scalars_kernel(const double* __restrict__ ds, double w, double ratio,
-                                                                 int n3, const double* __restrict__ fit,
-                                                                 double target_maxabs, double* scal) {
-  // max |coordinate| of the current fit -> bound of the pair distances (scal[7], gauss_exp2_tab<SAFE>)
-  __shared__ double red[32];
-  double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
-  int k = threadIdx.x;
-  for (; k + 3072 < n3; k += 4096) {
-    m0 = fmax(m0, fabs(fit[k]));
-    m1 = fmax(m1, fabs(fit[k + 1024]));
-    m2 = fmax(m2, fabs(fit[k + 2048]));
-    m3 = fmax(m3, fabs(fit[k + 3072]));
+// ---- CPD: fit and scalars for the E-step from the state block ----------------------------------
+// What the CPD E-step needs from the fit, in one pass and one launch (were four: two finite checks, the AoS -> SoA copy and a
+// one-block reduction): fit_soa, the failure flag for a non-finite fit / sigma2, and -- by the last block to finish, which
+// also resets the two words of `sync` for the next launch -- the scalars: scal[0] = sigma2, scal[1] = a = 1, scal[2] = c
+// (CPD.scala:69-70), scal[7] = bound of the pair distances from max |coordinate| of fit and target (gauss_exp2_tab<SAFE>).
+// The maximum is exact in any order, so the result does not depend on which block comes last.
+__global__ void __launch_bounds__(256) cpd_prepare_kernel(int M, const double* __restrict__ fit /*AoS*/, double* __restrict__ fit_soa,
+                                                          const double* __restrict__ ds, double w, double ratio,
+                                                          double target_maxabs, int* __restrict__ fail_flag,
+                                                          unsigned long long* __restrict__ sync /*[2]: max bits, ticket*/,
+                                                          double* __restrict__ scal) {
+  __shared__ double red[8];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double m = 0.0;
+  int bad = 0;
+  if (i < M) {
+    const double x = fit[3 * i], y = fit[3 * i + 1], z = fit[3 * i + 2];
+    fit_soa[i] = x; fit_soa[M + i] = y; fit_soa[2 * (size_t)M + i] = z;
+    bad = !(fabs(x) < INFINITY) || !(fabs(y) < INFINITY) || !(fabs(z) < INFINITY);
+    m = fmax(fmax(fabs(x), fabs(y)), fabs(z));
   }
-  for (; k < n3; k += 1024) m0 = fmax(m0, fabs(fit[k]));
-  double m = fmax(fmax(m0, m1), fmax(m2, m3));
+  bad = __syncthreads_or(bad);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x >= 32) return;
-  m = red[threadIdx.x];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  red[0] = m;
   if (threadIdx.x != 0) return;
+  for (int k = 1; k < 8; ++k) m = fmax(m, red[k]);
+  if (bad) *fail_flag = 1;
+  atomicMax(sync, (unsigned long long)__double_as_longlong(m));   // non-negative doubles order like their bit patterns
+  __threadfence();
+  if (atomicAdd(sync + 1, 1ULL) != (unsigned long long)gridDim.x - 1) return;
+  __threadfence();
+  const double fmaxabs = __longlong_as_double((long long)atomicExch(sync, 0ULL));
+  sync[1] = 0ULL;
   const double sigma2 = ds[DS_SIGMA2];
+  if (!(fabs(sigma2) < INFINITY)) *fail_flag = 1;
   const double t = 2.0 * 3.14159265358979323846 * sigma2;
   scal[0] = sigma2;
   scal[1] = 1.0;
   scal[2] = w / (1.0 - w) * (t * sqrt(t)) * ratio;  // CPD.scala:69-70
-  const double s = red[0] + target_maxabs;
-  scal[7] = 3.0 * s * s;
+  const double s2 = fmaxabs + target_maxabs;
+  scal[7] = 3.0 * s2 * s2;
 }
 
 // xpx total (fixed order) appended behind the row block for the all-reduce.  One CTA of 256 threads.
@@ -686,6 +696,7 @@ struct gingr_registration {
   bool skip_fit_refresh = false;        // MH step: the proposal's fit is evaluated after the random override
   const int* sample_counter = nullptr;  // device counter keyed into the posterior-sample stream (null: the iteration)
   struct McmcState* mcmc = nullptr;  // Metropolis-Hastings chain state (mcmc.cuh), created by gingr_mcmc_configure
+  DevBuf<unsigned long long> prep_sync;   // [2] cpd_prepare_kernel: running maximum and block ticket (self-resetting)
   DevBuf<double> wrow, u, resid, inst_a, inst_b, newshape, fit_local, gathered, fit;
   DevBuf<double> vec;          // 8 * rp scratch vectors
   DevBuf<double> gt_part, sums_part, pro_part, pro_sums;
@@ -1346,6 +1357,7 @@ int32_t gingr_registration_create(gingr_ctx* ctx, const gingr_model* model, cons
   A(g->rows_ext.alloc((size_t)4 * M + 8));
   A(g->Mx.alloc((size_t)(r + 8) * rp));
   if (ctx->nranks > 1) A(g->Mx_packed.alloc(gram_packed_doubles(g->gram) + rp));
+  A(g->prep_sync.alloc(2)); A(cudaMemsetAsync(g->prep_sync.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
   A(g->wrow.alloc((size_t)3 * Mmax)); A(g->u.alloc((size_t)3 * Mmax)); A(g->resid.alloc((size_t)3 * Mmax));
   A(g->inst_a.alloc((size_t)3 * Mmax)); A(g->inst_b.alloc((size_t)3 * Mmax));
   A(g->newshape.alloc((size_t)3 * Mmax)); A(g->fit_local.alloc((size_t)3 * Mmax));
@@ -1390,7 +1402,7 @@ int32_t gingr_registration_destroy(gingr_registration* g) {
   g->estep.release(); g->closest.release(); g->gram.release();
   g->fit_pgrid.release(); g->fit_tgrid.release();
   g->fit_normals.release(); g->fit_soa.release(); g->rev_tid.release(); g->rev_cp.release(); g->rev_wcnt.release(); g->rev_scratch.release();
-  g->rows_ext.release(); g->Mx.release(); g->wrow.release(); g->u.release(); g->resid.release(); g->inst_a.release(); g->inst_b.release();
+  g->prep_sync.release(); g->rows_ext.release(); g->Mx.release(); g->wrow.release(); g->u.release(); g->resid.release(); g->inst_a.release(); g->inst_b.release();
   g->newshape.release(); g->fit_local.release(); g->gathered.release(); g->fit.release(); g->vec.release();
   g->gt_part.release(); g->sums_part.release(); g->pro_part.release(); g->pro_sums.release();
   g->ds.release(); g->is.release(); g->flags.release(); g->alpha.release(); g->cholws.release();
@@ -1520,12 +1532,10 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
   const double* icp_wcnt = nullptr;
   if (cfg.algorithm == GINGR_ALGO_CPD) {
     // non-finite fit / sigma2 / target: the reference's P is all NaN and the posterior fails
-    GINGR_TRY(validate_finite_enqueue(ctx, 3 * M, g->fit.p, g->is.p + IS_FAIL_POST));
-    GINGR_TRY(validate_finite_enqueue(ctx, 1, g->ds.p + DS_SIGMA2, g->is.p + IS_FAIL_POST));
     if (tg->nonfinite) GINGR_TRY(validate_finite_enqueue(ctx, 3 * tg->N_total, tg->verts.p, g->is.p + IS_FAIL_POST));
-    GINGR_TRY(aos_to_soa_enqueue(ctx, M, g->fit.p, g->estep.fit_soa.p));
-    cpd_estep_scalars_kernel<<<1, 1024, 0, st>>>(g->ds.p, cfg.w, (double)M / (double)tg->N_total, 3 * M, g->fit.p,
-                                                tg->maxabs, g->estep.scal.p);
+    cpd_prepare_kernel<<<ceil_div(M, 256), 256, 0, st>>>(M, g->fit.p, g->estep.fit_soa.p, g->ds.p, cfg.w,
+                                                         (double)M / (double)tg->N_total, tg->maxabs, g->is.p + IS_FAIL_POST,
+                                                         g->prep_sync.p, g->estep.scal.p);
     GINGR_LAUNCHED(ctx);
     if (tg->N > 0) {
       EstepEvents ee;
