@@ -369,7 +369,10 @@ def run_ours(args):
                         "evaluators, accept / reject on the device), divided among the GPUs (replicas, no collective)",
             "gpus": world, "chains": 1024, "mh_steps_per_chain": c5["steps"], "chain_steps_per_s": float(agg[0]) / float(tmax[0]),
             "chain_steps_per_s_per_gpu": float(agg[0]) / float(tmax[0]) / world, "acceptance_rate": float(agg[1]) / (1024 * (c5["steps"] + 3)),
-            "launches_per_chain_step": float(agg[2]) / float(agg[0]), "finite": c5["finite"]}
+            "launches_per_chain_step": float(agg[2]) / float(agg[0]),
+            "launches_per_mh_step_per_gpu": float(agg[2]) / world / c5["steps"],
+            "path": "one batched kernel sequence per MH step for all chains of a GPU (blockIdx.z = chain, gingr_b200/csrc/batch.cuh)",
+            "finite": c5["finite"]}
         if world == 1:
             secondary["c1_icp"] = bs.c1_icp(ctx)
             secondary["c3_multiresolution"] = bs.c3_pipeline(ctx)

@@ -148,7 +148,7 @@ def icp_200k(ctx, root, iters=5, rank=64):
     return out
 
 
-def c5_mcmc(ctx, world, rank, n_total=1024, iters=20, rho=0.5):
+def c5_mcmc(ctx, world, rank, n_total=1024, iters=50, rho=0.5):
     """BASELINE configs[4]: n_total independent Metropolis-Hastings chains (informed ICP proposal mixed with the random
     pose / shape proposals, point-distance + prior evaluators, accept / reject on the device) of the C1 size, divided among
     the ranks (replicas, no collective).  Returns this rank's (steps, seconds, accepted); bench.py aggregates."""
