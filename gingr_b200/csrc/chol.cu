@@ -363,16 +363,18 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(int n, const double
 
 // n <= 64 (one block): plain right-looking back substitution by 64 threads -- the general kernel would spend 50 us
 // inverting the diagonal block with one thread per column, which only pays when it hides behind the flag waits.
-GINGR_KERNEL((32), chol_backsolve_small_kernel, int n, const double* __restrict__ L, int ld,
-                                                                  const double* __restrict__ z, double* __restrict__ c) {
+GINGR_KERNEL((128), chol_backsolve_small_kernel, int n, const double* __restrict__ L, int ld,
+                                                                   const double* __restrict__ z, double* __restrict__ c) {
   __shared__ double sLs[NB * SP];
   __shared__ double sinv[NB];
-  const int lane = threadIdx.x;
-  for (int e = lane; e < NB * NB; e += 32) {
+  // four warps bring the block in (coalesced rows; one warp alone spent 10 us of its 20 here), warp 0 substitutes
+  for (int e = threadIdx.x; e < NB * NB; e += 128) {
     const int i = e >> 6, j = e & 63;
     sLs[i * SP + j] = (i < n && j <= i) ? L[(size_t)i * ld + j] : (i == j ? 1.0 : 0.0);
   }
-  __syncwarp();
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   sinv[lane] = 1.0 / sLs[lane * SP + lane];
   sinv[lane + 32] = 1.0 / sLs[(lane + 32) * SP + lane + 32];
   __syncwarp();
@@ -462,7 +464,7 @@ int32_t chol_backsolve_enqueue(gingr_ctx* ctx, int n, const double* d_L, int ld,
   static const int env_df = [] { const char* e = getenv("GINGR_CHOL_DF"); return e ? atoi(e) : 1; }();
   if (ws != nullptr && env_df != 0 && nb > 1) return chol_backsolve_z_enqueue(ctx, n, d_L, ld, d_z, d_c, *ws);
   if (nb == 1) {
-    GINGR_LAUNCH(ctx, chol_backsolve_small_kernel, 1, 32, 0, ctx->stream, n, d_L, ld, d_z, d_c);
+    GINGR_LAUNCH(ctx, chol_backsolve_small_kernel, 1, 128, 0, ctx->stream, n, d_L, ld, d_z, d_c);
     GINGR_LAUNCHED(ctx);
     GINGR_CUDA_TRY(ctx, cudaGetLastError());
     return GINGR_OK;

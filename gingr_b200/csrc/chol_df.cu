@@ -399,6 +399,55 @@ GINGR_KERNEL((DF_THREADS, 1), chol_df_kernel, const DfParams& P) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// n <= 64: the whole matrix is ONE diagonal block.  The data-flow kernel above would run its single task with 216 registers
+// and 209 KB of shared memory -- one CTA per SM, which is what bounds a batch of 1024 chains of rank 50 (batch.cuh: 7 waves of
+// 17 us).  Here: load, potrf64, write L, forward-substitute the rows below the square (x = b Z^T with Z = L^-1 from the same
+// pass), 70 KB and <= 128 registers: two CTAs per SM, and nothing but the factorisation between load and store.
+// ---------------------------------------------------------------------------------------------
+constexpr size_t SMALL_SMEM = (size_t)(TILE_DOUBLES + TB * G2P * 2 + TB + 32 + 32) * sizeof(double) + 64;
+
+GINGR_KERNEL((DF_THREADS, 2), chol_small_kernel, int n, int nrows, double* __restrict__ A, int ld, int* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char small_smem[];
+  double* sT = reinterpret_cast<double*>(small_smem);                  // [64][TP] the block, later a batch of extra rows
+  double2* G2 = reinterpret_cast<double2*>(sT + TILE_DOUBLES);           // [64][G2P]
+  double* sDiag = reinterpret_cast<double*>(G2 + TB * G2P);             // [64]
+  double* sSub = sDiag + TB;                                            // [32]
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sSub + 32);   // [32]
+  const int tid = threadIdx.x;
+  if (tid < 32) mbar_init(&sBar[tid], 1);
+  for (int e = tid; e < TB * TB; e += DF_THREADS) {
+    const int r = e >> 6, c = e & 63;
+    sT[r * TP + c] = (r < n && c <= r) ? A[(size_t)r * ld + c] : (r == c ? 1.0 : 0.0);   // identity-padded beyond the valid part
+  }
+  __syncthreads();
+  const bool bad = potrf64(sT, G2, sDiag, sSub, sBar, 0u, tid, 0);
+  if (bad && tid == 0) info[0] = 1;
+  for (int e = tid; e < TB * TB; e += DF_THREADS) {
+    const int r = e >> 6, c = e & 63;
+    if (r < n && c <= r) A[(size_t)r * ld + c] = potrf_L(G2, sDiag, sSub, r, c);
+  }
+  // rows below the square part (right-hand sides): x[c] = sum_{k <= c} b[k] Z[c][k], 64 rows at a time through sT
+  for (int e0 = n; e0 < nrows; e0 += TB) {
+    const int cnt = min(TB, nrows - e0);
+    __syncthreads();
+    for (int e = tid; e < cnt * TB; e += DF_THREADS) {
+      const int r = e >> 6, c = e & 63;
+      sT[r * TP + c] = c < n ? A[(size_t)(e0 + r) * ld + c] : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < cnt * TB; e += DF_THREADS) {
+      const int r = e >> 6, c = e & 63;
+      if (c < n) {
+        const double* er = sT + r * TP;
+        double s0 = 0.0;
+        for (int k = 0; k <= c; ++k) s0 = fma(er[k], potrf_Z(G2, c, k), s0);
+        A[(size_t)(e0 + r) * ld + c] = s0;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward substitution  L^T c = z  with the published inverses Z_k = L_kk^-1 of the factorisation above: one CTA per
 // 64-block, blocks become ready from the last one up.  CTA k accumulates  z_k - sum_{i>k} L_ik^T c_i  as the c_i appear
 // and finishes with c_k = Z_k^T acc.  Everything the critical step needs is in shared memory BEFORE its flag arrives:
@@ -527,6 +576,18 @@ int32_t cholesky_df_enqueue(gingr_ctx* ctx, int n, int nrows, double* d_A, int l
   if ((size_t)(2 + (size_t)P.nb * P.nbr) > ws.sync.n || (size_t)P.nb * TB * TB > ws.linv.n)
     return gingr_fail(ctx, GINGR_ERR_ARG, "cholesky: workspace too small");
   if ((ld & 1) != 0 || (((uintptr_t)d_A) & 15) != 0) return gingr_fail(ctx, GINGR_ERR_ARG, "cholesky: matrix must be 16-byte aligned with an even pitch");
+  static const int env_small = [] { const char* e = getenv("GINGR_CHOL_SMALL"); return e ? atoi(e) : 1; }();
+  if (P.nb == 1 && env_small) {
+    static thread_local int attr_small = -1;
+    if (attr_small != ctx->device) {
+      GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
+      attr_small = ctx->device;
+    }
+    GINGR_LAUNCH(ctx, chol_small_kernel, 1, DF_THREADS, SMALL_SMEM, ctx->stream, n, nrows, d_A, ld, d_info);
+    GINGR_LAUNCHED(ctx);
+    GINGR_CUDA_TRY(ctx, cudaGetLastError());
+    return GINGR_OK;
+  }
   P.sync = ws.sync.p;
   P.linv = ws.linv.p;
   P.info = d_info;
