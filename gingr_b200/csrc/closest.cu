@@ -90,6 +90,7 @@ GINGR_KERNEL((QT), surface_kernel, int M, const double* __restrict__ q, int N,
                                                      const int32_t* __restrict__ tri, double* __restrict__ part_d2,
                                                      int32_t* __restrict__ part_tri, double* __restrict__ part_cp) {
   __shared__ double st[TT][9];
+  __shared__ double sb[TT][6];   // bounding box of the staged triangle (lo, hi)
   const int i = blockIdx.x * QT + threadIdx.x;
   const int per = (T + gridDim.y - 1) / gridDim.y;
   const int t_begin = blockIdx.y * per, t_end = min(T, t_begin + per);
@@ -106,7 +107,19 @@ GINGR_KERNEL((QT), surface_kernel, int M, const double* __restrict__ q, int N,
       st[t][k] = verts[(size_t)(k % 3) * N + v];
     }
     __syncthreads();
+    for (int e = threadIdx.x; e < cnt * 3; e += QT) {
+      const int t = e / 3, k = e % 3;
+      const double a = st[t][k], b = st[t][3 + k], c = st[t][6 + k];
+      sb[t][k] = fmin(a, fmin(b, c));
+      sb[t][3 + k] = fmax(a, fmax(b, c));
+    }
+    __syncthreads();
     for (int t = 0; t < cnt; ++t) {
+      // a triangle lies inside its box: it cannot beat the best (strict <, so it cannot replace an equal one either)
+      // when the box is farther -- by more than the rounding of this bound
+      const double ex = fmax(fmax(sb[t][0] - qx, qx - sb[t][3]), 0.0), ey = fmax(fmax(sb[t][1] - qy, qy - sb[t][4]), 0.0),
+                   ez = fmax(fmax(sb[t][2] - qz, qz - sb[t][5]), 0.0);
+      if ((ex * ex + ey * ey + ez * ez) * (1.0 - 1e-12) > best) continue;
       double cx, cy, cz;
       closest_on_triangle(qx, qy, qz, &st[t][0], &st[t][3], &st[t][6], cx, cy, cz);
       const double dx = qx - cx, dy = qy - cy, dz = qz - cz;
@@ -510,7 +523,8 @@ int32_t icp_correspondence_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, const M
   }
   if (tgt.T <= 0 || tpl.T <= 0 || !tpl.normals || !tgt.normals || !tgt.boundary || !tgt.aos)
     return gingr_fail(ctx, GINGR_ERR_ARG, "the mesh flavours of the ICP correspondence need template and target triangles");
-  const int s_surf = std::min(ws.s_surf, std::max(1, ceil_div(tgt.T, TT / 4)));
+  // (chains batched in one launch fill the machine by themselves: long candidate ranges prune better, batch.cuh)
+  const int s_surf = ctx->rec ? std::min(ws.s_surf, 2) : std::min(ws.s_surf, std::max(1, ceil_div(tgt.T, TT / 4)));
   int s_line = std::min(ws.s_line, std::max(1, ceil_div(tpl.T, TT / 4)));
   const bool tgt_grid = tgt.tgrid && tgt.tgrid->built, tpl_grid = tpl.tgrid && tpl.tgrid->built;
   double* o_sd2 = ws.surf_d2.p + q0;   // not o_d2: the nearest-vertex search below reuses that
@@ -573,7 +587,7 @@ int32_t surface_distance_enqueue(gingr_ctx* ctx, ClosestWorkspace& ws, int nq, c
     GINGR_TRY(grid_surface_enqueue(ctx, *mesh.tgrid, nq, d_q, mesh.aos, mesh.tri, ws.d2.p, nullptr, ws.cp.p, nullptr));
     return GINGR_OK;
   }
-  const int s_surf = std::min(ws.s_surf, std::max(1, ceil_div(mesh.T, TT / 4)));
+  const int s_surf = ctx->rec ? std::min(ws.s_surf, 2) : std::min(ws.s_surf, std::max(1, ceil_div(mesh.T, TT / 4)));
   GINGR_LAUNCH(ctx, surface_kernel, dim3(ceil_div(nq, QT), s_surf), QT, 0, st, nq, d_q, mesh.n, mesh.soa, mesh.T, mesh.tri, ws.part_d2.p,
                                                                 ws.part_idx.p, ws.part_cp.p);
   GINGR_LAUNCHED(ctx);

@@ -285,8 +285,56 @@ GINGR_KERNEL((GRAM_WS_THREADS, 1), gram_ws_kernel, int rows, int rp, const doubl
   }
 
   // ---------------- consumers ----------------
-  const int wm = warp >> 2, wn = warp & 3;             // 2 x 4 warps, warp tile 64 x 32
   const int g = lane >> 2, t = lane & 3;
+  if (rp < 64) {
+    // rank < 64 (one tile, its upper-left quarter incl. the rhs in row rp: the small problems of batched chains, C1): the 64 x 64 corner is cut
+    // into 16 x 32 pieces, one per warp -- with the 64 x 32 pieces below two warps would do all the MMAs and six none
+    const int r0w = (warp & 3) * 16, c0w = (warp >> 2) * 32;
+    unsigned it = 0;
+    for (int si = s_first; si < s_last; ++si) {
+      const GramSegment sg = segs[si];
+      double acc[2][4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int ch = sg.c0; ch < sg.c1; ++ch, ++it) {
+        const int stage = it % STAGES;
+        mbar_wait(bar0 + 8 * stage, (it / STAGES) & 1);
+        const double* tA = sA + (size_t)stage * BK * PITCH + r0w + g;
+        const double* tB = sA + (size_t)stage * BK * PITCH + c0w + g;    // one tile: always diagonal
+        const double* tW = sW + stage * BK;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 4; ++k4) {
+          const int kk = k4 * 4 + t;
+          const double wk = wrow ? tW[kk] : 1.0;
+          double af[2], bf[4];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) af[i] = tA[kk * PITCH + i * 8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bf[j] = tB[kk * PITCH + j * 8] * wk;
+          if (k4 == BK / 4 - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (STAGES + stage));
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+      }
+      double* out = partial + (size_t)sg.slot * BT * BT;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = r0w + i * 8 + g, col = c0w + j * 8 + 2 * t;
+          *reinterpret_cast<double2*>(out + (size_t)row * BT + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+    }
+    return;
+  }
+  const int wm = warp >> 2, wn = warp & 3;             // 2 x 4 warps, warp tile 64 x 32
   unsigned it = 0;
   for (int si = s_first; si < s_last; ++si) {
     const GramSegment sg = segs[si];
