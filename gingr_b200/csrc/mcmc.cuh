@@ -392,11 +392,9 @@ struct McmcState {
 
 using namespace gingr;
 
-static uint64_t g_mcmc_epoch = 1;   // bumped whenever a chain's buffers or configuration go away: batched plans are stale
-
 static void mcmc_release(gingr_registration* g) {
   if (!g->mcmc) return;
-  ++g_mcmc_epoch;   // declared below: a batched plan that names this chain is stale
+  ++g_batch_epoch;   // a batched plan that names this chain is stale
   g->mcmc->release();
   delete g->mcmc;
   g->mcmc = nullptr;
@@ -411,6 +409,9 @@ static void mcmc_invalidate(gingr_registration* g) {
 static void mcmc_drop_graph(McmcState* mc) {
   if (mc->graph_exec) cudaGraphExecDestroy(mc->graph_exec);
   mc->graph_exec = nullptr;
+}
+static void mcmc_drop_chain_graph(gingr_registration* g) {
+  if (g && g->mcmc) mcmc_drop_graph(g->mcmc);
 }
 
 // EvaluatorWrapper.logValue pieces of the state in the working buffers (fit, alpha): out[0] = ModelEvaluator,
@@ -819,135 +820,12 @@ int32_t gingr_mcmc_chain(gingr_registration* g, int32_t iters, uint64_t seed) {
   return GINGR_OK;
 }
 
-// ---- the MH step of many chains as ONE kernel sequence (batch.cuh) ------------------------------------------------------
-// Every chain's step is recorded (arguments only, nothing is launched), the sequences are checked to be the same launch
-// for launch, the argument tuples go to the device as [launch][chain] arrays and the batched forms of the kernels are
-// captured as one graph: blockIdx.z = chain.  The plan is kept until the set of chains, the seed or a chain's configuration
-// changes.
-struct McmcBatchPlan {
-  std::vector<gingr_registration*> regs;
-  std::vector<double> step_lengths;
-  uint64_t seed = 0, epoch = 0;
-  int device = -1;
-  bool unsupported = false;     // a launch / copy on the path is not batch-aware, or the chains differ: per-chain graphs
-  int nlaunch = 0;
-  DevBuf<unsigned char> d_args;
-  cudaGraphExec_t exec = nullptr;
-  void drop() {
-    if (exec) cudaGraphExecDestroy(exec);
-    exec = nullptr;
-    regs.clear();
-    step_lengths.clear();
-    unsupported = false;
-    nlaunch = 0;
-  }
-};
-
-static bool mcmc_batch_plan_current(const McmcBatchPlan& bp, gingr_ctx* ctx, gingr_registration** regs, int n, uint64_t seed) {
-  if (bp.epoch != g_mcmc_epoch || bp.device != ctx->device || bp.seed != seed || (int)bp.regs.size() != n) return false;
-  for (int k = 0; k < n; ++k)
-    if (bp.regs[k] != regs[k] || bp.step_lengths[k] != regs[k]->last_out.step_length) return false;
-  return true;
-}
-
-static int32_t mcmc_batch_plan_build(gingr_ctx* ctx, gingr_registration** regs, int n, uint64_t seed, McmcBatchPlan& bp) {
-  bp.drop();
-  bp.epoch = g_mcmc_epoch;
-  bp.device = ctx->device;
-  bp.seed = seed;
-  bp.regs.assign(regs, regs + n);
-  for (int k = 0; k < n; ++k) bp.step_lengths.push_back(regs[k]->last_out.step_length);
-  cudaStream_t st = ctx->stream;
-  // a chain's Gram on few CTAs: with n chains in one launch the machine is filled by the chains, and the empty CTAs of
-  // the 148-wide schedule would each still cost a slot with 200 KB of shared memory
-  const int cap = std::max(1, (2 * ctx->num_sms) / n);
-  for (int k = 0; k < n; ++k) {
-    gingr_registration* g = regs[k];
-    if (g->gram.ncta > cap) {
-      GINGR_TRY(g->gram.build(ctx, g->gram.rows, g->gram.r, g->gram.rp, cap));
-      drop_graph(g);
-      mcmc_drop_graph(g->mcmc);
-      g->mcmc->primed = false;   // the kept posterior was formed in the other summation order
-    }
-  }
+// ---- the MH step of many chains as ONE kernel sequence (batch.cuh; the plan and its builder: update.cu) -------------------
+static int32_t mcmc_batch_plan_build(gingr_ctx* ctx, gingr_registration** regs, int n, uint64_t seed, BatchPlan& bp) {
+  GINGR_TRY(batch_cap_gram(ctx, regs, n));
   for (int k = 0; k < n; ++k)
     if (!regs[k]->mcmc->primed) GINGR_TRY(mcmc_prime(regs[k]));
-  // 1. record: inside a capture, so that whatever is not batch-aware is caught in the discarded graph instead of running
-  std::vector<LaunchRecorder> rec((size_t)n);
-  const int64_t l0 = ctx->launches;
-  GINGR_CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  int32_t rc = GINGR_OK;
-  for (int k = 0; k < n && rc >= 0; ++k) {
-    ctx->rec = &rec[k];
-    rc = enqueue_mcmc_step(regs[k], seed + (uint64_t)k);
-  }
-  ctx->rec = nullptr;
-  ctx->launches = l0;
-  cudaGraph_t stray = nullptr;
-  const cudaError_t ec = cudaStreamEndCapture(st, &stray);
-  size_t stray_nodes = 0;
-  if (stray) {
-    cudaGraphGetNodes(stray, nullptr, &stray_nodes);
-    cudaGraphDestroy(stray);
-  }
-  if (rc < 0) return rc;
-  GINGR_CUDA_TRY(ctx, ec);
-  // 2. the same sequence for every chain?
-  bool same = stray_nodes == 0 && !rec[0].recs.empty();
-  const std::vector<LaunchRecord>& r0 = rec[0].recs;
-  for (int k = 1; k < n && same; ++k) {
-    const std::vector<LaunchRecord>& rk = rec[k].recs;
-    same = rk.size() == r0.size();
-    for (size_t i = 0; i < r0.size() && same; ++i)
-      same = rk[i].fn == r0[i].fn && rk[i].arg_bytes == r0[i].arg_bytes && rk[i].smem == r0[i].smem &&
-             rk[i].grid.x == r0[i].grid.x && rk[i].grid.y == r0[i].grid.y && rk[i].grid.z == r0[i].grid.z &&
-             rk[i].block.x == r0[i].block.x && rk[i].block.y == r0[i].block.y && rk[i].block.z == r0[i].block.z;
-  }
-  for (size_t i = 0; i < r0.size() && same; ++i) same = r0[i].grid.z == 1;
-  if (!same) {
-    if (getenv("GINGR_MCMC_BATCH_VERBOSE"))
-      fprintf(stderr, "gingr_mcmc_batch: not batchable (%zu stray stream operations, %zu recorded launches): per-chain graphs\n",
-              stray_nodes, r0.size());
-    bp.unsupported = true;
-    return GINGR_OK;
-  }
-  // 3. argument arrays [launch][chain]
-  std::vector<size_t> off(r0.size());
-  size_t total = 0;
-  for (size_t i = 0; i < r0.size(); ++i) {
-    off[i] = total;
-    total += ((size_t)r0[i].arg_bytes * n + 255) / 256 * 256;
-  }
-  std::vector<unsigned char> h(total, 0);
-  for (size_t i = 0; i < r0.size(); ++i)
-    for (int k = 0; k < n; ++k)
-      memcpy(h.data() + off[i] + (size_t)k * r0[i].arg_bytes, rec[k].args.data() + rec[k].recs[i].arg_off, r0[i].arg_bytes);
-  GINGR_CUDA_TRY(ctx, bp.d_args.alloc(total));
-  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(bp.d_args.p, h.data(), total, cudaMemcpyHostToDevice, st));
-  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  // 4. the batched sequence as one graph
-  for (size_t i = 0; i < r0.size(); ++i)
-    if (r0[i].smem > 48 * 1024)
-      GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(r0[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r0[i].smem));
-  GINGR_CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  cudaError_t el = cudaSuccess;
-  for (size_t i = 0; i < r0.size() && el == cudaSuccess; ++i) {
-    const void* p = bp.d_args.p + off[i];
-    void* params[1] = {(void*)&p};
-    el = cudaLaunchKernel(r0[i].fn, dim3(r0[i].grid.x, r0[i].grid.y, (unsigned)n), r0[i].block, params, r0[i].smem, st);
-  }
-  cudaGraph_t graph = nullptr;
-  const cudaError_t e2 = cudaStreamEndCapture(st, &graph);
-  if (el != cudaSuccess || e2 != cudaSuccess) {
-    if (graph) cudaGraphDestroy(graph);
-    GINGR_CUDA_TRY(ctx, el);
-    GINGR_CUDA_TRY(ctx, e2);
-  }
-  const cudaError_t e3 = cudaGraphInstantiate(&bp.exec, graph, 0);
-  cudaGraphDestroy(graph);
-  GINGR_CUDA_TRY(ctx, e3);
-  bp.nlaunch = (int)r0.size();
-  return GINGR_OK;
+  return batch_plan_build(ctx, regs, n, seed, /*kind=*/2, bp, [&](int k) { return enqueue_mcmc_step(regs[k], seed + (uint64_t)k); });
 }
 
 // Independent chains batched on one GPU (BASELINE config 5): chain k uses seed + k.  The chains' steps run as one
@@ -965,8 +843,8 @@ int32_t gingr_mcmc_batch(gingr_registration** regs, int32_t n, int32_t iters, ui
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   static const int batched = [] { const char* e = getenv("GINGR_MCMC_BATCHED"); return e ? atoi(e) : 1; }();
   if (batched && n >= 2 && n <= 65535 && graphs_enabled(ctx)) {
-    static thread_local McmcBatchPlan bp;
-    if (!mcmc_batch_plan_current(bp, ctx, regs, n, seed)) {
+    static thread_local BatchPlan bp;
+    if (!batch_plan_current(bp, ctx, regs, n, seed, 2)) {
       const int32_t rc = mcmc_batch_plan_build(ctx, regs, n, seed, bp);
       if (rc < 0) { bp.drop(); return rc; }
     }

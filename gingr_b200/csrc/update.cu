@@ -727,8 +727,10 @@ struct gingr_registration {
 static int32_t model_build_constants(gingr_ctx* ctx, gingr_model* m);
 static int32_t model_upload_topology(gingr_ctx* ctx, gingr_model* m, const int32_t* tri, int T);
 static void drop_graph(gingr_registration* g);
+static uint64_t g_batch_epoch = 1;   // bumped whenever a chain's captured sequence goes stale (drop_graph, mcmc_release): so are batched plans
 static void mcmc_release(gingr_registration* g);     // mcmc.cuh
 static void mcmc_invalidate(gingr_registration* g);  // mcmc.cuh: the device state changed outside the MH chain
+static void mcmc_drop_chain_graph(gingr_registration* g);   // mcmc.cuh: the captured MH step of the chain is stale
 
 // reference triangles, vertex -> triangle adjacency and boundary flags of a model (ICP mesh flavours)
 static int32_t model_upload_topology(gingr_ctx* ctx, gingr_model* m, const int32_t* tri, int T) {
@@ -1727,6 +1729,7 @@ static bool graphs_enabled(const gingr_ctx* ctx) {
 }
 
 static void drop_graph(gingr_registration* g) {
+  ++g_batch_epoch;
   if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
   g->graph_exec = nullptr;
   g->graph_prob = -1;
@@ -1835,6 +1838,143 @@ static int32_t replay_chain_graphs(gingr_ctx* ctx, ChainStreamPool* sp, int n, i
     GINGR_CUDA_TRY(ctx, cudaEventRecord(sp->join_ev[q], sp->streams[q]));
     GINGR_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, sp->join_ev[q], 0));
   }
+  return GINGR_OK;
+}
+
+// ---- many chains, ONE kernel sequence (batch.cuh) ---------------------------------------------------------------------
+// Every chain's step is recorded (arguments only, nothing is launched), the sequences are checked to be the same launch
+// for launch, the argument tuples go to the device as [launch][chain] arrays and the batched forms of the kernels are
+// captured as one graph: blockIdx.z = chain.  A plan is kept until the set of chains, the seed, the kind of step or a
+// chain's configuration changes.  Users: gingr_mcmc_batch (mcmc.cuh) and gingr_update_batch.
+struct BatchPlan {
+  std::vector<gingr_registration*> regs;
+  std::vector<double> step_lengths;
+  uint64_t seed = 0, epoch = 0;
+  int device = -1, kind = 0;    // kind: 1 update (deterministic), 3 update (sampled), 2 Metropolis-Hastings step
+  bool unsupported = false;     // a launch / copy on the path is not batch-aware, or the chains differ: per-chain graphs
+  int nlaunch = 0;
+  DevBuf<unsigned char> d_args;
+  cudaGraphExec_t exec = nullptr;
+  void drop() {
+    if (exec) cudaGraphExecDestroy(exec);
+    exec = nullptr;
+    regs.clear();
+    step_lengths.clear();
+    unsupported = false;
+    nlaunch = 0;
+  }
+};
+
+static bool batch_plan_current(const BatchPlan& bp, gingr_ctx* ctx, gingr_registration** regs, int n, uint64_t seed, int kind) {
+  if (bp.epoch != g_batch_epoch || bp.device != ctx->device || bp.seed != seed || bp.kind != kind || (int)bp.regs.size() != n)
+    return false;
+  for (int k = 0; k < n; ++k)
+    if (bp.regs[k] != regs[k] || bp.step_lengths[k] != regs[k]->last_out.step_length) return false;
+  return true;
+}
+
+// a chain's Gram on few CTAs: with n chains in one launch the machine is filled by the chains, and the empty CTAs of the
+// 148-wide schedule would each still cost a slot with 200 KB of shared memory
+static int32_t batch_cap_gram(gingr_ctx* ctx, gingr_registration** regs, int n) {
+  const int cap = std::max(1, (2 * ctx->num_sms) / n);
+  for (int k = 0; k < n; ++k) {
+    gingr_registration* g = regs[k];
+    if (g->gram.ncta > cap) {
+      GINGR_TRY(g->gram.build(ctx, g->gram.rows, g->gram.r, g->gram.rp, cap));
+      drop_graph(g);
+      mcmc_invalidate(g);   // a kept posterior was formed in the other summation order
+      mcmc_drop_chain_graph(g);
+    }
+  }
+  return GINGR_OK;
+}
+
+template <typename F>
+static int32_t batch_plan_build(gingr_ctx* ctx, gingr_registration** regs, int n, uint64_t seed, int kind, BatchPlan& bp,
+                                F&& enqueue_chain) {
+  bp.drop();
+  bp.epoch = g_batch_epoch;
+  bp.device = ctx->device;
+  bp.seed = seed;
+  bp.kind = kind;
+  bp.regs.assign(regs, regs + n);
+  for (int k = 0; k < n; ++k) bp.step_lengths.push_back(regs[k]->last_out.step_length);
+  cudaStream_t st = ctx->stream;
+  // 1. record: inside a capture, so that whatever is not batch-aware is caught in the discarded graph instead of running
+  std::vector<LaunchRecorder> rec((size_t)n);
+  const int64_t l0 = ctx->launches;
+  GINGR_CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int32_t rc = GINGR_OK;
+  for (int k = 0; k < n && rc >= 0; ++k) {
+    ctx->rec = &rec[k];
+    rc = enqueue_chain(k);
+  }
+  ctx->rec = nullptr;
+  ctx->launches = l0;
+  cudaGraph_t stray = nullptr;
+  const cudaError_t ec = cudaStreamEndCapture(st, &stray);
+  size_t stray_nodes = 0;
+  if (stray) {
+    cudaGraphGetNodes(stray, nullptr, &stray_nodes);
+    cudaGraphDestroy(stray);
+  }
+  if (rc < 0) return rc;
+  GINGR_CUDA_TRY(ctx, ec);
+  // 2. the same sequence for every chain?
+  bool same = stray_nodes == 0 && !rec[0].recs.empty();
+  const std::vector<LaunchRecord>& r0 = rec[0].recs;
+  for (int k = 1; k < n && same; ++k) {
+    const std::vector<LaunchRecord>& rk = rec[k].recs;
+    same = rk.size() == r0.size();
+    for (size_t i = 0; i < r0.size() && same; ++i)
+      same = rk[i].fn == r0[i].fn && rk[i].arg_bytes == r0[i].arg_bytes && rk[i].smem == r0[i].smem &&
+             rk[i].grid.x == r0[i].grid.x && rk[i].grid.y == r0[i].grid.y && rk[i].grid.z == r0[i].grid.z &&
+             rk[i].block.x == r0[i].block.x && rk[i].block.y == r0[i].block.y && rk[i].block.z == r0[i].block.z;
+  }
+  for (size_t i = 0; i < r0.size() && same; ++i) same = r0[i].grid.z == 1;
+  if (!same) {
+    if (getenv("GINGR_BATCH_VERBOSE"))
+      fprintf(stderr, "gingr batch: not batchable (%zu stray stream operations, %zu recorded launches): per-chain graphs\n",
+              stray_nodes, r0.size());
+    bp.unsupported = true;
+    return GINGR_OK;
+  }
+  // 3. argument arrays [launch][chain]
+  std::vector<size_t> off(r0.size());
+  size_t total = 0;
+  for (size_t i = 0; i < r0.size(); ++i) {
+    off[i] = total;
+    total += ((size_t)r0[i].arg_bytes * n + 255) / 256 * 256;
+  }
+  std::vector<unsigned char> h(total, 0);
+  for (size_t i = 0; i < r0.size(); ++i)
+    for (int k = 0; k < n; ++k)
+      memcpy(h.data() + off[i] + (size_t)k * r0[i].arg_bytes, rec[k].args.data() + rec[k].recs[i].arg_off, r0[i].arg_bytes);
+  GINGR_CUDA_TRY(ctx, bp.d_args.alloc(total));
+  GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(bp.d_args.p, h.data(), total, cudaMemcpyHostToDevice, st));
+  GINGR_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  // 4. the batched sequence as one graph
+  for (size_t i = 0; i < r0.size(); ++i)
+    if (r0[i].smem > 48 * 1024)
+      GINGR_CUDA_TRY(ctx, cudaFuncSetAttribute(r0[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r0[i].smem));
+  GINGR_CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  cudaError_t el = cudaSuccess;
+  for (size_t i = 0; i < r0.size() && el == cudaSuccess; ++i) {
+    const void* p = bp.d_args.p + off[i];
+    void* params[1] = {(void*)&p};
+    el = cudaLaunchKernel(r0[i].fn, dim3(r0[i].grid.x, r0[i].grid.y, (unsigned)n), r0[i].block, params, r0[i].smem, st);
+  }
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+  if (el != cudaSuccess || e2 != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    GINGR_CUDA_TRY(ctx, el);
+    GINGR_CUDA_TRY(ctx, e2);
+  }
+  const cudaError_t e3 = cudaGraphInstantiate(&bp.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  GINGR_CUDA_TRY(ctx, e3);
+  bp.nlaunch = (int)r0.size();
   return GINGR_OK;
 }
 
@@ -1951,6 +2091,29 @@ int32_t gingr_update_batch(gingr_registration** regs, int32_t n, int32_t iters, 
   }
   if (ctx->nranks != 1) return gingr_fail(ctx, GINGR_ERR_UNSUPPORTED, "gingr_update_batch: chains are replicas, one ctx per GPU without a communicator");
   GINGR_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  // one batched kernel sequence per iteration for all chains (batch.cuh) when every launch of the iteration is batch-aware
+  // (the ICP flavours on the scans; the CPD E-step is not: per-chain graphs), GINGR_UPDATE_BATCHED=0: always per-chain graphs
+  static const int batched = [] { const char* e = getenv("GINGR_UPDATE_BATCHED"); return e ? atoi(e) : 1; }();
+  if (batched && n >= 2 && n <= 65535 && graphs_enabled(ctx)) {
+    static thread_local BatchPlan bp;
+    const int kind = probabilistic ? 3 : 1;
+    if (!batch_plan_current(bp, ctx, regs, n, seed, kind)) {
+      int32_t rc = batch_cap_gram(ctx, regs, n);
+      if (rc >= 0)
+        rc = batch_plan_build(ctx, regs, n, seed, kind, bp, [&](int k) -> int32_t {
+          GINGR_TRY(enqueue_iteration(regs[k], probabilistic != 0, seed + (uint64_t)k));
+          GINGR_LAUNCH(ctx, bump_iteration_kernel, 1, 1, 0, ctx->stream, regs[k]->is.p);
+          GINGR_LAUNCHED(ctx);
+          return GINGR_OK;
+        });
+      if (rc < 0) { bp.drop(); return rc; }
+    }
+    if (!bp.unsupported) {
+      for (int it = 0; it < iters; ++it) GINGR_CUDA_TRY(ctx, cudaGraphLaunch(bp.exec, ctx->stream));
+      ctx->launches += (int64_t)iters * bp.nlaunch;
+      return GINGR_OK;
+    }
+  }
   ChainStreamPool* sp = nullptr;
   GINGR_TRY(chain_stream_pool(ctx, &sp));
   // capture (or re-key) every chain's graph on the ctx stream first: capture is not concurrent
