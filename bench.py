@@ -374,6 +374,7 @@ def run_ours(args):
             "path": "one batched kernel sequence per MH step for all chains of a GPU (blockIdx.z = chain, gingr_b200/csrc/batch.cuh)",
             "finite": c5["finite"]}
         if world == 1:
+            secondary["c5_update_batch"] = bs.c5_update_batch(ctx)
             secondary["c1_icp"] = bs.c1_icp(ctx)
             secondary["c3_multiresolution"] = bs.c3_pipeline(ctx)
             secondary["icp_200k"] = bs.icp_200k(ctx, ROOT)

@@ -186,3 +186,34 @@ def c5_mcmc(ctx, world, rank, n_total=1024, iters=50, rho=0.5):
         c.close()
     model.close(); tgt.close()
     return {"chains": n, "steps": iters, "seconds": dt, "accepted": acc, "launches": launches, "finite": ok}
+
+
+def c5_update_batch(ctx, n=1024, iters=50):
+    """The informed proposal alone, batched: n independent probabilistic ICP registrations of the C1 size advancing by
+    update(current, probabilistic = true) + propose (gingr_update_batch; one batched kernel sequence per iteration)."""
+    from gingr_b200 import api, synthetic
+    M, N, r = 100, 100, 50
+    ref, tri = synthetic.sphere_mesh(M)
+    mean, basis, var = synthetic.make_gpmm(ref, r, 1)
+    tv, tt = synthetic.sphere_mesh(N)
+    model = api.Model(ctx, ref, mean, basis, var, tri)
+    tgt = api.Target(ctx, synthetic.make_target(tv, 0), tt)
+    cfg = api.IcpConfiguration(maxIterations=10 ** 6, initialSigma=1.0, endSigma=1.0)
+    chains = [api.IcpRegistration(ctx, model, tgt, cfg) for _ in range(n)]
+    for c in chains:
+        c.initializeState(globalTransformation=api.RIGID_TRANSFORMS)
+    api.update_batch(chains, 3, probabilistic=True, seed=0)
+    ctx.synchronize()
+    l0 = ctx.launch_count
+    t0 = time.perf_counter()
+    api.update_batch(chains, iters, probabilistic=True, seed=0)
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    launches = ctx.launch_count - l0
+    ok = bool(np.all(np.isfinite(chains[-1].downloadState().fit)))
+    for c in chains:
+        c.close()
+    model.close(); tgt.close()
+    return {"workload": f"{n} independent probabilistic ICP registrations of the C1 size (informed proposal only), gingr_update_batch",
+            "chains": n, "iterations_per_chain": iters, "chain_iterations_per_s": n * iters / dt, "ms_per_iteration_of_all_chains": dt / iters * 1e3,
+            "launches_per_iteration_of_all_chains": launches / iters, "finite": ok}

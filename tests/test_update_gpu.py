@@ -313,6 +313,35 @@ def test_probabilistic_retry_counter(ctx, oracle):
     reg.close()
 
 
+def test_large_batch_runs_as_one_kernel_sequence(ctx, oracle):
+    """gingr_update_batch with many ICP chains: one launch per step of the iteration's kernel sequence serves all chains
+    (batch.cuh).  A batched chain's Gram runs on fewer CTAs (another summation order): 1e-9 against the solo chains."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 100, 100, 30, seed=14)
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    n, iters = 64, 3
+    cfg = api.IcpConfiguration(initialSigma=2.0, endSigma=1.0)
+    chains = [api.IcpRegistration(ctx, dm, dt, cfg) for _ in range(n)]
+    for k, c in enumerate(chains):
+        c.initializeState(translation=np.array([0.01 * k, 0.0, 0.0]))       # different states, same kernel sequence
+    l0 = ctx.launch_count
+    api.update_batch(chains, iters)
+    ctx.synchronize()
+    assert (ctx.launch_count - l0) / iters < 100, "the batched sequence did not run"
+    for k in (0, 5, n - 1):
+        solo = api.IcpRegistration(ctx, dm, dt, cfg)
+        solo.initializeState(translation=np.array([0.01 * k, 0.0, 0.0]))
+        solo.updateChain(iters)
+        a, b = chains[k].downloadState(), solo.downloadState()
+        assert a.iteration == iters == b.iteration
+        np.testing.assert_allclose(a.fit, b.fit, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(a.modelParameters.shape, b.modelParameters.shape, rtol=1e-8, atol=1e-9)
+        solo.close()
+    for c in chains:
+        c.close()
+
+
 def test_batched_chains_equal_independent_chains(ctx, oracle):
     """gingr_update_batch (BASELINE config 5: batched MCMC chains, replicas only): n chains sharing model and target,
     each with its own state and Philox stream, give exactly what the same chains give one by one."""
