@@ -267,8 +267,11 @@ GINGR_API int32_t gingr_update_chain_sampled(gingr_registration* reg, int32_t it
 /* Independent registrations / MCMC chains batched on one GPU (BASELINE config 5; SURVEY.md 8e "replicas only"):
  * `iters` update+propose steps of each of the n registrations (all created on the same ctx, typically sharing one
  * model and one target handle, each with its own device-resident state).  Chain k uses seed + k when
- * probabilistic != 0.  The chains' captured iteration graphs are replayed on a pool of streams; the call returns
- * after enqueueing, results are read with gingr_state_download per chain. */
+ * probabilistic != 0.  All chains advance through ONE batched kernel sequence per iteration (every kernel launched once
+ * with blockIdx.z = chain; csrc/batch.cuh) when every launch of the iteration has a batched form -- the ICP flavours on the
+ * scans do --, otherwise the chains' captured iteration graphs are replayed on a pool of streams (CPD).  The call returns
+ * after enqueueing, results are read with gingr_state_download per chain.  Per chain the arithmetic is that of the chain
+ * alone, up to the summation order of its Gram partials when many chains share the GPU. */
 GINGR_API int32_t gingr_update_batch(gingr_registration** regs, int32_t n, int32_t iters, int32_t probabilistic,
                                      uint64_t seed);
 /* Read back the device-resident state after gingr_update_chain / gingr_update_batch. */
@@ -311,7 +314,9 @@ GINGR_API int32_t gingr_log_transition_probability(gingr_registration* reg, cons
  * or random proposal, posterior of the proposal (kept when accepted), both transition densities of the mixture, accept /
  * reject, best-sample tracking.  Random numbers: Philox4x32-10, key = seed, counter = (index, MH step, purpose, 0). */
 GINGR_API int32_t gingr_mcmc_chain(gingr_registration* reg, int32_t iters, uint64_t seed);
-/* Independent chains batched on one GPU (BASELINE config 5); chain k uses seed + k. */
+/* Independent chains batched on one GPU (BASELINE config 5); chain k uses seed + k.  One batched kernel sequence per MH
+ * step serves all chains (see gingr_update_batch); a step with a launch that has no batched form falls back to per-chain
+ * step graphs. */
 GINGR_API int32_t gingr_mcmc_batch(gingr_registration** regs, int32_t n, int32_t iters, uint64_t seed);
 /* values[16] / counts[32]: see mcmc.cuh (log values of current / proposal / best, transition densities, accept counts per
  * generator). */
