@@ -7,6 +7,8 @@
 //   gemvT       out[a] = s_a sum_k Phi[k][a] u[k]   right-hand side Q^T L^-1 (y - m) of the regression
 //               (SURVEY.md A3).  Thread per column, rows split over CTAs, fixed-order reduction.
 // Both read Phi (8 * 3M * r bytes) exactly once; Phi is row-major [3M][rp] so both are fully coalesced.
+#include <stdint.h>
+
 #include <algorithm>
 
 #include "batch.cuh"
@@ -143,6 +145,57 @@ GINGR_KERNEL((256), dense_matvec_kernel, int r, const double* __restrict__ A, in
   }
 }
 
+// The same product with TWO warps per row and 16-byte loads, four per lane in flight: a 32 MB matrix that the Gram has pushed
+// out of L2 ran at 2.2 TB/s with one warp per row and 8-byte loads (2000 warps x 1 KB in flight).  Needs 16-byte aligned A and
+// x and an even pitch.  Block = 4 rows x 2 halves; the halves meet in shared memory (fixed order).
+GINGR_KERNEL((256), dense_matvec2_kernel, int r, const double* __restrict__ A, int ld, const double* __restrict__ x,
+             double* __restrict__ y, int* __restrict__ flag_in, int* __restrict__ flag_out) {
+  __shared__ double sp[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 4 + (warp >> 1), half = warp & 1;
+  double s = 0.0;
+  bool bad_in = false;
+  if (row < r) {
+    const int n2 = r >> 1, h2 = (n2 + 1) >> 1;                 // pairs of columns; the first half takes h2 of them
+    const int b1 = half ? n2 : h2;
+    const double2* p2 = reinterpret_cast<const double2*>(A + (size_t)row * ld);
+    const double2* x2 = reinterpret_cast<const double2*>(x);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
+    int b = (half ? h2 : 0) + lane;
+    for (; b + 96 < b1; b += 128) {
+      const double2 m0 = p2[b], m1 = p2[b + 32], m2 = p2[b + 64], m3 = p2[b + 96];
+      const double2 v0 = x2[b], v1 = x2[b + 32], v2 = x2[b + 64], v3 = x2[b + 96];
+      bad_in = bad_in || !(fabs(v0.x) < INFINITY) || !(fabs(v0.y) < INFINITY) || !(fabs(v1.x) < INFINITY) || !(fabs(v1.y) < INFINITY) ||
+               !(fabs(v2.x) < INFINITY) || !(fabs(v2.y) < INFINITY) || !(fabs(v3.x) < INFINITY) || !(fabs(v3.y) < INFINITY);
+      a0 = fma(m0.x, v0.x, a0); a1 = fma(m0.y, v0.y, a1);
+      a2 = fma(m1.x, v1.x, a2); a3 = fma(m1.y, v1.y, a3);
+      a4 = fma(m2.x, v2.x, a4); a5 = fma(m2.y, v2.y, a5);
+      a6 = fma(m3.x, v3.x, a6); a7 = fma(m3.y, v3.y, a7);
+    }
+    for (; b < b1; b += 32) {
+      const double2 m0 = p2[b], v0 = x2[b];
+      bad_in = bad_in || !(fabs(v0.x) < INFINITY) || !(fabs(v0.y) < INFINITY);
+      a0 = fma(m0.x, v0.x, a0); a1 = fma(m0.y, v0.y, a1);
+    }
+    if (half == 1 && (r & 1) && lane == 0) {                   // odd r: the last column
+      const double xv = x[r - 1];
+      bad_in = bad_in || !(fabs(xv) < INFINITY);
+      a0 = fma(A[(size_t)row * ld + r - 1], xv, a0);
+    }
+    s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (flag_in && row == 0 && __any_sync(0xffffffffu, bad_in) && lane == 0) *flag_in = 1;
+  }
+  if (lane == 0) sp[warp] = s;
+  __syncthreads();
+  if (half == 0 && lane == 0 && row < r) {
+    const double t = sp[warp] + sp[warp + 1];
+    y[row] = t;
+    if (flag_out && !(fabs(t) < INFINITY)) *flag_out = 1;
+  }
+}
+
 __global__ void transpose_kernel(int n, const double* __restrict__ A, int lda, double* __restrict__ B, int ldb) {
   __shared__ double tile[32][33];
   const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
@@ -254,7 +307,10 @@ int32_t gemvT_enqueue(gingr_ctx* ctx, int rows, int r, int rp, const double* d_p
 
 int32_t dense_matvec_enqueue(gingr_ctx* ctx, int r, const double* d_A, int ld, const double* d_x, double* d_y,
                              int* d_flag_in, int* d_flag_out) {
-  GINGR_LAUNCH(ctx, dense_matvec_kernel, ceil_div(r * 32, 256), 256, 0, ctx->stream, r, d_A, ld, d_x, d_y, d_flag_in, d_flag_out);
+  if ((ld & 1) == 0 && ((((uintptr_t)d_A) | ((uintptr_t)d_x)) & 15) == 0)
+    GINGR_LAUNCH(ctx, dense_matvec2_kernel, ceil_div(r, 4), 256, 0, ctx->stream, r, d_A, ld, d_x, d_y, d_flag_in, d_flag_out);
+  else
+    GINGR_LAUNCH(ctx, dense_matvec_kernel, ceil_div(r * 32, 256), 256, 0, ctx->stream, r, d_A, ld, d_x, d_y, d_flag_in, d_flag_out);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;
