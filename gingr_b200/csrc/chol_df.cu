@@ -45,6 +45,9 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Release at gpu scope AFTER a CTA barrier: cumulative, so the plain global stores of every thread of the CTA that
+// happened before the barrier are visible to whoever acquires the flag -- no separate __threadfence() (it cost a second
+// fence per flag on the critical path; the same pattern as CUTLASS's Semaphore::release).
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
@@ -317,7 +320,6 @@ GINGR_KERNEL((DF_THREADS, 1), chol_df_kernel, const DfParams& P) {
         }
       __syncthreads();   // every thread's stores are issued; X is complete in shared memory (diagonal task)
       if (tid == DF_THREADS - 1) {   // the last warp pays for the fence, not the warp that leads the diagonal factorisation
-        __threadfence();
         st_release(&flags[rb * nb + cb], 1);
       }
       DF_STAMP(tile_id, 3);
@@ -354,20 +356,19 @@ GINGR_KERNEL((DF_THREADS, 1), chol_df_kernel, const DfParams& P) {
     }
     DF_STAMP(tile_id, 4);
     const double2* G2 = reinterpret_cast<const double2*>(bufI1);
-    const bool bad = potrf64(sA0, reinterpret_cast<double2*>(bufI1), sDiag, sSub, sBar, potrf_calls & 1u, tid, tile_id);
+    // Z = L^-1 is all the waiting tasks of this block column need: its rows go out WHILE the factorisation runs (the warps
+    // whose columns are eliminated copy them, potrf64), only the first 8 rows are left for afterwards
+    double* Z = P.linv + (size_t)j * TB * TB;
+    const bool bad = potrf64(sA0, reinterpret_cast<double2*>(bufI1), sDiag, sSub, sBar, potrf_calls & 1u, tid, tile_id, Z);
     ++potrf_calls;
     DF_STAMP(tile_id, 5);
     if (bad && tid == 0) P.info[0] = 1;
-    // publish Z = L^-1 first: it is all the waiting tasks of this block column need
-    double* Z = P.linv + (size_t)j * TB * TB;
-#pragma unroll 4
-    for (int e = tid; e < TB * (TB / 2); e += DF_THREADS) {
-      const int c = e >> 5, k = (e & 31) * 2;
+    {
+      const int c = tid >> 5, k = (tid & 31) * 2;     // 8 rows x 32 column pairs = 256 threads
       *reinterpret_cast<double2*>(Z + c * TB + k) = make_double2(potrf_Z(G2, c, k), potrf_Z(G2, c, k + 1));
     }
     __syncthreads();
     if (tid == 0) {
-      __threadfence();
       st_release(&flags[j * nb + j], 1);
     }
     DF_STAMP(tile_id, 6);
@@ -524,7 +525,6 @@ __global__ void __launch_bounds__(BS_THREADS) chol_backsolve_z_kernel(int n, con
   if (tid < kcnt) c[k0 + tid] = (sacc[tid] + sacc[TB + tid]) + (sacc[2 * TB + tid] + sacc[3 * TB + tid]);
   __syncthreads();
   if (tid == 0) {
-    __threadfence();
     st_release(&flags[k], 1);
     if (atomicAdd(&flags[nb], 1) == nb - 1) {   // last CTA out: every flag has been read for the last time
       for (int e = 0; e <= nb; ++e) flags[e] = 0;

@@ -75,9 +75,12 @@ __device__ __forceinline__ double potrf_Z(const double2* __restrict__ G2, int c,
 // Z = L^-1 as described above (read them with potrf_L / potrf_Z).  sBar: the 32 step barriers (initialised once per
 // kernel), parity: number of factorisations this CTA has run before, mod 2.  Returns true if a pivot was not positive and
 // finite.
+// Zout (optional): global [64][64] that receives Z row by row WHILE the factorisation runs -- rows 2 s and 2 s + 1 are final
+// as soon as step s is published (column s of G2), and the warps whose columns are all eliminated have nothing else to do:
+// warp s mod (s / 4) copies them.  Rows 0..7 (steps 0..3: no warp is idle yet) are left to the caller.
 __device__ __forceinline__ bool potrf64(const double* __restrict__ sT, double2* G2, double* __restrict__ sDiag,
                                         double* __restrict__ sSub, unsigned long long* sBar, unsigned parity, int tid,
-                                        int tile_id) {
+                                        int tile_id, double* __restrict__ Zout = nullptr) {
   const int lane = tid & 31, g = tid >> 5;
   (void)tile_id;
   DF_CLOCK(tile_id, 0);
@@ -171,6 +174,21 @@ __device__ __forceinline__ bool potrf64(const double* __restrict__ sT, double2* 
     }
   }
 #undef POTRF_UPDATE_PAIR
+  if (Zout != nullptr && g < 7) {
+#pragma unroll 1
+    for (int s = 4 * (g + 1); s < 32; ++s) {
+      if (s % (s >> 2) != g) continue;
+      mbar_wait(&sBar[s], parity);
+      const int c = 2 * s;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        const double2 v = G2[k * G2P + s];
+        Zout[c * 64 + k] = (k <= c) ? v.x : 0.0;
+        Zout[(c + 1) * 64 + k] = (k <= c + 1) ? v.y : 0.0;
+      }
+    }
+  }
   __syncthreads();
   DF_CLOCK(tile_id, 1);
   return __syncthreads_or(bad ? 1 : 0) != 0;
