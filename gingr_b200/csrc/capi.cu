@@ -171,6 +171,7 @@ static int32_t target_upload_into(gingr_ctx* ctx, gingr_target* t, int32_t N, co
     GINGR_TRY(gingr::grid_build_points_enqueue(ctx, *t->pgrid, N, va));
     if (T > 0) {
       t->tgrid = new gingr::SpatialGrid();
+      t->tgrid->entry_boxes = true;   // static grid, searched every iteration: boxes stored with the entries
       GINGR_TRY(t->tgrid->ensure(ctx, N, T, true));
       GINGR_TRY(gingr::grid_build_triangles_enqueue(ctx, *t->tgrid, N, va, T, t->tri.p));
     }

@@ -181,7 +181,7 @@ template <int PASS>
 __global__ void __launch_bounds__(256) grid_tri_kernel(int T, const double* __restrict__ verts_aos, const int32_t* __restrict__ tri,
                                                        GridParams* __restrict__ gp, const int32_t* __restrict__ cell_start,
                                                        int32_t* __restrict__ fill, int32_t* __restrict__ entries, int cap_entries,
-                                                       float4* __restrict__ tri_box) {
+                                                       float4* __restrict__ tri_box, float4* __restrict__ entry_box /*may be null*/) {
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (t >= T) return;
   const GridParams g = *gp;
@@ -202,7 +202,10 @@ __global__ void __launch_bounds__(256) grid_tri_kernel(int T, const double* __re
           atomicAdd(&fill[c], 1);
         } else {
           const int pos = cell_start[c] + atomicAdd(&fill[c], 1);
-          if (pos < cap_entries) entries[pos] = t;
+          if (pos < cap_entries) {
+            entries[pos] = t;
+            if (entry_box) { entry_box[2 * (size_t)pos] = blo; entry_box[2 * (size_t)pos + 1] = bhi; }
+          }
         }
       }
 }
@@ -304,6 +307,7 @@ int32_t SpatialGrid::ensure(gingr_ctx* ctx, int nv, int items, bool tri) {
   if (tri) {
     GINGR_CUDA_TRY(ctx, entries.alloc((size_t)cap_entries));
     GINGR_CUDA_TRY(ctx, tri_box.alloc((size_t)2 * std::max(items, 1)));
+    if (entry_boxes) GINGR_CUDA_TRY(ctx, entry_box.alloc((size_t)2 * cap_entries));
   } else {
     GINGR_CUDA_TRY(ctx, pts.alloc((size_t)std::max(items, 1)));
   }
@@ -313,6 +317,7 @@ int32_t SpatialGrid::ensure(gingr_ctx* ctx, int nv, int items, bool tri) {
 void SpatialGrid::release() {
   params.release(); cell_start.release(); fill.release(); entries.release(); pts.release(); bbox_part.release();
   tri_box.release();
+  entry_box.release();
   block_sums.release();
   built = false;
 }
@@ -370,11 +375,11 @@ int32_t grid_build_triangles_enqueue(gingr_ctx* ctx, SpatialGrid& g, int n, Vert
   cudaStream_t st = ctx->stream;
   GINGR_TRY(grid_common_head(ctx, g, n, v));
   grid_tri_kernel<0><<<ceil_div(T, 256), 256, 0, st>>>(T, v.p, d_tri, g.params.p, g.cell_start.p, g.fill.p, g.entries.p,
-                                                      g.cap_entries, g.tri_box.p);
+                                                      g.cap_entries, g.tri_box.p, nullptr);
   GINGR_LAUNCHED(ctx);
   GINGR_TRY(grid_scan(ctx, g));
   grid_tri_kernel<1><<<ceil_div(T, 256), 256, 0, st>>>(T, v.p, d_tri, g.params.p, g.cell_start.p, g.fill.p, g.entries.p,
-                                                      g.cap_entries, g.tri_box.p);
+                                                      g.cap_entries, g.tri_box.p, g.entry_boxes ? g.entry_box.p : nullptr);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   g.n_items = T;
@@ -670,7 +675,8 @@ __global__ void __launch_bounds__(WQ_WARPS * 32, WQ_MINB) grid_surface_warp_kern
     int M, const double4* __restrict__ order, const double* __restrict__ q, int T, const GridParams* __restrict__ gp,
     const int32_t* __restrict__ cell_start, const int32_t* __restrict__ entries, const float4* __restrict__ tri_box,
     const double* __restrict__ verts /*AoS*/, const int32_t* __restrict__ tri, double* __restrict__ d2,
-    int32_t* __restrict__ tri_out, double* __restrict__ cp, int descend /*GINGR_K2_DESCEND, A/B measurements*/) {
+    int32_t* __restrict__ tri_out, double* __restrict__ cp, int descend /*GINGR_K2_DESCEND, A/B measurements*/,
+    const float4* __restrict__ entry_box /*boxes stored with the entries (static grids), may be null*/) {
   __shared__ int s_queue[WQ_WARPS][WQ_CAP];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int slot = blockIdx.x * WQ_WARPS + w;
@@ -712,10 +718,12 @@ __global__ void __launch_bounds__(WQ_WARPS * 32, WQ_MINB) grid_surface_warp_kern
     __syncwarp();
   };
   // box test (+ home-cell de-duplication for sh >= 0) of the triangles t = first + lane ... and compaction into the queue
-  auto offer = [&](bool valid, int t, int x, int y, int z, int sh) {
+  auto offer = [&](bool valid, int t, int x, int y, int z, int sh, int e) {   // e >= 0: position in `entries`
     bool pass = false;
     if (valid) {
-      const float4 lo = tri_box[2 * t], hi = tri_box[2 * t + 1];
+      float4 lo, hi;
+      if (entry_box != nullptr && e >= 0) { lo = entry_box[2 * (size_t)e]; hi = entry_box[2 * (size_t)e + 1]; }   // streams with entries[e]
+      else { lo = tri_box[2 * t]; hi = tri_box[2 * t + 1]; }
       const double px = fmin(fmax(qx, (double)lo.x), (double)hi.x), py = fmin(fmax(qy, (double)lo.y), (double)hi.y),
                    pz = fmin(fmax(qz, (double)lo.z), (double)hi.z);
       const double ex = qx - px, ey = qy - py, ez = qz - pz;
@@ -734,7 +742,7 @@ __global__ void __launch_bounds__(WQ_WARPS * 32, WQ_MINB) grid_surface_warp_kern
     for (int base = e0; base < e1; base += 32) {
       const int e = base + lane;
       const bool valid = e < e1;
-      offer(valid, valid ? entries[e] : 0, x, y, z, sh);
+      offer(valid, valid ? entries[e] : 0, x, y, z, sh, e);
     }
   };
 
@@ -932,7 +940,7 @@ __global__ void __launch_bounds__(WQ_WARPS * 32, WQ_MINB) grid_surface_warp_kern
     // everything (overflowed grid, nothing near, ball too big): all triangles, 32 at a time
     qn = 0;
     best.d = INFINITY; best.x = best.y = best.z = 0.0; best.t = 0x7fffffff;
-    for (int base = 0; base < T; base += 32) offer(base + lane < T, base + lane, 0, 0, 0, -1);
+    for (int base = 0; base < T; base += 32) offer(base + lane < T, base + lane, 0, 0, 0, -1, -1);
     flush();
   }
   if (lane == 0) {
@@ -953,9 +961,10 @@ int32_t grid_surface_enqueue(gingr_ctx* ctx, const SpatialGrid& g, int M, const 
   if (!g.built || !g.triangles) return gingr_fail(ctx, GINGR_ERR_ARG, "grid_surface: triangle grid not built");
   if (warp_search_wanted()) {
     static const int descend = [] { const char* e = getenv("GINGR_K2_DESCEND"); return e ? atoi(e) : 1; }();
+    static const int use_entry_boxes = [] { const char* e = getenv("GINGR_K2_ENTRY_BOXES"); return e ? atoi(e) : 1; }();
     grid_surface_warp_kernel<<<ceil_div(M, WQ_WARPS), WQ_WARPS * 32, 0, ctx->stream>>>(
         M, order_ptr(order, M), d_q, g.n_items, g.params.p, g.cell_start.p, g.entries.p, g.tri_box.p, d_verts_aos, d_tri, d_d2,
-        d_tri_out, d_cp, descend);
+        d_tri_out, d_cp, descend, (g.entry_boxes && use_entry_boxes) ? g.entry_box.p : nullptr);
     GINGR_LAUNCHED(ctx);
     GINGR_CUDA_TRY(ctx, cudaGetLastError());
     return GINGR_OK;

@@ -32,6 +32,9 @@ struct SpatialGrid {
   DevBuf<int32_t> fill;        // [cap_cells + 1] counts, then the scatter cursor
   DevBuf<int32_t> entries;     // triangle grid: [cap_entries] triangle ids, cell-major
   DevBuf<float4> tri_box;      // triangle grid: [T][2] bounding box of each triangle, rounded outward to float
+  DevBuf<float4> entry_box;    // optional (entry_boxes, static grids): [cap_entries][2] the same box stored WITH each entry, so that
+                               // the surface search streams boxes cell by cell instead of gathering them through the triangle id
+  bool entry_boxes = false;    // set before ensure()
   DevBuf<double4> pts;         // point grid: [n] (x, y, z, original index as bits), cell-major
   DevBuf<double> bbox_part;    // [128][6]
   DevBuf<int32_t> block_sums;  // scan scratch
