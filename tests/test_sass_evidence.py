@@ -73,3 +73,28 @@ def test_cholesky_panel_factorises_in_registers_with_shuffles(kernels):
     for name in _find(table, "chol_panel_kernel"):
         c = table[name]
         assert _count(c, "SHFL") >= 500 and _count(c, "DFMA") >= 1000 and _count(c, "LDL") == 0 and _count(c, "STL") == 0
+
+
+def test_every_kernel_of_the_mh_step_has_a_batched_twin(kernels):
+    """csrc/batch.cuh: the kernels on the path of a Metropolis-Hastings step / an ICP iteration exist twice in the library --
+    `name` (arguments in the parameter bank) and `name_batched` (blockIdx.z = chain, arguments from an array) -- generated
+    from one body, so the twin carries the same arithmetic (the compiler may unroll the two differently: the check is on the
+    kind of arithmetic -- FP64 pipe, FP64 tensor instructions -- not on instruction counts)."""
+    _, table = kernels
+    names = ["multi_copy_kernel", "add_normal_kernel", "chol_backsolve_small_kernel", "chol_small_kernel", "dense_matvec_kernel",
+             "combine_kernel", "gemv_rows_kernel", "procrustes_sums_kernel", "procrustes_reduce_then_kernel", "coeff_residual_kernel",
+             "gemvT_kernel", "gemvT_reduce_kernel", "finalize_kernel", "mcmc_random_override_kernel", "fit_from_instance_kernel",
+             "pose_kernel", "vertex_normals_kernel", "surface_kernel", "surface_reduce_kernel", "mean_sqrt_kernel", "nn_vertex_kernel",
+             "nn_reduce_kernel", "line_mesh_kernel", "icp_weights_kernel", "obs_kernel", "sigma2_kernel", "gram_ws_kernel",
+             "gram_finish_kernel", "chol_df_kernel", "mcmc_residual_kernel", "mcmc_build_system_kernel", "mcmc_quadform_kernel",
+             "mcmc_distance_logpdf_kernel", "mcmc_decide_kernel", "mcmc_restore_ints_kernel", "bump_iteration_kernel"]
+
+    def fp(counter):
+        return (_count(counter, "DFMA") + _count(counter, "DMUL") + _count(counter, "DADD"), _count(counter, "DMMA"))
+    for n in names:
+        single = [k for k in table if re.search(r"\d+" + n + r"(E|I)", k) and "_batched" not in k]
+        twin = [k for k in table if re.search(r"\d+" + n + r"_batched(E|I)", k)]
+        assert single and twin, n
+        assert len(single) == len(twin), (n, single, twin)          # template kernels: one twin per instantiation
+        kinds = lambda ks: sorted((a > 0, b > 0) for a, b in (fp(table[k]) for k in ks))
+        assert kinds(single) == kinds(twin), n
