@@ -476,6 +476,12 @@ void estep_plan(const gingr_ctx* ctx, int M, int N, EstepPlan* p) {
   p->row_blocks = ceil_div(M, TPB * RB);
   p->col_splits = pick_splits_for_waves(p->row_blocks, ceil_div(N, 128), max(occ_b, 1) * ctx->num_sms);
   p->den_blocks = ceil_div(N, TPB);
+  // tuning overrides (tools/time_estep_phases.py)
+  if (const char* e = getenv("GINGR_ESTEP_SPLITS_A")) if (atoi(e) > 0) p->row_splits = std::min(atoi(e), ceil_div(M, 128));
+  if (const char* e = getenv("GINGR_ESTEP_SPLITS_B")) if (atoi(e) > 0) p->col_splits = std::min(atoi(e), ceil_div(N, 128));
+  if (getenv("GINGR_ESTEP_VERBOSE"))
+    fprintf(stderr, "estep plan M=%d N=%d: sweep A %d x %d CTAs (occupancy %d), sweep B %d x %d CTAs (occupancy %d)\n", M, N,
+            p->col_blocks, p->row_splits, occ_a, p->row_blocks, p->col_splits, occ_b);
 }
 
 int32_t EstepWorkspace::ensure(gingr_ctx* ctx, int M, int N) {
