@@ -774,7 +774,9 @@ class GingrAlgorithm:
 
 def update_batch(chains: Sequence[GingrAlgorithm], iters: int, probabilistic: bool = False, seed: int = 0):
     """`iters` update+propose steps of every chain (independent registrations on one ctx; gingr_update_batch).
-    Each chain must hold a device-resident state (initializeState / update); read results with downloadState()."""
+    Each chain must hold a device-resident state (initializeState / update); read results with downloadState().
+    All chains advance through one batched kernel sequence per iteration (one launch per kernel of the iteration, chain =
+    blockIdx.z) when the iteration is batch-aware -- the ICP flavours on the scans are; CPD replays per-chain graphs."""
     ctx = chains[0].ctx
     arr = (ctypes.c_void_p * len(chains))(*[c.handle for c in chains])
     ctx.check(ctx._lib.gingr_update_batch(arr, len(chains), int(iters), int(probabilistic), int(seed)))
@@ -788,7 +790,9 @@ def chain_range(n_chains: int, nranks: int, rank: int) -> Tuple[int, int]:
 
 
 def mcmc_batch(chains: Sequence[GingrAlgorithm], iters: int, seed: int = 0):
-    """`iters` MH steps of every chain (independent chains on one ctx; gingr_mcmc_batch); chain k uses seed + k."""
+    """`iters` MH steps of every chain (independent chains on one ctx; gingr_mcmc_batch); chain k uses seed + k.  One batched
+    kernel sequence per MH step serves all chains (csrc/batch.cuh); the chains are the chains solo runs with the same seeds
+    produce, up to the summation order of a chain's Gram partials when many chains share the GPU."""
     ctx = chains[0].ctx
     arr = (ctypes.c_void_p * len(chains))(*[c.handle for c in chains])
     ctx.check(ctx._lib.gingr_mcmc_batch(arr, len(chains), int(iters), int(seed)))
