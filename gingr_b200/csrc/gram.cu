@@ -420,7 +420,8 @@ GINGR_KERNEL((256), gram_finish_kernel, int r, int rp, int ld_out, const double*
   }
   // blockIdx.z slices the elements of the tile: a small matrix has few tiles and would otherwise be finished by a
   // handful of latency-bound CTAs
-  for (int e = slice * 256 + threadIdx.x; e < BT * BT; e += 256 * slices) {
+  const int e_end = min(BT, r - ta * BT) * BT;   // rows of the tile inside the matrix (a small rank uses a corner of its one tile)
+  for (int e = slice * 256 + threadIdx.x; e < e_end; e += 256 * slices) {
     const int row = e / BT, col = e % BT;
     const int a = ta * BT + row, b = tb * BT + col;
     if (a >= r || b >= r || b > a) continue;
