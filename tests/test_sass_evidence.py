@@ -98,3 +98,27 @@ def test_every_kernel_of_the_mh_step_has_a_batched_twin(kernels):
         assert len(single) == len(twin), (n, single, twin)          # template kernels: one twin per instantiation
         kinds = lambda ks: sorted((a > 0, b > 0) for a, b in (fp(table[k]) for k in ks))
         assert kinds(single) == kinds(twin), n
+
+
+def test_small_matrix_factorisation_fits_two_ctas_per_sm():
+    """chol_small_kernel (one 64 x 64 block; what 1024 batched chains of rank 50 factorise twice per MH step): at most 128
+    registers and no local memory in both forms, so that two CTAs of 256 threads share an SM -- the data-flow kernel it
+    replaces for n <= 64 needs 214 registers (one CTA per SM)."""
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", LIB], capture_output=True, text=True, check=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        m = re.match(r"\s*Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", line)
+        if m and name:
+            usage[name] = tuple(int(v) for v in m.groups())
+            name = None
+    small = {k: v for k, v in usage.items() if "chol_small_kernel" in k}
+    assert len(small) == 2, list(small)
+    for k, (reg, stack, shared, local) in small.items():
+        assert reg <= 128 and stack == 0 and local == 0, (k, reg, stack, local)
+    big = [v for k, v in usage.items() if "chol_df_kernel" in k and "batched" not in k]
+    assert big and big[0][0] > 128
