@@ -21,7 +21,7 @@
 // CPD:  f_i = 1, a = 1, c = w/(1-w) (2 pi sigma2)^{3/2} M/N           (CPD.scala:69-72)
 // BCPD: f_i = (1-w) (2 pi sigma2)^{-3/2} exp(-s/(2 sigma2) 3 Sigma_mm) alpha_m, a = (1-w), c = w/N
 //                                                                     (BCPD.scala:170-181)
-#include "common.cuh"
+#include "batch.cuh"
 #include "estep.cuh"
 #include "exp2_poly.cuh"
 
@@ -160,7 +160,7 @@ __device__ __forceinline__ void rowsum_tile(int cnt, const double4* __restrict__
 // fit  : moving points SoA [3][M] (+ row factor f[M]), target: SoA [3][N]
 // part : [gridDim.y][N] partial column sums
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB, ESTEP_MINB_A) estep_colsum_kernel(int M, int N, const double* __restrict__ fit,
+GINGR_KERNEL((TPB, ESTEP_MINB_A), estep_colsum_kernel, int M, int N, const double* __restrict__ fit,
                                                            const double* __restrict__ rowf,
                                                            const double* __restrict__ target,
                                                            const double* __restrict__ scal,
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(TPB, ESTEP_MINB_A) estep_colsum_kernel(int M, 
 // denominators.  scal[1] = a, scal[2] = c.  pack[j] = {x, y, z, w_j, w_j x, w_j y, w_j z, 0} * {1,1,1,2^-64,...}
 // xpx_part[blockIdx.x] = sum over the block's columns of Pt1_j |x_j|^2  (CPD.scala:142)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) estep_den_kernel(int N, int splits, const double* __restrict__ part,
+GINGR_KERNEL((TPB), estep_den_kernel, int N, int splits, const double* __restrict__ part,
                                                         const double* __restrict__ target,
                                                         const double* __restrict__ scal, double* __restrict__ pack,
                                                         double* __restrict__ pt1, double* __restrict__ xpx_part) {
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(TPB) estep_den_kernel(int N, int splits, const
 // sweep B: row sums.   grid = (row blocks, column splits)
 // part : [gridDim.y][4][M]  (P1, PX.x, PX.y, PX.z) partials, without the row factor
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB, ESTEP_MINB_B) estep_rowsum_kernel(int M, int N, const double* __restrict__ fit,
+GINGR_KERNEL((TPB, ESTEP_MINB_B), estep_rowsum_kernel, int M, int N, const double* __restrict__ fit,
                                                            const double* __restrict__ pack,
                                                            const double* __restrict__ scal,
                                                            double* __restrict__ part) {
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(TPB, ESTEP_MINB_B) estep_rowsum_kernel(int M, 
 }
 
 // fixed-order reduction of the row partials; applies the row factor.  out: [4][M]
-__global__ void __launch_bounds__(TPB) estep_rowreduce_kernel(int M, int splits, const double* __restrict__ part,
+GINGR_KERNEL((TPB), estep_rowreduce_kernel, int M, int splits, const double* __restrict__ part,
                                                               const double* __restrict__ rowf,
                                                               double* __restrict__ out) {
   // one thread per (quantity q, row i): 4 M threads instead of M (the M-thread form ran at 7 % occupancy: 51 us at
@@ -518,19 +518,19 @@ int32_t estep_enqueue(gingr_ctx* ctx, EstepWorkspace& ws, int M, int N, const do
   const double* rowf = use_rowf ? ws.rowf.p : nullptr;
   cudaStream_t st = ctx->stream;
   if (ev) cudaEventRecord(ev->a0, st);
-  estep_colsum_kernel<<<dim3(p.col_blocks, p.row_splits), TPB, 0, st>>>(M, N, ws.fit_soa.p, rowf, target_soa,
+  GINGR_LAUNCH(ctx, estep_colsum_kernel, dim3(p.col_blocks, p.row_splits), TPB, 0, st, M, N, ws.fit_soa.p, rowf, target_soa,
                                                                         ws.scal.p, ws.colpart.p);
   if (ev) cudaEventRecord(ev->a1, st);
   GINGR_LAUNCHED(ctx);
-  estep_den_kernel<<<p.den_blocks, TPB, 0, st>>>(N, p.row_splits, ws.colpart.p, target_soa, ws.scal.p, ws.pack.p,
+  GINGR_LAUNCH(ctx, estep_den_kernel, p.den_blocks, TPB, 0, st, N, p.row_splits, ws.colpart.p, target_soa, ws.scal.p, ws.pack.p,
                                                  ws.pt1.p, ws.xpx_part.p);
   GINGR_LAUNCHED(ctx);
   if (ev) cudaEventRecord(ev->b0, st);
-  estep_rowsum_kernel<<<dim3(p.row_blocks, p.col_splits), TPB, 0, st>>>(M, N, ws.fit_soa.p, ws.pack.p, ws.scal.p,
+  GINGR_LAUNCH(ctx, estep_rowsum_kernel, dim3(p.row_blocks, p.col_splits), TPB, 0, st, M, N, ws.fit_soa.p, ws.pack.p, ws.scal.p,
                                                                         ws.rowpart.p);
   if (ev) cudaEventRecord(ev->b1, st);
   GINGR_LAUNCHED(ctx);
-  estep_rowreduce_kernel<<<ceil_div(4 * M, TPB), TPB, 0, st>>>(M, p.col_splits, ws.rowpart.p, rowf, ws.rows.p);
+  GINGR_LAUNCH(ctx, estep_rowreduce_kernel, ceil_div(4 * M, TPB), TPB, 0, st, M, p.col_splits, ws.rowpart.p, rowf, ws.rows.p);
   GINGR_LAUNCHED(ctx);
   GINGR_CUDA_TRY(ctx, cudaGetLastError());
   return GINGR_OK;

@@ -122,7 +122,7 @@ __global__ void compact_gather_kernel(int M, int nranks, int Mmax, const double*
 // also resets the two words of `sync` for the next launch -- the scalars: scal[0] = sigma2, scal[1] = a = 1, scal[2] = c
 // (CPD.scala:69-70), scal[7] = bound of the pair distances from max |coordinate| of fit and target (gauss_exp2_tab<SAFE>).
 // The maximum is exact in any order, so the result does not depend on which block comes last.
-__global__ void __launch_bounds__(256) cpd_prepare_kernel(int M, const double* __restrict__ fit /*AoS*/, double* __restrict__ fit_soa,
+GINGR_KERNEL((256), cpd_prepare_kernel, int M, const double* __restrict__ fit /*AoS*/, double* __restrict__ fit_soa,
                                                           const double* __restrict__ ds, double w, double ratio,
                                                           double target_maxabs, int* __restrict__ fail_flag,
                                                           unsigned long long* __restrict__ sync /*[2]: max bits, ticket*/,
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) cpd_prepare_kernel(int M, const double* _
 }
 
 // xpx total (fixed order) appended behind the row block for the all-reduce.  One CTA of 256 threads.
-__global__ void xpx_total_kernel(int nparts, const double* __restrict__ parts, double* __restrict__ out) {
+GINGR_KERNEL_NB(xpx_total_kernel, int nparts, const double* __restrict__ parts, double* __restrict__ out) {
   __shared__ double red[256];
   double s = 0.0;
   for (int k = threadIdx.x; k < nparts; k += 256) s += parts[k];
@@ -1535,7 +1535,7 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
   if (cfg.algorithm == GINGR_ALGO_CPD) {
     // non-finite fit / sigma2 / target: the reference's P is all NaN and the posterior fails
     if (tg->nonfinite) GINGR_TRY(validate_finite_enqueue(ctx, 3 * tg->N_total, tg->verts.p, g->is.p + IS_FAIL_POST));
-    cpd_prepare_kernel<<<ceil_div(M, 256), 256, 0, st>>>(M, g->fit.p, g->estep.fit_soa.p, g->ds.p, cfg.w,
+    GINGR_LAUNCH(ctx, cpd_prepare_kernel, ceil_div(M, 256), 256, 0, st, M, g->fit.p, g->estep.fit_soa.p, g->ds.p, cfg.w,
                                                          (double)M / (double)tg->N_total, tg->maxabs, g->is.p + IS_FAIL_POST,
                                                          g->prep_sync.p, g->estep.scal.p);
     GINGR_LAUNCHED(ctx);
@@ -1544,9 +1544,8 @@ static int32_t enqueue_posterior_phase(gingr_registration* g) {
       const bool pe = g->ev(2) != nullptr;
       if (pe) { ee.a0 = *g->ev(2); ee.a1 = *g->ev(3); ee.b0 = *g->ev(4); ee.b1 = *g->ev(5); }
       GINGR_TRY(estep_enqueue(ctx, g->estep, M, tg->N, tg->soa.p, false, pe ? &ee : nullptr));
-      GINGR_CUDA_TRY(ctx, cudaMemcpyAsync(g->rows_ext.p, g->estep.rows.p, sizeof(double) * 4 * (size_t)M,
-                                          cudaMemcpyDeviceToDevice, st));
-      xpx_total_kernel<<<1, 256, 0, st>>>(g->estep.plan.den_blocks, g->estep.xpx_part.p, g->rows_ext.p + (size_t)4 * M);
+      GINGR_CUDA_TRY(ctx, gingr_copy_d2d(ctx, g->rows_ext.p, g->estep.rows.p, sizeof(double) * 4 * (size_t)M, st));
+      GINGR_LAUNCH(ctx, xpx_total_kernel, 1, 256, 0, st, g->estep.plan.den_blocks, g->estep.xpx_part.p, g->rows_ext.p + (size_t)4 * M);
       GINGR_LAUNCHED(ctx);
     } else {
       GINGR_CUDA_TRY(ctx, cudaMemsetAsync(g->rows_ext.p, 0, sizeof(double) * ((size_t)4 * M + 8), st));

@@ -342,6 +342,36 @@ def test_large_batch_runs_as_one_kernel_sequence(ctx, oracle):
         c.close()
 
 
+def test_large_cpd_batch_runs_as_one_kernel_sequence(ctx, oracle):
+    """The same for CPD registrations: E-step sweeps, Gram, factorisation and the update of 48 registrations as one batched
+    sequence (1e-9 against the solo runs: the batched Gram runs on fewer CTAs)."""
+    from gingr_b200 import api
+    m, target, tt = _problem(oracle, 120, 150, 20, seed=15)
+    dm = api.Model(ctx, m.ref, m.mean, m.basis, m.variance, m.tri)
+    dt = api.Target(ctx, target, tt)
+    n, iters = 48, 3
+    cfg = api.CpdConfiguration(maxIterations=40, w=0.1)
+    chains = [api.CpdRegistration(ctx, dm, dt, cfg) for _ in range(n)]
+    for k, c in enumerate(chains):
+        c.initializeState(translation=np.array([0.02 * k, 0.0, 0.0]))
+    l0 = ctx.launch_count
+    api.update_batch(chains, iters)
+    ctx.synchronize()
+    assert (ctx.launch_count - l0) / iters < 100, "the batched sequence did not run"
+    for k in (0, 9, n - 1):
+        solo = api.CpdRegistration(ctx, dm, dt, cfg)
+        solo.initializeState(translation=np.array([0.02 * k, 0.0, 0.0]))
+        solo.updateChain(iters)
+        a, b = chains[k].downloadState(), solo.downloadState()
+        assert a.iteration == iters == b.iteration
+        np.testing.assert_allclose(a.fit, b.fit, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(a.sigma2, b.sigma2, rtol=1e-9)
+        np.testing.assert_allclose(a.modelParameters.shape, b.modelParameters.shape, rtol=1e-8, atol=1e-9)
+        solo.close()
+    for c in chains:
+        c.close()
+
+
 def test_batched_chains_equal_independent_chains(ctx, oracle):
     """gingr_update_batch (BASELINE config 5: batched MCMC chains, replicas only): n chains sharing model and target,
     each with its own state and Philox stream, give exactly what the same chains give one by one."""
