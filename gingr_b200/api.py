@@ -776,7 +776,8 @@ def update_batch(chains: Sequence[GingrAlgorithm], iters: int, probabilistic: bo
     """`iters` update+propose steps of every chain (independent registrations on one ctx; gingr_update_batch).
     Each chain must hold a device-resident state (initializeState / update); read results with downloadState().
     All chains advance through one batched kernel sequence per iteration (one launch per kernel of the iteration, chain =
-    blockIdx.z) when the iteration is batch-aware -- the ICP flavours on the scans are; CPD replays per-chain graphs."""
+    blockIdx.z) when the iteration is batch-aware -- CPD and the ICP flavours on the scans are; the uniform-grid searches of
+    large meshes replay per-chain graphs."""
     ctx = chains[0].ctx
     arr = (ctypes.c_void_p * len(chains))(*[c.handle for c in chains])
     ctx.check(ctx._lib.gingr_update_batch(arr, len(chains), int(iters), int(probabilistic), int(seed)))

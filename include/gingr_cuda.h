@@ -268,8 +268,9 @@ GINGR_API int32_t gingr_update_chain_sampled(gingr_registration* reg, int32_t it
  * `iters` update+propose steps of each of the n registrations (all created on the same ctx, typically sharing one
  * model and one target handle, each with its own device-resident state).  Chain k uses seed + k when
  * probabilistic != 0.  All chains advance through ONE batched kernel sequence per iteration (every kernel launched once
- * with blockIdx.z = chain; csrc/batch.cuh) when every launch of the iteration has a batched form -- the ICP flavours on the
- * scans do --, otherwise the chains' captured iteration graphs are replayed on a pool of streams (CPD).  The call returns
+ * with blockIdx.z = chain; csrc/batch.cuh) when every launch of the iteration has a batched form -- CPD and the ICP flavours
+ * on the scans do --, otherwise (uniform-grid searches of large meshes, the reversed correspondence direction) the chains'
+ * captured iteration graphs are replayed on a pool of streams.  The call returns
  * after enqueueing, results are read with gingr_state_download per chain.  Per chain the arithmetic is that of the chain
  * alone, up to the summation order of its Gram partials when many chains share the GPU. */
 GINGR_API int32_t gingr_update_batch(gingr_registration** regs, int32_t n, int32_t iters, int32_t probabilistic,
